@@ -1,0 +1,327 @@
+// extern "C" surface: include/fhe_precompiles_b200.h.  Part 1 mirrors /root/reference/src/c_fhe.rs:8-141.
+#pragma GCC visibility push(default)
+#include "../../include/fhe_precompiles_b200.h"
+#pragma GCC visibility pop
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <exception>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "engine.h"
+#include "kernels.h"
+
+using namespace fheb;
+
+namespace {
+thread_local std::string tl_error;
+
+void set_error(const char *what) {
+    tl_error = what ? what : "unknown error";
+    static bool verbose = getenv("FHE_B200_QUIET") == nullptr;
+    if (verbose) fprintf(stderr, "[fhe_precompiles_b200] %s\n", tl_error.c_str());
+}
+
+// c_fhe.rs:34-54: success -> malloc'd copy; failure -> NULL / 0 / code
+int32_t finish(int32_t rc, const std::vector<uint8_t> &res, uint8_t **output, int64_t *output_length) {
+    if (rc == 0) {
+        uint8_t *buf = (uint8_t *)malloc(res.size() ? res.size() : 1);
+        if (!buf) rc = kErrSunscreen;
+        else {
+            memcpy(buf, res.data(), res.size());
+            *output = buf;
+            *output_length = (int64_t)res.size();
+            return 0;
+        }
+    }
+    *output = nullptr;
+    *output_length = 0;
+    return rc;
+}
+
+template <class F>
+int32_t guarded(F &&f, uint8_t **output, int64_t *output_length) {
+    std::vector<uint8_t> res;
+    int32_t rc;
+    try {
+        rc = f(&res);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        rc = kErrSunscreen;
+    } catch (...) {
+        set_error("unknown exception");
+        rc = kErrSunscreen;
+    }
+    return finish(rc, res, output, output_length);
+}
+
+int32_t run_binary(Op op, Shape shape, Kind kind, const uint8_t *bytes, size_t len, uint8_t **output, int64_t *output_length) {
+    return guarded([&](std::vector<uint8_t> *res) { return Engine::get().binary_op(op, shape, kind, Span{bytes, len}, res); },
+                   output, output_length);
+}
+
+// network keys (fhe.rs:118-119 include_bytes!): linked into the library by keys_blob.S
+extern "C" const uint8_t fhe_b200_network_pub[];
+extern "C" const uint8_t fhe_b200_network_pub_end[];
+extern "C" const uint8_t fhe_b200_network_pri[];
+extern "C" const uint8_t fhe_b200_network_pri_end[];
+
+struct OpDesc {
+    const char *name;
+    int32_t (*fn)(const uint8_t *, size_t, uint8_t **, int64_t *);
+};
+}  // namespace
+
+extern "C" {
+
+#define BIN(name, OP, SHAPE, KIND)                                                                                   \
+    int32_t c_fhe_##name(const uint8_t *bytes, size_t bytes_length, uint8_t **output, int64_t *output_length) {      \
+        return run_binary(Op::OP, Shape::SHAPE, Kind::KIND, bytes, bytes_length, output, output_length);             \
+    }
+#define BIN_TYPE(T, KIND)                        \
+    BIN(add_cipher##T##_cipher##T, Add, CtCt, KIND) \
+    BIN(add_cipher##T##_##T, Add, CtPt, KIND)       \
+    BIN(add_##T##_cipher##T, Add, PtCt, KIND)       \
+    BIN(sub_cipher##T##_cipher##T, Sub, CtCt, KIND) \
+    BIN(sub_cipher##T##_##T, Sub, CtPt, KIND)       \
+    BIN(sub_##T##_cipher##T, Sub, PtCt, KIND)       \
+    BIN(mul_cipher##T##_cipher##T, Mul, CtCt, KIND) \
+    BIN(mul_cipher##T##_##T, Mul, CtPt, KIND)       \
+    BIN(mul_##T##_cipher##T, Mul, PtCt, KIND)
+BIN_TYPE(u256, U256)
+BIN_TYPE(u64, U64)
+BIN_TYPE(i64, I64)
+BIN_TYPE(frac64, Frac64)
+
+#define THRESH(name, FN, KIND)                                                                                       \
+    int32_t c_fhe_##name(const uint8_t *bytes, size_t bytes_length, uint8_t **output, int64_t *output_length) {      \
+        return guarded(                                                                                              \
+            [&](std::vector<uint8_t> *res) {                                                                        \
+                return Engine::get().FN(Kind::KIND, Span{bytes, bytes_length},                                      \
+                                        Span{fhe_b200_network_pub, (size_t)(fhe_b200_network_pub_end - fhe_b200_network_pub)}, \
+                                        Span{fhe_b200_network_pri, (size_t)(fhe_b200_network_pri_end - fhe_b200_network_pri)}, \
+                                        res);                                                                       \
+            },                                                                                                       \
+            output, output_length);                                                                                  \
+    }
+#define THRESH_TYPE(T, KIND)           \
+    THRESH(encrypt_##T, encrypt, KIND) \
+    THRESH(reencrypt_##T, reencrypt, KIND) \
+    THRESH(decrypt_##T, decrypt, KIND)
+THRESH_TYPE(u256, U256)
+THRESH_TYPE(u64, U64)
+THRESH_TYPE(i64, I64)
+THRESH_TYPE(frac64, Frac64)
+
+// fhe.rs:701-703
+int32_t c_fhe_public_key_bytes(const uint8_t *, size_t, uint8_t **output, int64_t *output_length) {
+    std::vector<uint8_t> res(fhe_b200_network_pub, fhe_b200_network_pub_end);
+    return finish(0, res, output, output_length);
+}
+
+void fhe_free(const uint8_t *bytes) { free((void *)bytes); }
+
+const char *fhe_error(int32_t code) {
+    switch (code) {  // lib.rs:33-44
+        case 1: return "Unexpected end of file";
+        case 2: return "Platform architecture invalid";
+        case 3: return "Invalid encoding";
+        case 4: return "Overflow in FHE program";
+        case 5: return "Invalid decryption";
+        case 6: return "Invalid encryption";
+        case 7: return "Base sunscreen error";
+        default: return "Unknown error";
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ part 2
+const char *fhe_b200_last_error(void) { return tl_error.c_str(); }
+
+int32_t fhe_b200_device_count(void) { return device_count(); }
+
+int32_t fhe_b200_init(int32_t device) {
+    try {
+        device_context(device);
+        return 0;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
+}
+uint64_t fhe_b200_launch_count(void) { return launch_count(); }
+
+#define OPD(name) {#name, c_fhe_##name}
+#define OPD_TYPE(T)                                                                                              \
+    OPD(add_cipher##T##_cipher##T), OPD(add_cipher##T##_##T), OPD(add_##T##_cipher##T), OPD(sub_cipher##T##_cipher##T), \
+        OPD(sub_cipher##T##_##T), OPD(sub_##T##_cipher##T), OPD(mul_cipher##T##_cipher##T), OPD(mul_cipher##T##_##T),  \
+        OPD(mul_##T##_cipher##T)
+static const OpDesc kOps[] = {OPD_TYPE(u256),     OPD_TYPE(u64),        OPD_TYPE(i64),       OPD_TYPE(frac64),
+                              OPD(encrypt_u256),  OPD(encrypt_u64),     OPD(encrypt_i64),    OPD(encrypt_frac64),
+                              OPD(reencrypt_u256), OPD(reencrypt_u64),  OPD(reencrypt_i64),  OPD(reencrypt_frac64),
+                              OPD(decrypt_u256),  OPD(decrypt_u64),     OPD(decrypt_i64),    OPD(decrypt_frac64),
+                              OPD(public_key_bytes)};
+static const int kNumOps = (int)(sizeof(kOps) / sizeof(kOps[0]));
+
+int32_t fhe_b200_op_index(const char *name) {
+    if (!name) return -1;
+    for (int i = 0; i < kNumOps; i++)
+        if (strcmp(kOps[i].name, name) == 0) return i;
+    return -1;
+}
+const char *fhe_b200_op_name(int32_t index) { return (index >= 0 && index < kNumOps) ? kOps[index].name : nullptr; }
+
+int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
+    if (!calls || n == 0) return 0;
+    size_t nt = host_threads > 0 ? (size_t)host_threads : (size_t)std::thread::hardware_concurrency();
+    if (nt == 0) nt = 1;
+    if (nt > n) nt = n;
+    std::atomic<size_t> next{0};
+    std::atomic<int64_t> failed{0};
+    auto worker = [&]() {
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            fhe_b200_call &c = calls[i];
+            if (c.op < 0 || c.op >= kNumOps) {
+                c.status = kErrSunscreen;
+                c.output = nullptr;
+                c.output_length = 0;
+            } else {
+                c.status = kOps[c.op].fn(c.bytes, c.bytes_length, &c.output, &c.output_length);
+            }
+            if (c.status) failed.fetch_add(1);
+        }
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    return failed.load();
+}
+
+#define DEV_GUARD(body)                  \
+    try {                                \
+        body;                            \
+        return 0;                        \
+    } catch (const std::exception &e) {  \
+        set_error(e.what());             \
+        return -1;                       \
+    }
+
+int32_t fhe_b200_add(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_eltwise(a, b, out, n, 0, (cudaStream_t)stream), "add"));
+}
+int32_t fhe_b200_sub(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_eltwise(a, b, out, n, 1, (cudaStream_t)stream), "sub"));
+}
+int32_t fhe_b200_negate(int32_t device, const uint64_t *a, uint64_t *out, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_eltwise(a, a, out, n, 2, (cudaStream_t)stream), "negate"));
+}
+int32_t fhe_b200_plain_addsub(int32_t device, const uint64_t *ct, const uint16_t *plain, uint64_t *out, size_t n,
+                              int32_t mode, void *stream) {
+    DEV_GUARD(device_context(device);
+              cuda_throw(launch_plain_addsub(ct, plain, out, n, mode, (cudaStream_t)stream), "plain_addsub"));
+}
+int32_t fhe_b200_multiply_plain(int32_t device, const uint64_t *ct, const uint16_t *plain, uint64_t *out, size_t n,
+                                void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_mul_plain(ct, plain, out, n, (cudaStream_t)stream), "mul_plain"));
+}
+int32_t fhe_b200_multiply(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, void *stream) {
+    DEV_GUARD(Engine::get().multiply(device, a, b, out3, n, (cudaStream_t)stream));
+}
+int32_t fhe_b200_relinearize(int32_t device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, void *stream) {
+    DEV_GUARD(Engine::get().relinearize(device, c3, rk, out, n, (cudaStream_t)stream));
+}
+int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
+                           size_t n, void *stream) {
+    DEV_GUARD(Engine::get().mul_relin(device, a, b, rk, out, n, (cudaStream_t)stream));
+}
+int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,
+                     void *stream) {
+    if (!mods || n_mods < 1 || n_mods > kNumMod) {
+        set_error("fhe_b200_ntt: n_mods must be 1..6");
+        return -1;
+    }
+    LimbMods lm;
+    lm.n = n_mods;
+    for (int i = 0; i < kNumMod; i++) lm.mod[i] = 0;
+    for (int i = 0; i < n_mods; i++) {
+        if (mods[i] < 0 || mods[i] >= kNumMod) {
+            set_error("fhe_b200_ntt: bad modulus index");
+            return -1;
+        }
+        lm.mod[i] = mods[i];
+    }
+    DEV_GUARD(device_context(device); cuda_throw(launch_ntt(data, n_limbs, lm, inverse != 0, (cudaStream_t)stream), "ntt"));
+}
+int32_t fhe_b200_behz_extend(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *ext, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_behz_extend_tap(a, b, ext, n, (cudaStream_t)stream), "behz_extend"));
+}
+int32_t fhe_b200_behz_tensor(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *tens, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_behz_tensor(a, b, tens, n, (cudaStream_t)stream), "behz_tensor"));
+}
+int32_t fhe_b200_behz_floor_sk(int32_t device, const uint64_t *tens, uint64_t *out3, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_floor_sk(tens, out3, n, (cudaStream_t)stream), "floor_sk"));
+}
+
+int32_t fhe_b200_parse_public_key(const uint8_t *bytes, size_t len, uint64_t *pk_words, uint64_t *rk_words) {
+    try {
+        bool has = false;
+        int32_t rc = decode_public_key(Span{bytes, len}, pk_words, rk_words, &has);
+        if (rc == 0 && rk_words && !has) return kErrSunscreen;
+        return rc;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return kErrSunscreen;
+    }
+}
+int32_t fhe_b200_parse_private_key(const uint8_t *bytes, size_t len, uint64_t *sk_words) {
+    try {
+        return decode_private_key(Span{bytes, len}, sk_words);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return kErrSunscreen;
+    }
+}
+int32_t fhe_b200_parse_ciphertext(const uint8_t *bytes, size_t len, uint64_t *words, char *data_type, size_t cap) {
+    try {
+        CipherView v;
+        int32_t rc = decode_ciphertext(Span{bytes, len}, &v, words);
+        if (rc == 0 && data_type && cap) {
+            size_t k = v.data_type.size() < cap - 1 ? v.data_type.size() : cap - 1;
+            memcpy(data_type, v.data_type.data(), k);
+            data_type[k] = 0;
+        }
+        return rc;
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return kErrSunscreen;
+    }
+}
+int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, uint8_t **output, int64_t *output_length) {
+    return guarded(
+        [&](std::vector<uint8_t> *res) {
+            CipherView v;
+            v.data_type = data_type ? data_type : "";
+            // testnet Params (testnet.rs:8-14) in sunscreen's bincode layout
+            uint64_t w[6] = {(uint64_t)kN, 3, kModulus[MQ0], kModulus[MQ1], kModulus[MP], kT};
+            memcpy(v.params, w, 48);
+            memset(v.params + 48, 0, 8);
+            v.compr_mode = 2;
+            return encode_ciphertext(v, words, res);
+        },
+        output, output_length);
+}
+void fhe_b200_parms_id(int32_t which, uint64_t out[4]) {
+    try {
+        const HostContext &H = HostContext::get();
+        memcpy(out, which == 0 ? H.parms_id_key : H.parms_id_data, 32);
+    } catch (...) {
+        memset(out, 0, 32);
+    }
+}
+
+}  // extern "C"

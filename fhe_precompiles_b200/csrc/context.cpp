@@ -1,0 +1,320 @@
+// See context.h.  Derivation rules restated from SEAL 4.0 (un-vendored dependency of the reference,
+// Cargo.toml:16): util::get_primes, util::try_minimal_primitive_root, NTTTables::initialize,
+// SEALContext::validate (coeff_div_plain_modulus, upper-half constants) and RNSTool::initialize.
+#include "context.h"
+
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+
+#include "kernels.h"
+
+namespace fheb {
+
+typedef unsigned __int128 u128;
+
+u64 h_mulmod(u64 a, u64 b, u64 q) { return (u64)((u128)a * b % q); }
+u64 h_powmod(u64 b, u64 e, u64 q) {
+    u64 r = 1 % q;
+    b %= q;
+    for (; e; e >>= 1) {
+        if (e & 1) r = h_mulmod(r, b, q);
+        b = h_mulmod(b, b, q);
+    }
+    return r;
+}
+u64 h_invmod(u64 a, u64 q) { return h_powmod(a % q, q - 2, q); }
+static u64 shoup_of(u64 w, u64 q) { return (u64)(((u128)w << 64) / q); }
+static Shoup mk_shoup(u64 w, u64 q) { return Shoup{w, shoup_of(w, q)}; }
+
+// ---------------------------------------------------------------- BLAKE2b (RFC 7693)
+namespace {
+const uint64_t kIV[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
+                         0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
+const uint8_t kSigma[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+inline uint64_t rotr(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+void compress(uint64_t h[8], const uint8_t block[128], u128 t, bool last) {
+    uint64_t m[16], v[16];
+    memcpy(m, block, 128);
+    for (int i = 0; i < 8; i++) {
+        v[i] = h[i];
+        v[i + 8] = kIV[i];
+    }
+    v[12] ^= (uint64_t)t;
+    v[13] ^= (uint64_t)(t >> 64);
+    if (last) v[14] = ~v[14];
+    for (int r = 0; r < 12; r++) {
+        const uint8_t *s = kSigma[r];
+#define G(a, b, c, d, x, y)                 \
+    v[a] = v[a] + v[b] + x;                 \
+    v[d] = rotr(v[d] ^ v[a], 32);           \
+    v[c] = v[c] + v[d];                     \
+    v[b] = rotr(v[b] ^ v[c], 24);           \
+    v[a] = v[a] + v[b] + y;                 \
+    v[d] = rotr(v[d] ^ v[a], 16);           \
+    v[c] = v[c] + v[d];                     \
+    v[b] = rotr(v[b] ^ v[c], 63);
+        G(0, 4, 8, 12, m[s[0]], m[s[1]]);
+        G(1, 5, 9, 13, m[s[2]], m[s[3]]);
+        G(2, 6, 10, 14, m[s[4]], m[s[5]]);
+        G(3, 7, 11, 15, m[s[6]], m[s[7]]);
+        G(0, 5, 10, 15, m[s[8]], m[s[9]]);
+        G(1, 6, 11, 12, m[s[10]], m[s[11]]);
+        G(2, 7, 8, 13, m[s[12]], m[s[13]]);
+        G(3, 4, 9, 14, m[s[14]], m[s[15]]);
+#undef G
+    }
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+}  // namespace
+
+void blake2b(const void *in, size_t inlen, void *out, size_t outlen) {
+    uint64_t h[8];
+    for (int i = 0; i < 8; i++) h[i] = kIV[i];
+    h[0] ^= 0x01010000ULL ^ (uint64_t)outlen;
+    const uint8_t *p = (const uint8_t *)in;
+    u128 t = 0;
+    while (inlen > 128) {
+        t += 128;
+        compress(h, p, t, false);
+        p += 128;
+        inlen -= 128;
+    }
+    uint8_t block[128] = {0};
+    memcpy(block, p, inlen);
+    t += inlen;
+    compress(h, block, t, true);
+    memcpy(out, h, outlen);
+}
+
+// ---------------------------------------------------------------- number theory
+namespace {
+bool is_prime_u64(u64 n) {
+    static const u64 bases[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+    if (n < 2) return false;
+    for (u64 b : bases)
+        if (n % b == 0) return n == b;
+    u64 d = n - 1;
+    int s = 0;
+    while (!(d & 1)) d >>= 1, s++;
+    for (u64 b : bases) {
+        u64 x = h_powmod(b, d, n);
+        if (x == 1 || x == n - 1) continue;
+        bool composite = true;
+        for (int r = 1; r < s && composite; r++) {
+            x = h_mulmod(x, x, n);
+            if (x == n - 1) composite = false;
+        }
+        if (composite) return false;
+    }
+    return true;
+}
+// SEAL util::get_primes: descending primes congruent to 1 mod factor with exactly `bits` bits
+std::vector<u64> seal_get_primes(u64 factor, int bits, size_t count) {
+    std::vector<u64> out;
+    u64 v = (((u64)1 << bits) - 1) / factor * factor + 1;
+    const u64 lower = (u64)1 << (bits - 1);
+    for (; out.size() < count && v > lower; v -= factor)
+        if (is_prime_u64(v)) out.push_back(v);
+    if (out.size() != count) throw std::runtime_error("fhe_b200: not enough auxiliary primes");
+    return out;
+}
+// SEAL util::try_minimal_primitive_root: smallest primitive degree-th root of unity (degree = 2N)
+u64 minimal_root(u64 degree, u64 q) {
+    const u64 cof = (q - 1) / degree;
+    u64 root = 0;
+    for (u64 g = 2; g < q && !root; g++) {
+        u64 c = h_powmod(g, cof, q);
+        if (h_powmod(c, degree / 2, q) == q - 1) root = c;
+    }
+    const u64 sq = h_mulmod(root, root, q);
+    u64 best = root, cur = root;
+    for (u64 i = 0; i < degree; i += 2) {
+        if (cur < best) best = cur;
+        cur = h_mulmod(cur, sq, q);
+    }
+    return best;
+}
+u32 bitrev12(u32 x) {
+    u32 r = 0;
+    for (int i = 0; i < kLogN; i++) r = (r << 1) | ((x >> i) & 1);
+    return r;
+}
+
+void build(HostContext &H) {
+    // --- aux primes by SEAL's rule must equal the compile-time constants the kernels use
+    std::vector<u64> aux = seal_get_primes(2 * kN, 61, 4);
+    if (aux[0] != kModulus[MSK] || aux[1] != kGamma || aux[2] != kModulus[MB0] || aux[3] != kModulus[MB1])
+        throw std::runtime_error("fhe_b200: BEHZ auxiliary primes differ from compiled constants");
+    for (int i = 0; i < kNumMod; i++)
+        if (!is_prime_u64(kModulus[i]) || kModulus[i] % (2 * kN) != 1)
+            throw std::runtime_error("fhe_b200: modulus is not an NTT prime");
+
+    // --- twiddles
+    for (int mi = 0; mi < kNumMod; mi++) {
+        const u64 q = kModulus[mi];
+        const u64 psi = minimal_root(2 * kN, q);
+        H.root[mi] = psi;
+        H.twf[mi].resize(kN);
+        H.twi[mi].resize(kN);
+        u64 pw = 1;
+        for (u32 i = 0; i < (u32)kN; i++) {
+            u32 k = bitrev12(i);
+            H.twf[mi][k] = make_ulonglong2(pw, shoup_of(pw, q));
+            pw = h_mulmod(pw, psi, q);
+        }
+        for (u32 k = 0; k < (u32)kN; k++) {
+            u64 inv = h_invmod(H.twf[mi][k].x, q);
+            H.twi[mi][k] = make_ulonglong2(inv, shoup_of(inv, q));
+        }
+    }
+
+    DevConsts &c = H.dc;
+    memset(&c, 0, sizeof(c));
+    const u64 q0 = kModulus[MQ0], q1 = kModulus[MQ1], P = kModulus[MP];
+    const u64 b0 = kModulus[MB0], b1 = kModulus[MB1], msk = kModulus[MSK];
+    const u64 qs[2] = {q0, q1};
+    const u64 bsk[3] = {b0, b1, msk};
+    const u128 q = (u128)q0 * q1;
+    const u64 punct_q[2] = {q1, q0};  // q / q_l
+
+    for (int mi = 0; mi < kNumMod; mi++) {
+        const u64 m = kModulus[mi];
+        u64 ninv = h_invmod(kN, m);
+        c.ninv[mi] = mk_shoup(ninv, m);
+        c.ninv_t[mi] = mk_shoup(h_mulmod(ninv, kT % m, m), m);
+    }
+    H.inv_q1_mod_q0 = h_invmod(q1 % q0, q0);
+    H.inv_q0_mod_q1 = h_invmod(q0 % q1, q1);
+    const u64 inv_punct_q[2] = {H.inv_q1_mod_q0, H.inv_q0_mod_q1};
+
+    // base extension via m_tilde
+    for (int l = 0; l < 2; l++) {
+        c.ext_in[l] = mk_shoup(h_mulmod(kMTilde % qs[l], inv_punct_q[l], qs[l]), qs[l]);
+        c.punct_q_mod_mtilde[l] = (u32)(punct_q[l] & 0xffffffffull);
+        c.inv_punct_q[l] = mk_shoup(inv_punct_q[l], qs[l]);
+    }
+    {
+        u32 ql = (u32)(u64)q, x = ql;  // Newton iteration for q^-1 mod 2^32
+        for (int i = 0; i < 5; i++) x *= 2u - ql * x;
+        c.neg_inv_q_mod_mtilde = 0u - x;
+    }
+    for (int k = 0; k < 3; k++) {
+        const u64 p = bsk[k];
+        const u64 inv_mt = h_invmod(kMTilde % p, p);
+        const u64 q_mod_p = (u64)(q % p);
+        const u64 inv_q = h_invmod(q_mod_p, p);
+        c.extA[k] = h_mulmod(punct_q[0] % p, inv_mt, p);
+        c.extB[k] = h_mulmod(punct_q[1] % p, inv_mt, p);
+        c.extC[k] = h_mulmod(q_mod_p, inv_mt, p);
+        c.flV[k] = inv_q;
+        c.flA[k] = (p - h_mulmod(punct_q[0] % p, inv_q, p)) % p;
+        c.flB[k] = (p - h_mulmod(punct_q[1] % p, inv_q, p)) % p;
+    }
+    // Shenoy-Kumaresan
+    const u64 punct_B[2] = {b1, b0};
+    c.inv_punct_B[0] = mk_shoup(h_invmod(b1 % b0, b0), b0);
+    c.inv_punct_B[1] = mk_shoup(h_invmod(b0 % b1, b1), b1);
+    const u128 B = (u128)b0 * b1;
+    for (int j = 0; j < 2; j++) {
+        for (int l = 0; l < 2; l++) c.punct_B_mod_q[j][l] = punct_B[j] % qs[l];
+        c.punct_B_mod_msk[j] = punct_B[j] % msk;
+    }
+    c.inv_B_mod_msk = mk_shoup(h_invmod((u64)(B % msk), msk), msk);
+    for (int l = 0; l < 2; l++) {
+        c.B_mod_q[l] = (u64)(B % qs[l]);
+        c.neg_B_mod_q[l] = qs[l] - c.B_mod_q[l];
+    }
+    // key switching
+    c.half_P = P >> 1;
+    for (int l = 0; l < 2; l++) {
+        c.inv_P_mod_q[l] = mk_shoup(h_invmod(P % qs[l], qs[l]), qs[l]);
+        c.half_P_mod_q[l] = c.half_P % qs[l];
+    }
+    // plain ops
+    const u128 delta = q / kT;
+    for (int l = 0; l < 2; l++) {
+        c.delta_mod_q[l] = (u64)(delta % qs[l]);
+        c.upper_half_incr[l] = qs[l] - kT;
+    }
+    c.q_mod_t = (u64)(q % kT);
+    c.upper_half_threshold = (kT + 1) >> 1;
+
+    // parms_id (SEAL 4.0): BLAKE2b-256 over LE u64 words [scheme=BFV(1), N, q_i..., t]
+    {
+        uint64_t w_key[6] = {1, (uint64_t)kN, q0, q1, P, kT};
+        uint64_t w_data[5] = {1, (uint64_t)kN, q0, q1, kT};
+        blake2b(w_key, sizeof(w_key), H.parms_id_key, 32);
+        blake2b(w_data, sizeof(w_data), H.parms_id_data, 32);
+    }
+}
+}  // namespace
+
+const HostContext &HostContext::get() {
+    static HostContext *inst = nullptr;
+    static std::once_flag flag;
+    static std::string err;
+    std::call_once(flag, [] {
+        HostContext *h = new HostContext();
+        try {
+            build(*h);
+            inst = h;
+        } catch (const std::exception &e) {
+            err = e.what();
+            delete h;
+        }
+    });
+    if (!inst) throw std::runtime_error(err.empty() ? "fhe_b200: context build failed" : err);
+    return *inst;
+}
+
+// ---------------------------------------------------------------- per-device context
+namespace {
+constexpr int kMaxDevices = 64;
+DeviceContext g_dev[kMaxDevices];
+std::mutex g_dev_mu[kMaxDevices];
+
+void cuda_check(cudaError_t e, const char *what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string("fhe_b200: CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+}  // namespace
+
+int device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+DeviceContext &device_context(int device) {
+    if (device < 0 || device >= kMaxDevices) throw std::runtime_error("fhe_b200: bad device index");
+    std::lock_guard<std::mutex> lk(g_dev_mu[device]);
+    DeviceContext &d = g_dev[device];
+    cuda_check(cudaSetDevice(device), "cudaSetDevice (no CUDA device? this library has no CPU fallback)");
+    if (d.device == device) return d;
+    const HostContext &H = HostContext::get();
+    const size_t per = (size_t)kN * sizeof(ulonglong2);
+    void *mem = nullptr;
+    cuda_check(cudaMalloc(&mem, per * kNumMod * 2), "cudaMalloc(twiddles)");
+    for (int mi = 0; mi < kNumMod; mi++) {
+        char *f = (char *)mem + per * (size_t)(2 * mi);
+        char *i = f + per;
+        cuda_check(cudaMemcpy(f, H.twf[mi].data(), per, cudaMemcpyHostToDevice), "upload twf");
+        cuda_check(cudaMemcpy(i, H.twi[mi].data(), per, cudaMemcpyHostToDevice), "upload twi");
+        d.tabs.twf[mi] = (const ulonglong2 *)f;
+        d.tabs.twi[mi] = (const ulonglong2 *)i;
+    }
+    cuda_check(upload_constants(H.dc, d.tabs), "upload constants");
+    cuda_check(kernels_configure(), "kernel attributes");
+    d.table_mem = mem;
+    d.device = device;
+    return d;
+}
+
+}  // namespace fheb

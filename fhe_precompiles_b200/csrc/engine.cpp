@@ -1,0 +1,282 @@
+// See engine.h.
+#include "engine.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+
+#include "kernels.h"
+
+namespace fheb {
+
+void cuda_throw(cudaError_t e, const char *what) {
+    if (e != cudaSuccess)
+        throw std::runtime_error(std::string("fhe_b200: CUDA error in ") + what + ": " + cudaGetErrorString(e));
+}
+
+namespace {
+size_t env_size(const char *name, size_t dflt) {
+    const char *v = getenv(name);
+    if (!v || !*v) return dflt;
+    long long x = atoll(v);
+    return x > 0 ? (size_t)x : dflt;
+}
+uint64_t cheap_tag(Span s) {
+    // length + 4 sampled words: a pre-filter only, equality is decided by memcmp
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ s.n;
+    for (int i = 0; i < 4; i++) {
+        size_t off = s.n >= 8 ? (s.n - 8) * (size_t)i / 3 : 0;
+        uint64_t w = 0;
+        memcpy(&w, s.p + off, s.n >= 8 ? 8 : s.n);
+        h = (h ^ w) * 0xff51afd7ed558ccdull;
+    }
+    return h;
+}
+}  // namespace
+
+Engine &Engine::get() {
+    static Engine *e = new Engine();
+    return *e;
+}
+
+Engine::Engine() {
+    HostContext::get();
+    n_devices_ = device_count();
+    if (n_devices_ <= 0)
+        throw std::runtime_error("fhe_b200: no CUDA device visible; this library has no CPU fallback");
+    size_t max_dev = env_size("FHE_B200_MAX_DEVICES", (size_t)n_devices_);
+    if ((size_t)n_devices_ > max_dev) n_devices_ = (int)max_dev;
+    chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 148);
+    const size_t lanes_per_dev = env_size("FHE_B200_LANES", 4);
+    for (int d = 0; d < n_devices_; d++) {
+        device_context(d);
+        for (size_t i = 0; i < lanes_per_dev; i++) {
+            std::unique_ptr<Lane> l(new Lane());
+            l->device = d;
+            cuda_throw(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_throw(cudaMallocHost((void **)&l->h_a, kCtWords * 8), "cudaMallocHost");
+            cuda_throw(cudaMallocHost((void **)&l->h_b, kCtWords * 8), "cudaMallocHost");
+            cuda_throw(cudaMallocHost((void **)&l->h_out, kCtWords * 8), "cudaMallocHost");
+            cuda_throw(cudaMallocHost((void **)&l->h_plain, kN * 2), "cudaMallocHost");
+            cuda_throw(cudaMalloc((void **)&l->d_a, kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&l->d_b, kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&l->d_out, kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&l->d_plain, kN * 2), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&l->d_scratch, kScratchLimbsPerOp * kN * 8), "cudaMalloc");
+            lanes_.push_back(std::move(l));
+        }
+    }
+}
+
+Lane *Engine::acquire_lane() {
+    std::unique_lock<std::mutex> lk(lane_mu_);
+    for (;;) {
+        for (size_t k = 0; k < lanes_.size(); k++) {
+            Lane *l = lanes_[(next_lane_ + k) % lanes_.size()].get();
+            if (!l->busy) {
+                l->busy = true;
+                next_lane_ = (next_lane_ + k + 1) % lanes_.size();
+                return l;
+            }
+        }
+        lane_cv_.wait(lk);
+    }
+}
+void Engine::release_lane(Lane *l) {
+    {
+        std::lock_guard<std::mutex> lk(lane_mu_);
+        l->busy = false;
+    }
+    lane_cv_.notify_one();
+}
+
+// ---------------------------------------------------------------- key cache
+int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin) {
+    const uint64_t tag = cheap_tag(pk);
+    std::lock_guard<std::mutex> lk(key_mu_);
+    KeyEntry *hit = nullptr;
+    for (auto &e : keys_)
+        if (e->tag == tag && e->bytes.size() == pk.n && memcmp(e->bytes.data(), pk.p, pk.n) == 0) {
+            hit = e.get();
+            break;
+        }
+    if (!hit) {
+        std::unique_ptr<KeyEntry> e(new KeyEntry());
+        e->rk.resize(kRkWords);
+        int32_t rc = decode_public_key(pk, nullptr, e->rk.data(), &e->has_relin);
+        if (rc) return rc;
+        e->bytes.assign(pk.p, pk.p + pk.n);
+        e->tag = tag;
+        e->d_rk.assign((size_t)n_devices_, nullptr);
+        const size_t cap = env_size("FHE_B200_KEY_CACHE", 8);
+        if (keys_.size() >= cap) {  // evict least recently used
+            size_t victim = 0;
+            for (size_t i = 1; i < keys_.size(); i++)
+                if (keys_[i]->last_use < keys_[victim]->last_use) victim = i;
+            for (int d = 0; d < n_devices_; d++)
+                if (keys_[victim]->d_rk[(size_t)d]) {
+                    cudaSetDevice(d);
+                    cudaDeviceSynchronize();
+                    cudaFree(keys_[victim]->d_rk[(size_t)d]);
+                }
+            keys_.erase(keys_.begin() + (long)victim);
+        }
+        keys_.push_back(std::move(e));
+        hit = keys_.back().get();
+    }
+    hit->last_use = ++key_clock_;
+    if (!need_relin) {
+        if (d_rk) *d_rk = nullptr;
+        return kOk;
+    }
+    if (!hit->has_relin) return kErrSunscreen;  // sunscreen: relinearization keys required but absent
+    uint64_t *&slot = hit->d_rk[(size_t)device];
+    if (!slot) {
+        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+        cuda_throw(cudaMalloc((void **)&slot, kRkWords * 8), "cudaMalloc(rk)");
+        cuda_throw(cudaMemcpy(slot, hit->rk.data(), kRkWords * 8, cudaMemcpyHostToDevice), "upload rk");
+    }
+    *d_rk = slot;
+    return kOk;
+}
+
+// ---------------------------------------------------------------- scratch arenas
+uint64_t *Engine::scratch(int device, size_t ops) {
+    std::lock_guard<std::mutex> lk(arena_mu_);
+    if (arenas_.size() < (size_t)n_devices_) arenas_.resize((size_t)n_devices_);
+    Arena &a = arenas_[(size_t)device];
+    if (a.ops < ops) {
+        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+        if (a.p) {
+            cuda_throw(cudaDeviceSynchronize(), "sync before scratch regrow");
+            cudaFree(a.p);
+            a.p = nullptr;
+        }
+        cuda_throw(cudaMalloc((void **)&a.p, ops * kScratchLimbsPerOp * kN * 8), "cudaMalloc(scratch)");
+        a.ops = ops;
+    }
+    return a.p;
+}
+
+// ---------------------------------------------------------------- device-resident batched ops
+// scratch layout for a chunk of c ops: tens [c][15][N] | c3 [c][6][N] | ks [c][6][N]
+void Engine::mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
+                       cudaStream_t s) {
+    device_context(device);
+    const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
+    uint64_t *sc = scratch(device, chunk);
+    uint64_t *tens = sc, *c3 = tens + chunk * 15 * kN, *ks = c3 + chunk * 6 * kN;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t c = n - off < chunk ? n - off : chunk;
+        cuda_throw(launch_behz_tensor(a + off * kCtWords, b + off * kCtWords, tens, c, s), "behz_tensor");
+        cuda_throw(launch_floor_sk(tens, c3, c, s), "floor_sk");
+        cuda_throw(launch_relin_ks(c3, rk, ks, c, s), "relin_ks");
+        cuda_throw(launch_relin_finish(c3, ks, out + off * kCtWords, c, s), "relin_finish");
+    }
+}
+void Engine::multiply(int device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, cudaStream_t s) {
+    device_context(device);
+    const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
+    uint64_t *tens = scratch(device, chunk);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t c = n - off < chunk ? n - off : chunk;
+        cuda_throw(launch_behz_tensor(a + off * kCtWords, b + off * kCtWords, tens, c, s), "behz_tensor");
+        cuda_throw(launch_floor_sk(tens, out3 + off * 6 * kN, c, s), "floor_sk");
+    }
+}
+void Engine::relinearize(int device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, cudaStream_t s) {
+    device_context(device);
+    const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
+    uint64_t *sc = scratch(device, chunk);
+    uint64_t *ks = sc + chunk * 21 * kN;
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t c = n - off < chunk ? n - off : chunk;
+        cuda_throw(launch_relin_ks(c3 + off * 6 * kN, rk, ks, c, s), "relin_ks");
+        cuda_throw(launch_relin_finish(c3 + off * 6 * kN, ks, out + off * kCtWords, c, s), "relin_finish");
+    }
+}
+
+// ---------------------------------------------------------------- byte surface, one call
+namespace {
+struct LaneGuard {
+    Engine *e;
+    Lane *l;
+    void (Engine::*rel)(Lane *);
+    ~LaneGuard() { (e->*rel)(l); }
+};
+}  // namespace
+
+int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<uint8_t> *out) {
+    Span pk, sa, sb;
+    int32_t rc = unpack_binary_operation(in, &pk, &sa, &sb);
+    if (rc) return rc;
+
+    Lane *lane = acquire_lane();
+    LaneGuard guard{this, lane, &Engine::release_lane};
+    cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
+    cudaStream_t s = lane->stream;
+
+    // reference order (pack.rs:261-263): public key, then a, then b
+    const uint64_t *d_rk = nullptr;
+    const bool need_relin = (op == Op::Mul && shape == Shape::CtCt);
+    rc = relin_key(pk, lane->device, &d_rk, need_relin);
+    if (rc == kErrSunscreen && need_relin) {
+        // missing relin keys is a runtime (not a decoding) error: operands are still decoded first
+    } else if (rc) {
+        return rc;
+    }
+    const int32_t key_rc = rc;
+
+    CipherView va, vb;
+    const Span ct_a = (shape == Shape::PtCt) ? sb : sa;  // the ciphertext operand of ct-pt shapes
+    const Span pt = (shape == Shape::PtCt) ? sa : sb;
+    if (shape == Shape::CtCt) {
+        if ((rc = decode_ciphertext(sa, &va, lane->h_a))) return rc;
+        if ((rc = decode_ciphertext(sb, &vb, lane->h_b))) return rc;
+        if (!data_type_matches(va.data_type, kind) || !data_type_matches(vb.data_type, kind)) return kErrSunscreen;
+    } else if (shape == Shape::CtPt) {
+        if ((rc = decode_ciphertext(ct_a, &va, lane->h_a))) return rc;
+        if ((rc = encode_scalar(kind, pt, lane->h_plain))) return rc;
+        if (!data_type_matches(va.data_type, kind)) return kErrSunscreen;
+    } else {
+        if ((rc = encode_scalar(kind, pt, lane->h_plain))) return rc;
+        if ((rc = decode_ciphertext(ct_a, &va, lane->h_a))) return rc;
+        if (!data_type_matches(va.data_type, kind)) return kErrSunscreen;
+    }
+    if (key_rc) return key_rc;
+
+    cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D a");
+    if (shape == Shape::CtCt) {
+        cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D b");
+        if (op == Op::Mul) {
+            uint64_t *tens = lane->d_scratch, *c3 = tens + 15 * kN, *ks = c3 + 6 * kN;
+            cuda_throw(launch_behz_tensor(lane->d_a, lane->d_b, tens, 1, s), "behz_tensor");
+            cuda_throw(launch_floor_sk(tens, c3, 1, s), "floor_sk");
+            cuda_throw(launch_relin_ks(c3, d_rk, ks, 1, s), "relin_ks");
+            cuda_throw(launch_relin_finish(c3, ks, lane->d_out, 1, s), "relin_finish");
+        } else {
+            cuda_throw(launch_eltwise(lane->d_a, lane->d_b, lane->d_out, 1, op == Op::Add ? 0 : 1, s), "eltwise");
+        }
+    } else {
+        cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
+        if (op == Op::Mul) {
+            cuda_throw(launch_mul_plain(lane->d_a, lane->d_plain, lane->d_out, 1, s), "mul_plain");
+        } else {
+            // a + b: add_plain; ct - pt: sub_plain; pt - ct: negate(sub_plain(ct, pt))  
+            int mode = (op == Op::Add) ? 0 : (shape == Shape::CtPt ? 1 : 3);
+            cuda_throw(launch_plain_addsub(lane->d_a, lane->d_plain, lane->d_out, 1, mode, s), "plain_addsub");
+        }
+    }
+    cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    return encode_ciphertext(va, lane->h_out, out);
+}
+
+// ---------------------------------------------------------------- threshold API (placeholders until K11 lands)
+int32_t Engine::encrypt(Kind, Span, Span, Span, std::vector<uint8_t> *) { return kErrFailedEncryption; }
+int32_t Engine::reencrypt(Kind, Span, Span, Span, std::vector<uint8_t> *) { return kErrFailedEncryption; }
+int32_t Engine::decrypt(Kind, Span, Span, Span, std::vector<uint8_t> *) { return kErrFailedDecryption; }
+
+}  // namespace fheb

@@ -1,0 +1,95 @@
+// Dispatcher between the byte surface and the kernels: what FheApp (fhe.rs:56-780) + sunscreen's
+// Runtime::run do in the reference.  One process-wide Engine, re-entrant like the reference's
+// `FHE: Lazy<FheApp>` (testnet.rs:25).  There is no CPU path: every op runs on a CUDA device or fails.
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <vector>
+
+#include "codec.h"
+#include "context.h"
+
+namespace fheb {
+
+enum class Op : int { Add = 0, Sub = 1, Mul = 2 };
+enum class Shape : int { CtCt = 0, CtPt = 1, PtCt = 2 };
+
+// words of per-op scratch for multiply+relinearise: tensor (15 limbs) + size-3 result (6) + key-switch (6)
+constexpr size_t kScratchLimbsPerOp = 15 + 6 + 6;
+
+struct Lane {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t *h_a = nullptr, *h_b = nullptr, *h_out = nullptr;  // pinned, kCtWords each
+    uint16_t *h_plain = nullptr;                                // pinned, kN
+    uint64_t *d_a = nullptr, *d_b = nullptr, *d_out = nullptr, *d_scratch = nullptr;
+    uint16_t *d_plain = nullptr;
+    bool busy = false;
+};
+
+struct KeyEntry {
+    std::vector<uint8_t> bytes;  // exact PublicKey bytes this entry was parsed from
+    uint64_t tag = 0;            // cheap pre-filter
+    bool has_relin = false;
+    std::vector<uint64_t> rk;    // host copy [2][2][3][N]
+    std::vector<uint64_t *> d_rk;  // per device, lazily uploaded
+    uint64_t last_use = 0;
+};
+
+class Engine {
+   public:
+    static Engine &get();
+
+    // the 36 binary precompiles: bytes in -> bytes out (lib.rs error code)
+    int32_t binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<uint8_t> *out);
+
+    // device-resident batched entry points (pointers are device memory on `device`)
+    void mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
+                   cudaStream_t s);
+    void multiply(int device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, cudaStream_t s);
+    void relinearize(int device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, cudaStream_t s);
+
+    // threshold-network simulation API (fhe.rs:594-779) against the embedded network keys
+    int32_t encrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
+    int32_t reencrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
+    int32_t decrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
+
+    // per-device scratch arena for `ops` concurrent multiply+relin ops (grown on demand, never shrunk)
+    uint64_t *scratch(int device, size_t ops);
+    size_t chunk_ops() const { return chunk_ops_; }
+    int n_devices() const { return n_devices_; }
+
+    // relin key for the PublicKey bytes, parsed + validated once and cached by content
+    int32_t relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin);
+
+   private:
+    Engine();
+    Lane *acquire_lane();
+    void release_lane(Lane *);
+
+    int n_devices_ = 0;
+    size_t chunk_ops_ = 148;
+    std::vector<std::unique_ptr<Lane>> lanes_;
+    std::mutex lane_mu_;
+    std::condition_variable lane_cv_;
+    size_t next_lane_ = 0;
+
+    std::mutex key_mu_;
+    std::vector<std::unique_ptr<KeyEntry>> keys_;
+    uint64_t key_clock_ = 0;
+
+    struct Arena {
+        uint64_t *p = nullptr;
+        size_t ops = 0;
+    };
+    std::vector<Arena> arenas_;
+    std::mutex arena_mu_;
+};
+
+void cuda_throw(cudaError_t e, const char *what);
+uint64_t launch_count();
+
+}  // namespace fheb

@@ -1,0 +1,533 @@
+// sm_100a kernels for the BFV precompile hot path (add / sub / negate, plain ops, BEHZ multiply,
+// relinearisation) and their launchers.  Replaces the SEAL 4.0 Evaluator calls that
+// FheApp::run (/root/reference/src/fhe.rs:138-152) triggers for the 36 programs at
+// fhe.rs:814-1022.  Integer-pipe work: no tensor cores.
+//
+// Device data layouts (u64 everywhere, limb-major):
+//   data-level ciphertext   [poly 0..1][limb q0,q1][4096]                 128 KiB
+//   size-3 ciphertext       [poly 0..2][limb q0,q1][4096]
+//   BEHZ tensor scratch     [poly 0..2][limb q0,q1,b0,b1,msk][4096]       (already x t)
+//   key-switch scratch      [poly 0..1][limb q0,q1,P][4096]
+//   relin key               [digit 0..1][poly 0..1][limb q0,q1,P][4096]   NTT form, as in the key file
+//   plaintext               [4096] u16 coefficients < t, zero padded
+#include <atomic>
+#include <cstdio>
+
+#include "kernels.h"
+#include "ntt.cuh"
+
+namespace fheb {
+
+__constant__ DevConsts kc;
+__constant__ DevTables kt;
+
+cudaError_t upload_constants(const DevConsts &c, const DevTables &t) {
+    cudaError_t e = cudaMemcpyToSymbol(kc, &c, sizeof(c));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(kt, &t, sizeof(t));
+}
+
+// =====================================================================================
+// K1/K2: batched limb NTT (config 2 microbenchmark; also used by the parity tests)
+// =====================================================================================
+template <int MI, bool INV>
+__device__ __forceinline__ void ntt_limb_body(u64 *limb, u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 v[1][8];
+    if (!INV) {
+        load_natural(limb, v[0], t);
+        ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+        store_chunk8(limb, v[0], t);
+    } else {
+        load_chunk8(limb, v[0], t);
+        ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+        store_natural(limb, v[0], t);
+    }
+}
+
+template <bool INV>
+__global__ void __launch_bounds__(kThreads) k_ntt(u64 *data, LimbMods mods) {
+    extern __shared__ __align__(16) u64 smem[];
+    const int t = threadIdx.x;
+    u64 *limb = data + (size_t)blockIdx.x * kN;
+    switch (mods.mod[blockIdx.x % mods.n]) {
+        case MQ0: ntt_limb_body<MQ0, INV>(limb, smem, t); break;
+        case MQ1: ntt_limb_body<MQ1, INV>(limb, smem, t); break;
+        case MP: ntt_limb_body<MP, INV>(limb, smem, t); break;
+        case MB0: ntt_limb_body<MB0, INV>(limb, smem, t); break;
+        case MB1: ntt_limb_body<MB1, INV>(limb, smem, t); break;
+        default: ntt_limb_body<MSK, INV>(limb, smem, t); break;
+    }
+}
+
+// =====================================================================================
+// K3: ciphertext add / sub / negate   (SEAL add_poly_coeffmod / sub_poly_coeffmod / negate_poly_coeffmod)
+// =====================================================================================
+template <class M>
+__device__ __forceinline__ u64 eltop(u64 a, u64 b, int op) {
+    if (op == 0) return addmod<M>(a, b);
+    if (op == 1) return submod<M>(a, b);
+    return a ? M::q - a : 0;
+}
+// n2 = number of ulonglong2 elements; limb index = (element / N) & 1
+__global__ void __launch_bounds__(256) k_eltwise(const ulonglong2 *__restrict__ a, const ulonglong2 *__restrict__ b,
+                                                 ulonglong2 *__restrict__ out, size_t n2, int op) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        ulonglong2 x = a[i];
+        ulonglong2 y = (op == 2) ? make_ulonglong2(0, 0) : b[i];
+        int limb = (int)((i / (kN / 2)) & 1);
+        ulonglong2 r;
+        if (limb == 0) {
+            r.x = eltop<Mod<MQ0>>(x.x, y.x, op);
+            r.y = eltop<Mod<MQ0>>(x.y, y.y, op);
+        } else {
+            r.x = eltop<Mod<MQ1>>(x.x, y.x, op);
+            r.y = eltop<Mod<MQ1>>(x.y, y.y, op);
+        }
+        out[i] = r;
+    }
+}
+
+// =====================================================================================
+// K4: add_plain / sub_plain (+ optional negate for `pt - ct`)
+//     SEAL multiply_add_plain_with_scaling_variant / multiply_sub_plain_with_scaling_variant
+// mode bit0: subtract; bit1: negate the whole result afterwards
+// =====================================================================================
+template <class M>
+__device__ __forceinline__ u64 plain_scaled(u64 m, int l) {
+    // fix = floor((q mod t) * m + (t+1)/2) / t); scaled = Delta*m + fix mod q_l
+    u64 fix = (kc.q_mod_t * m + kc.upper_half_threshold) / kT;
+    u64 lo = kc.delta_mod_q[l] * m + fix;  // < 2^36 * 2^12 + small: fits
+    return reduce64<M>(lo);
+}
+__global__ void __launch_bounds__(256) k_plain_addsub(const u64 *__restrict__ ct, const unsigned short *__restrict__ plain,
+                                                      u64 *__restrict__ out, size_t n_ops, int mode) {
+    size_t total = n_ops * 4 * kN;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        size_t op = i / (4 * kN);
+        int rem = (int)(i % (4 * kN));
+        int poly = rem / (2 * kN);
+        int limb = (rem / kN) & 1;
+        int c = rem % kN;
+        u64 v = ct[i];
+        if (poly == 0) {
+            u64 m = plain[op * kN + c];
+            if (limb == 0) {
+                u64 s = plain_scaled<Mod<MQ0>>(m, 0);
+                v = (mode & 1) ? submod<Mod<MQ0>>(v, s) : addmod<Mod<MQ0>>(v, s);
+            } else {
+                u64 s = plain_scaled<Mod<MQ1>>(m, 1);
+                v = (mode & 1) ? submod<Mod<MQ1>>(v, s) : addmod<Mod<MQ1>>(v, s);
+            }
+        }
+        if (mode & 2) v = v ? (limb ? Mod<MQ1>::q : Mod<MQ0>::q) - v : 0;
+        out[i] = v;
+    }
+}
+
+// =====================================================================================
+// K5: multiply_plain   (SEAL Evaluator::multiply_plain_normal)
+// one CTA per (limb, op): NTT(lift(m)), NTT(c0), NTT(c1), dyadic, 2 x INTT
+// =====================================================================================
+template <int MI>
+__device__ __forceinline__ void mul_plain_body(const u64 *__restrict__ ct, const unsigned short *__restrict__ plain,
+                                               u64 *__restrict__ out, u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 v[3][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        u64 m = plain[r * kThreads + t];
+        v[0][r] = m + (m >= kc.upper_half_threshold ? kc.upper_half_incr[MI] : 0);
+    }
+    load_natural(ct + (size_t)(0 * 2 + MI) * kN, v[1], t);
+    load_natural(ct + (size_t)(1 * 2 + MI) * kN, v[2], t);
+    ntt_forward<M, 3, true>(v, smem, kt.twf[MI], t);
+    u64 d[2][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        d[0][r] = mulmod<M>(v[1][r], v[0][r]);
+        d[1][r] = mulmod<M>(v[2][r], v[0][r]);
+    }
+    ntt_inverse<M, 2>(d, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    store_natural(out + (size_t)(0 * 2 + MI) * kN, d[0], t);
+    store_natural(out + (size_t)(1 * 2 + MI) * kN, d[1], t);
+}
+__global__ void __launch_bounds__(kThreads, 1) k_mul_plain(const u64 *__restrict__ ct, const unsigned short *__restrict__ plain,
+                                                            u64 *__restrict__ out) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const u64 *c = ct + op * 4 * kN;
+    const unsigned short *p = plain + op * kN;
+    u64 *o = out + op * 4 * kN;
+    if (blockIdx.x == 0)
+        mul_plain_body<MQ0>(c, p, o, smem, threadIdx.x);
+    else
+        mul_plain_body<MQ1>(c, p, o, smem, threadIdx.x);
+}
+
+// =====================================================================================
+// K6+K1+K7+K2: BEHZ base extension -> forward NTT -> tensor -> inverse NTT (x t)
+//   SEAL Evaluator::bfv_multiply steps (1)-(6); RNSTool::fastbconv_m_tilde, RNSTool::sm_mrq
+// one CTA per (extended limb e = q0,q1,b0,b1,msk ; op)
+// =====================================================================================
+// Loads polynomial `poly` of a data-level ciphertext into pass-0 register layout in limb EI of the
+// extended base.  EI < 2: plain copy of the q-limb.  EI >= 2: fast base conversion through m_tilde with
+// the Montgomery correction, all per coefficient:
+//   tmp_l = x_l * (m~ * (q/q_l)^-1) mod q_l                     (canonical)
+//   r     = -(tmp_0*(q/q_0) + tmp_1*(q/q_1)) * q^-1 mod 2^32, centred
+//   x'_k  = (tmp_0*(q/q_0) + tmp_1*(q/q_1) + r*q) * m~^-1 mod p_k    (constants pre-multiplied by m~^-1)
+template <int EI>
+__device__ __forceinline__ void load_extended(const u64 *__restrict__ ct, int poly, u64 (&v)[8], int t) {
+    constexpr int MI = kExtLimb[EI];
+    using M = Mod<MI>;
+    if (EI < 2) {
+        load_natural(ct + (size_t)(poly * 2 + EI) * kN, v, t);
+    } else {
+        constexpr int K = EI - 2;
+        const u64 *x0 = ct + (size_t)(poly * 2 + 0) * kN;
+        const u64 *x1 = ct + (size_t)(poly * 2 + 1) * kN;
+        const u64 cA = kc.extA[K], cB = kc.extB[K], cC = kc.extC[K];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            int i = r * kThreads + t;
+            u64 t0 = shoup<Mod<MQ0>>(x0[i], kc.ext_in[0].w, kc.ext_in[0].ws);
+            u64 t1 = shoup<Mod<MQ1>>(x1[i], kc.ext_in[1].w, kc.ext_in[1].ws);
+            u32 ymt = (u32)t0 * kc.punct_q_mod_mtilde[0] + (u32)t1 * kc.punct_q_mod_mtilde[1];
+            u32 rm = ymt * kc.neg_inv_q_mod_mtilde;
+            u64 rr = rm;
+            if (rm >= 0x80000000u) rr += M::q - kMTilde;
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, t0, cA);
+            mac128(lo, hi, t1, cB);
+            mac128(lo, hi, rr, cC);
+            v[r] = reduce128<M>(hi, lo);
+        }
+    }
+}
+
+template <int EI>
+__device__ __forceinline__ void behz_tensor_body(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ tens,
+                                                 u64 *smem, int t) {
+    constexpr int MI = kExtLimb[EI];
+    using M = Mod<MI>;
+    const ulonglong2 *twf = kt.twf[MI];
+    // a0, a1: transform in buffers 0-1, then park the results in buffers 2-3 at this thread's own
+    // pass-9 slots (same slots the inverse transform later overwrites, so no cross-thread hazard)
+    {
+        u64 A[2][8];
+        load_extended<EI>(a, 0, A[0], t);
+        load_extended<EI>(a, 1, A[1], t);
+        ntt_forward<M, 2, true>(A, smem, twf, t);
+        smem_store<2, 9>(smem + 2 * kN, A, t);
+    }
+    u64 B[2][8];
+    load_extended<EI>(b, 0, B[0], t);
+    load_extended<EI>(b, 1, B[1], t);
+    ntt_forward<M, 2, true>(B, smem, twf, t);
+    u64 D[3][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int slot = swz(elem_index<9>(t, r));
+        const u64 a0 = smem[2 * kN + slot], a1 = smem[3 * kN + slot];
+        D[0][r] = mulmod<M>(a0, B[0][r]);
+        u64 lo = 0, hi = 0;
+        mac128(lo, hi, a0, B[1][r]);
+        mac128(lo, hi, a1, B[0][r]);
+        D[1][r] = reduce128<M>(hi, lo);
+        D[2][r] = mulmod<M>(a1, B[1][r]);
+    }
+    ntt_inverse<M, 3>(D, smem, kt.twi[MI], t, kc.ninv_t[MI].w, kc.ninv_t[MI].ws);
+#pragma unroll
+    for (int p = 0; p < 3; p++) store_natural(tens + (size_t)(p * 5 + EI) * kN, D[p], t);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_behz_tensor(const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                              u64 *__restrict__ tens) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const u64 *pa = a + op * 4 * kN;
+    const u64 *pb = b + op * 4 * kN;
+    u64 *pt = tens + op * 15 * kN;
+    const int t = threadIdx.x;
+    switch (blockIdx.x) {
+        case 0: behz_tensor_body<0>(pa, pb, pt, smem, t); break;
+        case 1: behz_tensor_body<1>(pa, pb, pt, smem, t); break;
+        case 2: behz_tensor_body<2>(pa, pb, pt, smem, t); break;
+        case 3: behz_tensor_body<3>(pa, pb, pt, smem, t); break;
+        default: behz_tensor_body<4>(pa, pb, pt, smem, t); break;
+    }
+}
+
+// debug / parity tap: base extension only, ext layout [4 polys a0,a1,b0,b1][5 limbs][N]
+template <int EI>
+__device__ __forceinline__ void extend_only_body(const u64 *a, const u64 *b, u64 *ext, int t) {
+    u64 v[8];
+    for (int p = 0; p < 4; p++) {
+        load_extended<EI>(p < 2 ? a : b, p & 1, v, t);
+        store_natural(ext + (size_t)(p * 5 + EI) * kN, v, t);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_behz_extend_tap(const u64 *a, const u64 *b, u64 *ext) {
+    const size_t op = blockIdx.y;
+    const u64 *pa = a + op * 4 * kN;
+    const u64 *pb = b + op * 4 * kN;
+    u64 *pe = ext + op * 20 * kN;
+    const int t = threadIdx.x;
+    switch (blockIdx.x) {
+        case 0: extend_only_body<0>(pa, pb, pe, t); break;
+        case 1: extend_only_body<1>(pa, pb, pe, t); break;
+        case 2: extend_only_body<2>(pa, pb, pe, t); break;
+        case 3: extend_only_body<3>(pa, pb, pe, t); break;
+        default: extend_only_body<4>(pa, pb, pe, t); break;
+    }
+}
+
+// =====================================================================================
+// K8: fast_floor + fastbconv_sk   (SEAL RNSTool::fast_floor, RNSTool::fastbconv_sk), per coefficient
+//   tens [op][3][5][N] (x t, canonical)  ->  c3 [op][3][2][N]
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
+    using Q0 = Mod<MQ0>;
+    using Q1 = Mod<MQ1>;
+    using B0 = Mod<MB0>;
+    using B1 = Mod<MB1>;
+    using SK = Mod<MSK>;
+    size_t total = n_ops * 3 * kN;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        size_t opp = g / kN;  // op*3 + poly
+        int i = (int)(g % kN);
+        const u64 *in = tens + opp * 5 * kN + i;
+        u64 v0 = in[0 * kN], v1 = in[1 * kN], vb0 = in[2 * kN], vb1 = in[3 * kN], vsk = in[4 * kN];
+        // fast_floor: q-part -> Bsk, f_k = (v_k - conv_k) * q^-1 mod p_k  (constants merged)
+        u64 t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
+        u64 t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
+        u64 f0, f1, f2;
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, vb0, kc.flV[0]);
+            mac128(lo, hi, t0, kc.flA[0]);
+            mac128(lo, hi, t1, kc.flB[0]);
+            f0 = reduce128<B0>(hi, lo);
+        }
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, vb1, kc.flV[1]);
+            mac128(lo, hi, t0, kc.flA[1]);
+            mac128(lo, hi, t1, kc.flB[1]);
+            f1 = reduce128<B1>(hi, lo);
+        }
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, vsk, kc.flV[2]);
+            mac128(lo, hi, t0, kc.flA[2]);
+            mac128(lo, hi, t1, kc.flB[2]);
+            f2 = reduce128<SK>(hi, lo);
+        }
+        // fastbconv_sk
+        u64 tb0 = shoup<B0>(f0, kc.inv_punct_B[0].w, kc.inv_punct_B[0].ws);
+        u64 tb1 = shoup<B1>(f1, kc.inv_punct_B[1].w, kc.inv_punct_B[1].ws);
+        u64 h;
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, tb0, kc.punct_B_mod_msk[0]);
+            mac128(lo, hi, tb1, kc.punct_B_mod_msk[1]);
+            h = reduce128<SK>(hi, lo);
+        }
+        u64 alpha = shoup<SK>(h + (SK::q - f2), kc.inv_B_mod_msk.w, kc.inv_B_mod_msk.ws);
+        bool neg = alpha > (SK::q >> 1);
+        u64 am = neg ? SK::q - alpha : alpha;
+        u64 *out = c3 + opp * 2 * kN + i;
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, tb0, kc.punct_B_mod_q[0][0]);
+            mac128(lo, hi, tb1, kc.punct_B_mod_q[1][0]);
+            mac128(lo, hi, am, neg ? kc.B_mod_q[0] : kc.neg_B_mod_q[0]);
+            out[0] = reduce128<Q0>(hi, lo);
+        }
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, tb0, kc.punct_B_mod_q[0][1]);
+            mac128(lo, hi, tb1, kc.punct_B_mod_q[1][1]);
+            mac128(lo, hi, am, neg ? kc.B_mod_q[1] : kc.neg_B_mod_q[1]);
+            out[kN] = reduce128<Q1>(hi, lo);
+        }
+    }
+}
+
+// =====================================================================================
+// K9a: key switching core  (SEAL Evaluator::switch_key_inplace, BFV branch, up to the inverse NTTs)
+// one CTA per (key modulus J = q0,q1,P ; op): 2 digit NTTs, MAC with the relin key, 2 INTTs
+//   c3 [op][3][2][N]  ->  ks [op][2][3][N]   (coefficient form, canonical)
+// =====================================================================================
+template <int MI>
+__device__ __forceinline__ void relin_ks_body(const u64 *__restrict__ c2, const u64 *__restrict__ rk, u64 *__restrict__ ks,
+                                              u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 D[2][8];
+    load_natural(c2, D[0], t);       // digit 0: residues mod q0 as integers
+    load_natural(c2 + kN, D[1], t);  // digit 1: residues mod q1 as integers
+    // lazy forward transform absorbs the "mod p_J" of the digit (inputs < 2^36 < 4 p_J)
+    ntt_forward<M, 2, true>(D, smem, kt.twf[MI], t);
+    u64 E[2][8];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        u64 k0[8], k1[8];
+        load_chunk8_ldg(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN, k0, t);
+        load_chunk8_ldg(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN, k1, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, D[0][r], k0[r]);
+            mac128(lo, hi, D[1][r], k1[r]);
+            E[k][r] = reduce128<M>(hi, lo);
+        }
+    }
+    ntt_inverse<M, 2>(E, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    store_natural(ks + (size_t)(0 * 3 + MI) * kN, E[0], t);
+    store_natural(ks + (size_t)(1 * 3 + MI) * kN, E[1], t);
+}
+__global__ void __launch_bounds__(kThreads, 1) k_relin_ks(const u64 *__restrict__ c3, const u64 *__restrict__ rk,
+                                                           u64 *__restrict__ ks) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const u64 *c2 = c3 + op * 6 * kN + 4 * kN;
+    u64 *pk = ks + op * 6 * kN;
+    const int t = threadIdx.x;
+    switch (blockIdx.x) {
+        case 0: relin_ks_body<MQ0>(c2, rk, pk, smem, t); break;
+        case 1: relin_ks_body<MQ1>(c2, rk, pk, smem, t); break;
+        default: relin_ks_body<MP>(c2, rk, pk, smem, t); break;
+    }
+}
+
+// =====================================================================================
+// K9b: rounded division by P and accumulation into (c0, c1)   (tail of switch_key_inplace)
+//   out[op][k][l][i] = c3[op][k][l][i] + (ks[k][l][i] - ((ks[k][P][i] + P/2 mod P) mod q_l - (P/2 mod q_l))) * P^-1 mod q_l
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_relin_finish(const u64 *__restrict__ c3, const u64 *__restrict__ ks,
+                                                      u64 *__restrict__ out, size_t n_ops) {
+    using Q0 = Mod<MQ0>;
+    using Q1 = Mod<MQ1>;
+    using PP = Mod<MP>;
+    size_t total = n_ops * 2 * kN;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        size_t op = g / (2 * kN);
+        int k = (int)((g / kN) & 1);
+        int i = (int)(g % kN);
+        const u64 *pk = ks + (op * 2 + k) * 3 * kN + i;
+        const u64 *pc = c3 + (op * 3 + k) * 2 * kN + i;
+        u64 *po = out + (op * 2 + k) * 2 * kN + i;
+        u64 last = csub<PP>(pk[2 * kN] + kc.half_P, PP::q);
+        {
+            u64 tl = submod<Q0>(reduce64<Q0>(last), kc.half_P_mod_q[0]);
+            u64 d = submod<Q0>(pk[0], tl);
+            u64 v = shoup<Q0>(d, kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws);
+            po[0] = addmod<Q0>(v, pc[0]);
+        }
+        {
+            u64 tl = submod<Q1>(reduce64<Q1>(last), kc.half_P_mod_q[1]);
+            u64 d = submod<Q1>(pk[kN], tl);
+            u64 v = shoup<Q1>(d, kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws);
+            po[kN] = addmod<Q1>(v, pc[kN]);
+        }
+    }
+}
+
+// =====================================================================================
+// launchers
+// =====================================================================================
+static const int kSmem1 = 1 * kN * 8, kSmem2 = 2 * kN * 8, kSmem3 = 3 * kN * 8, kSmem4 = 4 * kN * 8;
+
+cudaError_t kernels_configure() {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_mul_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem3);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_behz_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_relin_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+static std::atomic<unsigned long long> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+
+static int eltwise_grid(size_t n, int block) {
+    size_t g = (n + block - 1) / block;
+    size_t cap = 148 * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+cudaError_t launch_ntt(u64 *data, size_t n_limbs, const LimbMods &mods, bool inverse, cudaStream_t s) {
+    if (n_limbs == 0) return cudaSuccess;
+    if (inverse)
+        k_ntt<true><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
+    else
+        k_ntt<false><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eltwise(const u64 *a, const u64 *b, u64 *out, size_t n_ops, int op, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    size_t n2 = n_ops * 4 * kN / 2;
+    k_eltwise<<<eltwise_grid(n2, 256), 256, 0, s>>>((const ulonglong2 *)a, (const ulonglong2 *)b, (ulonglong2 *)out, n2, op);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_plain_addsub(const u64 *ct, const unsigned short *plain, u64 *out, size_t n_ops, int mode, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_plain_addsub<<<eltwise_grid(n_ops * 4 * kN, 256), 256, 0, s>>>(ct, plain, out, n_ops, mode);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mul_plain(const u64 *ct, const unsigned short *plain, u64 *out, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    for (size_t done = 0; done < n_ops;) {
+        size_t c = n_ops - done < 65535 ? n_ops - done : 65535;
+        k_mul_plain<<<dim3(2, (unsigned)c), kThreads, kSmem3, s>>>(ct + done * 4 * kN, plain + done * kN, out + done * 4 * kN);
+        if (done) g_launches.fetch_add(1, std::memory_order_relaxed);
+        done += c;
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_behz_extend_tap(const u64 *a, const u64 *b, u64 *ext, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_behz_extend_tap<<<dim3(5, (unsigned)n_ops), kThreads, 0, s>>>(a, b, ext);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *tens, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_behz_tensor<<<dim3(5, (unsigned)n_ops), kThreads, kSmem4, s>>>(a, b, tens);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_floor_sk<<<eltwise_grid(n_ops * 3 * kN, 256), 256, 0, s>>>(tens, c3, n_ops);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_relin_ks<<<dim3(3, (unsigned)n_ops), kThreads, kSmem2, s>>>(c3, rk, ks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_relin_finish(const u64 *c3, const u64 *ks, u64 *out, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_relin_finish<<<eltwise_grid(n_ops * 2 * kN, 256), 256, 0, s>>>(c3, ks, out, n_ops);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+}  // namespace fheb

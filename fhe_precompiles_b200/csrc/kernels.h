@@ -1,0 +1,32 @@
+// Launchers of the sm_100a kernels in kernels.cu (device pointers, caller-chosen stream).
+#pragma once
+#include <cstddef>
+
+#include "devconsts.h"
+
+namespace fheb {
+
+struct LimbMods {
+    int n;               // limbs per polynomial in the caller's layout
+    int mod[kNumMod];    // modulus index of each limb
+};
+
+cudaError_t upload_constants(const DevConsts &c, const DevTables &t);  // to the current device
+cudaError_t kernels_configure();                                       // opt-in shared memory sizes, current device
+
+// data: n_limbs consecutive 4096-word limbs, limb i uses modulus mods.mod[i % mods.n]; in place
+cudaError_t launch_ntt(u64 *data, size_t n_limbs, const LimbMods &mods, bool inverse, cudaStream_t s);
+// op: 0 add, 1 sub, 2 negate(a)
+cudaError_t launch_eltwise(const u64 *a, const u64 *b, u64 *out, size_t n_ops, int op, cudaStream_t s);
+// mode bit0: subtract, bit1: negate result
+cudaError_t launch_plain_addsub(const u64 *ct, const unsigned short *plain, u64 *out, size_t n_ops, int mode, cudaStream_t s);
+cudaError_t launch_mul_plain(const u64 *ct, const unsigned short *plain, u64 *out, size_t n_ops, cudaStream_t s);
+cudaError_t launch_behz_extend_tap(const u64 *a, const u64 *b, u64 *ext, size_t n_ops, cudaStream_t s);
+cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *tens, size_t n_ops, cudaStream_t s);
+cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s);
+cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
+cudaError_t launch_relin_finish(const u64 *c3, const u64 *ks, u64 *out, size_t n_ops, cudaStream_t s);
+
+uint64_t launch_count();
+
+}  // namespace fheb

@@ -1,0 +1,238 @@
+// Negacyclic NTT building blocks, N = 4096, one CTA of 512 threads, 8 coefficients per thread.
+// Replaces SEAL ntt_negacyclic_harvey / inverse_ntt_negacyclic_harvey (util/ntt.h, dwthandler.h)
+// as used by Evaluator::bfv_multiply / switch_key_inplace / multiply_plain on the reference's hot
+// path (FheApp::run, /root/reference/src/fhe.rs:138-152).  Same transform: forward takes natural
+// order to bit-reversed order with twiddle table rp[bitrev(i)] = psi^i, inverse undoes it and
+// scales by a caller-supplied constant (N^-1, possibly merged with another scalar).
+//
+// Structure: the 12 radix-2 stages are grouped into 4 register-resident radix-8 passes.
+// Pass with first stage S0 keeps index bits (11-S0, 10-S0, 9-S0) in registers; the other nine bits
+// are the thread id.  Between passes the 8 values go through shared memory with an XOR swizzle that
+// makes every pass's 64-bit accesses bank-conflict-free for a half warp (see swz()).
+// Twiddles are (w, floor(w*2^64/q)) pairs read through the read-only path from an L2-resident table.
+#pragma once
+#include "modarith.cuh"
+
+namespace fheb {
+
+constexpr int kThreads = 512;
+
+// physical slot of logical coefficient i inside a 4096-entry shared buffer
+__device__ __forceinline__ int swz(int i) { return i ^ ((i >> 4) & 7) ^ (((i >> 6) & 1) << 3); }
+
+// logical index of register r (0..7) of thread t in the pass whose first stage is S0
+template <int S0>
+__device__ __forceinline__ int elem_index(int t, int r) {
+    constexpr int LB = 9 - S0;
+    int lower = t & ((1 << LB) - 1);
+    int upper = t >> LB;
+    return (upper << (12 - S0)) | (r << LB) | lower;
+}
+
+template <int S0>
+__device__ __forceinline__ int pass_upper(int t) {
+    return t >> (9 - S0);
+}
+
+// ---------------------------------------------------------------- butterflies
+// forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY)
+template <class M>
+__device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
+    if (M::kSmall) {
+        // no conditional subtraction: bound grows by 2q per stage (<= 26q < 2^42 after 12 stages)
+        u64 T = shoup_lazy<M>(Y, w, ws);
+        Y = X + (M::two_q - T);
+        X = X + T;
+    } else {
+        // Harvey: inputs in [0,4q), outputs in [0,4q)
+        u64 x = csub<M>(X, M::two_q);
+        u64 T = shoup_lazy<M>(Y, w, ws);
+        X = x + T;
+        Y = x + (M::two_q - T);
+    }
+}
+// inverse (Gentleman-Sande): (X, Y) -> (X + Y, w(X - Y)); G = global stage index 0..11
+template <class M, int G>
+__device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
+    if (M::kSmall) {
+        // inputs < 2^(G+1) q, X output < 2^(G+2) q, Y output < 2q
+        constexpr u64 K = M::q << (G + 1);
+        u64 D = X + (K - Y);
+        X = X + Y;
+        Y = shoup_lazy<M>(D, w, ws);
+    } else {
+        // Harvey: inputs and outputs in [0,2q)
+        u64 D = X + (M::two_q - Y);
+        X = csub<M>(X + Y, M::two_q);
+        Y = shoup_lazy<M>(D, w, ws);
+    }
+}
+
+__device__ __forceinline__ ulonglong2 ldtw(const ulonglong2 *__restrict__ tw, int i) { return __ldg(tw + i); }
+
+// ---------------------------------------------------------------- register radix-8 passes
+// v[p][r]: r = 4*r2 + 2*r1 + r0, r2 <-> index bit 11-S0 (largest gap)
+template <class M, int NP, int S0>
+__device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__restrict__ tw, int upper) {
+    {
+        ulonglong2 w = ldtw(tw, (1 << S0) + upper);
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) fwd_bfly<M>(v[p][r], v[p][r + 4], w.x, w.y);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        ulonglong2 w = ldtw(tw, (2 << S0) + 2 * upper + h);
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) fwd_bfly<M>(v[p][4 * h + r], v[p][4 * h + r + 2], w.x, w.y);
+    }
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        ulonglong2 w = ldtw(tw, (4 << S0) + 4 * upper + h);
+#pragma unroll
+        for (int p = 0; p < NP; p++) fwd_bfly<M>(v[p][2 * h], v[p][2 * h + 1], w.x, w.y);
+    }
+}
+
+// inverse pass over the same register bits, stages in reverse order. G0 = global index of its first stage.
+template <class M, int NP, int S0, int G0>
+__device__ __forceinline__ void inv_pass(u64 (&v)[NP][8], const ulonglong2 *__restrict__ tw, int upper) {
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        ulonglong2 w = ldtw(tw, (4 << S0) + 4 * upper + h);
+#pragma unroll
+        for (int p = 0; p < NP; p++) inv_bfly<M, G0>(v[p][2 * h], v[p][2 * h + 1], w.x, w.y);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        ulonglong2 w = ldtw(tw, (2 << S0) + 2 * upper + h);
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int r = 0; r < 2; r++) inv_bfly<M, G0 + 1>(v[p][4 * h + r], v[p][4 * h + r + 2], w.x, w.y);
+    }
+    {
+        ulonglong2 w = ldtw(tw, (1 << S0) + upper);
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) inv_bfly<M, G0 + 2>(v[p][r], v[p][r + 4], w.x, w.y);
+    }
+}
+
+// ---------------------------------------------------------------- shared-memory exchange
+// smem: NP consecutive 4096-entry buffers
+template <int NP, int S0>
+__device__ __forceinline__ void smem_store(u64 *smem, const u64 (&v)[NP][8], int t) {
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) smem[p * kN + swz(elem_index<S0>(t, r))] = v[p][r];
+}
+template <int NP, int S0>
+__device__ __forceinline__ void smem_load(const u64 *smem, u64 (&v)[NP][8], int t) {
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[p][r] = smem[p * kN + swz(elem_index<S0>(t, r))];
+}
+
+// ---------------------------------------------------------------- whole transforms on registers
+// Forward NTT of NP polynomials.
+//  in : v holds coefficients elem_index<0>(t, r) = r*512 + t   (natural order, any value < 2^62 small / < 4q large)
+//  out: v holds NTT values at positions elem_index<9>(t, r) = 8*t + r, reduced to [0, q) if kCanon
+//       (else small primes < 2^42, large primes < 4q)
+template <class M, int NP, bool kCanon>
+__device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t) {
+    fwd_pass<M, NP, 0>(v, tw, pass_upper<0>(t));
+    smem_store<NP, 0>(smem, v, t);
+    __syncthreads();
+    smem_load<NP, 3>(smem, v, t);
+    fwd_pass<M, NP, 3>(v, tw, pass_upper<3>(t));
+    smem_store<NP, 3>(smem, v, t);
+    __syncthreads();
+    smem_load<NP, 6>(smem, v, t);
+    fwd_pass<M, NP, 6>(v, tw, pass_upper<6>(t));
+    smem_store<NP, 6>(smem, v, t);
+    __syncthreads();
+    smem_load<NP, 9>(smem, v, t);
+    fwd_pass<M, NP, 9>(v, tw, pass_upper<9>(t));
+    if (kCanon) {
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+                if (M::kSmall)
+                    v[p][r] = reduce64<M>(v[p][r]);
+                else
+                    v[p][r] = csub<M>(csub<M>(v[p][r], M::two_q), M::q);
+            }
+    }
+    __syncthreads();  // smem may be reused by the caller
+}
+
+// Inverse NTT of NP polynomials.
+//  in : v holds NTT values at positions 8*t + r, each < 2q
+//  out: v holds coefficients r*512 + t, multiplied by (sc, scs) (Shoup pair, e.g. N^-1), in [0, q)
+template <class M, int NP>
+__device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t, u64 sc,
+                                            u64 scs) {
+    inv_pass<M, NP, 9, 0>(v, tw, pass_upper<9>(t));
+    smem_store<NP, 9>(smem, v, t);
+    __syncthreads();
+    smem_load<NP, 6>(smem, v, t);
+    inv_pass<M, NP, 6, 3>(v, tw, pass_upper<6>(t));
+    smem_store<NP, 6>(smem, v, t);
+    __syncthreads();
+    smem_load<NP, 3>(smem, v, t);
+    inv_pass<M, NP, 3, 6>(v, tw, pass_upper<3>(t));
+    smem_store<NP, 3>(smem, v, t);
+    __syncthreads();
+    smem_load<NP, 0>(smem, v, t);
+    inv_pass<M, NP, 0, 9>(v, tw, pass_upper<0>(t));
+#pragma unroll
+    for (int p = 0; p < NP; p++)
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[p][r] = shoup<M>(v[p][r], sc, scs);
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- global <-> register helpers
+// natural-order limb (4096 u64) -> registers in pass-0 layout (coalesced 8-byte accesses)
+__device__ __forceinline__ void load_natural(const u64 *__restrict__ g, u64 (&v)[8], int t) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = g[r * kThreads + t];
+}
+__device__ __forceinline__ void store_natural(u64 *__restrict__ g, const u64 (&v)[8], int t) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) g[r * kThreads + t] = v[r];
+}
+// bit-reversed-domain limb <-> registers in pass-9 layout (thread owns 8 consecutive values, 16-byte accesses)
+__device__ __forceinline__ void load_chunk8(const u64 *__restrict__ g, u64 (&v)[8], int t) {
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(g + 8 * t);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        ulonglong2 x = p[r];
+        v[2 * r] = x.x;
+        v[2 * r + 1] = x.y;
+    }
+}
+__device__ __forceinline__ void load_chunk8_ldg(const u64 *__restrict__ g, u64 (&v)[8], int t) {
+    const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(g + 8 * t);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        ulonglong2 x = __ldg(p + r);
+        v[2 * r] = x.x;
+        v[2 * r + 1] = x.y;
+    }
+}
+__device__ __forceinline__ void store_chunk8(u64 *__restrict__ g, const u64 (&v)[8], int t) {
+    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(g + 8 * t);
+#pragma unroll
+    for (int r = 0; r < 4; r++) p[r] = make_ulonglong2(v[2 * r], v[2 * r + 1]);
+}
+
+}  // namespace fheb

@@ -1,0 +1,49 @@
+// Compile-time parameter set of the testnet (reference: /root/reference/src/testnet.rs:8-14)
+// plus the BEHZ auxiliary base SEAL 4.0 derives from it (RNSTool::initialize; restated in
+// context.cpp, which re-derives these values at start-up and refuses to run on a mismatch).
+#pragma once
+#include <cstdint>
+
+namespace fheb {
+
+typedef uint64_t u64;
+typedef unsigned int u32;
+
+constexpr int kLogN = 12;
+constexpr int kN = 1 << kLogN;
+constexpr u64 kT = 4096;  // plain modulus
+
+// modulus indices
+enum : int { MQ0 = 0, MQ1 = 1, MP = 2, MB0 = 3, MB1 = 4, MSK = 5, kNumMod = 6 };
+
+constexpr u64 kModulus[kNumMod] = {
+    0xffffee001ull,          // q0  (36 bit)
+    0xffffc4001ull,          // q1  (36 bit)
+    0x1ffffe0001ull,         // P   (37 bit, special / key-switch prime)
+    0x1ffffffffffa4001ull,   // b0  (61 bit)  BEHZ base B
+    0x1ffffffffff92001ull,   // b1  (61 bit)
+    0x1ffffffffffde001ull,   // m_sk (61 bit)
+};
+constexpr u64 kGamma = 0x1ffffffffffce001ull;  // decrypt-only aux prime
+constexpr u64 kMTilde = 1ull << 32;
+
+// limb order of the extended BEHZ base q U Bsk used in all 5-limb device buffers
+constexpr int kExtLimb[5] = {MQ0, MQ1, MB0, MB1, MSK};
+
+// floor(2^128 / q) as (hi, lo), q < 2^63 and not a power of two
+struct U128c {
+    u64 hi, lo;
+};
+constexpr U128c barrett_ratio(u64 q) {
+    u64 rem = 1, hi = 0, lo = 0;
+    for (int i = 0; i < 128; i++) {
+        rem <<= 1;
+        u64 bit = rem >= q ? 1 : 0;
+        if (bit) rem -= q;
+        hi = (hi << 1) | (lo >> 63);
+        lo = (lo << 1) | bit;
+    }
+    return U128c{hi, lo};
+}
+
+}  // namespace fheb

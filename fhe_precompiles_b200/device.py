@@ -1,0 +1,125 @@
+"""Device-resident batched entry points (part 2 of include/fhe_precompiles_b200.h) on torch CUDA tensors.
+
+torch is plumbing only: it owns device memory and streams; every op is a call into the C-ABI library.
+Tensors are int64 views of uint64 words (torch has no general uint64 ops), C-contiguous:
+  ciphertext [n, 2, 2, 4096], size-3 ciphertext [n, 3, 2, 4096], relin key [2, 2, 3, 4096],
+  plaintext [n, 4096] int16 (coefficients < 4096).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence
+
+import torch
+
+from . import _lib
+
+N = 4096
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise RuntimeError("fhe_precompiles_b200: " + _lib.last_error())
+
+
+def _dev(t: torch.Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("fhe_precompiles_b200 has no CPU path: tensors must live on a CUDA device")
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream(dev: int) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def init(device: int = 0) -> None:
+    _check(_lib.lib().fhe_b200_init(device))
+
+
+def launch_count() -> int:
+    return int(_lib.lib().fhe_b200_launch_count())
+
+
+def _binary(fn, a: torch.Tensor, b: torch.Tensor, out_shape) -> torch.Tensor:
+    dev = _dev(a)
+    _dev(b)
+    n = a.shape[0]
+    out = torch.empty(out_shape, dtype=torch.int64, device=a.device)
+    _check(fn(dev, a.data_ptr(), b.data_ptr(), out.data_ptr(), n, _stream(dev)))
+    return out
+
+
+def add(a, b):
+    return _binary(_lib.lib().fhe_b200_add, a, b, a.shape)
+
+
+def sub(a, b):
+    return _binary(_lib.lib().fhe_b200_sub, a, b, a.shape)
+
+
+def negate(a):
+    dev = _dev(a)
+    out = torch.empty_like(a)
+    _check(_lib.lib().fhe_b200_negate(dev, a.data_ptr(), out.data_ptr(), a.shape[0], _stream(dev)))
+    return out
+
+
+def plain_addsub(ct, plain, mode: int):
+    dev = _dev(ct)
+    _dev(plain)
+    assert plain.dtype == torch.int16 and plain.shape == (ct.shape[0], N)
+    out = torch.empty_like(ct)
+    _check(_lib.lib().fhe_b200_plain_addsub(dev, ct.data_ptr(), plain.data_ptr(), out.data_ptr(), ct.shape[0], mode, _stream(dev)))
+    return out
+
+
+def multiply_plain(ct, plain):
+    dev = _dev(ct)
+    _dev(plain)
+    assert plain.dtype == torch.int16 and plain.shape == (ct.shape[0], N)
+    out = torch.empty_like(ct)
+    _check(_lib.lib().fhe_b200_multiply_plain(dev, ct.data_ptr(), plain.data_ptr(), out.data_ptr(), ct.shape[0], _stream(dev)))
+    return out
+
+
+def multiply(a, b):
+    return _binary(_lib.lib().fhe_b200_multiply, a, b, (a.shape[0], 3, 2, N))
+
+
+def relinearize(c3, rk):
+    return _binary(_lib.lib().fhe_b200_relinearize, c3, rk, (c3.shape[0], 2, 2, N))
+
+
+def mul_relin(a, b, rk, out=None):
+    dev = _dev(a)
+    _dev(b)
+    _dev(rk)
+    if out is None:
+        out = torch.empty_like(a)
+    _check(_lib.lib().fhe_b200_mul_relin(dev, a.data_ptr(), b.data_ptr(), rk.data_ptr(), out.data_ptr(), a.shape[0], _stream(dev)))
+    return out
+
+
+def ntt_(data: torch.Tensor, mods: Sequence[int], inverse: bool = False) -> torch.Tensor:
+    """In-place batched NTT over data[..., 4096]; limb i (flattened) uses modulus mods[i % len(mods)]."""
+    dev = _dev(data)
+    arr = (ctypes.c_int32 * len(mods))(*mods)
+    _check(_lib.lib().fhe_b200_ntt(dev, data.data_ptr(), data.numel() // N, arr, len(mods), int(inverse), _stream(dev)))
+    return data
+
+
+def behz_extend(a, b):
+    return _binary(_lib.lib().fhe_b200_behz_extend, a, b, (a.shape[0], 4, 5, N))
+
+
+def behz_tensor(a, b):
+    return _binary(_lib.lib().fhe_b200_behz_tensor, a, b, (a.shape[0], 3, 5, N))
+
+
+def behz_floor_sk(tens):
+    dev = _dev(tens)
+    out = torch.empty((tens.shape[0], 3, 2, N), dtype=torch.int64, device=tens.device)
+    _check(_lib.lib().fhe_b200_behz_floor_sk(dev, tens.data_ptr(), out.data_ptr(), tens.shape[0], _stream(dev)))
+    return out

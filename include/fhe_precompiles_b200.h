@@ -1,0 +1,162 @@
+/*
+ * fhe_precompiles_b200 -- C ABI of the B200-native BFV precompile engine.
+ *
+ * Part 1 is the drop-in boundary: exactly the symbols the reference's staticlib exports
+ * (/root/reference/src/c_fhe.rs:8-141, stamped by create_c_precompile_function! at c_fhe.rs:74-141,
+ * plus fhe_free c_fhe.rs:61-64 and fhe_error c_fhe.rs:66-71), with the same signature, ownership and
+ * error codes (/root/reference/src/lib.rs:14-27).  Input framing is pack.rs:119-266.
+ *
+ * Part 2 (fhe_b200_*) is the batch / device-resident extension the north star asks for; the single-call
+ * surface of part 1 is a batch of one over the same engine.  There is no CPU fallback anywhere: without a
+ * CUDA device every compute entry point fails (part 1: code 7, part 2: -1) and fhe_b200_last_error() says why.
+ */
+#ifndef FHE_PRECOMPILES_B200_H
+#define FHE_PRECOMPILES_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Part 1: reference surface ------------------------------------------------------------------
+ * int32_t c_fhe_X(const uint8_t* bytes, size_t bytes_length, uint8_t** output, int64_t* output_length)
+ *   returns 0 and a malloc'd *output (release with fhe_free) of *output_length bytes, or an error code
+ *   1..7 with *output = NULL, *output_length = 0.                                  (c_fhe.rs:23-56)      */
+#define FHE_PRECOMPILE(name) \
+    int32_t c_fhe_##name(const uint8_t *bytes, size_t bytes_length, uint8_t **output, int64_t *output_length)
+
+/* u256: replaces c_fhe.rs:74-84 (FheApp methods fhe.rs:161-576) */
+FHE_PRECOMPILE(add_cipheru256_cipheru256);
+FHE_PRECOMPILE(add_cipheru256_u256);
+FHE_PRECOMPILE(add_u256_cipheru256);
+FHE_PRECOMPILE(sub_cipheru256_cipheru256);
+FHE_PRECOMPILE(sub_cipheru256_u256);
+FHE_PRECOMPILE(sub_u256_cipheru256);
+FHE_PRECOMPILE(mul_cipheru256_cipheru256);
+FHE_PRECOMPILE(mul_cipheru256_u256);
+FHE_PRECOMPILE(mul_u256_cipheru256);
+
+/* u64: replaces c_fhe.rs:87-97 (FheApp methods fhe.rs:161-576) */
+FHE_PRECOMPILE(add_cipheru64_cipheru64);
+FHE_PRECOMPILE(add_cipheru64_u64);
+FHE_PRECOMPILE(add_u64_cipheru64);
+FHE_PRECOMPILE(sub_cipheru64_cipheru64);
+FHE_PRECOMPILE(sub_cipheru64_u64);
+FHE_PRECOMPILE(sub_u64_cipheru64);
+FHE_PRECOMPILE(mul_cipheru64_cipheru64);
+FHE_PRECOMPILE(mul_cipheru64_u64);
+FHE_PRECOMPILE(mul_u64_cipheru64);
+
+/* i64: replaces c_fhe.rs:100-110 (FheApp methods fhe.rs:161-576) */
+FHE_PRECOMPILE(add_cipheri64_cipheri64);
+FHE_PRECOMPILE(add_cipheri64_i64);
+FHE_PRECOMPILE(add_i64_cipheri64);
+FHE_PRECOMPILE(sub_cipheri64_cipheri64);
+FHE_PRECOMPILE(sub_cipheri64_i64);
+FHE_PRECOMPILE(sub_i64_cipheri64);
+FHE_PRECOMPILE(mul_cipheri64_cipheri64);
+FHE_PRECOMPILE(mul_cipheri64_i64);
+FHE_PRECOMPILE(mul_i64_cipheri64);
+
+/* frac64: replaces c_fhe.rs:113-123 (FheApp methods fhe.rs:161-576) */
+FHE_PRECOMPILE(add_cipherfrac64_cipherfrac64);
+FHE_PRECOMPILE(add_cipherfrac64_frac64);
+FHE_PRECOMPILE(add_frac64_cipherfrac64);
+FHE_PRECOMPILE(sub_cipherfrac64_cipherfrac64);
+FHE_PRECOMPILE(sub_cipherfrac64_frac64);
+FHE_PRECOMPILE(sub_frac64_cipherfrac64);
+FHE_PRECOMPILE(mul_cipherfrac64_cipherfrac64);
+FHE_PRECOMPILE(mul_cipherfrac64_frac64);
+FHE_PRECOMPILE(mul_frac64_cipherfrac64);
+
+/* threshold-network simulation API: replaces c_fhe.rs:126-141 (fhe.rs:594-779) */
+FHE_PRECOMPILE(encrypt_u256);
+FHE_PRECOMPILE(encrypt_u64);
+FHE_PRECOMPILE(encrypt_i64);
+FHE_PRECOMPILE(encrypt_frac64);
+FHE_PRECOMPILE(reencrypt_u256);
+FHE_PRECOMPILE(reencrypt_u64);
+FHE_PRECOMPILE(reencrypt_i64);
+FHE_PRECOMPILE(reencrypt_frac64);
+FHE_PRECOMPILE(decrypt_u256);
+FHE_PRECOMPILE(decrypt_u64);
+FHE_PRECOMPILE(decrypt_i64);
+FHE_PRECOMPILE(decrypt_frac64);
+FHE_PRECOMPILE(public_key_bytes);
+
+/* replaces c_fhe.rs:61-64: frees a buffer returned through `output` (libc free) */
+void fhe_free(const uint8_t *bytes);
+/* replaces c_fhe.rs:66-71: NUL-terminated message for an error code (strings of lib.rs:33-44).  The
+ * reference leaks a fresh CString per call; this returns a pointer to static storage -- never free it. */
+const char *fhe_error(int32_t error_code);
+
+/* ---- Part 2: batch and device-resident extension ------------------------------------------------ */
+
+/* Text of the last failure on the calling thread ("" if none). Valid until the thread's next call. */
+const char *fhe_b200_last_error(void);
+/* Number of usable CUDA devices (0 if none). */
+int32_t fhe_b200_device_count(void);
+/* Builds the per-device context (twiddles in HBM, constants, kernel attributes). 0 / -1. */
+int32_t fhe_b200_init(int32_t device);
+/* Kernels launched by this process so far (for benchmark bookkeeping). */
+uint64_t fhe_b200_launch_count(void);
+
+/* One entry of a through-the-byte-surface batch. `op` indexes fhe_b200_op_name(). */
+typedef struct fhe_b200_call {
+    int32_t op;            /* in : precompile index, see fhe_b200_op_index() */
+    int32_t status;        /* out: 0 or lib.rs error code */
+    const uint8_t *bytes;  /* in : packed input (pack.rs framing) */
+    size_t bytes_length;   /* in */
+    uint8_t *output;       /* out: malloc'd result, release with fhe_free */
+    int64_t output_length; /* out */
+} fhe_b200_call;
+/* Index of a precompile by its reference name without the c_fhe_ prefix (e.g. "mul_cipheri64_cipheri64"); -1 if unknown. */
+int32_t fhe_b200_op_index(const char *name);
+const char *fhe_b200_op_name(int32_t index);
+/* Runs n independent precompile calls, codec on `host_threads` host threads (0 = all cores), arithmetic
+ * sharded over every visible GPU. Returns the number of calls whose status != 0. */
+int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads);
+
+/* Device-resident entry points. All pointers are device memory on `device`; `stream` is a cudaStream_t
+ * (NULL = default stream); work is enqueued, not synchronised. Return 0 / -1.
+ * Layouts (uint64 words, limb-major): ciphertext [2 polys][2 limbs q0,q1][4096]; size-3 ciphertext
+ * [3][2][4096]; relin key [2 digits][2 polys][3 limbs q0,q1,P][4096] (NTT form as stored in the key file);
+ * plaintext [4096] uint16 coefficients < 4096. n = number of independent ops (batch dimension outermost). */
+int32_t fhe_b200_add(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, void *stream);
+int32_t fhe_b200_sub(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *out, size_t n, void *stream);
+int32_t fhe_b200_negate(int32_t device, const uint64_t *a, uint64_t *out, size_t n, void *stream);
+/* mode bit0: subtract the plaintext instead of adding; bit1: negate the result (pt - ct) */
+int32_t fhe_b200_plain_addsub(int32_t device, const uint64_t *ct, const uint16_t *plain, uint64_t *out, size_t n,
+                              int32_t mode, void *stream);
+int32_t fhe_b200_multiply_plain(int32_t device, const uint64_t *ct, const uint16_t *plain, uint64_t *out, size_t n,
+                                void *stream);
+/* BFV multiply (BEHZ) without / with relinearisation */
+int32_t fhe_b200_multiply(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, void *stream);
+int32_t fhe_b200_relinearize(int32_t device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, void *stream);
+int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
+                           size_t n, void *stream);
+/* Batched negacyclic NTT in place over n_limbs limbs of 4096 words; limb i uses modulus mods[i % n_mods]
+ * (0 q0, 1 q1, 2 P, 3 b0, 4 b1, 5 m_sk). inverse != 0: bit-reversed -> natural, scaled by N^-1. */
+int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,
+                     void *stream);
+/* Stage taps used by the parity tests: BEHZ base extension [n][4][5][4096], tensor [n][3][5][4096] (x t),
+ * floor + Shenoy-Kumaresan [n][3][2][4096]. */
+int32_t fhe_b200_behz_extend(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *ext, size_t n, void *stream);
+int32_t fhe_b200_behz_tensor(int32_t device, const uint64_t *a, const uint64_t *b, uint64_t *tens, size_t n, void *stream);
+int32_t fhe_b200_behz_floor_sk(int32_t device, const uint64_t *tens, uint64_t *out3, size_t n, void *stream);
+
+/* Host-side format helpers (no GPU needed): parse a sunscreen PublicKey and write its relinearisation key
+ * (2*2*3*4096 words) and/or public key (2*3*4096 words); either pointer may be NULL. lib.rs error code. */
+int32_t fhe_b200_parse_public_key(const uint8_t *bytes, size_t len, uint64_t *pk_words, uint64_t *rk_words);
+int32_t fhe_b200_parse_private_key(const uint8_t *bytes, size_t len, uint64_t *sk_words);
+/* sunscreen::Ciphertext bytes <-> 2*2*4096 coefficient words (data_type kept in a caller buffer) */
+int32_t fhe_b200_parse_ciphertext(const uint8_t *bytes, size_t len, uint64_t *words, char *data_type, size_t data_type_cap);
+int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, uint8_t **output, int64_t *output_length);
+/* parms_id (4 words) of the key level (which = 0) or the data level (which = 1) */
+void fhe_b200_parms_id(int32_t which, uint64_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

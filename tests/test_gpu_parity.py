@@ -1,0 +1,212 @@
+"""GPU parity: every kernel behind the C ABI, bit-compared with the CPU oracle on the same inputs.
+Bar: bit-exact (integer work).  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from helpers import KINDS, MODULI, N, REF_A, REF_B, REF_EXPECT, decrypt_value, encrypt_value, oracle_binary, plain_u16, precompile_name, random_ct, value_of
+from oracle import bfv
+from oracle import formats as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+
+    from fhe_precompiles_b200 import device
+
+    assert torch.cuda.is_available(), "no CUDA device: the product has no CPU path"
+    device.init(0)
+    return device
+
+
+def to_dev(a: np.ndarray):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def to_np(t) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint64)
+
+
+def edge_ct(n_rand: int, seed: int) -> np.ndarray:
+    """random residues plus the edge polynomials: all zero, all q-1, single max coefficient"""
+    rng = np.random.default_rng(seed)
+    cts = random_ct(rng, n_rand + 3)
+    cts[n_rand] = 0
+    for l in range(2):
+        cts[n_rand + 1, :, l, :] = MODULI[l] - 1
+    cts[n_rand + 2] = 0
+    cts[n_rand + 2, 0, 0, 0] = MODULI[0] - 1
+    cts[n_rand + 2, 1, 1, N - 1] = MODULI[1] - 1
+    return cts
+
+
+@pytest.mark.parametrize("mod", range(6))
+def test_ntt_forward_inverse(dev, mod):
+    rng = np.random.default_rng(100 + mod)
+    x = rng.integers(0, MODULI[mod], size=(5, N), dtype=np.uint64)
+    x[3] = 0
+    x[4] = MODULI[mod] - 1
+    want = bfv.ntt_fwd(x, mod)
+    d = to_dev(x)
+    dev.ntt_(d, [mod], inverse=False)
+    got = to_np(d)
+    assert np.array_equal(got, want)
+    dev.ntt_(d, [mod], inverse=True)
+    assert np.array_equal(to_np(d), x)
+    # inverse on arbitrary canonical input too
+    y = to_dev(x)
+    dev.ntt_(y, [mod], inverse=True)
+    assert np.array_equal(to_np(y), bfv.ntt_inv(x, mod))
+
+
+def test_ntt_mixed_limbs(dev):
+    rng = np.random.default_rng(7)
+    x = np.stack([rng.integers(0, MODULI[m], size=(4, N), dtype=np.uint64) for m in (0, 1, 2)], axis=1)  # [4][3][N]
+    d = to_dev(x)
+    dev.ntt_(d, [0, 1, 2])
+    got = to_np(d)
+    for m in range(3):
+        assert np.array_equal(got[:, m], bfv.ntt_fwd(x[:, m], m))
+
+
+def test_add_sub_negate(dev):
+    a, b = edge_ct(5, 1), edge_ct(5, 2)[::-1].copy()
+    da, db = to_dev(a), to_dev(b)
+    assert np.array_equal(to_np(dev.add(da, db)), np.stack([bfv.add(x, y) for x, y in zip(a, b)]))
+    assert np.array_equal(to_np(dev.sub(da, db)), np.stack([bfv.sub(x, y) for x, y in zip(a, b)]))
+    assert np.array_equal(to_np(dev.negate(da)), np.stack([bfv.negate(x) for x in a]))
+
+
+def test_plain_ops(dev):
+    import torch
+
+    cts = edge_ct(5, 3)
+    rng = np.random.default_rng(4)
+    plains = rng.integers(0, 4096, size=(len(cts), N), dtype=np.uint16)
+    plains[0] = 0
+    plains[1] = 4095
+    plains[2] = 0
+    plains[2, 5] = 2048  # exactly the upper-half threshold
+    dct = to_dev(cts)
+    dpl = torch.from_numpy(plains.view(np.int16)).cuda()
+    for mode, fn in ((0, bfv.add_plain), (1, bfv.sub_plain), (3, lambda c, p: bfv.negate(bfv.sub_plain(c, p)))):
+        got = to_np(dev.plain_addsub(dct, dpl, mode))
+        want = np.stack([fn(c, p.astype(np.uint64)) for c, p in zip(cts, plains)])
+        assert np.array_equal(got, want), f"plain_addsub mode {mode}"
+    got = to_np(dev.multiply_plain(dct, dpl))
+    want = np.stack([bfv.multiply_plain(c, p.astype(np.uint64)) for c, p in zip(cts, plains)])
+    assert np.array_equal(got, want)
+
+
+def test_behz_stages(dev):
+    a, b = edge_ct(3, 5), edge_ct(3, 6)[::-1].copy()
+    da, db = to_dev(a), to_dev(b)
+    ext = to_np(dev.behz_extend(da, db))
+    want_ext = np.stack([bfv.behz_extend(x, y) for x, y in zip(a, b)])
+    assert np.array_equal(ext, want_ext), "fastbconv_m_tilde + sm_mrq"
+    tens = to_np(dev.behz_tensor(da, db))
+    want_tens = np.stack([bfv.behz_tensor(e) for e in want_ext])
+    assert np.array_equal(tens, want_tens), "NTT + tensor + INTT * t"
+    c3 = to_np(dev.behz_floor_sk(to_dev(want_tens)))
+    want_c3 = np.stack([bfv.behz_floor_sk(t) for t in want_tens])
+    assert np.array_equal(c3, want_c3), "fast_floor + fastbconv_sk"
+    assert np.array_equal(to_np(dev.multiply(da, db)), want_c3), "bfv_multiply"
+
+
+def test_relinearize_and_mul_relin(dev, keys):
+    a, b = edge_ct(3, 8), edge_ct(3, 9)[::-1].copy()
+    da, db, drk = to_dev(a), to_dev(b), to_dev(keys.rk)
+    c3 = np.stack([bfv.multiply(x, y) for x, y in zip(a, b)])
+    want = np.stack([bfv.relinearize(c, keys.rk) for c in c3])
+    assert np.array_equal(to_np(dev.relinearize(to_dev(c3), drk)), want), "switch_key_inplace"
+    assert np.array_equal(to_np(dev.mul_relin(da, db, drk)), want), "multiply + relinearize"
+
+
+def test_mul_relin_real_encryptions_chunked(dev, keys):
+    """batch larger than the engine's chunk (148): every op bit-exact vs oracle on a sample, all decrypt."""
+    rng = np.random.default_rng(2)
+    n = 300
+    vals_a = rng.integers(-(2**15), 2**15, size=n)
+    vals_b = rng.integers(-(2**15), 2**15, size=n)
+    a = np.stack([encrypt_value(keys, "i64", int(v), 1000 + i) for i, v in enumerate(vals_a)])
+    b = np.stack([encrypt_value(keys, "i64", int(v), 5000 + i) for i, v in enumerate(vals_b)])
+    out = to_np(dev.mul_relin(to_dev(a), to_dev(b), to_dev(keys.rk)))
+    for i in list(range(0, n, 37)) + [147, 148, 149, n - 1]:
+        assert np.array_equal(out[i], bfv.mul_relin(a[i], b[i], keys.rk)), f"op {i}"
+    for i in range(0, n, 5):
+        assert decrypt_value(keys, "i64", out[i]) == int(vals_a[i]) * int(vals_b[i])
+
+
+# ---------------------------------------------------------------- the byte surface (C ABI part 1)
+SHAPES = ("ctct", "ctpt", "ptct")
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("op", ("add", "sub", "mul"))
+@pytest.mark.parametrize("shape", SHAPES)
+def test_precompile_matches_reference_tests(keys, kind, op, shape):
+    """fhe.rs:1070-2076 `precompile_*_works`: 16 op 4 through pack_binary_operation -> precompile ->
+    deserialize -> decrypt; plus byte equality with the oracle's result serialised by the format oracle."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    a_val, b_val = value_of(kind, REF_A), value_of(kind, REF_B)
+    ct_a = encrypt_value(keys, kind, a_val, 11)
+    ct_b = encrypt_value(keys, kind, b_val, 12)
+    ser = lambda ct: F.make_ciphertext(kind, ct).to_bytes()
+    if shape == "ctct":
+        args, oargs = (ser(ct_a), ser(ct_b)), (ct_a, ct_b)
+    elif shape == "ctpt":
+        args, oargs = (ser(ct_a), pack.SERIALIZE[kind](b_val)), (ct_a, b_val)
+    else:
+        args, oargs = (pack.SERIALIZE[kind](a_val), ser(ct_b)), (a_val, ct_b)
+    name = precompile_name(op, shape, kind)
+    out = getattr(FHE, name)(pack.pack_binary_operation(keys.pub_bytes, *args))
+    want = oracle_binary(op, shape, kind, *oargs, keys.rk)
+    assert out == F.make_ciphertext(kind, want).to_bytes(), "packed ciphertext bytes differ from the oracle's"
+    got_ct = F.Ciphertext.from_bytes(out)
+    assert decrypt_value(keys, kind, got_ct.polys()) == value_of(kind, REF_EXPECT[op])
+
+
+def test_precompile_errors(keys):
+    from fhe_precompiles_b200 import FHE, FheError, pack
+
+    ct = F.make_ciphertext("i64", encrypt_value(keys, "i64", 3, 1)).to_bytes()
+    good = pack.pack_binary_operation(keys.pub_bytes, ct, ct)
+
+    def code(fn, data):
+        with pytest.raises(FheError) as e:
+            fn(data)
+        return e.value.code
+
+    assert code(FHE.add_cipheri64_cipheri64, b"\x00\x01") == 1  # pack.rs:244-246
+    assert code(FHE.add_cipheri64_cipheri64, good[:8] + b"junk" + good[12:]) == 3  # key fails to deserialize
+    assert code(FHE.add_cipheri64_i64, pack.pack_binary_operation(keys.pub_bytes, ct, b"\x00" * 7)) == 3  # pack.rs:86
+    assert code(FHE.add_cipheru64_cipheru64, good) == 7  # argument type mismatch -> sunscreen runtime error
+    bad_off = bytearray(good)
+    bad_off[0:4] = (len(good) + 5).to_bytes(4, "big")
+    assert code(FHE.add_cipheri64_cipheri64, bytes(bad_off)) == 1  # reference panics; we bounds-check
+    # transparent result must be accepted (fhe.rs:2124-2140): ct - ct = all-zero ciphertext
+    out = FHE.sub_cipheri64_cipheri64(good)
+    assert not F.Ciphertext.from_bytes(out).polys().any()
+
+
+def test_batch_surface(keys):
+    from fhe_precompiles_b200 import FHE, pack
+
+    calls, wants = [], []
+    for i in range(12):
+        kind = KINDS[i % 4]
+        a, b = encrypt_value(keys, kind, value_of(kind, 3 + i), 50 + i), encrypt_value(keys, kind, value_of(kind, 2), 90 + i)
+        sa, sb = (F.make_ciphertext(kind, x).to_bytes() for x in (a, b))
+        op = ("add", "sub", "mul")[i % 3]
+        calls.append((precompile_name(op, "ctct", kind), pack.pack_binary_operation(keys.pub_bytes, sa, sb)))
+        wants.append(F.make_ciphertext(kind, oracle_binary(op, "ctct", kind, a, b, keys.rk)).to_bytes())
+    calls.append(("add_cipheri64_cipheri64", b"\x00"))
+    res = FHE.run_batch(calls, host_threads=4)
+    assert [r[0] for r in res[:-1]] == [0] * 12 and res[-1][0] == 1
+    for (st, out), want in zip(res[:-1], wants):
+        assert out == want
