@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ct x ct fhe_multiply + relinearisation (BASELINE.json `metric`).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine (one process per GPU)
+  python bench.py --impl reference --gpus N --steps K ...   # the CPU restatement of the SEAL path (oracle/)
+
+A "step" is one pass of the hot path over one batch of 4,096 synthetic ciphertext pairs per GPU
+(BASELINE.json configs[2]).  `value` = whole-job ops/s with inputs resident in HBM; `e2e` = the same metric
+through the C-ABI host-buffer entry point (fhe_b200_mul_relin_host: pinned host limb arrays in, H2D + kernels
++ D2H inside the timed region).  One JSON line on stdout from rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N = 4096
+Q = (0xFFFFEE001, 0xFFFFC4001)
+CT_BYTES = 2 * 2 * N * 8  # 131,072
+ALGO_BYTES_PER_OP = 3 * CT_BYTES  # read a, read b, write result = 393,216 B
+# 47 limb-NTTs x 24,576 butterflies + ~0.79 M pointwise modmuls per op
+MODMUL_PER_OP = 47 * 24576 + 790528
+# a 64-bit Shoup/Barrett modmul needs >= 10 32x32-bit multiply-adds (4 for the high product, 3 + 3 for two low ones)
+MAD_PER_MODMUL = 10
+METRIC = "ct_ct_fhe_multiply_relin_ops_per_sec"
+WORKLOAD = "batch of 4096 ct*ct fhe_multiply+relinearize per GPU, testnet BFV params (N=4096, q=72b, t=4096)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int) -> None:
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self) -> None:
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=1.0)
+        s = sorted(self.samples)
+        return {
+            "sm_mhz": s[len(s) // 2] if s else None,
+            "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons),
+            "samples": len(s),
+        }
+
+
+def synth_ciphertexts(torch, n: int, seed: int, device) -> "torch.Tensor":
+    """[n,2,2,4096] int64: uniform residues mod (q0, q1) -- synthetic data-level ciphertexts."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    out = torch.empty((n, 2, 2, N), dtype=torch.int64, device=device)
+    for l in range(2):
+        out[:, :, l, :] = torch.randint(0, Q[l], (n, 2, N), generator=g, device=device, dtype=torch.int64)
+    return out
+
+
+def cpu_baseline(a_np, b_np, rk_np, threads: int):
+    """Times the oracle (CPU restatement of the SEAL 4.0 path) on a bounded sample. Returns (ops/s, outputs)."""
+    from oracle import bfv
+
+    out, secs = bfv.batch_mul_relin(a_np, b_np, rk_np, threads)
+    return a_np.shape[0] / secs, out, secs
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+
+    from oracle import bfv
+    from oracle import formats as F
+
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(2)
+    sample = max(cores * 2, 32)
+    a = np.empty((sample, 2, 2, N), dtype=np.uint64)
+    b = np.empty_like(a)
+    for l in range(2):
+        a[:, :, l, :] = rng.integers(0, Q[l], size=(sample, 2, N), dtype=np.uint64)
+        b[:, :, l, :] = rng.integers(0, Q[l], size=(sample, 2, N), dtype=np.uint64)
+    pk = F.PublicKey.from_bytes(open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read())
+    rk = bfv.rk_array(pk.relin())
+    for _ in range(args.warmup):
+        bfv.batch_mul_relin(a, b, rk, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        bfv.batch_mul_relin(a, b, rk, cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference",
+        "metric": METRIC,
+        "value": value,
+        "unit": "ops/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic uniform residues",
+        "config": {"workload": WORKLOAD, "sample_ops_per_step": sample},
+        "cpu_baseline": {
+            "value": value,
+            "unit": "ops/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{sample} ct*ct multiply+relin per step on {cores} host threads; the reference's SEAL-backed "
+            "path cannot be built here (no Rust toolchain, SEAL un-vendored), so this is the C restatement in oracle/",
+        },
+        "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="ct x ct ops per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="ops in the CPU-baseline sample (0 = ~20 s of CPU work)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # plumbing only: barrier + max-over-ranks of the timing
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from fhe_precompiles_b200 import device as fdev
+
+    fdev.init(local_rank)
+    n = args.batch
+    a = synth_ciphertexts(torch, n, 2 + 2 * rank, dev)
+    b = synth_ciphertexts(torch, n, 3 + 2 * rank, dev)
+    out = torch.empty_like(a)
+    net_pub = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read()
+    _, rk_host = fdev.parse_public_key(net_pub)
+    rk = rk_host.to(dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- device-resident timed region
+    for _ in range(args.warmup):
+        fdev.mul_relin(a, b, rk, out=out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    fdev.set_kernel_timing(True)
+    launches0 = fdev.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        fdev.mul_relin(a, b, rk, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = fdev.launch_count() - launches0
+    kt = fdev.kernel_timing_report(local_rank)
+    fdev.set_kernel_timing(False)
+    clocks = sampler.stop()
+    barrier()
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max = float(t_ms.item())
+    value = world * n * args.steps / (ms_max * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        a_h = a.cpu().pin_memory()
+        b_h = b.cpu().pin_memory()
+        out_h = torch.empty_like(a_h).pin_memory()
+        for _ in range(2):
+            fdev.mul_relin_host(a_h, b_h, rk_host, out_h, device=local_rank)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fdev.mul_relin_host(a_h, b_h, rk_host, out_h, device=local_rank)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        dt_max = float(t_e.item())
+        same = bool(torch.equal(out_h, out.cpu()))
+        e2e = {
+            "value": world * n * args.steps / dt_max,
+            "unit": "ops/s",
+            "h2d_bytes_per_step": 2 * n * CT_BYTES + rk_host.numel() * 8,
+            "d2h_bytes_per_step": n * CT_BYTES,
+            "api": "fhe_b200_mul_relin_host (C ABI, pinned host limb arrays)",
+            "matches_device_resident_result": same,
+        }
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (live CUDA-event durations from the timed region)
+    peak_gbs, peak_src = measured_peaks()
+    dom = max(kt, key=lambda k: kt[k][0])
+    dom_ms, dom_launches = kt[dom]
+    total_kernel_ms = sum(v[0] for v in kt.values())
+    ops_per_launch = n * args.steps / max(dom_launches, 1)
+    avg_launch_ms = dom_ms / max(dom_launches, 1)
+    achieved = ops_per_launch * ALGO_BYTES_PER_OP / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm",
+        "kernel": dom,
+        "achieved": achieved,
+        "peak": peak_gbs,
+        "unit": "GB/s",
+        "frac": achieved / peak_gbs,
+        "traffic": None,
+        "peak_source": peak_src,
+        "avg_launch_ms": avg_launch_ms,
+        "ops_per_launch": ops_per_launch,
+        "kernel_share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
+        "kernel_ms": {k: v[0] for k, v in kt.items()},
+        "note": "the fused multiply kernels are integer-pipe bound (SURVEY 8d); see int_pipe",
+    }
+    try:
+        peak_mad = fdev.int_peak(local_rank, wide=True)
+        ach_mad = (n * args.steps / (ms * 1e-3)) * MODMUL_PER_OP * MAD_PER_MODMUL / 1e12
+        int_pipe = {
+            "achieved": ach_mad,
+            "peak": peak_mad,
+            "unit": "T mad.wide.u32/s",
+            "frac": ach_mad / peak_mad,
+            "model": f"{MODMUL_PER_OP} 64-bit modmul/op x {MAD_PER_MODMUL} 32-bit mads; peak = measured microbenchmark",
+        }
+    except Exception as e:  # pragma: no cover
+        int_pipe = {"error": str(e)}
+
+    line = {
+        "metric": METRIC,
+        "value": value,
+        "unit": "ops/s",
+        "n_gpus": world,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u64",
+        "data": "synthetic uniform residues mod (q0,q1), seed 2",
+        "config": {
+            "workload": WORKLOAD,
+            "ops_per_gpu_per_step": n,
+            "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
+            "sharding": f"{world} rank(s), independent batches, no collective",
+            "chunk_ops": int(os.environ.get("FHE_B200_CHUNK_OPS", "148")),
+        },
+        "roofline": roofline,
+        "int_pipe": int_pipe,
+        "clocks": clocks,
+        "gpu_launches": int(launches),
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+
+    # ---------------- CPU baseline on the box's host cores (N=1 only), also the parity checker for the sample
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = args.cpu_sample or min(n, max(64, int(20.0 / 0.010)))  # ~20 s of single-core work at ~10 ms/op
+        a_np = a[:sample].cpu().numpy().view(np.uint64)
+        b_np = b[:sample].cpu().numpy().view(np.uint64)
+        rk_np = rk_host.numpy().view(np.uint64)
+        cpu_ops, cpu_out, secs = cpu_baseline(a_np, b_np, rk_np, cores)
+        line["cpu_baseline"] = {
+            "value": cpu_ops,
+            "unit": "ops/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"first {sample} ops of the same batch, oracle/ C restatement of the SEAL 4.0 path, {cores} threads, {secs:.2f} s",
+            "bit_exact_vs_gpu": bool(np.array_equal(cpu_out, out[:sample].cpu().numpy().view(np.uint64))),
+        }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -72,6 +72,18 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_plain_addsub.argtypes = [i32, vp, vp, vp, sz, i32, vp]
     L.fhe_b200_multiply_plain.argtypes = [i32, vp, vp, vp, sz, vp]
     L.fhe_b200_mul_relin.argtypes = [i32, vp, vp, vp, vp, sz, vp]
+    L.fhe_b200_mul_relin_host.argtypes = [i32, vp, vp, vp, vp, sz]
+    L.fhe_b200_mul_relin_host.restype = i32
+    L.fhe_b200_int_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
+    L.fhe_b200_int_peak.restype = i32
+    L.fhe_b200_bfly_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
+    L.fhe_b200_bfly_peak.restype = i32
+    L.fhe_b200_set_fused.argtypes = [i32]
+    L.fhe_b200_set_fused.restype = None
+    L.fhe_b200_set_kernel_timing.argtypes = [i32]
+    L.fhe_b200_set_kernel_timing.restype = None
+    L.fhe_b200_kernel_timing_report.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    L.fhe_b200_kernel_timing_report.restype = i32
     L.fhe_b200_ntt.argtypes = [i32, vp, sz, ctypes.POINTER(i32), i32, i32, vp]
     L.fhe_b200_behz_extend.argtypes = [i32, vp, vp, vp, sz, vp]
     L.fhe_b200_behz_floor_sk.argtypes = [i32, vp, vp, sz, vp]

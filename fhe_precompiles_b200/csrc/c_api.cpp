@@ -239,6 +239,33 @@ int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b,
                            size_t n, void *stream) {
     DEV_GUARD(Engine::get().mul_relin(device, a, b, rk, out, n, (cudaStream_t)stream));
 }
+int32_t fhe_b200_int_peak(int32_t device, int32_t wide, double *tera_mads_per_s) {
+    DEV_GUARD(device_context(device); cuda_throw(measure_int_peak(wide, tera_mads_per_s), "int_peak"));
+}
+int32_t fhe_b200_bfly_peak(int32_t device, int32_t mod, double *giga_bfly_per_s) {
+    DEV_GUARD(device_context(device); cuda_throw(measure_bfly_peak(mod, giga_bfly_per_s), "bfly_peak"));
+}
+void fhe_b200_set_fused(int32_t on) {
+    try {
+        Engine::get().set_fused(on != 0);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+    }
+}
+void fhe_b200_set_kernel_timing(int32_t on) {
+    try {
+        Engine::get().set_kernel_timing(on != 0);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+    }
+}
+int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[8], uint64_t launches[8]) {
+    DEV_GUARD(Engine::get().kernel_timing_report(device, ms, launches));
+}
+int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
+                                size_t n) {
+    DEV_GUARD(Engine::get().mul_relin_host(device, a, b, rk, out, n));
+}
 int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,
                      void *stream) {
     if (!mods || n_mods < 1 || n_mods > kNumMod) {

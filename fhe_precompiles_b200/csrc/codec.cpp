@@ -208,6 +208,22 @@ void seal_deflate(const uint8_t *payload, size_t len, uint8_t compr, std::vector
     write_seal_header(out->data(), compr, out->size());
 }
 
+// Params that differ from the testnet set: SEAL-valid ones deserialize in the reference and fail later in
+// Runtime::run (code 7); garbage fails inside deserialize (code 3).  `p` points at N, k, then k primes, t.
+int32_t foreign_params_code(const uint8_t *p, uint64_t k) {
+    uint64_t n, t;
+    memcpy(&n, p, 8);
+    if (n < 1024 || n > 32768 || (n & (n - 1)) || k < 1 || k > 16) return kErrInvalidEncoding;
+    for (uint64_t i = 0; i < k; i++) {
+        uint64_t q;
+        memcpy(&q, p + 16 + 8 * i, 8);
+        if (q < 2 || (q >> 60) || q % (2 * n) != 1 || !is_prime_u64(q)) return kErrInvalidEncoding;
+    }
+    memcpy(&t, p + 16 + 8 * k, 8);
+    if (t < 2 || (t >> 60)) return kErrInvalidEncoding;
+    return kErrSunscreen;
+}
+
 // sunscreen Params (bincode): N, k, q_i.., t, scheme u32, security u32.  Must equal the testnet set.
 bool params_are_testnet(const uint8_t *p) {
     uint64_t w[6];
@@ -285,13 +301,12 @@ int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words) {
     if (!params) return kErrInvalidEncoding;
     uint64_t k;
     memcpy(&k, params + 8, 8);
-    if (k != 3) return kErrSunscreen;  // not the testnet parameter set
-    if (!r.take(kParamsBytes - 16)) return kErrInvalidEncoding;
-    memcpy(view->params, params, kParamsBytes);
+    if (k > 64 || !r.take((size_t)k * 8 + 16)) return kErrInvalidEncoding;
     uint64_t blen = r.u64v();
     const uint8_t *blob = r.take((size_t)blen);
     if (!blob || !r.done()) return kErrInvalidEncoding;
-    if (!params_are_testnet(view->params)) return kErrSunscreen;
+    if (k != 3 || !params_are_testnet(params)) return foreign_params_code(params, k);
+    memcpy(view->params, params, kParamsBytes);
 
     thread_local std::vector<uint8_t> payload;
     int32_t rc = seal_inflate(blob, (size_t)blen, 0, &payload, &view->compr_mode);
@@ -396,7 +411,7 @@ int32_t decode_public_key(Span in, uint64_t *pk_words, uint64_t *rk_words, bool 
     {
         uint64_t k;
         memcpy(&k, params + 8, 8);
-        if (k != 3 || !params_are_testnet(params)) return kErrSunscreen;
+        if (k != 3 || !params_are_testnet(params)) return foreign_params_code(params, k);
     }
     std::vector<uint8_t> payload;
     int32_t rc = seal_inflate(blob, blen, 0, &payload, nullptr);
@@ -419,7 +434,7 @@ int32_t decode_public_key(Span in, uint64_t *pk_words, uint64_t *rk_words, bool 
         if (!read_with_context(r, &params, &blob, &blen)) return kErrInvalidEncoding;
         uint64_t k;
         memcpy(&k, params + 8, 8);
-        if (k != 3 || !params_are_testnet(params)) return kErrSunscreen;
+        if (k != 3 || !params_are_testnet(params)) return foreign_params_code(params, k);
         rc = seal_inflate(blob, blen, 0, &payload, nullptr);
         if (rc) return rc;
         // KSwitchKeys payload: parms_id, dim1, then per row: dim2, { SEAL header(compr none) + PublicKey payload }

@@ -95,7 +95,6 @@ void blake2b(const void *in, size_t inlen, void *out, size_t outlen) {
 }
 
 // ---------------------------------------------------------------- number theory
-namespace {
 bool is_prime_u64(u64 n) {
     static const u64 bases[] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
     if (n < 2) return false;
@@ -116,6 +115,7 @@ bool is_prime_u64(u64 n) {
     }
     return true;
 }
+namespace {
 // SEAL util::get_primes: descending primes congruent to 1 mod factor with exactly `bits` bits
 std::vector<u64> seal_get_primes(u64 factor, int bits, size_t count) {
     std::vector<u64> out;

@@ -38,6 +38,7 @@ int device_count();
 u64 h_mulmod(u64 a, u64 b, u64 q);
 u64 h_powmod(u64 b, u64 e, u64 q);
 u64 h_invmod(u64 a, u64 q);  // q prime
+bool is_prime_u64(u64 n);
 
 // BLAKE2b with variable digest length (RFC 7693), used for SEAL parms_id
 void blake2b(const void *in, size_t inlen, void *out, size_t outlen);

@@ -48,7 +48,8 @@ Engine::Engine() {
         throw std::runtime_error("fhe_b200: no CUDA device visible; this library has no CPU fallback");
     size_t max_dev = env_size("FHE_B200_MAX_DEVICES", (size_t)n_devices_);
     if ((size_t)n_devices_ > max_dev) n_devices_ = (int)max_dev;
-    chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 148);
+    chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 2048);
+    fused_ = env_size("FHE_B200_FUSED", 0) != 0;
     const size_t lanes_per_dev = env_size("FHE_B200_LANES", 4);
     for (int d = 0; d < n_devices_; d++) {
         device_context(d);
@@ -162,40 +163,138 @@ uint64_t *Engine::scratch(int device, size_t ops) {
 
 // ---------------------------------------------------------------- device-resident batched ops
 // scratch layout for a chunk of c ops: tens [c][15][N] | c3 [c][6][N] | ks [c][6][N]
+cudaEvent_t Engine::take_event() {
+    if (!event_pool_.empty()) {
+        cudaEvent_t e = event_pool_.back();
+        event_pool_.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cuda_throw(cudaEventCreate(&e), "cudaEventCreate");
+    return e;
+}
+void Engine::set_kernel_timing(bool on) { timing_ = on; }
+void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint64_t launches[kNumTimedKernels]) {
+    cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+    cuda_throw(cudaDeviceSynchronize(), "sync for timing report");
+    for (int k = 0; k < kNumTimedKernels; k++) ms[k] = 0, launches[k] = 0;
+    for (auto &t : timed_) {
+        float f = 0;
+        cuda_throw(cudaEventElapsedTime(&f, t.e0, t.e1), "cudaEventElapsedTime");
+        ms[t.kernel] += f;
+        launches[t.kernel]++;
+        event_pool_.push_back(t.e0);
+        event_pool_.push_back(t.e1);
+    }
+    timed_.clear();
+}
+
+// kernel ids: 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt, 5 k_tensor_intt,
+//             6 k_digit_ntt, 7 k_ks_intt
+#define TIMED(id, call, what)                                        \
+    do {                                                             \
+        if (timed) {                                                 \
+            TimedLaunch tl{id, take_event(), take_event()};          \
+            cuda_throw(cudaEventRecord(tl.e0, s), "event record");   \
+            cuda_throw(call, what);                                  \
+            cuda_throw(cudaEventRecord(tl.e1, s), "event record");   \
+            timed_.push_back(tl);                                    \
+        } else {                                                     \
+            cuda_throw(call, what);                                  \
+        }                                                            \
+    } while (0)
+
+// BEHZ multiply of c ops: a, b -> m.c3 (size-3 ciphertexts)
+void Engine::enqueue_mul(const uint64_t *a, const uint64_t *b, const ScratchMap &m, size_t c, cudaStream_t s, bool timed) {
+    if (fused_) {
+        TIMED(0, launch_behz_tensor(a, b, m.tens, c, s), "behz_tensor");
+    } else {
+        TIMED(4, launch_ext_ntt(a, b, m.nttbuf, c, s), "ext_ntt");
+        TIMED(5, launch_tensor_intt(m.nttbuf, m.tens, c, s), "tensor_intt");
+    }
+    TIMED(1, launch_floor_sk(m.tens, m.c3, c, s), "floor_sk");
+}
+// relinearise c size-3 ciphertexts c3 -> out
+void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out, const ScratchMap &m, size_t c, cudaStream_t s,
+                           bool timed) {
+    if (fused_) {
+        TIMED(2, launch_relin_ks(c3, rk, m.ks, c, s), "relin_ks");
+    } else {
+        TIMED(6, launch_digit_ntt(c3, m.dig, c, s), "digit_ntt");
+        TIMED(7, launch_ks_intt(m.dig, rk, m.ks, c, s), "ks_intt");
+    }
+    TIMED(3, launch_relin_finish(c3, m.ks, out, c, s), "relin_finish");
+}
+
 void Engine::mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
                        cudaStream_t s) {
     device_context(device);
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    uint64_t *sc = scratch(device, chunk);
-    uint64_t *tens = sc, *c3 = tens + chunk * 15 * kN, *ks = c3 + chunk * 6 * kN;
+    ScratchMap m(scratch(device, chunk), chunk);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
-        cuda_throw(launch_behz_tensor(a + off * kCtWords, b + off * kCtWords, tens, c, s), "behz_tensor");
-        cuda_throw(launch_floor_sk(tens, c3, c, s), "floor_sk");
-        cuda_throw(launch_relin_ks(c3, rk, ks, c, s), "relin_ks");
-        cuda_throw(launch_relin_finish(c3, ks, out + off * kCtWords, c, s), "relin_finish");
+        enqueue_mul(a + off * kCtWords, b + off * kCtWords, m, c, s, timing_);
+        enqueue_relin(m.c3, rk, out + off * kCtWords, m, c, s, timing_);
     }
 }
 void Engine::multiply(int device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, cudaStream_t s) {
     device_context(device);
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    uint64_t *tens = scratch(device, chunk);
+    ScratchMap m(scratch(device, chunk), chunk);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
-        cuda_throw(launch_behz_tensor(a + off * kCtWords, b + off * kCtWords, tens, c, s), "behz_tensor");
-        cuda_throw(launch_floor_sk(tens, out3 + off * 6 * kN, c, s), "floor_sk");
+        ScratchMap mm = m;
+        mm.c3 = out3 + off * 6 * kN;
+        enqueue_mul(a + off * kCtWords, b + off * kCtWords, mm, c, s, false);
     }
 }
 void Engine::relinearize(int device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, cudaStream_t s) {
     device_context(device);
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    uint64_t *sc = scratch(device, chunk);
-    uint64_t *ks = sc + chunk * 21 * kN;
+    ScratchMap m(scratch(device, chunk), chunk);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
-        cuda_throw(launch_relin_ks(c3 + off * 6 * kN, rk, ks, c, s), "relin_ks");
-        cuda_throw(launch_relin_finish(c3 + off * 6 * kN, ks, out + off * kCtWords, c, s), "relin_finish");
+        enqueue_relin(c3 + off * 6 * kN, rk, out + off * kCtWords, m, c, s, false);
     }
+}
+
+// ---------------------------------------------------------------- host-buffer batch (H2D | kernels | D2H overlapped)
+void Engine::mul_relin_host(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n) {
+    device_context(device);
+    {
+        std::lock_guard<std::mutex> lk(arena_mu_);
+        if (pipes_.size() < (size_t)n_devices_) pipes_.resize((size_t)n_devices_);
+        if (!pipes_[(size_t)device]) pipes_[(size_t)device].reset(new HostPipe());
+    }
+    HostPipe &P = *pipes_[(size_t)device];
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (!P.ready) {
+        P.chunk = env_size("FHE_B200_PIPE_CHUNK_OPS", 256);
+        cuda_throw(cudaMalloc((void **)&P.d_rk, kRkWords * 8), "cudaMalloc(rk)");
+        for (auto &sl : P.slot) {
+            cuda_throw(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_throw(cudaMalloc((void **)&sl.d_a, P.chunk * kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_b, P.chunk * kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_out, P.chunk * kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_scratch, P.chunk * kScratchLimbsPerOp * kN * 8), "cudaMalloc");
+        }
+        P.ready = true;
+    }
+    cuda_throw(cudaMemcpyAsync(P.d_rk, rk, kRkWords * 8, cudaMemcpyHostToDevice, P.slot[0].stream), "H2D rk");
+    cuda_throw(cudaStreamSynchronize(P.slot[0].stream), "sync rk");
+    size_t i = 0;
+    for (size_t off = 0; off < n; off += P.chunk, i++) {
+        const size_t c = n - off < P.chunk ? n - off : P.chunk;
+        PipeSlot &sl = P.slot[i % kPipeSlots];
+        cudaStream_t s = sl.stream;
+        cuda_throw(cudaMemcpyAsync(sl.d_a, a + off * kCtWords, c * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D a");
+        cuda_throw(cudaMemcpyAsync(sl.d_b, b + off * kCtWords, c * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D b");
+        ScratchMap m(sl.d_scratch, P.chunk);
+        enqueue_mul(sl.d_a, sl.d_b, m, c, s, false);
+        enqueue_relin(m.c3, P.d_rk, sl.d_out, m, c, s, false);
+        cuda_throw(cudaMemcpyAsync(out + off * kCtWords, sl.d_out, c * kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H out");
+    }
+    for (auto &sl : P.slot) cuda_throw(cudaStreamSynchronize(sl.stream), "pipe sync");
 }
 
 // ---------------------------------------------------------------- byte surface, one call
@@ -251,11 +350,9 @@ int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<ui
     if (shape == Shape::CtCt) {
         cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D b");
         if (op == Op::Mul) {
-            uint64_t *tens = lane->d_scratch, *c3 = tens + 15 * kN, *ks = c3 + 6 * kN;
-            cuda_throw(launch_behz_tensor(lane->d_a, lane->d_b, tens, 1, s), "behz_tensor");
-            cuda_throw(launch_floor_sk(tens, c3, 1, s), "floor_sk");
-            cuda_throw(launch_relin_ks(c3, d_rk, ks, 1, s), "relin_ks");
-            cuda_throw(launch_relin_finish(c3, ks, lane->d_out, 1, s), "relin_finish");
+            ScratchMap m(lane->d_scratch, 1);
+            enqueue_mul(lane->d_a, lane->d_b, m, 1, s, false);
+            enqueue_relin(m.c3, d_rk, lane->d_out, m, 1, s, false);
         } else {
             cuda_throw(launch_eltwise(lane->d_a, lane->d_b, lane->d_out, 1, op == Op::Add ? 0 : 1, s), "eltwise");
         }

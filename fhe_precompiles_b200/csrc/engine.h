@@ -17,8 +17,16 @@ namespace fheb {
 enum class Op : int { Add = 0, Sub = 1, Mul = 2 };
 enum class Shape : int { CtCt = 0, CtPt = 1, PtCt = 2 };
 
-// words of per-op scratch for multiply+relinearise: tensor (15 limbs) + size-3 result (6) + key-switch (6)
-constexpr size_t kScratchLimbsPerOp = 15 + 6 + 6;
+// limbs of per-op scratch for multiply+relinearise:
+// tensor (15) + size-3 result (6) + key-switch (6) + NTT-domain operands (20) + NTT-domain digits (6)
+constexpr size_t kScratchLimbsPerOp = 15 + 6 + 6 + 20 + 6;
+
+// offsets (in limbs, per chunk of `c` ops) of the scratch regions
+struct ScratchMap {
+    uint64_t *tens, *c3, *ks, *nttbuf, *dig;
+    ScratchMap(uint64_t *base, size_t c)
+        : tens(base), c3(tens + c * 15 * kN), ks(c3 + c * 6 * kN), nttbuf(ks + c * 6 * kN), dig(nttbuf + c * 20 * kN) {}
+};
 
 struct Lane {
     int device = 0;
@@ -52,6 +60,17 @@ class Engine {
     void multiply(int device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, cudaStream_t s);
     void relinearize(int device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, cudaStream_t s);
 
+    // host-buffer batched entry point: a, b, out are host memory (pinned for full PCIe rate), rk host words.
+    // H2D, kernels and D2H of consecutive chunks overlap on `kPipeSlots` streams.  Synchronous.
+    void mul_relin_host(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n);
+
+    // Optional per-kernel timing of mul_relin(): CUDA events around every launch on the caller's stream.
+    // kernel ids: see kKernelNames.  report() synchronises the device.
+    static constexpr int kNumTimedKernels = 8;
+    void set_kernel_timing(bool on);
+    void set_fused(bool on) { fused_ = on; }  // choose k_behz_tensor/k_relin_ks (true) or the split kernels (false)
+    void kernel_timing_report(int device, double ms[kNumTimedKernels], uint64_t launches[kNumTimedKernels]);
+
     // threshold-network simulation API (fhe.rs:594-779) against the embedded network keys
     int32_t encrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
     int32_t reencrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
@@ -71,7 +90,7 @@ class Engine {
     void release_lane(Lane *);
 
     int n_devices_ = 0;
-    size_t chunk_ops_ = 148;
+    size_t chunk_ops_ = 2048;
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::mutex lane_mu_;
     std::condition_variable lane_cv_;
@@ -80,6 +99,34 @@ class Engine {
     std::mutex key_mu_;
     std::vector<std::unique_ptr<KeyEntry>> keys_;
     uint64_t key_clock_ = 0;
+
+    static constexpr int kPipeSlots = 3;
+    struct PipeSlot {
+        cudaStream_t stream = nullptr;
+        uint64_t *d_a = nullptr, *d_b = nullptr, *d_out = nullptr, *d_scratch = nullptr;
+    };
+    struct HostPipe {
+        bool ready = false;
+        size_t chunk = 0;
+        uint64_t *d_rk = nullptr;
+        PipeSlot slot[kPipeSlots];
+        std::mutex mu;
+    };
+    std::vector<std::unique_ptr<HostPipe>> pipes_;
+
+    struct TimedLaunch {
+        int kernel;
+        cudaEvent_t e0, e1;
+    };
+    bool fused_ = false;  // FHE_B200_FUSED=1: multi-polynomial-per-CTA kernels (k_behz_tensor, k_relin_ks)
+    bool timing_ = false;
+    void enqueue_mul(const uint64_t *a, const uint64_t *b, const ScratchMap &m, size_t c, cudaStream_t s, bool timed);
+    void enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out, const ScratchMap &m, size_t c, cudaStream_t s,
+                       bool timed);
+    void timed_launch(int kernel, cudaStream_t s, bool timed, cudaError_t e0, const char *what);
+    std::vector<TimedLaunch> timed_;
+    std::vector<cudaEvent_t> event_pool_;
+    cudaEvent_t take_event();
 
     struct Arena {
         uint64_t *p = nullptr;

@@ -285,6 +285,86 @@ __global__ void __launch_bounds__(kThreads) k_behz_extend_tap(const u64 *a, cons
 }
 
 // =====================================================================================
+// Split variant of the BEHZ front end (default): one polynomial per CTA, 58-64 registers, 32 KiB smem,
+// two CTAs per SM.  Same arithmetic as k_behz_tensor; the NTT-domain limbs go through an L2-resident
+// scratch [op][4 polys a0,a1,b0,b1][5 limbs][N] instead of shared memory.
+//   k_ext_ntt     : base extension (limb >= 2) + forward NTT            grid (20 = poly*5+limb, ops)
+//   k_tensor_intt : dyadic tensor term + inverse NTT (x N^-1 t)          grid (15 = d*5+limb, ops)
+// =====================================================================================
+template <int EI>
+__device__ __forceinline__ void ext_ntt_body(const u64 *__restrict__ ct, int poly, u64 *__restrict__ dst, u64 *smem, int t) {
+    constexpr int MI = kExtLimb[EI];
+    using M = Mod<MI>;
+    u64 v[1][8];
+    load_extended<EI>(ct, poly, v[0], t);
+    ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+    store_chunk8(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                          u64 *__restrict__ nttbuf) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int p = blockIdx.x / 5, e = blockIdx.x % 5;
+    const u64 *ct = (p < 2 ? a : b) + op * 4 * kN;
+    u64 *dst = nttbuf + (op * 20 + blockIdx.x) * kN;
+    const int t = threadIdx.x;
+    switch (e) {
+        case 0: ext_ntt_body<0>(ct, p & 1, dst, smem, t); break;
+        case 1: ext_ntt_body<1>(ct, p & 1, dst, smem, t); break;
+        case 2: ext_ntt_body<2>(ct, p & 1, dst, smem, t); break;
+        case 3: ext_ntt_body<3>(ct, p & 1, dst, smem, t); break;
+        default: ext_ntt_body<4>(ct, p & 1, dst, smem, t); break;
+    }
+}
+
+template <int EI>
+__device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int d, u64 *__restrict__ dst, u64 *smem, int t) {
+    constexpr int MI = kExtLimb[EI];
+    using M = Mod<MI>;
+    // nb: [4 polys][5 limbs][N] of this op; polys a0,a1,b0,b1
+    const u64 *a0 = nb + (size_t)(0 * 5 + EI) * kN, *a1 = nb + (size_t)(1 * 5 + EI) * kN;
+    const u64 *b0 = nb + (size_t)(2 * 5 + EI) * kN, *b1 = nb + (size_t)(3 * 5 + EI) * kN;
+    u64 v[1][8];
+    if (d == 1) {
+        u64 x0[8], x1[8], y0[8], y1[8];
+        load_chunk8(a0, x0, t);
+        load_chunk8(b1, y1, t);
+        load_chunk8(a1, x1, t);
+        load_chunk8(b0, y0, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, x0[r], y1[r]);
+            mac128(lo, hi, x1[r], y0[r]);
+            v[0][r] = reduce128<M>(hi, lo);
+        }
+    } else {
+        u64 x[8], y[8];
+        load_chunk8(d == 0 ? a0 : a1, x, t);
+        load_chunk8(d == 0 ? b0 : b1, y, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(x[r], y[r]);
+    }
+    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv_t[MI].w, kc.ninv_t[MI].ws);
+    store_natural(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int d = blockIdx.x / 5, e = blockIdx.x % 5;
+    const u64 *nb = nttbuf + op * 20 * kN;
+    u64 *dst = tens + (op * 15 + blockIdx.x) * kN;
+    const int t = threadIdx.x;
+    switch (e) {
+        case 0: tensor_intt_body<0>(nb, d, dst, smem, t); break;
+        case 1: tensor_intt_body<1>(nb, d, dst, smem, t); break;
+        case 2: tensor_intt_body<2>(nb, d, dst, smem, t); break;
+        case 3: tensor_intt_body<3>(nb, d, dst, smem, t); break;
+        default: tensor_intt_body<4>(nb, d, dst, smem, t); break;
+    }
+}
+
+// =====================================================================================
 // K8: fast_floor + fastbconv_sk   (SEAL RNSTool::fast_floor, RNSTool::fastbconv_sk), per coefficient
 //   tens [op][3][5][N] (x t, canonical)  ->  c3 [op][3][2][N]
 // =====================================================================================
@@ -404,6 +484,67 @@ __global__ void __launch_bounds__(kThreads, 1) k_relin_ks(const u64 *__restrict_
 }
 
 // =====================================================================================
+// Split variant of the key-switch core (default), same arithmetic as k_relin_ks:
+//   k_digit_ntt : NTT_J([c2]_I)                       grid (6 = I*3+J, ops)   -> dig [op][2][3][N]
+//   k_ks_intt   : INTT_J(sum_I dig[I][J] * rk[I][k][J]) grid (6 = k*3+J, ops) -> ks  [op][2][3][N]
+// =====================================================================================
+template <int MI>
+__device__ __forceinline__ void digit_ntt_body(const u64 *__restrict__ src, u64 *__restrict__ dst, u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 v[1][8];
+    load_natural(src, v[0], t);
+    ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+    store_chunk8(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_digit_ntt(const u64 *__restrict__ c3, u64 *__restrict__ dig) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int I = blockIdx.x / 3, J = blockIdx.x % 3;
+    const u64 *src = c3 + op * 6 * kN + 4 * kN + (size_t)I * kN;
+    u64 *dst = dig + (op * 6 + blockIdx.x) * kN;
+    const int t = threadIdx.x;
+    switch (J) {
+        case 0: digit_ntt_body<MQ0>(src, dst, smem, t); break;
+        case 1: digit_ntt_body<MQ1>(src, dst, smem, t); break;
+        default: digit_ntt_body<MP>(src, dst, smem, t); break;
+    }
+}
+template <int MI>
+__device__ __forceinline__ void ks_intt_body(const u64 *__restrict__ dg, const u64 *__restrict__ rk, int k, u64 *__restrict__ dst,
+                                             u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 d0[8], d1[8], k0[8], k1[8];
+    load_chunk8(dg + (size_t)(0 * 3 + MI) * kN, d0, t);
+    load_chunk8(dg + (size_t)(1 * 3 + MI) * kN, d1, t);
+    load_chunk8_ldg(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN, k0, t);
+    load_chunk8_ldg(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN, k1, t);
+    u64 v[1][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        u64 lo = 0, hi = 0;
+        mac128(lo, hi, d0[r], k0[r]);
+        mac128(lo, hi, d1[r], k1[r]);
+        v[0][r] = reduce128<M>(hi, lo);
+    }
+    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    store_natural(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_ks_intt(const u64 *__restrict__ dig, const u64 *__restrict__ rk,
+                                                          u64 *__restrict__ ks) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int k = blockIdx.x / 3, J = blockIdx.x % 3;
+    const u64 *dg = dig + op * 6 * kN;
+    u64 *dst = ks + (op * 6 + blockIdx.x) * kN;
+    const int t = threadIdx.x;
+    switch (J) {
+        case 0: ks_intt_body<MQ0>(dg, rk, k, dst, smem, t); break;
+        case 1: ks_intt_body<MQ1>(dg, rk, k, dst, smem, t); break;
+        default: ks_intt_body<MP>(dg, rk, k, dst, smem, t); break;
+    }
+}
+
+// =====================================================================================
 // K9b: rounded division by P and accumulation into (c0, c1)   (tail of switch_key_inplace)
 //   out[op][k][l][i] = c3[op][k][l][i] + (ks[k][l][i] - ((ks[k][P][i] + P/2 mod P) mod q_l - (P/2 mod q_l))) * P^-1 mod q_l
 // =====================================================================================
@@ -435,6 +576,133 @@ __global__ void __launch_bounds__(256) k_relin_finish(const u64 *__restrict__ c3
             po[kN] = addmod<Q1>(v, pc[kN]);
         }
     }
+}
+
+// =====================================================================================
+// integer-pipe peak microbenchmark (roofline denominator for the multiply kernels; not on the hot path)
+// 16 independent mad chains per thread; WIDE: mad.wide.u32 (32x32+64 -> 64), else mad.lo.u32
+// =====================================================================================
+// MODE 0: mad.lo.u32, 1: mad.wide.u32, 2: add.u32 (ALU pipe), 3: mad.lo.u32 + add.u32 interleaved (dual issue),
+//      4: mad.wide.u32 + add.u32 interleaved
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int_peak(u64 *out, int iters) {
+    u32 a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 7u;
+    u64 acc[16];
+    u32 s[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) acc[j] = a + j, s[j] = b + j;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (MODE == 1 || MODE == 4) {
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
+            } else if (MODE == 0 || MODE == 3) {
+                u32 x = (u32)acc[j];
+                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
+                acc[j] = x;
+            }
+            if (MODE >= 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(s[j]) : "r"(s[(j + 1) & 15]));
+        }
+    }
+    u64 r = 0;
+#pragma unroll
+    for (int j = 0; j < 16; j++) r ^= acc[j] ^ s[j];
+    if (r == 0x123456789abcdefull) out[0] = r;  // keep the chains alive
+}
+
+// Register-only butterfly throughput: every thread runs `iters` forward radix-8 passes (12 butterflies each)
+// on 8 resident values with twiddles held in registers -- the practical integer-pipe ceiling of the NTT inner
+// loop, free of memory and barrier effects.
+template <int MI>
+__global__ void __launch_bounds__(kThreads) k_bfly_peak(u64 *out, int iters, ulonglong2 tw0) {
+    using M = Mod<MI>;
+    u64 v[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[r] = (threadIdx.x * 8 + r) * 0x9E3779B97F4A7C15ull % M::q;
+    u64 w = tw0.x % M::q, ws = tw0.y;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) fwd_bfly<M, 2>(v[r], v[r + 4], w, ws);
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            fwd_bfly<M, 3>(v[r], v[r + 2], w, ws);
+            fwd_bfly<M, 3>(v[4 + r], v[6 + r], w, ws);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) fwd_bfly<M, 4>(v[2 * r], v[2 * r + 1], w, ws);
+        if (M::kSmall) {  // keep the lazy values inside the range the real transform guarantees
+#pragma unroll
+            for (int r = 0; r < 8; r++) v[r] &= (1ull << 42) - 1;
+        }
+    }
+    u64 acc = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) acc ^= v[r];
+    if (acc == tw0.x) out[0] = acc;
+}
+cudaError_t measure_bfly_peak(int mod, double *giga_bfly_per_s) {
+    u64 *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, 8);
+    if (e != cudaSuccess) return e;
+    const int iters = 2048, grid = 148 * 4;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    ulonglong2 tw = make_ulonglong2(0x123456789ull, 0x9abcdef012345678ull);
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        if (mod < 3)
+            k_bfly_peak<MQ0><<<grid, kThreads>>>(d, iters, tw);
+        else
+            k_bfly_peak<MB0><<<grid, kThreads>>>(d, iters, tw);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    *giga_bfly_per_s = (double)grid * kThreads * iters * 12.0 / (best * 1e-3) / 1e9;
+    return cudaGetLastError();
+}
+
+// result: 1e12 "primary" ops per second (mads for modes 0,1,3,4; adds for mode 2)
+cudaError_t measure_int_peak(int mode, double *tera_ops_per_s) {
+    u64 *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, 8);
+    if (e != cudaSuccess) return e;
+    const int iters = 8192, grid = 148 * 8, block = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        switch (mode) {
+            case 0: k_int_peak<0><<<grid, block>>>(d, iters); break;
+            case 1: k_int_peak<1><<<grid, block>>>(d, iters); break;
+            case 2: k_int_peak<2><<<grid, block>>>(d, iters); break;
+            case 3: k_int_peak<3><<<grid, block>>>(d, iters); break;
+            default: k_int_peak<4><<<grid, block>>>(d, iters); break;
+        }
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (e != cudaSuccess) return e;
+    *tera_ops_per_s = (double)grid * block * iters * 16.0 / (best * 1e-3) / 1e12;
+    return cudaGetLastError();
 }
 
 // =====================================================================================
@@ -508,6 +776,30 @@ cudaError_t launch_behz_extend_tap(const u64 *a, const u64 *b, u64 *ext, size_t 
 cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *tens, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
     k_behz_tensor<<<dim3(5, (unsigned)n_ops), kThreads, kSmem4, s>>>(a, b, tens);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_digit_ntt(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_digit_ntt<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(c3, dig);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_ks_intt(const u64 *dig, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ks_intt<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(dig, rk, ks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

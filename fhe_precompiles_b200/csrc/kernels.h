@@ -23,10 +23,19 @@ cudaError_t launch_plain_addsub(const u64 *ct, const unsigned short *plain, u64 
 cudaError_t launch_mul_plain(const u64 *ct, const unsigned short *plain, u64 *out, size_t n_ops, cudaStream_t s);
 cudaError_t launch_behz_extend_tap(const u64 *a, const u64 *b, u64 *ext, size_t n_ops, cudaStream_t s);
 cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *tens, size_t n_ops, cudaStream_t s);
+// split (one polynomial per CTA) variants; scratch: nttbuf [n][4][5][N], dig [n][2][3][N]
+cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s);
+cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaStream_t s);
+cudaError_t launch_digit_ntt(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s);
+cudaError_t launch_ks_intt(const u64 *dig, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s);
 cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
 cudaError_t launch_relin_finish(const u64 *c3, const u64 *ks, u64 *out, size_t n_ops, cudaStream_t s);
 
 uint64_t launch_count();
+// integer multiply-add peak of the current device in 1e12 mad/s (microbenchmark, synchronous)
+cudaError_t measure_int_peak(int mode, double *tera_ops_per_s);
+// register-only NTT butterfly rate (1e9 butterflies/s) for a small (mod < 3) or a 61-bit prime
+cudaError_t measure_bfly_peak(int mod, double *giga_bfly_per_s);
 
 }  // namespace fheb

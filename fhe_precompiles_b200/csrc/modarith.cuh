@@ -1,25 +1,70 @@
-// 64-bit modular arithmetic on the sm_100a integer pipe.
+// 64-bit modular arithmetic on the sm_100a integer pipes.
 // Replaces SEAL util/uintarithsmallmod.h (barrett_reduce_64/128, MultiplyUIntModOperand)
 // on the reference's hot path (FheApp::run, /root/reference/src/fhe.rs:138-152).
 //
+// B200 has two integer issue paths per SM sub-partition, each 16 lanes wide: the FMA pipe (IMAD,
+// IMAD.WIDE) and the ALU pipe (IADD3, LOP3, SEL, ISETP, SHF).  Everything here is written on 32-bit
+// halves so that the multiply-accumulate chains carry on the FMA pipe (IMAD.WIDE accumulates 64 bits
+// for free) and only the unavoidable adds / selects land on the ALU pipe; the first version (plain
+// __umul64hi + 64-bit adds) was ALU-bound at 2 ALU : 1 FMA instructions (profiles/r1a).
+//
 // Two prime classes, selected at compile time by Mod<MI>::kSmall:
-//  * 36/37-bit data and key-switch primes (q0, q1, P): 27 bits of headroom in a 64-bit word, so
-//    butterflies never conditionally subtract; values drift up to ~2^50 and are reduced once.
-//  * 61-bit BEHZ primes (b0, b1, m_sk): Harvey lazy ranges [0,4q) forward / [0,2q) inverse.
+//  * 36/37-bit data and key-switch primes (q0, q1, P) = 2^b - c with c < 2^18: 27 bits of headroom in a
+//    word, so butterflies never conditionally subtract, the Shoup quotient drops its lowest partial
+//    product, and reduction is a pseudo-Mersenne fold.
+//  * 61-bit BEHZ primes (b0, b1, m_sk) = 2^61 - c: Harvey-style lazy ranges with a conditional
+//    subtraction every other forward stage ([0,8q) fits a word).
 #pragma once
 #include "params.h"
 
 namespace fheb {
+
+constexpr int mod_bits(u64 q) {
+    int b = 0;
+    while (q) {
+        b++;
+        q >>= 1;
+    }
+    return b;
+}
 
 template <int MI>
 struct Mod {
     static constexpr int kIndex = MI;
     static constexpr u64 q = kModulus[MI];
     static constexpr u64 two_q = 2 * kModulus[MI];
-    static constexpr u64 r1 = barrett_ratio(kModulus[MI]).hi;  // floor(2^128/q) >> 64 == floor(2^64/q)
+    static constexpr u64 four_q = 4 * kModulus[MI];
+    static constexpr u64 r1 = barrett_ratio(kModulus[MI]).hi;  // floor(2^64/q)
     static constexpr u64 r0 = barrett_ratio(kModulus[MI]).lo;
     static constexpr bool kSmall = kModulus[MI] < (1ull << 40);
+    static constexpr int kBits = mod_bits(kModulus[MI]);           // q < 2^kBits
+    static constexpr u64 kC = (1ull << kBits) - kModulus[MI];      // q = 2^kBits - kC, kC < 2^19
+    static constexpr u64 kMask = (1ull << kBits) - 1;
+    static constexpr u64 neg_q = 0 - kModulus[MI];                 // -q mod 2^64
 };
+
+// 32-bit building blocks as PTX so that ptxas sees exactly the partial products we want
+__device__ __forceinline__ void unpack64(u64 x, u32 &lo, u32 &hi) { asm("mov.b64 {%0,%1}, %2;" : "=r"(lo), "=r"(hi) : "l"(x)); }
+__device__ __forceinline__ u64 pack64(u32 lo, u32 hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+__device__ __forceinline__ u64 mul_wide(u32 a, u32 b) {
+    u64 r;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ u64 mad_wide(u32 a, u32 b, u64 c) {
+    u64 r;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u32 mad_lo(u32 a, u32 b, u32 c) {
+    u32 r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
 
 __device__ __forceinline__ u64 mulhi64(u64 a, u64 b) { return __umul64hi(a, b); }
 
@@ -36,19 +81,69 @@ __device__ __forceinline__ u64 csub(u64 x, u64 m) {
     return x >= m ? x - m : x;
 }
 
-// Shoup multiplication by a precomputed (w, ws = floor(w * 2^64 / q)); any 64-bit x; result in [0, 2q)
+// acc + x*w - H*q (mod 2^64) with H ~ floor(x*ws/2^64): Shoup multiplication by the precomputed pair
+// (w, ws = floor(w*2^64/q)) fused with an accumulate.  q = 2^B - c, so -H*q = H*c - (H << B).
+//   exact quotient : adds a value in [0, 2q) for any 64-bit x
+//   kApprox        : drops the x_lo*ws_lo partial product and one carry (H low by <= 2): adds [0, 4q)
+// SASS per call: 5-6 IMAD.WIDE + 4 IMAD on the FMA pipe, 4-8 IADD3 on the ALU pipe.
+template <class M, bool kApprox>
+__device__ __forceinline__ u64 shoup_acc(u64 acc, u64 x, u64 w, u64 ws) {
+    constexpr u32 c = (u32)M::kC;
+    u32 xl, xh, wl, wh, sl, sh;
+    unpack64(x, xl, xh);
+    unpack64(w, wl, wh);
+    unpack64(ws, sl, sh);
+    u64 H;
+    if (kApprox) {
+        u32 ul, uh, vl, vh;
+        unpack64(mul_wide(xh, sl), ul, uh);
+        unpack64(mul_wide(xl, sh), vl, vh);
+        H = mad_wide(xh, sh, pack64(uh, 0)) + vh;
+    } else {
+        u32 tl, th, ul, uh, vl, vh;
+        unpack64(mul_wide(xl, sl), tl, th);
+        unpack64(mad_wide(xh, sl, pack64(th, 0)), ul, uh);
+        unpack64(mad_wide(xl, sh, pack64(ul, 0)), vl, vh);
+        H = mad_wide(xh, sh, pack64(uh, 0)) + vh;
+    }
+    u32 hl, hh, al, ah;
+    unpack64(H, hl, hh);
+    u64 a = mad_wide(xl, wl, acc);
+    a = mad_wide(hl, c, a);
+    unpack64(a, al, ah);
+    ah = mad_lo(xl, wh, ah);
+    ah = mad_lo(xh, wl, ah);
+    ah = mad_lo(hh, c, ah);
+    ah -= hl << (M::kBits - 32);
+    return pack64(al, ah);
+}
+// x*w mod q, lazy: [0, 2q) for any 64-bit x
 template <class M>
 __device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws) {
-    return x * w - mulhi64(x, ws) * M::q;
+    return shoup_acc<M, false>(0, x, w, ws);
 }
 template <class M>
 __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws) {
     return csub<M>(shoup_lazy<M>(x, w, ws), M::q);
 }
 
+// pseudo-Mersenne fold: x -> (x mod 2^b) + floor(x / 2^b) * c, congruent to x mod q.
+// Result < 2^b + 2^(64-b) * c; one more conditional subtraction is canonical whenever that is < 2q.
+template <class M>
+__device__ __forceinline__ u64 fold(u64 x) {
+    const u64 k = x >> M::kBits;
+    return (x & M::kMask) + k * M::kC;
+}
+// canonical residue of x when fold(x) < 2q: small primes x < 2^55, 61-bit primes any x
+template <class M>
+__device__ __forceinline__ u64 canon(u64 x) {
+    return csub<M>(fold<M>(x), M::q);
+}
+
 // x mod q for any 64-bit x (SEAL barrett_reduce_64)
 template <class M>
 __device__ __forceinline__ u64 reduce64(u64 x) {
+    if (!M::kSmall) return canon<M>(x);  // fold(x) <= 2^61 - 1 + 7c < 2q
     u64 r = x - mulhi64(x, M::r1) * M::q;
     return csub<M>(r, M::q);
 }
@@ -73,7 +168,9 @@ __device__ __forceinline__ u64 reduce128(u64 hi, u64 lo) {
 
 template <class M>
 __device__ __forceinline__ u64 mulmod(u64 a, u64 b) {
-    return reduce128<M>(mulhi64(a, b), a * b);
+    u64 lo = 0, hi = 0;
+    mac128(lo, hi, a, b);
+    return reduce128<M>(hi, lo);
 }
 
 template <class M>

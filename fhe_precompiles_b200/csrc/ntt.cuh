@@ -35,34 +35,37 @@ __device__ __forceinline__ int pass_upper(int t) {
 }
 
 // ---------------------------------------------------------------- butterflies
-// forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY)
-template <class M>
+// forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY), lazily.  G = global stage index 0..11.
+//  small primes: T = wY in [0,4q) (approximate Shoup quotient); bounds grow by 4q per stage, never reduced.
+//  61-bit primes: stage inputs < 4q, 6q, then X is brought back below 4q on every even stage >= 2
+//                 (one conditional subtraction per two stages; 8q < 2^64).
+template <class M, int G>
 __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     if (M::kSmall) {
-        // no conditional subtraction: bound grows by 2q per stage (<= 26q < 2^42 after 12 stages)
-        u64 T = shoup_lazy<M>(Y, w, ws);
-        Y = X + (M::two_q - T);
-        X = X + T;
+        const u64 Xo = shoup_acc<M, true>(X, Y, w, ws);
+        Y = (X + X + M::four_q) - Xo;  // X + 4q - T
+        X = Xo;
     } else {
-        // Harvey: inputs in [0,4q), outputs in [0,4q)
-        u64 x = csub<M>(X, M::two_q);
-        u64 T = shoup_lazy<M>(Y, w, ws);
-        X = x + T;
-        Y = x + (M::two_q - T);
+        u64 x = X;
+        if (G >= 2 && (G % 2) == 0) x = csub<M>(x, M::four_q);
+        const u64 Xo = shoup_acc<M, false>(x, Y, w, ws);
+        Y = (x + x + M::two_q) - Xo;  // x + 2q - T
+        X = Xo;
     }
 }
+// bound of the forward outputs in units of q: small 1 + 4*12 (from canonical input), large 8
 // inverse (Gentleman-Sande): (X, Y) -> (X + Y, w(X - Y)); G = global stage index 0..11
 template <class M, int G>
 __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     if (M::kSmall) {
-        // inputs < 2^(G+1) q, X output < 2^(G+2) q, Y output < 2q
-        constexpr u64 K = M::q << (G + 1);
-        u64 D = X + (K - Y);
+        // inputs < 4q * 2^G, X output < 4q * 2^(G+1), Y output < 4q
+        constexpr u64 K = M::four_q << G;
+        const u64 D = X + (K - Y);
         X = X + Y;
-        Y = shoup_lazy<M>(D, w, ws);
+        Y = shoup_acc<M, true>(0, D, w, ws);
     } else {
         // Harvey: inputs and outputs in [0,2q)
-        u64 D = X + (M::two_q - Y);
+        const u64 D = X + (M::two_q - Y);
         X = csub<M>(X + Y, M::two_q);
         Y = shoup_lazy<M>(D, w, ws);
     }
@@ -79,7 +82,7 @@ __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__re
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
-            for (int r = 0; r < 4; r++) fwd_bfly<M>(v[p][r], v[p][r + 4], w.x, w.y);
+            for (int r = 0; r < 4; r++) fwd_bfly<M, S0>(v[p][r], v[p][r + 4], w.x, w.y);
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -87,13 +90,13 @@ __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__re
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
-            for (int r = 0; r < 2; r++) fwd_bfly<M>(v[p][4 * h + r], v[p][4 * h + r + 2], w.x, w.y);
+            for (int r = 0; r < 2; r++) fwd_bfly<M, S0 + 1>(v[p][4 * h + r], v[p][4 * h + r + 2], w.x, w.y);
     }
 #pragma unroll
     for (int h = 0; h < 4; h++) {
         ulonglong2 w = ldtw(tw, (4 << S0) + 4 * upper + h);
 #pragma unroll
-        for (int p = 0; p < NP; p++) fwd_bfly<M>(v[p][2 * h], v[p][2 * h + 1], w.x, w.y);
+        for (int p = 0; p < NP; p++) fwd_bfly<M, S0 + 2>(v[p][2 * h], v[p][2 * h + 1], w.x, w.y);
     }
 }
 
@@ -142,9 +145,9 @@ __device__ __forceinline__ void smem_load(const u64 *smem, u64 (&v)[NP][8], int 
 
 // ---------------------------------------------------------------- whole transforms on registers
 // Forward NTT of NP polynomials.
-//  in : v holds coefficients elem_index<0>(t, r) = r*512 + t   (natural order, any value < 2^62 small / < 4q large)
+//  in : v holds coefficients elem_index<0>(t, r) = r*512 + t   (natural order; small primes < 2^42, large < 4q)
 //  out: v holds NTT values at positions elem_index<9>(t, r) = 8*t + r, reduced to [0, q) if kCanon
-//       (else small primes < 2^42, large primes < 4q)
+//       (else small primes < in + 48q, large primes < 8q)
 template <class M, int NP, bool kCanon>
 __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t) {
     fwd_pass<M, NP, 0>(v, tw, pass_upper<0>(t));
@@ -164,18 +167,13 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                if (M::kSmall)
-                    v[p][r] = reduce64<M>(v[p][r]);
-                else
-                    v[p][r] = csub<M>(csub<M>(v[p][r], M::two_q), M::q);
-            }
+            for (int r = 0; r < 8; r++) v[p][r] = canon<M>(v[p][r]);  // small: < 2^43; large: < 8q
     }
     __syncthreads();  // smem may be reused by the caller
 }
 
 // Inverse NTT of NP polynomials.
-//  in : v holds NTT values at positions 8*t + r, each < 2q
+//  in : v holds NTT values at positions 8*t + r, each < 2q (small primes: < 4q)
 //  out: v holds coefficients r*512 + t, multiplied by (sc, scs) (Shoup pair, e.g. N^-1), in [0, q)
 template <class M, int NP>
 __device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t, u64 sc,

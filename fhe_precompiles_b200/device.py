@@ -123,3 +123,56 @@ def behz_floor_sk(tens):
     out = torch.empty((tens.shape[0], 3, 2, N), dtype=torch.int64, device=tens.device)
     _check(_lib.lib().fhe_b200_behz_floor_sk(dev, tens.data_ptr(), out.data_ptr(), tens.shape[0], _stream(dev)))
     return out
+
+
+def mul_relin_host(a: torch.Tensor, b: torch.Tensor, rk: torch.Tensor, out: torch.Tensor, device: int = 0) -> torch.Tensor:
+    """a, b, out: HOST tensors [n,2,2,4096] int64 (pinned for full PCIe rate); rk: host [2,2,3,4096]."""
+    for t in (a, b, rk, out):
+        if t.is_cuda or not t.is_contiguous():
+            raise ValueError("mul_relin_host takes contiguous host tensors")
+    _check(_lib.lib().fhe_b200_mul_relin_host(device, a.data_ptr(), b.data_ptr(), rk.data_ptr(), out.data_ptr(), a.shape[0]))
+    return out
+
+
+KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt")
+
+
+def set_kernel_timing(on: bool) -> None:
+    _lib.lib().fhe_b200_set_kernel_timing(int(on))
+
+
+def kernel_timing_report(device: int = 0) -> dict:
+    """{kernel: (total ms, launches)} accumulated by mul_relin() since the last report."""
+    ms = (ctypes.c_double * 8)()
+    cnt = (ctypes.c_uint64 * 8)()
+    _check(_lib.lib().fhe_b200_kernel_timing_report(device, ms, cnt))
+    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(8) if cnt[i]}
+
+
+def parse_public_key(data: bytes):
+    """PublicKey bytes -> (pk [2,3,4096], rk [2,2,3,4096]) int64 host tensors, via the library's codec."""
+    pk = torch.empty((2, 3, N), dtype=torch.int64)
+    rk = torch.empty((2, 2, 3, N), dtype=torch.int64)
+    rc = _lib.lib().fhe_b200_parse_public_key(data, len(data), pk.data_ptr(), rk.data_ptr())
+    if rc != 0:
+        raise RuntimeError(f"parse_public_key failed with code {rc}")
+    return pk, rk
+
+
+def int_peak(device: int = 0, wide=True) -> float:
+    """Measured integer multiply-add peak in 1e12 mad/s (mad.wide.u32 or mad.lo.u32 microbenchmark)."""
+    v = ctypes.c_double()
+    _check(_lib.lib().fhe_b200_int_peak(device, int(wide), ctypes.byref(v)))
+    return float(v.value)
+
+
+def bfly_peak(device: int = 0, mod: int = 0) -> float:
+    """Register-only NTT butterfly rate in 1e9 butterflies/s (mod 0-2: small primes, 3-5: 61-bit primes)."""
+    v = ctypes.c_double()
+    _check(_lib.lib().fhe_b200_bfly_peak(device, mod, ctypes.byref(v)))
+    return float(v.value)
+
+
+def set_fused(on: bool) -> None:
+    """Select the multi-polynomial-per-CTA kernels (True) or the one-polynomial-per-CTA kernels (False, default)."""
+    _lib.lib().fhe_b200_set_fused(int(on))

@@ -136,6 +136,24 @@ int32_t fhe_b200_multiply(int32_t device, const uint64_t *a, const uint64_t *b, 
 int32_t fhe_b200_relinearize(int32_t device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, void *stream);
 int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
                            size_t n, void *stream);
+/* Same op on HOST buffers (pin them for full PCIe rate): copies in, computes and copies out chunk by chunk with
+ * the three phases of consecutive chunks overlapped; returns when `out` is complete. rk: host words. */
+int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
+                                size_t n);
+/* Integer-pipe peak of `device` in 1e12 multiply-adds/s, measured by a register-only microbenchmark
+ * (wide: 0 mad.lo.u32, 1 mad.wide.u32, 2 add.u32, 3 mad.lo+add interleaved, 4 mad.wide+add). Denominator of the integer roofline; synchronous. */
+int32_t fhe_b200_int_peak(int32_t device, int32_t wide, double *tera_mads_per_s);
+/* Register-only NTT butterfly rate of `device` in 1e9 butterflies/s for modulus class of `mod` (0-2: 36/37-bit,
+ * 3-5: 61-bit): the compute ceiling of the transform's inner loop without memory or barriers. */
+int32_t fhe_b200_bfly_peak(int32_t device, int32_t mod, double *giga_bfly_per_s);
+/* Kernel variant of multiply / relinearise: 0 (default) one polynomial per CTA (k_ext_ntt, k_tensor_intt,
+ * k_digit_ntt, k_ks_intt); 1 multi-polynomial CTAs (k_behz_tensor, k_relin_ks). Same results. */
+void fhe_b200_set_fused(int32_t on);
+/* Per-kernel timing of fhe_b200_mul_relin (CUDA events around each launch, on the caller's stream).
+ * ms / launches are indexed 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt,
+ * 5 k_tensor_intt, 6 k_digit_ntt, 7 k_ks_intt; the report synchronises the device and resets the accumulators. */
+void fhe_b200_set_kernel_timing(int32_t on);
+int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[8], uint64_t launches[8]);
 /* Batched negacyclic NTT in place over n_limbs limbs of 4096 words; limb i uses modulus mods[i % n_mods]
  * (0 q0, 1 q1, 2 P, 3 b0, 4 b1, 5 m_sk). inverse != 0: bit-reversed -> natural, scaled by N^-1. */
 int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,

@@ -1,0 +1,13 @@
+#!/bin/bash
+# Profiling recipe of /opt/skills/guides/B200_PROFILING.md applied to bench.py (run under gpurun, 1 GPU).
+# usage: scripts/gpu_profile.sh <tag>     -> gpurun_out/<tag>_{launches.csv,prof.ncu-rep,...}
+set -u
+TAG=${1:-r1}
+OUT=gpurun_out
+mkdir -p $OUT
+CMD="python bench.py --steps 2 --warmup 3 --batch 592 --no-cpu-baseline --no-e2e"
+$CMD > $OUT/${TAG}_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
+$CMD > $OUT/${TAG}_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:'k_behz_tensor|k_floor_sk|k_relin_ks|k_relin_finish' -s 24 -c 8 -o $OUT/${TAG}_prof -f $CMD > $OUT/${TAG}_ncu_full.log 2>&1
+tail -3 $OUT/${TAG}_ncu_full.log

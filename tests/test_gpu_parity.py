@@ -126,8 +126,21 @@ def test_relinearize_and_mul_relin(dev, keys):
     assert np.array_equal(to_np(dev.mul_relin(da, db, drk)), want), "multiply + relinearize"
 
 
+def test_fused_kernel_variant(dev, keys):
+    """the multi-polynomial-per-CTA kernels (k_behz_tensor, k_relin_ks) give the same bits as the default split ones"""
+    a, b = edge_ct(3, 18), edge_ct(3, 19)[::-1].copy()
+    da, db, drk = to_dev(a), to_dev(b), to_dev(keys.rk)
+    want = np.stack([bfv.mul_relin(x, y, keys.rk) for x, y in zip(a, b)])
+    try:
+        dev.set_fused(True)
+        assert np.array_equal(to_np(dev.mul_relin(da, db, drk)), want)
+    finally:
+        dev.set_fused(False)
+    assert np.array_equal(to_np(dev.mul_relin(da, db, drk)), want)
+
+
 def test_mul_relin_real_encryptions_chunked(dev, keys):
-    """batch larger than the engine's chunk (148): every op bit-exact vs oracle on a sample, all decrypt."""
+    """batch larger than the engine's chunk (FHE_B200_CHUNK_OPS=128 set by the driver line below): bit-exact vs oracle on a sample, all decrypt."""
     rng = np.random.default_rng(2)
     n = 300
     vals_a = rng.integers(-(2**15), 2**15, size=n)
