@@ -72,6 +72,10 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_plain_addsub.argtypes = [i32, vp, vp, vp, sz, i32, vp]
     L.fhe_b200_multiply_plain.argtypes = [i32, vp, vp, vp, sz, vp]
     L.fhe_b200_mul_relin.argtypes = [i32, vp, vp, vp, vp, sz, vp]
+    L.fhe_b200_encrypt.argtypes = [i32, vp, vp, vp, vp, sz, vp]
+    L.fhe_b200_encrypt.restype = i32
+    L.fhe_b200_decrypt.argtypes = [i32, vp, vp, vp, sz, vp]
+    L.fhe_b200_decrypt.restype = i32
     L.fhe_b200_mul_relin_host.argtypes = [i32, vp, vp, vp, vp, sz]
     L.fhe_b200_mul_relin_host.restype = i32
     L.fhe_b200_int_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]

@@ -242,6 +242,13 @@ int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b,
 int32_t fhe_b200_int_peak(int32_t device, int32_t wide, double *tera_mads_per_s) {
     DEV_GUARD(device_context(device); cuda_throw(measure_int_peak(wide, tera_mads_per_s), "int_peak"));
 }
+int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
+                         void *stream) {
+    DEV_GUARD(Engine::get().encrypt_device(device, pk, plain, seeds, ct, n, (cudaStream_t)stream));
+}
+int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, void *stream) {
+    DEV_GUARD(Engine::get().decrypt_device(device, ct, sk, plain, n, (cudaStream_t)stream));
+}
 int32_t fhe_b200_bfly_peak(int32_t device, int32_t mod, double *giga_bfly_per_s) {
     DEV_GUARD(device_context(device); cuda_throw(measure_bfly_peak(mod, giga_bfly_per_s), "bfly_peak"));
 }

@@ -42,6 +42,11 @@ struct DevConsts {
     u64 half_P;
     u64 half_P_mod_q[2];
 
+    // ---- decryption (Decryptor::bfv_decrypt): CRT recombination and exact round(t*x/q)
+    Shoup crt_inv[2];     // (q/q_l)^-1 mod q_l  (= inv_punct_q)
+    u64 q_lo, q_hi;       // q = q0*q1 as a 128-bit integer
+    u64 qhalf_lo, qhalf_hi;  // (q-1)/2
+
     // ---- plain ops (multiply_add_plain_with_scaling_variant, multiply_plain_normal)
     u64 delta_mod_q[2];       // floor(q/t) mod q_l
     u64 q_mod_t;              // q mod t

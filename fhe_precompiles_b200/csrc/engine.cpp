@@ -94,9 +94,8 @@ void Engine::release_lane(Lane *l) {
 }
 
 // ---------------------------------------------------------------- key cache
-int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin) {
+KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
     const uint64_t tag = cheap_tag(pk);
-    std::lock_guard<std::mutex> lk(key_mu_);
     KeyEntry *hit = nullptr;
     for (auto &e : keys_)
         if (e->tag == tag && e->bytes.size() == pk.n && memcmp(e->bytes.data(), pk.p, pk.n) == 0) {
@@ -106,28 +105,42 @@ int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_
     if (!hit) {
         std::unique_ptr<KeyEntry> e(new KeyEntry());
         e->rk.resize(kRkWords);
-        int32_t rc = decode_public_key(pk, nullptr, e->rk.data(), &e->has_relin);
-        if (rc) return rc;
+        e->pk.resize(kPkWords);
+        *rc = decode_public_key(pk, e->pk.data(), e->rk.data(), &e->has_relin);
+        if (*rc) return nullptr;
         e->bytes.assign(pk.p, pk.p + pk.n);
         e->tag = tag;
         e->d_rk.assign((size_t)n_devices_, nullptr);
+        e->d_pk.assign((size_t)n_devices_, nullptr);
         const size_t cap = env_size("FHE_B200_KEY_CACHE", 8);
         if (keys_.size() >= cap) {  // evict least recently used
             size_t victim = 0;
             for (size_t i = 1; i < keys_.size(); i++)
                 if (keys_[i]->last_use < keys_[victim]->last_use) victim = i;
-            for (int d = 0; d < n_devices_; d++)
-                if (keys_[victim]->d_rk[(size_t)d]) {
-                    cudaSetDevice(d);
-                    cudaDeviceSynchronize();
-                    cudaFree(keys_[victim]->d_rk[(size_t)d]);
-                }
+            for (int d = 0; d < n_devices_; d++) {
+                uint64_t *ptrs[2] = {keys_[victim]->d_rk[(size_t)d], keys_[victim]->d_pk[(size_t)d]};
+                for (uint64_t *ptr : ptrs)
+                    if (ptr) {
+                        cudaSetDevice(d);
+                        cudaDeviceSynchronize();
+                        cudaFree(ptr);
+                    }
+            }
             keys_.erase(keys_.begin() + (long)victim);
         }
         keys_.push_back(std::move(e));
         hit = keys_.back().get();
     }
     hit->last_use = ++key_clock_;
+    *rc = kOk;
+    return hit;
+}
+
+int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin) {
+    std::lock_guard<std::mutex> lk(key_mu_);
+    int32_t rc = kOk;
+    KeyEntry *hit = find_or_parse_key(pk, &rc);
+    if (!hit) return rc;
     if (!need_relin) {
         if (d_rk) *d_rk = nullptr;
         return kOk;
@@ -141,6 +154,35 @@ int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_
     }
     *d_rk = slot;
     return kOk;
+}
+
+int32_t Engine::public_key(Span pk, int device, const uint64_t **d_pk) {
+    std::lock_guard<std::mutex> lk(key_mu_);
+    int32_t rc = kOk;
+    KeyEntry *hit = find_or_parse_key(pk, &rc);
+    if (!hit) return rc;
+    uint64_t *&slot = hit->d_pk[(size_t)device];
+    if (!slot) {
+        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+        cuda_throw(cudaMalloc((void **)&slot, kPkWords * 8), "cudaMalloc(pk)");
+        cuda_throw(cudaMemcpy(slot, hit->pk.data(), kPkWords * 8, cudaMemcpyHostToDevice), "upload pk");
+    }
+    *d_pk = slot;
+    return kOk;
+}
+
+const uint64_t *Engine::network_sk(int device, Span net_pri) {
+    std::lock_guard<std::mutex> lk(sk_mu_);
+    if (d_net_sk_.size() < (size_t)n_devices_) d_net_sk_.assign((size_t)n_devices_, nullptr);
+    uint64_t *&slot = d_net_sk_[(size_t)device];
+    if (!slot) {
+        std::vector<uint64_t> sk(3 * kN);
+        if (decode_private_key(net_pri, sk.data()) != kOk) throw std::runtime_error("fhe_b200: embedded network private key is corrupt");
+        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+        cuda_throw(cudaMalloc((void **)&slot, sk.size() * 8), "cudaMalloc(sk)");
+        cuda_throw(cudaMemcpy(slot, sk.data(), sk.size() * 8, cudaMemcpyHostToDevice), "upload sk");
+    }
+    return slot;
 }
 
 // ---------------------------------------------------------------- scratch arenas
@@ -371,9 +413,135 @@ int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<ui
     return encode_ciphertext(va, lane->h_out, out);
 }
 
-// ---------------------------------------------------------------- threshold API (placeholders until K11 lands)
-int32_t Engine::encrypt(Kind, Span, Span, Span, std::vector<uint8_t> *) { return kErrFailedEncryption; }
-int32_t Engine::reencrypt(Kind, Span, Span, Span, std::vector<uint8_t> *) { return kErrFailedEncryption; }
-int32_t Engine::decrypt(Kind, Span, Span, Span, std::vector<uint8_t> *) { return kErrFailedDecryption; }
+// ---------------------------------------------------------------- device-resident encrypt / decrypt
+void Engine::encrypt_device(int device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
+                            cudaStream_t s) {
+    device_context(device);
+    const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
+    uint64_t *encbuf = scratch(device, chunk);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t c = n - off < chunk ? n - off : chunk;
+        cuda_throw(launch_encrypt(pk, plain + off * kN, seeds + off, encbuf, ct + off * kCtWords, c, s), "encrypt");
+    }
+}
+void Engine::decrypt_device(int device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, cudaStream_t s) {
+    device_context(device);
+    const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
+    uint64_t *xbuf = scratch(device, chunk);
+    for (size_t off = 0; off < n; off += chunk) {
+        const size_t c = n - off < chunk ? n - off : chunk;
+        cuda_throw(launch_decrypt(ct + off * kCtWords, sk, xbuf, plain + off * kN, c, s), "decrypt");
+    }
+}
+
+// ---------------------------------------------------------------- threshold-network simulation API (fhe.rs:594-779)
+namespace {
+// the reference's private 512-bit constant mixed into the encrypt seed (fhe.rs:604-609)
+const uint8_t kSeedConstant[64] = {15,  17,  225, 5,   30,  1,   237, 218, 130, 19,  37,  95,  222, 218, 244, 172,
+                                   214, 175, 175, 110, 173, 103, 172, 60,  43,  76,  40,  150, 215, 96,  23,  78,
+                                   22,  39,  30,  177, 107, 130, 124, 109, 27,  96,  206, 125, 104, 241, 10,  40,
+                                   88,  238, 117, 118, 79,  113, 213, 110, 148, 179, 53,  19,  227, 154, 151, 122};
+uint64_t seed_from_hash(const std::vector<uint8_t> &msg) {
+    uint8_t h[64];
+    sha512(msg.data(), msg.size(), h);
+    uint64_t s = 0;  // first of the eight little-endian u64 words the reference hands to SEAL (fhe.rs:47-54)
+    memcpy(&s, h, 8);
+    return s;
+}
+const char *type_name_of(Kind k) {
+    switch (k) {
+        case Kind::I64: return "sunscreen::types::bfv::signed::Signed,0.8.1,true";
+        case Kind::U64: return "sunscreen::types::bfv::unsigned::Unsigned<1>,0.8.1,true";
+        case Kind::U256: return "sunscreen::types::bfv::unsigned::Unsigned<4>,0.8.1,true";
+        default: return "sunscreen::types::bfv::fractional::Fractional<64>,0.8.1,true";
+    }
+}
+void testnet_params(uint8_t out[kParamsBytes]) {
+    uint64_t w[6] = {(uint64_t)kN, 3, kModulus[MQ0], kModulus[MQ1], kModulus[MP], kT};
+    memcpy(out, w, 48);
+    memset(out + 48, 0, 8);
+}
+}  // namespace
+
+// encrypts the scalar operand `scalar` under `pk_bytes` with `seed`; uses the lane's plain / out buffers
+int32_t Engine::encrypt_plain(Kind kind, const uint16_t *, Span scalar, Span pk_bytes, uint64_t seed, CipherView *view, Lane *lane,
+                              std::vector<uint8_t> *out) {
+    int32_t rc = encode_scalar(kind, scalar, lane->h_plain);
+    if (rc) return rc == kErrSunscreen ? kErrFailedEncryption : rc;
+    const uint64_t *d_pk = nullptr;
+    rc = public_key(pk_bytes, lane->device, &d_pk);
+    if (rc) return rc;
+    cudaStream_t s = lane->stream;
+    lane->h_b[0] = seed;
+    cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
+    cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, 8, cudaMemcpyHostToDevice, s), "H2D seed");
+    cuda_throw(launch_encrypt(d_pk, lane->d_plain, lane->d_b, lane->d_scratch, lane->d_out, 1, s), "encrypt");
+    cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    return encode_ciphertext(*view, lane->h_out, out);
+}
+
+int32_t Engine::encrypt(Kind kind, Span in, Span net_pub, Span, std::vector<uint8_t> *out) {
+    Span plain, public_data;
+    int32_t rc = unpack_two_arguments(in, &plain, &public_data);
+    if (rc) return rc;
+    // seed = SHA-512(public_data || constant || plain bytes)   (fhe.rs:600-611)
+    std::vector<uint8_t> msg(public_data.p, public_data.p + public_data.n);
+    msg.insert(msg.end(), kSeedConstant, kSeedConstant + 64);
+    msg.insert(msg.end(), plain.p, plain.p + plain.n);
+    Lane *lane = acquire_lane();
+    LaneGuard guard{this, lane, &Engine::release_lane};
+    cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
+    CipherView view;
+    view.data_type = type_name_of(kind);
+    testnet_params(view.params);
+    return encrypt_plain(kind, nullptr, plain, net_pub, seed_from_hash(msg), &view, lane, out);
+}
+
+int32_t Engine::decrypt(Kind kind, Span in, Span, Span net_pri, std::vector<uint8_t> *out) {
+    Lane *lane = acquire_lane();
+    LaneGuard guard{this, lane, &Engine::release_lane};
+    cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
+    CipherView view;
+    int32_t rc = decode_ciphertext(in, &view, lane->h_a);
+    if (rc) return rc == kErrSunscreen ? kErrFailedDecryption : rc;
+    if (!data_type_matches(view.data_type, kind)) return kErrFailedDecryption;  // fhe.rs:696 map_err
+    const uint64_t *d_sk = network_sk(lane->device, net_pri);
+    cudaStream_t s = lane->stream;
+    cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D ct");
+    cuda_throw(launch_decrypt(lane->d_a, d_sk, lane->d_scratch, lane->d_plain, 1, s), "decrypt");
+    cuda_throw(cudaMemcpyAsync(lane->h_plain, lane->d_plain, kN * 2, cudaMemcpyDeviceToHost, s), "D2H plain");
+    cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    decode_scalar(kind, lane->h_plain, kN, out);
+    return kOk;
+}
+
+int32_t Engine::reencrypt(Kind kind, Span in, Span, Span net_pri, std::vector<uint8_t> *out) {
+    Span pk, ct, public_data;
+    int32_t rc = unpack_binary_operation(in, &pk, &ct, &public_data);
+    if (rc) return rc;
+    Lane *lane = acquire_lane();
+    LaneGuard guard{this, lane, &Engine::release_lane};
+    cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
+    // reference order: key, ciphertext, public data are all deserialised first (pack.rs:261-263)
+    const uint64_t *d_pk = nullptr;
+    if ((rc = public_key(pk, lane->device, &d_pk))) return rc;
+    CipherView view;
+    if ((rc = decode_ciphertext(ct, &view, lane->h_a))) return rc == kErrSunscreen ? kErrFailedDecryption : rc;
+    if (!data_type_matches(view.data_type, kind)) return kErrFailedDecryption;
+    const uint64_t *d_sk = network_sk(lane->device, net_pri);
+    cudaStream_t s = lane->stream;
+    cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D ct");
+    cuda_throw(launch_decrypt(lane->d_a, d_sk, lane->d_scratch, lane->d_plain, 1, s), "decrypt");
+    cuda_throw(cudaMemcpyAsync(lane->h_plain, lane->d_plain, kN * 2, cudaMemcpyDeviceToHost, s), "D2H plain");
+    cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    std::vector<uint8_t> scalar;
+    decode_scalar(kind, lane->h_plain, kN, &scalar);
+    // seed = SHA-512(public_data || whole input || plain bytes)   (fhe.rs:676, 646-649)
+    std::vector<uint8_t> msg(public_data.p, public_data.p + public_data.n);
+    msg.insert(msg.end(), in.p, in.p + in.n);
+    msg.insert(msg.end(), scalar.begin(), scalar.end());
+    return encrypt_plain(kind, nullptr, Span{scalar.data(), scalar.size()}, pk, seed_from_hash(msg), &view, lane, out);
+}
 
 }  // namespace fheb

@@ -43,7 +43,9 @@ struct KeyEntry {
     uint64_t tag = 0;            // cheap pre-filter
     bool has_relin = false;
     std::vector<uint64_t> rk;    // host copy [2][2][3][N]
+    std::vector<uint64_t> pk;    // host copy [2][3][N]
     std::vector<uint64_t *> d_rk;  // per device, lazily uploaded
+    std::vector<uint64_t *> d_pk;
     uint64_t last_use = 0;
 };
 
@@ -83,6 +85,12 @@ class Engine {
 
     // relin key for the PublicKey bytes, parsed + validated once and cached by content
     int32_t relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin);
+    // encryption key [2][3][N] on `device` for the PublicKey bytes (same cache)
+    int32_t public_key(Span pk, int device, const uint64_t **d_pk);
+    // device-resident batched encrypt / decrypt (pointers on `device`)
+    void encrypt_device(int device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
+                        cudaStream_t s);
+    void decrypt_device(int device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, cudaStream_t s);
 
    private:
     Engine();
@@ -96,6 +104,12 @@ class Engine {
     std::condition_variable lane_cv_;
     size_t next_lane_ = 0;
 
+    KeyEntry *find_or_parse_key(Span pk, int32_t *rc);  // key_mu_ held
+    const uint64_t *network_sk(int device, Span net_pri);
+    int32_t encrypt_plain(Kind kind, const uint16_t *plain_host_unused, Span scalar, Span pk_bytes, uint64_t seed, CipherView *view,
+                          Lane *lane, std::vector<uint8_t> *out);
+    std::vector<uint64_t *> d_net_sk_;
+    std::mutex sk_mu_;
     std::mutex key_mu_;
     std::vector<std::unique_ptr<KeyEntry>> keys_;
     uint64_t key_clock_ = 0;

@@ -579,6 +579,181 @@ __global__ void __launch_bounds__(256) k_relin_finish(const u64 *__restrict__ c3
 }
 
 // =====================================================================================
+// K11a: decryption   (SEAL Decryptor::bfv_decrypt, size-2 ciphertexts; fhe.rs:688-699)
+//   k_decrypt_dot   : x_l = c0_l + INTT(NTT(c1_l) * s_l)            grid (2 limbs, ops) -> xbuf [op][2][N]
+//   k_decrypt_round : m = round(t * CRT(x_0, x_1) / q) mod t        per coefficient     -> plain [op][N] u16
+// SEAL rounds through the {t, gamma} base conversion; the exact rounding below gives the same plaintext
+// whenever the noise budget is positive.
+// =====================================================================================
+template <int MI>
+__device__ __forceinline__ void decrypt_dot_body(const u64 *__restrict__ ct, const u64 *__restrict__ sk, u64 *__restrict__ x,
+                                                 u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 v[1][8], s[8], c0[8];
+    load_natural(ct + (size_t)(1 * 2 + MI) * kN, v[0], t);
+    ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+    load_chunk8_ldg(sk + (size_t)MI * kN, s, t);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(v[0][r], s[r]);
+    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    load_natural(ct + (size_t)(0 * 2 + MI) * kN, c0, t);
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[0][r] = addmod<M>(v[0][r], c0[r]);
+    store_natural(x + (size_t)MI * kN, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_decrypt_dot(const u64 *__restrict__ ct, const u64 *__restrict__ sk,
+                                                              u64 *__restrict__ xbuf) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    if (blockIdx.x == 0)
+        decrypt_dot_body<MQ0>(ct + op * 4 * kN, sk, xbuf + op * 2 * kN, smem, threadIdx.x);
+    else
+        decrypt_dot_body<MQ1>(ct + op * 4 * kN, sk, xbuf + op * 2 * kN, smem, threadIdx.x);
+}
+__global__ void __launch_bounds__(256) k_decrypt_round(const u64 *__restrict__ xbuf, unsigned short *__restrict__ plain,
+                                                       size_t n_ops) {
+    using Q0 = Mod<MQ0>;
+    using Q1 = Mod<MQ1>;
+    size_t total = n_ops * kN;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    const u64 qlo = kc.q_lo, qhi = kc.q_hi;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        size_t op = g / kN;
+        int i = (int)(g % kN);
+        u64 v0 = shoup<Q0>(xbuf[(op * 2 + 0) * kN + i], kc.crt_inv[0].w, kc.crt_inv[0].ws);
+        u64 v1 = shoup<Q1>(xbuf[(op * 2 + 1) * kN + i], kc.crt_inv[1].w, kc.crt_inv[1].ws);
+        // X = v0*q1 + v1*q0 mod q   (< 2q before the subtraction)
+        u64 lo = 0, hi = 0;
+        mac128(lo, hi, v0, Q1::q);
+        mac128(lo, hi, v1, Q0::q);
+        if (hi > qhi || (hi == qhi && lo >= qlo)) {
+            u64 nl = lo - qlo;
+            hi = hi - qhi - (lo < qlo);
+            lo = nl;
+        }
+        // long division of t*X by q, t = 2^12: 12 shift-subtract steps
+        u32 quo = 0;
+#pragma unroll
+        for (int b = 0; b < kLogT; b++) {
+            hi = (hi << 1) | (lo >> 63);
+            lo <<= 1;
+            bool ge = hi > qhi || (hi == qhi && lo >= qlo);
+            if (ge) {
+                u64 nl = lo - qlo;
+                hi = hi - qhi - (lo < qlo);
+                lo = nl;
+            }
+            quo = (quo << 1) | (ge ? 1u : 0u);
+        }
+        // round to nearest (ties up): floor((tX + (q-1)/2) / q) = quo + [rem + (q-1)/2 >= q]
+        u64 sl = lo + kc.qhalf_lo;
+        u64 sh = hi + kc.qhalf_hi + (sl < lo);
+        if (sh > qhi || (sh == qhi && sl >= qlo)) quo += 1;
+        plain[g] = (unsigned short)(quo & (kT - 1));
+    }
+}
+
+// =====================================================================================
+// K11b: public-key encryption   (SEAL Encryptor::encrypt_zero_asymmetric at the key level +
+//       RNSTool::divide_and_round_q_last_inplace + multiply_add_plain_with_scaling_variant; fhe.rs:594-618)
+// Randomness is a counter-based generator keyed by a caller-supplied 64-bit seed per op: a valid BFV
+// encryption, deterministic in (seed, plaintext, key), NOT SEAL's Blake2xb sampler stream.
+//   k_encrypt_core   : INTT_J(pk_j[J] * NTT_J(u)) + e_j    grid (3 moduli, ops) -> encbuf [op][2][3][N]
+//   k_encrypt_finish : drop P with rounding, add Delta*m   per coefficient      -> ct [op][2][2][N]
+// =====================================================================================
+__device__ __forceinline__ u64 mix64(u64 z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+// ternary secret-like sample in {-1,0,1}, uniform (rejection on 2-bit draws)
+__device__ __forceinline__ int sample_ternary(u64 seed, int i) {
+    u64 r = mix64(seed ^ (0x7465726eull << 32) ^ (u64)i);
+    for (int k = 0; k < 32; k++) {
+        int d = (int)((r >> (2 * k)) & 3);
+        if (d != 3) return d - 1;
+    }
+    return 0;
+}
+// centred binomial error, 21 + 21 bits (sigma ~ 3.24, |e| <= 21) -- SEAL 4.0's default noise shape
+__device__ __forceinline__ int sample_cbd(u64 seed, int poly, int i) {
+    u64 r = mix64(seed ^ ((0x65727200ull + (u64)poly) << 32) ^ (u64)i);
+    return __popcll(r & 0x1fffffull) - __popcll((r >> 21) & 0x1fffffull);
+}
+template <int MI>
+__device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, u64 seed, u64 *__restrict__ enc, u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 v[1][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        int u = sample_ternary(seed, r * kThreads + t);
+        v[0][r] = u < 0 ? M::q - 1 : (u64)u;
+    }
+    ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+    u64 w[2][8];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        u64 k[8];
+        load_chunk8_ldg(pk + (size_t)(j * 3 + MI) * kN, k, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) w[j][r] = mulmod<M>(v[0][r], k[r]);
+    }
+    ntt_inverse<M, 2>(w, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            int e = sample_cbd(seed, j, r * kThreads + t);
+            u64 ev = e < 0 ? M::q - (u64)(-e) : (u64)e;
+            w[j][r] = addmod<M>(w[j][r], ev);
+        }
+        store_natural(enc + (size_t)(j * 3 + MI) * kN, w[j], t);
+    }
+}
+__global__ void __launch_bounds__(kThreads, 1) k_encrypt_core(const u64 *__restrict__ pk, const u64 *__restrict__ seeds,
+                                                               u64 *__restrict__ encbuf) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const u64 seed = seeds[op];
+    u64 *enc = encbuf + op * 6 * kN;
+    switch (blockIdx.x) {
+        case 0: encrypt_core_body<MQ0>(pk, seed, enc, smem, threadIdx.x); break;
+        case 1: encrypt_core_body<MQ1>(pk, seed, enc, smem, threadIdx.x); break;
+        default: encrypt_core_body<MP>(pk, seed, enc, smem, threadIdx.x); break;
+    }
+}
+__global__ void __launch_bounds__(256) k_encrypt_finish(const u64 *__restrict__ encbuf, const unsigned short *__restrict__ plain,
+                                                        u64 *__restrict__ ct, size_t n_ops) {
+    using Q0 = Mod<MQ0>;
+    using Q1 = Mod<MQ1>;
+    using PP = Mod<MP>;
+    size_t total = n_ops * 2 * kN;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        size_t op = g / (2 * kN);
+        int j = (int)((g / kN) & 1);
+        int i = (int)(g % kN);
+        const u64 *pe = encbuf + (op * 2 + j) * 3 * kN + i;
+        u64 *po = ct + (op * 2 + j) * 2 * kN + i;
+        u64 last = csub<PP>(pe[2 * kN] + kc.half_P, PP::q);
+        u64 m = (j == 0) ? plain[op * kN + i] : 0;
+        {
+            u64 tl = submod<Q0>(reduce64<Q0>(last), kc.half_P_mod_q[0]);
+            u64 v = shoup<Q0>(submod<Q0>(pe[0], tl), kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws);
+            if (j == 0) v = addmod<Q0>(v, plain_scaled<Q0>(m, 0));
+            po[0] = v;
+        }
+        {
+            u64 tl = submod<Q1>(reduce64<Q1>(last), kc.half_P_mod_q[1]);
+            u64 v = shoup<Q1>(submod<Q1>(pe[kN], tl), kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws);
+            if (j == 0) v = addmod<Q1>(v, plain_scaled<Q1>(m, 1));
+            po[kN] = v;
+        }
+    }
+}
+
+// =====================================================================================
 // integer-pipe peak microbenchmark (roofline denominator for the multiply kernels; not on the hot path)
 // 16 independent mad chains per thread; WIDE: mad.wide.u32 (32x32+64 -> 64), else mad.lo.u32
 // =====================================================================================
@@ -716,6 +891,8 @@ cudaError_t kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_behz_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_encrypt_core, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_relin_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
     return cudaSuccess;
@@ -801,6 +978,21 @@ cudaError_t launch_ks_intt(const u64 *dig, const u64 *rk, u64 *ks, size_t n_ops,
     if (n_ops == 0) return cudaSuccess;
     k_ks_intt<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(dig, rk, ks);
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_decrypt_dot<<<dim3(2, (unsigned)n_ops), kThreads, kSmem1, s>>>(ct, sk, xbuf);
+    k_decrypt_round<<<eltwise_grid(n_ops * kN, 256), 256, 0, s>>>(xbuf, plain, n_ops);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64 *seeds, u64 *encbuf, u64 *ct, size_t n_ops,
+                           cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_encrypt_core<<<dim3(3, (unsigned)n_ops), kThreads, kSmem2, s>>>(pk, seeds, encbuf);
+    k_encrypt_finish<<<eltwise_grid(n_ops * 2 * kN, 256), 256, 0, s>>>(encbuf, plain, ct, n_ops);
+    g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {

@@ -12,6 +12,7 @@ typedef unsigned int u32;
 constexpr int kLogN = 12;
 constexpr int kN = 1 << kLogN;
 constexpr u64 kT = 4096;  // plain modulus
+constexpr int kLogT = 12;
 
 // modulus indices
 enum : int { MQ0 = 0, MQ1 = 1, MP = 2, MB0 = 3, MB1 = 4, MSK = 5, kNumMod = 6 };

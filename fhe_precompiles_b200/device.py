@@ -176,3 +176,24 @@ def bfly_peak(device: int = 0, mod: int = 0) -> float:
 def set_fused(on: bool) -> None:
     """Select the multi-polynomial-per-CTA kernels (True) or the one-polynomial-per-CTA kernels (False, default)."""
     _lib.lib().fhe_b200_set_fused(int(on))
+
+
+def encrypt(pk: torch.Tensor, plain: torch.Tensor, seeds: torch.Tensor) -> torch.Tensor:
+    """pk [2,3,4096] int64, plain [n,4096] int16, seeds [n] int64 (all on one CUDA device) -> ct [n,2,2,4096]."""
+    dev = _dev(pk)
+    _dev(plain)
+    _dev(seeds)
+    n = plain.shape[0]
+    assert plain.dtype == torch.int16 and seeds.dtype == torch.int64 and seeds.numel() == n
+    ct = torch.empty((n, 2, 2, N), dtype=torch.int64, device=pk.device)
+    _check(_lib.lib().fhe_b200_encrypt(dev, pk.data_ptr(), plain.data_ptr(), seeds.data_ptr(), ct.data_ptr(), n, _stream(dev)))
+    return ct
+
+
+def decrypt(ct: torch.Tensor, sk: torch.Tensor) -> torch.Tensor:
+    """ct [n,2,2,4096], sk [>=2,4096] int64 (NTT form) -> plaintext coefficients [n,4096] int16."""
+    dev = _dev(ct)
+    _dev(sk)
+    plain = torch.empty((ct.shape[0], N), dtype=torch.int16, device=ct.device)
+    _check(_lib.lib().fhe_b200_decrypt(dev, ct.data_ptr(), sk.data_ptr(), plain.data_ptr(), ct.shape[0], _stream(dev)))
+    return plain

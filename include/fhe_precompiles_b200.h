@@ -136,6 +136,12 @@ int32_t fhe_b200_multiply(int32_t device, const uint64_t *a, const uint64_t *b, 
 int32_t fhe_b200_relinearize(int32_t device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, void *stream);
 int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
                            size_t n, void *stream);
+/* Public-key encryption of n plaintexts (uint16 [n][4096]) under pk [2][3][4096] (NTT form, key level) with one
+ * 64-bit seed per op: a valid BFV encryption, deterministic in (seed, plaintext, key); the sampler stream is this
+ * library's own, not SEAL's. Decryption of n size-2 ciphertexts with sk [>=2 limbs][4096] (NTT form) -> plaintexts. */
+int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
+                         void *stream);
+int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, void *stream);
 /* Same op on HOST buffers (pin them for full PCIe rate): copies in, computes and copies out chunk by chunk with
  * the three phases of consecutive chunks overlapped; returns when `out` is complete. rk: host words. */
 int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,

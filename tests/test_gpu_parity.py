@@ -223,3 +223,94 @@ def test_batch_surface(keys):
     assert [r[0] for r in res[:-1]] == [0] * 12 and res[-1][0] == 1
     for (st, out), want in zip(res[:-1], wants):
         assert out == want
+
+
+# ---------------------------------------------------------------- encrypt / decrypt (config 5, threshold API)
+def test_device_decrypt_matches_oracle(dev, keys):
+    import torch
+
+    rng = np.random.default_rng(21)
+    vals = [int(v) for v in rng.integers(-(2**40), 2**40, size=24)]
+    cts = np.stack([encrypt_value(keys, "i64", v, 300 + i) for i, v in enumerate(vals)])
+    prod = np.stack([bfv.mul_relin(cts[i], cts[(i + 1) % len(cts)], keys.rk) for i in range(4)])  # noisier inputs too
+    allct = np.concatenate([cts, prod])
+    plain = dev.decrypt(to_dev(allct), to_dev(keys.sk)).cpu().numpy().view(np.uint16)
+    for i, ct in enumerate(allct):
+        want, budget = bfv.decrypt(ct, keys.sk)
+        assert budget > 0
+        assert np.array_equal(plain[i].astype(np.uint64), want), f"ciphertext {i}"
+    assert [bfv.decode("i64", p.astype(np.uint64)) for p in plain[: len(vals)]] == vals
+
+
+def test_device_encrypt_roundtrip(dev, keys):
+    """config 5 shape: pk-encrypt random i64 under the network key on the GPU, decrypt with network.pri, all equal;
+    the GPU sampler is the library's own, so the check is decrypt-equality, noise budget and determinism."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    n = 64
+    vals = [int(v) for v in rng.integers(-(2**62), 2**62, size=n)]
+    plains = np.stack([plain_u16("i64", v) for v in vals])
+    seeds = torch.arange(1000, 1000 + n, dtype=torch.int64).cuda()
+    dpl = torch.from_numpy(plains.view(np.int16)).cuda()
+    dpk = to_dev(keys.net_pk)
+    ct = dev.encrypt(dpk, dpl, seeds)
+    ct2 = dev.encrypt(dpk, dpl, seeds)
+    assert torch.equal(ct, ct2), "deterministic in (seed, plaintext, key)"
+    cts = to_np(ct)
+    assert not np.array_equal(cts[0, 1], cts[1, 1]), "different seeds give different randomness"
+    for l in range(2):
+        assert (cts[:, :, l, :] < MODULI[l]).all()
+    for i in range(n):
+        plain, budget = bfv.decrypt(cts[i], keys.net_sk)
+        assert budget >= 50, f"fresh noise budget {budget}"
+        assert bfv.decode("i64", plain) == vals[i]
+    # GPU decrypt agrees
+    got = dev.decrypt(ct, to_dev(keys.net_sk)).cpu().numpy().view(np.uint16)
+    assert np.array_equal(got[:, :64], plains[:, :64]) and not got[:, 64:].any()
+    # and the ciphertexts multiply correctly under the network relin keys
+    prod = to_np(dev.mul_relin(ct[:8], ct[8:16], to_dev(keys.net_rk)))
+    for i in range(8):
+        assert bfv.decode("i64", bfv.decrypt(prod[i], keys.net_sk)[0]) == (vals[i] * vals[8 + i] + 2**63) % 2**64 - 2**63
+
+
+@pytest.mark.parametrize("kind,value", [("u256", 12), ("u64", 12), ("i64", 12), ("frac64", 12.0), ("i64", -7), ("frac64", -2.75),
+                                        ("u256", 2**200 + 5), ("u64", 2**64 - 1)])
+def test_threshold_api_roundtrip(keys, kind, value):
+    """fhe.rs:2248-2303 fhe_decrypt_test: encrypt -> decrypt round trip for all four types (value 12), plus edge values."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    ser = pack.SERIALIZE[kind](value)
+    enc = getattr(FHE, f"encrypt_{kind}")(pack.pack_two_arguments(ser, bytes([1, 2, 3])))
+    assert getattr(FHE, f"encrypt_{kind}")(pack.pack_two_arguments(ser, bytes([1, 2, 3]))) == enc  # deterministic
+    assert getattr(FHE, f"encrypt_{kind}")(pack.pack_two_arguments(ser, bytes([1, 2, 4]))) != enc  # seed depends on public data
+    ct = F.Ciphertext.from_bytes(enc)
+    assert decrypt_value(keys, kind, ct.polys(), network=True) == value_of(kind, value)
+    dec = getattr(FHE, f"decrypt_{kind}")(pack.pack_one_argument(enc))
+    assert pack.deserialize_scalar(kind, dec) == value_of(kind, value)
+
+
+def test_encrypt_same_seed_and_value_works(keys):
+    """fhe.rs:2124-2140: two identical encrypts subtract to a transparent ciphertext that decrypts to 0."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    inp = pack.pack_two_arguments(pack.serialize_u256(16), bytes([1, 2, 3, 4]))
+    a, b = FHE.encrypt_u256(inp), FHE.encrypt_u256(inp)
+    out = FHE.sub_cipheru256_cipheru256(pack.pack_binary_operation(keys.net_pub_bytes, a, b))
+    assert pack.deserialize_scalar("u256", FHE.decrypt_u256(out)) == 0
+
+
+def test_reencrypt(keys):
+    """fhe.rs:2143-2245 fhe_refresh_test / fhe_reencrypt_test without the SEAL-PRNG-dependent SHA-512 KATs:
+    encrypt under the network key, reencrypt to tests/data/public_key.bin, decrypt with tests/data/private_key.bin."""
+    from fhe_precompiles_b200 import FHE, FheError, pack
+
+    enc = FHE.encrypt_u256(pack.pack_two_arguments(pack.serialize_u256(12), bytes([1, 2, 3])))
+    re = FHE.reencrypt_u256(pack.pack_binary_operation(keys.pub_bytes, enc, bytes([1, 2, 3])))
+    assert decrypt_value(keys, "u256", F.Ciphertext.from_bytes(re).polys()) == 12
+    re_net = FHE.reencrypt_u256(pack.pack_binary_operation(keys.net_pub_bytes, enc, bytes([1, 2, 3])))
+    assert pack.deserialize_scalar("u256", FHE.decrypt_u256(re_net)) == 12
+    assert FHE.public_key_bytes() == keys.net_pub_bytes
+    with pytest.raises(FheError) as e:
+        FHE.decrypt_i64(enc)  # a u256 ciphertext is not an i64 ciphertext
+    assert e.value.code == 5
