@@ -1,0 +1,93 @@
+"""The C-ABI shared library loads and exports every symbol include/fhe_precompiles_b200.h declares; without a GPU
+every compute entry point fails loudly (there is no CPU fallback).  CPU only."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from helpers import ROOT
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fhe_precompiles_b200 import _lib
+
+    return _lib.lib()
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include/fhe_precompiles_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"FHE_PRECOMPILE\((\w+)\);", hdr))
+    syms = {"c_fhe_" + n for n in names}
+    syms |= set(re.findall(r"\b(fhe_b200_\w+|fhe_free|fhe_error)\s*\(", hdr))
+    syms.discard("fhe_b200_call")
+    return syms
+
+
+def test_reference_surface_is_complete(lib):
+    from fhe_precompiles_b200 import _lib
+
+    # the 49 names of c_fhe.rs:74-141 + fhe_free + fhe_error
+    assert len(_lib.PRECOMPILES) == 49 and len(set(_lib.PRECOMPILES)) == 49
+    ref = open(os.path.join(ROOT, "tests/data/c_fhe_symbols.txt")).read().split()
+    assert sorted(ref) == sorted(_lib.PRECOMPILES)
+    for n in _lib.PRECOMPILES:
+        assert hasattr(lib, "c_fhe_" + n)
+
+
+def test_every_declared_symbol_is_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 51 + 20
+    missing = [s for s in sorted(syms) if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_error_strings_match_lib_rs(lib):
+    want = {1: "Unexpected end of file", 2: "Platform architecture invalid", 3: "Invalid encoding", 4: "Overflow in FHE program",
+            5: "Invalid decryption", 6: "Invalid encryption", 7: "Base sunscreen error", 0: "Unknown error", 99: "Unknown error"}
+    for code, msg in want.items():
+        assert lib.fhe_error(code).decode() == msg
+
+
+def test_op_table(lib):
+    from fhe_precompiles_b200 import _lib
+
+    for n in _lib.PRECOMPILES:
+        idx = lib.fhe_b200_op_index(n.encode())
+        assert idx >= 0 and lib.fhe_b200_op_name(idx).decode() == n
+    assert lib.fhe_b200_op_index(b"nope") == -1
+
+
+def test_public_key_bytes_needs_no_gpu(lib):
+    from fhe_precompiles_b200 import FHE
+
+    assert FHE.public_key_bytes() == open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read()
+
+
+def test_no_cpu_fallback():
+    """On a box without a CUDA device the product path must fail loudly, never compute on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    from fhe_precompiles_b200 import FHE, FheError, _lib
+
+    with pytest.raises(FheError) as e:
+        FHE.add_cipheri64_cipheri64(b"\x00" * 16)
+    assert e.value.code == 7 and "no CPU fallback" in str(e.value)
+    assert _lib.lib().fhe_b200_init(0) == -1
+    from fhe_precompiles_b200 import device
+
+    with pytest.raises(RuntimeError):
+        device.add(torch.zeros((1, 2, 2, 4096), dtype=torch.int64), torch.zeros((1, 2, 2, 4096), dtype=torch.int64))
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "fhe_precompiles_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in text and "from oracle" not in text and "bfv_oracle" not in text, f
