@@ -242,11 +242,10 @@ def main() -> None:
     fdev.set_kernel_timing(False)
     clocks = sampler.stop()
     barrier()
-    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max = float(t_ms.item())
-    value = world * n * args.steps / (ms_max * 1e-3)
+    from fhe_precompiles_b200.sharding import max_over_ranks, whole_job_rate
+
+    ms_max = max_over_ranks(ms, dist, dev)
+    value = whole_job_rate(n * args.steps, world, ms_max * 1e-3)
 
     # ---------------- end to end through the C ABI with host buffers
     e2e = None
@@ -263,10 +262,7 @@ def main() -> None:
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        dt_max = float(t_e.item())
+        dt_max = max_over_ranks(dt, dist, dev)
         same = bool(torch.equal(out_h, out.cpu()))
         e2e = {
             "value": world * n * args.steps / dt_max,
@@ -290,6 +286,14 @@ def main() -> None:
     ops_per_launch = n * args.steps / max(dom_launches, 1)
     avg_launch_ms = dom_ms / max(dom_launches, 1)
     achieved = ops_per_launch * ALGO_BYTES_PER_OP / (avg_launch_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per op of each kernel from the committed ncu capture (profiles/), scaled to one launch
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            per_op = json.load(f)["dram_bytes_per_op"].get(dom)
+        if per_op is not None:
+            traffic = per_op * ops_per_launch
+    except Exception:
+        traffic = None
     roofline = {
         "bound": "hbm",
         "kernel": dom,
@@ -297,7 +301,7 @@ def main() -> None:
         "peak": peak_gbs,
         "unit": "GB/s",
         "frac": achieved / peak_gbs,
-        "traffic": None,
+        "traffic": traffic,
         "peak_source": peak_src,
         "avg_launch_ms": avg_launch_ms,
         "ops_per_launch": ops_per_launch,
@@ -306,14 +310,21 @@ def main() -> None:
         "note": "the fused multiply kernels are integer-pipe bound (SURVEY 8d); see int_pipe",
     }
     try:
-        peak_mad = fdev.int_peak(local_rank, wide=True)
-        ach_mad = (n * args.steps / (ms * 1e-3)) * MODMUL_PER_OP * MAD_PER_MODMUL / 1e12
+        peak_mad = fdev.int_peak(local_rank, wide=1)
+        ops_s = n * args.steps / (ms * 1e-3)
+        ach_mad = ops_s * MODMUL_PER_OP * MAD_PER_MODMUL / 1e12
+        # butterfly-rate ceiling: register-only NTT inner loop, per prime class (26 small + 21 large limb-NTTs per op)
+        bf_small, bf_big = fdev.bfly_peak(local_rank, 0), fdev.bfly_peak(local_rank, 3)
+        ntt_floor_us = 24576 * (26 / bf_small + 21 / bf_big) * 1e-3
         int_pipe = {
             "achieved": ach_mad,
             "peak": peak_mad,
             "unit": "T mad.wide.u32/s",
             "frac": ach_mad / peak_mad,
             "model": f"{MODMUL_PER_OP} 64-bit modmul/op x {MAD_PER_MODMUL} 32-bit mads; peak = measured microbenchmark",
+            "butterfly_peak_G_per_s": {"36-37 bit primes": bf_small, "61 bit primes": bf_big},
+            "ntt_only_floor_us_per_op": ntt_floor_us,
+            "frac_of_butterfly_ceiling": ntt_floor_us * 1e-6 * ops_s,
         }
     except Exception as e:  # pragma: no cover
         int_pipe = {"error": str(e)}
@@ -336,7 +347,8 @@ def main() -> None:
             "ops_per_gpu_per_step": n,
             "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
             "sharding": f"{world} rank(s), independent batches, no collective",
-            "chunk_ops": int(os.environ.get("FHE_B200_CHUNK_OPS", "148")),
+            "chunk_ops": int(os.environ.get("FHE_B200_CHUNK_OPS", "2048")),
+            "kernels": "split" if not int(os.environ.get("FHE_B200_FUSED", "0")) else "fused",
         },
         "roofline": roofline,
         "int_pipe": int_pipe,
