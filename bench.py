@@ -116,6 +116,60 @@ def cpu_baseline(a_np, b_np, rk_np, threads: int):
     return a_np.shape[0] / secs, out, secs
 
 
+def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 200) -> dict:
+    """p50 / p99 of one c_fhe_mul_cipheri64_cipheri64 call (warm key cache): packed bytes in, packed bytes out,
+    i.e. bincode + zstd inflate of two ciphertexts, H2D, six kernels, D2H, zstd deflate.  Also times the codec alone."""
+    import ctypes
+
+    import numpy as np
+
+    from fhe_precompiles_b200 import FHE, _lib, pack
+
+    L = _lib.lib()
+    dt = b"sunscreen::types::bfv::signed::Signed,0.8.1,true"
+
+    def to_bytes(t):
+        w = t.cpu().numpy().view(np.uint64).copy()
+        out, n = ctypes.c_void_p(), ctypes.c_int64()
+        assert L.fhe_b200_write_ciphertext(w.ctypes.data, dt, ctypes.byref(out), ctypes.byref(n)) == 0
+        buf = ctypes.string_at(out.value, n.value)
+        L.fhe_free(out)
+        return buf
+
+    ca, cb = to_bytes(a[0]), to_bytes(b[0])
+    packed = pack.pack_binary_operation(net_pub, ca, cb)
+    for _ in range(5):
+        out = FHE.mul_cipheri64_cipheri64(packed)
+    ts = []
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        out = FHE.mul_cipheri64_cipheri64(packed)
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    # codec alone: inflate both operands + deflate one result, same thread
+    words = np.zeros(4 * N, dtype=np.uint64)
+    name = ctypes.create_string_buffer(128)
+    cs = []
+    for _ in range(50):
+        t0 = time.perf_counter()
+        L.fhe_b200_parse_ciphertext(ca, len(ca), words.ctypes.data, name, 128)
+        L.fhe_b200_parse_ciphertext(cb, len(cb), words.ctypes.data, name, 128)
+        o, n = ctypes.c_void_p(), ctypes.c_int64()
+        L.fhe_b200_write_ciphertext(words.ctypes.data, dt, ctypes.byref(o), ctypes.byref(n))
+        L.fhe_free(o)
+        cs.append(time.perf_counter() - t0)
+    cs.sort()
+    return {
+        "api": "c_fhe_mul_cipheri64_cipheri64 (packed bytes in/out, warm key cache)",
+        "calls": calls,
+        "p50_ms": ts[len(ts) // 2] * 1e3,
+        "p99_ms": ts[min(len(ts) - 1, int(len(ts) * 0.99))] * 1e3,
+        "codec_only_p50_ms": cs[len(cs) // 2] * 1e3,
+        "input_bytes": len(packed),
+        "output_bytes": len(out),
+    }
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -278,6 +332,11 @@ def main() -> None:
             dist.destroy_process_group()
         return
 
+    # ---------------- single-call latency through the reference's byte surface (metric: "p50 call latency")
+    latency = None
+    if not args.no_e2e:
+        latency = call_latency(fdev, a, b, local_rank, net_pub)
+
     # ---------------- roofline of the dominant kernel (live CUDA-event durations from the timed region)
     peak_gbs, peak_src = measured_peaks()
     dom = max(kt, key=lambda k: kt[k][0])
@@ -357,6 +416,8 @@ def main() -> None:
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if latency is not None:
+        line["latency"] = latency
 
     # ---------------- CPU baseline on the box's host cores (N=1 only), also the parity checker for the sample
     if world == 1 and not args.no_cpu_baseline:
@@ -366,7 +427,13 @@ def main() -> None:
         b_np = b[:sample].cpu().numpy().view(np.uint64)
         rk_np = rk_host.numpy().view(np.uint64)
         cpu_ops, cpu_out, secs = cpu_baseline(a_np, b_np, rk_np, cores)
+        one = []
+        for i in range(5):
+            _, _, sec1 = cpu_baseline(a_np[i : i + 1], b_np[i : i + 1], rk_np, 1)
+            one.append(sec1)
+        one.sort()
         line["cpu_baseline"] = {
+            "p50_call_ms_arithmetic_only_1_thread": one[len(one) // 2] * 1e3,
             "value": cpu_ops,
             "unit": "ops/s",
             "cores": cores,

@@ -42,6 +42,8 @@ class FheApp:
         """
         L = _lib.lib()
         n = len(calls)
+        if n == 0:
+            return []
         arr = (_lib.BatchCall * n)()
         keep = []
         for i, (name, data) in enumerate(calls):

@@ -1,0 +1,129 @@
+"""The other BASELINE.json configs as measured parity cases (not the contract bench line):
+  config 2: NTT / INTT microbenchmark over the key-level limbs, batch 1..65,536 polynomials
+  config 4: mixed precompile batch (add/sub/mul x ct.ct/ct.pt/pt.ct x 4 types) device-resident, cost-weighted
+  config 5: pk-encrypt of 16,384 plaintexts under the network key + decrypt round trip
+Writes one JSON object to stdout. Run on a B200: python scripts/bench_configs.py"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fhe_precompiles_b200 import device as fdev  # noqa: E402
+
+N = 4096
+MODULI = (0xFFFFEE001, 0xFFFFC4001, 0x1FFFFE0001)
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+def rand_ct(n, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    out = torch.empty((n, 2, 2, N), dtype=torch.int64, device="cuda")
+    for l in range(2):
+        out[:, :, l, :] = torch.randint(0, MODULI[l], (n, 2, N), generator=g, device="cuda", dtype=torch.int64)
+    return out
+
+
+def main():
+    fdev.init(0)
+    res = {}
+    # ---- config 2
+    ntt = []
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    for batch in (1, 4, 16, 64, 256, 1024, 4096, 16384, 65536):
+        x = torch.empty((batch, 3, N), dtype=torch.int64, device="cuda")
+        for l in range(3):
+            x[:, l, :] = torch.randint(0, MODULI[l], (batch, N), generator=g, device="cuda", dtype=torch.int64)
+        f = timeit(lambda: fdev.ntt_(x, [0, 1, 2]))
+        i = timeit(lambda: fdev.ntt_(x, [0, 1, 2], inverse=True))
+        ntt.append({"polys": batch, "limbs": 3 * batch, "fwd_ms": f, "inv_ms": i,
+                    "fwd_Mlimb_per_s": 3 * batch / f / 1e3, "inv_Mlimb_per_s": 3 * batch / i / 1e3,
+                    "fwd_GBps": 3 * batch * 65536 / f / 1e6})
+        del x
+    res["config2_ntt"] = ntt
+    # ---- config 4: 65,536 mixed calls on one GPU (device-resident operands), grouped by kernel family
+    net_pub = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read()
+    pk_h, rk_h = fdev.parse_public_key(net_pub)
+    rk, pk = rk_h.cuda(), pk_h.cuda()
+    rng = np.random.default_rng(3)
+    n_calls = 65536
+    ops = rng.integers(0, 3, n_calls)      # add, sub, mul
+    shapes = rng.integers(0, 3, n_calls)   # ctct, ctpt, ptct
+    counts = {(o, s): int(((ops == o) & (shapes == s)).sum()) for o in range(3) for s in range(3)}
+    pool = 4096
+    a, b = rand_ct(pool, 10), rand_ct(pool, 11)
+    plain = torch.randint(0, 2, (pool, N), device="cuda", dtype=torch.int16)
+    out = torch.empty_like(a)
+
+    def run_family(o, s, n):
+        done = 0
+        while done < n:
+            c = min(pool, n - done)
+            if s == 0:
+                if o == 0:
+                    fdev.add(a[:c], b[:c])
+                elif o == 1:
+                    fdev.sub(a[:c], b[:c])
+                else:
+                    fdev.mul_relin(a[:c], b[:c], rk, out=out[:c])
+            else:
+                if o == 2:
+                    fdev.multiply_plain(a[:c], plain[:c])
+                else:
+                    fdev.plain_addsub(a[:c], plain[:c], 0 if o == 0 else (1 if s == 1 else 3))
+            done += c
+
+    def run_all():
+        for (o, s), n in counts.items():
+            run_family(o, s, n)
+
+    ms = timeit(run_all, iters=3, warm=1)
+    res["config4_mixed"] = {"calls": n_calls, "ms": ms, "calls_per_s": n_calls / ms * 1e3,
+                            "mix": {f"{'add sub mul'.split()[o]}_{'ctct ctpt ptct'.split()[s]}": n for (o, s), n in counts.items()}}
+    # ---- config 5: encrypt 16,384 random i64 under the network key, decrypt, compare
+    n = 16384
+    vals = rng.integers(-(2**62), 2**62, n)
+    mag = np.abs(vals).astype(np.uint64)
+    bits = ((mag[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & 1).astype(np.int64)
+    coeff = np.where(vals[:, None] < 0, bits * 4095, bits)
+    pl = np.zeros((n, N), dtype=np.int16)
+    pl[:, :64] = coeff.astype(np.uint16).view(np.int16)
+    dpl = torch.from_numpy(pl).cuda()
+    seeds = torch.arange(n, dtype=torch.int64, device="cuda") + 7
+    sk = torch.empty((3, N), dtype=torch.int64)
+    from fhe_precompiles_b200 import _lib
+    pri = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pri"), "rb").read()
+    assert _lib.lib().fhe_b200_parse_private_key(pri, len(pri), sk.data_ptr()) == 0
+    dsk = sk.cuda()
+    enc_ms = timeit(lambda: fdev.encrypt(pk, dpl, seeds), iters=3, warm=1)
+    ct = fdev.encrypt(pk, dpl, seeds)
+    dec_ms = timeit(lambda: fdev.decrypt(ct, dsk), iters=3, warm=1)
+    back = fdev.decrypt(ct, dsk)
+    res["config5_encrypt_decrypt"] = {"plaintexts": n, "encrypt_ms": enc_ms, "encrypt_per_s": n / enc_ms * 1e3,
+                                      "decrypt_ms": dec_ms, "decrypt_per_s": n / dec_ms * 1e3,
+                                      "roundtrip_all_equal": bool(torch.equal(back, dpl))}
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()

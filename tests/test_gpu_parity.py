@@ -314,3 +314,49 @@ def test_reencrypt(keys):
     with pytest.raises(FheError) as e:
         FHE.decrypt_i64(enc)  # a u256 ciphertext is not an i64 ciphertext
     assert e.value.code == 5
+
+
+# ---------------------------------------------------------------- full-size, size-independent properties
+def test_full_batch_roundtrip_properties(dev, keys):
+    """BASELINE config 3 size (4,096 ops): encrypt -> multiply+relinearise -> decrypt equals the plaintext products for every
+    op; (a + b) - b == a and a - a == 0 bit-exactly; 64 ops spot-checked bit-exactly against the oracle."""
+    import torch
+
+    n = 4096
+    rng = np.random.default_rng(2)
+    va = rng.integers(-(2**15), 2**15, n)
+    vb = rng.integers(-(2**15), 2**15, n)
+
+    def plains(vals):
+        mag = np.abs(vals).astype(np.uint64)
+        bits = ((mag[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & 1).astype(np.int64)
+        out = np.zeros((len(vals), N), dtype=np.int16)
+        out[:, :64] = np.where(vals[:, None] < 0, bits * 4095, bits).astype(np.uint16).view(np.int16)
+        return torch.from_numpy(out).cuda()
+
+    pk, rk, sk = to_dev(keys.net_pk), to_dev(keys.net_rk), to_dev(keys.net_sk)
+    a = dev.encrypt(pk, plains(va), torch.arange(n, dtype=torch.int64).cuda())
+    b = dev.encrypt(pk, plains(vb), torch.arange(n, 2 * n, dtype=torch.int64).cuda())
+    prod = dev.mul_relin(a, b, rk)
+    dec = dev.decrypt(prod, sk).cpu().numpy().view(np.uint16).astype(np.int64)
+    dec = np.where(dec >= 2048, dec - 4096, dec)  # centred coefficients; value = sum c_i 2^i
+    got = (dec[:, :64] * (1 << np.arange(64, dtype=np.int64))[None, :]).sum(axis=1)  # products < 2^31: no wrap
+    assert np.array_equal(got, va * vb)
+    s = dev.add(a, b)
+    assert torch.equal(dev.sub(s, b), a)
+    assert not dev.sub(a, a).any()
+    assert torch.equal(dev.negate(dev.negate(a)), a)
+    an, bn, pn = to_np(a), to_np(b), to_np(prod)
+    for i in range(0, n, 64):
+        assert np.array_equal(pn[i], bfv.mul_relin(an[i], bn[i], keys.net_rk)), f"op {i}"
+
+
+def test_empty_batches(dev, keys):
+    import torch
+
+    e = torch.empty((0, 2, 2, N), dtype=torch.int64, device="cuda")
+    rk = to_dev(keys.rk)
+    assert dev.add(e, e).shape[0] == 0 and dev.mul_relin(e, e, rk).shape[0] == 0 and dev.multiply(e, e).shape[0] == 0
+    from fhe_precompiles_b200 import FHE
+
+    assert FHE.run_batch([]) == []
