@@ -159,7 +159,17 @@ def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 200
         L.fhe_free(o)
         cs.append(time.perf_counter() - t0)
     cs.sort()
+    # throughput of the same call through fhe_b200_batch (codec on all host threads, GPU lanes shared)
+    nb = 64 * max(1, (os.cpu_count() or 1) // 8)
+    batch_calls = [("mul_cipheri64_cipheri64", packed)] * nb
+    FHE.run_batch(batch_calls[: min(nb, 32)])
+    t0 = time.perf_counter()
+    res = FHE.run_batch(batch_calls)
+    bt = time.perf_counter() - t0
+    assert all(st == 0 for st, _ in res) and res[0][1] == out
     return {
+        "byte_surface_batch": {"calls": nb, "calls_per_s": nb / bt, "host_threads": os.cpu_count(),
+                               "api": "fhe_b200_batch (packed bytes; zstd codec on host threads)"},
         "api": "c_fhe_mul_cipheri64_cipheri64 (packed bytes in/out, warm key cache)",
         "calls": calls,
         "p50_ms": ts[len(ts) // 2] * 1e3,

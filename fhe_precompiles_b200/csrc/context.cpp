@@ -383,7 +383,15 @@ DeviceContext &device_context(int device) {
         d.tabs.twf[mi] = (const ulonglong2 *)f;
         d.tabs.twi[mi] = (const ulonglong2 *)i;
     }
-    cuda_check(upload_constants(H.dc, d.tabs), "upload constants");
+    {
+        std::vector<DevTwLow> lo(1);
+        for (int mi = 0; mi < kNumMod; mi++)
+            for (int k = 0; k < 64; k++) {
+                lo[0].f[mi][k] = H.twf[mi][(size_t)k];
+                lo[0].i[mi][k] = H.twi[mi][(size_t)k];
+            }
+        cuda_check(upload_constants(H.dc, d.tabs, lo[0]), "upload constants");
+    }
     cuda_check(kernels_configure(), "kernel attributes");
     d.table_mem = mem;
     d.device = device;

@@ -54,6 +54,13 @@ struct DevConsts {
     u64 upper_half_incr[2];   // q_l - t
 };
 
+// twiddles of the first six stages (table indices 1..63), read through the constant cache: they are
+// CTA-uniform (first pass) or warp-uniform (second pass)
+struct DevTwLow {
+    ulonglong2 f[kNumMod][64];
+    ulonglong2 i[kNumMod][64];
+};
+
 struct DevTables {
     const ulonglong2 *twf[kNumMod];  // [k] = (rp[k], rp[k] Shoup), rp[bitrev(i)] = psi^i
     const ulonglong2 *twi[kNumMod];  // [k] = (rp[k]^-1, Shoup)

@@ -14,6 +14,10 @@
 #include <cstdio>
 
 #include "kernels.h"
+
+namespace fheb {
+__constant__ DevTwLow ktl;  // defined before ntt.cuh, which reads it
+}
 #include "ntt.cuh"
 
 namespace fheb {
@@ -21,8 +25,10 @@ namespace fheb {
 __constant__ DevConsts kc;
 __constant__ DevTables kt;
 
-cudaError_t upload_constants(const DevConsts &c, const DevTables &t) {
+cudaError_t upload_constants(const DevConsts &c, const DevTables &t, const DevTwLow &lo) {
     cudaError_t e = cudaMemcpyToSymbol(kc, &c, sizeof(c));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(ktl, &lo, sizeof(lo));
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(kt, &t, sizeof(t));
 }
@@ -297,7 +303,8 @@ __device__ __forceinline__ void ext_ntt_body(const u64 *__restrict__ ct, int pol
     using M = Mod<MI>;
     u64 v[1][8];
     load_extended<EI>(ct, poly, v[0], t);
-    ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+    // 36-bit limbs stay lazy (< 2^43): the tensor's 128-bit accumulate absorbs it; 61-bit limbs must be canonical
+    ntt_forward<M, 1, !M::kSmall>(v, smem, kt.twf[MI], t);
     store_chunk8(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__ a, const u64 *__restrict__ b,
@@ -493,7 +500,7 @@ __device__ __forceinline__ void digit_ntt_body(const u64 *__restrict__ src, u64 
     using M = Mod<MI>;
     u64 v[1][8];
     load_natural(src, v[0], t);
-    ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+    ntt_forward<M, 1, false>(v, smem, kt.twf[MI], t);  // lazy (< 2^43): the key MAC reduces a 128-bit sum anyway
     store_chunk8(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_digit_ntt(const u64 *__restrict__ c3, u64 *__restrict__ dig) {

@@ -11,7 +11,7 @@ struct LimbMods {
     int mod[kNumMod];    // modulus index of each limb
 };
 
-cudaError_t upload_constants(const DevConsts &c, const DevTables &t);  // to the current device
+cudaError_t upload_constants(const DevConsts &c, const DevTables &t, const DevTwLow &lo);  // to the current device
 cudaError_t kernels_configure();                                       // opt-in shared memory sizes, current device
 
 // data: n_limbs consecutive 4096-word limbs, limb i uses modulus mods.mod[i % mods.n]; in place

@@ -71,14 +71,20 @@ __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     }
 }
 
-__device__ __forceinline__ ulonglong2 ldtw(const ulonglong2 *__restrict__ tw, int i) { return __ldg(tw + i); }
+// twiddle (w, Shoup quotient) number i of modulus M: stages 0..5 (i < 64) come from constant memory (CTA- or
+// warp-uniform addresses), the rest from the L2/L1-resident table through the read-only path
+template <class M, bool kInv, int S0>
+__device__ __forceinline__ ulonglong2 ldtw(const ulonglong2 *__restrict__ tw, int i) {
+    if (S0 <= 3) return kInv ? ktl.i[M::kIndex][i] : ktl.f[M::kIndex][i];
+    return __ldg(tw + i);
+}
 
 // ---------------------------------------------------------------- register radix-8 passes
 // v[p][r]: r = 4*r2 + 2*r1 + r0, r2 <-> index bit 11-S0 (largest gap)
 template <class M, int NP, int S0>
 __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__restrict__ tw, int upper) {
     {
-        ulonglong2 w = ldtw(tw, (1 << S0) + upper);
+        ulonglong2 w = ldtw<M, false, S0>(tw, (1 << S0) + upper);
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
@@ -86,7 +92,7 @@ __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__re
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        ulonglong2 w = ldtw(tw, (2 << S0) + 2 * upper + h);
+        ulonglong2 w = ldtw<M, false, S0>(tw, (2 << S0) + 2 * upper + h);
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
@@ -94,7 +100,7 @@ __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__re
     }
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-        ulonglong2 w = ldtw(tw, (4 << S0) + 4 * upper + h);
+        ulonglong2 w = ldtw<M, false, S0>(tw, (4 << S0) + 4 * upper + h);
 #pragma unroll
         for (int p = 0; p < NP; p++) fwd_bfly<M, S0 + 2>(v[p][2 * h], v[p][2 * h + 1], w.x, w.y);
     }
@@ -105,20 +111,20 @@ template <class M, int NP, int S0, int G0>
 __device__ __forceinline__ void inv_pass(u64 (&v)[NP][8], const ulonglong2 *__restrict__ tw, int upper) {
 #pragma unroll
     for (int h = 0; h < 4; h++) {
-        ulonglong2 w = ldtw(tw, (4 << S0) + 4 * upper + h);
+        ulonglong2 w = ldtw<M, true, S0>(tw, (4 << S0) + 4 * upper + h);
 #pragma unroll
         for (int p = 0; p < NP; p++) inv_bfly<M, G0>(v[p][2 * h], v[p][2 * h + 1], w.x, w.y);
     }
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        ulonglong2 w = ldtw(tw, (2 << S0) + 2 * upper + h);
+        ulonglong2 w = ldtw<M, true, S0>(tw, (2 << S0) + 2 * upper + h);
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
             for (int r = 0; r < 2; r++) inv_bfly<M, G0 + 1>(v[p][4 * h + r], v[p][4 * h + r + 2], w.x, w.y);
     }
     {
-        ulonglong2 w = ldtw(tw, (1 << S0) + upper);
+        ulonglong2 w = ldtw<M, true, S0>(tw, (1 << S0) + upper);
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll

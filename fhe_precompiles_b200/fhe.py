@@ -45,13 +45,15 @@ class FheApp:
         if n == 0:
             return []
         arr = (_lib.BatchCall * n)()
-        keep = []
+        keep = {}
         for i, (name, data) in enumerate(calls):
             idx = L.fhe_b200_op_index(name.encode())
             if idx < 0:
                 raise KeyError(name)
-            buf = (ctypes.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
-            keep.append(buf)
+            buf = keep.get(id(data))  # the same bytes object may back many calls
+            if buf is None:
+                buf = (ctypes.c_char * max(len(data), 1)).from_buffer_copy(data or b"\0")
+                keep[id(data)] = buf
             arr[i].op = idx
             arr[i].bytes = ctypes.cast(buf, ctypes.c_void_p)
             arr[i].bytes_length = len(data)
