@@ -352,7 +352,8 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
 #pragma unroll
         for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(x[r], y[r]);
     }
-    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv_t[MI].w, kc.ninv_t[MI].ws);
+    // outputs stay in [0, 2q): k_floor_sk's Shoup / 128-bit reductions take any such value
+    ntt_inverse<M, 1, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI].w, kc.ninv_t[MI].ws);
     store_natural(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restri
 
 // =====================================================================================
 // K8: fast_floor + fastbconv_sk   (SEAL RNSTool::fast_floor, RNSTool::fastbconv_sk), per coefficient
-//   tens [op][3][5][N] (x t, canonical)  ->  c3 [op][3][2][N]
+//   tens [op][3][5][N] (x t, any representative in [0, 2q))  ->  c3 [op][3][2][N]
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
     using Q0 = Mod<MQ0>;

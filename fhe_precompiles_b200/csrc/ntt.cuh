@@ -180,8 +180,8 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
 
 // Inverse NTT of NP polynomials.
 //  in : v holds NTT values at positions 8*t + r, each < 2q (small primes: < 4q)
-//  out: v holds coefficients r*512 + t, multiplied by (sc, scs) (Shoup pair, e.g. N^-1), in [0, q)
-template <class M, int NP>
+//  out: v holds coefficients r*512 + t, multiplied by (sc, scs) (Shoup pair, e.g. N^-1), in [0, q) ([0, 2q) if !kCanon)
+template <class M, int NP, bool kCanon = true>
 __device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t, u64 sc,
                                             u64 scs) {
     inv_pass<M, NP, 9, 0>(v, tw, pass_upper<9>(t));
@@ -200,7 +200,7 @@ __device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ul
 #pragma unroll
     for (int p = 0; p < NP; p++)
 #pragma unroll
-        for (int r = 0; r < 8; r++) v[p][r] = shoup<M>(v[p][r], sc, scs);
+        for (int r = 0; r < 8; r++) v[p][r] = kCanon ? shoup<M>(v[p][r], sc, scs) : shoup_lazy<M>(v[p][r], sc, scs);
     __syncthreads();
 }
 
