@@ -98,6 +98,24 @@ class ClockSampler(threading.Thread):
         }
 
 
+def bind_to_gpu_numa_node(index: int) -> None:
+    """Pin this rank to the CPUs local to its GPU (NVML affinity) so pinned staging memory is first-touched on the
+    GPU's NUMA node; matters for the host-buffer (e2e) path when 8 ranks share the box."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        local = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        allowed = os.sched_getaffinity(0) & local
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 def synth_ciphertexts(torch, n: int, seed: int, device) -> "torch.Tensor":
     """[n,2,2,4096] int64: uniform residues mod (q0, q1) -- synthetic data-level ciphertexts."""
     g = torch.Generator(device=device)
@@ -262,12 +280,15 @@ def main() -> None:
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bind_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
-        import torch.distributed as dist  # plumbing only: barrier + max-over-ranks of the timing
+        # plumbing only: a barrier and the max-over-ranks of the timing. The path has no data exchange between GPUs,
+        # so no NCCL communicator is created (gloo over loopback carries the two scalars).
+        import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("gloo")
 
     from fhe_precompiles_b200 import device as fdev
 
@@ -308,7 +329,7 @@ def main() -> None:
     barrier()
     from fhe_precompiles_b200.sharding import max_over_ranks, whole_job_rate
 
-    ms_max = max_over_ranks(ms, dist, dev)
+    ms_max = max_over_ranks(ms, dist)
     value = whole_job_rate(n * args.steps, world, ms_max * 1e-3)
 
     # ---------------- end to end through the C ABI with host buffers
@@ -326,7 +347,7 @@ def main() -> None:
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
-        dt_max = max_over_ranks(dt, dist, dev)
+        dt_max = max_over_ranks(dt, dist)
         same = bool(torch.equal(out_h, out.cpu()))
         e2e = {
             "value": world * n * args.steps / dt_max,

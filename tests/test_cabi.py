@@ -91,3 +91,22 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in text and "from oracle" not in text and "bfv_oracle" not in text, f
+
+
+def test_header_is_valid_c(tmp_path):
+    """include/fhe_precompiles_b200.h must be consumable by a plain C compiler (cgo, JNI stubs ...)."""
+    import subprocess
+
+    src = tmp_path / "use.c"
+    src.write_text('#include "fhe_precompiles_b200.h"\nint main(void) { fhe_b200_call c; c.op = 0; return (int)sizeof(c) == 0; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_rust_shim_lists_every_precompile():
+    from fhe_precompiles_b200 import _lib
+
+    text = open(os.path.join(ROOT, "bindings/rust/src/lib.rs")).read()
+    for n in _lib.PRECOMPILES:
+        assert f"fn c_fhe_{n}(" in text and f"pub fn {n}(&self" in text
