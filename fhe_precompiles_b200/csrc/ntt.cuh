@@ -133,20 +133,33 @@ __device__ __forceinline__ void inv_pass(u64 (&v)[NP][8], const ulonglong2 *__re
 }
 
 // ---------------------------------------------------------------- shared-memory exchange
+// swz() is linear over GF(2) and only rewrites index bits 0..3, so the slot of register r is
+//   swz(idx0 ^ (r << LB)) = swz(idx0) ^ swz(r << LB) = (base ^ X_r) + A_r
+// with compile-time X_r (the part inside bits 0..3) and A_r (the rest, carry-free because idx0 is zero there).
+// One base per pass, at most one LOP3 per access, the rest folds into the LDS/STS immediate offset.
+__host__ __device__ constexpr int swz_c(int i) { return i ^ ((i >> 4) & 7) ^ (((i >> 6) & 1) << 3); }
+template <int S0>
+struct PassSlot {
+    static constexpr int LB = 9 - S0;
+    __host__ __device__ static constexpr int x(int r) { return swz_c(r << LB) & 0xF; }
+    __host__ __device__ static constexpr int a(int r) { return swz_c(r << LB) & ~0xF; }
+};
 // smem: NP consecutive 4096-entry buffers
 template <int NP, int S0>
 __device__ __forceinline__ void smem_store(u64 *smem, const u64 (&v)[NP][8], int t) {
+    const int base = swz(elem_index<S0>(t, 0));
 #pragma unroll
     for (int p = 0; p < NP; p++)
 #pragma unroll
-        for (int r = 0; r < 8; r++) smem[p * kN + swz(elem_index<S0>(t, r))] = v[p][r];
+        for (int r = 0; r < 8; r++) smem[p * kN + (base ^ PassSlot<S0>::x(r)) + PassSlot<S0>::a(r)] = v[p][r];
 }
 template <int NP, int S0>
 __device__ __forceinline__ void smem_load(const u64 *smem, u64 (&v)[NP][8], int t) {
+    const int base = swz(elem_index<S0>(t, 0));
 #pragma unroll
     for (int p = 0; p < NP; p++)
 #pragma unroll
-        for (int r = 0; r < 8; r++) v[p][r] = smem[p * kN + swz(elem_index<S0>(t, r))];
+        for (int r = 0; r < 8; r++) v[p][r] = smem[p * kN + (base ^ PassSlot<S0>::x(r)) + PassSlot<S0>::a(r)];
 }
 
 // ---------------------------------------------------------------- whole transforms on registers
