@@ -300,6 +300,20 @@ void build(HostContext &H) {
         c.B_mod_q[l] = (u64)(B % qs[l]);
         c.neg_B_mod_q[l] = qs[l] - c.B_mod_q[l];
     }
+    for (int j = 0; j < 2; j++) {
+        const u64 p = bsk[j], ib = c.inv_punct_B[j].w;
+        c.skV[j] = h_mulmod(c.flV[j], ib, p);
+        c.skA[j] = h_mulmod(c.flA[j], ib, p);
+        c.skB[j] = h_mulmod(c.flB[j], ib, p);
+    }
+    {
+        const u64 ib = c.inv_B_mod_msk.w;
+        c.alK[0] = h_mulmod(c.punct_B_mod_msk[0], ib, msk);
+        c.alK[1] = h_mulmod(c.punct_B_mod_msk[1], ib, msk);
+        c.alK[2] = (msk - h_mulmod(c.flV[2], ib, msk)) % msk;
+        c.alK[3] = (msk - h_mulmod(c.flA[2], ib, msk)) % msk;
+        c.alK[4] = (msk - h_mulmod(c.flB[2], ib, msk)) % msk;
+    }
     // key switching
     c.half_P = P >> 1;
     for (int l = 0; l < 2; l++) {

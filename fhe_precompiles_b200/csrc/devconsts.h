@@ -29,6 +29,12 @@ struct DevConsts {
     u64 flV[3], flA[3], flB[3];  // f_k = v_k*flV + tmp0*flA + tmp1*flB mod p_k
                                  //   flV = q^-1, flA = -(q/q_0) q^-1, flB = -(q/q_1) q^-1
 
+    // merged forms used by k_floor_sk (one reduction per output instead of one per SEAL step):
+    //   tb_j  = [f_j * (B/b_j)^-1]_{b_j}      = v_bj*skV[j] + tmp0*skA[j] + tmp1*skB[j]            (j = 0,1)
+    //   alpha = [(h - f_msk) * B^-1]_{m_sk}    = tb0*alK[0] + tb1*alK[1] + v_msk*alK[2] + tmp0*alK[3] + tmp1*alK[4]
+    u64 skV[2], skA[2], skB[2];
+    u64 alK[5];
+
     // ---- fastbconv_sk
     Shoup inv_punct_B[2];      // (B/b_j)^-1 mod b_j
     u64 punct_B_mod_q[2][2];   // [j][l]

@@ -392,39 +392,31 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
         // fast_floor: q-part -> Bsk, f_k = (v_k - conv_k) * q^-1 mod p_k  (constants merged)
         u64 t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
         u64 t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
-        u64 f0, f1, f2;
+        // fastbconv_sk inputs, constants merged (devconsts.h): tb_j = [f_j (B/b_j)^-1]_{b_j}
+        u64 tb0, tb1, alpha;
         {
             u64 lo = 0, hi = 0;
-            mac128(lo, hi, vb0, kc.flV[0]);
-            mac128(lo, hi, t0, kc.flA[0]);
-            mac128(lo, hi, t1, kc.flB[0]);
-            f0 = reduce128<B0>(hi, lo);
+            mac128(lo, hi, vb0, kc.skV[0]);
+            mac128(lo, hi, t0, kc.skA[0]);
+            mac128(lo, hi, t1, kc.skB[0]);
+            tb0 = reduce128<B0>(hi, lo);
         }
         {
             u64 lo = 0, hi = 0;
-            mac128(lo, hi, vb1, kc.flV[1]);
-            mac128(lo, hi, t0, kc.flA[1]);
-            mac128(lo, hi, t1, kc.flB[1]);
-            f1 = reduce128<B1>(hi, lo);
+            mac128(lo, hi, vb1, kc.skV[1]);
+            mac128(lo, hi, t0, kc.skA[1]);
+            mac128(lo, hi, t1, kc.skB[1]);
+            tb1 = reduce128<B1>(hi, lo);
         }
-        {
+        {  // alpha = [(B-part converted to m_sk  -  f_msk) * B^-1]_{m_sk}
             u64 lo = 0, hi = 0;
-            mac128(lo, hi, vsk, kc.flV[2]);
-            mac128(lo, hi, t0, kc.flA[2]);
-            mac128(lo, hi, t1, kc.flB[2]);
-            f2 = reduce128<SK>(hi, lo);
+            mac128(lo, hi, tb0, kc.alK[0]);
+            mac128(lo, hi, tb1, kc.alK[1]);
+            mac128(lo, hi, vsk, kc.alK[2]);
+            mac128(lo, hi, t0, kc.alK[3]);
+            mac128(lo, hi, t1, kc.alK[4]);
+            alpha = reduce128<SK>(hi, lo);
         }
-        // fastbconv_sk
-        u64 tb0 = shoup<B0>(f0, kc.inv_punct_B[0].w, kc.inv_punct_B[0].ws);
-        u64 tb1 = shoup<B1>(f1, kc.inv_punct_B[1].w, kc.inv_punct_B[1].ws);
-        u64 h;
-        {
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, tb0, kc.punct_B_mod_msk[0]);
-            mac128(lo, hi, tb1, kc.punct_B_mod_msk[1]);
-            h = reduce128<SK>(hi, lo);
-        }
-        u64 alpha = shoup<SK>(h + (SK::q - f2), kc.inv_B_mod_msk.w, kc.inv_B_mod_msk.ws);
         bool neg = alpha > (SK::q >> 1);
         u64 am = neg ? SK::q - alpha : alpha;
         u64 *out = c3 + opp * 2 * kN + i;

@@ -37,8 +37,8 @@ __device__ __forceinline__ int pass_upper(int t) {
 // ---------------------------------------------------------------- butterflies
 // forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY), lazily.  G = global stage index 0..11.
 //  small primes: T = wY in [0,4q) (approximate Shoup quotient); bounds grow by 4q per stage, never reduced.
-//  61-bit primes: stage inputs < 4q, 6q, then X is brought back below 4q on every even stage >= 2
-//                 (one conditional subtraction per two stages; 8q < 2^64).
+//  61-bit primes: T in [0,2q); stage inputs grow 2q -> 4q -> 6q -> 8q (< 2^64) and X is folded back below 2q
+//                 (3 instructions: q = 2^61 - c) on every third stage.
 template <class M, int G>
 __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     if (M::kSmall) {
@@ -47,26 +47,30 @@ __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
         X = Xo;
     } else {
         u64 x = X;
-        if (G >= 2 && (G % 2) == 0) x = csub<M>(x, M::four_q);
+        if (G > 0 && (G % 3) == 0) x = fold<M>(x);  // < 8q  ->  < 2^61 + 7c < 2q
         const u64 Xo = shoup_acc<M, false>(x, Y, w, ws);
         Y = (x + x + M::two_q) - Xo;  // x + 2q - T
         X = Xo;
     }
 }
-// bound of the forward outputs in units of q: small 1 + 4*12 (from canonical input), large 8
 // inverse (Gentleman-Sande): (X, Y) -> (X + Y, w(X - Y)); G = global stage index 0..11
+//  small primes: inputs < 4q * 2^G, X output < 4q * 2^(G+1), Y output < 4q; never reduced.
+//  61-bit primes: even stages take inputs < 2q and leave X + Y < 4q unreduced; odd stages take inputs < 4q and
+//                 fold X + Y (< 8q) back below 2q.  Y outputs are always < 2q.
 template <class M, int G>
 __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     if (M::kSmall) {
-        // inputs < 4q * 2^G, X output < 4q * 2^(G+1), Y output < 4q
         constexpr u64 K = M::four_q << G;
         const u64 D = X + (K - Y);
         X = X + Y;
         Y = shoup_acc<M, true>(0, D, w, ws);
-    } else {
-        // Harvey: inputs and outputs in [0,2q)
+    } else if ((G % 2) == 0) {
         const u64 D = X + (M::two_q - Y);
-        X = csub<M>(X + Y, M::two_q);
+        X = X + Y;
+        Y = shoup_lazy<M>(D, w, ws);
+    } else {
+        const u64 D = X + (M::four_q - Y);
+        X = fold<M>(X + Y);
         Y = shoup_lazy<M>(D, w, ws);
     }
 }
@@ -164,9 +168,9 @@ __device__ __forceinline__ void smem_load(const u64 *smem, u64 (&v)[NP][8], int 
 
 // ---------------------------------------------------------------- whole transforms on registers
 // Forward NTT of NP polynomials.
-//  in : v holds coefficients elem_index<0>(t, r) = r*512 + t   (natural order; small primes < 2^42, large < 4q)
+//  in : v holds coefficients elem_index<0>(t, r) = r*512 + t   (natural order; small primes < 2^42, large < 2q)
 //  out: v holds NTT values at positions elem_index<9>(t, r) = 8*t + r, reduced to [0, q) if kCanon
-//       (else small primes < in + 48q, large primes < 8q)
+//       (else small primes < in + 48q, large primes < 8q).  Large-prime inputs must be < 2q.
 template <class M, int NP, bool kCanon>
 __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t) {
     fwd_pass<M, NP, 0>(v, tw, pass_upper<0>(t));
