@@ -258,6 +258,9 @@ void build(HostContext &H) {
         u64 ninv = h_invmod(kN, m);
         c.ninv[mi] = mk_shoup(ninv, m);
         c.ninv_t[mi] = mk_shoup(h_mulmod(ninv, kT % m, m), m);
+        const u64 w_last = H.twi[mi][1].x;  // inverse twiddle of the last Gentleman-Sande stage
+        c.ninv_w[mi] = mk_shoup(h_mulmod(ninv, w_last, m), m);
+        c.ninv_t_w[mi] = mk_shoup(h_mulmod(c.ninv_t[mi].w, w_last, m), m);
     }
     H.inv_q1_mod_q0 = h_invmod(q1 % q0, q0);
     H.inv_q0_mod_q1 = h_invmod(q0 % q1, q1);

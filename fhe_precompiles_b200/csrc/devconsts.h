@@ -17,6 +17,10 @@ struct DevConsts {
     // inverse-NTT output scalings per modulus
     Shoup ninv[kNumMod];    // N^-1
     Shoup ninv_t[kNumMod];  // N^-1 * t   (BEHZ step 6 folded into the inverse transform)
+    // the same scalings pre-multiplied by the last inverse stage's twiddle (table index 1), so that the scaling
+    // costs one multiplication per butterfly of the last stage instead of one per coefficient
+    Shoup ninv_w[kNumMod];
+    Shoup ninv_t_w[kNumMod];
 
     // ---- BEHZ base extension q -> Bsk via m_tilde (RNSTool::fastbconv_m_tilde + sm_mrq)
     Shoup ext_in[2];              // m_tilde * (q/q_l)^-1 mod q_l

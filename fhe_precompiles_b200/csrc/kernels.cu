@@ -46,7 +46,7 @@ __device__ __forceinline__ void ntt_limb_body(u64 *limb, u64 *smem, int t) {
         store_chunk8(limb, v[0], t);
     } else {
         load_chunk8(limb, v[0], t);
-        ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+        ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
         store_natural(limb, v[0], t);
     }
 }
@@ -156,7 +156,7 @@ __device__ __forceinline__ void mul_plain_body(const u64 *__restrict__ ct, const
         d[0][r] = mulmod<M>(v[1][r], v[0][r]);
         d[1][r] = mulmod<M>(v[2][r], v[0][r]);
     }
-    ntt_inverse<M, 2>(d, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    ntt_inverse<M, 2>(d, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
     store_natural(out + (size_t)(0 * 2 + MI) * kN, d[0], t);
     store_natural(out + (size_t)(1 * 2 + MI) * kN, d[1], t);
 }
@@ -244,7 +244,7 @@ __device__ __forceinline__ void behz_tensor_body(const u64 *__restrict__ a, cons
         D[1][r] = reduce128<M>(hi, lo);
         D[2][r] = mulmod<M>(a1, B[1][r]);
     }
-    ntt_inverse<M, 3>(D, smem, kt.twi[MI], t, kc.ninv_t[MI].w, kc.ninv_t[MI].ws);
+    ntt_inverse<M, 3>(D, smem, kt.twi[MI], t, kc.ninv_t[MI], kc.ninv_t_w[MI]);
 #pragma unroll
     for (int p = 0; p < 3; p++) store_natural(tens + (size_t)(p * 5 + EI) * kN, D[p], t);
 }
@@ -353,7 +353,7 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
         for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(x[r], y[r]);
     }
     // outputs stay in [0, 2q): k_floor_sk's Shoup / 128-bit reductions take any such value
-    ntt_inverse<M, 1, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI].w, kc.ninv_t[MI].ws);
+    ntt_inverse<M, 1, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI], kc.ninv_t_w[MI]);
     store_natural(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
@@ -465,7 +465,7 @@ __device__ __forceinline__ void relin_ks_body(const u64 *__restrict__ c2, const 
             E[k][r] = reduce128<M>(hi, lo);
         }
     }
-    ntt_inverse<M, 2>(E, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    ntt_inverse<M, 2>(E, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
     store_natural(ks + (size_t)(0 * 3 + MI) * kN, E[0], t);
     store_natural(ks + (size_t)(1 * 3 + MI) * kN, E[1], t);
 }
@@ -526,7 +526,7 @@ __device__ __forceinline__ void ks_intt_body(const u64 *__restrict__ dg, const u
         mac128(lo, hi, d1[r], k1[r]);
         v[0][r] = reduce128<M>(hi, lo);
     }
-    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
     store_natural(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_ks_intt(const u64 *__restrict__ dig, const u64 *__restrict__ rk,
@@ -595,7 +595,7 @@ __device__ __forceinline__ void decrypt_dot_body(const u64 *__restrict__ ct, con
     load_chunk8_ldg(sk + (size_t)MI * kN, s, t);
 #pragma unroll
     for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(v[0][r], s[r]);
-    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
     load_natural(ct + (size_t)(0 * 2 + MI) * kN, c0, t);
 #pragma unroll
     for (int r = 0; r < 8; r++) v[0][r] = addmod<M>(v[0][r], c0[r]);
@@ -699,7 +699,7 @@ __device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, u6
 #pragma unroll
         for (int r = 0; r < 8; r++) w[j][r] = mulmod<M>(v[0][r], k[r]);
     }
-    ntt_inverse<M, 2>(w, smem, kt.twi[MI], t, kc.ninv[MI].w, kc.ninv[MI].ws);
+    ntt_inverse<M, 2>(w, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll

@@ -11,6 +11,7 @@
 // makes every pass's 64-bit accesses bank-conflict-free for a half warp (see swz()).
 // Twiddles are (w, floor(w*2^64/q)) pairs read through the read-only path from an L2-resident table.
 #pragma once
+#include "devconsts.h"
 #include "modarith.cuh"
 
 namespace fheb {
@@ -110,9 +111,22 @@ __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__re
     }
 }
 
+// last Gentleman-Sande stage (G = 11) with the output scaling merged in: (X, Y) -> (s(X + Y), s w (X - Y)),
+// both through exact Shoup multiplications, results in [0, 2q) or canonical
+template <class M, bool kCanon>
+__device__ __forceinline__ void inv_bfly_last(u64 &X, u64 &Y, const Shoup &s, const Shoup &sw) {
+    constexpr u64 K = M::kSmall ? (M::four_q << 11) : M::four_q;  // >= the stage's input bound (odd stage: < 4q for 61-bit)
+    const u64 D = X + (K - Y);
+    const u64 S = X + Y;
+    X = kCanon ? shoup<M>(S, s.w, s.ws) : shoup_lazy<M>(S, s.w, s.ws);
+    Y = kCanon ? shoup<M>(D, sw.w, sw.ws) : shoup_lazy<M>(D, sw.w, sw.ws);
+}
+
 // inverse pass over the same register bits, stages in reverse order. G0 = global index of its first stage.
-template <class M, int NP, int S0, int G0>
-__device__ __forceinline__ void inv_pass(u64 (&v)[NP][8], const ulonglong2 *__restrict__ tw, int upper) {
+// kLast (only with S0 == 0): the pass's final stage is the transform's last one and applies the scaling (s, sw).
+template <class M, int NP, int S0, int G0, bool kLast = false, bool kCanon = true>
+__device__ __forceinline__ void inv_pass(u64 (&v)[NP][8], const ulonglong2 *__restrict__ tw, int upper, const Shoup *s = nullptr,
+                                         const Shoup *sw = nullptr) {
 #pragma unroll
     for (int h = 0; h < 4; h++) {
         ulonglong2 w = ldtw<M, true, S0>(tw, (4 << S0) + 4 * upper + h);
@@ -127,7 +141,12 @@ __device__ __forceinline__ void inv_pass(u64 (&v)[NP][8], const ulonglong2 *__re
 #pragma unroll
             for (int r = 0; r < 2; r++) inv_bfly<M, G0 + 1>(v[p][4 * h + r], v[p][4 * h + r + 2], w.x, w.y);
     }
-    {
+    if (kLast) {
+#pragma unroll
+        for (int p = 0; p < NP; p++)
+#pragma unroll
+            for (int r = 0; r < 4; r++) inv_bfly_last<M, kCanon>(v[p][r], v[p][r + 4], *s, *sw);
+    } else {
         ulonglong2 w = ldtw<M, true, S0>(tw, (1 << S0) + upper);
 #pragma unroll
         for (int p = 0; p < NP; p++)
@@ -197,10 +216,11 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
 
 // Inverse NTT of NP polynomials.
 //  in : v holds NTT values at positions 8*t + r, each < 2q (small primes: < 4q)
-//  out: v holds coefficients r*512 + t, multiplied by (sc, scs) (Shoup pair, e.g. N^-1), in [0, q) ([0, 2q) if !kCanon)
+//  out: v holds coefficients r*512 + t, multiplied by the scalar sc (scw = sc * last-stage twiddle), in [0, q)
+//       ([0, 2q) if !kCanon)
 template <class M, int NP, bool kCanon = true>
-__device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t, u64 sc,
-                                            u64 scs) {
+__device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t, const Shoup &sc,
+                                            const Shoup &scw) {
     inv_pass<M, NP, 9, 0>(v, tw, pass_upper<9>(t));
     smem_store<NP, 9>(smem, v, t);
     __syncthreads();
@@ -213,11 +233,7 @@ __device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ul
     smem_store<NP, 3>(smem, v, t);
     __syncthreads();
     smem_load<NP, 0>(smem, v, t);
-    inv_pass<M, NP, 0, 9>(v, tw, pass_upper<0>(t));
-#pragma unroll
-    for (int p = 0; p < NP; p++)
-#pragma unroll
-        for (int r = 0; r < 8; r++) v[p][r] = kCanon ? shoup<M>(v[p][r], sc, scs) : shoup_lazy<M>(v[p][r], sc, scs);
+    inv_pass<M, NP, 0, 9, true, kCanon>(v, tw, pass_upper<0>(t), &sc, &scw);
     __syncthreads();
 }
 
