@@ -94,6 +94,24 @@ void Engine::release_lane(Lane *l) {
 }
 
 // ---------------------------------------------------------------- key cache
+KeyPin &KeyPin::operator=(KeyPin &&o) noexcept {
+    if (this != &o) {
+        release();
+        e_ = o.e_;
+        k_ = o.k_;
+        o.k_ = nullptr;
+    }
+    return *this;
+}
+void KeyPin::release() {
+    if (k_) e_->unpin_key(k_);
+    k_ = nullptr;
+}
+void Engine::unpin_key(KeyEntry *k) {
+    std::lock_guard<std::mutex> lk(key_mu_);
+    k->users--;
+}
+
 KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
     const uint64_t tag = cheap_tag(pk);
     KeyEntry *hit = nullptr;
@@ -113,20 +131,21 @@ KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
         e->d_rk.assign((size_t)n_devices_, nullptr);
         e->d_pk.assign((size_t)n_devices_, nullptr);
         const size_t cap = env_size("FHE_B200_KEY_CACHE", 8);
-        if (keys_.size() >= cap) {  // evict least recently used
-            size_t victim = 0;
-            for (size_t i = 1; i < keys_.size(); i++)
-                if (keys_[i]->last_use < keys_[victim]->last_use) victim = i;
-            for (int d = 0; d < n_devices_; d++) {
-                uint64_t *ptrs[2] = {keys_[victim]->d_rk[(size_t)d], keys_[victim]->d_pk[(size_t)d]};
-                for (uint64_t *ptr : ptrs)
-                    if (ptr) {
-                        cudaSetDevice(d);
-                        cudaDeviceSynchronize();
-                        cudaFree(ptr);
-                    }
+        if (keys_.size() >= cap) {  // evict the least recently used entry nobody is using; if all are pinned, grow
+            long victim = -1;
+            for (size_t i = 0; i < keys_.size(); i++)
+                if (keys_[i]->users == 0 && (victim < 0 || keys_[i]->last_use < keys_[(size_t)victim]->last_use)) victim = (long)i;
+            if (victim >= 0) {
+                for (int d = 0; d < n_devices_; d++) {
+                    uint64_t *ptrs[2] = {keys_[(size_t)victim]->d_rk[(size_t)d], keys_[(size_t)victim]->d_pk[(size_t)d]};
+                    for (uint64_t *ptr : ptrs)
+                        if (ptr) {
+                            cudaSetDevice(d);
+                            cudaFree(ptr);  // no holder left: every user synchronised its stream before unpinning
+                        }
+                }
+                keys_.erase(keys_.begin() + victim);
             }
-            keys_.erase(keys_.begin() + (long)victim);
         }
         keys_.push_back(std::move(e));
         hit = keys_.back().get();
@@ -136,7 +155,7 @@ KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
     return hit;
 }
 
-int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin) {
+int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin, KeyPin *pin) {
     std::lock_guard<std::mutex> lk(key_mu_);
     int32_t rc = kOk;
     KeyEntry *hit = find_or_parse_key(pk, &rc);
@@ -153,10 +172,12 @@ int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_
         cuda_throw(cudaMemcpy(slot, hit->rk.data(), kRkWords * 8, cudaMemcpyHostToDevice), "upload rk");
     }
     *d_rk = slot;
+    hit->users++;
+    *pin = KeyPin(this, hit);
     return kOk;
 }
 
-int32_t Engine::public_key(Span pk, int device, const uint64_t **d_pk) {
+int32_t Engine::public_key(Span pk, int device, const uint64_t **d_pk, KeyPin *pin) {
     std::lock_guard<std::mutex> lk(key_mu_);
     int32_t rc = kOk;
     KeyEntry *hit = find_or_parse_key(pk, &rc);
@@ -168,6 +189,8 @@ int32_t Engine::public_key(Span pk, int device, const uint64_t **d_pk) {
         cuda_throw(cudaMemcpy(slot, hit->pk.data(), kPkWords * 8, cudaMemcpyHostToDevice), "upload pk");
     }
     *d_pk = slot;
+    hit->users++;
+    *pin = KeyPin(this, hit);
     return kOk;
 }
 
@@ -219,6 +242,7 @@ void Engine::set_kernel_timing(bool on) { timing_ = on; }
 void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint64_t launches[kNumTimedKernels]) {
     cuda_throw(cudaSetDevice(device), "cudaSetDevice");
     cuda_throw(cudaDeviceSynchronize(), "sync for timing report");
+    std::lock_guard<std::mutex> tlk(timed_mu_);
     for (int k = 0; k < kNumTimedKernels; k++) ms[k] = 0, launches[k] = 0;
     for (auto &t : timed_) {
         float f = 0;
@@ -236,6 +260,7 @@ void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint6
 #define TIMED(id, call, what)                                        \
     do {                                                             \
         if (timed) {                                                 \
+            std::lock_guard<std::mutex> tlk(timed_mu_);              \
             TimedLaunch tl{id, take_event(), take_event()};          \
             cuda_throw(cudaEventRecord(tl.e0, s), "event record");   \
             cuda_throw(call, what);                                  \
@@ -362,7 +387,8 @@ int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<ui
     // reference order (pack.rs:261-263): public key, then a, then b
     const uint64_t *d_rk = nullptr;
     const bool need_relin = (op == Op::Mul && shape == Shape::CtCt);
-    rc = relin_key(pk, lane->device, &d_rk, need_relin);
+    KeyPin pin;
+    rc = relin_key(pk, lane->device, &d_rk, need_relin, &pin);
     if (rc == kErrSunscreen && need_relin) {
         // missing relin keys is a runtime (not a decoding) error: operands are still decoded first
     } else if (rc) {
@@ -469,7 +495,8 @@ int32_t Engine::encrypt_plain(Kind kind, const uint16_t *, Span scalar, Span pk_
     int32_t rc = encode_scalar(kind, scalar, lane->h_plain);
     if (rc) return rc == kErrSunscreen ? kErrFailedEncryption : rc;
     const uint64_t *d_pk = nullptr;
-    rc = public_key(pk_bytes, lane->device, &d_pk);
+    KeyPin pin;
+    rc = public_key(pk_bytes, lane->device, &d_pk, &pin);
     if (rc) return rc;
     cudaStream_t s = lane->stream;
     lane->h_b[0] = seed;
@@ -525,7 +552,8 @@ int32_t Engine::reencrypt(Kind kind, Span in, Span, Span net_pri, std::vector<ui
     cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
     // reference order: key, ciphertext, public data are all deserialised first (pack.rs:261-263)
     const uint64_t *d_pk = nullptr;
-    if ((rc = public_key(pk, lane->device, &d_pk))) return rc;
+    KeyPin pin;  // validates the target key first, as the reference's unpack order does; encrypt_plain re-pins it
+    if ((rc = public_key(pk, lane->device, &d_pk, &pin))) return rc;
     CipherView view;
     if ((rc = decode_ciphertext(ct, &view, lane->h_a))) return rc == kErrSunscreen ? kErrFailedDecryption : rc;
     if (!data_type_matches(view.data_type, kind)) return kErrFailedDecryption;

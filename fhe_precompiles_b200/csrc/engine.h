@@ -47,6 +47,25 @@ struct KeyEntry {
     std::vector<uint64_t *> d_rk;  // per device, lazily uploaded
     std::vector<uint64_t *> d_pk;
     uint64_t last_use = 0;
+    int users = 0;  // calls currently holding device pointers of this entry (guarded by Engine::key_mu_); pinned against eviction
+};
+
+class Engine;
+// RAII pin on a cached key: the entry's device buffers stay allocated until every holder is gone
+class KeyPin {
+   public:
+    KeyPin() = default;
+    KeyPin(Engine *e, KeyEntry *k) : e_(e), k_(k) {}
+    KeyPin(const KeyPin &) = delete;
+    KeyPin &operator=(const KeyPin &) = delete;
+    KeyPin(KeyPin &&o) noexcept : e_(o.e_), k_(o.k_) { o.k_ = nullptr; }
+    KeyPin &operator=(KeyPin &&o) noexcept;
+    ~KeyPin() { release(); }
+    void release();
+
+   private:
+    Engine *e_ = nullptr;
+    KeyEntry *k_ = nullptr;
 };
 
 class Engine {
@@ -84,9 +103,11 @@ class Engine {
     int n_devices() const { return n_devices_; }
 
     // relin key for the PublicKey bytes, parsed + validated once and cached by content
-    int32_t relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin);
+    // `pin` keeps the entry (and its device buffers) alive until it is destroyed
+    int32_t relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin, KeyPin *pin);
     // encryption key [2][3][N] on `device` for the PublicKey bytes (same cache)
-    int32_t public_key(Span pk, int device, const uint64_t **d_pk);
+    int32_t public_key(Span pk, int device, const uint64_t **d_pk, KeyPin *pin);
+    void unpin_key(KeyEntry *k);
     // device-resident batched encrypt / decrypt (pointers on `device`)
     void encrypt_device(int device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
                         cudaStream_t s);
@@ -139,6 +160,7 @@ class Engine {
                        bool timed);
     void timed_launch(int kernel, cudaStream_t s, bool timed, cudaError_t e0, const char *what);
     std::vector<TimedLaunch> timed_;
+    std::mutex timed_mu_;
     std::vector<cudaEvent_t> event_pool_;
     cudaEvent_t take_event();
 

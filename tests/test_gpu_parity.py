@@ -360,3 +360,54 @@ def test_empty_batches(dev, keys):
     from fhe_precompiles_b200 import FHE
 
     assert FHE.run_batch([]) == []
+
+
+# ---------------------------------------------------------------- re-entrancy and the key cache
+def test_concurrent_calls_and_key_cache_eviction(keys, monkeypatch):
+    """the C ABI is re-entrant like the reference's global FheApp (testnet.rs:25): 8 threads x mixed precompiles under
+    4 distinct public keys with a 2-entry key cache (forcing evictions while other threads hold keys); every result must
+    equal the oracle's bytes."""
+    import threading
+
+    from fhe_precompiles_b200 import FHE, pack
+
+    monkeypatch.setenv("FHE_B200_KEY_CACHE", "2")
+    t_pk, n_pk = F.PublicKey.from_bytes(keys.pub_bytes), F.PublicKey.from_bytes(keys.net_pub_bytes)
+    variants = [
+        (keys.pub_bytes, keys.rk),
+        (keys.net_pub_bytes, keys.net_rk),
+        (F.PublicKey(t_pk.public_key, None, n_pk.relin_key).to_bytes(), keys.net_rk),
+        (F.PublicKey(n_pk.public_key, None, t_pk.relin_key).to_bytes(), keys.rk),
+    ]
+    a, b = encrypt_value(keys, "i64", 21, 70), encrypt_value(keys, "i64", -3, 71)
+    sa, sb = (F.make_ciphertext("i64", x).to_bytes() for x in (a, b))
+    want = {}
+    for vi, (pkb, rk) in enumerate(variants):
+        want[("mul", vi)] = F.make_ciphertext("i64", bfv.mul_relin(a, b, rk)).to_bytes()
+        want[("add", vi)] = F.make_ciphertext("i64", bfv.add(a, b)).to_bytes()
+        want[("mulp", vi)] = F.make_ciphertext("i64", bfv.multiply_plain(a, bfv.encode("i64", 5))).to_bytes()
+    errors = []
+
+    def worker(tid):
+        try:
+            for it in range(6):
+                vi = (tid + it) % 4
+                pkb = variants[vi][0]
+                kind = ("mul", "add", "mulp")[(tid + it) % 3]
+                if kind == "mul":
+                    out = FHE.mul_cipheri64_cipheri64(pack.pack_binary_operation(pkb, sa, sb))
+                elif kind == "add":
+                    out = FHE.add_cipheri64_cipheri64(pack.pack_binary_operation(pkb, sa, sb))
+                else:
+                    out = FHE.mul_cipheri64_i64(pack.pack_binary_operation(pkb, sa, pack.serialize_i64(5)))
+                if out != want[(kind, vi)]:
+                    errors.append((tid, it, kind, vi))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
