@@ -28,8 +28,9 @@ CT_BYTES = 2 * 2 * N * 8  # 131,072
 ALGO_BYTES_PER_OP = 3 * CT_BYTES  # read a, read b, write result = 393,216 B
 # 47 limb-NTTs x 24,576 butterflies + ~0.79 M pointwise modmuls per op
 MODMUL_PER_OP = 47 * 24576 + 790528
-# a 64-bit Shoup/Barrett modmul needs >= 10 32x32-bit multiply-adds (4 for the high product, 3 + 3 for two low ones)
-MAD_PER_MODMUL = 10
+# FMA-pipe cost of one Shoup modmul as written in modarith.cuh: 5 IMAD.WIDE (quarter rate on B200: 32 per clock per SM,
+# measured) + 4 IMAD (half rate) = 7 IMAD.WIDE equivalents; the 61-bit primes need one more wide product (8)
+WIDE_EQ_PER_MODMUL = 7.4
 METRIC = "ct_ct_fhe_multiply_relin_ops_per_sec"
 WORKLOAD = "batch of 4096 ct*ct fhe_multiply+relinearize per GPU, testnet BFV params (N=4096, q=72b, t=4096)"
 
@@ -397,21 +398,24 @@ def main() -> None:
         "ops_per_launch": ops_per_launch,
         "kernel_share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
         "kernel_ms": {k: v[0] for k, v in kt.items()},
-        "note": "the fused multiply kernels are integer-pipe bound (SURVEY 8d); see int_pipe",
+        "note": "the multiply kernels are bound by the FMA (integer multiply) pipe, not HBM (SURVEY 8d); see int_pipe",
     }
     try:
-        peak_mad = fdev.int_peak(local_rank, wide=1)
+        peak_wide = fdev.int_peak(local_rank, wide=1)  # T IMAD.WIDE/s (mul.wide.u32 with a loop-carried operand)
+        peak_lo = fdev.int_peak(local_rank, wide=0)
         ops_s = n * args.steps / (ms * 1e-3)
-        ach_mad = ops_s * MODMUL_PER_OP * MAD_PER_MODMUL / 1e12
+        ach = ops_s * MODMUL_PER_OP * WIDE_EQ_PER_MODMUL / 1e12
         # butterfly-rate ceiling: register-only NTT inner loop, per prime class (26 small + 21 large limb-NTTs per op)
         bf_small, bf_big = fdev.bfly_peak(local_rank, 0), fdev.bfly_peak(local_rank, 3)
         ntt_floor_us = 24576 * (26 / bf_small + 21 / bf_big) * 1e-3
         int_pipe = {
-            "achieved": ach_mad,
-            "peak": peak_mad,
-            "unit": "T mad.wide.u32/s",
-            "frac": ach_mad / peak_mad,
-            "model": f"{MODMUL_PER_OP} 64-bit modmul/op x {MAD_PER_MODMUL} 32-bit mads; peak = measured microbenchmark",
+            "achieved": ach,
+            "peak": peak_wide,
+            "unit": "T IMAD.WIDE-equivalents/s (FMA pipe)",
+            "frac": ach / peak_wide,
+            "model": f"{MODMUL_PER_OP} 64-bit modmul/op x {WIDE_EQ_PER_MODMUL} IMAD.WIDE equivalents (5-6 IMAD.WIDE + 4 IMAD at half cost); "
+            "peak = measured mul.wide.u32 rate",
+            "measured_pipe_rates_T_per_s": {"IMAD.WIDE": peak_wide, "IMAD": peak_lo},
             "butterfly_peak_G_per_s": {"36-37 bit primes": bf_small, "61 bit primes": bf_big},
             "ntt_only_floor_us_per_op": ntt_floor_us,
             "frac_of_butterfly_ceiling": ntt_floor_us * 1e-6 * ops_s,

@@ -757,101 +757,113 @@ __global__ void __launch_bounds__(256) k_encrypt_finish(const u64 *__restrict__ 
 // integer-pipe peak microbenchmark (roofline denominator for the multiply kernels; not on the hot path)
 // 16 independent mad chains per thread; WIDE: mad.wide.u32 (32x32+64 -> 64), else mad.lo.u32
 // =====================================================================================
-// MODE 0: mad.lo.u32, 1: mad.wide.u32, 2: add.u32 (ALU pipe), 3: mad.lo.u32 + add.u32 interleaved (dual issue),
-//      4: mad.wide.u32 + add.u32 interleaved
+// MODE 0: mad.lo.u32 (IMAD), 1: mul.wide.u32 (IMAD.WIDE), 2: add.cc/addc pairs (IADD3 + IADD3.X, counted as 2 ops),
+//      3: mad.lo + add interleaved (counts both), 4: mul.wide + add interleaved (counts both).
+// Every multiply has a loop-carried multiplicand so that ptxas cannot strength-reduce it.
 template <int MODE>
-__global__ void __launch_bounds__(256) k_int_peak(u64 *out, int iters) {
-    u32 a = threadIdx.x * 2654435761u + 1u, b = blockIdx.x * 40503u + 7u;
-    u64 acc[16];
-    u32 s[16];
+__global__ void __launch_bounds__(1024) k_int_peak(u64 *out, int iters, u32 a, u32 b) {
+    u32 x[16], y[16];
 #pragma unroll
-    for (int j = 0; j < 16; j++) acc[j] = a + j, s[j] = b + j;
+    for (int j = 0; j < 16; j++) {
+        x[j] = threadIdx.x * 77u + j + a;
+        y[j] = threadIdx.x * 13u + j * b;
+    }
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int j = 0; j < 16; j++) {
+            if (MODE == 0 || MODE == 3) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
             if (MODE == 1 || MODE == 4) {
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
-            } else if (MODE == 0 || MODE == 3) {
-                u32 x = (u32)acc[j];
-                asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x) : "r"(a), "r"(b));
-                acc[j] = x;
+                u64 t;
+                asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(t) : "r"(x[j]), "r"(a));
+                x[j] = (u32)(t >> 32) + (u32)t;  // one extra add keeps both halves live
             }
-            if (MODE >= 2) asm volatile("add.u32 %0, %0, %1;" : "+r"(s[j]) : "r"(s[(j + 1) & 15]));
+            if (MODE == 2) asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.u32 %1, %1, %3;" : "+r"(x[j]), "+r"(y[j]) : "r"(a), "r"(b));
+            if (MODE == 3 || MODE == 4) asm volatile("add.u32 %0, %0, %1;" : "+r"(y[j]) : "r"(a));
         }
     }
-    u64 r = 0;
+    u32 r = 0;
 #pragma unroll
-    for (int j = 0; j < 16; j++) r ^= acc[j] ^ s[j];
-    if (r == 0x123456789abcdefull) out[0] = r;  // keep the chains alive
+    for (int j = 0; j < 16; j++) r ^= x[j] ^ y[j];
+    if (r == 0x12345u) out[0] = r;
 }
 
 // Register-only butterfly throughput: every thread runs `iters` forward radix-8 passes (12 butterflies each)
 // on 8 resident values with twiddles held in registers -- the practical integer-pipe ceiling of the NTT inner
 // loop, free of memory and barrier effects.
-template <int MI>
-__global__ void __launch_bounds__(kThreads) k_bfly_peak(u64 *out, int iters, ulonglong2 tw0) {
+template <int MI, int NV, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_bfly_peak(u64 *out, int iters, ulonglong2 tw0) {
     using M = Mod<MI>;
-    u64 v[8];
+    u64 v[NV];
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[r] = (threadIdx.x * 8 + r) * 0x9E3779B97F4A7C15ull % M::q;
+    for (int r = 0; r < NV; r++) v[r] = ((threadIdx.x * NV + r) * 0x9E3779B97F4A7C15ull >> 8) % M::q;
     u64 w = tw0.x % M::q, ws = tw0.y;
     for (int i = 0; i < iters; i++) {
+        // log2(NV) butterfly stages over the NV resident values (stage indices chosen so that the 61-bit path folds
+        // once every third stage, as in the real transform)
 #pragma unroll
-        for (int r = 0; r < 4; r++) fwd_bfly<M, 2>(v[r], v[r + 4], w, ws);
+        for (int r = 0; r < NV / 2; r++) fwd_bfly<M, 3>(v[r], v[r + NV / 2], w, ws);
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            fwd_bfly<M, 3>(v[r], v[r + 2], w, ws);
-            fwd_bfly<M, 3>(v[4 + r], v[6 + r], w, ws);
-        }
+        for (int r = 0; r < NV / 2; r++) fwd_bfly<M, 4>(v[(r / (NV / 4)) * (NV / 2) + r % (NV / 4)], v[(r / (NV / 4)) * (NV / 2) + r % (NV / 4) + NV / 4], w, ws);
 #pragma unroll
-        for (int r = 0; r < 4; r++) fwd_bfly<M, 4>(v[2 * r], v[2 * r + 1], w, ws);
+        for (int r = 0; r < NV / 2; r++) fwd_bfly<M, 5>(v[2 * r], v[2 * r + 1], w, ws);
         if (M::kSmall) {  // keep the lazy values inside the range the real transform guarantees
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[r] &= (1ull << 42) - 1;
+            for (int r = 0; r < NV; r++) v[r] &= (1ull << 40) - 1;
         }
     }
     u64 acc = 0;
 #pragma unroll
-    for (int r = 0; r < 8; r++) acc ^= v[r];
+    for (int r = 0; r < NV; r++) acc ^= v[r];
     if (acc == tw0.x) out[0] = acc;
 }
-cudaError_t measure_bfly_peak(int mod, double *giga_bfly_per_s) {
-    u64 *d = nullptr;
-    cudaError_t e = cudaMalloc((void **)&d, 8);
-    if (e != cudaSuccess) return e;
-    const int iters = 2048, grid = 148 * 4;
+template <int MI, int NV, int THREADS>
+static float time_bfly(u64 *d, int iters, int grid, ulonglong2 tw) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float best = 1e30f;
-    ulonglong2 tw = make_ulonglong2(0x123456789ull, 0x9abcdef012345678ull);
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(e0);
-        if (mod < 3)
-            k_bfly_peak<MQ0><<<grid, kThreads>>>(d, iters, tw);
-        else
-            k_bfly_peak<MB0><<<grid, kThreads>>>(d, iters, tw);
+        k_bfly_peak<MI, NV, THREADS><<<grid, THREADS>>>(d, iters, tw);
         cudaEventRecord(e1);
-        e = cudaEventSynchronize(e1);
-        if (e != cudaSuccess) break;
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
         if (rep > 0 && ms < best) best = ms;
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    cudaFree(d);
+    return best;
+}
+// mod 0-2: small primes, 3-5: 61-bit; mod + 10: 16 values per thread / 256 threads (ILP experiment)
+cudaError_t measure_bfly_peak(int mod, double *giga_bfly_per_s) {
+    u64 *d = nullptr;
+    cudaError_t e = cudaMalloc((void **)&d, 8);
     if (e != cudaSuccess) return e;
-    *giga_bfly_per_s = (double)grid * kThreads * iters * 12.0 / (best * 1e-3) / 1e9;
+    const int iters = 2048;
+    ulonglong2 tw = make_ulonglong2(0x123456789ull, 0x9abcdef012345678ull);
+    float ms;
+    double bfly;
+    if (mod >= 10) {
+        const int grid = 148 * 8;
+        ms = (mod - 10) < 3 ? time_bfly<MQ0, 16, 256>(d, iters, grid, tw) : time_bfly<MB0, 16, 256>(d, iters, grid, tw);
+        bfly = (double)grid * 256 * iters * 24.0;
+    } else {
+        const int grid = 148 * 4;
+        ms = mod < 3 ? time_bfly<MQ0, 8, kThreads>(d, iters, grid, tw) : time_bfly<MB0, 8, kThreads>(d, iters, grid, tw);
+        bfly = (double)grid * kThreads * iters * 12.0;
+    }
+    cudaFree(d);
+    *giga_bfly_per_s = bfly / (ms * 1e-3) / 1e9;
     return cudaGetLastError();
 }
 
-// result: 1e12 "primary" ops per second (mads for modes 0,1,3,4; adds for mode 2)
+// result: 1e12 thread-level operations per second (see the MODE list above for what is counted)
 cudaError_t measure_int_peak(int mode, double *tera_ops_per_s) {
     u64 *d = nullptr;
     cudaError_t e = cudaMalloc((void **)&d, 8);
     if (e != cudaSuccess) return e;
-    const int iters = 8192, grid = 148 * 8, block = 256;
+    const int iters = 4096, grid = 148 * 2, block = 1024;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -859,11 +871,11 @@ cudaError_t measure_int_peak(int mode, double *tera_ops_per_s) {
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(e0);
         switch (mode) {
-            case 0: k_int_peak<0><<<grid, block>>>(d, iters); break;
-            case 1: k_int_peak<1><<<grid, block>>>(d, iters); break;
-            case 2: k_int_peak<2><<<grid, block>>>(d, iters); break;
-            case 3: k_int_peak<3><<<grid, block>>>(d, iters); break;
-            default: k_int_peak<4><<<grid, block>>>(d, iters); break;
+            case 0: k_int_peak<0><<<grid, block>>>(d, iters, 3, 5); break;
+            case 1: k_int_peak<1><<<grid, block>>>(d, iters, 3, 5); break;
+            case 2: k_int_peak<2><<<grid, block>>>(d, iters, 3, 5); break;
+            case 3: k_int_peak<3><<<grid, block>>>(d, iters, 3, 5); break;
+            default: k_int_peak<4><<<grid, block>>>(d, iters, 3, 5); break;
         }
         cudaEventRecord(e1);
         e = cudaEventSynchronize(e1);
@@ -876,7 +888,8 @@ cudaError_t measure_int_peak(int mode, double *tera_ops_per_s) {
     cudaEventDestroy(e1);
     cudaFree(d);
     if (e != cudaSuccess) return e;
-    *tera_ops_per_s = (double)grid * block * iters * 16.0 / (best * 1e-3) / 1e12;
+    const double per = (mode == 2 || mode == 3 || mode == 4) ? 2.0 : 1.0;
+    *tera_ops_per_s = (double)grid * block * iters * 16.0 * per / (best * 1e-3) / 1e12;
     return cudaGetLastError();
 }
 

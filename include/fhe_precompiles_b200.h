@@ -147,7 +147,7 @@ int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk,
 int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
                                 size_t n);
 /* Integer-pipe peak of `device` in 1e12 multiply-adds/s, measured by a register-only microbenchmark
- * (wide: 0 mad.lo.u32, 1 mad.wide.u32, 2 add.u32, 3 mad.lo+add interleaved, 4 mad.wide+add). Denominator of the integer roofline; synchronous. */
+ * (wide: 0 mad.lo.u32 [IMAD], 1 mul.wide.u32 [IMAD.WIDE], 2 add.cc+addc, 3 mad.lo+add, 4 mul.wide+add). Denominator of the integer roofline; synchronous. */
 int32_t fhe_b200_int_peak(int32_t device, int32_t wide, double *tera_mads_per_s);
 /* Register-only NTT butterfly rate of `device` in 1e9 butterflies/s for modulus class of `mod` (0-2: 36/37-bit,
  * 3-5: 61-bit): the compute ceiling of the transform's inner loop without memory or barriers. */

@@ -56,6 +56,11 @@ def main():
     print(f"  relinearize: {ms:.3f} ms ({ms / n * 1e3:.2f} us/op)")
     ms = timeit(lambda: device.add(a, b))
     print(f"  add:         {ms:.3f} ms  -> {n * 393216 / ms / 1e6:.0f} GB/s")
+    pl = torch.randint(0, 4096, (n, N), dtype=torch.int16, device="cuda")
+    ms = timeit(lambda: device.plain_addsub(a, pl, 0))
+    print(f"  add_plain:   {ms:.3f} ms  -> {n * (2 * 131072 + 8192) / ms / 1e6:.0f} GB/s, {n / ms * 1e3 / 1e6:.2f} M ops/s")
+    ms = timeit(lambda: device.multiply_plain(a, pl))
+    print(f"  mul_plain:   {ms:.3f} ms  ({ms / n * 1e3:.3f} us/op) -> {n / ms * 1e3 / 1e6:.2f} M ops/s")
     for m in (0, 3):
         x = torch.from_numpy(rng.integers(0, MODULI[m], size=(n * 4, N), dtype=np.uint64).view(np.int64)).cuda()
         ms = timeit(lambda: device.ntt_(x, [m]))
