@@ -84,9 +84,11 @@ __device__ __forceinline__ u64 csub(u64 x, u64 m) {
 // acc + x*w - H*q (mod 2^64) with H ~ floor(x*ws/2^64): Shoup multiplication by the precomputed pair
 // (w, ws = floor(w*2^64/q)) fused with an accumulate.  q = 2^B - c, so -H*q = H*c - (H << B).
 //   exact quotient : adds a value in [0, 2q) for any 64-bit x
-//   kApprox        : drops the x_lo*ws_lo partial product and one carry (H low by <= 2): adds [0, 4q)
-// SASS per call: 5-6 IMAD.WIDE + 4 IMAD on the FMA pipe, 4-8 IADD3 on the ALU pipe.
-template <class M, bool kApprox>
+//   approximate 1  : drops the x_lo*ws_lo partial product and one carry (H low by <= 2): adds [0, 4q)
+//   approximate 2  : x < 2^44 only; also estimates the x_hi*ws_lo term from 16 bits (H low by <= 3): adds [0, 5q)
+// FMA pipe per call (IMAD.WIDE 4 cycles, IMAD 2): exact 6+4 (32), approximate 1: 5+4 (28), approximate 2: 4+5 (26).
+// kApprox: 0 exact, 1 approximate for any 64-bit x ([0,4q)), 2 approximate for x < 2^44 ([0,5q), one wide multiply fewer)
+template <class M, int kApprox>
 __device__ __forceinline__ u64 shoup_acc(u64 acc, u64 x, u64 w, u64 ws) {
     constexpr u32 c = (u32)M::kC;
     u32 xl, xh, wl, wh, sl, sh;
@@ -94,7 +96,14 @@ __device__ __forceinline__ u64 shoup_acc(u64 acc, u64 x, u64 w, u64 ws) {
     unpack64(w, wl, wh);
     unpack64(ws, sl, sh);
     u64 H;
-    if (kApprox) {
+    if (kApprox == 2) {
+        // x < 2^44, so xh < 2^12 and floor(xh*sl / 2^32) is estimated from the top 16 bits of sl with one low
+        // multiply (IMAD: half the FMA-pipe cost of IMAD.WIDE); the estimate is low by at most 1
+        u32 vl, vh;
+        const u32 uh = (xh * (sl >> 16)) >> 16;
+        unpack64(mul_wide(xl, sh), vl, vh);
+        H = mad_wide(xh, sh, pack64(uh, 0)) + vh;
+    } else if (kApprox == 1) {
         u32 ul, uh, vl, vh;
         unpack64(mul_wide(xh, sl), ul, uh);
         unpack64(mul_wide(xl, sh), vl, vh);
@@ -120,7 +129,7 @@ __device__ __forceinline__ u64 shoup_acc(u64 acc, u64 x, u64 w, u64 ws) {
 // x*w mod q, lazy: [0, 2q) for any 64-bit x
 template <class M>
 __device__ __forceinline__ u64 shoup_lazy(u64 x, u64 w, u64 ws) {
-    return shoup_acc<M, false>(0, x, w, ws);
+    return shoup_acc<M, 0>(0, x, w, ws);
 }
 template <class M>
 __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws) {

@@ -37,25 +37,25 @@ __device__ __forceinline__ int pass_upper(int t) {
 
 // ---------------------------------------------------------------- butterflies
 // forward (Cooley-Tukey): (X, Y) -> (X + wY, X - wY), lazily.  G = global stage index 0..11.
-//  small primes: T = wY in [0,4q) (approximate Shoup quotient); bounds grow by 4q per stage, never reduced.
+//  small primes: T = wY in [0,5q) (approximate Shoup quotient); bounds grow by 5q per stage (< 2^43 after 12), never reduced.
 //  61-bit primes: T in [0,2q); stage inputs grow 2q -> 4q -> 6q -> 8q (< 2^64) and X is folded back below 2q
 //                 (3 instructions: q = 2^61 - c) on every third stage.
 template <class M, int G>
 __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     if (M::kSmall) {
-        const u64 Xo = shoup_acc<M, true>(X, Y, w, ws);
-        Y = (X + X + M::four_q) - Xo;  // X + 4q - T
+        const u64 Xo = shoup_acc<M, 2>(X, Y, w, ws);  // Y < 2^43 throughout the forward transform
+        Y = (X + X + 5 * M::q) - Xo;  // X + 5q - T
         X = Xo;
     } else {
         u64 x = X;
         if (G > 0 && (G % 3) == 0) x = fold<M>(x);  // < 8q  ->  < 2^61 + 7c < 2q
-        const u64 Xo = shoup_acc<M, false>(x, Y, w, ws);
+        const u64 Xo = shoup_acc<M, 0>(x, Y, w, ws);
         Y = (x + x + M::two_q) - Xo;  // x + 2q - T
         X = Xo;
     }
 }
 // inverse (Gentleman-Sande): (X, Y) -> (X + Y, w(X - Y)); G = global stage index 0..11
-//  small primes: inputs < 4q * 2^G, X output < 4q * 2^(G+1), Y output < 4q; never reduced.
+//  small primes: inputs < 4q * 2^G, X output < 4q * 2^(G+1), Y output < 4q; never reduced (< 2^51 at the end).
 //  61-bit primes: even stages take inputs < 2q and leave X + Y < 4q unreduced; odd stages take inputs < 4q and
 //                 fold X + Y (< 8q) back below 2q.  Y outputs are always < 2q.
 template <class M, int G>
@@ -64,7 +64,7 @@ __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
         constexpr u64 K = M::four_q << G;
         const u64 D = X + (K - Y);
         X = X + Y;
-        Y = shoup_acc<M, true>(0, D, w, ws);
+        Y = shoup_acc<M, 1>(0, D, w, ws);  // D can reach 2^51: the 16-bit estimate of variant 2 does not apply
     } else if ((G % 2) == 0) {
         const u64 D = X + (M::two_q - Y);
         X = X + Y;
