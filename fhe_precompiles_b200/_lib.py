@@ -40,10 +40,17 @@ def lib() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-            "(nvcc, sm_100a). There is no CPU fallback."
-        )
+        # not a fallback: this compiles the same CUDA library in-tree (nvcc, sm_100a) when a checkout has no binary yet
+        import subprocess
+
+        try:
+            subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(os.cpu_count() or 4)], check=True,
+                           stdout=subprocess.DEVNULL)
+        except Exception as e:  # noqa: BLE001
+            raise RuntimeError(
+                f"{LIB_PATH} is missing and could not be built ({e}); build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). There is no CPU fallback."
+            ) from e
     L = ctypes.CDLL(LIB_PATH)
     vp, sz, i32, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int32, ctypes.c_int64
     for name in PRECOMPILES:
