@@ -42,11 +42,11 @@ __device__ __forceinline__ void ntt_limb_body(u64 *limb, u64 *smem, int t) {
     u64 v[1][8];
     if (!INV) {
         load_natural(limb, v[0], t);
-        ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
+        ntt_forward<M, 1, true, false>(v, smem, kt.twf[MI], t);
         store_chunk8(limb, v[0], t);
     } else {
         load_chunk8(limb, v[0], t);
-        ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
+        ntt_inverse<M, 1, true, false>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
         store_natural(limb, v[0], t);
     }
 }
@@ -304,7 +304,7 @@ __device__ __forceinline__ void ext_ntt_body(const u64 *__restrict__ ct, int pol
     u64 v[1][8];
     load_extended<EI>(ct, poly, v[0], t);
     // 36-bit limbs stay lazy (< 2^43): the tensor's 128-bit accumulate absorbs it; 61-bit limbs must be canonical
-    ntt_forward<M, 1, !M::kSmall>(v, smem, kt.twf[MI], t);
+    ntt_forward<M, 1, !M::kSmall, false>(v, smem, kt.twf[MI], t);
     store_chunk8(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__ a, const u64 *__restrict__ b,
@@ -353,7 +353,7 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
         for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(x[r], y[r]);
     }
     // outputs stay in [0, 2q): k_floor_sk's Shoup / 128-bit reductions take any such value
-    ntt_inverse<M, 1, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI], kc.ninv_t_w[MI]);
+    ntt_inverse<M, 1, false, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI], kc.ninv_t_w[MI]);
     store_natural(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
@@ -493,7 +493,7 @@ __device__ __forceinline__ void digit_ntt_body(const u64 *__restrict__ src, u64 
     using M = Mod<MI>;
     u64 v[1][8];
     load_natural(src, v[0], t);
-    ntt_forward<M, 1, false>(v, smem, kt.twf[MI], t);  // lazy (< 2^43): the key MAC reduces a 128-bit sum anyway
+    ntt_forward<M, 1, false, false>(v, smem, kt.twf[MI], t);  // lazy (< 2^43): the key MAC reduces a 128-bit sum anyway
     store_chunk8(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_digit_ntt(const u64 *__restrict__ c3, u64 *__restrict__ dig) {
@@ -526,7 +526,7 @@ __device__ __forceinline__ void ks_intt_body(const u64 *__restrict__ dg, const u
         mac128(lo, hi, d1[r], k1[r]);
         v[0][r] = reduce128<M>(hi, lo);
     }
-    ntt_inverse<M, 1>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
+    ntt_inverse<M, 1, true, false>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
     store_natural(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_ks_intt(const u64 *__restrict__ dig, const u64 *__restrict__ rk,

@@ -21,6 +21,12 @@ constexpr int kThreads = 512;
 // physical slot of logical coefficient i inside a 4096-entry shared buffer
 __device__ __forceinline__ int swz(int i) { return i ^ ((i >> 4) & 7) ^ (((i >> 6) & 1) << 3); }
 
+// The exchange between the first two passes involves the whole CTA; the one between passes S0=3 and S0=6 stays inside
+// 64 consecutive threads (same index bits 11..9) and the one between S0=6 and S0=9 inside 8 consecutive threads (one
+// warp), so they use a 2-warp named barrier and __syncwarp(): warps of one CTA drift apart and their memory phases
+// overlap other warps' multiply phases.
+__device__ __forceinline__ void sync_group64(int t) { asm volatile("bar.sync %0, 64;" ::"r"(1 + (t >> 6)) : "memory"); }
+
 // logical index of register r (0..7) of thread t in the pass whose first stage is S0
 template <int S0>
 __device__ __forceinline__ int elem_index(int t, int r) {
@@ -190,7 +196,7 @@ __device__ __forceinline__ void smem_load(const u64 *smem, u64 (&v)[NP][8], int 
 //  in : v holds coefficients elem_index<0>(t, r) = r*512 + t   (natural order; small primes < 2^42, large < 2q)
 //  out: v holds NTT values at positions elem_index<9>(t, r) = 8*t + r, reduced to [0, q) if kCanon
 //       (else small primes < in + 48q, large primes < 8q).  Large-prime inputs must be < 2q.
-template <class M, int NP, bool kCanon>
+template <class M, int NP, bool kCanon, bool kTrailSync = true>
 __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t) {
     fwd_pass<M, NP, 0>(v, tw, pass_upper<0>(t));
     smem_store<NP, 0>(smem, v, t);
@@ -198,11 +204,11 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
     smem_load<NP, 3>(smem, v, t);
     fwd_pass<M, NP, 3>(v, tw, pass_upper<3>(t));
     smem_store<NP, 3>(smem, v, t);
-    __syncthreads();
+    sync_group64(t);
     smem_load<NP, 6>(smem, v, t);
     fwd_pass<M, NP, 6>(v, tw, pass_upper<6>(t));
     smem_store<NP, 6>(smem, v, t);
-    __syncthreads();
+    __syncwarp();
     smem_load<NP, 9>(smem, v, t);
     fwd_pass<M, NP, 9>(v, tw, pass_upper<9>(t));
     if (kCanon) {
@@ -211,30 +217,30 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
 #pragma unroll
             for (int r = 0; r < 8; r++) v[p][r] = canon<M>(v[p][r]);  // small: < 2^43; large: < 8q
     }
-    __syncthreads();  // smem may be reused by the caller
+    if (kTrailSync) __syncthreads();  // smem may be reused by the caller
 }
 
 // Inverse NTT of NP polynomials.
 //  in : v holds NTT values at positions 8*t + r, each < 2q (small primes: < 4q)
 //  out: v holds coefficients r*512 + t, multiplied by the scalar sc (scw = sc * last-stage twiddle), in [0, q)
 //       ([0, 2q) if !kCanon)
-template <class M, int NP, bool kCanon = true>
+template <class M, int NP, bool kCanon = true, bool kTrailSync = true>
 __device__ __forceinline__ void ntt_inverse(u64 (&v)[NP][8], u64 *smem, const ulonglong2 *__restrict__ tw, int t, const Shoup &sc,
                                             const Shoup &scw) {
     inv_pass<M, NP, 9, 0>(v, tw, pass_upper<9>(t));
     smem_store<NP, 9>(smem, v, t);
-    __syncthreads();
+    __syncwarp();
     smem_load<NP, 6>(smem, v, t);
     inv_pass<M, NP, 6, 3>(v, tw, pass_upper<6>(t));
     smem_store<NP, 6>(smem, v, t);
-    __syncthreads();
+    sync_group64(t);
     smem_load<NP, 3>(smem, v, t);
     inv_pass<M, NP, 3, 6>(v, tw, pass_upper<3>(t));
     smem_store<NP, 3>(smem, v, t);
     __syncthreads();
     smem_load<NP, 0>(smem, v, t);
     inv_pass<M, NP, 0, 9, true, kCanon>(v, tw, pass_upper<0>(t), &sc, &scw);
-    __syncthreads();
+    if (kTrailSync) __syncthreads();
 }
 
 // ---------------------------------------------------------------- global <-> register helpers
