@@ -175,7 +175,9 @@ const char *fhe_b200_op_name(int32_t index) { return (index >= 0 && index < kNum
 
 int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     if (!calls || n == 0) return 0;
-    size_t nt = host_threads > 0 ? (size_t)host_threads : (size_t)std::thread::hardware_concurrency();
+    // default: two workers per core -- each call blocks ~0.3 ms on its GPU lane, during which another worker can run
+    // the zstd codec of the next call
+    size_t nt = host_threads > 0 ? (size_t)host_threads : 2 * (size_t)std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
     if (nt > n) nt = n;
     std::atomic<size_t> next{0};

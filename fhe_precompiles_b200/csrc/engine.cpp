@@ -50,7 +50,7 @@ Engine::Engine() {
     if ((size_t)n_devices_ > max_dev) n_devices_ = (int)max_dev;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 2048);
     fused_ = env_size("FHE_B200_FUSED", 0) != 0;
-    const size_t lanes_per_dev = env_size("FHE_B200_LANES", 16);
+    const size_t lanes_per_dev = env_size("FHE_B200_LANES", 32);
     for (int d = 0; d < n_devices_; d++) {
         device_context(d);
         for (size_t i = 0; i < lanes_per_dev; i++) {
