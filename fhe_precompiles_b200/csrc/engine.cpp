@@ -50,6 +50,10 @@ Engine::Engine() {
     if ((size_t)n_devices_ > max_dev) n_devices_ = (int)max_dev;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 2048);
     fused_ = env_size("FHE_B200_FUSED", 0) != 0;
+    {
+        const char *v = getenv("FHE_B200_SUBCHUNK_OPS");
+        subchunk_ops_ = (v && *v) ? (size_t)atoll(v) : 0;  // opt-in L2-resident fork/join pipeline (e.g. 96); 0 = off
+    }
     const size_t lanes_per_dev = env_size("FHE_B200_LANES", 32);
     for (int d = 0; d < n_devices_; d++) {
         device_context(d);
@@ -293,9 +297,51 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
     TIMED(3, launch_relin_finish(c3, m.ks, out, c, s), "relin_finish");
 }
 
+void Engine::mul_relin_forked(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
+                              cudaStream_t s) {
+    {
+        std::lock_guard<std::mutex> lk(arena_mu_);
+        if (forks_.size() < (size_t)n_devices_) forks_.resize((size_t)n_devices_);
+    }
+    ForkSet &F = forks_[(size_t)device];
+    const size_t sub = subchunk_ops_;
+    if (!F.ready || F.ops < sub) {
+        cuda_throw(cudaDeviceSynchronize(), "sync before fork-set rebuild");
+        for (int i = 0; i < kForkStreams; i++) {
+            if (!F.ready) {
+                cuda_throw(cudaStreamCreateWithFlags(&F.stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
+                cuda_throw(cudaEventCreateWithFlags(&F.join[i], cudaEventDisableTiming), "cudaEventCreate");
+            }
+            if (F.scratch[i]) cudaFree(F.scratch[i]);
+            cuda_throw(cudaMalloc((void **)&F.scratch[i], sub * kScratchLimbsPerOp * kN * 8), "cudaMalloc(sub scratch)");
+        }
+        if (!F.ready) cuda_throw(cudaEventCreateWithFlags(&F.fork, cudaEventDisableTiming), "cudaEventCreate");
+        F.ready = true;
+        F.ops = sub;
+    }
+    cuda_throw(cudaEventRecord(F.fork, s), "fork record");
+    for (int i = 0; i < kForkStreams; i++) cuda_throw(cudaStreamWaitEvent(F.stream[i], F.fork, 0), "fork wait");
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += sub, k++) {
+        const size_t c = n - off < sub ? n - off : sub;
+        const int i = (int)(k % kForkStreams);
+        ScratchMap m(F.scratch[i], sub);
+        enqueue_mul(a + off * kCtWords, b + off * kCtWords, m, c, F.stream[i], timing_);
+        enqueue_relin(m.c3, rk, out + off * kCtWords, m, c, F.stream[i], timing_);
+    }
+    for (int i = 0; i < kForkStreams; i++) {
+        cuda_throw(cudaEventRecord(F.join[i], F.stream[i]), "join record");
+        cuda_throw(cudaStreamWaitEvent(s, F.join[i], 0), "join wait");
+    }
+}
+
 void Engine::mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
                        cudaStream_t s) {
     device_context(device);
+    if (subchunk_ops_ && n > subchunk_ops_) {
+        mul_relin_forked(device, a, b, rk, out, n, s);
+        return;
+    }
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
     ScratchMap m(scratch(device, chunk), chunk);
     for (size_t off = 0; off < n; off += chunk) {

@@ -164,6 +164,22 @@ class Engine {
     std::vector<cudaEvent_t> event_pool_;
     cudaEvent_t take_event();
 
+    // L2-resident pipelining of multiply+relinearise: the batch is cut into sub-chunks whose scratch (1.7 MB per op)
+    // fits the 126 MB L2 and the sub-chunks alternate over kForkStreams internal streams, so that one sub-chunk's
+    // kernel tails overlap the other's heads while producer->consumer scratch stays on chip. 0 = off.
+    static constexpr int kForkStreams = 2;
+    size_t subchunk_ops_ = 0;
+    struct ForkSet {
+        bool ready = false;
+        cudaStream_t stream[kForkStreams];
+        cudaEvent_t fork, join[kForkStreams];
+        uint64_t *scratch[kForkStreams] = {nullptr, nullptr};
+        size_t ops = 0;
+    };
+    std::vector<ForkSet> forks_;
+    void mul_relin_forked(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
+                          cudaStream_t s);
+
     struct Arena {
         uint64_t *p = nullptr;
         size_t ops = 0;

@@ -18,9 +18,8 @@ def _call(name: str, data: bytes) -> bytes:
     L = _lib.lib()
     out = ctypes.c_void_p()
     out_len = ctypes.c_int64()
-    buf = (ctypes.c_char * len(data)).from_buffer_copy(data) if data else None
-    rc = getattr(L, "c_fhe_" + name)(ctypes.cast(buf, ctypes.c_void_p) if buf is not None else None, len(data),
-                                     ctypes.byref(out), ctypes.byref(out_len))
+    # `bytes` is passed by reference (ctypes hands the C side a pointer into the object): no copy of the ~590 KB input
+    rc = getattr(L, "c_fhe_" + name)(data if data else None, len(data), ctypes.byref(out), ctypes.byref(out_len))
     if rc != 0:
         raise FheError(rc, _lib.last_error() if rc == 7 else "")
     try:
