@@ -1,0 +1,195 @@
+"""TEST INFRASTRUCTURE ONLY -- attempt at a bit-exact restatement of SEAL 4.0's seeded public-key encryption
+(the path behind `FheApp::encrypt`, /root/reference/src/fhe.rs:594-618, pinned there by SHA-512 known answers at
+fhe.rs:2111-2116 / 2175-2180 / 2234-2239).
+
+sunscreen 0.8.1 / seal_fhe / SEAL are not vendored, so every piece below is a restatement of published algorithms:
+  * BLAKE2xb (BLAKE2X spec) as SEAL's Blake2xbPRNG uses it: 4096-byte buffers, blake2xb(out, 4096, counter_le64, key=seed)
+  * SEAL util::sample_poly_ternary: std::uniform_int_distribution<uint64_t>(0, 2) over a 32-bit engine -- libstdc++'s
+    algorithm is version dependent, both known variants are provided
+  * SEAL util::sample_poly_cbd (6 bytes per coefficient, 21 + 21 bits)
+  * SEAL util::encrypt_zero_asymmetric + RNSTool::divide_and_round_q_last_inplace + multiply_add_plain_with_scaling_variant
+`scripts/kat_search.py` tries the combinations against the reference's known answers.
+"""
+from __future__ import annotations
+
+import struct
+from typing import Callable, List
+
+import numpy as np
+
+from . import bfv
+from . import formats as F
+
+MASK64 = (1 << 64) - 1
+IV = [0x6A09E667F3BCC908, 0xBB67AE8584CAA73B, 0x3C6EF372FE94F82B, 0xA54FF53A5F1D36F1,
+      0x510E527FADE682D1, 0x9B05688C2B3E6C1F, 0x1F83D9ABFB41BD6B, 0x5BE0CD19137E2179]
+SIGMA = [
+    [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15], [14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3],
+    [11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4], [7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8],
+    [9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13], [2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9],
+    [12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11], [13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10],
+    [6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5], [10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0],
+    [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15], [14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3],
+]
+
+
+def _rotr(x: int, n: int) -> int:
+    return ((x >> n) | (x << (64 - n))) & MASK64
+
+
+def _compress(h: List[int], block: bytes, t: int, last: bool) -> None:
+    m = struct.unpack("<16Q", block)
+    v = h[:] + IV[:]
+    v[12] ^= t & MASK64
+    v[13] ^= (t >> 64) & MASK64
+    if last:
+        v[14] ^= MASK64
+    for r in range(12):
+        s = SIGMA[r]
+        for i, (a, b, c, d) in enumerate(((0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15),
+                                          (0, 5, 10, 15), (1, 6, 11, 12), (2, 7, 8, 13), (3, 4, 9, 14))):
+            x, y = m[s[2 * i]], m[s[2 * i + 1]]
+            v[a] = (v[a] + v[b] + x) & MASK64
+            v[d] = _rotr(v[d] ^ v[a], 32)
+            v[c] = (v[c] + v[d]) & MASK64
+            v[b] = _rotr(v[b] ^ v[c], 24)
+            v[a] = (v[a] + v[b] + y) & MASK64
+            v[d] = _rotr(v[d] ^ v[a], 16)
+            v[c] = (v[c] + v[d]) & MASK64
+            v[b] = _rotr(v[b] ^ v[c], 63)
+    for i in range(8):
+        h[i] ^= v[i] ^ v[i + 8]
+
+
+def blake2b_param(data: bytes, param: bytes, key: bytes = b"", outlen: int = 64) -> bytes:
+    """BLAKE2b with an explicit 64-byte parameter block (RFC 7693 section 2.5 layout)."""
+    assert len(param) == 64
+    h = [iv ^ p for iv, p in zip(IV, struct.unpack("<8Q", param))]
+    buf = (key.ljust(128, b"\0") if key else b"") + data
+    t = 0
+    while len(buf) > 128:
+        t += 128
+        _compress(h, buf[:128], t, False)
+        buf = buf[128:]
+    t += len(buf)
+    _compress(h, buf.ljust(128, b"\0"), t, True)
+    return struct.pack("<8Q", *h)[:outlen]
+
+
+def _param(digest_length, key_length, fanout, depth, leaf_length, node_offset, xof_length, node_depth, inner_length) -> bytes:
+    return struct.pack("<BBBBIIIBB", digest_length, key_length, fanout, depth, leaf_length, node_offset, xof_length,
+                       node_depth, inner_length) + b"\0" * 14 + b"\0" * 16 + b"\0" * 16
+
+
+def blake2xb(outlen: int, data: bytes, key: bytes) -> bytes:
+    """BLAKE2Xb as in the BLAKE2 reference blake2xb.c (which SEAL bundles)."""
+    root = blake2b_param(data, _param(64, len(key), 1, 1, 0, 0, outlen, 0, 0), key, 64)
+    out = b""
+    i = 0
+    while len(out) < outlen:
+        bs = min(64, outlen - len(out))
+        out += blake2b_param(root, _param(bs, 0, 0, 0, 64, i, outlen, 0, 64), b"", bs)
+        i += 1
+    return out
+
+
+class Blake2xbPRNG:
+    """SEAL Blake2xbPRNG: 4096-byte buffer refilled with blake2xb(counter as LE u64, key = 64-byte seed)."""
+
+    BUF = 4096
+
+    def __init__(self, seed_words: List[int]) -> None:
+        self.seed = struct.pack("<8Q", *seed_words)
+        self.counter = 0
+        self.buf = b""
+        self.pos = 0
+        self._refill()
+
+    def _refill(self) -> None:
+        self.buf = blake2xb(self.BUF, struct.pack("<Q", self.counter), self.seed)
+        self.counter += 1
+        self.pos = 0
+
+    def generate(self, n: int) -> bytes:
+        out = b""
+        while n:
+            take = min(n, self.BUF - self.pos)
+            out += self.buf[self.pos : self.pos + take]
+            self.pos += take
+            n -= take
+            if self.pos == self.BUF:
+                self._refill()
+        return out
+
+    def u32(self) -> int:
+        return struct.unpack("<I", self.generate(4))[0]
+
+
+# ---- std::uniform_int_distribution<uint64_t>(0, 2) over a 32-bit URNG, libstdc++
+def uniform3_lemire(prng: Blake2xbPRNG) -> int:
+    """libstdc++ >= 11: _S_nd (Lemire's nearly divisionless) because the engine range is exactly 2^32."""
+    rng = 3
+    product = prng.u32() * rng
+    low = product & 0xFFFFFFFF
+    if low < rng:
+        threshold = ((1 << 32) - rng) % rng
+        while low < threshold:
+            product = prng.u32() * rng
+            low = product & 0xFFFFFFFF
+    return product >> 32
+
+
+def uniform3_downscale(prng: Blake2xbPRNG) -> int:
+    """libstdc++ <= 10: classic downscaling with rejection."""
+    uerange = 3
+    scaling = 0xFFFFFFFF // uerange
+    past = uerange * scaling
+    while True:
+        r = prng.u32()
+        if r < past:
+            return r // scaling
+
+
+def sample_ternary(prng: Blake2xbPRNG, uniform3: Callable[[Blake2xbPRNG], int], n: int = F.N) -> np.ndarray:
+    return np.array([uniform3(prng) - 1 for _ in range(n)], dtype=np.int64)
+
+
+def sample_cbd(prng: Blake2xbPRNG, n: int = F.N) -> np.ndarray:
+    raw = np.frombuffer(prng.generate(6 * n), dtype=np.uint8).reshape(n, 6).copy()
+    raw[:, 2] &= 0x1F
+    raw[:, 5] &= 0x1F
+    pop = np.unpackbits(raw, axis=1).reshape(n, 6, 8).sum(axis=2).astype(np.int64)
+    return pop[:, 0] + pop[:, 1] + pop[:, 2] - pop[:, 3] - pop[:, 4] - pop[:, 5]
+
+
+def encrypt_seeded(pk: np.ndarray, plain: np.ndarray, seed_words: List[int], uniform3=uniform3_lemire,
+                   noise_before_u: bool = False) -> np.ndarray:
+    """SEAL Encryptor::encrypt (BFV, asymmetric, with modulus switching) with a seeded Blake2xb PRNG.
+    pk: [2][3][N] NTT form; returns the data-level ciphertext [2][2][N]."""
+    mods = bfv.moduli()[:3]
+    prng = Blake2xbPRNG(seed_words)
+    u = sample_ternary(prng, uniform3)
+    c = np.zeros((2, 3, F.N), dtype=np.uint64)
+    for J in range(3):
+        q = mods[J]
+        uj = np.where(u < 0, q - 1, u).astype(np.uint64)
+        un = bfv.ntt_fwd(uj, J)
+        for j in range(2):
+            prod = (un.astype(object) * pk[j, J].astype(object)) % q
+            c[j, J] = bfv.ntt_inv(np.array(prod, dtype=np.uint64), J)
+    for j in range(2):
+        e = sample_cbd(prng)
+        for J in range(3):
+            q = mods[J]
+            c[j, J] = ((c[j, J].astype(object) + np.where(e < 0, q + e, e).astype(object)) % q).astype(np.uint64)
+    # RNSTool::divide_and_round_q_last_inplace per polynomial
+    P = mods[2]
+    half = P >> 1
+    out = np.zeros((2, 2, F.N), dtype=np.uint64)
+    for j in range(2):
+        last = (c[j, 2].astype(object) + half) % P
+        for l in range(2):
+            q = mods[l]
+            t = (last % q - half % q) % q
+            out[j, l] = (((c[j, l].astype(object) - t) % q) * pow(P, -1, q) % q).astype(np.uint64)
+    return bfv.add_plain(out, plain)
