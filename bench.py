@@ -210,7 +210,7 @@ def run_reference(args) -> None:
 
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(2)
-    sample = max(cores * 2, 32)
+    sample = max(cores * 16, 256)  # ~0.1 s of wall time per step with every host thread busy
     a = np.empty((sample, 2, 2, N), dtype=np.uint64)
     b = np.empty_like(a)
     for l in range(2):
