@@ -44,13 +44,29 @@ def rand_ct(n, seed):
 
 
 def main():
-    fdev.init(0)
-    res = {}
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # barrier + max-over-ranks only (gloo): the configs shard with no collective
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    from fhe_precompiles_b200.sharding import call_cost, max_over_ranks, shard_by_cost, shard_range
+
+    def sync():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    fdev.init(local)
+    res = {"n_gpus": world}
     # ---- config 2
     ntt = []
     g = torch.Generator(device="cuda")
     g.manual_seed(1)
-    for batch in (1, 4, 16, 64, 256, 1024, 4096, 16384, 65536):
+    for batch in ((1, 4, 16, 64, 256, 1024, 4096, 16384, 65536) if world == 1 else ()):
         x = torch.empty((batch, 3, N), dtype=torch.int64, device="cuda")
         for l in range(3):
             x[:, l, :] = torch.randint(0, MODULI[l], (batch, N), generator=g, device="cuda", dtype=torch.int64)
@@ -69,6 +85,11 @@ def main():
     n_calls = 65536
     ops = rng.integers(0, 3, n_calls)      # add, sub, mul
     shapes = rng.integers(0, 3, n_calls)   # ctct, ctpt, ptct
+    # cost-weighted sharding of the calls over the ranks (mul ct x ct dominates); every rank runs only its share
+    names = [f"{('add', 'sub', 'mul')[o]}_" + ("cipheri64_cipheri64" if s == 0 else "cipheri64_i64" if s == 1 else "i64_cipheri64")
+             for o, s in zip(ops, shapes)]
+    mine = shard_by_cost([call_cost(nm) for nm in names], world)[rank]
+    ops, shapes = ops[mine], shapes[mine]
     counts = {(o, s): int(((ops == o) & (shapes == s)).sum()) for o in range(3) for s in range(3)}
     pool = 4096
     a, b = rand_ct(pool, 10), rand_ct(pool, 11)
@@ -97,32 +118,43 @@ def main():
         for (o, s), n in counts.items():
             run_family(o, s, n)
 
-    ms = timeit(run_all, iters=3, warm=1)
-    res["config4_mixed"] = {"calls": n_calls, "ms": ms, "calls_per_s": n_calls / ms * 1e3,
+    sync()
+    ms = max_over_ranks(timeit(run_all, iters=3, warm=1), dist)
+    sync()
+    res["config4_mixed"] = {"calls": n_calls, "ms": ms, "calls_per_s": n_calls / ms * 1e3, "calls_on_rank0": len(mine),
                             "mix": {f"{'add sub mul'.split()[o]}_{'ctct ctpt ptct'.split()[s]}": n for (o, s), n in counts.items()}}
     # ---- config 5: encrypt 16,384 random i64 under the network key, decrypt, compare
-    n = 16384
-    vals = rng.integers(-(2**62), 2**62, n)
+    n_total = 16384
+    lo, hi = shard_range(n_total, rank, world)
+    n = hi - lo
+    vals = rng.integers(-(2**62), 2**62, n_total)[lo:hi]
     mag = np.abs(vals).astype(np.uint64)
     bits = ((mag[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & 1).astype(np.int64)
     coeff = np.where(vals[:, None] < 0, bits * 4095, bits)
     pl = np.zeros((n, N), dtype=np.int16)
     pl[:, :64] = coeff.astype(np.uint16).view(np.int16)
     dpl = torch.from_numpy(pl).cuda()
-    seeds = torch.arange(n, dtype=torch.int64, device="cuda") + 7
+    seeds = torch.arange(lo, hi, dtype=torch.int64, device="cuda") + 7
     sk = torch.empty((3, N), dtype=torch.int64)
     from fhe_precompiles_b200 import _lib
     pri = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pri"), "rb").read()
     assert _lib.lib().fhe_b200_parse_private_key(pri, len(pri), sk.data_ptr()) == 0
     dsk = sk.cuda()
-    enc_ms = timeit(lambda: fdev.encrypt(pk, dpl, seeds), iters=3, warm=1)
+    sync()
+    enc_ms = max_over_ranks(timeit(lambda: fdev.encrypt(pk, dpl, seeds), iters=3, warm=1), dist)
     ct = fdev.encrypt(pk, dpl, seeds)
-    dec_ms = timeit(lambda: fdev.decrypt(ct, dsk), iters=3, warm=1)
+    sync()
+    dec_ms = max_over_ranks(timeit(lambda: fdev.decrypt(ct, dsk), iters=3, warm=1), dist)
     back = fdev.decrypt(ct, dsk)
-    res["config5_encrypt_decrypt"] = {"plaintexts": n, "encrypt_ms": enc_ms, "encrypt_per_s": n / enc_ms * 1e3,
-                                      "decrypt_ms": dec_ms, "decrypt_per_s": n / dec_ms * 1e3,
-                                      "roundtrip_all_equal": bool(torch.equal(back, dpl))}
-    print(json.dumps(res))
+    ok = float(torch.equal(back, dpl))
+    ok = -max_over_ranks(-ok, dist)  # min over ranks
+    res["config5_encrypt_decrypt"] = {"plaintexts": n_total, "encrypt_ms": enc_ms, "encrypt_per_s": n_total / enc_ms * 1e3,
+                                      "decrypt_ms": dec_ms, "decrypt_per_s": n_total / dec_ms * 1e3,
+                                      "roundtrip_all_equal": bool(ok)}
+    if rank == 0:
+        print(json.dumps(res))
+    if dist is not None:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
