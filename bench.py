@@ -291,6 +291,7 @@ def main() -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("gloo")
 
+    os.environ.setdefault("FHE_B200_DEVICES", str(local_rank))  # this rank's byte-surface calls stay on its own GPU
     from fhe_precompiles_b200 import device as fdev
 
     fdev.init(local_rank)

@@ -54,8 +54,26 @@ Engine::Engine() {
         const char *v = getenv("FHE_B200_SUBCHUNK_OPS");
         subchunk_ops_ = (v && *v) ? (size_t)atoll(v) : 0;  // opt-in L2-resident fork/join pipeline (e.g. 96); 0 = off
     }
+    // byte-surface devices: FHE_B200_DEVICES="0,3" restricts single calls and batches to those GPUs (default: all).
+    // Under a one-process-per-GPU launcher each rank sets it to its own device.
+    if (const char *v = getenv("FHE_B200_DEVICES")) {
+        for (const char *p = v; *p;) {
+            char *end = nullptr;
+            long d = strtol(p, &end, 10);
+            if (end == p) break;
+            if (d >= 0 && d < n_devices_) lane_devices_.push_back((int)d);
+            p = (*end == ',') ? end + 1 : end;
+        }
+    }
+    if (lane_devices_.empty())
+        for (int d = 0; d < n_devices_; d++) lane_devices_.push_back(d);
+}
+
+// Lanes (stream + pinned staging + device buffers for one in-flight call) are created on the first byte-surface call,
+// so device-resident users never pay for them.  lane_mu_ held.
+void Engine::create_lanes() {
     const size_t lanes_per_dev = env_size("FHE_B200_LANES", 32);
-    for (int d = 0; d < n_devices_; d++) {
+    for (int d : lane_devices_) {
         device_context(d);
         for (size_t i = 0; i < lanes_per_dev; i++) {
             std::unique_ptr<Lane> l(new Lane());
@@ -77,6 +95,7 @@ Engine::Engine() {
 
 Lane *Engine::acquire_lane() {
     std::unique_lock<std::mutex> lk(lane_mu_);
+    if (lanes_.empty()) create_lanes();
     for (;;) {
         for (size_t k = 0; k < lanes_.size(); k++) {
             Lane *l = lanes_[(next_lane_ + k) % lanes_.size()].get();
@@ -140,6 +159,8 @@ KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
             for (size_t i = 0; i < keys_.size(); i++)
                 if (keys_[i]->users == 0 && (victim < 0 || keys_[i]->last_use < keys_[(size_t)victim]->last_use)) victim = (long)i;
             if (victim >= 0) {
+                int cur = 0;
+                cudaGetDevice(&cur);  // the caller has already selected its lane's device: restore it afterwards
                 for (int d = 0; d < n_devices_; d++) {
                     uint64_t *ptrs[2] = {keys_[(size_t)victim]->d_rk[(size_t)d], keys_[(size_t)victim]->d_pk[(size_t)d]};
                     for (uint64_t *ptr : ptrs)
@@ -148,6 +169,7 @@ KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
                             cudaFree(ptr);  // no holder left: every user synchronised its stream before unpinning
                         }
                 }
+                cudaSetDevice(cur);
                 keys_.erase(keys_.begin() + victim);
             }
         }

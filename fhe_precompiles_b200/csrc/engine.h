@@ -115,6 +115,8 @@ class Engine {
 
    private:
     Engine();
+    void create_lanes();
+    std::vector<int> lane_devices_;
     Lane *acquire_lane();
     void release_lane(Lane *);
 
