@@ -411,3 +411,31 @@ def test_concurrent_calls_and_key_cache_eviction(keys, monkeypatch):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_second_device_and_cross_device_batch(dev, keys):
+    """per-device contexts: the same kernels on cuda:1 (own twiddles / constants / key copies) and a byte-surface batch whose
+    calls are spread over every GPU. Skipped on single-GPU boxes."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from fhe_precompiles_b200 import FHE, pack
+
+    dev.init(1)
+    a, b = edge_ct(3, 31), edge_ct(3, 32)[::-1].copy()
+    want = np.stack([bfv.mul_relin(x, y, keys.rk) for x, y in zip(a, b)])
+    t1 = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).to("cuda:1")
+    with torch.cuda.device(1):
+        got = dev.mul_relin(t1(a), t1(b), t1(keys.rk)).cpu().numpy().view(np.uint64)
+        x = np.random.default_rng(1).integers(0, MODULI[4], size=(3, N), dtype=np.uint64)
+        d = t1(x)
+        dev.ntt_(d, [4])
+        assert np.array_equal(d.cpu().numpy().view(np.uint64), bfv.ntt_fwd(x, 4))
+    assert np.array_equal(got, want)
+    ca, cb = encrypt_value(keys, "i64", 9, 1), encrypt_value(keys, "i64", -5, 2)
+    sa, sb = (F.make_ciphertext("i64", c).to_bytes() for c in (ca, cb))
+    packed = pack.pack_binary_operation(keys.pub_bytes, sa, sb)
+    wm = F.make_ciphertext("i64", bfv.mul_relin(ca, cb, keys.rk)).to_bytes()
+    res = FHE.run_batch([("mul_cipheri64_cipheri64", packed)] * 24, host_threads=8)
+    assert all(st == 0 and out == wm for st, out in res)
