@@ -130,3 +130,45 @@ def test_library_codec_rejects_malformed_inputs(lib, keys):
     pk = np.zeros(2 * 3 * N, dtype=np.uint64)
     assert lib.fhe_b200_parse_public_key(keys.pub_bytes[:-3], len(keys.pub_bytes) - 3, pk.ctypes.data, None) == 3
     assert lib.fhe_b200_parse_public_key(keys.pri_bytes, len(keys.pri_bytes), pk.ctypes.data, None) == 3
+
+
+def test_codec_survives_mutated_inputs(lib, keys):
+    """boundary hardening: random truncations, bit flips and length-field edits of valid ciphertext / key bytes must come
+    back as error codes (or parse cleanly), never crash or read out of bounds (the reference panics on some of these)."""
+    rng = np.random.default_rng(1234)
+    good_ct = open(os.path.join(ROOT, "tests/golden/ct_i64_16_seed11.bin"), "rb").read()
+    words = np.zeros(4 * N, dtype=np.uint64)
+    pk_words = np.zeros(2 * 3 * N, dtype=np.uint64)
+    rk_words = np.zeros(2 * 2 * 3 * N, dtype=np.uint64)
+    dt = ctypes.create_string_buffer(64)  # deliberately small: long type strings must be truncated, not overflow
+
+    def mutate(buf: bytes) -> bytes:
+        b = bytearray(buf)
+        kind = rng.integers(0, 5)
+        if kind == 0:
+            return bytes(b[: rng.integers(0, len(b))])
+        if kind == 1:
+            for _ in range(rng.integers(1, 8)):
+                b[rng.integers(0, len(b))] ^= 1 << rng.integers(0, 8)
+            return bytes(b)
+        if kind == 2:  # clobber one of the early length / count fields
+            off = int(rng.integers(0, 200))
+            b[off : off + 8] = int(rng.integers(0, 2**63)).to_bytes(8, "little")
+            return bytes(b)
+        if kind == 3:
+            return bytes(b) + bytes(rng.integers(0, 256, size=rng.integers(1, 64), dtype=np.uint8))
+        i = rng.integers(0, len(b) - 16)
+        b[i : i + 16] = bytes(rng.integers(0, 256, size=16, dtype=np.uint8))
+        return bytes(b)
+
+    codes = set()
+    for _ in range(150):
+        m = mutate(good_ct)
+        codes.add(lib.fhe_b200_parse_ciphertext(m, len(m), words.ctypes.data, dt, 64))
+    for _ in range(40):
+        m = mutate(keys.pub_bytes)
+        codes.add(lib.fhe_b200_parse_public_key(m, len(m), pk_words.ctypes.data, rk_words.ctypes.data))
+        m = mutate(keys.pri_bytes)
+        codes.add(lib.fhe_b200_parse_private_key(m, len(m), pk_words.ctypes.data))
+    assert codes <= {0, 3, 7}, codes
+    assert 3 in codes
