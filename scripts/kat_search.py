@@ -33,10 +33,11 @@ def main():
     plain = bfv.encode("u256", 12)
     cts = {}
     for uname, ufn in (("lemire", S.uniform3_lemire), ("downscale", S.uniform3_downscale)):
-        ct = S.encrypt_seeded(pk, plain, list(seed), ufn)
-        p, budget = bfv.decrypt(ct, sk)
-        print(uname, "decrypts to", bfv.decode("u256", p), "budget", budget)
-        cts[uname] = ct
+        for nname, nfn in (("normal", S.sample_clipped_normal), ("cbd", S.sample_cbd)):
+            ct = S.encrypt_seeded(pk, plain, list(seed), ufn, nfn)
+            p, budget = bfv.decrypt(ct, sk)
+            print(uname, nname, "decrypts to", bfv.decode("u256", p), "budget", budget)
+            cts[uname + "+" + nname] = ct
     bases = ["sunscreen::types::bfv::unsigned::Unsigned", "sunscreen::types::bfv::Unsigned", "sunscreen::types::Unsigned",
              "sunscreen_runtime::types::bfv::unsigned::Unsigned", "Unsigned"]
     suffixes = ["", "<4>", "256", "<256>", "4", "<4usize>", "<4_usize>"]

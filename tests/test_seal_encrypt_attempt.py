@@ -33,3 +33,20 @@ def test_seeded_encryption_is_valid_and_deterministic(keys):
     assert set(np.unique(u)) == {-1, 0, 1} and abs(u.mean()) < 0.05
     e = S.sample_cbd(prng)
     assert np.abs(e).max() <= 21 and 2.9 < e.std() < 3.6
+    g = S.sample_clipped_normal(prng)
+    assert np.abs(g).max() <= 19 and 0.22 < (g == 0).mean() < 0.27 and 7.0 < g.var() < 8.8
+
+
+def test_key_fixture_errors_identify_the_truncated_gaussian_sampler(keys):
+    """every key file's error polynomial has P(0) ~ 0.245 and variance ~ 7.9: sigma = 3.2 Gaussian truncated toward zero
+    (SEAL_USE_GAUSSIAN_NOISE), not the centred binomial of stock SEAL 4.0 (P(0) = 0.122, variance 10.5)"""
+    from helpers import MODULI
+
+    errs = []
+    for pk, sk in ((keys.pk, keys.sk), (keys.net_pk, keys.net_sk)):
+        q = MODULI[0]
+        e = (pk[0, 0].astype(object) + pk[1, 0].astype(object) * sk[0].astype(object)) % q
+        e = bfv.ntt_inv(np.array(e, dtype=np.uint64), 0).astype(np.int64)
+        errs.append(np.where(e > q // 2, e - q, e))
+    e = np.concatenate(errs)
+    assert 0.22 < (e == 0).mean() < 0.27 and 7.2 < e.var() < 8.6 and np.abs(e).max() <= 19
