@@ -658,7 +658,8 @@ __global__ void __launch_bounds__(256) k_decrypt_round(const u64 *__restrict__ x
 // K11b: public-key encryption   (SEAL Encryptor::encrypt_zero_asymmetric at the key level +
 //       RNSTool::divide_and_round_q_last_inplace + multiply_add_plain_with_scaling_variant; fhe.rs:594-618)
 // Randomness is a counter-based generator keyed by a caller-supplied 64-bit seed per op: a valid BFV
-// encryption, deterministic in (seed, plaintext, key), NOT SEAL's Blake2xb sampler stream.
+// encryption with SEAL's distributions (uniform ternary u, truncated sigma = 3.2 Gaussian errors), deterministic in
+// (seed, plaintext, key), NOT SEAL's Blake2xb sampler stream.
 //   k_encrypt_core   : INTT_J(pk_j[J] * NTT_J(u)) + e_j    grid (3 moduli, ops) -> encbuf [op][2][3][N]
 //   k_encrypt_finish : drop P with rounding, add Delta*m   per coefficient      -> ct [op][2][2][N]
 // =====================================================================================
@@ -677,10 +678,15 @@ __device__ __forceinline__ int sample_ternary(u64 seed, int i) {
     }
     return 0;
 }
-// centred binomial error, 21 + 21 bits (sigma ~ 3.24, |e| <= 21) -- SEAL 4.0's default noise shape
-__device__ __forceinline__ int sample_cbd(u64 seed, int poly, int i) {
+// Error sample with the distribution the reference's SEAL build uses (identified from its key fixtures, DESIGN.md
+// section 7): Gaussian, sigma = 3.2, clipped at 6 sigma, truncated toward zero (P(0) = 0.245, variance 7.9).
+// Box-Muller on two 24-bit uniforms from the counter-based generator; 24 bits reach 5.77 sigma, inside the clip.
+__device__ __forceinline__ int sample_noise(u64 seed, int poly, int i) {
     u64 r = mix64(seed ^ ((0x65727200ull + (u64)poly) << 32) ^ (u64)i);
-    return __popcll(r & 0x1fffffull) - __popcll((r >> 21) & 0x1fffffull);
+    const float u1 = ((float)(u32)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
+    const float u2 = (float)(u32)((r >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
+    const float g = sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2) * 3.2f;
+    return (int)fminf(fmaxf(g, -19.0f), 19.0f);
 }
 template <int MI>
 __device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, u64 seed, u64 *__restrict__ enc, u64 *smem, int t) {
@@ -705,7 +711,7 @@ __device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, u6
     for (int j = 0; j < 2; j++) {
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            int e = sample_cbd(seed, j, r * kThreads + t);
+            int e = sample_noise(seed, j, r * kThreads + t);
             u64 ev = e < 0 ? M::q - (u64)(-e) : (u64)e;
             w[j][r] = addmod<M>(w[j][r], ev);
         }
