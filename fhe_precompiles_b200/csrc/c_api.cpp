@@ -3,6 +3,8 @@
 #include "../../include/fhe_precompiles_b200.h"
 #pragma GCC visibility pop
 
+#include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -173,28 +175,71 @@ int32_t fhe_b200_op_index(const char *name) {
 }
 const char *fhe_b200_op_name(int32_t index) { return (index >= 0 && index < kNumOps) ? kOps[index].name : nullptr; }
 
+// ops 0..35 of kOps are the binary precompiles, laid out type-major: index = 9 * type + 3 * op + shape
+static bool binary_desc(int32_t index, Op *op, Shape *shape, Kind *kind) {
+    if (index < 0 || index >= 36) return false;
+    static const Kind kinds[4] = {Kind::U256, Kind::U64, Kind::I64, Kind::Frac64};
+    *kind = kinds[index / 9];
+    *op = (Op)((index % 9) / 3);
+    *shape = (Shape)(index % 3);
+    return true;
+}
+
 int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     if (!calls || n == 0) return 0;
-    // default: two workers per core -- each call blocks ~0.3 ms on its GPU lane, during which another worker can run
-    // the zstd codec of the next call
+    // Workers take TILES of consecutive calls: the binary precompiles of a tile share one lane, one H2D / D2H per operand
+    // array and one batched kernel sequence per operation class (Engine::binary_tile), so launch and synchronisation cost
+    // is paid per tile, not per call.  Two workers per core: while one waits on its lane another runs the codec.
     size_t nt = host_threads > 0 ? (size_t)host_threads : 2 * (size_t)std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
-    if (nt > n) nt = n;
+    size_t tile = Engine::get().tile_ops();
+    while (tile > 1 && (n + tile - 1) / tile < nt) tile /= 2;  // keep every worker busy on small batches
+    const size_t tiles = (n + tile - 1) / tile;
+    if (nt > tiles) nt = tiles;
     std::atomic<size_t> next{0};
     std::atomic<int64_t> failed{0};
     auto worker = [&]() {
+        std::vector<TileItem> items;
+        std::vector<size_t> which;
         for (;;) {
-            size_t i = next.fetch_add(1);
-            if (i >= n) break;
-            fhe_b200_call &c = calls[i];
-            if (c.op < 0 || c.op >= kNumOps) {
-                c.status = kErrSunscreen;
-                c.output = nullptr;
-                c.output_length = 0;
-            } else {
-                c.status = kOps[c.op].fn(c.bytes, c.bytes_length, &c.output, &c.output_length);
+            const size_t t = next.fetch_add(1);
+            if (t >= tiles) break;
+            const size_t lo = t * tile, hi = std::min(n, lo + tile);
+            items.clear();
+            which.clear();
+            for (size_t i = lo; i < hi; i++) {
+                fhe_b200_call &c = calls[i];
+                Op op;
+                Shape shape;
+                Kind kind;
+                if (binary_desc(c.op, &op, &shape, &kind)) {
+                    items.push_back(TileItem{op, shape, kind, Span{c.bytes, c.bytes_length}, {}, 0});
+                    which.push_back(i);
+                } else if (c.op < 0 || c.op >= kNumOps) {
+                    c.status = kErrSunscreen;
+                    c.output = nullptr;
+                    c.output_length = 0;
+                } else {
+                    c.status = kOps[c.op].fn(c.bytes, c.bytes_length, &c.output, &c.output_length);
+                }
             }
-            if (c.status) failed.fetch_add(1);
+            if (!items.empty()) {
+                try {
+                    Engine::get().binary_tile(items.data(), items.size());
+                } catch (const std::exception &e) {
+                    set_error(e.what());
+                    for (auto &it : items) it.rc = kErrSunscreen;
+                } catch (...) {
+                    set_error("unknown exception");
+                    for (auto &it : items) it.rc = kErrSunscreen;
+                }
+                for (size_t k = 0; k < items.size(); k++) {
+                    fhe_b200_call &c = calls[which[k]];
+                    c.status = finish(items[k].rc, items[k].out, &c.output, &c.output_length);
+                }
+            }
+            for (size_t i = lo; i < hi; i++)
+                if (calls[i].status) failed.fetch_add(1);
         }
     };
     std::vector<std::thread> th;
@@ -350,6 +395,11 @@ int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, 
             return encode_ciphertext(v, words, res);
         },
         output, output_length);
+}
+int32_t fhe_b200_set_zstd_writer(int32_t mode) {
+    int32_t prev = fheb::zstd_writer();
+    if (mode >= 0) fheb::set_zstd_writer(mode);
+    return prev;
 }
 void fhe_b200_parms_id(int32_t which, uint64_t out[4]) {
     try {

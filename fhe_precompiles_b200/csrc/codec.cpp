@@ -4,7 +4,10 @@
 #include <dlfcn.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -148,6 +151,202 @@ void write_seal_header(uint8_t *p, uint8_t compr, uint64_t size) {
     memcpy(p + 8, &size, 8);
 }
 
+// ---------------------------------------------------------------- structure-aware zstd frames for ciphertext payloads
+// A SEAL ciphertext payload is a 97-byte prefix followed by little-endian 64-bit words that are residues of 36-bit
+// primes: bytes 5..7 of every word are zero.  libzstd at SEAL's default level spends ~0.5-1.5 ms per ciphertext
+// finding that out (and ends at ~88.5 KB); the structure can be written down directly as a standard zstd frame
+// (RFC 8878) at memcpy speed and 82 KB:
+//   block A : raw literals = prefix + word 0 + low 5 bytes of word 1, one sequence (LL 110, ML 3, offset 8) -- this
+//             makes 8 the first repeat offset
+//   block(s): raw literals = the low 5 bytes of every remaining word, one sequence per word (LL 5, ML 3, repeat
+//             offset 1); all three symbol tables in RLE mode, so the sequence bitstream is the end marker alone.
+// Any zstd decoder reads it (the reference's SEAL uses ZSTD_decompressStream); words >= 2^40 fall back to libzstd.
+// The reader recognises exactly this layout and unpacks it directly; everything else goes to libzstd.
+std::atomic<int> g_zstd_writer{-1};  // -1 unset (read FHE_B200_ZSTD_WRITER), 0 libzstd level 3, 1 structured frames
+constexpr size_t kPackPrefix = kCtHeaderBytes;
+constexpr size_t kBlockAContent = kPackPrefix + 16;
+constexpr size_t kBlockALits = kPackPrefix + 13;
+static_assert(kBlockALits >= 64 && kBlockALits < 128, "block A literal length must use LL code 25");
+constexpr size_t kPackBlockWords = 16384;  // 128 KiB of content, zstd's Block_Maximum_Size
+constexpr uint64_t kMask40 = (1ull << 40) - 1;
+
+struct PackLayout {  // header bytes around the literal runs, shared by the writer and the recogniser
+    static size_t frame_header(uint8_t *o, size_t content) {
+        const uint8_t h[5] = {0x28, 0xB5, 0x2F, 0xFD, 0xA0};  // magic, single segment + 4-byte content size
+        memcpy(o, h, 5);
+        const uint32_t fcs = (uint32_t)content;
+        memcpy(o + 5, &fcs, 4);
+        return 9;
+    }
+    static size_t literals_header(uint8_t *o, size_t n) {  // Raw_Literals_Block
+        if (n < 32) {
+            o[0] = (uint8_t)(n << 3);
+            return 1;
+        }
+        if (n < 4096) {
+            const uint16_t v = (uint16_t)((1u << 2) | (n << 4));
+            memcpy(o, &v, 2);
+            return 2;
+        }
+        const uint32_t v = (uint32_t)((3u << 2) | (n << 4));
+        memcpy(o, &v, 3);
+        return 3;
+    }
+    static size_t seq_count(uint8_t *o, size_t n) {
+        if (n < 128) {
+            o[0] = (uint8_t)n;
+            return 1;
+        }
+        if (n < 0x7F00) {
+            o[0] = (uint8_t)((n >> 8) + 0x80);
+            o[1] = (uint8_t)n;
+            return 2;
+        }
+        o[0] = 0xFF;
+        const uint16_t v = (uint16_t)(n - 0x7F00);
+        memcpy(o + 1, &v, 2);
+        return 3;
+    }
+    static void block_header(uint8_t *o, size_t size, bool last) {
+        const uint32_t v = (uint32_t)((last ? 1u : 0u) | (2u << 1) | (size << 3));  // Compressed_Block
+        memcpy(o, &v, 3);
+    }
+    // sequence section of block A: 1 sequence, RLE tables LL code 25 / OF code 3 / ML code 0; bitstream (read from the
+    // top): offset extra 3 bits = 11 - 8, literal-length extra 6 bits = 110 - 64, under the end marker
+    static size_t block_a_sequences(uint8_t *o) {
+        const uint32_t bits = (uint32_t)(kBlockALits - 64) | (3u << 6) | (1u << 9);
+        const uint8_t s[7] = {0x01, 0x54, 25, 3, 0, (uint8_t)bits, (uint8_t)(bits >> 8)};
+        memcpy(o, s, 7);
+        return 7;
+    }
+    // sequence section of a word block: m sequences, RLE tables LL code 5 / OF code 0 (repeat offset 1) / ML code 0
+    static size_t word_sequences(uint8_t *o, size_t m) {
+        size_t k = seq_count(o, m);
+        const uint8_t s[5] = {0x54, 5, 0, 0, 0x01};
+        memcpy(o + k, s, 5);
+        return k + 5;
+    }
+};
+
+// payload (prefix + 8*w bytes) -> zstd frame at dst (capacity >= len + 64).  0 when the payload does not have the shape.
+size_t zstd_pack40(const uint8_t *src, size_t len, uint8_t *dst) {
+    if (len < kBlockAContent || ((len - kPackPrefix) & 7) || len > 0xFFFFFFFFull) return 0;
+    const size_t w = (len - kPackPrefix) / 8;
+    if (w >= 16) {  // constant data (a transparent all-zero ciphertext) compresses to a few hundred bytes with libzstd
+        uint64_t first, v, diff = 0;
+        memcpy(&first, src + kPackPrefix, 8);
+        for (size_t i = 1; i < 16; i++) {
+            memcpy(&v, src + kPackPrefix + 8 * i, 8);
+            diff |= v ^ first;
+        }
+        if (!diff) return 0;
+    }
+    uint64_t acc = 0;
+    uint8_t *o = dst;
+    o += PackLayout::frame_header(o, len);
+    {  // block A
+        uint8_t *bh = o;
+        o += 3;
+        o += PackLayout::literals_header(o, kBlockALits);
+        memcpy(o, src, kBlockALits);
+        o += kBlockALits;
+        uint64_t w0, w1;
+        memcpy(&w0, src + kPackPrefix, 8);
+        memcpy(&w1, src + kPackPrefix + 8, 8);
+        acc |= w0 | w1;
+        o += PackLayout::block_a_sequences(o);
+        PackLayout::block_header(bh, (size_t)(o - bh - 3), w == 2);
+    }
+    const uint8_t *in = src + kBlockAContent;
+    for (size_t done = 2; done < w;) {
+        const size_t m = std::min(kPackBlockWords, w - done);
+        uint8_t *bh = o;
+        o += 3;
+        o += PackLayout::literals_header(o, 5 * m);
+        for (size_t i = 0; i < m; i++) {  // 8-byte store, 5-byte stride: the 3 spill bytes are overwritten next
+            uint64_t v;
+            memcpy(&v, in + 8 * i, 8);
+            acc |= v;
+            memcpy(o + 5 * i, &v, 8);
+        }
+        o += 5 * m;
+        in += 8 * m;
+        done += m;
+        o += PackLayout::word_sequences(o, m);
+        PackLayout::block_header(bh, (size_t)(o - bh - 3), done == w);
+    }
+    if (acc & ~kMask40) return 0;
+    return (size_t)(o - dst);
+}
+
+// the inverse, for frames with exactly that layout.  false: not ours (the caller hands the frame to libzstd)
+bool zstd_unpack40(const uint8_t *src, size_t slen, std::vector<uint8_t> *out) {
+    uint8_t hdr[16];
+    if (slen < 9 + 3 + 2 + kBlockALits + 7) return false;
+    uint32_t fcs;
+    memcpy(&fcs, src + 5, 4);
+    const size_t len = fcs;
+    if (len < kBlockAContent || ((len - kPackPrefix) & 7) || len > kMaxInflate) return false;
+    PackLayout::frame_header(hdr, len);
+    if (memcmp(src, hdr, 9) != 0) return false;
+    const size_t w = (len - kPackPrefix) / 8;
+    // walk the headers first (cheap), then unpack
+    size_t pos = 9;
+    {
+        const size_t lh = PackLayout::literals_header(hdr + 3, kBlockALits);
+        const size_t body = lh + kBlockALits + 7;
+        PackLayout::block_header(hdr, body, w == 2);
+        if (memcmp(src + pos, hdr, 3 + lh) != 0) return false;
+        PackLayout::block_a_sequences(hdr);
+        if (memcmp(src + pos + 3 + lh + kBlockALits, hdr, 7) != 0) return false;
+        pos += 3 + body;
+    }
+    out->resize(len + 8);  // 8 bytes of slack for the word-wide stores below
+    uint8_t *dst = out->data();
+    {
+        const uint8_t *lit = src + 9 + 3 + 2;
+        memcpy(dst, lit, kBlockALits);
+        memset(dst + kBlockALits, 0, 3);
+        // the match copies bytes 5..7 of word 0: they must be zero for the result to be what the fast path assumes
+        if (dst[kPackPrefix + 5] | dst[kPackPrefix + 6] | dst[kPackPrefix + 7]) return false;
+    }
+    uint8_t *o = dst + kBlockAContent;
+    for (size_t done = 2; done < w;) {
+        const size_t m = std::min(kPackBlockWords, w - done);
+        const size_t lh = PackLayout::literals_header(hdr + 3, 5 * m);
+        uint8_t sq[8];
+        const size_t sl = PackLayout::word_sequences(sq, m);
+        const size_t body = lh + 5 * m + sl;
+        if (pos + 3 + body > slen) return false;
+        PackLayout::block_header(hdr, body, done + m == w);
+        if (memcmp(src + pos, hdr, 3 + lh) != 0) return false;
+        const uint8_t *lit = src + pos + 3 + lh;
+        if (memcmp(lit + 5 * m, sq, sl) != 0) return false;
+        for (size_t i = 0; i < m; i++) {  // 8-byte load (the sequence section follows the literals, sl >= 6 > 3)
+            uint64_t v;
+            memcpy(&v, lit + 5 * i, 8);
+            v &= kMask40;
+            memcpy(o + 8 * i, &v, 8);
+        }
+        o += 8 * m;
+        done += m;
+        pos += 3 + body;
+    }
+    if (pos != slen) return false;
+    out->resize(len);
+    return true;
+}
+
+int zstd_writer_mode() {
+    int m = g_zstd_writer.load(std::memory_order_relaxed);
+    if (m < 0) {
+        const char *e = getenv("FHE_B200_ZSTD_WRITER");
+        m = (e && (!strcmp(e, "lib") || !strcmp(e, "0"))) ? 0 : 1;
+        g_zstd_writer.store(m, std::memory_order_relaxed);
+    }
+    return m;
+}
+
 // SEAL blob -> decompressed payload.  `expect` = exact payload size required (0: any up to kMaxInflate)
 int32_t seal_inflate(const uint8_t *blob, size_t len, size_t expect, std::vector<uint8_t> *out, uint8_t *compr_out) {
     SealHeader h;
@@ -162,6 +361,10 @@ int32_t seal_inflate(const uint8_t *blob, size_t len, size_t expect, std::vector
         return kOk;
     }
     if (h.compr == 2) {
+        if (zstd_unpack40(body, blen, out)) {
+            if (expect && out->size() != expect) return kErrInvalidEncoding;
+            return kOk;
+        }
         const ZstdApi &z = zapi();
         if (!z.ok) throw std::runtime_error("fhe_b200: libzstd.so.1 is required to read SEAL blobs");
         unsigned long long sz = z.getFrameContentSize(body, blen);
@@ -186,6 +389,7 @@ int32_t seal_inflate(const uint8_t *blob, size_t len, size_t expect, std::vector
 }
 
 void seal_deflate(const uint8_t *payload, size_t len, uint8_t compr, std::vector<uint8_t> *out) {
+    size_t packed = 0;
     if (compr == 0) {
         out->resize(kSealHeader + len);
         memcpy(out->data() + kSealHeader, payload, len);
@@ -195,6 +399,9 @@ void seal_deflate(const uint8_t *payload, size_t len, uint8_t compr, std::vector
         if (compress2(out->data() + kSealHeader, &cap, payload, (uLong)len, Z_DEFAULT_COMPRESSION) != Z_OK)
             throw std::runtime_error("fhe_b200: zlib compress failed");
         out->resize(kSealHeader + cap);
+    } else if (zstd_writer_mode() == 1 && (out->resize(kSealHeader + len + 64), true) &&
+               (packed = zstd_pack40(payload, len, out->data() + kSealHeader)) != 0) {
+        out->resize(kSealHeader + packed);
     } else {
         const ZstdApi &z = zapi();
         if (!z.ok) throw std::runtime_error("fhe_b200: libzstd.so.1 is required to write SEAL blobs");
@@ -262,6 +469,8 @@ bool parse_ct_meta(const uint8_t *p, size_t len, CtMeta *m) {
 }  // namespace
 
 bool zstd_available() { return zapi().ok; }
+void set_zstd_writer(int mode) { g_zstd_writer.store(mode ? 1 : 0, std::memory_order_relaxed); }
+int zstd_writer() { return zstd_writer_mode(); }
 
 // ---------------------------------------------------------------- framing
 static uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }

@@ -53,6 +53,9 @@ int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words);
 
 // Serialises a size-2 data-level ciphertext (bincode + SEAL + compression) into `out`.
 int32_t encode_ciphertext(const CipherView &view, const uint64_t *words, std::vector<uint8_t> *out);
+// zstd writer for ciphertext payloads: 1 (default) = structure-aware standard frames (codec.cpp), 0 = libzstd level 3
+void set_zstd_writer(int mode);
+int zstd_writer();
 
 // Parses a sunscreen::PublicKey; if `rk_words` is non-null the relinearisation key is written there as
 // [digit 0..1][poly 0..1][limb q0,q1,P][N] (2*2*3*4096 words).  `has_relin` reports whether the key

@@ -1,6 +1,8 @@
 // See engine.h.
 #include "engine.h"
 
+#include <algorithm>
+
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -48,6 +50,8 @@ Engine::Engine() {
         throw std::runtime_error("fhe_b200: no CUDA device visible; this library has no CPU fallback");
     size_t max_dev = env_size("FHE_B200_MAX_DEVICES", (size_t)n_devices_);
     if ((size_t)n_devices_ > max_dev) n_devices_ = (int)max_dev;
+    tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
+    if (tile_ops_ < 1) tile_ops_ = 1;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 2048);
     fused_ = env_size("FHE_B200_FUSED", 0) != 0;
     {
@@ -79,18 +83,29 @@ void Engine::create_lanes() {
             std::unique_ptr<Lane> l(new Lane());
             l->device = d;
             cuda_throw(cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking), "cudaStreamCreate");
-            cuda_throw(cudaMallocHost((void **)&l->h_a, kCtWords * 8), "cudaMallocHost");
-            cuda_throw(cudaMallocHost((void **)&l->h_b, kCtWords * 8), "cudaMallocHost");
-            cuda_throw(cudaMallocHost((void **)&l->h_out, kCtWords * 8), "cudaMallocHost");
-            cuda_throw(cudaMallocHost((void **)&l->h_plain, kN * 2), "cudaMallocHost");
-            cuda_throw(cudaMalloc((void **)&l->d_a, kCtWords * 8), "cudaMalloc");
-            cuda_throw(cudaMalloc((void **)&l->d_b, kCtWords * 8), "cudaMalloc");
-            cuda_throw(cudaMalloc((void **)&l->d_out, kCtWords * 8), "cudaMalloc");
-            cuda_throw(cudaMalloc((void **)&l->d_plain, kN * 2), "cudaMalloc");
-            cuda_throw(cudaMalloc((void **)&l->d_scratch, kScratchLimbsPerOp * kN * 8), "cudaMalloc");
+            ensure_capacity(l.get(), 1);
             lanes_.push_back(std::move(l));
         }
     }
+}
+
+// (re)allocates the lane's staging for `cap` calls; the lane is held by the caller and its stream is idle
+void Engine::ensure_capacity(Lane *l, size_t cap) {
+    if (l->cap >= cap) return;
+    cudaFreeHost(l->h_a), cudaFreeHost(l->h_b), cudaFreeHost(l->h_out), cudaFreeHost(l->h_plain);
+    cudaFree(l->d_a), cudaFree(l->d_b), cudaFree(l->d_out), cudaFree(l->d_plain), cudaFree(l->d_scratch);
+    l->cap = 0;
+    const size_t ct = cap * kCtWords * 8;
+    cuda_throw(cudaMallocHost((void **)&l->h_a, ct), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_b, ct), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_out, ct), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_plain, cap * kN * 2), "cudaMallocHost");
+    cuda_throw(cudaMalloc((void **)&l->d_a, ct), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_b, ct), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_out, ct), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_plain, cap * kN * 2), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_scratch, cap * kScratchLimbsPerOp * kN * 8), "cudaMalloc");
+    l->cap = cap;
 }
 
 Lane *Engine::acquire_lane() {
@@ -135,88 +150,111 @@ void Engine::unpin_key(KeyEntry *k) {
     k->users--;
 }
 
+// Content-addressed lookup.  The byte comparison (~400 KB) and a miss's parse run OUTSIDE key_mu_: candidates are pinned
+// under the lock (a pinned entry is never evicted and its `bytes` never change), compared without it.
 KeyEntry *Engine::find_or_parse_key(Span pk, int32_t *rc) {
     const uint64_t tag = cheap_tag(pk);
-    KeyEntry *hit = nullptr;
-    for (auto &e : keys_)
-        if (e->tag == tag && e->bytes.size() == pk.n && memcmp(e->bytes.data(), pk.p, pk.n) == 0) {
-            hit = e.get();
-            break;
-        }
-    if (!hit) {
-        std::unique_ptr<KeyEntry> e(new KeyEntry());
-        e->rk.resize(kRkWords);
-        e->pk.resize(kPkWords);
-        *rc = decode_public_key(pk, e->pk.data(), e->rk.data(), &e->has_relin);
-        if (*rc) return nullptr;
-        e->bytes.assign(pk.p, pk.p + pk.n);
-        e->tag = tag;
-        e->d_rk.assign((size_t)n_devices_, nullptr);
-        e->d_pk.assign((size_t)n_devices_, nullptr);
-        const size_t cap = env_size("FHE_B200_KEY_CACHE", 8);
-        if (keys_.size() >= cap) {  // evict the least recently used entry nobody is using; if all are pinned, grow
-            long victim = -1;
-            for (size_t i = 0; i < keys_.size(); i++)
-                if (keys_[i]->users == 0 && (victim < 0 || keys_[i]->last_use < keys_[(size_t)victim]->last_use)) victim = (long)i;
-            if (victim >= 0) {
-                int cur = 0;
-                cudaGetDevice(&cur);  // the caller has already selected its lane's device: restore it afterwards
-                for (int d = 0; d < n_devices_; d++) {
-                    uint64_t *ptrs[2] = {keys_[(size_t)victim]->d_rk[(size_t)d], keys_[(size_t)victim]->d_pk[(size_t)d]};
-                    for (uint64_t *ptr : ptrs)
-                        if (ptr) {
-                            cudaSetDevice(d);
-                            cudaFree(ptr);  // no holder left: every user synchronised its stream before unpinning
-                        }
-                }
-                cudaSetDevice(cur);
-                keys_.erase(keys_.begin() + victim);
-            }
-        }
-        keys_.push_back(std::move(e));
-        hit = keys_.back().get();
-    }
-    hit->last_use = ++key_clock_;
     *rc = kOk;
-    return hit;
+    for (size_t start = 0;;) {
+        KeyEntry *cand = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(key_mu_);
+            for (size_t k = start; k < keys_.size(); k++)
+                if (keys_[k]->tag == tag && keys_[k]->bytes.size() == pk.n) {
+                    cand = keys_[k].get();
+                    cand->users++;
+                    cand->last_use = ++key_clock_;
+                    start = k + 1;
+                    break;
+                }
+        }
+        if (!cand) break;
+        if (memcmp(cand->bytes.data(), pk.p, pk.n) == 0) return cand;  // pinned
+        unpin_key(cand);
+    }
+    std::unique_ptr<KeyEntry> e(new KeyEntry());
+    e->rk.resize(kRkWords);
+    e->pk.resize(kPkWords);
+    *rc = decode_public_key(pk, e->pk.data(), e->rk.data(), &e->has_relin);
+    if (*rc) return nullptr;
+    e->bytes.assign(pk.p, pk.p + pk.n);
+    e->tag = tag;
+    e->d_rk.assign((size_t)n_devices_, nullptr);
+    e->d_pk.assign((size_t)n_devices_, nullptr);
+    e->users = 1;
+    const size_t cap = env_size("FHE_B200_KEY_CACHE", 8);
+
+    std::lock_guard<std::mutex> lk(key_mu_);
+    for (auto &o : keys_)  // another thread may have inserted the same key meanwhile
+        if (o->tag == tag && o->bytes == e->bytes) {
+            o->users++;
+            o->last_use = ++key_clock_;
+            return o.get();
+        }
+    if (keys_.size() >= cap) {  // evict the least recently used entry nobody is using; if all are pinned, grow
+        long victim = -1;
+        for (size_t i = 0; i < keys_.size(); i++)
+            if (keys_[i]->users == 0 && (victim < 0 || keys_[i]->last_use < keys_[(size_t)victim]->last_use)) victim = (long)i;
+        if (victim >= 0) {
+            int cur = 0;
+            cudaGetDevice(&cur);  // the caller has already selected its lane's device: restore it afterwards
+            for (int d = 0; d < n_devices_; d++) {
+                uint64_t *ptrs[2] = {keys_[(size_t)victim]->d_rk[(size_t)d], keys_[(size_t)victim]->d_pk[(size_t)d]};
+                for (uint64_t *ptr : ptrs)
+                    if (ptr) {
+                        cudaSetDevice(d);
+                        cudaFree(ptr);  // no holder left: every user synchronised its stream before unpinning
+                    }
+            }
+            cudaSetDevice(cur);
+            keys_.erase(keys_.begin() + victim);
+        }
+    }
+    e->last_use = ++key_clock_;
+    keys_.push_back(std::move(e));
+    return keys_.back().get();
 }
 
 int32_t Engine::relin_key(Span pk, int device, const uint64_t **d_rk, bool need_relin, KeyPin *pin) {
-    std::lock_guard<std::mutex> lk(key_mu_);
     int32_t rc = kOk;
-    KeyEntry *hit = find_or_parse_key(pk, &rc);
+    KeyEntry *hit = find_or_parse_key(pk, &rc);  // pinned on success
     if (!hit) return rc;
+    KeyPin held(this, hit);
     if (!need_relin) {
         if (d_rk) *d_rk = nullptr;
         return kOk;
     }
     if (!hit->has_relin) return kErrSunscreen;  // sunscreen: relinearization keys required but absent
-    uint64_t *&slot = hit->d_rk[(size_t)device];
-    if (!slot) {
-        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
-        cuda_throw(cudaMalloc((void **)&slot, kRkWords * 8), "cudaMalloc(rk)");
-        cuda_throw(cudaMemcpy(slot, hit->rk.data(), kRkWords * 8, cudaMemcpyHostToDevice), "upload rk");
+    {
+        std::lock_guard<std::mutex> lk(key_mu_);
+        uint64_t *&slot = hit->d_rk[(size_t)device];
+        if (!slot) {
+            cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+            cuda_throw(cudaMalloc((void **)&slot, kRkWords * 8), "cudaMalloc(rk)");
+            cuda_throw(cudaMemcpy(slot, hit->rk.data(), kRkWords * 8, cudaMemcpyHostToDevice), "upload rk");
+        }
+        *d_rk = slot;
     }
-    *d_rk = slot;
-    hit->users++;
-    *pin = KeyPin(this, hit);
+    *pin = std::move(held);
     return kOk;
 }
 
 int32_t Engine::public_key(Span pk, int device, const uint64_t **d_pk, KeyPin *pin) {
-    std::lock_guard<std::mutex> lk(key_mu_);
     int32_t rc = kOk;
-    KeyEntry *hit = find_or_parse_key(pk, &rc);
+    KeyEntry *hit = find_or_parse_key(pk, &rc);  // pinned on success
     if (!hit) return rc;
-    uint64_t *&slot = hit->d_pk[(size_t)device];
-    if (!slot) {
-        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
-        cuda_throw(cudaMalloc((void **)&slot, kPkWords * 8), "cudaMalloc(pk)");
-        cuda_throw(cudaMemcpy(slot, hit->pk.data(), kPkWords * 8, cudaMemcpyHostToDevice), "upload pk");
+    KeyPin held(this, hit);
+    {
+        std::lock_guard<std::mutex> lk(key_mu_);
+        uint64_t *&slot = hit->d_pk[(size_t)device];
+        if (!slot) {
+            cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+            cuda_throw(cudaMalloc((void **)&slot, kPkWords * 8), "cudaMalloc(pk)");
+            cuda_throw(cudaMemcpy(slot, hit->pk.data(), kPkWords * 8, cudaMemcpyHostToDevice), "upload pk");
+        }
+        *d_pk = slot;
     }
-    *d_pk = slot;
-    hit->users++;
-    *pin = KeyPin(this, hit);
+    *pin = std::move(held);
     return kOk;
 }
 
@@ -443,68 +481,138 @@ struct LaneGuard {
 }  // namespace
 
 int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<uint8_t> *out) {
-    Span pk, sa, sb;
-    int32_t rc = unpack_binary_operation(in, &pk, &sa, &sb);
-    if (rc) return rc;
+    TileItem it{op, shape, kind, in, {}, 0};
+    binary_tile(&it, 1);
+    if (it.rc == 0) out->swap(it.out);
+    return it.rc;
+}
 
+void Engine::binary_tile(TileItem *items, size_t cnt) {
+    if (cnt == 0) return;
     Lane *lane = acquire_lane();
     LaneGuard guard{this, lane, &Engine::release_lane};
     cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
+    ensure_capacity(lane, cnt);
     cudaStream_t s = lane->stream;
 
-    // reference order (pack.rs:261-263): public key, then a, then b
-    const uint64_t *d_rk = nullptr;
-    const bool need_relin = (op == Op::Mul && shape == Shape::CtCt);
-    KeyPin pin;
-    rc = relin_key(pk, lane->device, &d_rk, need_relin, &pin);
-    if (rc == kErrSunscreen && need_relin) {
-        // missing relin keys is a runtime (not a decoding) error: operands are still decoded first
-    } else if (rc) {
-        return rc;
-    }
-    const int32_t key_rc = rc;
+    // device work classes; ct-ct first so that the second operand array is one prefix of the slots
+    enum Cls { kMulCt = 0, kAddCt, kSubCt, kMulPt, kAddPt, kSubCtPt, kSubPtCt };
+    struct Prep {
+        Span sa, sb;
+        const uint64_t *d_rk = nullptr;
+        KeyPin pin;
+        int32_t key_rc = 0;
+        CipherView va;
+        int cls = 0;
+        bool live = false;
+    };
+    std::vector<Prep> prep(cnt);
+    std::vector<size_t> order;
+    order.reserve(cnt);
 
-    CipherView va, vb;
-    const Span ct_a = (shape == Shape::PtCt) ? sb : sa;  // the ciphertext operand of ct-pt shapes
-    const Span pt = (shape == Shape::PtCt) ? sa : sb;
-    if (shape == Shape::CtCt) {
-        if ((rc = decode_ciphertext(sa, &va, lane->h_a))) return rc;
-        if ((rc = decode_ciphertext(sb, &vb, lane->h_b))) return rc;
-        if (!data_type_matches(va.data_type, kind) || !data_type_matches(vb.data_type, kind)) return kErrSunscreen;
-    } else if (shape == Shape::CtPt) {
-        if ((rc = decode_ciphertext(ct_a, &va, lane->h_a))) return rc;
-        if ((rc = encode_scalar(kind, pt, lane->h_plain))) return rc;
-        if (!data_type_matches(va.data_type, kind)) return kErrSunscreen;
-    } else {
-        if ((rc = encode_scalar(kind, pt, lane->h_plain))) return rc;
-        if ((rc = decode_ciphertext(ct_a, &va, lane->h_a))) return rc;
-        if (!data_type_matches(va.data_type, kind)) return kErrSunscreen;
-    }
-    if (key_rc) return key_rc;
-
-    cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D a");
-    if (shape == Shape::CtCt) {
-        cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D b");
-        if (op == Op::Mul) {
-            ScratchMap m(lane->d_scratch, 1);
-            enqueue_mul(lane->d_a, lane->d_b, m, 1, s, false);
-            enqueue_relin(m.c3, d_rk, lane->d_out, m, 1, s, false);
-        } else {
-            cuda_throw(launch_eltwise(lane->d_a, lane->d_b, lane->d_out, 1, op == Op::Add ? 0 : 1, s), "eltwise");
+    // pass 1, reference order (pack.rs:261-263): framing, then the public key
+    for (size_t i = 0; i < cnt; i++) {
+        TileItem &it = items[i];
+        Prep &p = prep[i];
+        Span pk;
+        if ((it.rc = unpack_binary_operation(it.in, &pk, &p.sa, &p.sb))) continue;
+        const bool need_relin = (it.op == Op::Mul && it.shape == Shape::CtCt);
+        int32_t rc = relin_key(pk, lane->device, &p.d_rk, need_relin, &p.pin);
+        if (rc == kErrSunscreen && need_relin) {
+            // missing relin keys is a runtime (not a decoding) error: operands are still decoded first
+        } else if (rc) {
+            it.rc = rc;
+            continue;
         }
-    } else {
-        cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
-        if (op == Op::Mul) {
-            cuda_throw(launch_mul_plain(lane->d_a, lane->d_plain, lane->d_out, 1, s), "mul_plain");
+        p.key_rc = rc;
+        if (it.shape == Shape::CtCt) p.cls = it.op == Op::Mul ? kMulCt : (it.op == Op::Add ? kAddCt : kSubCt);
+        else if (it.op == Op::Mul) p.cls = kMulPt;
+        else if (it.op == Op::Add) p.cls = kAddPt;
+        else p.cls = it.shape == Shape::CtPt ? kSubCtPt : kSubPtCt;
+        p.live = true;
+        order.push_back(i);
+    }
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
+        if (prep[x].cls != prep[y].cls) return prep[x].cls < prep[y].cls;
+        return prep[x].cls == kMulCt && prep[x].d_rk < prep[y].d_rk;
+    });
+
+    // pass 2: operands into adjacent staging slots, class by class; a call that fails here gives its slot to the next
+    struct Run {
+        int cls;
+        const uint64_t *d_rk;
+        size_t begin, end;
+    };
+    std::vector<Run> runs;
+    std::vector<size_t> slot_item;
+    size_t slots = 0, ctct_slots = 0;
+    for (size_t i : order) {
+        TileItem &it = items[i];
+        Prep &p = prep[i];
+        uint64_t *ha = lane->h_a + slots * kCtWords;
+        uint64_t *hb = lane->h_b + slots * kCtWords;
+        uint16_t *hp = lane->h_plain + slots * kN;
+        int32_t rc = 0;
+        if (it.shape == Shape::CtCt) {
+            CipherView vb;
+            if (!(rc = decode_ciphertext(p.sa, &p.va, ha)) && !(rc = decode_ciphertext(p.sb, &vb, hb)))
+                if (!data_type_matches(p.va.data_type, it.kind) || !data_type_matches(vb.data_type, it.kind)) rc = kErrSunscreen;
+        } else if (it.shape == Shape::CtPt) {
+            if (!(rc = decode_ciphertext(p.sa, &p.va, ha)) && !(rc = encode_scalar(it.kind, p.sb, hp)))
+                if (!data_type_matches(p.va.data_type, it.kind)) rc = kErrSunscreen;
         } else {
+            if (!(rc = encode_scalar(it.kind, p.sa, hp)) && !(rc = decode_ciphertext(p.sb, &p.va, ha)))
+                if (!data_type_matches(p.va.data_type, it.kind)) rc = kErrSunscreen;
+        }
+        if (!rc) rc = p.key_rc;
+        if (rc) {
+            it.rc = rc;
+            p.live = false;
+            continue;
+        }
+        const uint64_t *rk = p.cls == kMulCt ? p.d_rk : nullptr;
+        if (runs.empty() || runs.back().cls != p.cls || runs.back().d_rk != rk) runs.push_back(Run{p.cls, rk, slots, slots});
+        runs.back().end = ++slots;
+        if (p.cls <= kSubCt) ctct_slots = slots;
+        slot_item.push_back(i);
+    }
+    if (slots == 0) return;
+
+    cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, slots * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D a");
+    if (ctct_slots)
+        cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, ctct_slots * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D b");
+    if (slots > ctct_slots)
+        cuda_throw(cudaMemcpyAsync(lane->d_plain + ctct_slots * kN, lane->h_plain + ctct_slots * kN, (slots - ctct_slots) * kN * 2,
+                                   cudaMemcpyHostToDevice, s),
+                   "H2D plain");
+    for (const Run &r : runs) {
+        const size_t c = r.end - r.begin;
+        const uint64_t *a = lane->d_a + r.begin * kCtWords;
+        const uint64_t *b = lane->d_b + r.begin * kCtWords;
+        const uint16_t *pl = lane->d_plain + r.begin * kN;
+        uint64_t *o = lane->d_out + r.begin * kCtWords;
+        switch (r.cls) {
+            case kMulCt: {
+                ScratchMap m(lane->d_scratch, c);
+                enqueue_mul(a, b, m, c, s, false);
+                enqueue_relin(m.c3, r.d_rk, o, m, c, s, false);
+                break;
+            }
+            case kAddCt: cuda_throw(launch_eltwise(a, b, o, c, 0, s), "eltwise"); break;
+            case kSubCt: cuda_throw(launch_eltwise(a, b, o, c, 1, s), "eltwise"); break;
+            case kMulPt: cuda_throw(launch_mul_plain(a, pl, o, c, s), "mul_plain"); break;
             // a + b: add_plain; ct - pt: sub_plain; pt - ct: negate(sub_plain(ct, pt))  
-            int mode = (op == Op::Add) ? 0 : (shape == Shape::CtPt ? 1 : 3);
-            cuda_throw(launch_plain_addsub(lane->d_a, lane->d_plain, lane->d_out, 1, mode, s), "plain_addsub");
+            case kAddPt: cuda_throw(launch_plain_addsub(a, pl, o, c, 0, s), "plain_addsub"); break;
+            case kSubCtPt: cuda_throw(launch_plain_addsub(a, pl, o, c, 1, s), "plain_addsub"); break;
+            default: cuda_throw(launch_plain_addsub(a, pl, o, c, 3, s), "plain_addsub"); break;
         }
     }
-    cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, slots * kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
-    return encode_ciphertext(va, lane->h_out, out);
+    for (size_t k = 0; k < slots; k++) {
+        TileItem &it = items[slot_item[k]];
+        it.rc = encode_ciphertext(prep[slot_item[k]].va, lane->h_out + k * kCtWords, &it.out);
+    }
 }
 
 // ---------------------------------------------------------------- device-resident encrypt / decrypt

@@ -28,14 +28,26 @@ struct ScratchMap {
         : tens(base), c3(tens + c * 15 * kN), ks(c3 + c * 6 * kN), nttbuf(ks + c * 6 * kN), dig(nttbuf + c * 20 * kN) {}
 };
 
+// A lane = one stream + staging for `cap` calls (1 until a tile of the batch surface needs more).
 struct Lane {
     int device = 0;
     cudaStream_t stream = nullptr;
-    uint64_t *h_a = nullptr, *h_b = nullptr, *h_out = nullptr;  // pinned, kCtWords each
-    uint16_t *h_plain = nullptr;                                // pinned, kN
+    size_t cap = 0;
+    uint64_t *h_a = nullptr, *h_b = nullptr, *h_out = nullptr;  // pinned, cap * kCtWords each
+    uint16_t *h_plain = nullptr;                                // pinned, cap * kN
     uint64_t *d_a = nullptr, *d_b = nullptr, *d_out = nullptr, *d_scratch = nullptr;
     uint16_t *d_plain = nullptr;
     bool busy = false;
+};
+
+// one call of the 36 binary precompiles inside a tile of the batch surface
+struct TileItem {
+    Op op;
+    Shape shape;
+    Kind kind;
+    Span in;
+    std::vector<uint8_t> out;
+    int32_t rc = 0;
 };
 
 struct KeyEntry {
@@ -74,6 +86,11 @@ class Engine {
 
     // the 36 binary precompiles: bytes in -> bytes out (lib.rs error code)
     int32_t binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<uint8_t> *out);
+    // `cnt` independent binary precompile calls on ONE lane: operands decoded into adjacent staging slots, one H2D / D2H
+    // per operand array and one batched kernel sequence per (operation, relin key) class instead of per call.
+    // Per-call results and error codes are exactly those of binary_op (which is a tile of one).
+    void binary_tile(TileItem *items, size_t cnt);
+    size_t tile_ops() const { return tile_ops_; }
 
     // device-resident batched entry points (pointers are device memory on `device`)
     void mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
@@ -116,6 +133,8 @@ class Engine {
    private:
     Engine();
     void create_lanes();
+    void ensure_capacity(Lane *lane, size_t cap);
+    size_t tile_ops_ = 16;
     std::vector<int> lane_devices_;
     Lane *acquire_lane();
     void release_lane(Lane *);
@@ -127,7 +146,7 @@ class Engine {
     std::condition_variable lane_cv_;
     size_t next_lane_ = 0;
 
-    KeyEntry *find_or_parse_key(Span pk, int32_t *rc);  // key_mu_ held
+    KeyEntry *find_or_parse_key(Span pk, int32_t *rc);  // returns the entry PINNED (users + 1); takes key_mu_ itself
     const uint64_t *network_sk(int device, Span net_pri);
     int32_t encrypt_plain(Kind kind, const uint16_t *plain_host_unused, Span scalar, Span pk_bytes, uint64_t seed, CipherView *view,
                           Lane *lane, std::vector<uint8_t> *out);

@@ -178,6 +178,11 @@ int32_t fhe_b200_parse_private_key(const uint8_t *bytes, size_t len, uint64_t *s
 int32_t fhe_b200_parse_ciphertext(const uint8_t *bytes, size_t len, uint64_t *words, char *data_type, size_t data_type_cap);
 int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, uint8_t **output, int64_t *output_length);
 /* parms_id (4 words) of the key level (which = 0) or the data level (which = 1) */
+/* How zstd-mode ciphertext payloads are WRITTEN: 1 (default) = structure-aware standard zstd frames (raw 5-byte literals +
+ * repeat-offset matches for the three zero bytes of every 36-bit residue; ~82 KB, memcpy speed), 0 = libzstd level 3 as
+ * SEAL's default does (~88.5 KB, ~1 ms).  Both are RFC 8878 frames any SEAL build reads.  mode < 0 only queries.
+ * Returns the previous mode.  Also settable with FHE_B200_ZSTD_WRITER=lib. */
+int32_t fhe_b200_set_zstd_writer(int32_t mode);
 void fhe_b200_parms_id(int32_t which, uint64_t out[4]);
 
 #ifdef __cplusplus

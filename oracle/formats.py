@@ -89,6 +89,47 @@ class _Zstd:
         lib.ZSTD_isError.argtypes = [ctypes.c_size_t]
         self.lib = lib
 
+    def decompress_stream(self, data: bytes, in_chunk: int = 1000, out_chunk: int = 4096) -> bytes:
+        """ZSTD_decompressStream fed in small pieces -- the API SEAL's Serialization::Load uses."""
+
+        class Buf(ctypes.Structure):
+            _fields_ = [("p", ctypes.c_void_p), ("size", ctypes.c_size_t), ("pos", ctypes.c_size_t)]
+
+        L = self.lib
+        L.ZSTD_createDStream.restype = ctypes.c_void_p
+        L.ZSTD_freeDStream.argtypes = [ctypes.c_void_p]
+        L.ZSTD_decompressStream.restype = ctypes.c_size_t
+        L.ZSTD_decompressStream.argtypes = [ctypes.c_void_p, ctypes.POINTER(Buf), ctypes.POINTER(Buf)]
+        ds = L.ZSTD_createDStream()
+        out = bytearray()
+        obuf = ctypes.create_string_buffer(out_chunk)
+        try:
+            pos, ret = 0, 1
+            while pos < len(data):
+                piece = ctypes.create_string_buffer(data[pos : pos + in_chunk], min(in_chunk, len(data) - pos))
+                ib = Buf(ctypes.cast(piece, ctypes.c_void_p), len(piece), 0)
+                while ib.pos < ib.size:
+                    ob = Buf(ctypes.cast(obuf, ctypes.c_void_p), out_chunk, 0)
+                    ret = L.ZSTD_decompressStream(ds, ctypes.byref(ob), ctypes.byref(ib))
+                    if L.ZSTD_isError(ret):
+                        raise ValueError("zstd stream decompress failed")
+                    out += obuf.raw[: ob.pos]
+                pos += len(piece)
+            while ret != 0:  # flush what the decoder still holds
+                ib = Buf(None, 0, 0)
+                ob = Buf(ctypes.cast(obuf, ctypes.c_void_p), out_chunk, 0)
+                ret = L.ZSTD_decompressStream(ds, ctypes.byref(ob), ctypes.byref(ib))
+                if L.ZSTD_isError(ret):
+                    raise ValueError("zstd stream decompress failed")
+                out += obuf.raw[: ob.pos]
+                if ob.pos == 0:
+                    break
+            if ret != 0:
+                raise ValueError("zstd stream ended inside a frame")
+        finally:
+            L.ZSTD_freeDStream(ds)
+        return bytes(out)
+
     def compress(self, data: bytes, level: int = 3) -> bytes:
         bound = self.lib.ZSTD_compressBound(len(data))
         out = ctypes.create_string_buffer(bound)
@@ -210,9 +251,163 @@ def seal_unwrap(blob: bytes) -> Tuple[bytes, int]:
     raise ValueError("unsupported compr_mode %d" % compr)
 
 
-def seal_wrap(payload: bytes, compr: int = COMPR_ZSTD, level: int = 3) -> bytes:
-    body = payload if compr == COMPR_NONE else zstd().compress(payload, level)
+def seal_wrap(payload: bytes, compr: int = COMPR_ZSTD, level: int = 3, structured: bool = False) -> bytes:
+    if compr == COMPR_NONE:
+        body = payload
+    else:
+        body = zstd_structured_frame(payload) if structured else None
+        if body is None:
+            body = zstd().compress(payload, level)
     return seal_header(compr, SEAL_HEADER_SIZE + len(body)) + body
+
+
+# --------------------------------------------------------------------------- structured zstd frames
+# The product writes zstd-mode ciphertext payloads as hand-laid-out RFC 8878 frames (csrc/codec.cpp, zstd_pack40).
+# This is the independent restatement of that layout, straight from the RFC, used to check the bytes; the mini decoder
+# below reads such frames WITHOUT libzstd (raw literals + RLE-mode sequences only), so the layout is checked twice:
+# by the reference decoder (libzstd) and by the RFC's rules.
+CT_PREFIX = 97  # SEAL ciphertext payload bytes before the coefficient words
+_LL_BASE = list(range(16)) + [16, 18, 20, 22, 24, 28, 32, 40, 48, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]
+_LL_BITS = [0] * 16 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+_ML_BASE = list(range(3, 35)) + [35, 37, 39, 41, 43, 47, 51, 59, 67, 83, 99, 131, 259, 515, 1027, 2051, 4099, 8195, 16387, 32771, 65539]
+_ML_BITS = [0] * 32 + [1, 1, 1, 1, 2, 2, 3, 3, 4, 4, 5, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16]
+
+
+def _raw_literals_header(n: int) -> bytes:
+    if n < 32:
+        return bytes([n << 3])
+    if n < 4096:
+        return struct.pack("<H", (1 << 2) | (n << 4))
+    return struct.pack("<I", (3 << 2) | (n << 4))[:3]
+
+
+def _sequence_count(n: int) -> bytes:
+    if n < 128:
+        return bytes([n])
+    if n < 0x7F00:
+        return bytes([(n >> 8) + 0x80, n & 0xFF])
+    return b"\xff" + struct.pack("<H", n - 0x7F00)
+
+
+def _block(content: bytes, last: bool) -> bytes:
+    return struct.pack("<I", int(last) | (2 << 1) | (len(content) << 3))[:3] + content
+
+
+def zstd_structured_frame(payload: bytes, block_words: int = 16384) -> Optional[bytes]:
+    """prefix(97) + 64-bit words below 2^40 -> zstd frame: block A (raw literals: prefix, word 0, 5 bytes of word 1; one
+    sequence LL=110 ML=3 offset=8), then blocks of 5-byte literals with one (LL=5, ML=3, repeat-offset-1) sequence per word.
+    None when the payload does not have that shape (the caller then uses libzstd)."""
+    n = len(payload)
+    if n < CT_PREFIX + 16 or (n - CT_PREFIX) % 8:
+        return None
+    words = np.frombuffer(payload, dtype="<u8", offset=CT_PREFIX)
+    if (words >> np.uint64(40)).any() or (len(words) >= 16 and (words[:16] == words[0]).all()):
+        return None
+    w = len(words)
+    out = b"\x28\xb5\x2f\xfd\xa0" + struct.pack("<I", n)
+    lits_a = CT_PREFIX + 13
+    bits = (lits_a - 64) | (3 << 6) | (1 << 9)  # from the top: end marker, offset extra (11 - 8), literal-length extra
+    out += _block(_raw_literals_header(lits_a) + payload[:lits_a] + bytes([1, 0x54, 25, 3, 0]) + struct.pack("<H", bits), w == 2)
+    low5 = np.frombuffer(payload, dtype=np.uint8, offset=CT_PREFIX).reshape(w, 8)[:, :5]
+    done = 2
+    while done < w:
+        m = min(block_words, w - done)
+        lits = low5[done : done + m].tobytes()
+        done += m
+        out += _block(_raw_literals_header(5 * m) + lits + _sequence_count(m) + bytes([0x54, 5, 0, 0, 1]), done == w)
+    return out
+
+
+def zstd_mini_decode(frame: bytes) -> bytes:
+    """RFC 8878 decoder for the subset the structured writer uses: single-segment frames, compressed blocks with raw
+    literals and all three sequence tables in RLE mode. Raises ValueError on anything else."""
+    if frame[:4] != b"\x28\xb5\x2f\xfd":
+        raise ValueError("not a zstd frame")
+    fhd = frame[4]
+    if fhd & 0x20 == 0 or fhd & 0x0F:
+        raise ValueError("only single-segment frames without checksum / dictionary")
+    fcs_len = {0: 1, 1: 2, 2: 4, 3: 8}[fhd >> 6]
+    fcs = int.from_bytes(frame[5 : 5 + fcs_len], "little") + (256 if fcs_len == 2 else 0)
+    pos = 5 + fcs_len
+    out = bytearray()
+    rep = [1, 4, 8]
+    last = False
+    while not last:
+        bh = int.from_bytes(frame[pos : pos + 3], "little")
+        last, btype, bsize = bool(bh & 1), (bh >> 1) & 3, bh >> 3
+        pos += 3
+        blk = frame[pos : pos + bsize]
+        if len(blk) != bsize or btype != 2:
+            raise ValueError("only complete compressed blocks")
+        pos += bsize
+        # literals section
+        ltype, sf = blk[0] & 3, (blk[0] >> 2) & 3
+        if ltype != 0:
+            raise ValueError("only raw literals")
+        if sf in (0, 2):
+            nlit, p = blk[0] >> 3, 1
+        elif sf == 1:
+            nlit, p = int.from_bytes(blk[:2], "little") >> 4, 2
+        else:
+            nlit, p = int.from_bytes(blk[:3], "little") >> 4, 3
+        lits = blk[p : p + nlit]
+        p += nlit
+        # sequences section
+        b0 = blk[p]
+        if b0 < 128:
+            nseq, p = b0, p + 1
+        elif b0 < 255:
+            nseq, p = ((b0 - 128) << 8) + blk[p + 1], p + 2
+        else:
+            nseq, p = blk[p + 1] + (blk[p + 2] << 8) + 0x7F00, p + 3
+        lp = 0
+        if nseq:
+            modes = blk[p]
+            if modes != 0x54:
+                raise ValueError("only RLE-mode sequence tables")
+            ll_code, of_code, ml_code = blk[p + 1], blk[p + 2], blk[p + 3]
+            stream = blk[p + 4 :]
+            if not stream or stream[-1] == 0:
+                raise ValueError("bad bitstream end")
+            bits = int.from_bytes(stream, "little")
+            top = bits.bit_length() - 1  # position of the end marker; fields are read downward from it
+
+            def read(nb: int) -> int:
+                nonlocal top
+                if nb > top:
+                    raise ValueError("bitstream underflow")
+                top -= nb
+                return (bits >> top) & ((1 << nb) - 1)
+
+            for _ in range(nseq):
+                of_value = (1 << of_code) + read(of_code)
+                ml = _ML_BASE[ml_code] + read(_ML_BITS[ml_code])
+                ll = _LL_BASE[ll_code] + read(_LL_BITS[ll_code])
+                if of_value > 3:
+                    offset = of_value - 3
+                    rep = [offset, rep[0], rep[1]]
+                else:
+                    idx = of_value - 1 + (1 if ll == 0 else 0)
+                    if idx == 0:
+                        offset = rep[0]
+                    elif idx == 3:
+                        offset = rep[0] - 1
+                        rep = [offset, rep[0], rep[1]]
+                    else:
+                        offset = rep[idx]
+                        rep = [offset] + [r for i, r in enumerate(rep) if i != idx][:2]
+                out += lits[lp : lp + ll]
+                lp += ll
+                if offset > len(out) or offset == 0:
+                    raise ValueError("offset beyond window")
+                for _ in range(ml):
+                    out.append(out[-offset])
+            if top != 0:
+                raise ValueError("bitstream not fully consumed")
+        out += lits[lp:]
+    if pos != len(frame) or len(out) != fcs:
+        raise ValueError("frame size mismatch")
+    return bytes(out)
 
 
 def dynarray_payload(words: np.ndarray) -> bytes:
@@ -411,11 +606,12 @@ class Ciphertext:
     data_type: str
     parts: List[Tuple[Params, SealCiphertext]] = field(default_factory=list)
 
-    def to_bytes(self, compr: int = COMPR_ZSTD) -> bytes:
+    def to_bytes(self, compr: int = COMPR_ZSTD, structured: bool = False) -> bytes:
+        """structured=True: zstd payloads laid out as the product's default writer does (zstd_structured_frame)."""
         dt = self.data_type.encode()
         out = struct.pack("<Q", len(dt)) + dt + struct.pack("<I", 0) + struct.pack("<Q", len(self.parts))
         for params, ct in self.parts:
-            out += WithContext(params, seal_wrap(ct.payload(), compr)).to_bytes()
+            out += WithContext(params, seal_wrap(ct.payload(), compr, structured=structured)).to_bytes()
         return out
 
     @staticmethod

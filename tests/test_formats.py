@@ -100,10 +100,104 @@ def test_library_codec_agrees_with_format_oracle(lib, keys):
     dt = ctypes.create_string_buffer(256)
     assert lib.fhe_b200_parse_ciphertext(buf, len(buf), words.ctypes.data, dt, 256) == 0
     assert np.array_equal(words.reshape(2, 2, N), F.Ciphertext.from_bytes(buf).polys())
-    out, n = ctypes.c_void_p(), ctypes.c_int64()
-    assert lib.fhe_b200_write_ciphertext(words.ctypes.data, dt.value, ctypes.byref(out), ctypes.byref(n)) == 0
-    assert ctypes.string_at(out.value, n.value) == buf  # byte-identical re-serialisation (zstd level 3)
-    lib.fhe_free(out)
+    prev = lib.fhe_b200_set_zstd_writer(0)
+    try:
+        out, n = ctypes.c_void_p(), ctypes.c_int64()
+        assert lib.fhe_b200_write_ciphertext(words.ctypes.data, dt.value, ctypes.byref(out), ctypes.byref(n)) == 0
+        assert ctypes.string_at(out.value, n.value) == buf  # libzstd writer: byte-identical re-serialisation (level 3)
+        lib.fhe_free(out)
+    finally:
+        lib.fhe_b200_set_zstd_writer(prev)
+
+
+def _frame_of(ct_bytes: bytes) -> bytes:
+    """the zstd frame inside a serialised sunscreen Ciphertext"""
+    r = F.Reader(ct_bytes)
+    r.take(r.u64())
+    r.u32(), r.u64()
+    blob = F.WithContext.read(r).blob
+    assert blob[5] == F.COMPR_ZSTD
+    return blob[16:]
+
+
+def test_structured_zstd_frames(lib, keys):
+    """The default writer lays ciphertext payloads out as RFC 8878 frames by hand (codec.cpp zstd_pack40). The bytes must
+    equal the format oracle's independent restatement, decode to the same payload with libzstd (one-shot and streaming,
+    which is what SEAL uses) and with the oracle's RFC-only mini decoder, and both of the library's readers must agree."""
+    assert lib.fhe_b200_set_zstd_writer(-1) == 1, "structured frames are the default writer"
+    rng = np.random.default_rng(77)
+    dt = F.data_type_string("i64").encode()
+    words = np.zeros(4 * N, dtype=np.uint64)
+    name = ctypes.create_string_buffer(256)
+
+    def write(polys):
+        w = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1)
+        out, n = ctypes.c_void_p(), ctypes.c_int64()
+        assert lib.fhe_b200_write_ciphertext(w.ctypes.data, dt, ctypes.byref(out), ctypes.byref(n)) == 0
+        b = ctypes.string_at(out.value, n.value)
+        lib.fhe_free(out)
+        return b
+
+    q = bfv.moduli()[:2]
+    cases = [np.stack([[rng.integers(0, q[l], N, dtype=np.uint64) for l in range(2)] for _ in range(2)]) for _ in range(3)]
+    cases.append(np.stack([[np.full(N, q[l] - 1, dtype=np.uint64) for l in range(2)] for _ in range(2)]))  # constant: libzstd
+    cases.append(np.zeros((2, 2, N), dtype=np.uint64))  # transparent: libzstd path
+    edge = cases[0].copy()
+    edge[0, 0, :2] = 0  # block A's two words
+    edge[1, 1, -1] = q[1] - 1
+    cases.append(edge)
+    sizes = []
+    for polys in cases:
+        got = write(polys)
+        want = F.make_ciphertext("i64", polys)
+        assert got == want.to_bytes(structured=True)
+        frame, payload = _frame_of(got), want.parts[0][1].payload()
+        assert F.zstd().decompress(frame) == payload
+        assert F.zstd().decompress_stream(frame, in_chunk=777, out_chunk=1000) == payload
+        structured = frame[4] == 0xA0 and len(frame) > 5 * 4 * N
+        if structured:
+            assert F.zstd_mini_decode(frame) == payload
+            assert len(frame) == 9 + (3 + 2 + 110 + 7) + (3 + 3 + 5 * (4 * N - 2) + 2 + 5)
+        sizes.append((len(frame), len(F.zstd().compress(payload, 3))))
+        for blob in (got, want.to_bytes()):  # the recogniser and the libzstd reader
+            assert lib.fhe_b200_parse_ciphertext(blob, len(blob), words.ctypes.data, name, 256) == 0
+            assert np.array_equal(words.reshape(2, 2, N), polys)
+    assert sizes[0][0] < sizes[0][1], "structured frames are smaller than libzstd level 3 on real residues"
+    assert sizes[4][0] < 1000, "constant data still goes to libzstd"
+
+
+def test_structured_frame_reader_is_strict(lib, keys):
+    """Every single-byte edit of the header bytes of a structured frame must either be rejected or decode (through the
+    libzstd fallback) to exactly what libzstd itself says; literal edits change only the word they belong to."""
+    rng = np.random.default_rng(78)
+    q = bfv.moduli()[:2]
+    polys = np.stack([[rng.integers(0, q[l], N, dtype=np.uint64) for l in range(2)] for _ in range(2)])
+    good = F.make_ciphertext("i64", polys).to_bytes(structured=True)
+    frame = _frame_of(good)
+    start = good.index(frame)
+    words = np.zeros(4 * N, dtype=np.uint64)
+    name = ctypes.create_string_buffer(256)
+    header_positions = list(range(0, 9 + 3 + 2)) + list(range(9 + 5 + 110, 9 + 5 + 110 + 7 + 6)) + list(range(len(frame) - 8, len(frame)))
+    for pos in header_positions:
+        for flip in (0x01, 0x80):
+            bad = bytearray(good)
+            bad[start + pos] ^= flip
+            bad = bytes(bad)
+            rc = lib.fhe_b200_parse_ciphertext(bad, len(bad), words.ctypes.data, name, 256)
+            try:
+                ref = F.Ciphertext.from_bytes(bad).polys()
+            except Exception:  # noqa: BLE001
+                ref = None
+            if ref is None or (ref >= np.array(q, dtype=np.uint64)[None, :, None]).any():
+                assert rc == 3, (pos, flip, rc)
+            else:
+                assert rc == 0 and np.array_equal(words.reshape(2, 2, N), ref), (pos, flip)
+    # a literal byte belongs to exactly one coefficient
+    bad = bytearray(good)
+    bad[start + 9 + 122 + 6 + 5 * 100] ^= 0x04
+    assert lib.fhe_b200_parse_ciphertext(bytes(bad), len(bad), words.ctypes.data, name, 256) == 0
+    assert np.array_equal(words.reshape(2, 2, N), F.Ciphertext.from_bytes(bytes(bad)).polys())
+    assert (words.reshape(2, 2, N) != polys).sum() == 1
 
 
 def test_library_codec_rejects_malformed_inputs(lib, keys):

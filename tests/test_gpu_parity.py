@@ -179,7 +179,7 @@ def test_precompile_matches_reference_tests(keys, kind, op, shape):
     name = precompile_name(op, shape, kind)
     out = getattr(FHE, name)(pack.pack_binary_operation(keys.pub_bytes, *args))
     want = oracle_binary(op, shape, kind, *oargs, keys.rk)
-    assert out == F.make_ciphertext(kind, want).to_bytes(), "packed ciphertext bytes differ from the oracle's"
+    assert out == F.make_ciphertext(kind, want).to_bytes(structured=True), "packed ciphertext bytes differ from the oracle's"
     got_ct = F.Ciphertext.from_bytes(out)
     assert decrypt_value(keys, kind, got_ct.polys()) == value_of(kind, REF_EXPECT[op])
 
@@ -217,12 +217,82 @@ def test_batch_surface(keys):
         sa, sb = (F.make_ciphertext(kind, x).to_bytes() for x in (a, b))
         op = ("add", "sub", "mul")[i % 3]
         calls.append((precompile_name(op, "ctct", kind), pack.pack_binary_operation(keys.pub_bytes, sa, sb)))
-        wants.append(F.make_ciphertext(kind, oracle_binary(op, "ctct", kind, a, b, keys.rk)).to_bytes())
+        wants.append(F.make_ciphertext(kind, oracle_binary(op, "ctct", kind, a, b, keys.rk)).to_bytes(structured=True))
     calls.append(("add_cipheri64_cipheri64", b"\x00"))
     res = FHE.run_batch(calls, host_threads=4)
     assert [r[0] for r in res[:-1]] == [0] * 12 and res[-1][0] == 1
     for (st, out), want in zip(res[:-1], wants):
         assert out == want
+
+
+def test_batch_tiles_equal_single_calls(keys):
+    """fhe_b200_batch runs tiles of calls through one lane (Engine::binary_tile): every operation class, two keys, and an error
+    at each stage of the reference's decode order must give exactly the status and bytes of the single-call symbol."""
+    from fhe_precompiles_b200 import FHE, FheError, pack
+
+    rng = np.random.default_rng(404)
+    pk_no_relin = F.PublicKey(F.PublicKey.from_bytes(keys.pub_bytes).public_key, None, None).to_bytes()
+    calls = []
+    for i in range(44):
+        kind = KINDS[i % 4]
+        op = ("add", "sub", "mul")[(i // 4) % 3]
+        shape = SHAPES[(i // 2) % 3]
+        va, vb = value_of(kind, 2 + i % 5), value_of(kind, 1 + i % 3)
+        ca = F.make_ciphertext(kind, encrypt_value(keys, kind, va, 500 + i)).to_bytes()
+        cb = F.make_ciphertext(kind, encrypt_value(keys, kind, vb, 600 + i)).to_bytes(structured=bool(i & 1))
+        sc = pack.SERIALIZE[kind](vb)
+        args = {"ctct": (ca, cb), "ctpt": (ca, sc), "ptct": (sc, cb)}[shape]
+        pkb = keys.net_pub_bytes if i % 7 == 3 else keys.pub_bytes
+        data = pack.pack_binary_operation(pkb, *args)
+        fault = i % 11
+        if fault == 4:
+            data = data[:9]  # framing: code 1
+        elif fault == 5:
+            data = pack.pack_binary_operation(pkb[:-5], *args)  # key does not deserialise: 3
+        elif fault == 6 and shape != "ptct":
+            data = pack.pack_binary_operation(pkb, ca[:-7], args[1])  # operand a: 3
+        elif fault == 7 and shape == "ctct":
+            other = KINDS[(i + 1) % 4]
+            data = pack.pack_binary_operation(pkb, ca, F.make_ciphertext(other, encrypt_value(keys, other, 1, 9)).to_bytes())  # type: 7
+        elif fault == 8:
+            data = pack.pack_binary_operation(pk_no_relin, *args)  # missing relin keys: 7 for ct*ct only
+        calls.append((precompile_name(op, shape, kind), data))
+    want = []
+    for name, data in calls:
+        try:
+            want.append((0, getattr(FHE, name)(data)))
+        except FheError as e:
+            want.append((e.code, b""))
+    assert {st for st, _ in want} >= {0, 1, 3, 7}
+    for threads in (1, 2, 16):
+        got = FHE.run_batch(calls, host_threads=threads)
+        assert [g[0] for g in got] == [w[0] for w in want], threads
+        assert all(g[1] == w[1] for g, w in zip(got, want)), threads
+    order = rng.permutation(len(calls))
+    got = FHE.run_batch([calls[i] for i in order], host_threads=2)
+    assert all(got[k] == want[i] for k, i in enumerate(order))
+
+
+def test_libzstd_writer_mode_and_chained_calls(keys):
+    """FHE_B200_ZSTD_WRITER=lib / fhe_b200_set_zstd_writer(0): outputs are libzstd level-3 frames, byte-identical to the format
+    oracle's default serialisation. And outputs of one call (structured frames) are valid inputs of the next."""
+    from fhe_precompiles_b200 import FHE, _lib, pack
+
+    a, b = encrypt_value(keys, "i64", 6, 401), encrypt_value(keys, "i64", -7, 402)
+    sa, sb = (F.make_ciphertext("i64", x).to_bytes() for x in (a, b))
+    packed = pack.pack_binary_operation(keys.pub_bytes, sa, sb)
+    prod = bfv.mul_relin(a, b, keys.rk)
+    L = _lib.lib()
+    prev = L.fhe_b200_set_zstd_writer(0)
+    try:
+        assert FHE.mul_cipheri64_cipheri64(packed) == F.make_ciphertext("i64", prod).to_bytes()
+    finally:
+        L.fhe_b200_set_zstd_writer(prev)
+    out1 = FHE.mul_cipheri64_cipheri64(packed)
+    assert out1 == F.make_ciphertext("i64", prod).to_bytes(structured=True)
+    out2 = FHE.add_cipheri64_cipheri64(pack.pack_binary_operation(keys.pub_bytes, out1, sa))  # structured frame as input
+    assert out2 == F.make_ciphertext("i64", bfv.add(prod, a)).to_bytes(structured=True)
+    assert decrypt_value(keys, "i64", F.Ciphertext.from_bytes(out2).polys()) == -42 + 6
 
 
 # ---------------------------------------------------------------- encrypt / decrypt (config 5, threshold API)
@@ -386,9 +456,9 @@ def test_concurrent_calls_and_key_cache_eviction(keys, monkeypatch):
     sa, sb = (F.make_ciphertext("i64", x).to_bytes() for x in (a, b))
     want = {}
     for vi, (pkb, rk) in enumerate(variants):
-        want[("mul", vi)] = F.make_ciphertext("i64", bfv.mul_relin(a, b, rk)).to_bytes()
-        want[("add", vi)] = F.make_ciphertext("i64", bfv.add(a, b)).to_bytes()
-        want[("mulp", vi)] = F.make_ciphertext("i64", bfv.multiply_plain(a, bfv.encode("i64", 5))).to_bytes()
+        want[("mul", vi)] = F.make_ciphertext("i64", bfv.mul_relin(a, b, rk)).to_bytes(structured=True)
+        want[("add", vi)] = F.make_ciphertext("i64", bfv.add(a, b)).to_bytes(structured=True)
+        want[("mulp", vi)] = F.make_ciphertext("i64", bfv.multiply_plain(a, bfv.encode("i64", 5))).to_bytes(structured=True)
     errors = []
 
     def worker(tid):
@@ -439,6 +509,6 @@ def test_second_device_and_cross_device_batch(dev, keys):
     ca, cb = encrypt_value(keys, "i64", 9, 1), encrypt_value(keys, "i64", -5, 2)
     sa, sb = (F.make_ciphertext("i64", c).to_bytes() for c in (ca, cb))
     packed = pack.pack_binary_operation(keys.pub_bytes, sa, sb)
-    wm = F.make_ciphertext("i64", bfv.mul_relin(ca, cb, keys.rk)).to_bytes()
+    wm = F.make_ciphertext("i64", bfv.mul_relin(ca, cb, keys.rk)).to_bytes(structured=True)
     res = FHE.run_batch([("mul_cipheri64_cipheri64", packed)] * 24, host_threads=8)
     assert all(st == 0 and out == wm for st, out in res)
