@@ -135,7 +135,7 @@ def cpu_baseline(a_np, b_np, rk_np, threads: int):
     return a_np.shape[0] / secs, out, secs
 
 
-def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 200) -> dict:
+def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 1000) -> dict:
     """p50 / p99 of one c_fhe_mul_cipheri64_cipheri64 call (warm key cache): packed bytes in, packed bytes out,
     i.e. bincode + zstd inflate of two ciphertexts, H2D, six kernels, D2H, zstd deflate.  Also times the codec alone."""
     import ctypes
@@ -171,6 +171,17 @@ def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 200
         out = FHE.mul_cipheri64_cipheri64(packed)
         ts.append(time.perf_counter() - t0)
     ts.sort()
+    # phase split of the same call: host clock around the codec phases, CUDA events on the lane's stream
+    L.fhe_b200_set_call_timing(1)
+    phases = ("unpack_key", "parse_inflate", "h2d", "kernels", "d2h", "deflate", "total")
+    rows = []
+    us = (ctypes.c_double * 7)()
+    for _ in range(calls):
+        FHE.mul_cipheri64_cipheri64(packed)
+        L.fhe_b200_last_call_breakdown(us)
+        rows.append(list(us))
+    L.fhe_b200_set_call_timing(0)
+    split = {f"{k}_us": sorted(r[i] for r in rows)[len(rows) // 2] for i, k in enumerate(phases)}
     tc = []
     for _ in range(calls):
         t0 = time.perf_counter()
@@ -226,6 +237,7 @@ def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 200
         "p50_ms": ts[len(ts) // 2] * 1e3,
         "p99_ms": ts[min(len(ts) - 1, int(len(ts) * 0.99))] * 1e3,
         "chained_p50_ms": tc[len(tc) // 2] * 1e3,
+        "p50_split": split,
         "operand_frames": "libzstd level 3 (as SEAL writes them); chained_* = this library's structured frames",
         "codec_only_p50_ms": cs[len(cs) // 2] * 1e3,
         "input_bytes": len(packed),
@@ -503,8 +515,34 @@ def main() -> None:
             _, _, sec1 = cpu_baseline(a_np[i : i + 1], b_np[i : i + 1], rk_np, 1)
             one.append(sec1)
         one.sort()
+        # what one call costs the reference on one core THROUGH the byte surface: it deserialises the public key (two zstd
+        # blobs), both operands, runs the arithmetic and deflates the result at zstd level 3 (fhe.rs:21-30, pack.rs:238-266)
+        from oracle import formats as OF
+
+        z = OF.zstd()
+        pkp = OF.PublicKey.from_bytes(net_pub)
+        key_blobs = [pkp.public_key.blob[16:], pkp.relin_key.blob[16:]]  # the zstd frames inside the two SEAL blobs
+        ct_payload = OF.fresh_data_ciphertext(a_np[0]).payload()
+        ct_blob = z.compress(ct_payload, 3)
+
+        def med(fn, reps=9):
+            t = []
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                fn()
+                t.append(time.perf_counter() - t0)
+            return sorted(t)[len(t) // 2] * 1e3
+
+        codec_ms = {
+            "inflate_key_ms": med(lambda: [z.decompress(kb) for kb in key_blobs]),
+            "inflate_2_operands_ms": med(lambda: [z.decompress(ct_blob), z.decompress(ct_blob)]),
+            "deflate_result_ms": med(lambda: z.compress(ct_payload, 3)),
+        }
+        arith_ms = one[len(one) // 2] * 1e3
         line["cpu_baseline"] = {
-            "p50_call_ms_arithmetic_only_1_thread": one[len(one) // 2] * 1e3,
+            "byte_surface_call_ms_1_thread": {**codec_ms, "arithmetic_ms": arith_ms, "total_ms": arith_ms + sum(codec_ms.values()),
+                                              "note": "libzstd calls + oracle arithmetic only; bincode parsing and SEAL context checks not counted"},
+            "p50_call_ms_arithmetic_only_1_thread": arith_ms,
             "value": cpu_ops,
             "unit": "ops/s",
             "cores": cores,

@@ -91,6 +91,10 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_bfly_peak.restype = i32
     L.fhe_b200_set_fused.argtypes = [i32]
     L.fhe_b200_set_fused.restype = None
+    L.fhe_b200_set_call_timing.argtypes = [i32]
+    L.fhe_b200_set_call_timing.restype = None
+    L.fhe_b200_last_call_breakdown.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    L.fhe_b200_last_call_breakdown.restype = None
     L.fhe_b200_set_kernel_timing.argtypes = [i32]
     L.fhe_b200_set_kernel_timing.restype = None
     L.fhe_b200_kernel_timing_report.argtypes = [i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]

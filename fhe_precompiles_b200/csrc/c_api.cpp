@@ -306,6 +306,17 @@ void fhe_b200_set_fused(int32_t on) {
         set_error(e.what());
     }
 }
+void fhe_b200_set_call_timing(int32_t on) {
+    try {
+        Engine::get().set_call_timing(on != 0);
+    } catch (...) {
+    }
+}
+void fhe_b200_last_call_breakdown(double us[7]) {
+    const CallBreakdown &b = Engine::last_call_breakdown();
+    const double v[7] = {b.unpack_key_us, b.decode_us, b.h2d_us, b.kernels_us, b.d2h_us, b.encode_us, b.total_us};
+    for (int i = 0; i < 7; i++) us[i] = v[i];
+}
 void fhe_b200_set_kernel_timing(int32_t on) {
     try {
         Engine::get().set_kernel_timing(on != 0);

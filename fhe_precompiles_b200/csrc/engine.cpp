@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <chrono>
 
 #include <cstdlib>
 #include <cstring>
@@ -480,6 +481,14 @@ struct LaneGuard {
 };
 }  // namespace
 
+namespace {
+thread_local CallBreakdown tl_breakdown;
+inline double us_since(std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+}
+}  // namespace
+const CallBreakdown &Engine::last_call_breakdown() { return tl_breakdown; }
+
 int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<uint8_t> *out) {
     TileItem it{op, shape, kind, in, {}, 0};
     binary_tile(&it, 1);
@@ -489,11 +498,15 @@ int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<ui
 
 void Engine::binary_tile(TileItem *items, size_t cnt) {
     if (cnt == 0) return;
+    const bool timed = call_timing_.load(std::memory_order_relaxed);
+    const auto t_start = std::chrono::steady_clock::now();
     Lane *lane = acquire_lane();
     LaneGuard guard{this, lane, &Engine::release_lane};
     cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
     ensure_capacity(lane, cnt);
     cudaStream_t s = lane->stream;
+    if (timed && !lane->ev[0])
+        for (auto &e : lane->ev) cuda_throw(cudaEventCreate(&e), "cudaEventCreate");
 
     // device work classes; ct-ct first so that the second operand array is one prefix of the slots
     enum Cls { kMulCt = 0, kAddCt, kSubCt, kMulPt, kAddPt, kSubCtPt, kSubPtCt };
@@ -532,6 +545,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         p.live = true;
         order.push_back(i);
     }
+    const double t_unpack = us_since(t_start);
     std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
         if (prep[x].cls != prep[y].cls) return prep[x].cls < prep[y].cls;
         return prep[x].cls == kMulCt && prep[x].d_rk < prep[y].d_rk;
@@ -577,7 +591,9 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         slot_item.push_back(i);
     }
     if (slots == 0) return;
+    const double t_decode = us_since(t_start);
 
+    if (timed) cudaEventRecord(lane->ev[0], s);
     cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, slots * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D a");
     if (ctct_slots)
         cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, ctct_slots * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D b");
@@ -585,6 +601,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         cuda_throw(cudaMemcpyAsync(lane->d_plain + ctct_slots * kN, lane->h_plain + ctct_slots * kN, (slots - ctct_slots) * kN * 2,
                                    cudaMemcpyHostToDevice, s),
                    "H2D plain");
+    if (timed) cudaEventRecord(lane->ev[1], s);
     for (const Run &r : runs) {
         const size_t c = r.end - r.begin;
         const uint64_t *a = lane->d_a + r.begin * kCtWords;
@@ -607,11 +624,26 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
             default: cuda_throw(launch_plain_addsub(a, pl, o, c, 3, s), "plain_addsub"); break;
         }
     }
+    if (timed) cudaEventRecord(lane->ev[2], s);
     cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, slots * kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    if (timed) cudaEventRecord(lane->ev[3], s);
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    const double t_device = us_since(t_start);
     for (size_t k = 0; k < slots; k++) {
         TileItem &it = items[slot_item[k]];
         it.rc = encode_ciphertext(prep[slot_item[k]].va, lane->h_out + k * kCtWords, &it.out);
+    }
+    if (timed) {
+        CallBreakdown &b = tl_breakdown;
+        float ms[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ms[k], lane->ev[k], lane->ev[k + 1]);
+        b.unpack_key_us = t_unpack;
+        b.decode_us = t_decode - t_unpack;
+        b.h2d_us = ms[0] * 1e3;
+        b.kernels_us = ms[1] * 1e3;
+        b.d2h_us = ms[2] * 1e3;
+        b.total_us = us_since(t_start);
+        b.encode_us = b.total_us - t_device;
     }
 }
 

@@ -38,6 +38,12 @@ struct Lane {
     uint64_t *d_a = nullptr, *d_b = nullptr, *d_out = nullptr, *d_scratch = nullptr;
     uint16_t *d_plain = nullptr;
     bool busy = false;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call-breakdown timing (created on first use)
+};
+
+// where the time of the last binary call (or tile) on this thread went, microseconds
+struct CallBreakdown {
+    double unpack_key_us = 0, decode_us = 0, h2d_us = 0, kernels_us = 0, d2h_us = 0, encode_us = 0, total_us = 0;
 };
 
 // one call of the 36 binary precompiles inside a tile of the batch surface
@@ -91,6 +97,10 @@ class Engine {
     // Per-call results and error codes are exactly those of binary_op (which is a tile of one).
     void binary_tile(TileItem *items, size_t cnt);
     size_t tile_ops() const { return tile_ops_; }
+    // per-call phase timing of binary_tile (host clock around the codec phases, CUDA events around the copies and the
+    // kernels on the lane's stream); off by default
+    void set_call_timing(bool on) { call_timing_ = on; }
+    static const CallBreakdown &last_call_breakdown();
 
     // device-resident batched entry points (pointers are device memory on `device`)
     void mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
@@ -135,6 +145,7 @@ class Engine {
     void create_lanes();
     void ensure_capacity(Lane *lane, size_t cap);
     size_t tile_ops_ = 16;
+    std::atomic<bool> call_timing_{false};
     std::vector<int> lane_devices_;
     Lane *acquire_lane();
     void release_lane(Lane *);

@@ -158,6 +158,11 @@ void fhe_b200_set_fused(int32_t on);
 /* Per-kernel timing of fhe_b200_mul_relin (CUDA events around each launch, on the caller's stream).
  * ms / launches are indexed 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt,
  * 5 k_tensor_intt, 6 k_digit_ntt, 7 k_ks_intt; the report synchronises the device and resets the accumulators. */
+/* Phase timing of the byte surface (parse+inflate / H2D / kernels / D2H / deflate).  When on, every binary
+ * precompile call records, for the calling thread: us[0] framing + key lookup, us[1] operand decode (bincode + zstd inflate
+ * + range checks), us[2] H2D, us[3] kernels, us[4] D2H (CUDA events on the lane's stream), us[5] result encode, us[6] total. */
+void fhe_b200_set_call_timing(int32_t on);
+void fhe_b200_last_call_breakdown(double us[7]);
 void fhe_b200_set_kernel_timing(int32_t on);
 int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[8], uint64_t launches[8]);
 /* Batched negacyclic NTT in place over n_limbs limbs of 4096 words; limb i uses modulus mods[i % n_mods]
