@@ -42,6 +42,22 @@ def main() -> None:
             dtm = time.perf_counter() - t0
             assert all(st == 0 for st, _ in r)
             res[f"{name}_threads{th}"] = round(n / dtm)
+        # small batches: latency of the C call alone (array prepared before, outputs freed after), default threads
+        buf = (ctypes.c_char * len(packed)).from_buffer_copy(packed)
+        op = L.fhe_b200_op_index(b"mul_cipheri64_cipheri64")
+        for small in (1, 4, 16, 64, 256):
+            arr = (_lib.BatchCall * small)()
+            ts = []
+            for _ in range(40):
+                for i in range(small):
+                    arr[i].op, arr[i].bytes, arr[i].bytes_length = op, ctypes.cast(buf, ctypes.c_void_p), len(packed)
+                t0 = time.perf_counter()
+                failed = L.fhe_b200_batch(arr, small, 0)
+                ts.append(time.perf_counter() - t0)
+                assert failed == 0
+                for i in range(small):
+                    L.fhe_free(arr[i].output)
+            res[f"{name}_batch{small}_p50_ms"] = round(sorted(ts)[20] * 1e3, 3)
     print(json.dumps(res))
 
 
