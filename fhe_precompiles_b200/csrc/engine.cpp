@@ -3,6 +3,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
+
+#include "host_pool.h"
 
 #include <cstdlib>
 #include <cstring>
@@ -51,6 +54,10 @@ Engine::Engine() {
         throw std::runtime_error("fhe_b200: no CUDA device visible; this library has no CPU fallback");
     size_t max_dev = env_size("FHE_B200_MAX_DEVICES", (size_t)n_devices_);
     if ((size_t)n_devices_ > max_dev) n_devices_ = (int)max_dev;
+    {
+        const char *v = getenv("FHE_B200_HELPER_DECODE");
+        helper_decode_ = !(v && *v == '0');
+    }
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 2048);
@@ -569,8 +576,21 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         int32_t rc = 0;
         if (it.shape == Shape::CtCt) {
             CipherView vb;
-            if (!(rc = decode_ciphertext(p.sa, &p.va, ha)) && !(rc = decode_ciphertext(p.sb, &vb, hb)))
-                if (!data_type_matches(p.va.data_type, it.kind) || !data_type_matches(vb.data_type, it.kind)) rc = kErrSunscreen;
+            if (cnt == 1 && helper_decode_) {
+                // a single call: inflate the second operand on a pool thread while this one inflates the first (a tile
+                // already keeps every core busy).  If no pool thread is free the caller does both, in order.
+                int32_t rcs[2] = {0, 0};
+                std::atomic<int> next{0};
+                const std::function<void()> fn = [&] {
+                    for (int k; (k = next.fetch_add(1)) < 2;)
+                        rcs[k] = k == 0 ? decode_ciphertext(p.sa, &p.va, ha) : decode_ciphertext(p.sb, &vb, hb);
+                };
+                HostPool::get().run(1, fn);
+                rc = rcs[0] ? rcs[0] : rcs[1];  // reference order: a's error wins
+            } else if (!(rc = decode_ciphertext(p.sa, &p.va, ha))) {
+                rc = decode_ciphertext(p.sb, &vb, hb);
+            }
+            if (!rc && (!data_type_matches(p.va.data_type, it.kind) || !data_type_matches(vb.data_type, it.kind))) rc = kErrSunscreen;
         } else if (it.shape == Shape::CtPt) {
             if (!(rc = decode_ciphertext(p.sa, &p.va, ha)) && !(rc = encode_scalar(it.kind, p.sb, hp)))
                 if (!data_type_matches(p.va.data_type, it.kind)) rc = kErrSunscreen;

@@ -145,6 +145,7 @@ class Engine {
     void create_lanes();
     void ensure_capacity(Lane *lane, size_t cap);
     size_t tile_ops_ = 16;
+    bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
     std::atomic<bool> call_timing_{false};
     std::vector<int> lane_devices_;
     Lane *acquire_lane();
