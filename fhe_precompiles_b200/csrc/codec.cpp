@@ -337,6 +337,41 @@ bool zstd_unpack40(const uint8_t *src, size_t slen, std::vector<uint8_t> *out) {
     return true;
 }
 
+// header walk of zstd_unpack40 without touching the literals: is this frame in the structured layout for `len` content bytes?
+bool zstd_is_pack40(const uint8_t *src, size_t slen, size_t len) {
+    uint8_t hdr[16];
+    if (slen < 9 + 3 + 2 + kBlockALits + 7 || len < kBlockAContent || ((len - kPackPrefix) & 7)) return false;
+    PackLayout::frame_header(hdr, len);
+    if (memcmp(src, hdr, 9) != 0) return false;
+    const size_t w = (len - kPackPrefix) / 8;
+    size_t pos = 9;
+    {
+        const size_t lh = PackLayout::literals_header(hdr + 3, kBlockALits);
+        const size_t body = lh + kBlockALits + 7;
+        PackLayout::block_header(hdr, body, w == 2);
+        if (memcmp(src + pos, hdr, 3 + lh) != 0) return false;
+        PackLayout::block_a_sequences(hdr);
+        if (memcmp(src + pos + 3 + lh + kBlockALits, hdr, 7) != 0) return false;
+        const uint8_t *w0 = src + pos + 3 + lh + kPackPrefix;
+        if (w0[5] | w0[6] | w0[7]) return false;
+        pos += 3 + body;
+    }
+    for (size_t done = 2; done < w;) {
+        const size_t m = std::min(kPackBlockWords, w - done);
+        const size_t lh = PackLayout::literals_header(hdr + 3, 5 * m);
+        uint8_t sq[8];
+        const size_t sl = PackLayout::word_sequences(sq, m);
+        const size_t body = lh + 5 * m + sl;
+        if (pos + 3 + body > slen) return false;
+        PackLayout::block_header(hdr, body, done + m == w);
+        if (memcmp(src + pos, hdr, 3 + lh) != 0) return false;
+        if (memcmp(src + pos + 3 + lh + 5 * m, sq, sl) != 0) return false;
+        done += m;
+        pos += 3 + body;
+    }
+    return pos == slen;
+}
+
 int zstd_writer_mode() {
     int m = g_zstd_writer.load(std::memory_order_relaxed);
     if (m < 0) {
@@ -494,8 +529,7 @@ int32_t unpack_two_arguments(Span in, Span *a, Span *b) {
 }
 
 // ---------------------------------------------------------------- Ciphertext
-int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words) {
-    const HostContext &H = HostContext::get();
+int32_t parse_ciphertext_framing(Span in, CipherView *view, Span *blob_out) {
     Rd r(in.p, in.n);
     uint64_t slen = r.u64v();
     if (r.fail || slen > 4096) return kErrInvalidEncoding;
@@ -516,6 +550,57 @@ int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words) {
     if (!blob || !r.done()) return kErrInvalidEncoding;
     if (k != 3 || !params_are_testnet(params)) return foreign_params_code(params, k);
     memcpy(view->params, params, kParamsBytes);
+    *blob_out = Span{blob, (size_t)blen};
+    return kOk;
+}
+
+int classify_ciphertext_blob(Span blob, Span *frame, uint8_t *compr) {
+    SealHeader h;
+    if (!parse_seal_header(blob.p, blob.n, &h) || h.size < kSealHeader || h.size > blob.n) return -1;
+    *compr = h.compr;
+    if (h.compr != 2) return 0;
+    *frame = Span{blob.p + kSealHeader, (size_t)h.size - kSealHeader};
+    return zstd_is_pack40(frame->p, frame->n, kCtHeaderBytes + 8 * kCtWords) ? 2 : 1;
+}
+
+void canonical_ct_prefix(uint8_t *p) {
+    const HostContext &H = HostContext::get();
+    memcpy(p, H.parms_id_data, 32);
+    p[32] = 0;
+    const uint64_t size = 2, n = kN, k = 2, corr = 1, count = kCtWords;
+    const double scale = 1.0;
+    memcpy(p + 33, &size, 8);
+    memcpy(p + 41, &n, 8);
+    memcpy(p + 49, &k, 8);
+    memcpy(p + 57, &scale, 8);
+    memcpy(p + 65, &corr, 8);
+    write_seal_header(p + 73, 0, 24 + 8 * count);
+    memcpy(p + 89, &count, 8);
+}
+
+void wrap_ciphertext_blob(const CipherView &view, const uint8_t *body, size_t body_len, std::vector<uint8_t> *out) {
+    const size_t blob = kSealHeader + body_len;
+    out->resize(8 + view.data_type.size() + 12 + kParamsBytes + 8 + blob);
+    uint8_t *o = out->data();
+    const uint64_t dl = view.data_type.size(), one = 1, bl = blob;
+    const uint32_t zero = 0;
+    memcpy(o, &dl, 8), o += 8;
+    memcpy(o, view.data_type.data(), dl), o += dl;
+    memcpy(o, &zero, 4), o += 4;
+    memcpy(o, &one, 8), o += 8;
+    memcpy(o, view.params, kParamsBytes), o += kParamsBytes;
+    memcpy(o, &bl, 8), o += 8;
+    write_seal_header(o, view.compr_mode, blob);
+    memcpy(o + kSealHeader, body, body_len);
+}
+
+int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words) {
+    const HostContext &H = HostContext::get();
+    Span blob_span;
+    int32_t frc = parse_ciphertext_framing(in, view, &blob_span);
+    if (frc) return frc;
+    const uint8_t *blob = blob_span.p;
+    const size_t blen = blob_span.n;
 
     thread_local std::vector<uint8_t> payload;
     int32_t rc = seal_inflate(blob, (size_t)blen, 0, &payload, &view->compr_mode);
@@ -541,21 +626,10 @@ int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words) {
 }
 
 int32_t encode_ciphertext(const CipherView &view, const uint64_t *words, std::vector<uint8_t> *out) {
-    const HostContext &H = HostContext::get();
     thread_local std::vector<uint8_t> payload, blob;
     payload.resize(kCtHeaderBytes + kCtWords * 8);
     uint8_t *p = payload.data();
-    memcpy(p, H.parms_id_data, 32);
-    p[32] = 0;
-    const uint64_t size = 2, n = kN, k = 2, corr = 1, count = kCtWords;
-    const double scale = 1.0;
-    memcpy(p + 33, &size, 8);
-    memcpy(p + 41, &n, 8);
-    memcpy(p + 49, &k, 8);
-    memcpy(p + 57, &scale, 8);
-    memcpy(p + 65, &corr, 8);
-    write_seal_header(p + 73, 0, 24 + 8 * count);
-    memcpy(p + 89, &count, 8);
+    canonical_ct_prefix(p);
     memcpy(p + kCtHeaderBytes, words, kCtWords * 8);
     seal_deflate(payload.data(), payload.size(), view.compr_mode, &blob);
 

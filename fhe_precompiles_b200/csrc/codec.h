@@ -51,6 +51,17 @@ struct CipherView {
 // 16384 coefficient words to `words` (caller-owned, e.g. pinned staging).  Returns an lib.rs error code.
 int32_t decode_ciphertext(Span in, CipherView *view, uint64_t *words);
 
+// The pieces of decode_ciphertext / encode_ciphertext the device codec path needs (engine.cpp, codec_kernels.cu):
+// bincode framing only (data_type, params checks; `blob` = the SEAL blob inside)
+int32_t parse_ciphertext_framing(Span in, CipherView *view, Span *blob);
+// SEAL header of the blob: -1 malformed, 0 not zstd (compr none / zlib: host path), 1 zstd frame, 2 zstd frame in this library's
+// structured layout (every header byte verified); `frame` = the zstd frame, `compr` = the blob's compr_mode
+int classify_ciphertext_blob(Span blob, Span *frame, uint8_t *compr);
+// the 97 bytes every valid size-2 data-level coefficient-form ciphertext payload starts with
+void canonical_ct_prefix(uint8_t *prefix97);
+// bincode(Ciphertext) around an already compressed payload `body` (SEAL header with view.compr_mode added here)
+void wrap_ciphertext_blob(const CipherView &view, const uint8_t *body, size_t body_len, std::vector<uint8_t> *out);
+
 // Serialises a size-2 data-level ciphertext (bincode + SEAL + compression) into `out`.
 int32_t encode_ciphertext(const CipherView &view, const uint64_t *words, std::vector<uint8_t> *out);
 // zstd writer for ciphertext payloads: 1 (default) = structure-aware standard frames (codec.cpp), 0 = libzstd level 3

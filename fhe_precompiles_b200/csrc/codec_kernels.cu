@@ -1,0 +1,192 @@
+// Device side of the byte surface: the zstd frames of the ciphertext operands are inflated on the GPU and the
+// result is written as a structured zstd frame on the GPU, so the host moves compressed bytes only.
+//   k_zstd_inflate : one frame per warp (zstd_dec.h; lane 0 decodes, the frame's bitstreams are sequential by construction)
+//   k_ct_unpack    : 131,169-byte SEAL payload -> [2][2][N] words; checks the 97-byte prefix against the only value a valid
+//                    data-level ciphertext can have and every residue against its modulus
+//   k_unpack40     : the same for frames in this library's own structured layout (5-byte literals), fully parallel
+//   k_ct_pack40    : [2][2][N] words -> the complete structured frame (codec.cpp zstd_pack40 layout), byte for byte
+// Anything unusual is flagged and the host redoes that call with libzstd (codec.cpp), whose verdict is authoritative.
+#include <atomic>
+
+#include "codec_kernels.h"
+#include "params.h"
+#include "zstd_dec.h"
+
+namespace fheb {
+
+extern std::atomic<unsigned long long> g_codec_launches;
+std::atomic<unsigned long long> g_codec_launches{0};
+
+namespace {
+constexpr int kInflateWarps = 4;  // decoders per block
+constexpr u64 kQ0 = kModulus[0], kQ1 = kModulus[1];
+
+constexpr size_t kInflateSmemPerWarp = zd::kSeqTableEntries * sizeof(zd::SeqEntry) + zd::kRingBytes;
+constexpr size_t kInflateSmem = kInflateWarps * kInflateSmemPerWarp;
+
+__global__ void __launch_bounds__(kInflateWarps * 32) k_zstd_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
+                                                                      int32_t *status, zd::Work *work, int n) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * kInflateWarps + warp;
+    if (j >= n) return;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobZstd) return;
+    uint8_t *mine = smem + (size_t)warp * kInflateSmemPerWarp;
+    zd::Work *w = work + j;
+    if ((threadIdx.x & 31) == 0) zd::work_bind(w, (zd::SeqEntry *)mine);
+    __syncwarp();
+    size_t dlen = 0;
+    const int rc = zd::decode_frame(frames + job.src_off, job.src_len, payloads + (size_t)j * kPayloadStride, kCtPayloadBytes, &dlen, w,
+                                    mine + zd::kSeqTableEntries * sizeof(zd::SeqEntry));
+    if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
+}
+
+// payload (prefix 97 + 16384 words at byte offset 97) -> aligned words.  One block of 256 threads per job.
+__global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, const CodecJob *jobs, int32_t *status, const uint8_t *prefix,
+                                                   u64 *dst_a, u64 *dst_b) {
+    const int j = blockIdx.x;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobZstd || status[j] != kJobOk) return;
+    const uint8_t *p = payloads + (size_t)j * kPayloadStride;  // 8-byte aligned
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    int mybad = 0;
+    if (threadIdx.x < kCtPrefixBytes) {
+        // byte 77 is SEAL's minor version inside the inner DynArray header: not constrained by the host parser either
+        if (threadIdx.x != 77 && p[threadIdx.x] != prefix[threadIdx.x]) mybad = 1;
+    }
+    u64 *dst = (job.operand ? dst_b : dst_a) + (size_t)job.slot * kCodecCtWords;
+    const u64 *p64 = (const u64 *)p;  // word i lives at bytes 97 + 8 i = 8 (12 + i) + 1
+    for (int i = threadIdx.x; i < kCodecCtWords; i += 256) {
+        const u64 w = (p64[12 + i] >> 8) | (p64[13 + i] << 56);
+        const u64 q = ((i >> 12) & 1) ? kQ1 : kQ0;
+        if (w >= q) mybad = 1;
+        dst[i] = w;
+    }
+    if (mybad) atomicOr(&bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0 && bad) status[j] = kJobFallback;
+}
+
+// structured frames: the host has verified every header byte; literals are at two fixed places of the frame
+__global__ void __launch_bounds__(256) k_unpack40(const uint8_t *frames, const CodecJob *jobs, int32_t *status, const uint8_t *prefix,
+                                                  u64 *dst_a, u64 *dst_b) {
+    const int j = blockIdx.x;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobPacked) return;
+    const uint8_t *f = frames + job.src_off;
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    int mybad = 0;
+    const uint8_t *la = f + 9 + 3 + 2;  // block A literals: prefix, word 0 (8 bytes), low 5 bytes of word 1
+    if (threadIdx.x < kCtPrefixBytes && threadIdx.x != 77 && la[threadIdx.x] != prefix[threadIdx.x]) mybad = 1;
+    u64 *dst = (job.operand ? dst_b : dst_a) + (size_t)job.slot * kCodecCtWords;
+    const uint8_t *lw = f + 9 + (3 + 2 + 110 + 7) + 3 + 3;  // literals of words 2..
+    for (int i = threadIdx.x; i < kCodecCtWords; i += 256) {
+        u64 w = 0;
+        if (i >= 2) {
+            const uint8_t *s = lw + 5 * (size_t)(i - 2);
+            w = (u64)s[0] | (u64)s[1] << 8 | (u64)s[2] << 16 | (u64)s[3] << 24 | (u64)s[4] << 32;
+        } else {
+            const uint8_t *s = la + kCtPrefixBytes + 8 * i;
+            const int nb = i == 0 ? 8 : 5;
+            for (int k = 0; k < nb; k++) w |= (u64)s[k] << (8 * k);
+        }
+        if (w >= (((i >> 12) & 1) ? kQ1 : kQ0)) mybad = 1;
+        dst[i] = w;
+    }
+    if (mybad) atomicOr(&bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) status[j] = bad ? kJobFallback : kJobOk;
+}
+
+// words -> complete structured frame (kPackedFrameBytes); flag = 1 when the first 16 words are equal (the host writer hands
+// constant data to libzstd, and so must the caller)
+__global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *frames, int32_t *constant_flag, const uint8_t *prefix) {
+    const int j = blockIdx.x;
+    const u64 *w = words + (size_t)j * kCodecCtWords;
+    uint8_t *f = frames + (size_t)j * kPackedFrameStride;
+    if (threadIdx.x == 0) {
+        // frame header: magic, single segment + 4-byte content size
+        const uint8_t h[9] = {0x28, 0xB5, 0x2F, 0xFD, 0xA0, (uint8_t)kCtPayloadBytes, (uint8_t)(kCtPayloadBytes >> 8),
+                              (uint8_t)(kCtPayloadBytes >> 16), (uint8_t)(kCtPayloadBytes >> 24)};
+        for (int k = 0; k < 9; k++) f[k] = h[k];
+        // block A: header (compressed block, 2 + 110 + 7 bytes), raw literal header (110), ... , one sequence
+        const uint32_t bh = (2u << 1) | ((2 + 110 + 7) << 3);
+        f[9] = (uint8_t)bh, f[10] = (uint8_t)(bh >> 8), f[11] = (uint8_t)(bh >> 16);
+        const uint32_t lh = (1u << 2) | (110u << 4);
+        f[12] = (uint8_t)lh, f[13] = (uint8_t)(lh >> 8);
+        const uint32_t bits = (110 - 64) | (3u << 6) | (1u << 9);
+        const uint8_t sq[7] = {0x01, 0x54, 25, 3, 0, (uint8_t)bits, (uint8_t)(bits >> 8)};
+        for (int k = 0; k < 7; k++) f[14 + 110 + k] = sq[k];
+        // word block: 16382 words
+        constexpr uint32_t m = (uint32_t)kCodecCtWords - 2, body = 3 + 5 * m + 2 + 5;
+        const uint32_t bh2 = 1u | (2u << 1) | (body << 3);
+        uint8_t *g = f + 9 + 122;
+        g[0] = (uint8_t)bh2, g[1] = (uint8_t)(bh2 >> 8), g[2] = (uint8_t)(bh2 >> 16);
+        const uint32_t lh2 = (3u << 2) | ((5 * m) << 4);
+        g[3] = (uint8_t)lh2, g[4] = (uint8_t)(lh2 >> 8), g[5] = (uint8_t)(lh2 >> 16);
+        uint8_t *t = g + 6 + 5 * m;
+        t[0] = (uint8_t)((m >> 8) + 0x80), t[1] = (uint8_t)m;
+        const uint8_t tail[5] = {0x54, 5, 0, 0, 0x01};
+        for (int k = 0; k < 5; k++) t[2 + k] = tail[k];
+        u64 diff = 0;
+        for (int k = 1; k < 16; k++) diff |= w[k] ^ w[0];
+        constant_flag[j] = diff == 0;
+    }
+    uint8_t *la = f + 14;
+    if (threadIdx.x < kCtPrefixBytes) la[threadIdx.x] = prefix[threadIdx.x];
+    uint8_t *lw = f + 9 + 122 + 6;
+    for (int i = threadIdx.x; i < kCodecCtWords; i += 256) {
+        const u64 v = w[i];
+        if (i >= 2) {
+            uint8_t *d = lw + 5 * (size_t)(i - 2);
+            d[0] = (uint8_t)v, d[1] = (uint8_t)(v >> 8), d[2] = (uint8_t)(v >> 16), d[3] = (uint8_t)(v >> 24), d[4] = (uint8_t)(v >> 32);
+        } else {
+            uint8_t *d = la + kCtPrefixBytes + 8 * i;
+            const int nb = i == 0 ? 8 : 5;
+            for (int k = 0; k < nb; k++) d[k] = (uint8_t)(v >> (8 * k));
+        }
+    }
+}
+}  // namespace
+
+size_t codec_work_bytes() { return sizeof(zd::Work); }
+
+cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status, void *work,
+                                 const uint8_t *prefix, u64 *dst_a, u64 *dst_b, int n_jobs, bool any_zstd, bool any_packed,
+                                 cudaStream_t s) {
+    if (n_jobs == 0) return cudaSuccess;
+    if (any_zstd) {
+        static std::atomic<bool> configured{false};  // per process; every device context sets it again harmlessly
+        cudaError_t e = cudaFuncSetAttribute(k_zstd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
+        if (e != cudaSuccess) return e;
+        configured.store(true);
+        k_zstd_inflate<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, kInflateSmem, s>>>(
+            frames, payloads, jobs, status, (zd::Work *)work, n_jobs);
+        g_codec_launches.fetch_add(1, std::memory_order_relaxed);
+        if (dst_a) {  // (the standalone inflate entry point stops at the payloads)
+            k_ct_unpack<<<n_jobs, 256, 0, s>>>(payloads, jobs, status, prefix, dst_a, dst_b);
+            g_codec_launches.fetch_add(1, std::memory_order_relaxed);
+        }
+    }
+    if (any_packed) {
+        k_unpack40<<<n_jobs, 256, 0, s>>>(frames, jobs, status, prefix, dst_a, dst_b);
+        g_codec_launches.fetch_add(1, std::memory_order_relaxed);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_codec_pack(const u64 *words, uint8_t *frames, int32_t *constant_flag, const uint8_t *prefix, int n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    k_ct_pack40<<<n, 256, 0, s>>>(words, frames, constant_flag, prefix);
+    g_codec_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+
+uint64_t codec_launch_count() { return g_codec_launches.load(); }
+
+}  // namespace fheb

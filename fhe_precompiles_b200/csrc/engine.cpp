@@ -5,6 +5,7 @@
 #include <chrono>
 #include <functional>
 
+#include "codec_kernels.h"
 #include "host_pool.h"
 
 #include <cstdlib>
@@ -57,6 +58,10 @@ Engine::Engine() {
     {
         const char *v = getenv("FHE_B200_HELPER_DECODE");
         helper_decode_ = !(v && *v == '0');
+        v = getenv("FHE_B200_DEVICE_CODEC");
+        device_codec_ = !(v && *v == '0');
+        v = getenv("FHE_B200_DEVICE_ZSTD");
+        device_zstd_ = v && *v == '1';
     }
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
@@ -114,6 +119,32 @@ void Engine::ensure_capacity(Lane *l, size_t cap) {
     cuda_throw(cudaMalloc((void **)&l->d_plain, cap * kN * 2), "cudaMalloc");
     cuda_throw(cudaMalloc((void **)&l->d_scratch, cap * kScratchLimbsPerOp * kN * 8), "cudaMalloc");
     l->cap = cap;
+}
+
+// device codec buffers for lane->cap calls (two ciphertext operands each)
+void Engine::ensure_codec(Lane *l) {
+    if (l->codec_cap >= l->cap) return;
+    cudaFreeHost(l->h_frames), cudaFreeHost(l->h_outframes), cudaFreeHost(l->h_jobs), cudaFreeHost(l->h_status);
+    cudaFree(l->d_frames), cudaFree(l->d_payloads), cudaFree(l->d_outframes), cudaFree(l->d_jobs), cudaFree(l->d_status), cudaFree(l->d_work);
+    l->codec_cap = 0;
+    const size_t cap = l->cap, ops = 2 * cap;
+    cuda_throw(cudaMallocHost((void **)&l->h_frames, ops * kFrameSlotBytes), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_outframes, cap * kPackedFrameStride), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_jobs, ops * sizeof(CodecJob)), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_status, 3 * cap * sizeof(int32_t)), "cudaMallocHost");
+    cuda_throw(cudaMalloc((void **)&l->d_frames, ops * kFrameSlotBytes), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_payloads, ops * kPayloadStride), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_outframes, cap * kPackedFrameStride), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_jobs, ops * sizeof(CodecJob)), "cudaMalloc");
+    cuda_throw(cudaMalloc((void **)&l->d_status, 3 * cap * sizeof(int32_t)), "cudaMalloc");
+    cuda_throw(cudaMalloc(&l->d_work, ops * codec_work_bytes()), "cudaMalloc");
+    if (!l->d_prefix) {
+        uint8_t prefix[kCtPrefixBytes];
+        canonical_ct_prefix(prefix);
+        cuda_throw(cudaMalloc((void **)&l->d_prefix, kCtPrefixBytes), "cudaMalloc");
+        cuda_throw(cudaMemcpy(l->d_prefix, prefix, kCtPrefixBytes, cudaMemcpyHostToDevice), "upload prefix");
+    }
+    l->codec_cap = cap;
 }
 
 Lane *Engine::acquire_lane() {
@@ -553,17 +584,178 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         order.push_back(i);
     }
     const double t_unpack = us_since(t_start);
-    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) {
-        if (prep[x].cls != prep[y].cls) return prep[x].cls < prep[y].cls;
-        return prep[x].cls == kMulCt && prep[x].d_rk < prep[y].d_rk;
-    });
-
-    // pass 2: operands into adjacent staging slots, class by class; a call that fails here gives its slot to the next
     struct Run {
         int cls;
         const uint64_t *d_rk;
         size_t begin, end;
     };
+    const auto by_class = [&](size_t x, size_t y) {
+        if (prep[x].cls != prep[y].cls) return prep[x].cls < prep[y].cls;
+        return prep[x].cls == kMulCt && prep[x].d_rk < prep[y].d_rk;
+    };
+    const auto launch_runs = [&](const std::vector<Run> &rs) {
+        for (const Run &r : rs) {
+            const size_t c = r.end - r.begin;
+            const uint64_t *a = lane->d_a + r.begin * kCtWords;
+            const uint64_t *b = lane->d_b + r.begin * kCtWords;
+            const uint16_t *pl = lane->d_plain + r.begin * kN;
+            uint64_t *o = lane->d_out + r.begin * kCtWords;
+            switch (r.cls) {
+                case kMulCt: {
+                    ScratchMap m(lane->d_scratch, c);
+                    enqueue_mul(a, b, m, c, s, false);
+                    enqueue_relin(m.c3, r.d_rk, o, m, c, s, false);
+                    break;
+                }
+                case kAddCt: cuda_throw(launch_eltwise(a, b, o, c, 0, s), "eltwise"); break;
+                case kSubCt: cuda_throw(launch_eltwise(a, b, o, c, 1, s), "eltwise"); break;
+                case kMulPt: cuda_throw(launch_mul_plain(a, pl, o, c, s), "mul_plain"); break;
+                // a + b: add_plain; ct - pt: sub_plain; pt - ct: negate(sub_plain(ct, pt))  
+                case kAddPt: cuda_throw(launch_plain_addsub(a, pl, o, c, 0, s), "plain_addsub"); break;
+                case kSubCtPt: cuda_throw(launch_plain_addsub(a, pl, o, c, 1, s), "plain_addsub"); break;
+                default: cuda_throw(launch_plain_addsub(a, pl, o, c, 3, s), "plain_addsub"); break;
+            }
+        }
+    };
+    std::stable_sort(order.begin(), order.end(), by_class);
+
+    // ---- device codec pass (tiles only): calls whose operands are zstd-mode ciphertexts with clean framing travel as
+    // compressed frames; the GPU inflates, validates, computes and packs the result frame.  Whatever is not perfectly
+    // ordinary -- and every operand the strict device decoder hands back -- is left for the host pass below, which
+    // reproduces the reference's checks and error codes in their order.
+    if (device_codec_ && cnt >= 2 && !order.empty()) {
+        ensure_codec(lane);
+        std::vector<Run> runs;
+        std::vector<size_t> slot_item, rest;
+        std::vector<int> slot_job0;
+        std::vector<size_t> staged_copies;  // (slot << 1 | operand) of operands inflated on the host
+        size_t slots = 0, ctct_slots = 0, fcur = 0;
+        int njobs = 0;
+        bool any_zstd = false, any_packed = false;
+        const bool pack_on_device = zstd_writer() == 1;
+        for (size_t i : order) {
+            TileItem &it = items[i];
+            Prep &p = prep[i];
+            bool clean = p.key_rc == 0;
+            Span frames[2];
+            int kinds[2] = {0, 0}, nct = 0;
+            const Span cts[2] = {it.shape == Shape::PtCt ? p.sb : p.sa, p.sb};
+            const int want_ct = it.shape == Shape::CtCt ? 2 : 1;
+            CipherView views[2];
+            bool host_staged[2] = {false, false};
+            for (int k = 0; clean && k < want_ct; k++) {
+                Span blob;
+                uint8_t compr = 0;
+                clean = parse_ciphertext_framing(cts[k], &views[k], &blob) == kOk && data_type_matches(views[k].data_type, it.kind);
+                if (!clean) break;
+                kinds[k] = classify_ciphertext_blob(blob, &frames[k], &compr);
+                clean = kinds[k] >= 1 && frames[k].n + 2 * kFramePad <= kFrameSlotBytes;
+                views[k].compr_mode = compr;
+                if (clean && kinds[k] == 1 && !device_zstd_) {
+                    // libzstd-written frame: inflated here (the device decoder is opt-in), staged as words
+                    uint64_t *h = (k == 0 ? lane->h_a : lane->h_b) + slots * kCtWords;
+                    clean = decode_ciphertext(cts[k], &views[k], h) == kOk;
+                    host_staged[k] = true;
+                }
+                nct++;
+            }
+            if (clean && it.shape != Shape::CtCt)
+                clean = encode_scalar(it.kind, it.shape == Shape::CtPt ? p.sb : p.sa, lane->h_plain + slots * kN) == kOk;
+            if (!clean) {
+                rest.push_back(i);
+                continue;
+            }
+            p.va = views[0];
+            slot_job0.push_back(njobs);
+            for (int k = 0; k < nct; k++) {
+                if (host_staged[k]) {
+                    staged_copies.push_back((slots << 1) | (size_t)k);
+                    continue;
+                }
+                const size_t off = fcur + kFramePad;
+                memcpy(lane->h_frames + off, frames[k].p, frames[k].n);
+                lane->h_jobs[njobs++] = CodecJob{off, (uint32_t)frames[k].n, kinds[k] == 2 ? kJobPacked : kJobZstd, (int32_t)slots, k};
+                (kinds[k] == 2 ? any_packed : any_zstd) = true;
+                fcur += (frames[k].n + 2 * kFramePad + 15) & ~(size_t)15;
+            }
+            const uint64_t *rk = p.cls == kMulCt ? p.d_rk : nullptr;
+            if (runs.empty() || runs.back().cls != p.cls || runs.back().d_rk != rk) runs.push_back(Run{p.cls, rk, slots, slots});
+            runs.back().end = ++slots;
+            if (p.cls <= kSubCt) ctct_slots = slots;
+            slot_item.push_back(i);
+        }
+        if (slots) {
+            slot_job0.push_back(njobs);
+            if (njobs) {
+                cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, fcur, cudaMemcpyHostToDevice, s), "H2D frames");
+                cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)njobs * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
+            }
+            // operands inflated on the host: one copy per run of adjacent slots of the same operand array
+            std::sort(staged_copies.begin(), staged_copies.end(), [](size_t x, size_t y) {
+                return (x & 1) != (y & 1) ? (x & 1) < (y & 1) : x < y;
+            });
+            for (size_t i0 = 0; i0 < staged_copies.size();) {
+                size_t i1 = i0 + 1;
+                while (i1 < staged_copies.size() && (staged_copies[i1] & 1) == (staged_copies[i0] & 1) &&
+                       (staged_copies[i1] >> 1) == (staged_copies[i1 - 1] >> 1) + 1)
+                    i1++;
+                const size_t slot = staged_copies[i0] >> 1, nsl = i1 - i0;
+                const bool second = staged_copies[i0] & 1;
+                cuda_throw(cudaMemcpyAsync((second ? lane->d_b : lane->d_a) + slot * kCtWords, (second ? lane->h_b : lane->h_a) + slot * kCtWords,
+                                           nsl * kCtWords * 8, cudaMemcpyHostToDevice, s),
+                           "H2D words");
+                i0 = i1;
+            }
+            if (slots > ctct_slots)
+                cuda_throw(cudaMemcpyAsync(lane->d_plain + ctct_slots * kN, lane->h_plain + ctct_slots * kN,
+                                           (slots - ctct_slots) * kN * 2, cudaMemcpyHostToDevice, s),
+                           "H2D plain");
+            cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix,
+                                            lane->d_a, lane->d_b, njobs, any_zstd, any_packed, s),
+                       "codec inflate");
+            launch_runs(runs);
+            int32_t *d_cflag = lane->d_status + 2 * lane->cap, *h_cflag = lane->h_status + 2 * lane->cap;
+            if (pack_on_device) {
+                cuda_throw(launch_codec_pack(lane->d_out, lane->d_outframes, d_cflag, lane->d_prefix, (int)slots, s), "codec pack");
+                cuda_throw(cudaMemcpyAsync(lane->h_outframes, lane->d_outframes, slots * kPackedFrameStride, cudaMemcpyDeviceToHost, s),
+                           "D2H frames");
+                cuda_throw(cudaMemcpyAsync(h_cflag, d_cflag, slots * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H flags");
+            } else {
+                cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, slots * kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+            }
+            if (njobs)
+                cuda_throw(cudaMemcpyAsync(lane->h_status, lane->d_status, (size_t)njobs * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
+                           "D2H status");
+            cuda_throw(cudaStreamSynchronize(s), "stream sync");
+            for (size_t k = 0; k < slots; k++) {
+                const size_t i = slot_item[k];
+                bool ok = true;
+                for (int j = slot_job0[k]; j < slot_job0[k + 1]; j++) ok = ok && lane->h_status[j] == kJobOk;
+                if (!ok) {
+                    rest.push_back(i);
+                    continue;
+                }
+                TileItem &it = items[i];
+                if (pack_on_device && !h_cflag[k]) {
+                    wrap_ciphertext_blob(prep[i].va, lane->h_outframes + k * kPackedFrameStride, kPackedFrameBytes, &it.out);
+                    it.rc = kOk;
+                } else {
+                    if (pack_on_device) {  // constant result (a transparent ciphertext): the host writer's libzstd path
+                        cuda_throw(cudaMemcpyAsync(lane->h_out + k * kCtWords, lane->d_out + k * kCtWords, kCtWords * 8,
+                                                   cudaMemcpyDeviceToHost, s),
+                                   "D2H");
+                        cuda_throw(cudaStreamSynchronize(s), "stream sync");
+                    }
+                    it.rc = encode_ciphertext(prep[i].va, lane->h_out + k * kCtWords, &it.out);
+                }
+                prep[i].live = false;
+            }
+        }
+        std::stable_sort(rest.begin(), rest.end(), by_class);
+        order.swap(rest);
+    }
+
+    // ---- host pass: operands into adjacent staging slots, class by class; a call that fails here gives its slot to the next
     std::vector<Run> runs;
     std::vector<size_t> slot_item;
     size_t slots = 0, ctct_slots = 0;
@@ -622,28 +814,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                                    cudaMemcpyHostToDevice, s),
                    "H2D plain");
     if (timed) cudaEventRecord(lane->ev[1], s);
-    for (const Run &r : runs) {
-        const size_t c = r.end - r.begin;
-        const uint64_t *a = lane->d_a + r.begin * kCtWords;
-        const uint64_t *b = lane->d_b + r.begin * kCtWords;
-        const uint16_t *pl = lane->d_plain + r.begin * kN;
-        uint64_t *o = lane->d_out + r.begin * kCtWords;
-        switch (r.cls) {
-            case kMulCt: {
-                ScratchMap m(lane->d_scratch, c);
-                enqueue_mul(a, b, m, c, s, false);
-                enqueue_relin(m.c3, r.d_rk, o, m, c, s, false);
-                break;
-            }
-            case kAddCt: cuda_throw(launch_eltwise(a, b, o, c, 0, s), "eltwise"); break;
-            case kSubCt: cuda_throw(launch_eltwise(a, b, o, c, 1, s), "eltwise"); break;
-            case kMulPt: cuda_throw(launch_mul_plain(a, pl, o, c, s), "mul_plain"); break;
-            // a + b: add_plain; ct - pt: sub_plain; pt - ct: negate(sub_plain(ct, pt))  
-            case kAddPt: cuda_throw(launch_plain_addsub(a, pl, o, c, 0, s), "plain_addsub"); break;
-            case kSubCtPt: cuda_throw(launch_plain_addsub(a, pl, o, c, 1, s), "plain_addsub"); break;
-            default: cuda_throw(launch_plain_addsub(a, pl, o, c, 3, s), "plain_addsub"); break;
-        }
-    }
+    launch_runs(runs);
     if (timed) cudaEventRecord(lane->ev[2], s);
     cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, slots * kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
     if (timed) cudaEventRecord(lane->ev[3], s);

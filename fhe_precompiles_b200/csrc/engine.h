@@ -38,6 +38,13 @@ struct Lane {
     uint64_t *d_a = nullptr, *d_b = nullptr, *d_out = nullptr, *d_scratch = nullptr;
     uint16_t *d_plain = nullptr;
     bool busy = false;
+    // device codec staging for tiles (allocated when a tile first uses it): compressed operand frames in, structured frames out
+    size_t codec_cap = 0;
+    uint8_t *h_frames = nullptr, *d_frames = nullptr, *d_payloads = nullptr, *h_outframes = nullptr, *d_outframes = nullptr;
+    uint8_t *d_prefix = nullptr;
+    struct CodecJob *h_jobs = nullptr, *d_jobs = nullptr;
+    int32_t *h_status = nullptr, *d_status = nullptr;  // [2 * cap] job status, then [cap] constant-result flags
+    void *d_work = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call-breakdown timing (created on first use)
 };
 
@@ -144,6 +151,9 @@ class Engine {
     Engine();
     void create_lanes();
     void ensure_capacity(Lane *lane, size_t cap);
+    void ensure_codec(Lane *lane);
+    bool device_codec_ = true;  // FHE_B200_DEVICE_CODEC=0: tiles decode and encode everything on the host
+    bool device_zstd_ = false;  // FHE_B200_DEVICE_ZSTD=1: libzstd-written operand frames are inflated on the GPU too (k_zstd_inflate)
     size_t tile_ops_ = 16;
     bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
     std::atomic<bool> call_timing_{false};

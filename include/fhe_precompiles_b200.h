@@ -188,6 +188,13 @@ int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, 
  * SEAL's default does (~88.5 KB, ~1 ms).  Both are RFC 8878 frames any SEAL build reads.  mode < 0 only queries.
  * Returns the previous mode.  Also settable with FHE_B200_ZSTD_WRITER=lib. */
 int32_t fhe_b200_set_zstd_writer(int32_t mode);
+/* Device-side zstd inflate of n ciphertext-payload frames (codec_kernels.cu, zstd_dec.h): what fhe_b200_batch uses for the
+ * operands of a tile.  frames[i] / lens[i] are host buffers; `out` receives n payloads of 131,169 bytes; status[i] = 1 when
+ * the frame was inflated (byte-identical to libzstd), 2 when the strict decoder hands it back to the host (unsupported
+ * feature, malformed frame, or content that is not a 131,169-byte payload).  The batch surface additionally
+ * checks the 97-byte prefix and every residue (k_ct_unpack); this entry point stops at the payload bytes.  elapsed_ms: kernels only. */
+int32_t fhe_b200_zstd_inflate(int32_t device, const uint8_t *const *frames, const size_t *lens, size_t n, uint8_t *out,
+                              int32_t *status, float *elapsed_ms);
 void fhe_b200_parms_id(int32_t which, uint64_t out[4]);
 
 #ifdef __cplusplus

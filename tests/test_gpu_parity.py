@@ -1,9 +1,11 @@
 """GPU parity: every kernel behind the C ABI, bit-compared with the CPU oracle on the same inputs.
 Bar: bit-exact (integer work).  Run on the B200 box: pytest -m gpu."""
+import os
+
 import numpy as np
 import pytest
 
-from helpers import KINDS, MODULI, N, REF_A, REF_B, REF_EXPECT, decrypt_value, encrypt_value, oracle_binary, plain_u16, precompile_name, random_ct, value_of
+from helpers import KINDS, MODULI, N, ROOT, REF_A, REF_B, REF_EXPECT, decrypt_value, encrypt_value, oracle_binary, plain_u16, precompile_name, random_ct, value_of
 from oracle import bfv
 from oracle import formats as F
 
@@ -271,6 +273,99 @@ def test_batch_tiles_equal_single_calls(keys):
     order = rng.permutation(len(calls))
     got = FHE.run_batch([calls[i] for i in order], host_threads=2)
     assert all(got[k] == want[i] for k, i in enumerate(order))
+
+
+def test_device_zstd_inflate_matches_libzstd(dev):
+    """k_zstd_inflate (csrc/zstd_dec.h on the device): ciphertext-payload frames written by libzstd at several levels, by the
+    structured writer, other content of the same size (Huffman literals, RLE, raw blocks) and corrupted frames. A frame the
+    device accepts must be byte-identical to libzstd's output; everything else must be handed back (status 2)."""
+    import ctypes
+
+    from fhe_precompiles_b200 import _lib
+
+    L = _lib.lib()
+    z = F.zstd()
+    rng = np.random.default_rng(2024)
+    size = 97 + 8 * 4 * N
+    ct = lambda: bytes(rng.integers(0, 256, 97, dtype=np.uint8)) + np.stack(
+        [rng.integers(0, MODULI[l], N, dtype=np.uint64) for _ in range(2) for l in range(2)]).tobytes()
+    text = bytes(rng.choice(list(b"abcdefgh \n"), size=size).astype(np.uint8))
+    payloads = [ct() for _ in range(6)] + [text, bytes(size), rng.integers(0, 256, size, dtype=np.uint8).tobytes()]
+    levels = [-3, 1, 3, 7, 12, 19, 3, 3, 3]
+    frames = [z.compress(p, lvl) for p, lvl in zip(payloads, levels)]
+    payloads.append(payloads[0]), frames.append(F.zstd_structured_frame(payloads[0]))
+    good = len(frames)
+    for it in range(40):  # corrupted variants
+        fr = bytearray(frames[it % 6])
+        if it % 3 == 0:
+            fr[rng.integers(0, len(fr))] ^= 1 << rng.integers(0, 8)
+        elif it % 3 == 1:
+            fr = fr[: rng.integers(1, len(fr))]
+        else:
+            i = rng.integers(0, len(fr) - 4)
+            fr[i : i + 4] = bytes(rng.integers(0, 256, 4, dtype=np.uint8))
+        frames.append(bytes(fr))
+        try:
+            ok = z.lib.ZSTD_getFrameContentSize(frames[-1], len(frames[-1])) == size
+            payloads.append(z.decompress(frames[-1]) if ok else None)
+        except ValueError:
+            payloads.append(None)
+    n = len(frames)
+    bufs = [ctypes.create_string_buffer(f, len(f)) for f in frames]
+    ptrs = (ctypes.c_void_p * n)(*[ctypes.cast(b, ctypes.c_void_p) for b in bufs])
+    lens = (ctypes.c_size_t * n)(*[len(f) for f in frames])
+    out = ctypes.create_string_buffer(n * size)
+    status = (ctypes.c_int32 * n)()
+    ms = ctypes.c_float()
+    assert L.fhe_b200_zstd_inflate(0, ptrs, lens, n, out, status, ctypes.byref(ms)) == 0
+    raw = out.raw
+    assert list(status[:good]) == [1] * good, "every well-formed frame is inflated on the device"
+    for i in range(n):
+        assert status[i] in (1, 2)
+        if status[i] == 1:
+            assert payloads[i] is not None and raw[i * size : (i + 1) * size] == payloads[i], i
+
+
+def test_batch_tiles_with_device_zstd(keys):
+    """FHE_B200_DEVICE_ZSTD=1: the operands of a tile are inflated by k_zstd_inflate instead of libzstd. Same statuses and bytes
+    as the single-call symbols (the knob is read when the engine starts, hence the subprocess)."""
+    import subprocess
+    import sys
+
+    code = """
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from helpers import KeySet, KINDS, encrypt_value, precompile_name, value_of
+from fhe_precompiles_b200 import FHE, FheError, pack
+from oracle import formats as F
+keys = KeySet.load()
+calls = []
+for i in range(24):
+    kind = KINDS[i %% 4]; op = ("add", "sub", "mul")[(i // 4) %% 3]; shape = ("ctct", "ctpt", "ptct")[(i // 2) %% 3]
+    va, vb = value_of(kind, 2 + i %% 5), value_of(kind, 1 + i %% 3)
+    ca = F.make_ciphertext(kind, encrypt_value(keys, kind, va, 700 + i)).to_bytes()
+    cb = F.make_ciphertext(kind, encrypt_value(keys, kind, vb, 800 + i)).to_bytes(structured=bool(i & 1))
+    sc = pack.SERIALIZE[kind](vb)
+    args = {"ctct": (ca, cb), "ctpt": (ca, sc), "ptct": (sc, cb)}[shape]
+    data = pack.pack_binary_operation(keys.pub_bytes, *args)
+    if i %% 9 == 4: data = pack.pack_binary_operation(keys.pub_bytes, ca[:-9], args[1]) if shape != "ptct" else data[:11]
+    if i %% 9 == 7:
+        bad = bytearray(ca); bad[-300] ^= 0x10
+        data = pack.pack_binary_operation(keys.pub_bytes, bytes(bad), args[1]) if shape != "ptct" else data
+    calls.append((precompile_name(op, shape, kind), data))
+want = []
+for name, data in calls:
+    try: want.append((0, getattr(FHE, name)(data)))
+    except FheError as e: want.append((e.code, b""))
+got = FHE.run_batch(calls, host_threads=2)
+assert got == want, [(g[0], w[0]) for g, w in zip(got, want)]
+assert sum(1 for st, _ in want if st == 0) >= 16 and any(st for st, _ in want)
+print("device-zstd tiles ok")
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, FHE_B200_DEVICE_ZSTD="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "device-zstd tiles ok" in r.stdout, r.stdout + r.stderr
 
 
 def test_libzstd_writer_mode_and_chained_calls(keys):

@@ -1,0 +1,17 @@
+// Host build of the device zstd decoder (fhe_precompiles_b200/csrc/zstd_dec.h) for tests/test_zstd_dec.py: the same source
+// that k_zstd_inflate runs, compiled with g++ so that it can be compared with libzstd and fuzzed without a GPU.
+#include <cstring>
+#include <vector>
+
+#include "zstd_dec.h"
+
+extern "C" int zd_decode(const uint8_t *src, size_t slen, uint8_t *dst, size_t cap, size_t *dlen) {
+    static thread_local fheb::zd::Work *w = nullptr;
+    if (!w) {
+        w = new fheb::zd::Work();
+        fheb::zd::work_bind(w, nullptr);
+    }
+    std::vector<uint8_t> buf(slen + 2 * fheb::zd::kPad, 0xAA);  // the decoder reads aligned words around the frame
+    memcpy(buf.data() + fheb::zd::kPad, src, slen);
+    return fheb::zd::decode_frame(buf.data() + fheb::zd::kPad, slen, dst, cap, dlen, w);
+}
