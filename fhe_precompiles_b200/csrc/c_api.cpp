@@ -441,7 +441,7 @@ int32_t fhe_b200_zstd_inflate(int32_t device, const uint8_t *const *frames, cons
         cudaEventCreate(&e0), cudaEventCreate(&e1);
         for (int rep = 0; rep < 6; rep++) {  // the last repetition is timed: the first ones bring the clocks up
             cudaEventRecord(e0, nullptr);
-            cuda_throw(launch_codec_inflate(d_frames, d_payloads, d_jobs, d_status, d_work, d_prefix, nullptr, nullptr, (int)n, true, false,
+            cuda_throw(launch_codec_inflate(d_frames, d_payloads, d_jobs, d_status, d_work, d_prefix, nullptr, nullptr, (int)n, true, false, false,
                                             nullptr),
                        "inflate");
             cudaEventRecord(e1, nullptr);

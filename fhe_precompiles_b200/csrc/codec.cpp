@@ -563,6 +563,16 @@ int classify_ciphertext_blob(Span blob, Span *frame, uint8_t *compr) {
     return zstd_is_pack40(frame->p, frame->n, kCtHeaderBytes + 8 * kCtWords) ? 2 : 1;
 }
 
+bool inflate_ct_payload(Span frame, uint8_t *dst) {
+    const ZstdApi &z = zapi();
+    if (!z.ok) throw std::runtime_error("fhe_b200: libzstd.so.1 is required to read SEAL blobs");
+    const size_t want = kCtHeaderBytes + 8 * kCtWords;
+    if (z.getFrameContentSize(frame.p, frame.n) != want) return false;
+    if (!tl_ctx.d) tl_ctx.d = z.createDCtx();
+    const size_t r = z.decompressDCtx(tl_ctx.d, dst, want, frame.p, frame.n);
+    return !z.isError(r) && r == want;
+}
+
 void canonical_ct_prefix(uint8_t *p) {
     const HostContext &H = HostContext::get();
     memcpy(p, H.parms_id_data, 32);

@@ -57,6 +57,9 @@ int32_t parse_ciphertext_framing(Span in, CipherView *view, Span *blob);
 // SEAL header of the blob: -1 malformed, 0 not zstd (compr none / zlib: host path), 1 zstd frame, 2 zstd frame in this library's
 // structured layout (every header byte verified); `frame` = the zstd frame, `compr` = the blob's compr_mode
 int classify_ciphertext_blob(Span blob, Span *frame, uint8_t *compr);
+// libzstd inflate of a ciphertext frame straight into `dst` (131,169 bytes, e.g. pinned staging); false unless the frame
+// holds exactly a payload of that size.  The content is validated on the device (k_ct_unpack).
+bool inflate_ct_payload(Span frame, uint8_t *dst);
 // the 97 bytes every valid size-2 data-level coefficient-form ciphertext payload starts with
 void canonical_ct_prefix(uint8_t *prefix97);
 // bincode(Ciphertext) around an already compressed payload `body` (SEAL header with view.compr_mode added here)

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, cons
                                                    u64 *dst_a, u64 *dst_b) {
     const int j = blockIdx.x;
     const CodecJob job = jobs[j];
-    if (job.kind != kJobZstd || status[j] != kJobOk) return;
+    if (job.kind == kJobZstd ? status[j] != kJobOk : job.kind != kJobPayload) return;
     const uint8_t *p = payloads + (size_t)j * kPayloadStride;  // 8-byte aligned
     __shared__ int bad;
     if (threadIdx.x == 0) bad = 0;
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, cons
     }
     if (mybad) atomicOr(&bad, 1);
     __syncthreads();
-    if (threadIdx.x == 0 && bad) status[j] = kJobFallback;
+    if (threadIdx.x == 0) status[j] = bad ? kJobFallback : kJobOk;
 }
 
 // structured frames: the host has verified every header byte; literals are at two fixed places of the frame
@@ -158,7 +158,7 @@ size_t codec_work_bytes() { return sizeof(zd::Work); }
 
 cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status, void *work,
                                  const uint8_t *prefix, u64 *dst_a, u64 *dst_b, int n_jobs, bool any_zstd, bool any_packed,
-                                 cudaStream_t s) {
+                                 bool any_payload, cudaStream_t s) {
     if (n_jobs == 0) return cudaSuccess;
     if (any_zstd) {
         static std::atomic<bool> configured{false};  // per process; every device context sets it again harmlessly
@@ -168,10 +168,10 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
         k_zstd_inflate<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, kInflateSmem, s>>>(
             frames, payloads, jobs, status, (zd::Work *)work, n_jobs);
         g_codec_launches.fetch_add(1, std::memory_order_relaxed);
-        if (dst_a) {  // (the standalone inflate entry point stops at the payloads)
-            k_ct_unpack<<<n_jobs, 256, 0, s>>>(payloads, jobs, status, prefix, dst_a, dst_b);
-            g_codec_launches.fetch_add(1, std::memory_order_relaxed);
-        }
+    }
+    if ((any_zstd || any_payload) && dst_a) {  // (the standalone inflate entry point stops at the payloads)
+        k_ct_unpack<<<n_jobs, 256, 0, s>>>(payloads, jobs, status, prefix, dst_a, dst_b);
+        g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (any_packed) {
         k_unpack40<<<n_jobs, 256, 0, s>>>(frames, jobs, status, prefix, dst_a, dst_b);

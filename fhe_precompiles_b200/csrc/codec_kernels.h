@@ -16,7 +16,7 @@ constexpr size_t kPackedFrameStride = 82064;
 constexpr size_t kFramePad = 16;                             // readable bytes required around every staged frame (zstd_dec.h kPad)
 constexpr size_t kFrameSlotBytes = 139264;                   // staging slot per operand: frame <= slot - 2 pads (zstd never expands by more)
 
-enum : int32_t { kJobNone = 0, kJobZstd = 1, kJobPacked = 2 };  // CodecJob::kind
+enum : int32_t { kJobNone = 0, kJobZstd = 1, kJobPacked = 2, kJobPayload = 3 };  // CodecJob::kind (3: payload inflated by the host)
 enum : int32_t { kJobPending = 0, kJobOk = 1, kJobFallback = 2 };  // status
 
 struct CodecJob {
@@ -31,7 +31,7 @@ size_t codec_work_bytes();  // decoder workspace per job
 // inflate + validate + unpack every job into dst_a / dst_b slots; status[j] = kJobOk or kJobFallback
 cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status, void *work,
                                  const uint8_t *prefix, uint64_t *dst_a, uint64_t *dst_b, int n_jobs, bool any_zstd,
-                                 bool any_packed, cudaStream_t s);
+                                 bool any_packed, bool any_payload, cudaStream_t s);
 // n result ciphertexts -> n structured frames (kPackedFrameStride apart); constant_flag[i] = 1 if the host must use libzstd instead
 cudaError_t launch_codec_pack(const uint64_t *words, uint8_t *frames, int32_t *constant_flag, const uint8_t *prefix, int n,
                               cudaStream_t s);

@@ -124,11 +124,12 @@ void Engine::ensure_capacity(Lane *l, size_t cap) {
 // device codec buffers for lane->cap calls (two ciphertext operands each)
 void Engine::ensure_codec(Lane *l) {
     if (l->codec_cap >= l->cap) return;
-    cudaFreeHost(l->h_frames), cudaFreeHost(l->h_outframes), cudaFreeHost(l->h_jobs), cudaFreeHost(l->h_status);
+    cudaFreeHost(l->h_frames), cudaFreeHost(l->h_payloads), cudaFreeHost(l->h_outframes), cudaFreeHost(l->h_jobs), cudaFreeHost(l->h_status);
     cudaFree(l->d_frames), cudaFree(l->d_payloads), cudaFree(l->d_outframes), cudaFree(l->d_jobs), cudaFree(l->d_status), cudaFree(l->d_work);
     l->codec_cap = 0;
     const size_t cap = l->cap, ops = 2 * cap;
     cuda_throw(cudaMallocHost((void **)&l->h_frames, ops * kFrameSlotBytes), "cudaMallocHost");
+    cuda_throw(cudaMallocHost((void **)&l->h_payloads, ops * kPayloadStride), "cudaMallocHost");
     cuda_throw(cudaMallocHost((void **)&l->h_outframes, cap * kPackedFrameStride), "cudaMallocHost");
     cuda_throw(cudaMallocHost((void **)&l->h_jobs, ops * sizeof(CodecJob)), "cudaMallocHost");
     cuda_throw(cudaMallocHost((void **)&l->h_status, 3 * cap * sizeof(int32_t)), "cudaMallocHost");
@@ -628,10 +629,10 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         std::vector<Run> runs;
         std::vector<size_t> slot_item, rest;
         std::vector<int> slot_job0;
-        std::vector<size_t> staged_copies;  // (slot << 1 | operand) of operands inflated on the host
+        std::vector<size_t> staged_copies;  // job indices (= payload slots) of operands inflated on the host, ascending
         size_t slots = 0, ctct_slots = 0, fcur = 0;
         int njobs = 0;
-        bool any_zstd = false, any_packed = false;
+        bool any_zstd = false, any_packed = false, any_payload = false;
         const bool pack_on_device = zstd_writer() == 1;
         for (size_t i : order) {
             TileItem &it = items[i];
@@ -652,9 +653,9 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                 clean = kinds[k] >= 1 && frames[k].n + 2 * kFramePad <= kFrameSlotBytes;
                 views[k].compr_mode = compr;
                 if (clean && kinds[k] == 1 && !device_zstd_) {
-                    // libzstd-written frame: inflated here (the device decoder is opt-in), staged as words
-                    uint64_t *h = (k == 0 ? lane->h_a : lane->h_b) + slots * kCtWords;
-                    clean = decode_ciphertext(cts[k], &views[k], h) == kOk;
+                    // libzstd-written frame: inflated here (the device decoder is opt-in) straight into the pinned payload slot
+                    // of its job; prefix and residues are validated by k_ct_unpack
+                    clean = inflate_ct_payload(frames[k], lane->h_payloads + (size_t)(njobs + k) * kPayloadStride);
                     host_staged[k] = true;
                 }
                 nct++;
@@ -669,7 +670,9 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
             slot_job0.push_back(njobs);
             for (int k = 0; k < nct; k++) {
                 if (host_staged[k]) {
-                    staged_copies.push_back((slots << 1) | (size_t)k);
+                    staged_copies.push_back((size_t)njobs);  // payload slot = job index
+                    lane->h_jobs[njobs++] = CodecJob{0, 0, kJobPayload, (int32_t)slots, k};
+                    any_payload = true;
                     continue;
                 }
                 const size_t off = fcur + kFramePad;
@@ -687,23 +690,17 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         if (slots) {
             slot_job0.push_back(njobs);
             if (njobs) {
-                cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, fcur, cudaMemcpyHostToDevice, s), "H2D frames");
+                if (fcur) cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, fcur, cudaMemcpyHostToDevice, s), "H2D frames");
                 cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)njobs * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
             }
-            // operands inflated on the host: one copy per run of adjacent slots of the same operand array
-            std::sort(staged_copies.begin(), staged_copies.end(), [](size_t x, size_t y) {
-                return (x & 1) != (y & 1) ? (x & 1) < (y & 1) : x < y;
-            });
+            // payloads inflated on the host: one copy per run of adjacent payload slots
             for (size_t i0 = 0; i0 < staged_copies.size();) {
                 size_t i1 = i0 + 1;
-                while (i1 < staged_copies.size() && (staged_copies[i1] & 1) == (staged_copies[i0] & 1) &&
-                       (staged_copies[i1] >> 1) == (staged_copies[i1 - 1] >> 1) + 1)
-                    i1++;
-                const size_t slot = staged_copies[i0] >> 1, nsl = i1 - i0;
-                const bool second = staged_copies[i0] & 1;
-                cuda_throw(cudaMemcpyAsync((second ? lane->d_b : lane->d_a) + slot * kCtWords, (second ? lane->h_b : lane->h_a) + slot * kCtWords,
-                                           nsl * kCtWords * 8, cudaMemcpyHostToDevice, s),
-                           "H2D words");
+                while (i1 < staged_copies.size() && staged_copies[i1] == staged_copies[i1 - 1] + 1) i1++;
+                const size_t j0 = staged_copies[i0];
+                cuda_throw(cudaMemcpyAsync(lane->d_payloads + j0 * kPayloadStride, lane->h_payloads + j0 * kPayloadStride,
+                                           (i1 - i0) * kPayloadStride, cudaMemcpyHostToDevice, s),
+                           "H2D payloads");
                 i0 = i1;
             }
             if (slots > ctct_slots)
@@ -711,7 +708,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                                            (slots - ctct_slots) * kN * 2, cudaMemcpyHostToDevice, s),
                            "H2D plain");
             cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix,
-                                            lane->d_a, lane->d_b, njobs, any_zstd, any_packed, s),
+                                            lane->d_a, lane->d_b, njobs, any_zstd, any_packed, any_payload, s),
                        "codec inflate");
             launch_runs(runs);
             int32_t *d_cflag = lane->d_status + 2 * lane->cap, *h_cflag = lane->h_status + 2 * lane->cap;

@@ -40,7 +40,7 @@ struct Lane {
     bool busy = false;
     // device codec staging for tiles (allocated when a tile first uses it): compressed operand frames in, structured frames out
     size_t codec_cap = 0;
-    uint8_t *h_frames = nullptr, *d_frames = nullptr, *d_payloads = nullptr, *h_outframes = nullptr, *d_outframes = nullptr;
+    uint8_t *h_frames = nullptr, *d_frames = nullptr, *h_payloads = nullptr, *d_payloads = nullptr, *h_outframes = nullptr, *d_outframes = nullptr;
     uint8_t *d_prefix = nullptr;
     struct CodecJob *h_jobs = nullptr, *d_jobs = nullptr;
     int32_t *h_status = nullptr, *d_status = nullptr;  // [2 * cap] job status, then [cap] constant-result flags
