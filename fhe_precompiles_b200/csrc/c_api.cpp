@@ -451,6 +451,8 @@ int32_t fhe_b200_zstd_inflate(int32_t device, const uint8_t *const *frames, cons
         cudaEventDestroy(e0), cudaEventDestroy(e1);
         cuda_throw(cudaMemcpy2D(out, kCtPayloadBytes, d_payloads, kPayloadStride, kCtPayloadBytes, n, cudaMemcpyDeviceToHost), "D2H");
         cuda_throw(cudaMemcpy(status, d_status, n * 4, cudaMemcpyDeviceToHost), "D2H");
+        for (size_t i = 0; i < n; i++)
+            if (status[i] != kJobOk) status[i] = kJobFallback;  // (frames too large to stage were never tried)
         cudaFree(d_frames), cudaFree(d_payloads), cudaFree(d_jobs), cudaFree(d_status), cudaFree(d_work), cudaFree(d_prefix);
         return 0;
     } catch (const std::exception &e) {

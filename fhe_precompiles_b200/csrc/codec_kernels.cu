@@ -42,7 +42,11 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_zstd_inflate(const uint8
     if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
 }
 
-// payload (prefix 97 + 16384 words at byte offset 97) -> aligned words.  One block of 256 threads per job.
+constexpr int kSplit = 8;  // blocks per ciphertext in the parallel kernels (latency of a single call)
+constexpr int kWordsPerBlock = kCodecCtWords / kSplit;
+
+// payload (prefix 97 + 16384 words at byte offset 97) -> aligned words.  kSplit blocks of 256 threads per job.
+// status protocol of the parallel kernels: the host clears status[] before the launch; a block only ever writes kJobFallback.
 __global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, const CodecJob *jobs, int32_t *status, const uint8_t *prefix,
                                                    u64 *dst_a, u64 *dst_b) {
     const int j = blockIdx.x;
@@ -53,13 +57,14 @@ __global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, cons
     if (threadIdx.x == 0) bad = 0;
     __syncthreads();
     int mybad = 0;
-    if (threadIdx.x < kCtPrefixBytes) {
+    if (blockIdx.y == 0 && threadIdx.x < kCtPrefixBytes) {
         // byte 77 is SEAL's minor version inside the inner DynArray header: not constrained by the host parser either
         if (threadIdx.x != 77 && p[threadIdx.x] != prefix[threadIdx.x]) mybad = 1;
     }
     u64 *dst = (job.operand ? dst_b : dst_a) + (size_t)job.slot * kCodecCtWords;
     const u64 *p64 = (const u64 *)p;  // word i lives at bytes 97 + 8 i = 8 (12 + i) + 1
-    for (int i = threadIdx.x; i < kCodecCtWords; i += 256) {
+    const int lo = blockIdx.y * kWordsPerBlock;
+    for (int i = lo + threadIdx.x; i < lo + kWordsPerBlock; i += 256) {
         const u64 w = (p64[12 + i] >> 8) | (p64[13 + i] << 56);
         const u64 q = ((i >> 12) & 1) ? kQ1 : kQ0;
         if (w >= q) mybad = 1;
@@ -67,7 +72,7 @@ __global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, cons
     }
     if (mybad) atomicOr(&bad, 1);
     __syncthreads();
-    if (threadIdx.x == 0) status[j] = bad ? kJobFallback : kJobOk;
+    if (threadIdx.x == 0 && bad) status[j] = kJobFallback;
 }
 
 // structured frames: the host has verified every header byte; literals are at two fixed places of the frame
@@ -82,10 +87,11 @@ __global__ void __launch_bounds__(256) k_unpack40(const uint8_t *frames, const C
     __syncthreads();
     int mybad = 0;
     const uint8_t *la = f + 9 + 3 + 2;  // block A literals: prefix, word 0 (8 bytes), low 5 bytes of word 1
-    if (threadIdx.x < kCtPrefixBytes && threadIdx.x != 77 && la[threadIdx.x] != prefix[threadIdx.x]) mybad = 1;
+    if (blockIdx.y == 0 && threadIdx.x < kCtPrefixBytes && threadIdx.x != 77 && la[threadIdx.x] != prefix[threadIdx.x]) mybad = 1;
     u64 *dst = (job.operand ? dst_b : dst_a) + (size_t)job.slot * kCodecCtWords;
     const uint8_t *lw = f + 9 + (3 + 2 + 110 + 7) + 3 + 3;  // literals of words 2..
-    for (int i = threadIdx.x; i < kCodecCtWords; i += 256) {
+    const int lo = blockIdx.y * kWordsPerBlock;
+    for (int i = lo + threadIdx.x; i < lo + kWordsPerBlock; i += 256) {
         u64 w = 0;
         if (i >= 2) {
             const uint8_t *s = lw + 5 * (size_t)(i - 2);
@@ -100,7 +106,7 @@ __global__ void __launch_bounds__(256) k_unpack40(const uint8_t *frames, const C
     }
     if (mybad) atomicOr(&bad, 1);
     __syncthreads();
-    if (threadIdx.x == 0) status[j] = bad ? kJobFallback : kJobOk;
+    if (threadIdx.x == 0 && bad) status[j] = kJobFallback;
 }
 
 // words -> complete structured frame (kPackedFrameBytes); flag = 1 when the first 16 words are equal (the host writer hands
@@ -109,7 +115,7 @@ __global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *fr
     const int j = blockIdx.x;
     const u64 *w = words + (size_t)j * kCodecCtWords;
     uint8_t *f = frames + (size_t)j * kPackedFrameStride;
-    if (threadIdx.x == 0) {
+    if (blockIdx.y == 0 && threadIdx.x == 0) {
         // frame header: magic, single segment + 4-byte content size
         const uint8_t h[9] = {0x28, 0xB5, 0x2F, 0xFD, 0xA0, (uint8_t)kCtPayloadBytes, (uint8_t)(kCtPayloadBytes >> 8),
                               (uint8_t)(kCtPayloadBytes >> 16), (uint8_t)(kCtPayloadBytes >> 24)};
@@ -138,9 +144,10 @@ __global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *fr
         constant_flag[j] = diff == 0;
     }
     uint8_t *la = f + 14;
-    if (threadIdx.x < kCtPrefixBytes) la[threadIdx.x] = prefix[threadIdx.x];
+    if (blockIdx.y == 0 && threadIdx.x < kCtPrefixBytes) la[threadIdx.x] = prefix[threadIdx.x];
     uint8_t *lw = f + 9 + 122 + 6;
-    for (int i = threadIdx.x; i < kCodecCtWords; i += 256) {
+    const int lo = blockIdx.y * kWordsPerBlock;
+    for (int i = lo + threadIdx.x; i < lo + kWordsPerBlock; i += 256) {
         const u64 v = w[i];
         if (i >= 2) {
             uint8_t *d = lw + 5 * (size_t)(i - 2);
@@ -160,6 +167,8 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
                                  const uint8_t *prefix, u64 *dst_a, u64 *dst_b, int n_jobs, bool any_zstd, bool any_packed,
                                  bool any_payload, cudaStream_t s) {
     if (n_jobs == 0) return cudaSuccess;
+    cudaError_t ce = cudaMemsetAsync(status, 0, (size_t)n_jobs * sizeof(int32_t), s);  // kJobPending
+    if (ce != cudaSuccess) return ce;
     if (any_zstd) {
         static std::atomic<bool> configured{false};  // per process; every device context sets it again harmlessly
         cudaError_t e = cudaFuncSetAttribute(k_zstd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
@@ -170,11 +179,11 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
         g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if ((any_zstd || any_payload) && dst_a) {  // (the standalone inflate entry point stops at the payloads)
-        k_ct_unpack<<<n_jobs, 256, 0, s>>>(payloads, jobs, status, prefix, dst_a, dst_b);
+        k_ct_unpack<<<dim3(n_jobs, kSplit), 256, 0, s>>>(payloads, jobs, status, prefix, dst_a, dst_b);
         g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if (any_packed) {
-        k_unpack40<<<n_jobs, 256, 0, s>>>(frames, jobs, status, prefix, dst_a, dst_b);
+        k_unpack40<<<dim3(n_jobs, kSplit), 256, 0, s>>>(frames, jobs, status, prefix, dst_a, dst_b);
         g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     }
     return cudaGetLastError();
@@ -182,7 +191,7 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
 
 cudaError_t launch_codec_pack(const u64 *words, uint8_t *frames, int32_t *constant_flag, const uint8_t *prefix, int n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    k_ct_pack40<<<n, 256, 0, s>>>(words, frames, constant_flag, prefix);
+    k_ct_pack40<<<dim3(n, kSplit), 256, 0, s>>>(words, frames, constant_flag, prefix);
     g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -151,14 +151,26 @@ void Engine::ensure_codec(Lane *l) {
 Lane *Engine::acquire_lane() {
     std::unique_lock<std::mutex> lk(lane_mu_);
     if (lanes_.empty()) create_lanes();
+    // lowest free lane of the least loaded device: a lone caller keeps reusing lane 0 (warm staging, codec buffers already grown)
     for (;;) {
-        for (size_t k = 0; k < lanes_.size(); k++) {
-            Lane *l = lanes_[(next_lane_ + k) % lanes_.size()].get();
-            if (!l->busy) {
-                l->busy = true;
-                next_lane_ = (next_lane_ + k + 1) % lanes_.size();
-                return l;
+        Lane *best = nullptr;
+        size_t best_busy = ~(size_t)0;
+        for (int d : lane_devices_) {
+            size_t busy = 0;
+            Lane *first_free = nullptr;
+            for (auto &l : lanes_) {
+                if (l->device != d) continue;
+                if (l->busy) busy++;
+                else if (!first_free) first_free = l.get();
             }
+            if (first_free && busy < best_busy) {
+                best = first_free;
+                best_busy = busy;
+            }
+        }
+        if (best) {
+            best->busy = true;
+            return best;
         }
         lane_cv_.wait(lk);
     }
@@ -535,6 +547,126 @@ int32_t Engine::binary_op(Op op, Shape shape, Kind kind, Span in, std::vector<ui
     return it.rc;
 }
 
+// One call whose inputs are perfectly ordinary (the overwhelmingly common case), arranged for latency: the public-key
+// comparison and the inflate of the first operand run on the caller while a pool thread inflates the second operand; payloads
+// are validated and unpacked on the GPU and the result frame is written there.  Returns false -- having produced nothing --
+// whenever anything deviates; binary_tile's general path then redoes the call and owns every error code.
+bool Engine::single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono::steady_clock::time_point t_start) {
+    Span pk, sa, sb;
+    if (unpack_binary_operation(it.in, &pk, &sa, &sb)) return false;
+    const int nct = it.shape == Shape::CtCt ? 2 : 1;
+    const Span cts[2] = {it.shape == Shape::PtCt ? sb : sa, sb};
+    CipherView views[2];
+    Span frames[2];
+    int kinds[2] = {0, 0};
+    for (int k = 0; k < nct; k++) {
+        Span blob;
+        uint8_t compr = 0;
+        if (parse_ciphertext_framing(cts[k], &views[k], &blob) != kOk || !data_type_matches(views[k].data_type, it.kind)) return false;
+        kinds[k] = classify_ciphertext_blob(blob, &frames[k], &compr);
+        if (kinds[k] < 1 || frames[k].n + 2 * kFramePad > kFrameSlotBytes) return false;
+        views[k].compr_mode = compr;
+    }
+    if (zstd_writer() != 1) return false;
+    ensure_codec(lane);
+    cudaStream_t s = lane->stream;
+
+    // operand k is job k: payload slot k (libzstd frames, inflated here) or a structured frame copied as it is
+    size_t frame_off[2] = {kFramePad, kFramePad + ((frames[0].n + 2 * kFramePad + 15) & ~(size_t)15)};
+    const auto stage = [&](int k) -> bool {
+        if (kinds[k] == 2) {
+            memcpy(lane->h_frames + frame_off[k], frames[k].p, frames[k].n);
+            return true;
+        }
+        return inflate_ct_payload(frames[k], lane->h_payloads + (size_t)k * kPayloadStride);
+    };
+    const bool need_relin = it.op == Op::Mul && it.shape == Shape::CtCt;
+    const uint64_t *d_rk = nullptr;
+    KeyPin pin;
+    int32_t key_rc = kOk;
+    bool staged[2] = {true, true};
+    std::atomic<int> next{0};
+    const std::function<void()> work = [&] {  // tasks: first operand, second operand (ct x ct only), key comparison
+        for (int t; (t = next.fetch_add(1)) < 3;) {
+            if (t == 2) key_rc = relin_key(pk, lane->device, &d_rk, need_relin, &pin);
+            else if (t < nct) staged[t] = stage(t);
+        }
+    };
+    HostPool::get().run((size_t)nct, work);
+    if (key_rc != kOk || !staged[0] || !staged[1]) return false;
+    if (it.shape != Shape::CtCt && encode_scalar(it.kind, it.shape == Shape::CtPt ? sb : sa, lane->h_plain) != kOk) return false;
+    const double t_decode = us_since(t_start);
+
+    bool any_payload = false, any_packed = false;
+    for (int k = 0; k < nct; k++) {
+        lane->h_jobs[k] = CodecJob{frame_off[k], (uint32_t)frames[k].n, kinds[k] == 2 ? kJobPacked : kJobPayload, 0, k};
+        (kinds[k] == 2 ? any_packed : any_payload) = true;
+    }
+    if (timed) cudaEventRecord(lane->ev[0], s);
+    cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)nct * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
+    if (any_packed) {
+        const size_t bytes = frame_off[nct - 1] + frames[nct - 1].n + kFramePad;
+        cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, bytes, cudaMemcpyHostToDevice, s), "H2D frames");
+    }
+    if (any_payload) {  // slots 0 and 1 are adjacent: one copy covers both when both are payloads
+        const int first = kinds[0] == 2 ? 1 : 0, last = (nct == 2 && kinds[1] != 2) ? 1 : 0;
+        if (last >= first)
+            cuda_throw(cudaMemcpyAsync(lane->d_payloads + (size_t)first * kPayloadStride, lane->h_payloads + (size_t)first * kPayloadStride,
+                                       (size_t)(last - first + 1) * kPayloadStride, cudaMemcpyHostToDevice, s),
+                       "H2D payloads");
+    }
+    if (it.shape != Shape::CtCt) cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
+    if (timed) cudaEventRecord(lane->ev[1], s);
+    cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix, lane->d_a,
+                                    lane->d_b, nct, false, any_packed, any_payload, s),
+               "codec unpack");
+    if (it.shape == Shape::CtCt) {
+        if (it.op == Op::Mul) {
+            ScratchMap m(lane->d_scratch, 1);
+            enqueue_mul(lane->d_a, lane->d_b, m, 1, s, false);
+            enqueue_relin(m.c3, d_rk, lane->d_out, m, 1, s, false);
+        } else {
+            cuda_throw(launch_eltwise(lane->d_a, lane->d_b, lane->d_out, 1, it.op == Op::Add ? 0 : 1, s), "eltwise");
+        }
+    } else if (it.op == Op::Mul) {
+        cuda_throw(launch_mul_plain(lane->d_a, lane->d_plain, lane->d_out, 1, s), "mul_plain");
+    } else {
+        const int mode = it.op == Op::Add ? 0 : (it.shape == Shape::CtPt ? 1 : 3);
+        cuda_throw(launch_plain_addsub(lane->d_a, lane->d_plain, lane->d_out, 1, mode, s), "plain_addsub");
+    }
+    int32_t *d_cflag = lane->d_status + nct, *h_cflag = lane->h_status + nct;  // right behind the job status: one copy back
+    cuda_throw(launch_codec_pack(lane->d_out, lane->d_outframes, d_cflag, lane->d_prefix, 1, s), "codec pack");
+    if (timed) cudaEventRecord(lane->ev[2], s);
+    cuda_throw(cudaMemcpyAsync(lane->h_outframes, lane->d_outframes, kPackedFrameBytes, cudaMemcpyDeviceToHost, s), "D2H frame");
+    cuda_throw(cudaMemcpyAsync(lane->h_status, lane->d_status, (size_t)(nct + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H status");
+    if (timed) cudaEventRecord(lane->ev[3], s);
+    cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    const double t_device = us_since(t_start);
+    for (int k = 0; k < nct; k++)
+        if (lane->h_status[k] == kJobFallback) return false;
+    if (h_cflag[0]) {  // constant result (a transparent ciphertext): the host writer's libzstd path
+        cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+        cuda_throw(cudaStreamSynchronize(s), "stream sync");
+        it.rc = encode_ciphertext(views[0], lane->h_out, &it.out);
+    } else {
+        wrap_ciphertext_blob(views[0], lane->h_outframes, kPackedFrameBytes, &it.out);
+        it.rc = kOk;
+    }
+    if (timed) {
+        CallBreakdown &b = tl_breakdown;
+        float ms[3] = {0, 0, 0};
+        for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ms[k], lane->ev[k], lane->ev[k + 1]);
+        b.unpack_key_us = 0;  // the key comparison overlaps the inflates on this path
+        b.decode_us = t_decode;
+        b.h2d_us = ms[0] * 1e3;
+        b.kernels_us = ms[1] * 1e3;
+        b.d2h_us = ms[2] * 1e3;
+        b.total_us = us_since(t_start);
+        b.encode_us = b.total_us - t_device;
+    }
+    return true;
+}
+
 void Engine::binary_tile(TileItem *items, size_t cnt) {
     if (cnt == 0) return;
     const bool timed = call_timing_.load(std::memory_order_relaxed);
@@ -546,6 +678,8 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
     cudaStream_t s = lane->stream;
     if (timed && !lane->ev[0])
         for (auto &e : lane->ev) cuda_throw(cudaEventCreate(&e), "cudaEventCreate");
+
+    if (cnt == 1 && device_codec_ && helper_decode_ && single_call_fast(lane, items[0], timed, t_start)) return;
 
     // device work classes; ct-ct first so that the second operand array is one prefix of the slots
     enum Cls { kMulCt = 0, kAddCt, kSubCt, kMulPt, kAddPt, kSubCtPt, kSubPtCt };
@@ -727,7 +861,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
             for (size_t k = 0; k < slots; k++) {
                 const size_t i = slot_item[k];
                 bool ok = true;
-                for (int j = slot_job0[k]; j < slot_job0[k + 1]; j++) ok = ok && lane->h_status[j] == kJobOk;
+                for (int j = slot_job0[k]; j < slot_job0[k + 1]; j++) ok = ok && lane->h_status[j] != kJobFallback;
                 if (!ok) {
                     rest.push_back(i);
                     continue;

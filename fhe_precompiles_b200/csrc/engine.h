@@ -3,6 +3,7 @@
 // `FHE: Lazy<FheApp>` (testnet.rs:25).  There is no CPU path: every op runs on a CUDA device or fails.
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <memory>
@@ -152,6 +153,7 @@ class Engine {
     void create_lanes();
     void ensure_capacity(Lane *lane, size_t cap);
     void ensure_codec(Lane *lane);
+    bool single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono::steady_clock::time_point t_start);
     bool device_codec_ = true;  // FHE_B200_DEVICE_CODEC=0: tiles decode and encode everything on the host
     bool device_zstd_ = false;  // FHE_B200_DEVICE_ZSTD=1: libzstd-written operand frames are inflated on the GPU too (k_zstd_inflate)
     size_t tile_ops_ = 16;
