@@ -62,6 +62,8 @@ Engine::Engine() {
         device_codec_ = !(v && *v == '0');
         v = getenv("FHE_B200_DEVICE_ZSTD");
         device_zstd_ = v && *v == '1';
+        v = getenv("FHE_B200_CALL_GRAPHS");
+        call_graphs_ = !(v && *v == '0');
     }
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
@@ -102,9 +104,15 @@ void Engine::create_lanes() {
     }
 }
 
+void Engine::drop_graphs(Lane *l) {
+    for (auto &g : l->graphs) cudaGraphExecDestroy(g.exec);
+    l->graphs.clear();
+}
+
 // (re)allocates the lane's staging for `cap` calls; the lane is held by the caller and its stream is idle
 void Engine::ensure_capacity(Lane *l, size_t cap) {
     if (l->cap >= cap) return;
+    drop_graphs(l);
     cudaFreeHost(l->h_a), cudaFreeHost(l->h_b), cudaFreeHost(l->h_out), cudaFreeHost(l->h_plain);
     cudaFree(l->d_a), cudaFree(l->d_b), cudaFree(l->d_out), cudaFree(l->d_plain), cudaFree(l->d_scratch);
     l->cap = 0;
@@ -124,6 +132,7 @@ void Engine::ensure_capacity(Lane *l, size_t cap) {
 // device codec buffers for lane->cap calls (two ciphertext operands each)
 void Engine::ensure_codec(Lane *l) {
     if (l->codec_cap >= l->cap) return;
+    drop_graphs(l);
     cudaFreeHost(l->h_frames), cudaFreeHost(l->h_payloads), cudaFreeHost(l->h_outframes), cudaFreeHost(l->h_jobs), cudaFreeHost(l->h_status);
     cudaFree(l->d_frames), cudaFree(l->d_payloads), cudaFree(l->d_outframes), cudaFree(l->d_jobs), cudaFree(l->d_status), cudaFree(l->d_work);
     l->codec_cap = 0;
@@ -572,7 +581,7 @@ bool Engine::single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono:
     cudaStream_t s = lane->stream;
 
     // operand k is job k: payload slot k (libzstd frames, inflated here) or a structured frame copied as it is
-    size_t frame_off[2] = {kFramePad, kFramePad + ((frames[0].n + 2 * kFramePad + 15) & ~(size_t)15)};
+    const size_t frame_off[2] = {kFramePad, kFramePad + kFrameSlotBytes};  // fixed places: the copies below are replayed as a graph
     const auto stage = [&](int k) -> bool {
         if (kinds[k] == 2) {
             memcpy(lane->h_frames + frame_off[k], frames[k].p, frames[k].n);
@@ -602,44 +611,73 @@ bool Engine::single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono:
         lane->h_jobs[k] = CodecJob{frame_off[k], (uint32_t)frames[k].n, kinds[k] == 2 ? kJobPacked : kJobPayload, 0, k};
         (kinds[k] == 2 ? any_packed : any_payload) = true;
     }
-    if (timed) cudaEventRecord(lane->ev[0], s);
-    cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)nct * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
-    if (any_packed) {
-        const size_t bytes = frame_off[nct - 1] + frames[nct - 1].n + kFramePad;
-        cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, bytes, cudaMemcpyHostToDevice, s), "H2D frames");
-    }
-    if (any_payload) {  // slots 0 and 1 are adjacent: one copy covers both when both are payloads
-        const int first = kinds[0] == 2 ? 1 : 0, last = (nct == 2 && kinds[1] != 2) ? 1 : 0;
-        if (last >= first)
-            cuda_throw(cudaMemcpyAsync(lane->d_payloads + (size_t)first * kPayloadStride, lane->h_payloads + (size_t)first * kPayloadStride,
-                                       (size_t)(last - first + 1) * kPayloadStride, cudaMemcpyHostToDevice, s),
-                       "H2D payloads");
-    }
-    if (it.shape != Shape::CtCt) cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
-    if (timed) cudaEventRecord(lane->ev[1], s);
-    cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix, lane->d_a,
-                                    lane->d_b, nct, false, any_packed, any_payload, s),
-               "codec unpack");
-    if (it.shape == Shape::CtCt) {
-        if (it.op == Op::Mul) {
-            ScratchMap m(lane->d_scratch, 1);
-            enqueue_mul(lane->d_a, lane->d_b, m, 1, s, false);
-            enqueue_relin(m.c3, d_rk, lane->d_out, m, 1, s, false);
-        } else {
-            cuda_throw(launch_eltwise(lane->d_a, lane->d_b, lane->d_out, 1, it.op == Op::Add ? 0 : 1, s), "eltwise");
-        }
-    } else if (it.op == Op::Mul) {
-        cuda_throw(launch_mul_plain(lane->d_a, lane->d_plain, lane->d_out, 1, s), "mul_plain");
-    } else {
-        const int mode = it.op == Op::Add ? 0 : (it.shape == Shape::CtPt ? 1 : 3);
-        cuda_throw(launch_plain_addsub(lane->d_a, lane->d_plain, lane->d_out, 1, mode, s), "plain_addsub");
-    }
     int32_t *d_cflag = lane->d_status + nct, *h_cflag = lane->h_status + nct;  // right behind the job status: one copy back
-    cuda_throw(launch_codec_pack(lane->d_out, lane->d_outframes, d_cflag, lane->d_prefix, 1, s), "codec pack");
-    if (timed) cudaEventRecord(lane->ev[2], s);
-    cuda_throw(cudaMemcpyAsync(lane->h_outframes, lane->d_outframes, kPackedFrameBytes, cudaMemcpyDeviceToHost, s), "D2H frame");
-    cuda_throw(cudaMemcpyAsync(lane->h_status, lane->d_status, (size_t)(nct + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H status");
-    if (timed) cudaEventRecord(lane->ev[3], s);
+    const auto enqueue = [&](bool ev) {
+        if (ev) cudaEventRecord(lane->ev[0], s);
+        cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)nct * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
+        for (int k = 0; k < nct; k++)
+            if (kinds[k] == 2)  // a structured frame has one size
+                cuda_throw(cudaMemcpyAsync(lane->d_frames + frame_off[k] - kFramePad, lane->h_frames + frame_off[k] - kFramePad,
+                                           kPackedFrameBytes + 2 * kFramePad, cudaMemcpyHostToDevice, s),
+                           "H2D frame");
+        if (any_payload) {  // slots 0 and 1 are adjacent: one copy covers both when both are payloads
+            const int first = kinds[0] == 2 ? 1 : 0, last = (nct == 2 && kinds[1] != 2) ? 1 : 0;
+            if (last >= first)
+                cuda_throw(cudaMemcpyAsync(lane->d_payloads + (size_t)first * kPayloadStride, lane->h_payloads + (size_t)first * kPayloadStride,
+                                           (size_t)(last - first + 1) * kPayloadStride, cudaMemcpyHostToDevice, s),
+                           "H2D payloads");
+        }
+        if (it.shape != Shape::CtCt) cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
+        if (ev) cudaEventRecord(lane->ev[1], s);
+        cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix, lane->d_a,
+                                        lane->d_b, nct, false, any_packed, any_payload, s),
+                   "codec unpack");
+        if (it.shape == Shape::CtCt) {
+            if (it.op == Op::Mul) {
+                ScratchMap m(lane->d_scratch, 1);
+                enqueue_mul(lane->d_a, lane->d_b, m, 1, s, false);
+                enqueue_relin(m.c3, d_rk, lane->d_out, m, 1, s, false);
+            } else {
+                cuda_throw(launch_eltwise(lane->d_a, lane->d_b, lane->d_out, 1, it.op == Op::Add ? 0 : 1, s), "eltwise");
+            }
+        } else if (it.op == Op::Mul) {
+            cuda_throw(launch_mul_plain(lane->d_a, lane->d_plain, lane->d_out, 1, s), "mul_plain");
+        } else {
+            const int mode = it.op == Op::Add ? 0 : (it.shape == Shape::CtPt ? 1 : 3);
+            cuda_throw(launch_plain_addsub(lane->d_a, lane->d_plain, lane->d_out, 1, mode, s), "plain_addsub");
+        }
+        cuda_throw(launch_codec_pack(lane->d_out, lane->d_outframes, d_cflag, lane->d_prefix, 1, s), "codec pack");
+        if (ev) cudaEventRecord(lane->ev[2], s);
+        cuda_throw(cudaMemcpyAsync(lane->h_outframes, lane->d_outframes, kPackedFrameBytes, cudaMemcpyDeviceToHost, s), "D2H frame");
+        cuda_throw(cudaMemcpyAsync(lane->h_status, lane->d_status, (size_t)(nct + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H status");
+        if (ev) cudaEventRecord(lane->ev[3], s);
+    };
+    // every size and pointer above is fixed for a given call shape on this lane (payload slots, structured frames and the
+    // result frame have constant sizes), so the sequence is replayed as a CUDA graph: ~13 launches and copies become one
+    if (call_graphs_ && !timed) {
+        cudaGraphExec_t exec = nullptr;
+        for (const auto &g : lane->graphs)
+            if (g.op == (int)it.op && g.shape == (int)it.shape && g.kind0 == kinds[0] && g.kind1 == kinds[1] && g.rk == d_rk) exec = g.exec;
+        if (!exec) {
+            if (lane->graphs.size() >= 16) drop_graphs(lane);
+            cudaGraph_t graph = nullptr;
+            cuda_throw(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "begin capture");
+            try {
+                enqueue(false);
+            } catch (...) {
+                cudaStreamEndCapture(s, &graph);
+                if (graph) cudaGraphDestroy(graph);
+                throw;
+            }
+            cuda_throw(cudaStreamEndCapture(s, &graph), "end capture");
+            cuda_throw(cudaGraphInstantiate(&exec, graph, 0), "graph instantiate");
+            cudaGraphDestroy(graph);
+            lane->graphs.push_back(Lane::CallGraph{(int)it.op, (int)it.shape, kinds[0], kinds[1], d_rk, exec});
+        }
+        cuda_throw(cudaGraphLaunch(exec, s), "graph launch");
+    } else {
+        enqueue(timed);
+    }
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
     const double t_device = us_since(t_start);
     for (int k = 0; k < nct; k++)

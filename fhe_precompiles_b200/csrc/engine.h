@@ -47,6 +47,14 @@ struct Lane {
     int32_t *h_status = nullptr, *d_status = nullptr;  // [2 * cap] job status, then [cap] constant-result flags
     void *d_work = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // call-breakdown timing (created on first use)
+    // CUDA graphs of the single-call fast path (copies + codec kernels + arithmetic), captured once per call shape and relin
+    // key on this lane's buffers; dropped whenever the buffers are reallocated
+    struct CallGraph {
+        int op, shape, kind0, kind1;
+        const uint64_t *rk;
+        cudaGraphExec_t exec;
+    };
+    std::vector<CallGraph> graphs;
 };
 
 // where the time of the last binary call (or tile) on this thread went, microseconds
@@ -155,6 +163,8 @@ class Engine {
     void ensure_codec(Lane *lane);
     bool single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono::steady_clock::time_point t_start);
     bool device_codec_ = true;  // FHE_B200_DEVICE_CODEC=0: tiles decode and encode everything on the host
+    bool call_graphs_ = true;   // FHE_B200_CALL_GRAPHS=0: the single-call fast path launches its kernels one by one
+    void drop_graphs(Lane *lane);
     bool device_zstd_ = false;  // FHE_B200_DEVICE_ZSTD=1: libzstd-written operand frames are inflated on the GPU too (k_zstd_inflate)
     size_t tile_ops_ = 16;
     bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
