@@ -25,7 +25,7 @@ constexpr size_t kInflateSmemPerWarp = zd::kSeqTableEntries * sizeof(zd::SeqEntr
 constexpr size_t kInflateSmem = kInflateWarps * kInflateSmemPerWarp;
 
 __global__ void __launch_bounds__(kInflateWarps * 32) k_zstd_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
-                                                                      int32_t *status, zd::Work *work, int n) {
+                                                                      int32_t *status, uint8_t *work, size_t work_stride, int n) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int warp = threadIdx.x >> 5;
     const int j = blockIdx.x * kInflateWarps + warp;
@@ -33,12 +33,48 @@ __global__ void __launch_bounds__(kInflateWarps * 32) k_zstd_inflate(const uint8
     const CodecJob job = jobs[j];
     if (job.kind != kJobZstd) return;
     uint8_t *mine = smem + (size_t)warp * kInflateSmemPerWarp;
-    zd::Work *w = work + j;
+    zd::Work *w = (zd::Work *)(work + (size_t)j * work_stride);  // first member of the job's scratch
     if ((threadIdx.x & 31) == 0) zd::work_bind(w, (zd::SeqEntry *)mine);
     __syncwarp();
     size_t dlen = 0;
     const int rc = zd::decode_frame(frames + job.src_off, job.src_len, payloads + (size_t)j * kPayloadStride, kCtPayloadBytes, &dlen, w,
                                     mine + zd::kSeqTableEntries * sizeof(zd::SeqEntry));
+    if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
+}
+
+// ---- two-phase inflate: thread-per-frame planning, warp-per-frame execution (zstd_dec.h, "two-phase decoding")
+constexpr int kPlanLanes = 8;  // frames per warp in phase 1: few enough that a small batch still spreads over many SMs
+struct JobScratch {            // per job, in the `work` buffer
+    zd::Work work;
+    zd::FramePlan plan;
+    uint64_t seqs[zd::kPlanMaxSeqs];
+    uint8_t lits[kCtPayloadBytes + 16];
+};
+
+__global__ void __launch_bounds__(128) k_zstd_plan(const uint8_t *frames, const CodecJob *jobs, JobScratch *scratch, int n) {
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPlanLanes + lane;
+    if (lane >= kPlanLanes || j >= n) return;
+    const CodecJob job = jobs[j];
+    JobScratch *sc = scratch + j;
+    sc->plan.status = zd::kZdFallback;
+    if (job.kind != kJobZstd) return;
+    zd::work_bind(&sc->work, nullptr);
+    zd::plan_frame(frames + job.src_off, job.src_len, kCtPayloadBytes, &sc->work, &sc->plan, sc->seqs, sc->lits);
+}
+
+__global__ void __launch_bounds__(kInflateWarps * 32) k_zstd_execute(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
+                                                                      int32_t *status, const JobScratch *scratch, int n) {
+    __shared__ __align__(16) uint8_t rings[kInflateWarps][zd::kRingBytes];
+    const int warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * kInflateWarps + warp;
+    if (j >= n) return;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobZstd) return;
+    const JobScratch *sc = scratch + j;
+    size_t dlen = 0;
+    const int rc = zd::execute_plan(frames + job.src_off, &sc->plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, &dlen,
+                                    rings[warp]);
     if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
 }
 
@@ -161,7 +197,10 @@ __global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *fr
 }
 }  // namespace
 
-size_t codec_work_bytes() { return sizeof(zd::Work); }
+size_t codec_work_bytes() { return sizeof(JobScratch); }
+
+static std::atomic<int> g_two_phase{0};
+void codec_set_two_phase(int on) { g_two_phase.store(on ? 1 : 0); }
 
 cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status, void *work,
                                  const uint8_t *prefix, u64 *dst_a, u64 *dst_b, int n_jobs, bool any_zstd, bool any_packed,
@@ -169,13 +208,18 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
     if (n_jobs == 0) return cudaSuccess;
     cudaError_t ce = cudaMemsetAsync(status, 0, (size_t)n_jobs * sizeof(int32_t), s);  // kJobPending
     if (ce != cudaSuccess) return ce;
-    if (any_zstd) {
-        static std::atomic<bool> configured{false};  // per process; every device context sets it again harmlessly
+    if (any_zstd && g_two_phase.load()) {
+        const int warps_per_block = 4, frames_per_block = warps_per_block * kPlanLanes;
+        k_zstd_plan<<<(n_jobs + frames_per_block - 1) / frames_per_block, warps_per_block * 32, 0, s>>>(frames, jobs, (JobScratch *)work,
+                                                                                                        n_jobs);
+        k_zstd_execute<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, 0, s>>>(frames, payloads, jobs, status,
+                                                                                                   (const JobScratch *)work, n_jobs);
+        g_codec_launches.fetch_add(2, std::memory_order_relaxed);
+    } else if (any_zstd) {
         cudaError_t e = cudaFuncSetAttribute(k_zstd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
         if (e != cudaSuccess) return e;
-        configured.store(true);
         k_zstd_inflate<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, kInflateSmem, s>>>(
-            frames, payloads, jobs, status, (zd::Work *)work, n_jobs);
+            frames, payloads, jobs, status, (uint8_t *)work, sizeof(JobScratch), n_jobs);
         g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if ((any_zstd || any_payload) && dst_a) {  // (the standalone inflate entry point stops at the payloads)

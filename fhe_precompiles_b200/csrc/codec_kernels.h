@@ -36,5 +36,8 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
 cudaError_t launch_codec_pack(const uint64_t *words, uint8_t *frames, int32_t *constant_flag, const uint8_t *prefix, int n,
                               cudaStream_t s);
 uint64_t codec_launch_count();
+// device zstd inflate: 0 (default) = one warp per frame throughout (lowest latency), 1 = two-phase (thread-per-frame planning +
+// warp-per-frame copies: 3.5x fewer instructions issued, ~1.5x the latency)
+void codec_set_two_phase(int on);
 
 }  // namespace fheb

@@ -440,6 +440,65 @@ ZD_HD void out_run(Frame *f, const uint8_t *src, int rle, size_t n) {
     f->flushed = f->pos;
 }
 
+// One sequence: `ll` literals from lit[*lpos..] (or the RLE byte), then `ml` bytes from `offset` back.  The lanes split the bytes.
+ZD_HD bool exec_sequence(Frame *f, const uint8_t *lit, int lit_rle, size_t regen, size_t block_start, size_t block_max, uint32_t ll,
+                         uint32_t ml, uint32_t offset, size_t *lpos_io, size_t *opos_io) {
+    const int lane = ZD_LANE;
+    uint8_t *out = f->dst;
+    uint8_t *ring = f->ring;
+    size_t lpos = *lpos_io, opos = *opos_io;
+    // execute: the lanes split the bytes
+    if (ll > regen - lpos) return false;
+    if ((size_t)ll + ml > f->cap - opos || opos + ll + ml - block_start > block_max) return false;
+    if (offset > opos + ll || offset > f->window) return false;
+    if (ring && ll + ml <= kFastBytes) {
+        // fast path: the sequence is written through the ring only, in one step.  Byte t < ll is a literal; byte ll + k of the
+        // match is byte (k mod offset) of the source period, which is one of this sequence's own literals, a byte the ring
+        // still holds after this sequence's writes, or -- further back -- a byte already flushed to global memory
+        // (pos - flushed < kFlushChunk at every sequence boundary, so everything older than the ring is in `out`).
+        // Slots written never alias slots read: both lie within one ring length.
+        const size_t from = opos + ll - offset, end = opos + ll + ml;
+        for (uint32_t t = (uint32_t)lane; t < ll + ml; t += ZD_NLANES) {
+            uint8_t v;
+            if (t < ll) {
+                v = lit_rle >= 0 ? (uint8_t)lit_rle : lit[lpos + t];
+            } else {
+                const uint32_t k = t - ll;
+                const size_t sidx = from + (offset >= ml ? k : k % offset);
+                if (sidx >= opos) v = lit_rle >= 0 ? (uint8_t)lit_rle : lit[lpos + (sidx - opos)];
+                else if (sidx + kRingBytes >= end) v = ring[sidx & (kRingBytes - 1)];
+                else v = out[sidx];
+            }
+            ring[(opos + t) & (kRingBytes - 1)] = v;
+        }
+        lpos += ll;
+        opos = end;
+        ZD_SYNC();
+        f->pos = opos;
+        if (opos - f->flushed >= kFlushChunk) out_flush(f, f->flushed + ((opos - f->flushed) & ~(kFlushChunk - 1)));
+    } else {
+        // general path (also the host's): everything below pos is in `out`
+        f->pos = opos;
+        out_run(f, lit_rle >= 0 ? nullptr : lit + lpos, lit_rle, ll);
+        lpos += ll;
+        opos += ll;
+        const size_t from = opos - offset;
+        for (uint32_t k = (uint32_t)lane; k < ml; k += ZD_NLANES) {
+            const uint8_t v = out[from + (offset >= ml ? k : k % offset)];
+            out[opos + k] = v;
+            if (ring && ml - k <= kRingBytes) ring[(opos + k) & (kRingBytes - 1)] = v;
+        }
+        ZD_SYNC();
+        opos += ml;
+        f->pos = opos;
+        f->flushed = opos;
+    }
+
+    *lpos_io = lpos;
+    *opos_io = opos;
+    return true;
+}
+
 ZD_FN int compressed_block(const uint8_t *src, size_t len, Frame *f, Work *w, size_t block_max) {
     if (len < 2) return kZdFallback;
     // ---- literals section
@@ -602,43 +661,7 @@ ZD_FN int compressed_block(const uint8_t *src, size_t len, Frame *f, Work *w, si
                 st_of = eo.next_base + back_read(b, eo.nb);
             }
             if (b.pos < 0) return kZdFallback;
-            // execute: the lanes split the bytes
-            if (ll > regen - lpos) return kZdFallback;
-            if ((size_t)ll + ml > f->cap - opos || opos + ll + ml - block_start > block_max) return kZdFallback;
-            if (offset > opos + ll || offset > f->window) return kZdFallback;
-            if (ring && ll + ml <= kFastBytes && (size_t)offset + ml <= kRingBytes) {
-                // fast path: through the ring only; nothing unflushed is overwritten (pos - flushed stays below the ring size)
-                for (uint32_t k = (uint32_t)lane; k < ll; k += ZD_NLANES)
-                    ring[(opos + k) & (kRingBytes - 1)] = lit_rle >= 0 ? (uint8_t)lit_rle : lit[lpos + k];
-                lpos += ll;
-                opos += ll;
-                ZD_SYNC();  // the match may read the literals just written by other lanes
-                const size_t from = opos - offset;
-                // byte k of the match is byte (k mod offset) of the source period; every source byte precedes opos, and the
-                // slots written never alias the slots read (offset + ml <= ring size)
-                for (uint32_t k = (uint32_t)lane; k < ml; k += ZD_NLANES)
-                    ring[(opos + k) & (kRingBytes - 1)] = ring[(from + (offset >= ml ? k : k % offset)) & (kRingBytes - 1)];
-                opos += ml;
-                ZD_SYNC();
-                f->pos = opos;
-                if (opos - f->flushed >= kFlushChunk) out_flush(f, f->flushed + ((opos - f->flushed) & ~(kFlushChunk - 1)));
-            } else {
-                // general path (also the host's): everything below pos is in `out`
-                f->pos = opos;
-                out_run(f, lit_rle >= 0 ? nullptr : lit + lpos, lit_rle, ll);
-                lpos += ll;
-                opos += ll;
-                const size_t from = opos - offset;
-                for (uint32_t k = (uint32_t)lane; k < ml; k += ZD_NLANES) {
-                    const uint8_t v = out[from + (offset >= ml ? k : k % offset)];
-                    out[opos + k] = v;
-                    if (ring && ml - k <= kRingBytes) ring[(opos + k) & (kRingBytes - 1)] = v;
-                }
-                ZD_SYNC();
-                opos += ml;
-                f->pos = opos;
-                f->flushed = opos;
-            }
+            if (!exec_sequence(f, lit, lit_rle, regen, block_start, block_max, ll, ml, offset, &lpos, &opos)) return kZdFallback;
         }
         if (b.pos != 0) return kZdFallback;  // libzstd insists on an exactly consumed stream in recent versions only
         f->rep[0] = r0, f->rep[1] = r1, f->rep[2] = r2;
@@ -701,6 +724,256 @@ ZD_FN int decode_frame(const uint8_t *src, size_t slen, uint8_t *dst, size_t cap
         if (last) break;
     }
     if (pos != slen || f.pos != (size_t)fcs) return kZdFallback;
+    *dlen = f.pos;
+    return kZdOk;
+}
+
+// ---------------------------------------------------------------- two-phase decoding (device: many frames in flight)
+// A frame's bitstreams are sequential, so one frame cannot use more than one thread for them -- but 32 frames can share a
+// warp.  Phase 1 (plan_frame, ONE THREAD per frame) walks the frame, decodes Huffman literals and turns every sequence
+// into a packed (literal length, match length, resolved offset) record; phase 2 (execute_plan, one warp per frame) only
+// copies bytes.  Same contract as decode_frame: kZdOk means byte-identical to libzstd, everything else goes back to the host.
+constexpr uint32_t kPlanMaxBlocks = 8;
+constexpr uint32_t kPlanMaxSeqs = 40960;
+
+struct BlockPlan {
+    uint32_t type;        // 0 raw, 1 RLE, 2 compressed
+    uint32_t src_off;     // raw: first byte; RLE: the byte; compressed: raw literals (when lit_in_src)
+    uint32_t size;        // raw / RLE: decompressed size
+    uint32_t lit_off;     // literals in the plan's literal buffer (Huffman) -- or in src (raw literals)
+    uint32_t lit_in_src;
+    int32_t lit_rle;      // >= 0: RLE literals
+    uint32_t regen, nseq, seq_off;
+};
+struct FramePlan {
+    int32_t status;
+    uint32_t nblocks, content, window;
+    BlockPlan blocks[kPlanMaxBlocks];
+};
+ZD_HD uint64_t seq_pack(uint32_t ll, uint32_t ml, uint32_t offset) { return (uint64_t)ll | (uint64_t)ml << 18 | (uint64_t)offset << 36; }
+
+// phase 1.  `lits` holds the Huffman-decoded literals of all blocks (capacity `cap` + 8), `seqs` kPlanMaxSeqs records.
+ZD_FN int plan_frame(const uint8_t *src, size_t slen, size_t cap, Work *w, FramePlan *plan, uint64_t *seqs, uint8_t *lits) {
+    plan->status = kZdFallback;
+    if (slen < 6 || le_at(src, 0, 4) != 0xFD2FB528ull) return kZdFallback;
+    const uint8_t fhd = byte_at(src, 4);
+    const int fcs_flag = fhd >> 6, single = (fhd >> 5) & 1;
+    if (fhd & 0x1F) return kZdFallback;
+    size_t pos = 5, window = 0;
+    if (!single) {
+        if (pos >= slen) return kZdFallback;
+        const uint8_t wd = byte_at(src, pos++);
+        const int wlog = 10 + (wd >> 3);
+        if (wlog > 27) return kZdFallback;
+        window = ((size_t)1 << wlog) + (((size_t)1 << wlog) >> 3) * (wd & 7);
+    }
+    const int fcs_bytes = fcs_flag == 0 ? (single ? 1 : 0) : fcs_flag == 1 ? 2 : fcs_flag == 2 ? 4 : 8;
+    if (fcs_bytes == 0 || pos + (size_t)fcs_bytes > slen) return kZdFallback;
+    uint64_t fcs = le_at(src, pos, fcs_bytes);
+    if (fcs_bytes == 2) fcs += 256;
+    pos += (size_t)fcs_bytes;
+    if (fcs > cap || fcs >= (1u << 27)) return kZdFallback;
+    if (single) window = (size_t)fcs;
+    const size_t block_max = window < kBlockMax ? window : kBlockMax;
+    plan->content = (uint32_t)fcs;
+    plan->window = (uint32_t)(window < (1u << 27) ? window : (1u << 27));
+    w->have_ll = w->have_of = w->have_ml = w->have_huf = 0;
+    uint32_t nblocks = 0, nseq_total = 0, lit_total = 0;
+    uint32_t r0 = 1, r1 = 4, r2 = 8;
+    for (;;) {
+        if (pos + 3 > slen || nblocks >= kPlanMaxBlocks) return kZdFallback;
+        const uint32_t bh = (uint32_t)le_at(src, pos, 3);
+        pos += 3;
+        const int last = bh & 1, type = (bh >> 1) & 3;
+        const size_t bsize = bh >> 3;
+        BlockPlan &bp = plan->blocks[nblocks++];
+        bp.type = (uint32_t)type;
+        if (type == 3 || bsize > block_max) return kZdFallback;
+        if (type == 0) {
+            if (pos + bsize > slen) return kZdFallback;
+            bp.src_off = (uint32_t)pos;
+            bp.size = (uint32_t)bsize;
+            pos += bsize;
+        } else if (type == 1) {
+            if (pos + 1 > slen) return kZdFallback;
+            bp.src_off = (uint32_t)pos;
+            bp.size = (uint32_t)bsize;
+            pos += 1;
+        } else {
+            if (bsize < 2 || pos + bsize > slen) return kZdFallback;
+            const uint8_t *b = src + pos;
+            const size_t len = bsize;
+            // literals section (same grammar as compressed_block)
+            const uint8_t b0 = byte_at(b, 0);
+            const int ltype = b0 & 3, sf = (b0 >> 2) & 3;
+            size_t hdr, regen, comp = 0;
+            int streams = 1;
+            if (ltype < 2) {
+                hdr = (sf == 0 || sf == 2) ? 1 : sf == 1 ? 2 : 3;
+                if (hdr > len) return kZdFallback;
+                regen = hdr == 1 ? (size_t)(b0 >> 3) : (size_t)(le_at(b, 0, (int)hdr) >> 4);
+                comp = ltype == 0 ? regen : 1;
+            } else {
+                hdr = sf <= 1 ? 3 : sf == 2 ? 4 : 5;
+                if (hdr > len) return kZdFallback;
+                const uint64_t v = le_at(b, 0, (int)hdr);
+                const int bits = sf <= 1 ? 10 : sf == 2 ? 14 : 18;
+                regen = (size_t)((v >> 4) & ((1u << bits) - 1));
+                comp = (size_t)(v >> (4 + bits));
+                streams = sf == 0 ? 1 : 4;
+            }
+            if (regen > block_max || hdr + comp > len) return kZdFallback;
+            bp.regen = (uint32_t)regen;
+            bp.lit_rle = -1;
+            bp.lit_in_src = 0;
+            const uint8_t *lsrc = b + hdr;
+            if (ltype == 0) {
+                bp.lit_in_src = 1;
+                bp.lit_off = (uint32_t)(pos + hdr);
+            } else if (ltype == 1) {
+                bp.lit_rle = byte_at(lsrc, 0);
+                bp.lit_off = 0;
+            } else {
+                if ((size_t)lit_total + regen > cap) return kZdFallback;
+                uint8_t *out = lits + lit_total;
+                size_t used = 0;
+                if (ltype == 2) {
+                    used = huf_read_tree(lsrc, comp, w);
+                    if (used == 0) return kZdFallback;
+                } else if (!w->have_huf) {
+                    return kZdFallback;
+                }
+                const uint8_t *hs = lsrc + used;
+                const size_t hlen = comp - used;
+                if (streams == 1) {
+                    if (!huf_stream(hs, hlen, out, regen, w)) return kZdFallback;
+                } else {
+                    if (hlen < 6 + 4 || regen < 6) return kZdFallback;
+                    const size_t s1 = (size_t)le_at(hs, 0, 2), s2 = (size_t)le_at(hs, 2, 2), s3 = (size_t)le_at(hs, 4, 2);
+                    const size_t seg = (regen + 3) / 4;
+                    if (6 + s1 + s2 + s3 >= hlen || 3 * seg > regen) return kZdFallback;
+                    const size_t s4 = hlen - 6 - s1 - s2 - s3;
+                    const uint8_t *q = hs + 6;
+                    if (!huf_stream(q, s1, out, seg, w) || !huf_stream(q + s1, s2, out + seg, seg, w) ||
+                        !huf_stream(q + s1 + s2, s3, out + 2 * seg, seg, w) ||
+                        !huf_stream(q + s1 + s2 + s3, s4, out + 3 * seg, regen - 3 * seg, w))
+                        return kZdFallback;
+                }
+                bp.lit_off = lit_total;
+                lit_total += (uint32_t)regen;
+            }
+            // sequences section
+            const uint8_t *ss = b + hdr + comp;
+            const size_t sl = len - hdr - comp;
+            if (sl < 1) return kZdFallback;
+            size_t nseq = byte_at(ss, 0), sh = 1;
+            if (nseq >= 128) {
+                if (nseq == 255) {
+                    if (sl < 3) return kZdFallback;
+                    nseq = (size_t)le_at(ss, 1, 2) + 0x7F00;
+                    sh = 3;
+                } else {
+                    if (sl < 2) return kZdFallback;
+                    nseq = ((nseq - 128) << 8) + byte_at(ss, 1);
+                    sh = 2;
+                }
+            }
+            bp.nseq = (uint32_t)nseq;
+            bp.seq_off = nseq_total;
+            if (nseq == 0) {
+                if (sl != 1) return kZdFallback;
+            } else {
+                if (nseq_total + nseq > kPlanMaxSeqs || sl < sh + 1) return kZdFallback;
+                const uint8_t modes = byte_at(ss, sh);
+                if (modes & 3) return kZdFallback;
+                size_t p = sh + 1;
+                int used = seq_table(modes >> 6, ss + p, sl - p, 0, w);
+                if (used < 0) return kZdFallback;
+                p += (size_t)used;
+                if ((used = seq_table((modes >> 4) & 3, ss + p, sl - p, 1, w)) < 0) return kZdFallback;
+                p += (size_t)used;
+                if ((used = seq_table((modes >> 2) & 3, ss + p, sl - p, 2, w)) < 0) return kZdFallback;
+                p += (size_t)used;
+                if (p >= sl) return kZdFallback;
+                BackBits bb;
+                if (!bb.init(ss + p, sl - p)) return kZdFallback;
+                const SeqEntry *tll = w->ll, *tof = w->of, *tml = w->ml;
+                uint32_t st_ll = back_read(bb, w->ll_log), st_of = back_read(bb, w->of_log), st_ml = back_read(bb, w->ml_log);
+                if (bb.pos < 0) return kZdFallback;
+                uint64_t *so = seqs + nseq_total;
+                size_t lsum = 0;
+                for (size_t i = 0; i < nseq; i++) {
+                    const SeqEntry el = tll[st_ll], eo = tof[st_of], em = tml[st_ml];
+                    const uint32_t ofv = eo.base_value + back_read(bb, eo.add_bits);
+                    const uint32_t ml = em.base_value + back_read(bb, em.add_bits);
+                    const uint32_t ll = el.base_value + back_read(bb, el.add_bits);
+                    uint32_t offset;
+                    if (ofv > 3) {
+                        offset = ofv - 3;
+                        r2 = r1, r1 = r0, r0 = offset;
+                    } else {
+                        const uint32_t idx = ofv - 1 + (ll == 0 ? 1 : 0);
+                        if (idx == 0) {
+                            offset = r0;
+                        } else {
+                            if (idx == 3 && r0 == 1) return kZdFallback;
+                            offset = idx == 1 ? r1 : idx == 2 ? r2 : r0 - 1;
+                            if (idx != 1) r2 = r1;
+                            r1 = r0, r0 = offset;
+                        }
+                    }
+                    if (i + 1 < nseq) {
+                        st_ll = el.next_base + back_read(bb, el.nb);
+                        st_ml = em.next_base + back_read(bb, em.nb);
+                        st_of = eo.next_base + back_read(bb, eo.nb);
+                    }
+                    lsum += ll;
+                    if (bb.pos < 0 || lsum > regen || offset >= (1u << 27)) return kZdFallback;
+                    so[i] = seq_pack(ll, ml, offset);
+                }
+                if (bb.pos != 0) return kZdFallback;
+                nseq_total += (uint32_t)nseq;
+            }
+            pos += bsize;
+        }
+        if (last) break;
+    }
+    if (pos != slen) return kZdFallback;
+    plan->nblocks = nblocks;
+    plan->status = kZdOk;
+    return kZdOk;
+}
+
+// phase 2 (warp-cooperative on the device, scalar on the host)
+ZD_FN int execute_plan(const uint8_t *src, const FramePlan *plan, const uint64_t *seqs, const uint8_t *lits, uint8_t *dst, size_t *dlen,
+                       uint8_t *ring = nullptr) {
+    if (plan->status != kZdOk) return kZdFallback;
+    const size_t window = plan->window;
+    const size_t block_max = window < kBlockMax ? window : kBlockMax;
+    Frame f{dst, (size_t)plan->content, 0, window, {1, 4, 8}, ring, 0};
+    for (uint32_t bi = 0; bi < plan->nblocks; bi++) {
+        const BlockPlan bp = plan->blocks[bi];
+        if (bp.type != 2) {
+            if (bp.size > f.cap - f.pos) return kZdFallback;
+            out_run(&f, bp.type == 0 ? src + bp.src_off : nullptr, bp.type == 0 ? -1 : (int)byte_at(src, bp.src_off), bp.size);
+            continue;
+        }
+        const uint8_t *lit = bp.lit_in_src ? src + bp.lit_off : lits + bp.lit_off;
+        size_t lpos = 0, opos = f.pos;
+        const size_t block_start = opos;
+        const uint64_t *so = seqs + bp.seq_off;
+        for (uint32_t i = 0; i < bp.nseq; i++) {
+            const uint64_t e = so[i];
+            if (!exec_sequence(&f, lit, bp.lit_rle, bp.regen, block_start, block_max, (uint32_t)(e & 0x3FFFF), (uint32_t)((e >> 18) & 0x3FFFF),
+                               (uint32_t)(e >> 36), &lpos, &opos))
+                return kZdFallback;
+        }
+        const size_t rest = bp.regen - lpos;
+        if (rest > f.cap - opos || opos + rest - block_start > block_max) return kZdFallback;
+        f.pos = opos;
+        out_run(&f, bp.lit_rle >= 0 ? nullptr : lit + lpos, bp.lit_rle, rest);
+    }
+    if (f.pos != (size_t)plan->content) return kZdFallback;
     *dlen = f.pos;
     return kZdOk;
 }

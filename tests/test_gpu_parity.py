@@ -275,14 +275,16 @@ def test_batch_tiles_equal_single_calls(keys):
     assert all(got[k] == want[i] for k, i in enumerate(order))
 
 
-def test_device_zstd_inflate_matches_libzstd(dev):
-    """k_zstd_inflate (csrc/zstd_dec.h on the device): ciphertext-payload frames written by libzstd at several levels, by the
+@pytest.mark.parametrize("two_phase", ["0", "1"])
+def test_device_zstd_inflate_matches_libzstd(dev, two_phase, monkeypatch):
+    """k_zstd_inflate / k_zstd_plan + k_zstd_execute (csrc/zstd_dec.h on the device): ciphertext-payload frames written by libzstd at several levels, by the
     structured writer, other content of the same size (Huffman literals, RLE, raw blocks) and corrupted frames. A frame the
     device accepts must be byte-identical to libzstd's output; everything else must be handed back (status 2)."""
     import ctypes
 
     from fhe_precompiles_b200 import _lib
 
+    monkeypatch.setenv("FHE_B200_ZSTD_TWO_PHASE", two_phase)  # read by the entry point on every call
     L = _lib.lib()
     z = F.zstd()
     rng = np.random.default_rng(2024)

@@ -15,3 +15,20 @@ extern "C" int zd_decode(const uint8_t *src, size_t slen, uint8_t *dst, size_t c
     memcpy(buf.data() + fheb::zd::kPad, src, slen);
     return fheb::zd::decode_frame(buf.data() + fheb::zd::kPad, slen, dst, cap, dlen, w);
 }
+
+// the two-phase pipeline (plan_frame + execute_plan), scalar on the host
+extern "C" int zd_decode_two_phase(const uint8_t *src, size_t slen, uint8_t *dst, size_t cap, size_t *dlen) {
+    static thread_local fheb::zd::Work *w = nullptr;
+    static thread_local fheb::zd::FramePlan *plan = nullptr;
+    static thread_local std::vector<uint64_t> seqs(fheb::zd::kPlanMaxSeqs);
+    if (!w) {
+        w = new fheb::zd::Work();
+        fheb::zd::work_bind(w, nullptr);
+        plan = new fheb::zd::FramePlan();
+    }
+    std::vector<uint8_t> buf(slen + 2 * fheb::zd::kPad, 0xAA), lits(cap + 8);
+    memcpy(buf.data() + fheb::zd::kPad, src, slen);
+    const uint8_t *f = buf.data() + fheb::zd::kPad;
+    if (fheb::zd::plan_frame(f, slen, cap, w, plan, seqs.data(), lits.data()) != fheb::zd::kZdOk) return 1;
+    return fheb::zd::execute_plan(f, plan, seqs.data(), lits.data(), dst, dlen);
+}
