@@ -178,7 +178,6 @@ class Engine {
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::mutex lane_mu_;
     std::condition_variable lane_cv_;
-    size_t next_lane_ = 0;
 
     KeyEntry *find_or_parse_key(Span pk, int32_t *rc);  // returns the entry PINNED (users + 1); takes key_mu_ itself
     const uint64_t *network_sk(int device, Span net_pri);

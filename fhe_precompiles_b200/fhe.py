@@ -28,6 +28,24 @@ def _call(name: str, data: bytes) -> bytes:
         L.fhe_free(out)
 
 
+def set_zstd_writer(structured: bool) -> bool:
+    """Extension: how zstd-mode results are written -- True (default) = structure-aware standard zstd frames (82 KB, ~30 us),
+    False = libzstd level 3 as SEAL's default does (~88.5 KB, ~1 ms). Returns the previous setting."""
+    return bool(_lib.lib().fhe_b200_set_zstd_writer(1 if structured else 0))
+
+
+def call_breakdown(enable: bool = True) -> dict:
+    """Extension: phase timing of this thread's last binary precompile call: microseconds spent on framing + key
+    lookup, operand parse + inflate, H2D, kernels, D2H, result encode, and in total. `enable` switches the recording on or off
+    for subsequent calls (it makes single calls launch kernel by kernel instead of replaying a CUDA graph)."""
+    L = _lib.lib()
+    us = (ctypes.c_double * 7)()
+    L.fhe_b200_last_call_breakdown(us)
+    L.fhe_b200_set_call_timing(1 if enable else 0)
+    keys = ("unpack_key_us", "parse_inflate_us", "h2d_us", "kernels_us", "d2h_us", "encode_us", "total_us")
+    return dict(zip(keys, us))
+
+
 class FheApp:
     """The 49 precompiles of fhe.rs:161-779 as methods; see `_lib.PRECOMPILES` for the list."""
 
