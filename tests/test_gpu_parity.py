@@ -583,6 +583,65 @@ def test_concurrent_calls_and_key_cache_eviction(keys, monkeypatch):
     assert not errors, errors
 
 
+def test_batches_and_single_calls_concurrently(keys):
+    """tiles (device codec, shared lanes, host pool) and single calls (fast path, CUDA-graph replay) from several threads at
+    once; every result must equal the oracle's bytes."""
+    import threading
+
+    from fhe_precompiles_b200 import FHE, pack
+
+    a, b = encrypt_value(keys, "i64", 11, 901), encrypt_value(keys, "i64", -4, 902)
+    sa = F.make_ciphertext("i64", a).to_bytes()
+    sb = F.make_ciphertext("i64", b).to_bytes(structured=True)
+    pm = pack.pack_binary_operation(keys.pub_bytes, sa, sb)
+    pn = pack.pack_binary_operation(keys.net_pub_bytes, sa, sb)
+    ps = pack.pack_binary_operation(keys.pub_bytes, sa, pack.serialize_i64(3))
+    want = {
+        "mul": F.make_ciphertext("i64", bfv.mul_relin(a, b, keys.rk)).to_bytes(structured=True),
+        "mul_net": F.make_ciphertext("i64", bfv.mul_relin(a, b, keys.net_rk)).to_bytes(structured=True),
+        "add": F.make_ciphertext("i64", bfv.add(a, b)).to_bytes(structured=True),
+        "mulp": F.make_ciphertext("i64", bfv.multiply_plain(a, bfv.encode("i64", 3))).to_bytes(structured=True),
+    }
+    batch = [("mul_cipheri64_cipheri64", pm), ("add_cipheri64_cipheri64", pm), ("mul_cipheri64_i64", ps),
+             ("mul_cipheri64_cipheri64", pn), ("sub_cipheri64_cipheri64", b"\x00")] * 5
+    batch_want = [want["mul"], want["add"], want["mulp"], want["mul_net"], None] * 5
+    errors = []
+
+    def batches(tid):
+        try:
+            for _ in range(4):
+                res = FHE.run_batch(batch, host_threads=3)
+                for (st, out), w in zip(res, batch_want):
+                    if (w is None and st != 1) or (w is not None and (st != 0 or out != w)):
+                        errors.append(("batch", tid, st))
+        except Exception as e:  # noqa: BLE001
+            errors.append(("batch", tid, repr(e)))
+
+    def singles(tid):
+        try:
+            for it in range(24):
+                which = ("mul", "add", "mulp", "mul_net")[(tid + it) % 4]
+                if which == "mul":
+                    out = FHE.mul_cipheri64_cipheri64(pm)
+                elif which == "add":
+                    out = FHE.add_cipheri64_cipheri64(pm)
+                elif which == "mulp":
+                    out = FHE.mul_cipheri64_i64(ps)
+                else:
+                    out = FHE.mul_cipheri64_cipheri64(pn)
+                if out != want[which]:
+                    errors.append(("single", tid, which))
+        except Exception as e:  # noqa: BLE001
+            errors.append(("single", tid, repr(e)))
+
+    threads = [threading.Thread(target=batches, args=(i,)) for i in range(2)] + [threading.Thread(target=singles, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:5]
+
+
 def test_second_device_and_cross_device_batch(dev, keys):
     """per-device contexts: the same kernels on cuda:1 (own twiddles / constants / key copies) and a byte-surface batch whose
     calls are spread over every GPU. Skipped on single-GPU boxes."""
