@@ -160,7 +160,7 @@ int32_t fhe_b200_init(int32_t device) {
         return -1;
     }
 }
-uint64_t fhe_b200_launch_count(void) { return launch_count(); }
+uint64_t fhe_b200_launch_count(void) { return launch_count() + codec_launch_count(); }
 
 #define OPD(name) {#name, c_fhe_##name}
 #define OPD_TYPE(T)                                                                                              \
