@@ -657,8 +657,12 @@ bool Engine::single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono:
     if (call_graphs_ && !timed) {
         cudaGraphExec_t exec = nullptr;
         for (const auto &g : lane->graphs)
-            if (g.op == (int)it.op && g.shape == (int)it.shape && g.kind0 == kinds[0] && g.kind1 == kinds[1] && g.rk == d_rk) exec = g.exec;
+            if (g.op == (int)it.op && g.shape == (int)it.shape && g.kind0 == kinds[0] && g.kind1 == kinds[1] && g.rk == d_rk) {
+                exec = g.exec;
+                count_launches(g.launches);
+            }
         if (!exec) {
+            const uint64_t before = launch_count() + codec_launch_count();
             if (lane->graphs.size() >= 16) drop_graphs(lane);
             cudaGraph_t graph = nullptr;
             cuda_throw(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal), "begin capture");
@@ -672,7 +676,8 @@ bool Engine::single_call_fast(Lane *lane, TileItem &it, bool timed, std::chrono:
             cuda_throw(cudaStreamEndCapture(s, &graph), "end capture");
             cuda_throw(cudaGraphInstantiate(&exec, graph, 0), "graph instantiate");
             cudaGraphDestroy(graph);
-            lane->graphs.push_back(Lane::CallGraph{(int)it.op, (int)it.shape, kinds[0], kinds[1], d_rk, exec});
+            lane->graphs.push_back(Lane::CallGraph{(int)it.op, (int)it.shape, kinds[0], kinds[1], d_rk, exec,
+                                                   launch_count() + codec_launch_count() - before});
         }
         cuda_throw(cudaGraphLaunch(exec, s), "graph launch");
     } else {

@@ -53,6 +53,7 @@ struct Lane {
         int op, shape, kind0, kind1;
         const uint64_t *rk;
         cudaGraphExec_t exec;
+        uint64_t launches;  // kernels inside, for the launch counter
     };
     std::vector<CallGraph> graphs;
 };

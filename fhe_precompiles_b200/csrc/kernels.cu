@@ -920,6 +920,7 @@ cudaError_t kernels_configure() {
 
 static std::atomic<unsigned long long> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
+void count_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 static int eltwise_grid(size_t n, int block) {
     size_t g = (n + block - 1) / block;

@@ -38,6 +38,7 @@ cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops,
 cudaError_t launch_relin_finish(const u64 *c3, const u64 *ks, u64 *out, size_t n_ops, cudaStream_t s);
 
 uint64_t launch_count();
+void count_launches(uint64_t n);  // kernels replayed through a CUDA graph (the launchers only count at capture time)
 // integer multiply-add peak of the current device in 1e12 mad/s (microbenchmark, synchronous)
 cudaError_t measure_int_peak(int mode, double *tera_ops_per_s);
 // register-only NTT butterfly rate (1e9 butterflies/s) for a small (mod < 3) or a 61-bit prime
