@@ -583,6 +583,30 @@ def test_concurrent_calls_and_key_cache_eviction(keys, monkeypatch):
     assert not errors, errors
 
 
+def test_uncompressed_operands_echo_their_compr_mode(keys):
+    """SEAL blobs with compr_mode none are legal inputs (Serialization::Load reads any mode); the result echoes the mode of the
+    ciphertext operand. Such calls bypass the device codec (single call and inside a tile) and go through the host pass."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    a, b = encrypt_value(keys, "u64", 9, 1001), encrypt_value(keys, "u64", 5, 1002)
+    raw_a = F.make_ciphertext("u64", a).to_bytes(compr=F.COMPR_NONE)
+    raw_b = F.make_ciphertext("u64", b).to_bytes(compr=F.COMPR_NONE)
+    z_b = F.make_ciphertext("u64", b).to_bytes()
+    want_mul = F.make_ciphertext("u64", bfv.mul_relin(a, b, keys.rk))
+    want_sub = F.make_ciphertext("u64", bfv.sub(a, b))
+    p_raw = pack.pack_binary_operation(keys.pub_bytes, raw_a, raw_b)
+    p_mixed = pack.pack_binary_operation(keys.pub_bytes, raw_a, z_b)  # the first operand's mode is echoed
+    for packed in (p_raw, p_mixed):
+        assert FHE.mul_cipheru64_cipheru64(packed) == want_mul.to_bytes(compr=F.COMPR_NONE)
+        assert FHE.sub_cipheru64_cipheru64(packed) == want_sub.to_bytes(compr=F.COMPR_NONE)
+    p_z = pack.pack_binary_operation(keys.pub_bytes, F.make_ciphertext("u64", a).to_bytes(), z_b)
+    res = FHE.run_batch([("mul_cipheru64_cipheru64", p_raw), ("mul_cipheru64_cipheru64", p_z), ("sub_cipheru64_cipheru64", p_mixed),
+                         ("mul_cipheru64_cipheru64", p_z)], host_threads=1)
+    assert res == [(0, want_mul.to_bytes(compr=F.COMPR_NONE)), (0, want_mul.to_bytes(structured=True)),
+                   (0, want_sub.to_bytes(compr=F.COMPR_NONE)), (0, want_mul.to_bytes(structured=True))]
+    assert decrypt_value(keys, "u64", F.Ciphertext.from_bytes(res[0][1]).polys()) == 45
+
+
 def test_batches_and_single_calls_concurrently(keys):
     """tiles (device codec, shared lanes, host pool) and single calls (fast path, CUDA-graph replay) from several threads at
     once; every result must equal the oracle's bytes."""
