@@ -248,12 +248,20 @@ def seal_unwrap(blob: bytes) -> Tuple[bytes, int]:
         return body, compr
     if compr == COMPR_ZSTD:
         return zstd().decompress(body), compr
+    if compr == COMPR_ZLIB:
+        import zlib
+
+        return zlib.decompress(body), compr
     raise ValueError("unsupported compr_mode %d" % compr)
 
 
 def seal_wrap(payload: bytes, compr: int = COMPR_ZSTD, level: int = 3, structured: bool = False) -> bytes:
     if compr == COMPR_NONE:
         body = payload
+    elif compr == COMPR_ZLIB:
+        import zlib
+
+        body = zlib.compress(payload)  # SEAL's zlib mode: zlib container, default level
     else:
         body = zstd_structured_frame(payload) if structured else None
         if body is None:

@@ -218,6 +218,9 @@ def test_library_codec_rejects_malformed_inputs(lib, keys):
     # uncompressed SEAL blobs (compr_mode none) are accepted too
     ct = F.Ciphertext.from_bytes(good)
     assert parse(ct.to_bytes(compr=F.COMPR_NONE)) == 0
+    # ... and zlib ones (compr_mode 1)
+    assert parse(ct.to_bytes(compr=F.COMPR_ZLIB)) == 0
+    assert np.array_equal(words.reshape(2, 2, N), ct.polys())
     # key-level parms_id on a ciphertext is invalid
     ct.parts[0][1].parms_id = F.PARMS_ID_KEY
     assert parse(ct.to_bytes()) == 3

@@ -605,6 +605,11 @@ def test_uncompressed_operands_echo_their_compr_mode(keys):
     assert res == [(0, want_mul.to_bytes(compr=F.COMPR_NONE)), (0, want_mul.to_bytes(structured=True)),
                    (0, want_sub.to_bytes(compr=F.COMPR_NONE)), (0, want_mul.to_bytes(structured=True))]
     assert decrypt_value(keys, "u64", F.Ciphertext.from_bytes(res[0][1]).polys()) == 45
+    # zlib mode (compr_mode 1) is echoed too
+    zl_a = F.make_ciphertext("u64", a).to_bytes(compr=F.COMPR_ZLIB)
+    out = FHE.mul_cipheru64_cipheru64(pack.pack_binary_operation(keys.pub_bytes, zl_a, z_b))
+    got = F.Ciphertext.from_bytes(out)
+    assert np.array_equal(got.polys(), want_mul.polys()) and out == want_mul.to_bytes(compr=F.COMPR_ZLIB)
 
 
 def test_batches_and_single_calls_concurrently(keys):
