@@ -110,3 +110,17 @@ def test_rust_shim_lists_every_precompile():
     text = open(os.path.join(ROOT, "bindings/rust/src/lib.rs")).read()
     for n in _lib.PRECOMPILES:
         assert f"fn c_fhe_{n}(" in text and f"pub fn {n}(&self" in text
+
+
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/fhe_precompiles_b200.h must be consumable by a C compiler (the reference's consumers bind it through cgo / C
+    shims): examples/c_caller.c builds with -std=c11 -pedantic against the shared library and runs its GPU-free part."""
+    import subprocess
+
+    exe = tmp_path / "c_caller"
+    lib_dir = os.path.join(ROOT, "fhe_precompiles_b200")
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_caller.c"), "-L" + lib_dir, "-lfhe_precompiles_b200",
+                    "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "network public key: 410994 bytes" in r.stdout, r.stdout + r.stderr

@@ -583,6 +583,25 @@ def test_concurrent_calls_and_key_cache_eviction(keys, monkeypatch):
     assert not errors, errors
 
 
+def test_plain_c_caller(keys, tmp_path):
+    """examples/c_caller.c: the drop-in surface from C (single call + batch), on a packed input written by the format oracle."""
+    import subprocess
+
+    from fhe_precompiles_b200 import pack
+
+    a, b = encrypt_value(keys, "i64", 16, 1101), encrypt_value(keys, "i64", 4, 1102)
+    packed = pack.pack_binary_operation(keys.pub_bytes, F.make_ciphertext("i64", a).to_bytes(), F.make_ciphertext("i64", b).to_bytes())
+    (tmp_path / "in.bin").write_bytes(packed)
+    exe = tmp_path / "c_caller"
+    lib_dir = os.path.join(ROOT, "fhe_precompiles_b200")
+    subprocess.run(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_caller.c"), "-L" + lib_dir,
+                    "-lfhe_precompiles_b200", "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe), str(tmp_path / "in.bin")], capture_output=True, text=True, timeout=300)
+    want = len(F.make_ciphertext("i64", bfv.mul_relin(a, b, keys.rk)).to_bytes(structured=True))
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert f"result ciphertext: {want} bytes" in r.stdout and f"batch: 0 failed, outputs {want} and {want} bytes" in r.stdout, r.stdout
+
+
 def test_uncompressed_operands_echo_their_compr_mode(keys):
     """SEAL blobs with compr_mode none are legal inputs (Serialization::Load reads any mode); the result echoes the mode of the
     ciphertext operand. Such calls bypass the device codec (single call and inside a tile) and go through the host pass."""
