@@ -3,6 +3,11 @@
 // SEALContext::validate (coeff_div_plain_modulus, upper-half constants) and RNSTool::initialize.
 #include "context.h"
 
+#include <dlfcn.h>
+
+#include <cstdlib>
+#include <initializer_list>
+
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -114,33 +119,58 @@ const uint64_t kSha512K[80] = {
     0x113f9804bef90daeULL, 0x1b710b35131c471bULL, 0x28db77f523047d84ULL, 0x32caab7b40c72493ULL, 0x3c9ebe0a15c9bebcULL,
     0x431d67c49c100d4cULL, 0x4cc5d4becb3e42b6ULL, 0x597f299cfc657e2aULL, 0x5fcb6fab3ad6faecULL, 0x6c44198c4a475817ULL};
 inline uint64_t ror64(uint64_t x, int n) { return (x >> n) | (x << (64 - n)); }
+// FIPS 180-4 compression function; rounds unrolled by eight so that the working variables never move
+#define SHA512_RND(a, b, c, d, e, f, g, h, i)                                                                   \
+    {                                                                                                           \
+        const uint64_t t1 = h + (ror64(e, 14) ^ ror64(e, 18) ^ ror64(e, 41)) + (g ^ (e & (f ^ g))) + kSha512K[i] + w[i]; \
+        const uint64_t t2 = (ror64(a, 28) ^ ror64(a, 34) ^ ror64(a, 39)) + (((a | b) & c) | (a & b));           \
+        d += t1;                                                                                                \
+        h = t1 + t2;                                                                                            \
+    }
 void sha512_block(uint64_t h[8], const uint8_t *p) {
     uint64_t w[80];
     for (int i = 0; i < 16; i++) {
-        uint64_t v = 0;
-        for (int k = 0; k < 8; k++) v = (v << 8) | p[8 * i + k];
-        w[i] = v;
+        uint64_t v;
+        memcpy(&v, p + 8 * i, 8);
+        w[i] = __builtin_bswap64(v);
     }
     for (int i = 16; i < 80; i++) {
-        uint64_t s0 = ror64(w[i - 15], 1) ^ ror64(w[i - 15], 8) ^ (w[i - 15] >> 7);
-        uint64_t s1 = ror64(w[i - 2], 19) ^ ror64(w[i - 2], 61) ^ (w[i - 2] >> 6);
+        const uint64_t s0 = ror64(w[i - 15], 1) ^ ror64(w[i - 15], 8) ^ (w[i - 15] >> 7);
+        const uint64_t s1 = ror64(w[i - 2], 19) ^ ror64(w[i - 2], 61) ^ (w[i - 2] >> 6);
         w[i] = w[i - 16] + s0 + w[i - 7] + s1;
     }
     uint64_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
-    for (int i = 0; i < 80; i++) {
-        uint64_t S1 = ror64(e, 14) ^ ror64(e, 18) ^ ror64(e, 41);
-        uint64_t ch = (e & f) ^ (~e & g);
-        uint64_t t1 = hh + S1 + ch + kSha512K[i] + w[i];
-        uint64_t S0 = ror64(a, 28) ^ ror64(a, 34) ^ ror64(a, 39);
-        uint64_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint64_t t2 = S0 + mj;
-        hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+    for (int i = 0; i < 80; i += 8) {
+        SHA512_RND(a, b, c, d, e, f, g, hh, i)
+        SHA512_RND(hh, a, b, c, d, e, f, g, i + 1)
+        SHA512_RND(g, hh, a, b, c, d, e, f, i + 2)
+        SHA512_RND(f, g, hh, a, b, c, d, e, i + 3)
+        SHA512_RND(e, f, g, hh, a, b, c, d, i + 4)
+        SHA512_RND(d, e, f, g, hh, a, b, c, i + 5)
+        SHA512_RND(c, d, e, f, g, hh, a, b, i + 6)
+        SHA512_RND(b, c, d, e, f, g, hh, a, i + 7)
     }
     h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
 }
+#undef SHA512_RND
+
+// OpenSSL's SHA512 (assembly, AVX2) when libcrypto is on the machine: reencrypt hashes ~500 KB per call (fhe.rs:632-678)
+typedef unsigned char *(*Sha512Fn)(const unsigned char *, size_t, unsigned char *);
+Sha512Fn libcrypto_sha512() {
+    static Sha512Fn fn = [] {
+        if (getenv("FHE_B200_NO_LIBCRYPTO")) return (Sha512Fn) nullptr;
+        for (const char *name : {"libcrypto.so.3", "libcrypto.so.1.1", "libcrypto.so"}) {
+            if (void *h = dlopen(name, RTLD_NOW | RTLD_LOCAL)) {
+                if (void *sym = dlsym(h, "SHA512")) return (Sha512Fn)sym;
+            }
+        }
+        return (Sha512Fn) nullptr;
+    }();
+    return fn;
+}
 }  // namespace
 
-void sha512(const void *in, size_t inlen, uint8_t out[64]) {
+void sha512_portable(const void *in, size_t inlen, uint8_t out[64]) {
     uint64_t h[8] = {0x6a09e667f3bcc908ULL, 0xbb67ae8584caa73bULL, 0x3c6ef372fe94f82bULL, 0xa54ff53a5f1d36f1ULL,
                      0x510e527fade682d1ULL, 0x9b05688c2b3e6c1fULL, 0x1f83d9abfb41bd6bULL, 0x5be0cd19137e2179ULL};
     const uint8_t *p = (const uint8_t *)in;
@@ -160,6 +190,14 @@ void sha512(const void *in, size_t inlen, uint8_t out[64]) {
     if (tl == 256) sha512_block(h, tail + 128);
     for (int i = 0; i < 8; i++)
         for (int k = 0; k < 8; k++) out[8 * i + k] = (uint8_t)(h[i] >> (56 - 8 * k));
+}
+
+void sha512(const void *in, size_t inlen, uint8_t out[64]) {
+    if (Sha512Fn f = libcrypto_sha512()) {
+        f((const unsigned char *)in, inlen, out);
+        return;
+    }
+    sha512_portable(in, inlen, out);
 }
 
 // ---------------------------------------------------------------- number theory

@@ -41,7 +41,8 @@ u64 h_invmod(u64 a, u64 q);  // q prime
 bool is_prime_u64(u64 n);
 
 // SHA-512 (FIPS 180-4), used for the deterministic-encryption seeds of fhe.rs:600-611, 646-649
-void sha512(const void *in, size_t inlen, uint8_t out[64]);
+void sha512(const void *in, size_t inlen, uint8_t out[64]);           // libcrypto's when present, else the portable one
+void sha512_portable(const void *in, size_t inlen, uint8_t out[64]);  // own FIPS 180-4 implementation
 
 // BLAKE2b with variable digest length (RFC 7693), used for SEAL parms_id
 void blake2b(const void *in, size_t inlen, void *out, size_t outlen);
