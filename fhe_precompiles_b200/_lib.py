@@ -117,6 +117,8 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_write_ciphertext.restype = i32
     L.fhe_b200_zstd_inflate.argtypes = [i32, vp, vp, ctypes.c_size_t, vp, vp, vp]
     L.fhe_b200_zstd_inflate.restype = i32
+    L.fhe_b200_sha512.argtypes = [vp, ctypes.c_size_t, i32, vp]
+    L.fhe_b200_sha512.restype = None
     L.fhe_b200_set_zstd_writer.argtypes = [i32]
     L.fhe_b200_set_zstd_writer.restype = i32
     L.fhe_b200_parms_id.argtypes = [i32, vp]

@@ -464,6 +464,10 @@ int32_t fhe_b200_zstd_inflate(int32_t device, const uint8_t *const *frames, cons
         return -1;
     }
 }
+void fhe_b200_sha512(const uint8_t *bytes, size_t len, int32_t portable, uint8_t out[64]) {
+    if (portable) fheb::sha512_portable(bytes, len, out);
+    else fheb::sha512(bytes, len, out);
+}
 int32_t fhe_b200_set_zstd_writer(int32_t mode) {
     int32_t prev = fheb::zstd_writer();
     if (mode >= 0) fheb::set_zstd_writer(mode);

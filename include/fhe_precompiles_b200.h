@@ -187,6 +187,9 @@ int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, 
  * repeat-offset matches for the three zero bytes of every 36-bit residue; ~82 KB, memcpy speed), 0 = libzstd level 3 as
  * SEAL's default does (~88.5 KB, ~1 ms).  Both are RFC 8878 frames any SEAL build reads.  mode < 0 only queries.
  * Returns the previous mode.  Also settable with FHE_B200_ZSTD_WRITER=lib. */
+/* The SHA-512 behind the encrypt / reencrypt seed (fhe.rs:600-612): portable != 0 forces the built-in implementation,
+ * 0 uses libcrypto's when the machine has it.  Exposed so that tests can pin both against a known-good SHA-512. */
+void fhe_b200_sha512(const uint8_t *bytes, size_t len, int32_t portable, uint8_t out[64]);
 int32_t fhe_b200_set_zstd_writer(int32_t mode);
 /* Device-side zstd inflate of n ciphertext-payload frames (codec_kernels.cu, zstd_dec.h): what fhe_b200_batch uses for the
  * operands of a tile.  frames[i] / lens[i] are host buffers; `out` receives n payloads of 131,169 bytes; status[i] = 1 when

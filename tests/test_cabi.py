@@ -124,3 +124,21 @@ def test_header_is_plain_c_and_example_links(tmp_path):
                     "-Wl,-rpath," + lib_dir, "-o", str(exe)], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "network public key: 410994 bytes" in r.stdout, r.stdout + r.stderr
+
+
+def test_sha512_matches_hashlib():
+    """the seed of encrypt / reencrypt is SHA-512 of caller data (fhe.rs:600-612): both implementations behind it (built-in and
+    libcrypto's when present) against Python's, across the padding boundaries"""
+    import ctypes
+    import hashlib
+
+    from fhe_precompiles_b200 import _lib
+
+    L = _lib.lib()
+    rng = __import__("numpy").random.default_rng(9)
+    out = ctypes.create_string_buffer(64)
+    for n in [0, 1, 3, 55, 56, 111, 112, 113, 127, 128, 129, 239, 240, 255, 256, 1000, 4097, 500001]:
+        data = bytes(rng.integers(0, 256, n, dtype="uint8"))
+        for portable in (0, 1):
+            L.fhe_b200_sha512(data, n, portable, out)
+            assert out.raw == hashlib.sha512(data).digest(), (n, portable)
