@@ -381,7 +381,7 @@ void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint6
 }
 
 // kernel ids: 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt, 5 k_tensor_intt,
-//             6 k_digit_ntt, 7 k_ks_intt
+//             6 k_digit_ntt, 7 k_ks_intt, 8 k_ext_conv
 #define TIMED(id, call, what)                                        \
     do {                                                             \
         if (timed) {                                                 \
@@ -401,6 +401,7 @@ void Engine::enqueue_mul(const uint64_t *a, const uint64_t *b, const ScratchMap 
     if (fused_) {
         TIMED(0, launch_behz_tensor(a, b, m.tens, c, s), "behz_tensor");
     } else {
+        if (ext_split()) TIMED(8, launch_ext_conv(a, b, m.nttbuf, c, s), "ext_conv");
         TIMED(4, launch_ext_ntt(a, b, m.nttbuf, c, s), "ext_ntt");
         TIMED(5, launch_tensor_intt(m.nttbuf, m.tens, c, s), "tensor_intt");
     }

@@ -325,6 +325,67 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__
     }
 }
 
+// ---- default front end: base extension as its own elementwise kernel (FHE_B200_EXT_SPLIT=0 selects k_ext_ntt above)
+// k_ext_conv computes the three auxiliary-limb residues of every coefficient ONCE (the per-limb CTAs of k_ext_ntt each redo
+// the two q-limb products and the m~ correction) in a full-occupancy elementwise kernel and leaves them, coefficient domain,
+// in the scratch slots the transforms then work on in place.  The transform-only kernel needs 40 registers: 3 CTAs per SM
+// instead of 2.  431.9 k -> 444.7 k ops/s; the same split of the tensor product (elementwise + in-place inverse transforms)
+// was slower (the elementwise pass moves 1.1 MB per op through DRAM) and is not kept.
+template <int K>
+__device__ __forceinline__ u64 ext_one(u64 t0, u64 t1, u32 rm) {
+    using M = Mod<kExtLimb[2 + K]>;
+    u64 rr = rm;
+    if (rm >= 0x80000000u) rr += M::q - kMTilde;
+    u64 lo = 0, hi = 0;
+    mac128(lo, hi, t0, kc.extA[K]);
+    mac128(lo, hi, t1, kc.extB[K]);
+    mac128(lo, hi, rr, kc.extC[K]);
+    return reduce128<M>(hi, lo);
+}
+__global__ void __launch_bounds__(256) k_ext_conv(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf,
+                                                  size_t n_ops) {
+    const size_t total = n_ops * 4 * kN;  // (op, poly a0 a1 b0 b1, coefficient)
+    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (size_t)gridDim.x * 256) {
+        const size_t op = g / (4 * kN);
+        const int p = (int)((g / kN) & 3), i = (int)(g & (kN - 1));
+        const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
+        const u64 t0 = shoup<Mod<MQ0>>(ct[i], kc.ext_in[0].w, kc.ext_in[0].ws);
+        const u64 t1 = shoup<Mod<MQ1>>(ct[kN + i], kc.ext_in[1].w, kc.ext_in[1].ws);
+        const u32 ymt = (u32)t0 * kc.punct_q_mod_mtilde[0] + (u32)t1 * kc.punct_q_mod_mtilde[1];
+        const u32 rm = ymt * kc.neg_inv_q_mod_mtilde;
+        u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN + i;
+        dst[0] = ext_one<0>(t0, t1, rm);
+        dst[kN] = ext_one<1>(t0, t1, rm);
+        dst[2 * kN] = ext_one<2>(t0, t1, rm);
+    }
+}
+template <int EI>
+__device__ __forceinline__ void ntt_only_body(const u64 *__restrict__ src, u64 *__restrict__ dst, u64 *smem, int t) {
+    constexpr int MI = kExtLimb[EI];
+    using M = Mod<MI>;
+    u64 v[1][8];
+    load_natural(src, v[0], t);
+    ntt_forward<M, 1, !M::kSmall, false>(v, smem, kt.twf[MI], t);
+    store_chunk8(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 3) k_ext_ntt2(const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                           u64 *__restrict__ nttbuf) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int p = blockIdx.x / 5, e = blockIdx.x % 5;
+    u64 *dst = nttbuf + (op * 20 + blockIdx.x) * kN;
+    // q limbs come from the operand, auxiliary limbs are transformed in place (every load precedes the first CTA barrier)
+    const u64 *src = e < 2 ? (p < 2 ? a : b) + op * 4 * kN + (size_t)((p & 1) * 2 + e) * kN : dst;
+    const int t = threadIdx.x;
+    switch (e) {
+        case 0: ntt_only_body<0>(src, dst, smem, t); break;
+        case 1: ntt_only_body<1>(src, dst, smem, t); break;
+        case 2: ntt_only_body<2>(src, dst, smem, t); break;
+        case 3: ntt_only_body<3>(src, dst, smem, t); break;
+        default: ntt_only_body<4>(src, dst, smem, t); break;
+    }
+}
+
 template <int EI>
 __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int d, u64 *__restrict__ dst, u64 *smem, int t) {
     constexpr int MI = kExtLimb[EI];
@@ -333,25 +394,32 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
     const u64 *a0 = nb + (size_t)(0 * 5 + EI) * kN, *a1 = nb + (size_t)(1 * 5 + EI) * kN;
     const u64 *b0 = nb + (size_t)(2 * 5 + EI) * kN, *b1 = nb + (size_t)(3 * 5 + EI) * kN;
     u64 v[1][8];
+    // two coefficients at a time, so that the products do not keep 32 operands live (the kernel fits 40 registers: 3 CTAs/SM)
+    const ulonglong2 *pa0 = reinterpret_cast<const ulonglong2 *>(a0 + 8 * t), *pa1 = reinterpret_cast<const ulonglong2 *>(a1 + 8 * t);
+    const ulonglong2 *pb0 = reinterpret_cast<const ulonglong2 *>(b0 + 8 * t), *pb1 = reinterpret_cast<const ulonglong2 *>(b1 + 8 * t);
     if (d == 1) {
-        u64 x0[8], x1[8], y0[8], y1[8];
-        load_chunk8(a0, x0, t);
-        load_chunk8(b1, y1, t);
-        load_chunk8(a1, x1, t);
-        load_chunk8(b0, y0, t);
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
+        for (int r = 0; r < 4; r++) {
+            const ulonglong2 x0 = pa0[r], y1 = pb1[r], x1 = pa1[r], y0 = pb0[r];
             u64 lo = 0, hi = 0;
-            mac128(lo, hi, x0[r], y1[r]);
-            mac128(lo, hi, x1[r], y0[r]);
-            v[0][r] = reduce128<M>(hi, lo);
+            mac128(lo, hi, x0.x, y1.x);
+            mac128(lo, hi, x1.x, y0.x);
+            v[0][2 * r] = reduce128<M>(hi, lo);
+            lo = 0, hi = 0;
+            mac128(lo, hi, x0.y, y1.y);
+            mac128(lo, hi, x1.y, y0.y);
+            v[0][2 * r + 1] = reduce128<M>(hi, lo);
+            asm volatile("" ::: "memory");
         }
     } else {
-        u64 x[8], y[8];
-        load_chunk8(d == 0 ? a0 : a1, x, t);
-        load_chunk8(d == 0 ? b0 : b1, y, t);
+        const ulonglong2 *px = d == 0 ? pa0 : pa1, *py = d == 0 ? pb0 : pb1;
 #pragma unroll
-        for (int r = 0; r < 8; r++) v[0][r] = mulmod<M>(x[r], y[r]);
+        for (int r = 0; r < 4; r++) {
+            const ulonglong2 x = px[r], y = py[r];
+            v[0][2 * r] = mulmod<M>(x.x, y.x);
+            v[0][2 * r + 1] = mulmod<M>(x.y, y.y);
+            asm volatile("" ::: "memory");
+        }
     }
     // outputs stay in [0, 2q): k_floor_sk's Shoup / 128-bit reductions take any such value
     ntt_inverse<M, 1, false, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI], kc.ninv_t_w[MI]);
@@ -977,9 +1045,25 @@ cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *tens, size_t n_o
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
+static int ext_split_mode() {
+    static const int mode = [] {
+        const char *v = getenv("FHE_B200_EXT_SPLIT");
+        return (v && *v == '0') ? 0 : 1;
+    }();
+    return mode;
+}
+bool ext_split() { return ext_split_mode() != 0; }
+cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ext_conv<<<eltwise_grid(n_ops * 4 * kN, 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+// with ext_split(): the transforms only (launch_ext_conv must have filled the auxiliary limbs); otherwise extension + transforms
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
+    if (ext_split_mode()) k_ext_ntt2<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
+    else k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

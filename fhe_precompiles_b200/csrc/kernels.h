@@ -24,6 +24,8 @@ cudaError_t launch_mul_plain(const u64 *ct, const unsigned short *plain, u64 *ou
 cudaError_t launch_behz_extend_tap(const u64 *a, const u64 *b, u64 *ext, size_t n_ops, cudaStream_t s);
 cudaError_t launch_behz_tensor(const u64 *a, const u64 *b, u64 *tens, size_t n_ops, cudaStream_t s);
 // split (one polynomial per CTA) variants; scratch: nttbuf [n][4][5][N], dig [n][2][3][N]
+bool ext_split();  // default: the base extension is its own elementwise kernel (FHE_B200_EXT_SPLIT=0: inside the transform kernel)
+cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s);
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s);
 cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaStream_t s);
 cudaError_t launch_digit_ntt(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s);

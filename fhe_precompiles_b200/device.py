@@ -134,7 +134,8 @@ def mul_relin_host(a: torch.Tensor, b: torch.Tensor, rk: torch.Tensor, out: torc
     return out
 
 
-KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt")
+KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt",
+                "k_ext_conv", "reserved")
 
 
 def set_kernel_timing(on: bool) -> None:
@@ -143,10 +144,10 @@ def set_kernel_timing(on: bool) -> None:
 
 def kernel_timing_report(device: int = 0) -> dict:
     """{kernel: (total ms, launches)} accumulated by mul_relin() since the last report."""
-    ms = (ctypes.c_double * 8)()
-    cnt = (ctypes.c_uint64 * 8)()
+    ms = (ctypes.c_double * 10)()
+    cnt = (ctypes.c_uint64 * 10)()
     _check(_lib.lib().fhe_b200_kernel_timing_report(device, ms, cnt))
-    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(8) if cnt[i]}
+    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(10) if cnt[i]}
 
 
 def parse_public_key(data: bytes):
