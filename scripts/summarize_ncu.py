@@ -49,6 +49,7 @@ for r in rows[2:]:
         f"{f(r, 'smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} | "
         f"{f(r, 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'):.1f} | "
         f"{f(r, 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | "
+        f"{f(r, 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed'):.1f} | "
         f"{f(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} | {int(f(r, 'launch__registers_per_thread'))} | "
         + ", ".join(f"{n} {v:.2f}" for v, n in stalls)
         + " |"
@@ -57,10 +58,12 @@ os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
 with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as out:
     out.write(f"# ncu --set full, tag {tag}: one launch of each kernel, {ops} ct x ct ops per launch (B200, clocks not locked)\n\n")
     out.write("Source: `scripts/gpu_profile.sh` (bench.py under ncu after the same command exited 0 without it).\n"
-              "issue% = smsp__issue_active; ALU% = sm__inst_executed_pipe_alu (peak 0.5 warp-inst/clk/SMSP); FMA% = sm__pipe_fma_cycles_active;\n"
+              "issue% = smsp__issue_active; ALU% = sm__inst_executed_pipe_alu (peak 0.5 warp-inst/clk/SMSP); FMA% = sm__pipe_fma_cycles_active\n"
+              "(heavy + lite halves averaged); FMA-heavy% = sm__pipe_fmaheavy_cycles_active -- IMAD / IMAD.WIDE issue only to the heavy half, so\n"
+              "this is the integer-multiply pipe's utilisation and the limiter of every multiply kernel;\n"
               "stalls = warps stalled per issue (top 4).\n\n")
-    out.write("| kernel | grid | us/launch | us/op | DRAM MB/launch | DRAM KB/op | DRAM % | issue % | ALU % | FMA cyc % | warps % | regs | top stalls |\n")
-    out.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
+    out.write("| kernel | grid | us/launch | us/op | DRAM MB/launch | DRAM KB/op | DRAM % | issue % | ALU % | FMA cyc % | FMA-heavy % | warps % | regs | top stalls |\n")
+    out.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     out.write("\n".join(lines) + "\n")
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as out:
     json.dump({"tag": tag, "ops_per_launch": ops, "dram_bytes_per_op": traffic}, out, indent=1)
