@@ -355,6 +355,24 @@ void build(HostContext &H) {
         c.alK[3] = (msk - h_mulmod(c.flA[2], ib, msk)) % msk;
         c.alK[4] = (msk - h_mulmod(c.flB[2], ib, msk)) % msk;
     }
+    for (int k = 0; k < 3; k++) {
+        const u64 p = bsk[k];
+        c.extAs[k] = shoup_of(c.extA[k], p);
+        c.extBs[k] = shoup_of(c.extB[k], p);
+        c.extCs[k] = shoup_of(c.extC[k], p);
+        c.extNeg[k] = h_mulmod((p - kMTilde % p) % p, c.extC[k], p);
+    }
+    for (int j = 0; j < 2; j++) {
+        c.skVs[j] = shoup_of(c.skV[j], bsk[j]);
+        c.skAs[j] = shoup_of(c.skA[j], bsk[j]);
+        c.skBs[j] = shoup_of(c.skB[j], bsk[j]);
+        for (int l = 0; l < 2; l++) c.pBq[j][l] = mk_shoup(c.punct_B_mod_q[j][l], qs[l]);
+    }
+    for (int i = 0; i < 5; i++) c.alKs[i] = shoup_of(c.alK[i], msk);
+    for (int l = 0; l < 2; l++) {
+        c.Bq[l] = mk_shoup(c.B_mod_q[l], qs[l]);
+        c.nBq[l] = mk_shoup(c.neg_B_mod_q[l], qs[l]);
+    }
     // key switching
     c.half_P = P >> 1;
     for (int l = 0; l < 2; l++) {

@@ -39,6 +39,14 @@ struct DevConsts {
     u64 skV[2], skA[2], skB[2];
     u64 alK[5];
 
+    // Shoup quotients of the merged constants (k_ext_conv / k_floor_sk evaluate each output as one ShoupSum)
+    u64 extAs[3], extBs[3], extCs[3];
+    u64 extNeg[3];  // (p_k - m~) * extC[k] mod p_k: the correction term when the m~ residue is negative
+    u64 skVs[2], skAs[2], skBs[2];
+    u64 alKs[5];
+    Shoup pBq[2][2];      // punct_B_mod_q [j][l]
+    Shoup Bq[2], nBq[2];  // B_mod_q, neg_B_mod_q
+
     // ---- fastbconv_sk
     Shoup inv_punct_B[2];      // (B/b_j)^-1 mod b_j
     u64 punct_B_mod_q[2][2];   // [j][l]

@@ -331,16 +331,17 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__
 // in the scratch slots the transforms then work on in place.  The transform-only kernel needs 40 registers: 3 CTAs per SM
 // instead of 2.  431.9 k -> 444.7 k ops/s; the same split of the tensor product (elementwise + in-place inverse transforms)
 // was slower (the elementwise pass moves 1.1 MB per op through DRAM) and is not kept.
+// x'_k = t0*extA + t1*extB + r*extC (mod p_k), r the centred m~ residue, as one ShoupSum:
+// terms < p(1 + 2^-28) each, plus the constant for r < 0: below 4.01 p < 2^63, then one fold + conditional subtraction.
 template <int K>
 __device__ __forceinline__ u64 ext_one(u64 t0, u64 t1, u32 rm) {
     using M = Mod<kExtLimb[2 + K]>;
-    u64 rr = rm;
-    if (rm >= 0x80000000u) rr += M::q - kMTilde;
-    u64 lo = 0, hi = 0;
-    mac128(lo, hi, t0, kc.extA[K]);
-    mac128(lo, hi, t1, kc.extB[K]);
-    mac128(lo, hi, rr, kc.extC[K]);
-    return reduce128<M>(hi, lo);
+    ShoupSum<M> s;
+    s.lo = rm >= 0x80000000u ? kc.extNeg[K] : 0;
+    s.add(t0, kc.extA[K], kc.extAs[K]);
+    s.add(t1, kc.extB[K], kc.extBs[K]);
+    s.add32(rm, kc.extC[K], kc.extCs[K]);
+    return canon_k32<M>(s.value());
 }
 __global__ void __launch_bounds__(256) k_ext_conv(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf,
                                                   size_t n_ops) {
@@ -461,47 +462,50 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
         // fast_floor: q-part -> Bsk, f_k = (v_k - conv_k) * q^-1 mod p_k  (constants merged)
         u64 t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
         u64 t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
-        // fastbconv_sk inputs, constants merged (devconsts.h): tb_j = [f_j (B/b_j)^-1]_{b_j}
+        // fastbconv_sk inputs, constants merged (devconsts.h): tb_j = [f_j (B/b_j)^-1]_{b_j}.  Each output is one ShoupSum;
+        // tb_j and alpha are integers carried into another modulus, so they are made canonical.
         u64 tb0, tb1, alpha;
-        {
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, vb0, kc.skV[0]);
-            mac128(lo, hi, t0, kc.skA[0]);
-            mac128(lo, hi, t1, kc.skB[0]);
-            tb0 = reduce128<B0>(hi, lo);
+        {  // vb0 < 2 b0: terms < 1.25 p + 2 (1 + 2^-28) p
+            ShoupSum<B0> s;
+            s.add(vb0, kc.skV[0], kc.skVs[0]);
+            s.add(t0, kc.skA[0], kc.skAs[0]);
+            s.add(t1, kc.skB[0], kc.skBs[0]);
+            tb0 = canon_k32<B0>(s.value());
         }
         {
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, vb1, kc.skV[1]);
-            mac128(lo, hi, t0, kc.skA[1]);
-            mac128(lo, hi, t1, kc.skB[1]);
-            tb1 = reduce128<B1>(hi, lo);
+            ShoupSum<B1> s;
+            s.add(vb1, kc.skV[1], kc.skVs[1]);
+            s.add(t0, kc.skA[1], kc.skAs[1]);
+            s.add(t1, kc.skB[1], kc.skBs[1]);
+            tb1 = canon_k32<B1>(s.value());
         }
-        {  // alpha = [(B-part converted to m_sk  -  f_msk) * B^-1]_{m_sk}
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, tb0, kc.alK[0]);
-            mac128(lo, hi, tb1, kc.alK[1]);
-            mac128(lo, hi, vsk, kc.alK[2]);
-            mac128(lo, hi, t0, kc.alK[3]);
-            mac128(lo, hi, t1, kc.alK[4]);
-            alpha = reduce128<SK>(hi, lo);
+        {  // alpha = [(B-part converted to m_sk  -  f_msk) * B^-1]_{m_sk}; five terms < 1.25 p each: < 2^64
+            ShoupSum<SK> s;
+            s.add(tb0, kc.alK[0], kc.alKs[0]);
+            s.add(tb1, kc.alK[1], kc.alKs[1]);
+            s.add(vsk, kc.alK[2], kc.alKs[2]);
+            s.add(t0, kc.alK[3], kc.alKs[3]);
+            s.add(t1, kc.alK[4], kc.alKs[4]);
+            alpha = canon_k32<SK>(s.value());
         }
         bool neg = alpha > (SK::q >> 1);
         u64 am = neg ? SK::q - alpha : alpha;
         u64 *out = c3 + opp * 2 * kN + i;
-        {
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, tb0, kc.punct_B_mod_q[0][0]);
-            mac128(lo, hi, tb1, kc.punct_B_mod_q[1][0]);
-            mac128(lo, hi, am, neg ? kc.B_mod_q[0] : kc.neg_B_mod_q[0]);
-            out[0] = reduce128<Q0>(hi, lo);
+        {  // 36-bit targets: approximate quotients, three terms < 3.2 q each (< 2^40)
+            const Shoup kb = neg ? kc.Bq[0] : kc.nBq[0];
+            ShoupSum<Q0> s;
+            s.add_a1(tb0, kc.pBq[0][0].w, kc.pBq[0][0].ws);
+            s.add_a1(tb1, kc.pBq[1][0].w, kc.pBq[1][0].ws);
+            s.add_a1(am, kb.w, kb.ws);
+            out[0] = canon_k32<Q0>(s.value());
         }
         {
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, tb0, kc.punct_B_mod_q[0][1]);
-            mac128(lo, hi, tb1, kc.punct_B_mod_q[1][1]);
-            mac128(lo, hi, am, neg ? kc.B_mod_q[1] : kc.neg_B_mod_q[1]);
-            out[kN] = reduce128<Q1>(hi, lo);
+            const Shoup kb = neg ? kc.Bq[1] : kc.nBq[1];
+            ShoupSum<Q1> s;
+            s.add_a1(tb0, kc.pBq[0][1].w, kc.pBq[0][1].ws);
+            s.add_a1(tb1, kc.pBq[1][1].w, kc.pBq[1][1].ws);
+            s.add_a1(am, kb.w, kb.ws);
+            out[kN] = canon_k32<Q1>(s.value());
         }
     }
 }

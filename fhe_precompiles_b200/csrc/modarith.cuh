@@ -136,12 +136,83 @@ __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws) {
     return csub<M>(shoup_lazy<M>(x, w, ws), M::q);
 }
 
+// sum_k x_k * w_k mod q for precomputed Shoup pairs (w_k, ws_k): the products' low 64 bits and the quotient estimates
+// H_k are accumulated separately and -(sum H_k) * q is applied once, so a term costs its partial products only and the
+// whole sum one reduction.  Everything is mod 2^64 (wrap-around in either accumulator is harmless) and the result is
+// exact as long as the true value sum_k (x_k w_k - H_k q) stays below 2^64:
+//   add      exact quotient, any 64-bit x : term in [0, q + x q / 2^64)                 FMA pipe 5 wide + 2 low
+//   add32    the same for x < 2^32                                                       3 wide + 1 low
+//   add_a1   drops the x_lo*ws_lo partial product (H low by <= 2): adds another 2q       4 wide + 2 low
+// value(): one wide + one low multiply.  (The compiler's 128-bit mad/madc + fold sequence for the same sum issued twice
+// the multiplier cycles: duplicated partial products for the carries and multiplications by a zero high word.)
+template <class M>
+struct ShoupSum {
+    u64 lo = 0, hs = 0;
+    __device__ __forceinline__ void low_product(u32 xl, u32 xh, u64 w) {
+        u32 wl, wh, al, ah;
+        unpack64(w, wl, wh);
+        unpack64(mad_wide(xl, wl, lo), al, ah);
+        ah = mad_lo(xl, wh, ah);
+        ah = mad_lo(xh, wl, ah);
+        lo = pack64(al, ah);
+    }
+    __device__ __forceinline__ void add(u64 x, u64 w, u64 ws) {
+        u32 xl, xh, sl, sh, tl, th, ul, uh, vl, vh;
+        unpack64(x, xl, xh);
+        unpack64(ws, sl, sh);
+        unpack64(mul_wide(xl, sl), tl, th);
+        unpack64(mad_wide(xh, sl, pack64(th, 0)), ul, uh);
+        unpack64(mad_wide(xl, sh, pack64(ul, 0)), vl, vh);
+        hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh;
+        low_product(xl, xh, w);
+    }
+    __device__ __forceinline__ void add_a1(u64 x, u64 w, u64 ws) {
+        u32 xl, xh, sl, sh, ul, uh, vl, vh;
+        unpack64(x, xl, xh);
+        unpack64(ws, sl, sh);
+        unpack64(mul_wide(xh, sl), ul, uh);
+        unpack64(mul_wide(xl, sh), vl, vh);
+        hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh;
+        low_product(xl, xh, w);
+    }
+    __device__ __forceinline__ void add32(u32 x, u64 w, u64 ws) {
+        u32 sl, sh, tl, th, vl, vh, wl, wh, al, ah;
+        unpack64(ws, sl, sh);
+        unpack64(mul_wide(x, sl), tl, th);
+        unpack64(mad_wide(x, sh, pack64(th, 0)), vl, vh);
+        hs += vh;
+        unpack64(w, wl, wh);
+        unpack64(mad_wide(x, wl, lo), al, ah);
+        lo = pack64(al, mad_lo(x, wh, ah));
+    }
+    // sum - (sum H) q  =  sum + (sum H) c - ((sum H) << B)   (mod 2^64)
+    __device__ __forceinline__ u64 value() const {
+        constexpr u32 c = (u32)M::kC;
+        u32 hl, hh, al, ah;
+        unpack64(hs, hl, hh);
+        unpack64(mad_wide(hl, c, lo), al, ah);
+        ah = mad_lo(hh, c, ah);
+        ah -= hl << (M::kBits - 32);
+        return pack64(al, ah);
+    }
+};
+
 // pseudo-Mersenne fold: x -> (x mod 2^b) + floor(x / 2^b) * c, congruent to x mod q.
 // Result < 2^b + 2^(64-b) * c; one more conditional subtraction is canonical whenever that is < 2q.
 template <class M>
 __device__ __forceinline__ u64 fold(u64 x) {
     const u64 k = x >> M::kBits;
     return (x & M::kMask) + k * M::kC;
+}
+// the same when floor(x / 2^b) * c fits 32 bits (one low multiply instead of a 64-bit one)
+template <class M>
+__device__ __forceinline__ u64 fold_k32(u64 x) {
+    const u32 k = (u32)(x >> M::kBits);
+    return (x & M::kMask) + (u64)(k * (u32)M::kC);
+}
+template <class M>
+__device__ __forceinline__ u64 canon_k32(u64 x) {
+    return csub<M>(fold_k32<M>(x), M::q);
 }
 // canonical residue of x when fold(x) < 2q: small primes x < 2^55, 61-bit primes any x
 template <class M>
