@@ -402,14 +402,14 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const ulonglong2 x0 = pa0[r], y1 = pb1[r], x1 = pa1[r], y0 = pb0[r];
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, x0.x, y1.x);
-            mac128(lo, hi, x1.x, y0.x);
-            v[0][2 * r] = reduce128<M>(hi, lo);
-            lo = 0, hi = 0;
-            mac128(lo, hi, x0.y, y1.y);
-            mac128(lo, hi, x1.y, y0.y);
-            v[0][2 * r + 1] = reduce128<M>(hi, lo);
+            {
+                const u64 xs[2] = {x0.x, x1.x}, ys[2] = {y1.x, y0.x};
+                v[0][2 * r] = mulsum<M, 2>(xs, ys);
+            }
+            {
+                const u64 xs[2] = {x0.y, x1.y}, ys[2] = {y1.y, y0.y};
+                v[0][2 * r + 1] = mulsum<M, 2>(xs, ys);
+            }
             asm volatile("" ::: "memory");
         }
     } else {
@@ -417,8 +417,14 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const ulonglong2 x = px[r], y = py[r];
-            v[0][2 * r] = mulmod<M>(x.x, y.x);
-            v[0][2 * r + 1] = mulmod<M>(x.y, y.y);
+            {
+                const u64 xs[1] = {x.x}, ys[1] = {y.x};
+                v[0][2 * r] = mulsum<M, 1>(xs, ys);
+            }
+            {
+                const u64 xs[1] = {x.y}, ys[1] = {y.y};
+                v[0][2 * r + 1] = mulsum<M, 1>(xs, ys);
+            }
             asm volatile("" ::: "memory");
         }
     }
@@ -594,10 +600,8 @@ __device__ __forceinline__ void ks_intt_body(const u64 *__restrict__ dg, const u
     u64 v[1][8];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        u64 lo = 0, hi = 0;
-        mac128(lo, hi, d0[r], k0[r]);
-        mac128(lo, hi, d1[r], k1[r]);
-        v[0][r] = reduce128<M>(hi, lo);
+        const u64 xs[2] = {d0[r], d1[r]}, ys[2] = {k0[r], k1[r]};  // digits lazy (< 2^43), key canonical
+        v[0][r] = mulsum<M, 2>(xs, ys);
     }
     ntt_inverse<M, 1, true, false>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
     store_natural(dst, v[0], t);

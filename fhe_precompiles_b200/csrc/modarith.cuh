@@ -220,6 +220,89 @@ __device__ __forceinline__ u64 canon(u64 x) {
     return csub<M>(fold<M>(x), M::q);
 }
 
+// sum of NP (1 or 2) products x_i * y_i of two VARIABLES (no precomputed quotient), on explicit 32-bit partial products.
+// The compiler's lowering of mad.lo.cc.u64 / madc.hi.u64 + reduce128 recomputes partial products for the carries and
+// multiplies by zero high words; these issue 6-9 wide multiplies per call instead of 10-16.
+//
+// 61-bit primes, operands < 2^61, result in [0, 2q).  V = p00 + mid 2^32 + p11 2^64 (mid, p11 accumulate over the
+// products in mad.wide chains, no carries).  Quotient Q = qe + floor(qe c / 2^61) with qe ~ floor(V / 2^61) from the
+// column tops (low by < 3 + NP), so V - Q q < (4 + NP) q needs only the low 64 bits of V.
+template <class M, int NP>
+__device__ __forceinline__ u64 mulsum_large(const u64 (&x)[NP], const u64 (&y)[NP]) {
+    constexpr u32 c = (u32)M::kC;
+    u64 p00[NP], mid = 0, p11 = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        u32 xl, xh, yl, yh;
+        unpack64(x[i], xl, xh);
+        unpack64(y[i], yl, yh);
+        p00[i] = mul_wide(xl, yl);
+        mid = i == 0 ? mad_wide(xl, yh, mul_wide(xh, yl)) : mad_wide(xl, yh, mad_wide(xh, yl, mid));
+        p11 = i == 0 ? mul_wide(xh, yh) : mad_wide(xh, yh, p11);
+    }
+    u64 qe = (p11 << 3) + (mid >> 29) + (p00[0] >> 61);
+    u64 lo = p00[0];
+    if (NP == 2) {
+        qe += p00[NP - 1] >> 61;
+        lo += p00[NP - 1];  // mod 2^64
+    }
+    const u64 Q = qe + (mul_wide((u32)(qe >> 32), c) >> 29);
+    u32 ll, lh, Ql, Qh, al, ah;
+    unpack64(lo, ll, lh);
+    lh += (u32)mid;
+    unpack64(Q, Ql, Qh);
+    unpack64(mad_wide(Ql, c, pack64(ll, lh)), al, ah);
+    ah = mad_lo(Qh, c, ah);
+    ah -= Ql << 29;
+    return fold_k32<M>(pack64(al, ah));
+}
+// 36/37-bit primes q = 2^B - c, operands < 2^44, result in [0, 2q).  V = p00 + M' 2^32 with M' = mid + p11 2^32 < 2^58;
+// M' 2^32 = a_lo 2^32 + a_hi 2^B + b 2^2B  ==  a_lo 2^32 + a_hi c + b c^2, the p00 tops join a_hi, then two folds.
+template <class M, int NP>
+__device__ __forceinline__ u64 mulsum_small(const u64 (&x)[NP], const u64 (&y)[NP]) {
+    constexpr int B = M::kBits;
+    constexpr u32 c = (u32)M::kC;
+    constexpr u64 c2 = M::kC * M::kC;
+    constexpr int sh = 2 * B - 32;
+    u64 p00[NP];
+    u32 xl[NP], xh[NP], yl[NP], yh[NP], p11 = 0;
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        unpack64(x[i], xl[i], xh[i]);
+        unpack64(y[i], yl[i], yh[i]);
+        p00[i] = mul_wide(xl[i], yl[i]);
+        p11 = mad_lo(xh[i], yh[i], p11);
+    }
+    u64 mp = pack64(0, p11);
+#pragma unroll
+    for (int i = 0; i < NP; i++) mp = mad_wide(xl[i], yh[i], mad_wide(xh[i], yl[i], mp));
+    const u32 b = (u32)(mp >> sh);
+    const u64 a = mp & ((1ull << sh) - 1);
+    u64 T = (a >> (B - 32)) + (p00[0] >> B);
+    u64 S = p00[0] & M::kMask;
+    if (NP == 2) {
+        T += p00[NP - 1] >> B;
+        S += p00[NP - 1] & M::kMask;
+    }
+    u32 Tl, Th, sl, shi;
+    unpack64(T, Tl, Th);
+    unpack64(S, sl, shi);
+    shi += (u32)a & ((1u << (B - 32)) - 1);
+    unpack64(mad_wide(b, (u32)c2, mad_wide(Tl, c, pack64(sl, shi))), sl, shi);
+    shi = mad_lo(Th, c, shi);
+    shi = mad_lo(b, (u32)(c2 >> 32), shi);
+    S = pack64(sl, shi);
+    S = mad_wide((u32)(S >> B), c, S & M::kMask);
+    return fold_k32<M>(S);
+}
+template <class M, int NP>
+__device__ __forceinline__ u64 mulsum(const u64 (&x)[NP], const u64 (&y)[NP]) {
+    if constexpr (M::kSmall)
+        return mulsum_small<M, NP>(x, y);
+    else
+        return mulsum_large<M, NP>(x, y);
+}
+
 // x mod q for any 64-bit x (SEAL barrett_reduce_64)
 template <class M>
 __device__ __forceinline__ u64 reduce64(u64 x) {
