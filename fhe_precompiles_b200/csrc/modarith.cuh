@@ -109,11 +109,14 @@ __device__ __forceinline__ u64 shoup_acc(u64 acc, u64 x, u64 w, u64 ws) {
         unpack64(mul_wide(xl, sh), vl, vh);
         H = mad_wide(xh, sh, pack64(uh, 0)) + vh;
     } else {
+        // the middle column as one three-input add with two carries (ALU pipe): a multiply-add whose addend has a zero
+        // high word is split by ptxas into IMAD.WIDE + IADD3 + IMAD.X, and the IMAD.X occupies the multiplier pipe
         u32 tl, th, ul, uh, vl, vh;
         unpack64(mul_wide(xl, sl), tl, th);
-        unpack64(mad_wide(xh, sl, pack64(th, 0)), ul, uh);
-        unpack64(mad_wide(xl, sh, pack64(ul, 0)), vl, vh);
-        H = mad_wide(xh, sh, pack64(uh, 0)) + vh;
+        unpack64(mul_wide(xh, sl), ul, uh);
+        unpack64(mul_wide(xl, sh), vl, vh);
+        const u64 mc = (u64)ul + (u64)vl + (u64)th;
+        H = mul_wide(xh, sh) + (u64)uh + (u64)vh + (mc >> 32);
     }
     u32 hl, hh, al, ah;
     unpack64(H, hl, hh);
@@ -161,9 +164,10 @@ struct ShoupSum {
         unpack64(x, xl, xh);
         unpack64(ws, sl, sh);
         unpack64(mul_wide(xl, sl), tl, th);
-        unpack64(mad_wide(xh, sl, pack64(th, 0)), ul, uh);
-        unpack64(mad_wide(xl, sh, pack64(ul, 0)), vl, vh);
-        hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh;
+        unpack64(mul_wide(xh, sl), ul, uh);
+        unpack64(mul_wide(xl, sh), vl, vh);
+        const u64 mc = (u64)ul + (u64)vl + (u64)th;  // middle column: one three-input add, two carries (see shoup_acc)
+        hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh + (mc >> 32);
         low_product(xl, xh, w);
     }
     __device__ __forceinline__ void add_a1(u64 x, u64 w, u64 ws) {

@@ -54,7 +54,7 @@ __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
         X = Xo;
     } else {
         u64 x = X;
-        if (G > 0 && (G % 3) == 0) x = fold<M>(x);  // < 8q  ->  < 2^61 + 7c < 2q
+        if (G > 0 && (G % 3) == 0) x = fold_k32<M>(x);  // < 8q  ->  < 2^61 + 7c < 2q
         const u64 Xo = shoup_acc<M, 0>(x, Y, w, ws);
         Y = (x + x + M::two_q) - Xo;  // x + 2q - T
         X = Xo;
@@ -77,7 +77,7 @@ __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
         Y = shoup_lazy<M>(D, w, ws);
     } else {
         const u64 D = X + (M::four_q - Y);
-        X = fold<M>(X + Y);
+        X = fold_k32<M>(X + Y);
         Y = shoup_lazy<M>(D, w, ws);
     }
 }
@@ -215,7 +215,7 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll
-            for (int r = 0; r < 8; r++) v[p][r] = canon<M>(v[p][r]);  // small: < 2^43; large: < 8q
+            for (int r = 0; r < 8; r++) v[p][r] = canon_k32<M>(v[p][r]);  // small: < 2^43; large: < 8q
     }
     if (kTrailSync) __syncthreads();  // smem may be reused by the caller
 }
