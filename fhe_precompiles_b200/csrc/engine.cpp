@@ -381,7 +381,7 @@ void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint6
 }
 
 // kernel ids: 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt, 5 k_tensor_intt,
-//             6 k_digit_ntt, 7 k_ks_intt, 8 k_ext_conv
+//             6 k_digit_ntt, 7 k_ks_intt, 8 k_ext_conv, 9 k_ks_finish
 #define TIMED(id, call, what)                                        \
     do {                                                             \
         if (timed) {                                                 \
@@ -414,6 +414,10 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
         TIMED(2, launch_relin_ks(c3, rk, m.ks, c, s), "relin_ks");
     } else {
         TIMED(6, launch_digit_ntt(c3, m.dig, c, s), "digit_ntt");
+        if (ks_finish_fused()) {
+            TIMED(9, launch_ks_finish(m.dig, rk, c3, out, c, s), "ks_finish");
+            return;
+        }
         TIMED(7, launch_ks_intt(m.dig, rk, m.ks, c, s), "ks_intt");
     }
     TIMED(3, launch_relin_finish(c3, m.ks, out, c, s), "relin_finish");

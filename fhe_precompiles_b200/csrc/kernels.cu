@@ -621,6 +621,65 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks_intt(const u64 *__restrict__
     }
 }
 
+// ---- default key-switch tail: k_ks_intt and k_relin_finish in one kernel, grid (2 = output polynomial k, ops).
+// The CTA runs the three moduli in the order P, q0, q1: a thread owns the same eight coefficients (r*512 + t) after every
+// inverse transform, so the P-limb values needed by the rounded division stay in its registers and the key-switch result
+// never goes through the [op][2][3][N] scratch (FHE_B200_KS_FINISH=0 selects the two separate kernels).
+template <int MI>
+__device__ __forceinline__ void ks_mac_intt(const u64 *__restrict__ dg, const u64 *__restrict__ rk, int k, u64 (&v)[1][8], u64 *smem,
+                                            int t) {
+    using M = Mod<MI>;
+    u64 d0[8], d1[8], k0[8], k1[8];
+    load_chunk8(dg + (size_t)(0 * 3 + MI) * kN, d0, t);
+    load_chunk8(dg + (size_t)(1 * 3 + MI) * kN, d1, t);
+    load_chunk8_ldg(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN, k0, t);
+    load_chunk8_ldg(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN, k1, t);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const u64 xs[2] = {d0[r], d1[r]}, ys[2] = {k0[r], k1[r]};
+        v[0][r] = mulsum<M, 2>(xs, ys);
+    }
+    ntt_inverse<M, 1, true, true>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
+}
+template <int L>
+__device__ __forceinline__ void ks_finish_limb(const u64 (&v)[8], const u64 *last, const u64 *__restrict__ pc, u64 *__restrict__ po,
+                                               int t) {
+    using Q = Mod<L>;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        // last < P < 4 q_l: one fold; d canonical, so the 16-bit quotient estimate applies: c3 + d P^-1 < 6 q_l, one more fold
+        const u64 tl = submod<Q>(canon_k32<Q>(last[r * kThreads + t]), kc.half_P_mod_q[L]);
+        const u64 d = submod<Q>(v[r], tl);
+        po[r * kThreads + t] = canon_k32<Q>(shoup_acc<Q, 2>(pc[r * kThreads + t], d, kc.inv_P_mod_q[L].w, kc.inv_P_mod_q[L].ws));
+    }
+}
+__global__ void __launch_bounds__(kThreads, 2) k_ks_finish(const u64 *__restrict__ dig, const u64 *__restrict__ rk,
+                                                            const u64 *__restrict__ c3, u64 *__restrict__ out) {
+    extern __shared__ __align__(16) u64 smem[];
+    u64 *last = smem + kN;  // second 32 KiB: the P-limb values, each thread's own eight slots
+    const size_t op = blockIdx.y;
+    const int k = blockIdx.x, t = threadIdx.x;
+    const u64 *dg = dig + op * 6 * kN;
+    const u64 *pc = c3 + (op * 3 + k) * 2 * kN;
+    u64 *po = out + (op * 2 + k) * 2 * kN;
+    {
+        u64 v[1][8];
+        ks_mac_intt<MP>(dg, rk, k, v, smem, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) last[r * kThreads + t] = csub<Mod<MP>>(v[0][r] + kc.half_P, Mod<MP>::q);
+    }
+    {
+        u64 v[1][8];
+        ks_mac_intt<MQ0>(dg, rk, k, v, smem, t);
+        ks_finish_limb<MQ0>(v[0], last, pc, po, t);
+    }
+    {
+        u64 v[1][8];
+        ks_mac_intt<MQ1>(dg, rk, k, v, smem, t);
+        ks_finish_limb<MQ1>(v[0], last, pc + kN, po + kN, t);
+    }
+}
+
 // =====================================================================================
 // K9b: rounded division by P and accumulation into (c0, c1)   (tail of switch_key_inplace)
 //   out[op][k][l][i] = c3[op][k][l][i] + (ks[k][l][i] - ((ks[k][P][i] + P/2 mod P) mod q_l - (P/2 mod q_l))) * P^-1 mod q_l
@@ -641,16 +700,14 @@ __global__ void __launch_bounds__(256) k_relin_finish(const u64 *__restrict__ c3
         u64 *po = out + (op * 2 + k) * 2 * kN + i;
         u64 last = csub<PP>(pk[2 * kN] + kc.half_P, PP::q);
         {
-            u64 tl = submod<Q0>(reduce64<Q0>(last), kc.half_P_mod_q[0]);
+            u64 tl = submod<Q0>(canon_k32<Q0>(last), kc.half_P_mod_q[0]);  // last < P < 4 q_l
             u64 d = submod<Q0>(pk[0], tl);
-            u64 v = shoup<Q0>(d, kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws);
-            po[0] = addmod<Q0>(v, pc[0]);
+            po[0] = canon_k32<Q0>(shoup_acc<Q0, 2>(pc[0], d, kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws));  // < 6 q_l
         }
         {
-            u64 tl = submod<Q1>(reduce64<Q1>(last), kc.half_P_mod_q[1]);
+            u64 tl = submod<Q1>(canon_k32<Q1>(last), kc.half_P_mod_q[1]);  // last < P < 4 q_l
             u64 d = submod<Q1>(pk[kN], tl);
-            u64 v = shoup<Q1>(d, kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws);
-            po[kN] = addmod<Q1>(v, pc[kN]);
+            po[kN] = canon_k32<Q1>(shoup_acc<Q1, 2>(pc[kN], d, kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws));  // < 6 q_l
         }
     }
 }
@@ -822,13 +879,13 @@ __global__ void __launch_bounds__(256) k_encrypt_finish(const u64 *__restrict__ 
         u64 last = csub<PP>(pe[2 * kN] + kc.half_P, PP::q);
         u64 m = (j == 0) ? plain[op * kN + i] : 0;
         {
-            u64 tl = submod<Q0>(reduce64<Q0>(last), kc.half_P_mod_q[0]);
+            u64 tl = submod<Q0>(canon_k32<Q0>(last), kc.half_P_mod_q[0]);
             u64 v = shoup<Q0>(submod<Q0>(pe[0], tl), kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws);
             if (j == 0) v = addmod<Q0>(v, plain_scaled<Q0>(m, 0));
             po[0] = v;
         }
         {
-            u64 tl = submod<Q1>(reduce64<Q1>(last), kc.half_P_mod_q[1]);
+            u64 tl = submod<Q1>(canon_k32<Q1>(last), kc.half_P_mod_q[1]);
             u64 v = shoup<Q1>(submod<Q1>(pe[kN], tl), kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws);
             if (j == 0) v = addmod<Q1>(v, plain_scaled<Q1>(m, 1));
             po[kN] = v;
@@ -991,6 +1048,8 @@ cudaError_t kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_relin_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ks_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -1090,6 +1149,20 @@ cudaError_t launch_digit_ntt(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t
 cudaError_t launch_ks_intt(const u64 *dig, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
     k_ks_intt<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(dig, rk, ks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+static int ks_finish_mode() {
+    static const int mode = [] {
+        const char *v = getenv("FHE_B200_KS_FINISH");
+        return (v && *v == '0') ? 0 : 1;
+    }();
+    return mode;
+}
+bool ks_finish_fused() { return ks_finish_mode() != 0; }
+cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ks_finish<<<dim3(2, (unsigned)n_ops), kThreads, kSmem2, s>>>(dig, rk, c3, out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

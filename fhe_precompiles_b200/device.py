@@ -135,7 +135,7 @@ def mul_relin_host(a: torch.Tensor, b: torch.Tensor, rk: torch.Tensor, out: torc
 
 
 KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt",
-                "k_ext_conv", "reserved")
+                "k_ext_conv", "k_ks_finish")
 
 
 def set_kernel_timing(on: bool) -> None:
