@@ -436,6 +436,13 @@ def main() -> None:
             traffic = per_op * ops_per_launch
     except Exception:
         traffic = None
+    ncu_heavy = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            prof = json.load(f)
+        ncu_heavy = {"tag": prof.get("tag"), "pct": prof.get("fmaheavy_pct")}
+    except Exception:
+        pass
     roofline = {
         "bound": "hbm",
         "kernel": dom,
@@ -470,6 +477,9 @@ def main() -> None:
             "butterfly_peak_G_per_s": {"36-37 bit primes": bf_small, "61 bit primes": bf_big},
             "ntt_only_floor_us_per_op": ntt_floor_us,
             "frac_of_butterfly_ceiling": ntt_floor_us * 1e-6 * ops_s,
+            # sm__pipe_fmaheavy_cycles_active of the committed ncu capture (profiles/<tag>_kernels.md): IMAD / IMAD.WIDE issue
+            # only to the heavy half of the FMA pipe, so this is the measured utilisation of the limiter, per kernel
+            "ncu_fmaheavy_pct": ncu_heavy,
         }
     except Exception as e:  # pragma: no cover
         int_pipe = {"error": str(e)}

@@ -33,7 +33,7 @@ def to_bytes(r, name):
 
 
 stall_names = [h for h in hdr if "issue_stalled" in h and h.endswith(".ratio")]
-seen, lines, traffic = {}, [], {}
+seen, lines, traffic, heavy = {}, [], {}, {}
 for r in rows[2:]:
     k = r[idx["Kernel Name"]].split("(")[0].replace("void ", "").replace("fheb::", "")
     if k in seen:
@@ -42,6 +42,7 @@ for r in rows[2:]:
     dur_us = f(r, "gpu__time_duration.sum") * {"us": 1, "ms": 1e3, "ns": 1e-3}.get(units[idx["gpu__time_duration.sum"]], 1)
     dram = to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")
     traffic[k] = dram / ops
+    heavy[k] = f(r, 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed')
     stalls = sorted(((f(r, n), n.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", "")) for n in stall_names), reverse=True)[:4]
     lines.append(
         f"| {k} | {r[idx['Grid Size']]} | {dur_us:.1f} | {dur_us / ops:.3f} | {dram / 1e6:.1f} | {dram / ops / 1e3:.0f} | "
@@ -66,7 +67,7 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as out:
     out.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     out.write("\n".join(lines) + "\n")
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as out:
-    json.dump({"tag": tag, "ops_per_launch": ops, "dram_bytes_per_op": traffic}, out, indent=1)
+    json.dump({"tag": tag, "ops_per_launch": ops, "dram_bytes_per_op": traffic, "fmaheavy_pct": heavy}, out, indent=1)
 # launch list
 src = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
 if os.path.exists(src):
