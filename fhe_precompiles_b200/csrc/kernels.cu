@@ -395,7 +395,7 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
     const u64 *a0 = nb + (size_t)(0 * 5 + EI) * kN, *a1 = nb + (size_t)(1 * 5 + EI) * kN;
     const u64 *b0 = nb + (size_t)(2 * 5 + EI) * kN, *b1 = nb + (size_t)(3 * 5 + EI) * kN;
     u64 v[1][8];
-    // two coefficients at a time, so that the products do not keep 32 operands live (the kernel fits 40 registers: 3 CTAs/SM)
+    // two coefficients at a time, so that the products do not keep 32 operands live
     const ulonglong2 *pa0 = reinterpret_cast<const ulonglong2 *>(a0 + 8 * t), *pa1 = reinterpret_cast<const ulonglong2 *>(a1 + 8 * t);
     const ulonglong2 *pb0 = reinterpret_cast<const ulonglong2 *>(b0 + 8 * t), *pb1 = reinterpret_cast<const ulonglong2 *>(b1 + 8 * t);
     if (d == 1) {
@@ -410,7 +410,6 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
                 const u64 xs[2] = {x0.y, x1.y}, ys[2] = {y1.y, y0.y};
                 v[0][2 * r + 1] = mulsum<M, 2>(xs, ys);
             }
-            asm volatile("" ::: "memory");
         }
     } else {
         const ulonglong2 *px = d == 0 ? pa0 : pa1, *py = d == 0 ? pb0 : pb1;
@@ -425,7 +424,6 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
                 const u64 xs[1] = {x.y}, ys[1] = {y.y};
                 v[0][2 * r + 1] = mulsum<M, 1>(xs, ys);
             }
-            asm volatile("" ::: "memory");
         }
     }
     // outputs stay in [0, 2q): k_floor_sk's Shoup / 128-bit reductions take any such value
@@ -629,15 +627,21 @@ template <int MI>
 __device__ __forceinline__ void ks_mac_intt(const u64 *__restrict__ dg, const u64 *__restrict__ rk, int k, u64 (&v)[1][8], u64 *smem,
                                             int t) {
     using M = Mod<MI>;
-    u64 d0[8], d1[8], k0[8], k1[8];
-    load_chunk8(dg + (size_t)(0 * 3 + MI) * kN, d0, t);
-    load_chunk8(dg + (size_t)(1 * 3 + MI) * kN, d1, t);
-    load_chunk8_ldg(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN, k0, t);
-    load_chunk8_ldg(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN, k1, t);
+    const ulonglong2 *pd0 = reinterpret_cast<const ulonglong2 *>(dg + (size_t)(0 * 3 + MI) * kN + 8 * t);
+    const ulonglong2 *pd1 = reinterpret_cast<const ulonglong2 *>(dg + (size_t)(1 * 3 + MI) * kN + 8 * t);
+    const ulonglong2 *pk0 = reinterpret_cast<const ulonglong2 *>(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN + 8 * t);
+    const ulonglong2 *pk1 = reinterpret_cast<const ulonglong2 *>(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN + 8 * t);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const u64 xs[2] = {d0[r], d1[r]}, ys[2] = {k0[r], k1[r]};
-        v[0][r] = mulsum<M, 2>(xs, ys);
+    for (int r = 0; r < 4; r++) {  // two coefficients at a time: 16 operand registers live instead of 64
+        const ulonglong2 x0 = pd0[r], x1 = pd1[r], y0 = __ldg(pk0 + r), y1 = __ldg(pk1 + r);
+        {
+            const u64 xs[2] = {x0.x, x1.x}, ys[2] = {y0.x, y1.x};
+            v[0][2 * r] = mulsum<M, 2>(xs, ys);
+        }
+        {
+            const u64 xs[2] = {x0.y, x1.y}, ys[2] = {y0.y, y1.y};
+            v[0][2 * r + 1] = mulsum<M, 2>(xs, ys);
+        }
     }
     ntt_inverse<M, 1, true, true>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
 }
