@@ -369,6 +369,11 @@ void build(HostContext &H) {
         for (int l = 0; l < 2; l++) c.pBq[j][l] = mk_shoup(c.punct_B_mod_q[j][l], qs[l]);
     }
     for (int i = 0; i < 5; i++) c.alKs[i] = shoup_of(c.alK[i], msk);
+    c.q_w[0] = (u32)(u64)q;
+    c.q_w[1] = (u32)((u64)q >> 32);
+    c.q_w[2] = (u32)(u64)(q >> 64);
+    for (int j = 0; j < 2; j++) c.skD[j] = (u32)(msk - bsk[j]);
+    c.nib = mk_shoup((msk - c.inv_B_mod_msk.w) % msk, msk);
     for (int l = 0; l < 2; l++) {
         c.Bq[l] = mk_shoup(c.B_mod_q[l], qs[l]);
         c.nBq[l] = mk_shoup(c.neg_B_mod_q[l], qs[l]);

@@ -44,6 +44,9 @@ struct DevConsts {
     u64 extNeg[3];  // (p_k - m~) * extC[k] mod p_k: the correction term when the m~ residue is negative
     u64 skVs[2], skAs[2], skBs[2];
     u64 alKs[5];
+    u32 q_w[3];           // q = q0*q1 as three 32-bit words (q_w[2] < 2^8)
+    u32 skD[2];           // m_sk - b_j > 0: with every Bsk prime 2^61 - c, b_{j} == -skD[j] (mod m_sk)
+    Shoup nib;            // -(B^-1) mod m_sk
     Shoup pBq[2][2];      // punct_B_mod_q [j][l]
     Shoup Bq[2], nBq[2];  // B_mod_q, neg_B_mod_q
 

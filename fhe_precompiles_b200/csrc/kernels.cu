@@ -331,33 +331,50 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__
 // in the scratch slots the transforms then work on in place.  The transform-only kernel needs 40 registers: 3 CTAs per SM
 // instead of 2.  431.9 k -> 444.7 k ops/s; the same split of the tensor product (elementwise + in-place inverse transforms)
 // was slower (the elementwise pass moves 1.1 MB per op through DRAM) and is not kept.
-// x'_k = t0*extA + t1*extB + r*extC (mod p_k), r the centred m~ residue, as one ShoupSum:
-// terms < p(1 + 2^-28) each, plus the constant for r < 0: below 4.01 p < 2^63, then one fold + conditional subtraction.
-template <int K>
-__device__ __forceinline__ u64 ext_one(u64 t0, u64 t1, u32 rm) {
-    using M = Mod<kExtLimb[2 + K]>;
-    ShoupSum<M> s;
-    s.lo = rm >= 0x80000000u ? kc.extNeg[K] : 0;
-    s.add(t0, kc.extA[K], kc.extAs[K]);
-    s.add(t1, kc.extB[K], kc.extBs[K]);
-    s.add32(rm, kc.extC[K], kc.extCs[K]);
-    return canon_k32<M>(s.value());
+// y0 = t0 q1 + t1 q0 as a 128-bit integer (t_l canonical residues mod q_l): q_l = 2^36 - c_l, so
+// y0 = ((t0 + t1) << 36) - (t0 c1 + t1 c0), one multiply chain and a shift.  Shared by k_ext_conv and k_floor_sk.
+__device__ __forceinline__ void punctured_sum(u64 t0, u64 t1, u64 &ylo, u64 &yhi) {
+    constexpr u32 c0 = (u32)Mod<MQ0>::kC, c1 = (u32)Mod<MQ1>::kC;
+    u32 t0l, t0h, t1l, t1h, pl, ph;
+    unpack64(t0, t0l, t0h);
+    unpack64(t1, t1l, t1h);
+    unpack64(mad_wide(t0l, c1, mul_wide(t1l, c0)), pl, ph);
+    ph = mad_lo(t0h, c1, ph);  // t_h < 16
+    ph = mad_lo(t1h, c0, ph);
+    const u64 pv = pack64(pl, ph);  // t0 c1 + t1 c0 < 2^56
+    const u64 ts = t0 + t1, sh = ts << 36;
+    ylo = sh - pv;
+    yhi = (ts >> 28) - (sh < pv ? 1 : 0);
 }
+// Base extension in the integer domain.  SEAL's fastbconv_m_tilde + sm_mrq compute, per Bsk prime p_k,
+// (y0 + r q) m~^-1 mod p_k with r = -y0 q^-1 mod m~ centred: y0 + r q is an exact multiple of m~ = 2^32, so the value is the
+// INTEGER Z = (y0 + r q) / 2^32 (|Z| < 2^72) reduced mod p_k.  Z is formed once, as base + m 2^61 (- q if r < 0), and every
+// p_k = 2^61 - c_k needs only base + m c_k: two low multiplies per auxiliary limb instead of three Shoup products.
 __global__ void __launch_bounds__(256) k_ext_conv(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf,
                                                   size_t n_ops) {
     const size_t total = n_ops * 4 * kN;  // (op, poly a0 a1 b0 b1, coefficient)
+    const u32 qw0 = kc.q_w[0], qw1 = kc.q_w[1], qw2 = kc.q_w[2];
     for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (size_t)gridDim.x * 256) {
         const size_t op = g / (4 * kN);
         const int p = (int)((g / kN) & 3), i = (int)(g & (kN - 1));
         const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
         const u64 t0 = shoup<Mod<MQ0>>(ct[i], kc.ext_in[0].w, kc.ext_in[0].ws);
         const u64 t1 = shoup<Mod<MQ1>>(ct[kN + i], kc.ext_in[1].w, kc.ext_in[1].ws);
-        const u32 ymt = (u32)t0 * kc.punct_q_mod_mtilde[0] + (u32)t1 * kc.punct_q_mod_mtilde[1];
+        u64 ylo, yhi;
+        punctured_sum(t0, t1, ylo, yhi);
+        const u32 ymt = (u32)ylo;
         const u32 rm = ymt * kc.neg_inv_q_mod_mtilde;
+        const bool neg = rm >= 0x80000000u;
+        // (y0 + rm q) >> 32 = A + rm q_w1 + (rm q_w2 << 32); the low words of y0 and rm q_w0 cancel (carry iff non-zero)
+        const u64 A = ((ylo >> 32) | (yhi << 32)) + (mul_wide(rm, qw0) >> 32) + (ymt != 0 ? 1 : 0);
+        const u64 Bv = mul_wide(rm, qw1), Cv = mul_wide(rm, qw2);
+        const u64 sAB = A + Bv;
+        const u32 m = (u32)(sAB >> 61) + (sAB < A ? 8u : 0u) + (u32)(Cv >> 29);  // < 2^12
+        const u64 base = (sAB & ((1ull << 61) - 1)) + ((Cv & ((1ull << 29) - 1)) << 32);  // < 2^62
         u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN + i;
-        dst[0] = ext_one<0>(t0, t1, rm);
-        dst[kN] = ext_one<1>(t0, t1, rm);
-        dst[2 * kN] = ext_one<2>(t0, t1, rm);
+        dst[0] = canon_k32<Mod<MB0>>(base + (u64)(m * (u32)Mod<MB0>::kC) + (neg ? kc.extNeg[0] : 0));
+        dst[kN] = canon_k32<Mod<MB1>>(base + (u64)(m * (u32)Mod<MB1>::kC) + (neg ? kc.extNeg[1] : 0));
+        dst[2 * kN] = canon_k32<Mod<MSK>>(base + (u64)(m * (u32)Mod<MSK>::kC) + (neg ? kc.extNeg[2] : 0));
     }
 }
 template <int EI>
@@ -466,30 +483,30 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
         // fast_floor: q-part -> Bsk, f_k = (v_k - conv_k) * q^-1 mod p_k  (constants merged)
         u64 t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
         u64 t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
-        // fastbconv_sk inputs, constants merged (devconsts.h): tb_j = [f_j (B/b_j)^-1]_{b_j}.  Each output is one ShoupSum;
-        // tb_j and alpha are integers carried into another modulus, so they are made canonical.
-        u64 tb0, tb1, alpha;
-        {  // vb0 < 2 b0: terms < 1.25 p + 2 (1 + 2^-28) p
-            ShoupSum<B0> s;
-            s.add(vb0, kc.skV[0], kc.skVs[0]);
-            s.add(t0, kc.skA[0], kc.skAs[0]);
-            s.add(t1, kc.skB[0], kc.skBs[0]);
-            tb0 = canon_k32<B0>(s.value());
-        }
+        // The q-part of the value is the integer y0 = t0 q1 + t1 q0 (< 2^73); its residue mod a Bsk prime 2^61 - c is a fold.
+        u64 ylo, yhi;
+        punctured_sum(t0, t1, ylo, yhi);
+        const u64 y61 = ylo & ((1ull << 61) - 1);
+        const u32 yk = (u32)((ylo >> 61) | (yhi << 3));  // < 2^12
+        // tb_j = [(v_bj - y0) q^-1 (B/b_j)^-1]_{b_j}: one exact Shoup product (skV); canonical, it is carried into other moduli
+        const u64 xb0 = vb0 + B0::two_q - (y61 + (u64)(yk * (u32)B0::kC));
+        const u64 xb1 = vb1 + B1::two_q - (y61 + (u64)(yk * (u32)B1::kC));
+        const u64 tb0 = canon_k32<B0>(shoup_lazy<B0>(xb0, kc.skV[0], kc.skVs[0]));
+        const u64 tb1 = canon_k32<B1>(shoup_lazy<B1>(xb1, kc.skV[1], kc.skVs[1]));
+        // alpha = [(tb0 b1 + tb1 b0  -  (v_msk - y0) q^-1) B^-1]_{m_sk}, and b_j == -(m_sk - b_j) (mod m_sk) is 19 bits:
+        // w = tb0 skD[1] + tb1 skD[0] (82 bits, two multiply chains), folded below 2^63
+        u64 alpha;
         {
-            ShoupSum<B1> s;
-            s.add(vb1, kc.skV[1], kc.skVs[1]);
-            s.add(t0, kc.skA[1], kc.skAs[1]);
-            s.add(t1, kc.skB[1], kc.skBs[1]);
-            tb1 = canon_k32<B1>(s.value());
-        }
-        {  // alpha = [(B-part converted to m_sk  -  f_msk) * B^-1]_{m_sk}; five terms < 1.25 p each: < 2^64
-            ShoupSum<SK> s;
-            s.add(tb0, kc.alK[0], kc.alKs[0]);
-            s.add(tb1, kc.alK[1], kc.alKs[1]);
-            s.add(vsk, kc.alK[2], kc.alKs[2]);
-            s.add(t0, kc.alK[3], kc.alKs[3]);
-            s.add(t1, kc.alK[4], kc.alKs[4]);
+            u32 al, ah, bl, bh;
+            unpack64(tb0, al, ah);
+            unpack64(tb1, bl, bh);
+            const u64 wlo = mad_wide(al, kc.skD[1], mul_wide(bl, kc.skD[0]));
+            const u64 whi = mad_wide(ah, kc.skD[1], mul_wide(bh, kc.skD[0]));  // weight 2^32, < 2^49
+            const u64 wr = wlo + ((whi & ((1ull << 29) - 1)) << 32) + mul_wide((u32)(whi >> 29), (u32)SK::kC);
+            const u64 xs = vsk + SK::two_q - (y61 + (u64)(yk * (u32)SK::kC));
+            ShoupSum<SK> s;  // two terms < 1.5 q each
+            s.add(wr, kc.nib.w, kc.nib.ws);
+            s.add(xs, kc.alK[2], kc.alKs[2]);
             alpha = canon_k32<SK>(s.value());
         }
         bool neg = alpha > (SK::q >> 1);
