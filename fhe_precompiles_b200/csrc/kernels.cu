@@ -179,12 +179,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_mul_plain(const u64 *__restrict
 //   SEAL Evaluator::bfv_multiply steps (1)-(6); RNSTool::fastbconv_m_tilde, RNSTool::sm_mrq
 // one CTA per (extended limb e = q0,q1,b0,b1,msk ; op)
 // =====================================================================================
+// y0 = t0 q1 + t1 q0 as a 128-bit integer (t_l canonical residues mod q_l): q_l = 2^36 - c_l, so
+// y0 = ((t0 + t1) << 36) - (t0 c1 + t1 c0), one multiply chain and a shift.  Shared by k_ext_conv and k_floor_sk.
+__device__ __forceinline__ void punctured_sum(u64 t0, u64 t1, u64 &ylo, u64 &yhi) {
+    constexpr u32 c0 = (u32)Mod<MQ0>::kC, c1 = (u32)Mod<MQ1>::kC;
+    u32 t0l, t0h, t1l, t1h, pl, ph;
+    unpack64(t0, t0l, t0h);
+    unpack64(t1, t1l, t1h);
+    unpack64(mad_wide(t0l, c1, mul_wide(t1l, c0)), pl, ph);
+    ph = mad_lo(t0h, c1, ph);  // t_h < 16
+    ph = mad_lo(t1h, c0, ph);
+    const u64 pv = pack64(pl, ph);  // t0 c1 + t1 c0 < 2^56
+    const u64 ts = t0 + t1, sh = ts << 36;
+    ylo = sh - pv;
+    yhi = (ts >> 28) - (sh < pv ? 1 : 0);
+}
+// Shared part of the integer-domain base extension (see k_ext_conv): Z = base + m 2^61 (- q if neg)
+__device__ __forceinline__ void ext_shared(u64 x0, u64 x1, u64 &base, u32 &m, bool &neg) {
+    const u64 t0 = shoup<Mod<MQ0>>(x0, kc.ext_in[0].w, kc.ext_in[0].ws);
+    const u64 t1 = shoup<Mod<MQ1>>(x1, kc.ext_in[1].w, kc.ext_in[1].ws);
+    u64 ylo, yhi;
+    punctured_sum(t0, t1, ylo, yhi);
+    const u32 ymt = (u32)ylo;
+    const u32 rm = ymt * kc.neg_inv_q_mod_mtilde;
+    neg = rm >= 0x80000000u;
+    // (y0 + rm q) >> 32 = A + rm q_w1 + (rm q_w2 << 32); the low words of y0 and rm q_w0 cancel (carry iff non-zero)
+    const u64 A = ((ylo >> 32) | (yhi << 32)) + (mul_wide(rm, kc.q_w[0]) >> 32) + (ymt != 0 ? 1 : 0);
+    const u64 Bv = mul_wide(rm, kc.q_w[1]), Cv = mul_wide(rm, kc.q_w[2]);
+    const u64 sAB = A + Bv;
+    m = (u32)(sAB >> 61) + (sAB < A ? 8u : 0u) + (u32)(Cv >> 29);             // < 2^12
+    base = (sAB & ((1ull << 61) - 1)) + ((Cv & ((1ull << 29) - 1)) << 32);  // < 2^62
+}
+template <int K>
+__device__ __forceinline__ u64 ext_limb(u64 base, u32 m, bool neg) {
+    using M = Mod<kExtLimb[2 + K]>;
+    return canon_k32<M>(base + (u64)(m * (u32)M::kC) + (neg ? kc.extNeg[K] : 0));
+}
 // Loads polynomial `poly` of a data-level ciphertext into pass-0 register layout in limb EI of the
 // extended base.  EI < 2: plain copy of the q-limb.  EI >= 2: fast base conversion through m_tilde with
 // the Montgomery correction, all per coefficient:
 //   tmp_l = x_l * (m~ * (q/q_l)^-1) mod q_l                     (canonical)
 //   r     = -(tmp_0*(q/q_0) + tmp_1*(q/q_1)) * q^-1 mod 2^32, centred
-//   x'_k  = (tmp_0*(q/q_0) + tmp_1*(q/q_1) + r*q) * m~^-1 mod p_k    (constants pre-multiplied by m~^-1)
+//   x'_k  = (tmp_0*(q/q_0) + tmp_1*(q/q_1) + r*q) / 2^32  mod p_k     (integer domain: ext_shared / ext_limb)
 template <int EI>
 __device__ __forceinline__ void load_extended(const u64 *__restrict__ ct, int poly, u64 (&v)[8], int t) {
     constexpr int MI = kExtLimb[EI];
@@ -195,21 +231,14 @@ __device__ __forceinline__ void load_extended(const u64 *__restrict__ ct, int po
         constexpr int K = EI - 2;
         const u64 *x0 = ct + (size_t)(poly * 2 + 0) * kN;
         const u64 *x1 = ct + (size_t)(poly * 2 + 1) * kN;
-        const u64 cA = kc.extA[K], cB = kc.extB[K], cC = kc.extC[K];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             int i = r * kThreads + t;
-            u64 t0 = shoup<Mod<MQ0>>(x0[i], kc.ext_in[0].w, kc.ext_in[0].ws);
-            u64 t1 = shoup<Mod<MQ1>>(x1[i], kc.ext_in[1].w, kc.ext_in[1].ws);
-            u32 ymt = (u32)t0 * kc.punct_q_mod_mtilde[0] + (u32)t1 * kc.punct_q_mod_mtilde[1];
-            u32 rm = ymt * kc.neg_inv_q_mod_mtilde;
-            u64 rr = rm;
-            if (rm >= 0x80000000u) rr += M::q - kMTilde;
-            u64 lo = 0, hi = 0;
-            mac128(lo, hi, t0, cA);
-            mac128(lo, hi, t1, cB);
-            mac128(lo, hi, rr, cC);
-            v[r] = reduce128<M>(hi, lo);
+            u64 base;
+            u32 m;
+            bool neg;
+            ext_shared(x0[i], x1[i], base, m, neg);
+            v[r] = ext_limb<K>(base, m, neg);
         }
     }
 }
@@ -331,21 +360,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__
 // in the scratch slots the transforms then work on in place.  The transform-only kernel needs 40 registers: 3 CTAs per SM
 // instead of 2.  431.9 k -> 444.7 k ops/s; the same split of the tensor product (elementwise + in-place inverse transforms)
 // was slower (the elementwise pass moves 1.1 MB per op through DRAM) and is not kept.
-// y0 = t0 q1 + t1 q0 as a 128-bit integer (t_l canonical residues mod q_l): q_l = 2^36 - c_l, so
-// y0 = ((t0 + t1) << 36) - (t0 c1 + t1 c0), one multiply chain and a shift.  Shared by k_ext_conv and k_floor_sk.
-__device__ __forceinline__ void punctured_sum(u64 t0, u64 t1, u64 &ylo, u64 &yhi) {
-    constexpr u32 c0 = (u32)Mod<MQ0>::kC, c1 = (u32)Mod<MQ1>::kC;
-    u32 t0l, t0h, t1l, t1h, pl, ph;
-    unpack64(t0, t0l, t0h);
-    unpack64(t1, t1l, t1h);
-    unpack64(mad_wide(t0l, c1, mul_wide(t1l, c0)), pl, ph);
-    ph = mad_lo(t0h, c1, ph);  // t_h < 16
-    ph = mad_lo(t1h, c0, ph);
-    const u64 pv = pack64(pl, ph);  // t0 c1 + t1 c0 < 2^56
-    const u64 ts = t0 + t1, sh = ts << 36;
-    ylo = sh - pv;
-    yhi = (ts >> 28) - (sh < pv ? 1 : 0);
-}
 // Base extension in the integer domain.  SEAL's fastbconv_m_tilde + sm_mrq compute, per Bsk prime p_k,
 // (y0 + r q) m~^-1 mod p_k with r = -y0 q^-1 mod m~ centred: y0 + r q is an exact multiple of m~ = 2^32, so the value is the
 // INTEGER Z = (y0 + r q) / 2^32 (|Z| < 2^72) reduced mod p_k.  Z is formed once, as base + m 2^61 (- q if r < 0), and every
@@ -353,28 +367,18 @@ __device__ __forceinline__ void punctured_sum(u64 t0, u64 t1, u64 &ylo, u64 &yhi
 __global__ void __launch_bounds__(256) k_ext_conv(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf,
                                                   size_t n_ops) {
     const size_t total = n_ops * 4 * kN;  // (op, poly a0 a1 b0 b1, coefficient)
-    const u32 qw0 = kc.q_w[0], qw1 = kc.q_w[1], qw2 = kc.q_w[2];
     for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (size_t)gridDim.x * 256) {
         const size_t op = g / (4 * kN);
         const int p = (int)((g / kN) & 3), i = (int)(g & (kN - 1));
         const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
-        const u64 t0 = shoup<Mod<MQ0>>(ct[i], kc.ext_in[0].w, kc.ext_in[0].ws);
-        const u64 t1 = shoup<Mod<MQ1>>(ct[kN + i], kc.ext_in[1].w, kc.ext_in[1].ws);
-        u64 ylo, yhi;
-        punctured_sum(t0, t1, ylo, yhi);
-        const u32 ymt = (u32)ylo;
-        const u32 rm = ymt * kc.neg_inv_q_mod_mtilde;
-        const bool neg = rm >= 0x80000000u;
-        // (y0 + rm q) >> 32 = A + rm q_w1 + (rm q_w2 << 32); the low words of y0 and rm q_w0 cancel (carry iff non-zero)
-        const u64 A = ((ylo >> 32) | (yhi << 32)) + (mul_wide(rm, qw0) >> 32) + (ymt != 0 ? 1 : 0);
-        const u64 Bv = mul_wide(rm, qw1), Cv = mul_wide(rm, qw2);
-        const u64 sAB = A + Bv;
-        const u32 m = (u32)(sAB >> 61) + (sAB < A ? 8u : 0u) + (u32)(Cv >> 29);  // < 2^12
-        const u64 base = (sAB & ((1ull << 61) - 1)) + ((Cv & ((1ull << 29) - 1)) << 32);  // < 2^62
+        u64 base;
+        u32 m;
+        bool neg;
+        ext_shared(ct[i], ct[kN + i], base, m, neg);
         u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN + i;
-        dst[0] = canon_k32<Mod<MB0>>(base + (u64)(m * (u32)Mod<MB0>::kC) + (neg ? kc.extNeg[0] : 0));
-        dst[kN] = canon_k32<Mod<MB1>>(base + (u64)(m * (u32)Mod<MB1>::kC) + (neg ? kc.extNeg[1] : 0));
-        dst[2 * kN] = canon_k32<Mod<MSK>>(base + (u64)(m * (u32)Mod<MSK>::kC) + (neg ? kc.extNeg[2] : 0));
+        dst[0] = ext_limb<0>(base, m, neg);
+        dst[kN] = ext_limb<1>(base, m, neg);
+        dst[2 * kN] = ext_limb<2>(base, m, neg);
     }
 }
 template <int EI>
