@@ -502,7 +502,7 @@ def main() -> None:
             "ops_per_gpu_per_step": n,
             "l2": "inputs (1 GiB per GPU) exceed the 126 MB L2; no flush needed",
             "sharding": f"{world} rank(s), independent batches, no collective",
-            "chunk_ops": int(os.environ.get("FHE_B200_CHUNK_OPS", "2048")),
+            "chunk_ops": int(os.environ.get("FHE_B200_CHUNK_OPS", "4096")),
             "subchunk_ops": int(os.environ.get("FHE_B200_SUBCHUNK_OPS", "0")),
             "kernels": "split" if not int(os.environ.get("FHE_B200_FUSED", "0")) else "fused",
         },

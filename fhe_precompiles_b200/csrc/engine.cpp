@@ -67,7 +67,7 @@ Engine::Engine() {
     }
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
-    chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 2048);
+    chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 4096);
     fused_ = env_size("FHE_B200_FUSED", 0) != 0;
     {
         const char *v = getenv("FHE_B200_SUBCHUNK_OPS");

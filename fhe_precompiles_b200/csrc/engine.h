@@ -175,7 +175,7 @@ class Engine {
     void release_lane(Lane *);
 
     int n_devices_ = 0;
-    size_t chunk_ops_ = 2048;
+    size_t chunk_ops_ = 4096;
     std::vector<std::unique_ptr<Lane>> lanes_;
     std::mutex lane_mu_;
     std::condition_variable lane_cv_;
