@@ -26,11 +26,18 @@ N = 4096
 Q = (0xFFFFEE001, 0xFFFFC4001)
 CT_BYTES = 2 * 2 * N * 8  # 131,072
 ALGO_BYTES_PER_OP = 3 * CT_BYTES  # read a, read b, write result = 393,216 B
-# 47 limb-NTTs x 24,576 butterflies + ~0.79 M pointwise modmuls per op
-MODMUL_PER_OP = 47 * 24576 + 790528
-# FMA-pipe cost of one Shoup modmul as written in modarith.cuh: 5 IMAD.WIDE (quarter rate on B200: 32 per clock per SM,
-# measured) + 4 IMAD (half rate) = 7 IMAD.WIDE equivalents; the 61-bit primes need one more wide product (8)
-WIDE_EQ_PER_MODMUL = 7.4
+# 47 limb-NTTs x 24,576 butterflies per op
+BUTTERFLIES_PER_OP = 47 * 24576
+# FMA-pipe cost of the arithmetic as written (modarith.cuh), in IMAD.WIDE equivalents (IMAD.WIDE is quarter rate on B200: 32 per
+# clock per SM, measured; IMAD half rate = 0.5 equivalents):
+#   butterflies: 14 forward on 36/37-bit primes 4 wide + 5 low = 6.5, 12 inverse on them 5 + 4 = 7, 21 on 61-bit primes 6 + 3 = 7.5
+#                -> 7.07 on average
+#   pointwise  : counted from the kernels' SASS per coefficient -- k_ext_conv 42.5 x 16,384, k_floor_sk 113 x 12,288, the tensor
+#                (mulsum) 0.51 M, the key-switch MAC 0.28 M, the division by P 0.13 M -> 3.0 M per op
+# (the base conversions as SEAL states them, 0.79 M 64-bit modmuls, would be about twice the pointwise figure)
+WIDE_EQ_PER_BUTTERFLY = 7.07
+POINTWISE_WIDE_EQ_PER_OP = 3.0e6
+WIDE_EQ_PER_OP = BUTTERFLIES_PER_OP * WIDE_EQ_PER_BUTTERFLY + POINTWISE_WIDE_EQ_PER_OP
 METRIC = "ct_ct_fhe_multiply_relin_ops_per_sec"
 WORKLOAD = "batch of 4096 ct*ct fhe_multiply+relinearize per GPU, testnet BFV params (N=4096, q=72b, t=4096)"
 
@@ -462,7 +469,7 @@ def main() -> None:
         peak_wide = fdev.int_peak(local_rank, wide=1)  # T IMAD.WIDE/s (mul.wide.u32 with a loop-carried operand)
         peak_lo = fdev.int_peak(local_rank, wide=0)
         ops_s = n * args.steps / (ms * 1e-3)
-        ach = ops_s * MODMUL_PER_OP * WIDE_EQ_PER_MODMUL / 1e12
+        ach = ops_s * WIDE_EQ_PER_OP / 1e12
         # butterfly-rate ceiling: register-only NTT inner loop, per prime class (26 small + 21 large limb-NTTs per op)
         bf_small, bf_big = fdev.bfly_peak(local_rank, 0), fdev.bfly_peak(local_rank, 3)
         ntt_floor_us = 24576 * (26 / bf_small + 21 / bf_big) * 1e-3
@@ -471,8 +478,8 @@ def main() -> None:
             "peak": peak_wide,
             "unit": "T IMAD.WIDE-equivalents/s (FMA pipe)",
             "frac": ach / peak_wide,
-            "model": f"{MODMUL_PER_OP} 64-bit modmul/op x {WIDE_EQ_PER_MODMUL} IMAD.WIDE equivalents (5-6 IMAD.WIDE + 4 IMAD at half cost); "
-            "peak = measured mul.wide.u32 rate",
+            "model": f"{BUTTERFLIES_PER_OP} butterflies/op x {WIDE_EQ_PER_BUTTERFLY} + {POINTWISE_WIDE_EQ_PER_OP:.2e} pointwise IMAD.WIDE equivalents "
+            "(multiplies as written in modarith.cuh, IMAD = 0.5); peak = measured mul.wide.u32 rate",
             "measured_pipe_rates_T_per_s": {"IMAD.WIDE": peak_wide, "IMAD": peak_lo},
             "butterfly_peak_G_per_s": {"36-37 bit primes": bf_small, "61 bit primes": bf_big},
             "ntt_only_floor_us_per_op": ntt_floor_us,
