@@ -344,11 +344,11 @@ __device__ __forceinline__ u64 reduce128(u64 hi, u64 lo) {
     }
 }
 
+// canonical a*b mod q; operands below 2^44 (36/37-bit primes) or 2^61 (61-bit primes)
 template <class M>
 __device__ __forceinline__ u64 mulmod(u64 a, u64 b) {
-    u64 lo = 0, hi = 0;
-    mac128(lo, hi, a, b);
-    return reduce128<M>(hi, lo);
+    const u64 xs[1] = {a}, ys[1] = {b};
+    return csub<M>(mulsum<M, 1>(xs, ys), M::q);
 }
 
 template <class M>
