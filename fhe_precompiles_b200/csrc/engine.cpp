@@ -414,7 +414,9 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
         TIMED(2, launch_relin_ks(c3, rk, m.ks, c, s), "relin_ks");
     } else {
         TIMED(6, launch_digit_ntt(c3, m.dig, c, s), "digit_ntt");
-        if (ks_finish_fused()) {
+        // the fused tail runs the three moduli one after the other in two CTAs per op: right once the batch fills the GPU,
+        // three times the critical path for a single call
+        if (ks_finish_fused() && c >= 148) {
             TIMED(9, launch_ks_finish(m.dig, rk, c3, out, c, s), "ks_finish");
             return;
         }
