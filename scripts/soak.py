@@ -1,6 +1,6 @@
 """Differential soak of the ct x ct multiply + relinearise path: many batches of random and adversarial ciphertext pairs through
 the device-resident C-ABI entry point, bit-compared with the CPU oracle (all host threads).  Needs a GPU.
-usage: python scripts/soak.py [batches] [ops_per_batch]"""
+usage: python scripts/soak.py [batches] [ops_per_batch] [seed_base]"""
 import json
 import os
 import sys
@@ -47,6 +47,7 @@ def adversarial(rng, n):
 def main() -> None:
     batches = int(sys.argv[1]) if len(sys.argv) > 1 else 24
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+    seed_base = int(sys.argv[3]) if len(sys.argv) > 3 else 1000
     threads = os.cpu_count() or 1
     net_pub = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fhe_precompiles_b200/data/network.pub"), "rb").read()
     _, rk_host = fdev.parse_public_key(net_pub)
@@ -55,7 +56,7 @@ def main() -> None:
     mismatched = total = 0
     t0 = time.time()
     for b in range(batches):
-        rng = np.random.default_rng(1000 + b)
+        rng = np.random.default_rng(seed_base + b)
         if b % 3 == 2:
             a_np, b_np = adversarial(rng, n), adversarial(rng, n)
         else:
@@ -70,7 +71,7 @@ def main() -> None:
         total += n
         print(f"batch {b} ({'adversarial' if b % 3 == 2 else 'uniform'}): {n - bad}/{n} identical", flush=True)
     print(json.dumps({"ops": total, "mismatched_ops": mismatched, "coefficients_compared": total * 4 * N,
-                      "batches": batches, "adversarial_batches": batches // 3, "seconds": round(time.time() - t0, 1)}))
+                      "batches": batches, "adversarial_batches": batches // 3, "seed_base": seed_base, "seconds": round(time.time() - t0, 1)}))
 
 
 if __name__ == "__main__":
