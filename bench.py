@@ -142,6 +142,61 @@ def cpu_baseline(a_np, b_np, rk_np, threads: int):
     return a_np.shape[0] / secs, out, secs
 
 
+def e2e_frames(fdev, a_h, b_h, out_h, rk_host, device_index, steps, world, barrier, dist) -> dict:
+    """ops/s of fhe_b200_mul_relin_frames on pinned host buffers of structured frames; result frames checked against the
+    library's own serialisation of the limb-array result."""
+    import ctypes
+
+    import numpy as np
+    import torch
+
+    from fhe_precompiles_b200 import _lib
+    from fhe_precompiles_b200.sharding import max_over_ranks
+
+    L = _lib.lib()
+    dt_ = b"sunscreen::types::bfv::signed::Signed,0.8.1,true"
+    fb, fs = fdev.frame_bytes(), fdev.frame_stride()
+
+    def frame_of(words) -> np.ndarray:
+        o, ln = ctypes.c_void_p(), ctypes.c_int64()
+        w = np.ascontiguousarray(words)
+        if L.fhe_b200_write_ciphertext(w.ctypes.data, dt_, ctypes.byref(o), ctypes.byref(ln)) != 0:
+            raise RuntimeError("write_ciphertext failed")
+        raw = np.frombuffer(ctypes.string_at(o, ln.value), dtype=np.uint8)[ln.value - fb :].copy()  # the zstd frame is the tail
+        L.fhe_free(o)
+        return raw
+
+    n = a_h.shape[0]
+    an, bn = a_h.numpy().view(np.uint64), b_h.numpy().view(np.uint64)
+    fa = torch.zeros((n, fs), dtype=torch.uint8).pin_memory()
+    fbuf = torch.zeros((n, fs), dtype=torch.uint8).pin_memory()
+    for i in range(n):
+        fa[i, :fb] = torch.from_numpy(frame_of(an[i]))
+        fbuf[i, :fb] = torch.from_numpy(frame_of(bn[i]))
+    fo = torch.zeros((n, fs), dtype=torch.uint8).pin_memory()
+    st = torch.zeros((n,), dtype=torch.int32).pin_memory()
+    for _ in range(2):
+        fdev.mul_relin_frames(fa, fbuf, rk_host, fo, st, device=device_index)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        fdev.mul_relin_frames(fa, fbuf, rk_host, fo, st, device=device_index)
+    dt = time.perf_counter() - t0
+    barrier()
+    dt_max = max_over_ranks(dt, dist)
+    on = out_h.numpy().view(np.uint64)
+    same = all(bool((fo[i, :fb].numpy() == frame_of(on[i])).all()) for i in (0, 1, n // 2, n - 1))
+    return {
+        "value": world * n * steps / dt_max,
+        "unit": "ops/s",
+        "h2d_bytes_per_step": 2 * n * fs + rk_host.numel() * 8,
+        "d2h_bytes_per_step": n * fs + 12 * n,
+        "api": "fhe_b200_mul_relin_frames (C ABI, pinned host buffers of structured zstd frames, 82,054 bytes per ciphertext)",
+        "all_status_ok": bool((st == 0).all()),
+        "frames_match_limb_array_result": same,
+    }
+
+
 def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 1000) -> dict:
     """p50 / p99 of one c_fhe_mul_cipheri64_cipheri64 call (warm key cache): packed bytes in, packed bytes out,
     i.e. bincode + zstd inflate of two ciphertexts, H2D, six kernels, D2H, zstd deflate.  Also times the codec alone."""
@@ -412,6 +467,12 @@ def main() -> None:
             "api": "fhe_b200_mul_relin_host (C ABI, pinned host limb arrays)",
             "matches_device_resident_result": same,
         }
+        # the same batch with SERIALIZED operands: structured zstd frames (5 bytes per residue, what this library's precompiles
+        # return and accept) in and out through fhe_b200_mul_relin_frames; frames are unpacked / written on the GPU
+        try:
+            e2e["serialized"] = e2e_frames(fdev, a_h, b_h, out_h, rk_host, local_rank, args.steps, world, barrier, dist)
+        except Exception as ex:  # pragma: no cover
+            e2e["serialized"] = {"error": str(ex)}
 
     if rank != 0:
         if dist is not None:

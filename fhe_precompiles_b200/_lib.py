@@ -85,6 +85,12 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_decrypt.restype = i32
     L.fhe_b200_mul_relin_host.argtypes = [i32, vp, vp, vp, vp, sz]
     L.fhe_b200_mul_relin_host.restype = i32
+    L.fhe_b200_mul_relin_frames.argtypes = [i32, vp, vp, sz, vp, vp, sz, vp]
+    L.fhe_b200_mul_relin_frames.restype = i32
+    L.fhe_b200_frame_bytes.argtypes = []
+    L.fhe_b200_frame_bytes.restype = sz
+    L.fhe_b200_frame_stride.argtypes = []
+    L.fhe_b200_frame_stride.restype = sz
     L.fhe_b200_int_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]
     L.fhe_b200_int_peak.restype = i32
     L.fhe_b200_bfly_peak.argtypes = [i32, i32, ctypes.POINTER(ctypes.c_double)]

@@ -336,6 +336,12 @@ int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_
                                 size_t n) {
     DEV_GUARD(Engine::get().mul_relin_host(device, a, b, rk, out, n));
 }
+int32_t fhe_b200_mul_relin_frames(int32_t device, const uint8_t *a_frames, const uint8_t *b_frames, size_t stride, const uint64_t *rk,
+                                  uint8_t *out_frames, size_t n, int32_t *status) {
+    DEV_GUARD(Engine::get().mul_relin_frames(device, a_frames, b_frames, stride, rk, out_frames, n, status));
+}
+size_t fhe_b200_frame_bytes(void) { return kPackedFrameBytes; }
+size_t fhe_b200_frame_stride(void) { return kPackedFrameStride; }
 int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,
                      void *stream) {
     if (!mods || n_mods < 1 || n_mods > kNumMod) {

@@ -509,18 +509,18 @@ void Engine::mul_relin_host(int device, const uint64_t *a, const uint64_t *b, co
     }
     HostPipe &P = *pipes_[(size_t)device];
     std::lock_guard<std::mutex> lk(P.mu);
-    if (!P.ready) {
-        P.chunk = env_size("FHE_B200_PIPE_CHUNK_OPS", 256);
-        cuda_throw(cudaMalloc((void **)&P.d_rk, kRkWords * 8), "cudaMalloc(rk)");
-        for (auto &sl : P.slot) {
-            cuda_throw(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (!P.chunk) P.chunk = env_size("FHE_B200_PIPE_CHUNK_OPS", 256);
+    if (!P.d_rk) cuda_throw(cudaMalloc((void **)&P.d_rk, kRkWords * 8), "cudaMalloc(rk)");
+    for (auto &sl : P.slot) {
+        if (!sl.stream) cuda_throw(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!sl.d_a) {
             cuda_throw(cudaMalloc((void **)&sl.d_a, P.chunk * kCtWords * 8), "cudaMalloc");
             cuda_throw(cudaMalloc((void **)&sl.d_b, P.chunk * kCtWords * 8), "cudaMalloc");
             cuda_throw(cudaMalloc((void **)&sl.d_out, P.chunk * kCtWords * 8), "cudaMalloc");
             cuda_throw(cudaMalloc((void **)&sl.d_scratch, P.chunk * kScratchLimbsPerOp * kN * 8), "cudaMalloc");
         }
-        P.ready = true;
     }
+    P.ready = true;
     cuda_throw(cudaMemcpyAsync(P.d_rk, rk, kRkWords * 8, cudaMemcpyHostToDevice, P.slot[0].stream), "H2D rk");
     cuda_throw(cudaStreamSynchronize(P.slot[0].stream), "sync rk");
     size_t i = 0;
@@ -536,6 +536,99 @@ void Engine::mul_relin_host(int device, const uint64_t *a, const uint64_t *b, co
         cuda_throw(cudaMemcpyAsync(out + off * kCtWords, sl.d_out, c * kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H out");
     }
     for (auto &sl : P.slot) cuda_throw(cudaStreamSynchronize(sl.stream), "pipe sync");
+}
+
+// ---------------------------------------------------------------- serialized operands (structured frames), pipelined like the above
+// Operand i of an array is the zstd frame at f + i * stride (the body of a ciphertext this library serialized: 82,054 bytes,
+// codec_kernels.h).  Frames are copied as they are (5 bytes per residue instead of 8 over PCIe), validated and unpacked on the
+// GPU, and the result is written as a frame on the GPU: fout + i * kPackedFrameStride.  status[i]: 0 done, 1 an operand is not a
+// structured frame (or fails the range checks) - result undefined, use the byte surface -, 2 the result needs the generic writer.
+void Engine::mul_relin_frames(int device, const uint8_t *fa, const uint8_t *fb, size_t stride, const uint64_t *rk, uint8_t *fout,
+                              size_t n, int32_t *status) {
+    if (stride < kPackedFrameBytes) throw std::runtime_error("mul_relin_frames: stride smaller than a structured frame");
+    device_context(device);
+    {
+        std::lock_guard<std::mutex> lk(arena_mu_);
+        if (pipes_.size() < (size_t)n_devices_) pipes_.resize((size_t)n_devices_);
+        if (!pipes_[(size_t)device]) pipes_[(size_t)device].reset(new HostPipe());
+    }
+    HostPipe &P = *pipes_[(size_t)device];
+    std::lock_guard<std::mutex> lk(P.mu);
+    if (!P.chunk) P.chunk = env_size("FHE_B200_PIPE_CHUNK_OPS", 256);
+    if (!P.d_rk) cuda_throw(cudaMalloc((void **)&P.d_rk, kRkWords * 8), "cudaMalloc(rk)");
+    if (!P.d_prefix) {
+        uint8_t prefix[kCtPrefixBytes];
+        canonical_ct_prefix(prefix);
+        cuda_throw(cudaMalloc((void **)&P.d_prefix, kCtPrefixBytes), "cudaMalloc");
+        cuda_throw(cudaMemcpy(P.d_prefix, prefix, kCtPrefixBytes, cudaMemcpyHostToDevice), "upload prefix");
+    }
+    const size_t region = P.chunk * stride;  // one operand array of a chunk
+    for (auto &sl : P.slot) {
+        if (!sl.stream) cuda_throw(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+        if (!sl.d_a) {
+            cuda_throw(cudaMalloc((void **)&sl.d_a, P.chunk * kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_b, P.chunk * kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_out, P.chunk * kCtWords * 8), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_scratch, P.chunk * kScratchLimbsPerOp * kN * 8), "cudaMalloc");
+        }
+        if (sl.frame_stride != stride) {  // staging [pad | a frames | pad | b frames | pad], jobs interleaved a0 b0 a1 b1 ...
+            cudaFree(sl.d_frames), cudaFree(sl.d_outframes), cudaFree(sl.d_jobs), cudaFree(sl.d_status);
+            cuda_throw(cudaMalloc((void **)&sl.d_frames, 2 * region + 3 * kFramePad), "cudaMalloc");
+            cuda_throw(cudaMemset(sl.d_frames, 0, 2 * region + 3 * kFramePad), "cudaMemset");
+            cuda_throw(cudaMalloc((void **)&sl.d_outframes, P.chunk * kPackedFrameStride), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_jobs, 2 * P.chunk * sizeof(CodecJob)), "cudaMalloc");
+            cuda_throw(cudaMalloc((void **)&sl.d_status, 3 * P.chunk * sizeof(int32_t)), "cudaMalloc");
+            std::vector<CodecJob> jobs(2 * P.chunk);
+            for (size_t i = 0; i < P.chunk; i++) {
+                jobs[2 * i] = CodecJob{kFramePad + i * stride, (uint32_t)kPackedFrameBytes, kJobPacked, (int32_t)i, 0};
+                jobs[2 * i + 1] = CodecJob{2 * kFramePad + region + i * stride, (uint32_t)kPackedFrameBytes, kJobPacked, (int32_t)i, 1};
+            }
+            cuda_throw(cudaMemcpy(sl.d_jobs, jobs.data(), jobs.size() * sizeof(CodecJob), cudaMemcpyHostToDevice), "upload jobs");
+            sl.frame_stride = stride;
+        }
+    }
+    P.ready = true;
+    if (P.h_status_cap < 3 * n) {
+        if (P.h_status) cudaFreeHost(P.h_status);
+        cuda_throw(cudaMallocHost((void **)&P.h_status, 3 * n * sizeof(int32_t)), "cudaMallocHost");
+        P.h_status_cap = 3 * n;
+    }
+    cuda_throw(cudaMemcpyAsync(P.d_rk, rk, kRkWords * 8, cudaMemcpyHostToDevice, P.slot[0].stream), "H2D rk");
+    cuda_throw(cudaStreamSynchronize(P.slot[0].stream), "sync rk");
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += P.chunk, k++) {
+        const size_t c = n - off < P.chunk ? n - off : P.chunk;
+        PipeSlot &sl = P.slot[k % kPipeSlots];
+        cudaStream_t s = sl.stream;
+        // the last frame of an array may end before its stride does: never read past fa / fb + (n-1) * stride + frame
+        const size_t bytes = (c - 1) * stride + kPackedFrameBytes;
+        cuda_throw(cudaMemcpyAsync(sl.d_frames + kFramePad, fa + off * stride, bytes, cudaMemcpyHostToDevice, s), "H2D frames a");
+        cuda_throw(cudaMemcpyAsync(sl.d_frames + 2 * kFramePad + region, fb + off * stride, bytes, cudaMemcpyHostToDevice, s), "H2D frames b");
+        cuda_throw(launch_codec_inflate(sl.d_frames, nullptr, sl.d_jobs, sl.d_status, nullptr, P.d_prefix, sl.d_a, sl.d_b, (int)(2 * c), false,
+                                        true, false, s),
+                   "frame unpack");
+        ScratchMap m(sl.d_scratch, P.chunk);
+        enqueue_mul(sl.d_a, sl.d_b, m, c, s, false);
+        enqueue_relin(m.c3, P.d_rk, sl.d_out, m, c, s, false);
+        cuda_throw(launch_codec_pack(sl.d_out, sl.d_outframes, sl.d_status + 2 * P.chunk, P.d_prefix, (int)c, s), "frame pack");
+        cuda_throw(cudaMemcpyAsync(fout + off * kPackedFrameStride, sl.d_outframes, (c - 1) * kPackedFrameStride + kPackedFrameBytes,
+                                   cudaMemcpyDeviceToHost, s),
+                   "D2H frames");
+        cuda_throw(cudaMemcpyAsync(P.h_status + 3 * off, sl.d_status, 2 * c * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H status");
+        cuda_throw(cudaMemcpyAsync(P.h_status + 3 * off + 2 * c, sl.d_status + 2 * P.chunk, c * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
+                   "D2H flags");
+    }
+    for (auto &sl : P.slot) cuda_throw(cudaStreamSynchronize(sl.stream), "pipe sync");
+    if (status) {
+        for (size_t off = 0; off < n; off += P.chunk) {
+            const size_t c = n - off < P.chunk ? n - off : P.chunk;
+            const int32_t *st = P.h_status + 3 * off;
+            for (size_t i = 0; i < c; i++) {
+                const bool ok = st[2 * i] != kJobFallback && st[2 * i + 1] != kJobFallback;  // the unpack kernel only flags failures
+                status[off + i] = !ok ? 1 : (st[2 * c + i] ? 2 : 0);
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------- byte surface, one call

@@ -128,6 +128,9 @@ class Engine {
     // host-buffer batched entry point: a, b, out are host memory (pinned for full PCIe rate), rk host words.
     // H2D, kernels and D2H of consecutive chunks overlap on `kPipeSlots` streams.  Synchronous.
     void mul_relin_host(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n);
+    // the same on serialized operands: structured zstd frames (what this library writes) in, structured frames out
+    void mul_relin_frames(int device, const uint8_t *fa, const uint8_t *fb, size_t stride, const uint64_t *rk, uint8_t *fout, size_t n,
+                          int32_t *status);
 
     // Optional per-kernel timing of mul_relin(): CUDA events around every launch on the caller's stream.
     // kernel ids: see kKernelNames.  report() synchronises the device.
@@ -194,11 +197,19 @@ class Engine {
     struct PipeSlot {
         cudaStream_t stream = nullptr;
         uint64_t *d_a = nullptr, *d_b = nullptr, *d_out = nullptr, *d_scratch = nullptr;
+        // mul_relin_frames: staged operand frames, result frames, codec jobs / status
+        uint8_t *d_frames = nullptr, *d_outframes = nullptr;
+        struct CodecJob *d_jobs = nullptr;
+        int32_t *d_status = nullptr;
+        size_t frame_stride = 0;
     };
     struct HostPipe {
         bool ready = false;
         size_t chunk = 0;
         uint64_t *d_rk = nullptr;
+        uint8_t *d_prefix = nullptr;
+        int32_t *h_status = nullptr;  // pinned, 3 per op of the largest call so far
+        size_t h_status_cap = 0;
         PipeSlot slot[kPipeSlots];
         std::mutex mu;
     };

@@ -134,6 +134,27 @@ def mul_relin_host(a: torch.Tensor, b: torch.Tensor, rk: torch.Tensor, out: torc
     return out
 
 
+def mul_relin_frames(fa: torch.Tensor, fb: torch.Tensor, rk: torch.Tensor, out: torch.Tensor, status: torch.Tensor, device: int = 0) -> torch.Tensor:
+    """fa, fb: HOST uint8 tensors [n, stride] whose rows start with a structured frame (stride >= frame_bytes()); out: host uint8
+    [n, frame_stride()]; status: host int32 [n]; rk: host words [2,2,3,4096]."""
+    for t in (fa, fb, rk, out, status):
+        if t.is_cuda or not t.is_contiguous():
+            raise ValueError("mul_relin_frames takes contiguous host tensors")
+    if fa.shape != fb.shape or out.shape[1] != frame_stride() or status.numel() != fa.shape[0]:
+        raise ValueError("mul_relin_frames: shape mismatch")
+    _check(_lib.lib().fhe_b200_mul_relin_frames(device, fa.data_ptr(), fb.data_ptr(), fa.shape[1], rk.data_ptr(), out.data_ptr(), fa.shape[0],
+                                                status.data_ptr()))
+    return out
+
+
+def frame_bytes() -> int:
+    return int(_lib.lib().fhe_b200_frame_bytes())
+
+
+def frame_stride() -> int:
+    return int(_lib.lib().fhe_b200_frame_stride())
+
+
 KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt",
                 "k_ext_conv", "k_ks_finish")
 

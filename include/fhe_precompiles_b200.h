@@ -146,6 +146,18 @@ int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk,
  * the three phases of consecutive chunks overlapped; returns when `out` is complete. rk: host words. */
 int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
                                 size_t n);
+/* Same op on SERIALIZED operands. Operand i of an array is the zstd frame at frames + i * stride: the compressed body of a
+ * ciphertext as this library serializes it (a "structured frame": fhe_b200_frame_bytes() = 82,054 bytes, at byte 148 of the
+ * packed `Ciphertext`; what every precompile here returns and what chained calls carry). Frames cross PCIe as they are (5 bytes
+ * per residue instead of 8), are validated and unpacked on the GPU, and result i is written as a frame at
+ * out_frames + i * fhe_b200_frame_stride(). Pin the buffers for full PCIe rate. status[i]: 0 done; 1 an operand is not a
+ * structured frame or fails SEAL's range checks (result undefined: send that call through c_fhe_mul_*); 2 the result is not
+ * representable as a structured frame (transparent ciphertext). Replaces, for a batch, the bincode + SEAL load/save around
+ * Evaluator::multiply + relinearize_inplace in fhe_binary_op (/root/reference/src/fhe.rs:21-30). */
+int32_t fhe_b200_mul_relin_frames(int32_t device, const uint8_t *a_frames, const uint8_t *b_frames, size_t stride, const uint64_t *rk,
+                                  uint8_t *out_frames, size_t n, int32_t *status);
+size_t fhe_b200_frame_bytes(void);
+size_t fhe_b200_frame_stride(void);
 /* Integer-pipe peak of `device` in 1e12 multiply-adds/s, measured by a register-only microbenchmark
  * (wide: 0 mad.lo.u32 [IMAD], 1 mul.wide.u32 [IMAD.WIDE], 2 add.cc+addc, 3 mad.lo+add, 4 mul.wide+add). Denominator of the integer roofline; synchronous. */
 int32_t fhe_b200_int_peak(int32_t device, int32_t wide, double *tera_mads_per_s);

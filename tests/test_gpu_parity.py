@@ -716,3 +716,45 @@ def test_second_device_and_cross_device_batch(dev, keys):
     wm = F.make_ciphertext("i64", bfv.mul_relin(ca, cb, keys.rk)).to_bytes(structured=True)
     res = FHE.run_batch([("mul_cipheri64_cipheri64", packed)] * 24, host_threads=8)
     assert all(st == 0 and out == wm for st, out in res)
+
+
+def test_mul_relin_frames_matches_oracle(dev, keys):
+    """fhe_b200_mul_relin_frames: serialized operands (structured zstd frames) in, structured frames out, through the three-slot
+    pipeline (more ops than one pipeline chunk).  Result frames are byte-identical to the format oracle's frames of the oracle's
+    products; a frame that is not the structured layout and a residue >= q are flagged (status 1) without disturbing neighbours."""
+    import torch
+
+    n, bad_layout, bad_range = 300, 7, 123
+    cts_a, cts_b = random_ct(np.random.default_rng(41), n), random_ct(np.random.default_rng(42), n)  # (constant polynomials are not
+    # written as structured frames by any writer: they take the status-1 route like the libzstd frame below)
+    fb_, fs = dev.frame_bytes(), dev.frame_stride()
+    stride = fs + 32  # any stride >= the frame size works (e.g. whole packed ciphertexts)
+
+    def frames_of(cts):
+        buf = np.zeros((n, stride), dtype=np.uint8)
+        for i in range(n):
+            fr = F.zstd_structured_frame(F.fresh_data_ciphertext(cts[i]).payload())
+            assert fr is not None and len(fr) == fb_
+            buf[i, :fb_] = np.frombuffer(fr, dtype=np.uint8)
+        return buf
+
+    fa, fbuf = frames_of(cts_a), frames_of(cts_b)
+    lib_frame = F.zstd().compress(F.fresh_data_ciphertext(cts_a[bad_layout]).payload())  # a libzstd frame: valid zstd, not structured
+    fa[bad_layout, :] = 0
+    fa[bad_layout, : min(len(lib_frame), stride)] = np.frombuffer(lib_frame[:stride], dtype=np.uint8)
+    over = cts_b[bad_range].copy()
+    over[0, 0, 5] = MODULI[0]  # residue == q0
+    fbuf[bad_range, :fb_] = np.frombuffer(F.zstd_structured_frame(F.fresh_data_ciphertext(over).payload()), dtype=np.uint8)
+
+    ta, tb = torch.from_numpy(fa).pin_memory(), torch.from_numpy(fbuf).pin_memory()
+    out = torch.zeros((n, fs), dtype=torch.uint8).pin_memory()
+    status = torch.full((n,), -1, dtype=torch.int32).pin_memory()
+    rk = torch.from_numpy(keys.rk.view(np.int64))
+    dev.mul_relin_frames(ta, tb, rk, out, status)
+    st = status.numpy()
+    assert st[bad_layout] == 1 and st[bad_range] == 1
+    ok = [i for i in range(n) if i not in (bad_layout, bad_range)]
+    assert (st[ok] == 0).all()
+    for i in ok[:6] + ok[250:262] + ok[-4:]:
+        want = F.zstd_structured_frame(F.fresh_data_ciphertext(bfv.mul_relin(cts_a[i], cts_b[i], keys.rk)).payload())
+        assert out[i, :fb_].numpy().tobytes() == want, f"result frame {i} differs from the oracle's"
