@@ -289,7 +289,6 @@ void build(HostContext &H) {
     const u64 qs[2] = {q0, q1};
     const u64 bsk[3] = {b0, b1, msk};
     const u128 q = (u128)q0 * q1;
-    const u64 punct_q[2] = {q1, q0};  // q / q_l
 
     for (int mi = 0; mi < kNumMod; mi++) {
         const u64 m = kModulus[mi];
@@ -304,10 +303,9 @@ void build(HostContext &H) {
     H.inv_q0_mod_q1 = h_invmod(q0 % q1, q1);
     const u64 inv_punct_q[2] = {H.inv_q1_mod_q0, H.inv_q0_mod_q1};
 
-    // base extension via m_tilde
+    // base extension via m_tilde (integer domain: k_ext_conv needs q as words and -q mod p_k)
     for (int l = 0; l < 2; l++) {
         c.ext_in[l] = mk_shoup(h_mulmod(kMTilde % qs[l], inv_punct_q[l], qs[l]), qs[l]);
-        c.punct_q_mod_mtilde[l] = (u32)(punct_q[l] & 0xffffffffull);
         c.inv_punct_q[l] = mk_shoup(inv_punct_q[l], qs[l]);
     }
     {
@@ -315,68 +313,34 @@ void build(HostContext &H) {
         for (int i = 0; i < 5; i++) x *= 2u - ql * x;
         c.neg_inv_q_mod_mtilde = 0u - x;
     }
-    for (int k = 0; k < 3; k++) {
-        const u64 p = bsk[k];
-        const u64 inv_mt = h_invmod(kMTilde % p, p);
-        const u64 q_mod_p = (u64)(q % p);
-        const u64 inv_q = h_invmod(q_mod_p, p);
-        c.extA[k] = h_mulmod(punct_q[0] % p, inv_mt, p);
-        c.extB[k] = h_mulmod(punct_q[1] % p, inv_mt, p);
-        c.extC[k] = h_mulmod(q_mod_p, inv_mt, p);
-        c.flV[k] = inv_q;
-        c.flA[k] = (p - h_mulmod(punct_q[0] % p, inv_q, p)) % p;
-        c.flB[k] = (p - h_mulmod(punct_q[1] % p, inv_q, p)) % p;
-    }
-    // Shenoy-Kumaresan
-    const u64 punct_B[2] = {b1, b0};
-    c.inv_punct_B[0] = mk_shoup(h_invmod(b1 % b0, b0), b0);
-    c.inv_punct_B[1] = mk_shoup(h_invmod(b0 % b1, b1), b1);
-    const u128 B = (u128)b0 * b1;
-    for (int j = 0; j < 2; j++) {
-        for (int l = 0; l < 2; l++) c.punct_B_mod_q[j][l] = punct_B[j] % qs[l];
-        c.punct_B_mod_msk[j] = punct_B[j] % msk;
-    }
-    c.inv_B_mod_msk = mk_shoup(h_invmod((u64)(B % msk), msk), msk);
-    for (int l = 0; l < 2; l++) {
-        c.B_mod_q[l] = (u64)(B % qs[l]);
-        c.neg_B_mod_q[l] = qs[l] - c.B_mod_q[l];
-    }
-    for (int j = 0; j < 2; j++) {
-        const u64 p = bsk[j], ib = c.inv_punct_B[j].w;
-        c.skV[j] = h_mulmod(c.flV[j], ib, p);
-        c.skA[j] = h_mulmod(c.flA[j], ib, p);
-        c.skB[j] = h_mulmod(c.flB[j], ib, p);
-    }
-    {
-        const u64 ib = c.inv_B_mod_msk.w;
-        c.alK[0] = h_mulmod(c.punct_B_mod_msk[0], ib, msk);
-        c.alK[1] = h_mulmod(c.punct_B_mod_msk[1], ib, msk);
-        c.alK[2] = (msk - h_mulmod(c.flV[2], ib, msk)) % msk;
-        c.alK[3] = (msk - h_mulmod(c.flA[2], ib, msk)) % msk;
-        c.alK[4] = (msk - h_mulmod(c.flB[2], ib, msk)) % msk;
-    }
-    for (int k = 0; k < 3; k++) {
-        const u64 p = bsk[k];
-        c.extAs[k] = shoup_of(c.extA[k], p);
-        c.extBs[k] = shoup_of(c.extB[k], p);
-        c.extCs[k] = shoup_of(c.extC[k], p);
-        c.extNeg[k] = h_mulmod((p - kMTilde % p) % p, c.extC[k], p);
-    }
-    for (int j = 0; j < 2; j++) {
-        c.skVs[j] = shoup_of(c.skV[j], bsk[j]);
-        c.skAs[j] = shoup_of(c.skA[j], bsk[j]);
-        c.skBs[j] = shoup_of(c.skB[j], bsk[j]);
-        for (int l = 0; l < 2; l++) c.pBq[j][l] = mk_shoup(c.punct_B_mod_q[j][l], qs[l]);
-    }
-    for (int i = 0; i < 5; i++) c.alKs[i] = shoup_of(c.alK[i], msk);
     c.q_w[0] = (u32)(u64)q;
     c.q_w[1] = (u32)((u64)q >> 32);
     c.q_w[2] = (u32)(u64)(q >> 64);
-    for (int j = 0; j < 2; j++) c.skD[j] = (u32)(msk - bsk[j]);
-    c.nib = mk_shoup((msk - c.inv_B_mod_msk.w) % msk, msk);
+    u64 inv_q_mod[3];  // q^-1 mod p_k  (fast_floor)
+    for (int k = 0; k < 3; k++) {
+        const u64 p = bsk[k];
+        const u64 q_mod_p = (u64)(q % p);
+        inv_q_mod[k] = h_invmod(q_mod_p, p);
+        c.extNeg[k] = (p - q_mod_p) % p;
+    }
+    // Shenoy-Kumaresan, merged with fast_floor's last step (devconsts.h)
+    const u64 punct_B[2] = {b1, b0};
+    const u64 inv_punct_B[2] = {h_invmod(b1 % b0, b0), h_invmod(b0 % b1, b1)};  // (B/b_j)^-1 mod b_j
+    const u128 B = (u128)b0 * b1;
+    const u64 inv_B_mod_msk = h_invmod((u64)(B % msk), msk);
+    for (int j = 0; j < 2; j++) {
+        c.skV[j] = h_mulmod(inv_q_mod[j], inv_punct_B[j], bsk[j]);
+        c.skVs[j] = shoup_of(c.skV[j], bsk[j]);
+        c.skD[j] = (u32)(msk - bsk[j]);
+        for (int l = 0; l < 2; l++) c.pBq[j][l] = mk_shoup(punct_B[j] % qs[l], qs[l]);
+    }
+    c.alK2 = (msk - h_mulmod(inv_q_mod[2], inv_B_mod_msk, msk)) % msk;
+    c.alK2s = shoup_of(c.alK2, msk);
+    c.nib = mk_shoup((msk - inv_B_mod_msk) % msk, msk);
     for (int l = 0; l < 2; l++) {
-        c.Bq[l] = mk_shoup(c.B_mod_q[l], qs[l]);
-        c.nBq[l] = mk_shoup(c.neg_B_mod_q[l], qs[l]);
+        const u64 bq = (u64)(B % qs[l]);
+        c.Bq[l] = mk_shoup(bq, qs[l]);
+        c.nBq[l] = mk_shoup(qs[l] - bq, qs[l]);
     }
     // key switching
     c.half_P = P >> 1;

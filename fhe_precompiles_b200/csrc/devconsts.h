@@ -22,41 +22,24 @@ struct DevConsts {
     Shoup ninv_w[kNumMod];
     Shoup ninv_t_w[kNumMod];
 
-    // ---- BEHZ base extension q -> Bsk via m_tilde (RNSTool::fastbconv_m_tilde + sm_mrq)
-    Shoup ext_in[2];              // m_tilde * (q/q_l)^-1 mod q_l
-    u32 punct_q_mod_mtilde[2];    // (q/q_l) mod 2^32
-    u32 neg_inv_q_mod_mtilde;     // -q^-1 mod 2^32
-    u64 extA[3], extB[3], extC[3];  // per Bsk prime k: (q/q_0)*m~^-1, (q/q_1)*m~^-1, q*m~^-1 (mod p_k)
+    // ---- BEHZ base extension q -> Bsk via m_tilde (RNSTool::fastbconv_m_tilde + sm_mrq), integer domain (k_ext_conv)
+    Shoup ext_in[2];            // m_tilde * (q/q_l)^-1 mod q_l
+    u32 neg_inv_q_mod_mtilde;   // -q^-1 mod 2^32
+    u32 q_w[3];                 // q = q0*q1 as three 32-bit words (q_w[2] < 2^8)
+    u64 extNeg[3];              // -q mod p_k: added when the centred m~ residue is negative
 
-    // ---- fast_floor (input already multiplied by t)
-    Shoup inv_punct_q[2];        // (q/q_l)^-1 mod q_l
-    u64 flV[3], flA[3], flB[3];  // f_k = v_k*flV + tmp0*flA + tmp1*flB mod p_k
-                                 //   flV = q^-1, flA = -(q/q_0) q^-1, flB = -(q/q_1) q^-1
-
-    // merged forms used by k_floor_sk (one reduction per output instead of one per SEAL step):
-    //   tb_j  = [f_j * (B/b_j)^-1]_{b_j}      = v_bj*skV[j] + tmp0*skA[j] + tmp1*skB[j]            (j = 0,1)
-    //   alpha = [(h - f_msk) * B^-1]_{m_sk}    = tb0*alK[0] + tb1*alK[1] + v_msk*alK[2] + tmp0*alK[3] + tmp1*alK[4]
-    u64 skV[2], skA[2], skB[2];
-    u64 alK[5];
-
-    // Shoup quotients of the merged constants (k_ext_conv / k_floor_sk evaluate each output as one ShoupSum)
-    u64 extAs[3], extBs[3], extCs[3];
-    u64 extNeg[3];  // (p_k - m~) * extC[k] mod p_k: the correction term when the m~ residue is negative
-    u64 skVs[2], skAs[2], skBs[2];
-    u64 alKs[5];
-    u32 q_w[3];           // q = q0*q1 as three 32-bit words (q_w[2] < 2^8)
-    u32 skD[2];           // m_sk - b_j > 0: with every Bsk prime 2^61 - c, b_{j} == -skD[j] (mod m_sk)
-    Shoup nib;            // -(B^-1) mod m_sk
-    Shoup pBq[2][2];      // punct_B_mod_q [j][l]
-    Shoup Bq[2], nBq[2];  // B_mod_q, neg_B_mod_q
-
-    // ---- fastbconv_sk
-    Shoup inv_punct_B[2];      // (B/b_j)^-1 mod b_j
-    u64 punct_B_mod_q[2][2];   // [j][l]
-    u64 punct_B_mod_msk[2];
-    Shoup inv_B_mod_msk;
-    u64 B_mod_q[2];      // prod(B) mod q_l
-    u64 neg_B_mod_q[2];  // q_l - prod(B) mod q_l
+    // ---- fast_floor + fastbconv_sk (input already multiplied by t), constants of SEAL's steps merged (k_floor_sk):
+    //   t_l   = v_l (q/q_l)^-1 mod q_l,   y0 = t0 q1 + t1 q0 (integer)
+    //   tb_j  = [(v_bj - y0) skV[j]]_{b_j},            skV[j] = q^-1 (B/b_j)^-1 mod b_j
+    //   alpha = [w nib + (v_msk - y0) alK2]_{m_sk},    w = tb0 skD[1] + tb1 skD[0],  nib = -(B^-1),  alK2 = -(q^-1 B^-1)
+    //   out_l = [tb0 pBq[0][l] + tb1 pBq[1][l] -/+ |alpha| Bq[l]]_{q_l}
+    Shoup inv_punct_q[2];  // (q/q_l)^-1 mod q_l
+    u64 skV[2], skVs[2];   // value and Shoup quotient
+    u64 alK2, alK2s;
+    u32 skD[2];            // m_sk - b_j > 0: with every Bsk prime 2^61 - c, b_j == -skD[j] (mod m_sk)
+    Shoup nib;
+    Shoup pBq[2][2];       // (B/b_j) mod q_l   [j][l]
+    Shoup Bq[2], nBq[2];   // prod(B) mod q_l and its negation
 
     // ---- key switching (switch_key_inplace, BFV branch)
     Shoup inv_P_mod_q[2];

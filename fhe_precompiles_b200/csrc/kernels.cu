@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
             const u64 xs = vsk + SK::two_q - (y61 + (u64)(yk * (u32)SK::kC));
             ShoupSum<SK> s;  // two terms < 1.5 q each
             s.add(wr, kc.nib.w, kc.nib.ws);
-            s.add(xs, kc.alK[2], kc.alKs[2]);
+            s.add(xs, kc.alK2, kc.alK2s);
             alpha = canon_k32<SK>(s.value());
         }
         bool neg = alpha > (SK::q >> 1);
