@@ -144,7 +144,6 @@ __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws) {
 // whole sum one reduction.  Everything is mod 2^64 (wrap-around in either accumulator is harmless) and the result is
 // exact as long as the true value sum_k (x_k w_k - H_k q) stays below 2^64:
 //   add      exact quotient, any 64-bit x : term in [0, q + x q / 2^64)                 FMA pipe 5 wide + 2 low
-//   add32    the same for x < 2^32                                                       3 wide + 1 low
 //   add_a1   drops the x_lo*ws_lo partial product (H low by <= 2): adds another 2q       4 wide + 2 low
 // value(): one wide + one low multiply.  (The compiler's 128-bit mad/madc + fold sequence for the same sum issued twice
 // the multiplier cycles: duplicated partial products for the carries and multiplications by a zero high word.)
@@ -178,16 +177,6 @@ struct ShoupSum {
         unpack64(mul_wide(xl, sh), vl, vh);
         hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh;
         low_product(xl, xh, w);
-    }
-    __device__ __forceinline__ void add32(u32 x, u64 w, u64 ws) {
-        u32 sl, sh, tl, th, vl, vh, wl, wh, al, ah;
-        unpack64(ws, sl, sh);
-        unpack64(mul_wide(x, sl), tl, th);
-        unpack64(mad_wide(x, sh, pack64(th, 0)), vl, vh);
-        hs += vh;
-        unpack64(w, wl, wh);
-        unpack64(mad_wide(x, wl, lo), al, ah);
-        lo = pack64(al, mad_lo(x, wh, ah));
     }
     // sum - (sum H) q  =  sum + (sum H) c - ((sum H) << B)   (mod 2^64)
     __device__ __forceinline__ u64 value() const {
