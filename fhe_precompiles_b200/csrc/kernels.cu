@@ -366,19 +366,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__
 // p_k = 2^61 - c_k needs only base + m c_k: two low multiplies per auxiliary limb instead of three Shoup products.
 __global__ void __launch_bounds__(256) k_ext_conv(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf,
                                                   size_t n_ops) {
-    const size_t total = n_ops * 4 * kN;  // (op, poly a0 a1 b0 b1, coefficient)
+    const size_t total = n_ops * 4 * (kN / 2);  // (op, poly a0 a1 b0 b1, coefficient pair): 16-byte loads and stores
     for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (size_t)gridDim.x * 256) {
-        const size_t op = g / (4 * kN);
-        const int p = (int)((g / kN) & 3), i = (int)(g & (kN - 1));
+        const size_t op = g / (4 * (kN / 2));
+        const int p = (int)((g / (kN / 2)) & 3), i = 2 * (int)(g & (kN / 2 - 1));
         const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
-        u64 base;
-        u32 m;
-        bool neg;
-        ext_shared(ct[i], ct[kN + i], base, m, neg);
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(ct + i), x1 = *reinterpret_cast<const ulonglong2 *>(ct + kN + i);
+        u64 base0, base1;
+        u32 m0, m1;
+        bool neg0, neg1;
+        ext_shared(x0.x, x1.x, base0, m0, neg0);
+        ext_shared(x0.y, x1.y, base1, m1, neg1);
         u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN + i;
-        dst[0] = ext_limb<0>(base, m, neg);
-        dst[kN] = ext_limb<1>(base, m, neg);
-        dst[2 * kN] = ext_limb<2>(base, m, neg);
+        *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(ext_limb<0>(base0, m0, neg0), ext_limb<0>(base1, m1, neg1));
+        *reinterpret_cast<ulonglong2 *>(dst + kN) = make_ulonglong2(ext_limb<1>(base0, m0, neg0), ext_limb<1>(base1, m1, neg1));
+        *reinterpret_cast<ulonglong2 *>(dst + 2 * kN) = make_ulonglong2(ext_limb<2>(base0, m0, neg0), ext_limb<2>(base1, m1, neg1));
     }
 }
 template <int EI>
@@ -1147,7 +1149,7 @@ static int ext_split_mode() {
 bool ext_split() { return ext_split_mode() != 0; }
 cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    k_ext_conv<<<eltwise_grid(n_ops * 4 * kN, 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
+    k_ext_conv<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
