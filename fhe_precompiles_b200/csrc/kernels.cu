@@ -473,19 +473,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restri
 // K8: fast_floor + fastbconv_sk   (SEAL RNSTool::fast_floor, RNSTool::fastbconv_sk), per coefficient
 //   tens [op][3][5][N] (x t, any representative in [0, 2q))  ->  c3 [op][3][2][N]
 // =====================================================================================
-__global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
+__device__ __forceinline__ void floor_sk_coeff(u64 v0, u64 v1, u64 vb0, u64 vb1, u64 vsk, u64 &o0, u64 &o1) {
     using Q0 = Mod<MQ0>;
     using Q1 = Mod<MQ1>;
     using B0 = Mod<MB0>;
     using B1 = Mod<MB1>;
     using SK = Mod<MSK>;
-    size_t total = n_ops * 3 * kN;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
-        size_t opp = g / kN;  // op*3 + poly
-        int i = (int)(g % kN);
-        const u64 *in = tens + opp * 5 * kN + i;
-        u64 v0 = in[0 * kN], v1 = in[1 * kN], vb0 = in[2 * kN], vb1 = in[3 * kN], vsk = in[4 * kN];
+    {
         // fast_floor: q-part -> Bsk, f_k = (v_k - conv_k) * q^-1 mod p_k  (constants merged)
         u64 t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
         u64 t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
@@ -517,14 +511,13 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
         }
         bool neg = alpha > (SK::q >> 1);
         u64 am = neg ? SK::q - alpha : alpha;
-        u64 *out = c3 + opp * 2 * kN + i;
         {  // 36-bit targets: approximate quotients, three terms < 3.2 q each (< 2^40)
             const Shoup kb = neg ? kc.Bq[0] : kc.nBq[0];
             ShoupSum<Q0> s;
             s.add_a1(tb0, kc.pBq[0][0].w, kc.pBq[0][0].ws);
             s.add_a1(tb1, kc.pBq[1][0].w, kc.pBq[1][0].ws);
             s.add_a1(am, kb.w, kb.ws);
-            out[0] = canon_k32<Q0>(s.value());
+            o0 = canon_k32<Q0>(s.value());
         }
         {
             const Shoup kb = neg ? kc.Bq[1] : kc.nBq[1];
@@ -532,8 +525,24 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
             s.add_a1(tb0, kc.pBq[0][1].w, kc.pBq[0][1].ws);
             s.add_a1(tb1, kc.pBq[1][1].w, kc.pBq[1][1].ws);
             s.add_a1(am, kb.w, kb.ws);
-            out[kN] = canon_k32<Q1>(s.value());
+            o1 = canon_k32<Q1>(s.value());
         }
+    }
+}
+__global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
+    const size_t total = n_ops * 3 * (kN / 2);  // (op, poly, coefficient pair): 16-byte loads and stores
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const size_t opp = g / (kN / 2);  // op*3 + poly
+        const int i = 2 * (int)(g % (kN / 2));
+        const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(tens + opp * 5 * kN + i);
+        const ulonglong2 v0 = in[0], v1 = in[kN / 2], vb0 = in[2 * (kN / 2)], vb1 = in[3 * (kN / 2)], vsk = in[4 * (kN / 2)];
+        u64 ax, ay, bx, by;  // limb q0 / q1 of the two coefficients
+        floor_sk_coeff(v0.x, v1.x, vb0.x, vb1.x, vsk.x, ax, bx);
+        floor_sk_coeff(v0.y, v1.y, vb0.y, vb1.y, vsk.y, ay, by);
+        ulonglong2 *out = reinterpret_cast<ulonglong2 *>(c3 + opp * 2 * kN + i);
+        out[0] = make_ulonglong2(ax, ay);
+        out[kN / 2] = make_ulonglong2(bx, by);
     }
 }
 
@@ -1210,7 +1219,7 @@ cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64
 }
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    k_floor_sk<<<eltwise_grid(n_ops * 3 * kN, 256), 256, 0, s>>>(tens, c3, n_ops);
+    k_floor_sk<<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
