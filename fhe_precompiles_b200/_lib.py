@@ -83,6 +83,12 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_encrypt.restype = i32
     L.fhe_b200_decrypt.argtypes = [i32, vp, vp, vp, sz, vp]
     L.fhe_b200_decrypt.restype = i32
+    L.fhe_b200_decrypt_checked.argtypes = [i32, vp, vp, vp, vp, sz, vp]
+    L.fhe_b200_decrypt_checked.restype = i32
+    L.fhe_b200_data_type_kind.argtypes = [ctypes.c_char_p]
+    L.fhe_b200_data_type_kind.restype = i32
+    L.fhe_b200_set_chunk_ops.argtypes = [i64]
+    L.fhe_b200_set_chunk_ops.restype = i64
     L.fhe_b200_mul_relin_host.argtypes = [i32, vp, vp, vp, vp, sz]
     L.fhe_b200_mul_relin_host.restype = i32
     L.fhe_b200_mul_relin_frames.argtypes = [i32, vp, vp, sz, vp, vp, sz, vp]

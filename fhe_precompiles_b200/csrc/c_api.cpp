@@ -301,8 +301,27 @@ int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *pla
 int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, void *stream) {
     DEV_GUARD(Engine::get().decrypt_device(device, ct, sk, plain, n, (cudaStream_t)stream));
 }
+int32_t fhe_b200_decrypt_checked(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, int32_t *exhausted, size_t n,
+                                 void *stream) {
+    DEV_GUARD(Engine::get().decrypt_device(device, ct, sk, plain, n, (cudaStream_t)stream, exhausted));
+}
 int32_t fhe_b200_bfly_peak(int32_t device, int32_t mod, double *giga_bfly_per_s) {
     DEV_GUARD(device_context(device); cuda_throw(measure_bfly_peak(mod, giga_bfly_per_s), "bfly_peak"));
+}
+int32_t fhe_b200_data_type_kind(const char *data_type) {
+    if (!data_type) return -1;
+    const std::string dt(data_type);
+    for (int k = 0; k < 4; k++)
+        if (data_type_matches(dt, (Kind)k)) return k;
+    return -1;
+}
+int64_t fhe_b200_set_chunk_ops(int64_t ops) {
+    try {
+        return (int64_t)Engine::get().set_chunk_ops(ops);
+    } catch (const std::exception &e) {
+        set_error(e.what());
+        return -1;
+    }
 }
 void fhe_b200_set_fused(int32_t on) {
     try {

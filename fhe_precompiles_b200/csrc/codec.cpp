@@ -782,15 +782,28 @@ int32_t decode_private_key(Span in, uint64_t *sk_words) {
 }
 
 // ---------------------------------------------------------------- scalar encoders (sunscreen types)
+// sunscreen's runtime compares every argument's Type (name, version, is_encrypted) with the compiled program's signature and
+// fails with an argument-mismatch error otherwise (-> code 7, fhe.rs:28).  The exact type names are pinned by no fixture of
+// the reference, so the rule lives in this one table: a data_type belongs to a kind iff the LAST PATH
+// SEGMENT of its name is exactly one of the kind's spellings -- Unsigned<1> never passes for Unsigned<4>, and a foreign
+// type never passes for anything.
 bool data_type_matches(const std::string &dt, Kind kind) {
-    size_t c1 = dt.find(',');
+    const size_t c1 = dt.find(',');
     if (c1 == std::string::npos) return false;
-    size_t c2 = dt.rfind(',');
-    std::string name = dt.substr(0, c1);
-    std::string enc = dt.substr(c2 + 1);
-    if (enc != "true") return false;
-    const char *want = kind == Kind::I64 ? "Signed" : kind == Kind::Frac64 ? "Fractional" : "Unsigned";
-    return name.find(want) != std::string::npos;
+    const size_t c2 = dt.rfind(',');
+    if (c2 == c1 || dt.compare(c2 + 1, std::string::npos, "true") != 0) return false;
+    size_t seg = dt.rfind("::", c1);
+    seg = (seg == std::string::npos || seg > c1) ? 0 : seg + 2;
+    const std::string last = dt.substr(seg, c1 - seg);
+    static const char *const kNames[4][2] = {
+        {"Unsigned<4>", "Unsigned256"},   // Kind::U256
+        {"Unsigned<1>", "Unsigned64"},    // Kind::U64
+        {"Signed", nullptr},              // Kind::I64
+        {"Fractional<64>", nullptr},      // Kind::Frac64
+    };
+    for (const char *n : kNames[(int)kind])
+        if (n && last == n) return true;
+    return false;
 }
 
 static uint64_t be_u64(const uint8_t *p) {

@@ -111,7 +111,42 @@ __global__ void __launch_bounds__(256) k_ct_unpack(const uint8_t *payloads, cons
     if (threadIdx.x == 0 && bad) status[j] = kJobFallback;
 }
 
-// structured frames: the host has verified every header byte; literals are at two fixed places of the frame
+// The 35 bytes of a structured frame that do not depend on the ciphertext (zstd_pack40 layout, codec.cpp): frame header,
+// block A header + raw-literals header + its one sequence, word-block header + raw-literals header, sequence count + tables.
+// One routine writes them (k_ct_pack40) or compares them (k_unpack40): a frame whose fixed bytes differ is not a structured
+// frame -- any zstd decoder would read something else or reject it -- and goes back to the host path.
+template <bool kWrite>
+__device__ __forceinline__ bool frame40_fixed(uint8_t *f) {
+    bool ok = true;
+    const auto put = [&](size_t at, uint8_t v) {
+        if (kWrite) f[at] = v;
+        else ok = ok && f[at] == v;
+    };
+    const uint8_t h[9] = {0x28, 0xB5, 0x2F, 0xFD, 0xA0, (uint8_t)kCtPayloadBytes, (uint8_t)(kCtPayloadBytes >> 8),
+                          (uint8_t)(kCtPayloadBytes >> 16), (uint8_t)(kCtPayloadBytes >> 24)};  // magic, single segment, content size
+    for (int k = 0; k < 9; k++) put(k, h[k]);
+    const uint32_t bh = (2u << 1) | ((2 + 110 + 7) << 3);  // block A: compressed block of 2 + 110 + 7 bytes
+    put(9, (uint8_t)bh), put(10, (uint8_t)(bh >> 8)), put(11, (uint8_t)(bh >> 16));
+    const uint32_t lh = (1u << 2) | (110u << 4);  // 110 raw literals
+    put(12, (uint8_t)lh), put(13, (uint8_t)(lh >> 8));
+    const uint32_t bits = (110 - 64) | (3u << 6) | (1u << 9);
+    const uint8_t sq[7] = {0x01, 0x54, 25, 3, 0, (uint8_t)bits, (uint8_t)(bits >> 8)};  // one sequence: LL 110, ML 3, offset 8
+    for (int k = 0; k < 7; k++) put(14 + 110 + k, sq[k]);
+    constexpr uint32_t m = (uint32_t)kCodecCtWords - 2, body = 3 + 5 * m + 2 + 5;  // word block: 16382 words, last block
+    const uint32_t bh2 = 1u | (2u << 1) | (body << 3);
+    const size_t g = 9 + 122;
+    put(g, (uint8_t)bh2), put(g + 1, (uint8_t)(bh2 >> 8)), put(g + 2, (uint8_t)(bh2 >> 16));
+    const uint32_t lh2 = (3u << 2) | ((5 * m) << 4);
+    put(g + 3, (uint8_t)lh2), put(g + 4, (uint8_t)(lh2 >> 8)), put(g + 5, (uint8_t)(lh2 >> 16));
+    const size_t t = g + 6 + 5 * (size_t)m;
+    put(t, (uint8_t)((m >> 8) + 0x80)), put(t + 1, (uint8_t)m);
+    const uint8_t tail[5] = {0x54, 5, 0, 0, 0x01};  // RLE tables, (LL 5, ML 3, repeat offset 1), end marker
+    for (int k = 0; k < 5; k++) put(t + 2 + k, tail[k]);
+    return ok;
+}
+
+// structured frames: literals are at two fixed places of the frame; block (j, 0) also verifies the frame's length and every
+// fixed byte, the other blocks the residues
 __global__ void __launch_bounds__(256) k_unpack40(const uint8_t *frames, const CodecJob *jobs, int32_t *status, const uint8_t *prefix,
                                                   u64 *dst_a, u64 *dst_b) {
     const int j = blockIdx.x;
@@ -124,6 +159,8 @@ __global__ void __launch_bounds__(256) k_unpack40(const uint8_t *frames, const C
     int mybad = 0;
     const uint8_t *la = f + 9 + 3 + 2;  // block A literals: prefix, word 0 (8 bytes), low 5 bytes of word 1
     if (blockIdx.y == 0 && threadIdx.x < kCtPrefixBytes && threadIdx.x != 77 && la[threadIdx.x] != prefix[threadIdx.x]) mybad = 1;
+    if (blockIdx.y == 0 && threadIdx.x == 128 && (job.src_len != kPackedFrameBytes || !frame40_fixed<false>(const_cast<uint8_t *>(f))))
+        mybad = 1;
     u64 *dst = (job.operand ? dst_b : dst_a) + (size_t)job.slot * kCodecCtWords;
     const uint8_t *lw = f + 9 + (3 + 2 + 110 + 7) + 3 + 3;  // literals of words 2..
     const int lo = blockIdx.y * kWordsPerBlock;
@@ -152,29 +189,7 @@ __global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *fr
     const u64 *w = words + (size_t)j * kCodecCtWords;
     uint8_t *f = frames + (size_t)j * kPackedFrameStride;
     if (blockIdx.y == 0 && threadIdx.x == 0) {
-        // frame header: magic, single segment + 4-byte content size
-        const uint8_t h[9] = {0x28, 0xB5, 0x2F, 0xFD, 0xA0, (uint8_t)kCtPayloadBytes, (uint8_t)(kCtPayloadBytes >> 8),
-                              (uint8_t)(kCtPayloadBytes >> 16), (uint8_t)(kCtPayloadBytes >> 24)};
-        for (int k = 0; k < 9; k++) f[k] = h[k];
-        // block A: header (compressed block, 2 + 110 + 7 bytes), raw literal header (110), ... , one sequence
-        const uint32_t bh = (2u << 1) | ((2 + 110 + 7) << 3);
-        f[9] = (uint8_t)bh, f[10] = (uint8_t)(bh >> 8), f[11] = (uint8_t)(bh >> 16);
-        const uint32_t lh = (1u << 2) | (110u << 4);
-        f[12] = (uint8_t)lh, f[13] = (uint8_t)(lh >> 8);
-        const uint32_t bits = (110 - 64) | (3u << 6) | (1u << 9);
-        const uint8_t sq[7] = {0x01, 0x54, 25, 3, 0, (uint8_t)bits, (uint8_t)(bits >> 8)};
-        for (int k = 0; k < 7; k++) f[14 + 110 + k] = sq[k];
-        // word block: 16382 words
-        constexpr uint32_t m = (uint32_t)kCodecCtWords - 2, body = 3 + 5 * m + 2 + 5;
-        const uint32_t bh2 = 1u | (2u << 1) | (body << 3);
-        uint8_t *g = f + 9 + 122;
-        g[0] = (uint8_t)bh2, g[1] = (uint8_t)(bh2 >> 8), g[2] = (uint8_t)(bh2 >> 16);
-        const uint32_t lh2 = (3u << 2) | ((5 * m) << 4);
-        g[3] = (uint8_t)lh2, g[4] = (uint8_t)(lh2 >> 8), g[5] = (uint8_t)(lh2 >> 16);
-        uint8_t *t = g + 6 + 5 * m;
-        t[0] = (uint8_t)((m >> 8) + 0x80), t[1] = (uint8_t)m;
-        const uint8_t tail[5] = {0x54, 5, 0, 0, 0x01};
-        for (int k = 0; k < 5; k++) t[2 + k] = tail[k];
+        frame40_fixed<true>(f);
         u64 diff = 0;
         for (int k = 1; k < 16; k++) diff |= w[k] ^ w[0];
         constant_flag[j] = diff == 0;

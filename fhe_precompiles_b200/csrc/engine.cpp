@@ -334,22 +334,93 @@ const uint64_t *Engine::network_sk(int device, Span net_pri) {
 }
 
 // ---------------------------------------------------------------- scratch arenas
-uint64_t *Engine::scratch(int device, size_t ops) {
-    std::lock_guard<std::mutex> lk(arena_mu_);
-    if (arenas_.size() < (size_t)n_devices_) arenas_.resize((size_t)n_devices_);
-    Arena &a = arenas_[(size_t)device];
-    if (a.ops < ops) {
-        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
-        if (a.p) {
-            cuda_throw(cudaDeviceSynchronize(), "sync before scratch regrow");
-            cudaFree(a.p);
-            a.p = nullptr;
+// One arena per (device, stream): two callers on different streams of one GPU never share scratch, and work already
+// enqueued on a stream keeps its arena until that stream has drained (a regrow or an eviction synchronises the owning stream
+// first).  A lease pins the arena while its holder is still enqueueing; at most FHE_B200_SCRATCH_ARENAS (default 4) idle arenas
+// stay allocated per device (a 4,096-op arena is 7 GB).
+Engine::StreamState *Engine::lease_scratch(int device, cudaStream_t s, size_t ops) {
+    std::unique_lock<std::mutex> lk(arena_mu_);
+    StreamState *st = nullptr;
+    for (auto &x : stream_states_)
+        if (x->device == device && x->stream == s) st = x.get();
+    if (!st) {
+        const size_t cap = env_size("FHE_B200_SCRATCH_ARENAS", 4);
+        for (;;) {  // evict idle arenas of this device, least recently used first
+            size_t have = 0;
+            long victim = -1;
+            for (size_t i = 0; i < stream_states_.size(); i++) {
+                StreamState &x = *stream_states_[i];
+                if (x.device != device) continue;
+                have++;
+                if (x.users == 0 && (victim < 0 || x.last_use < stream_states_[(size_t)victim]->last_use)) victim = (long)i;
+            }
+            if (have < cap || victim < 0) break;
+            StreamState &v = *stream_states_[(size_t)victim];
+            cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+            if (cudaStreamSynchronize(v.stream) != cudaSuccess) {  // the caller may have destroyed that stream since
+                cudaGetLastError();
+                cuda_throw(cudaDeviceSynchronize(), "sync before scratch eviction");
+            }
+            free_stream_state(v);
+            stream_states_.erase(stream_states_.begin() + victim);
         }
-        cuda_throw(cudaMalloc((void **)&a.p, ops * kScratchLimbsPerOp * kN * 8), "cudaMalloc(scratch)");
-        a.ops = ops;
+        stream_states_.emplace_back(new StreamState());
+        st = stream_states_.back().get();
+        st->device = device;
+        st->stream = s;
     }
-    return a.p;
+    // a regrow waits for other holders on the same stream (two threads driving one stream) and for the stream itself
+    arena_cv_.wait(lk, [&] { return st->ops >= ops || st->users == 0; });
+    if (st->ops < ops) {
+        cuda_throw(cudaSetDevice(device), "cudaSetDevice");
+        if (st->p) {
+            cuda_throw(cudaStreamSynchronize(s), "sync before scratch regrow");
+            cudaFree(st->p);
+            st->p = nullptr;
+            st->ops = 0;
+        }
+        cuda_throw(cudaMalloc((void **)&st->p, ops * kScratchLimbsPerOp * kN * 8), "cudaMalloc(scratch)");
+        st->ops = ops;
+    }
+    st->users++;
+    st->last_use = ++arena_clock_;
+    return st;
 }
+void Engine::release_scratch(StreamState *st) {
+    {
+        std::lock_guard<std::mutex> lk(arena_mu_);
+        st->users--;
+    }
+    arena_cv_.notify_all();
+}
+void Engine::free_stream_state(StreamState &v) {
+    if (v.p) cudaFree(v.p);
+    v.p = nullptr;
+    ForkSet &F = v.forks;
+    if (F.ready) {
+        for (int i = 0; i < kForkStreams; i++) {
+            if (F.scratch[i]) cudaFree(F.scratch[i]);
+            cudaStreamDestroy(F.stream[i]);
+            cudaEventDestroy(F.join[i]);
+        }
+        cudaEventDestroy(F.fork);
+        F.ready = false;
+    }
+}
+size_t Engine::set_chunk_ops(long long ops) {
+    std::lock_guard<std::mutex> lk(arena_mu_);
+    const size_t prev = chunk_ops_;
+    if (ops > 0) chunk_ops_ = (size_t)ops;
+    return prev;
+}
+namespace {
+struct ScratchLease {
+    Engine *e;
+    Engine::StreamState *st;
+    void (Engine::*rel)(Engine::StreamState *);
+    ~ScratchLease() { (e->*rel)(st); }
+};
+}  // namespace
 
 // ---------------------------------------------------------------- device-resident batched ops
 // scratch layout for a chunk of c ops: tens [c][15][N] | c3 [c][6][N] | ks [c][6][N]
@@ -414,9 +485,10 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
         TIMED(2, launch_relin_ks(c3, rk, m.ks, c, s), "relin_ks");
     } else {
         TIMED(6, launch_digit_ntt(c3, m.dig, c, s), "digit_ntt");
-        // the fused tail runs the three moduli one after the other in two CTAs per op: right once the batch fills the GPU,
-        // three times the critical path for a single call
-        if (ks_finish_fused() && c >= 148) {
+        // the fused tail runs the three moduli one after the other in two CTAs per op: right once 2c CTAs come close to the
+        // 296 resident ones (the 128-op chunks of the host-buffer pipelines included), three times the critical path for a
+        // single call or a small tile
+        if (ks_finish_fused() && c >= 96) {
             TIMED(9, launch_ks_finish(m.dig, rk, c3, out, c, s), "ks_finish");
             return;
         }
@@ -425,16 +497,12 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
     TIMED(3, launch_relin_finish(c3, m.ks, out, c, s), "relin_finish");
 }
 
-void Engine::mul_relin_forked(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
+void Engine::mul_relin_forked(StreamState *st, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
                               cudaStream_t s) {
-    {
-        std::lock_guard<std::mutex> lk(arena_mu_);
-        if (forks_.size() < (size_t)n_devices_) forks_.resize((size_t)n_devices_);
-    }
-    ForkSet &F = forks_[(size_t)device];
+    ForkSet &F = st->forks;  // owned by this (device, stream); the lease keeps it alive while we enqueue
     const size_t sub = subchunk_ops_;
     if (!F.ready || F.ops < sub) {
-        cuda_throw(cudaDeviceSynchronize(), "sync before fork-set rebuild");
+        cuda_throw(cudaStreamSynchronize(s), "sync before fork-set rebuild");
         for (int i = 0; i < kForkStreams; i++) {
             if (!F.ready) {
                 cuda_throw(cudaStreamCreateWithFlags(&F.stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
@@ -465,13 +533,16 @@ void Engine::mul_relin_forked(int device, const uint64_t *a, const uint64_t *b, 
 
 void Engine::mul_relin(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
                        cudaStream_t s) {
+    if (n == 0) return;
     device_context(device);
-    if (subchunk_ops_ && n > subchunk_ops_) {
-        mul_relin_forked(device, a, b, rk, out, n, s);
+    const bool forked = subchunk_ops_ && n > subchunk_ops_;
+    const size_t chunk = forked ? 0 : (chunk_ops_ < n ? chunk_ops_ : n);
+    ScratchLease lease{this, lease_scratch(device, s, chunk), &Engine::release_scratch};
+    if (forked) {
+        mul_relin_forked(lease.st, a, b, rk, out, n, s);
         return;
     }
-    const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    ScratchMap m(scratch(device, chunk), chunk);
+    ScratchMap m(lease.st->p, chunk);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
         enqueue_mul(a + off * kCtWords, b + off * kCtWords, m, c, s, timing_);
@@ -479,9 +550,11 @@ void Engine::mul_relin(int device, const uint64_t *a, const uint64_t *b, const u
     }
 }
 void Engine::multiply(int device, const uint64_t *a, const uint64_t *b, uint64_t *out3, size_t n, cudaStream_t s) {
+    if (n == 0) return;
     device_context(device);
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    ScratchMap m(scratch(device, chunk), chunk);
+    ScratchLease lease{this, lease_scratch(device, s, chunk), &Engine::release_scratch};
+    ScratchMap m(lease.st->p, chunk);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
         ScratchMap mm = m;
@@ -490,9 +563,11 @@ void Engine::multiply(int device, const uint64_t *a, const uint64_t *b, uint64_t
     }
 }
 void Engine::relinearize(int device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, cudaStream_t s) {
+    if (n == 0) return;
     device_context(device);
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    ScratchMap m(scratch(device, chunk), chunk);
+    ScratchLease lease{this, lease_scratch(device, s, chunk), &Engine::release_scratch};
+    ScratchMap m(lease.st->p, chunk);
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
         enqueue_relin(c3 + off * 6 * kN, rk, out + off * kCtWords, m, c, s, false);
@@ -1116,20 +1191,25 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
 void Engine::encrypt_device(int device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
                             cudaStream_t s) {
     device_context(device);
+    if (n == 0) return;
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    uint64_t *encbuf = scratch(device, chunk);
+    ScratchLease lease{this, lease_scratch(device, s, chunk), &Engine::release_scratch};
+    uint64_t *encbuf = lease.st->p;
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
-        cuda_throw(launch_encrypt(pk, plain + off * kN, seeds + off, encbuf, ct + off * kCtWords, c, s), "encrypt");
+        cuda_throw(launch_encrypt(pk, plain + off * kN, seeds + off * 8, encbuf, ct + off * kCtWords, c, s), "encrypt");
     }
 }
-void Engine::decrypt_device(int device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, cudaStream_t s) {
+void Engine::decrypt_device(int device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, cudaStream_t s,
+                            int32_t *exhausted) {
     device_context(device);
+    if (n == 0) return;
     const size_t chunk = chunk_ops_ < n ? chunk_ops_ : n;
-    uint64_t *xbuf = scratch(device, chunk);
+    ScratchLease lease{this, lease_scratch(device, s, chunk), &Engine::release_scratch};
+    uint64_t *xbuf = lease.st->p;
     for (size_t off = 0; off < n; off += chunk) {
         const size_t c = n - off < chunk ? n - off : chunk;
-        cuda_throw(launch_decrypt(ct + off * kCtWords, sk, xbuf, plain + off * kN, c, s), "decrypt");
+        cuda_throw(launch_decrypt(ct + off * kCtWords, sk, xbuf, plain + off * kN, c, s, exhausted ? exhausted + off : nullptr), "decrypt");
     }
 }
 
@@ -1140,11 +1220,16 @@ const uint8_t kSeedConstant[64] = {15,  17,  225, 5,   30,  1,   237, 218, 130, 
                                    214, 175, 175, 110, 173, 103, 172, 60,  43,  76,  40,  150, 215, 96,  23,  78,
                                    22,  39,  30,  177, 107, 130, 124, 109, 27,  96,  206, 125, 104, 241, 10,  40,
                                    88,  238, 117, 118, 79,  113, 213, 110, 148, 179, 53,  19,  227, 154, 151, 122};
-uint64_t seed_from_hash(const std::vector<uint8_t> &msg) {
+// the eight little-endian u64 words of SHA-512(msg) the reference hands to SEAL as the PRNG seed (fhe.rs:47-54, 611-616):
+// all 512 bits reach the device sampler
+struct Seed512 {
+    uint64_t w[8];
+};
+Seed512 seed_from_hash(const std::vector<uint8_t> &msg) {
     uint8_t h[64];
     sha512(msg.data(), msg.size(), h);
-    uint64_t s = 0;  // first of the eight little-endian u64 words the reference hands to SEAL (fhe.rs:47-54)
-    memcpy(&s, h, 8);
+    Seed512 s;
+    memcpy(s.w, h, 64);
     return s;
 }
 const char *type_name_of(Kind k) {
@@ -1163,7 +1248,7 @@ void testnet_params(uint8_t out[kParamsBytes]) {
 }  // namespace
 
 // encrypts the scalar operand `scalar` under `pk_bytes` with `seed`; uses the lane's plain / out buffers
-int32_t Engine::encrypt_plain(Kind kind, const uint16_t *, Span scalar, Span pk_bytes, uint64_t seed, CipherView *view, Lane *lane,
+int32_t Engine::encrypt_plain(Kind kind, Span scalar, Span pk_bytes, const uint64_t seed[8], CipherView *view, Lane *lane,
                               std::vector<uint8_t> *out) {
     int32_t rc = encode_scalar(kind, scalar, lane->h_plain);
     if (rc) return rc == kErrSunscreen ? kErrFailedEncryption : rc;
@@ -1172,9 +1257,9 @@ int32_t Engine::encrypt_plain(Kind kind, const uint16_t *, Span scalar, Span pk_
     rc = public_key(pk_bytes, lane->device, &d_pk, &pin);
     if (rc) return rc;
     cudaStream_t s = lane->stream;
-    lane->h_b[0] = seed;
+    memcpy(lane->h_b, seed, 64);
     cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
-    cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, 8, cudaMemcpyHostToDevice, s), "H2D seed");
+    cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, 64, cudaMemcpyHostToDevice, s), "H2D seed");
     cuda_throw(launch_encrypt(d_pk, lane->d_plain, lane->d_b, lane->d_scratch, lane->d_out, 1, s), "encrypt");
     cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
@@ -1195,7 +1280,7 @@ int32_t Engine::encrypt(Kind kind, Span in, Span net_pub, Span, std::vector<uint
     CipherView view;
     view.data_type = type_name_of(kind);
     testnet_params(view.params);
-    return encrypt_plain(kind, nullptr, plain, net_pub, seed_from_hash(msg), &view, lane, out);
+    return encrypt_plain(kind, plain, net_pub, seed_from_hash(msg).w, &view, lane, out);
 }
 
 int32_t Engine::decrypt(Kind kind, Span in, Span, Span net_pri, std::vector<uint8_t> *out) {
@@ -1209,9 +1294,13 @@ int32_t Engine::decrypt(Kind kind, Span in, Span, Span net_pri, std::vector<uint
     const uint64_t *d_sk = network_sk(lane->device, net_pri);
     cudaStream_t s = lane->stream;
     cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D ct");
-    cuda_throw(launch_decrypt(lane->d_a, d_sk, lane->d_scratch, lane->d_plain, 1, s), "decrypt");
+    int *d_flag = reinterpret_cast<int *>(lane->d_scratch + 2 * kN);  // right behind the [2][N] dot-product buffer
+    cuda_throw(launch_decrypt(lane->d_a, d_sk, lane->d_scratch, lane->d_plain, 1, s, d_flag), "decrypt");
     cuda_throw(cudaMemcpyAsync(lane->h_plain, lane->d_plain, kN * 2, cudaMemcpyDeviceToHost, s), "D2H plain");
+    cuda_throw(cudaMemcpyAsync(lane->h_out, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H noise flag");
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    // sunscreen's Runtime::decrypt refuses a ciphertext whose invariant noise budget is 0 (-> fhe.rs:643, 696)
+    if (*reinterpret_cast<const int *>(lane->h_out)) return kErrFailedDecryption;
     decode_scalar(kind, lane->h_plain, kN, out);
     return kOk;
 }
@@ -1233,16 +1322,20 @@ int32_t Engine::reencrypt(Kind kind, Span in, Span, Span net_pri, std::vector<ui
     const uint64_t *d_sk = network_sk(lane->device, net_pri);
     cudaStream_t s = lane->stream;
     cuda_throw(cudaMemcpyAsync(lane->d_a, lane->h_a, kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D ct");
-    cuda_throw(launch_decrypt(lane->d_a, d_sk, lane->d_scratch, lane->d_plain, 1, s), "decrypt");
+    int *d_flag = reinterpret_cast<int *>(lane->d_scratch + 2 * kN);  // right behind the [2][N] dot-product buffer
+    cuda_throw(launch_decrypt(lane->d_a, d_sk, lane->d_scratch, lane->d_plain, 1, s, d_flag), "decrypt");
     cuda_throw(cudaMemcpyAsync(lane->h_plain, lane->d_plain, kN * 2, cudaMemcpyDeviceToHost, s), "D2H plain");
+    cuda_throw(cudaMemcpyAsync(lane->h_out, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H noise flag");
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    // sunscreen's Runtime::decrypt refuses a ciphertext whose invariant noise budget is 0 (-> fhe.rs:643, 696)
+    if (*reinterpret_cast<const int *>(lane->h_out)) return kErrFailedDecryption;
     std::vector<uint8_t> scalar;
     decode_scalar(kind, lane->h_plain, kN, &scalar);
     // seed = SHA-512(public_data || whole input || plain bytes)   (fhe.rs:676, 646-649)
     std::vector<uint8_t> msg(public_data.p, public_data.p + public_data.n);
     msg.insert(msg.end(), in.p, in.p + in.n);
     msg.insert(msg.end(), scalar.begin(), scalar.end());
-    return encrypt_plain(kind, nullptr, Span{scalar.data(), scalar.size()}, pk, seed_from_hash(msg), &view, lane, out);
+    return encrypt_plain(kind, Span{scalar.data(), scalar.size()}, pk, seed_from_hash(msg).w, &view, lane, out);
 }
 
 }  // namespace fheb

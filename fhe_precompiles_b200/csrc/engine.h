@@ -144,9 +144,30 @@ class Engine {
     int32_t reencrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
     int32_t decrypt(Kind kind, Span in, Span net_pub, Span net_pri, std::vector<uint8_t> *out);
 
-    // per-device scratch arena for `ops` concurrent multiply+relin ops (grown on demand, never shrunk)
-    uint64_t *scratch(int device, size_t ops);
+    // L2-resident fork/join pipeline state of one (device, stream), see subchunk_ops_
+    static constexpr int kForkStreams = 2;
+    struct ForkSet {
+        bool ready = false;
+        cudaStream_t stream[kForkStreams];
+        cudaEvent_t fork, join[kForkStreams];
+        uint64_t *scratch[kForkStreams] = {nullptr, nullptr};
+        size_t ops = 0;
+    };
+    // scratch arena for `ops` concurrent multiply+relin ops, one per (device, caller stream): grown on demand, leased while
+    // a caller enqueues, evicted (after synchronising its stream) when more than FHE_B200_SCRATCH_ARENAS are idle on a device
+    struct StreamState {
+        int device = 0;
+        cudaStream_t stream = nullptr;
+        uint64_t *p = nullptr;
+        size_t ops = 0;
+        int users = 0;
+        uint64_t last_use = 0;
+        ForkSet forks;
+    };
+    StreamState *lease_scratch(int device, cudaStream_t s, size_t ops);
+    void release_scratch(StreamState *st);
     size_t chunk_ops() const { return chunk_ops_; }
+    size_t set_chunk_ops(long long ops);  // ops <= 0 only queries; returns the previous value
     int n_devices() const { return n_devices_; }
 
     // relin key for the PublicKey bytes, parsed + validated once and cached by content
@@ -158,7 +179,9 @@ class Engine {
     // device-resident batched encrypt / decrypt (pointers on `device`)
     void encrypt_device(int device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
                         cudaStream_t s);
-    void decrypt_device(int device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, cudaStream_t s);
+    // exhausted (optional, [n] ints on the device): 1 where the invariant noise budget is 0 (the plaintext is then garbage)
+    void decrypt_device(int device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, cudaStream_t s,
+                        int32_t *exhausted = nullptr);
 
    private:
     Engine();
@@ -185,8 +208,8 @@ class Engine {
 
     KeyEntry *find_or_parse_key(Span pk, int32_t *rc);  // returns the entry PINNED (users + 1); takes key_mu_ itself
     const uint64_t *network_sk(int device, Span net_pri);
-    int32_t encrypt_plain(Kind kind, const uint16_t *plain_host_unused, Span scalar, Span pk_bytes, uint64_t seed, CipherView *view,
-                          Lane *lane, std::vector<uint8_t> *out);
+    int32_t encrypt_plain(Kind kind, Span scalar, Span pk_bytes, const uint64_t seed[8], CipherView *view, Lane *lane,
+                          std::vector<uint8_t> *out);
     std::vector<uint64_t *> d_net_sk_;
     std::mutex sk_mu_;
     std::mutex key_mu_;
@@ -233,24 +256,13 @@ class Engine {
     // L2-resident pipelining of multiply+relinearise: the batch is cut into sub-chunks whose scratch (1.7 MB per op)
     // fits the 126 MB L2 and the sub-chunks alternate over kForkStreams internal streams, so that one sub-chunk's
     // kernel tails overlap the other's heads while producer->consumer scratch stays on chip. 0 = off.
-    static constexpr int kForkStreams = 2;
     size_t subchunk_ops_ = 0;
-    struct ForkSet {
-        bool ready = false;
-        cudaStream_t stream[kForkStreams];
-        cudaEvent_t fork, join[kForkStreams];
-        uint64_t *scratch[kForkStreams] = {nullptr, nullptr};
-        size_t ops = 0;
-    };
-    std::vector<ForkSet> forks_;
-    void mul_relin_forked(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
+    void mul_relin_forked(StreamState *st, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n,
                           cudaStream_t s);
-
-    struct Arena {
-        uint64_t *p = nullptr;
-        size_t ops = 0;
-    };
-    std::vector<Arena> arenas_;
+    void free_stream_state(StreamState &v);
+    std::vector<std::unique_ptr<StreamState>> stream_states_;
+    uint64_t arena_clock_ = 0;
+    std::condition_variable arena_cv_;
     std::mutex arena_mu_;
 };
 

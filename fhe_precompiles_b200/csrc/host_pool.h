@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <deque>
+#include <exception>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -15,6 +16,11 @@ namespace fheb {
 // run(k, fn) executes fn on up to k pool threads plus the caller and returns when every started copy has finished;
 // copies that no pool thread has picked up by the time the caller's own copy returns are withdrawn (fn drains a shared
 // work counter, so nothing is lost), which also makes concurrent and nested batches deadlock-free.
+//
+// Exceptions: fn may throw on any thread (a CUDA allocation failure, a missing libzstd, bad_alloc).  A pool thread never
+// lets one escape (that would be std::terminate for the whole host process): the first exception of a job is kept in the
+// job and rethrown on the CALLER once every copy has been withdrawn or has finished, so by the time run() unwinds nobody
+// holds a pointer into the caller's frame any more.  The same withdrawal + wait runs when the caller's own copy throws.
 class HostPool {
    public:
     static HostPool &get() {
@@ -35,22 +41,35 @@ class HostPool {
             job->queued = helpers;
         }
         cv_.notify_all();
-        fn();
-        std::unique_lock<std::mutex> lk(mu_);
-        for (auto it = queue_.begin(); it != queue_.end();)  // withdraw the copies nobody started
-            if (it->get() == job.get()) {
-                it = queue_.erase(it);
-                job->queued--;
-            } else {
-                ++it;
-            }
-        job->done_cv.wait(lk, [&] { return job->queued == 0; });
+        std::exception_ptr mine;
+        try {
+            fn();
+        } catch (...) {
+            mine = std::current_exception();
+        }
+        std::exception_ptr theirs;
+        {
+            std::unique_lock<std::mutex> lk(mu_);
+            for (auto it = queue_.begin(); it != queue_.end();)  // withdraw the copies nobody started
+                if (it->get() == job.get()) {
+                    it = queue_.erase(it);
+                    job->queued--;
+                } else {
+                    ++it;
+                }
+            job->done_cv.wait(lk, [&] { return job->queued == 0; });
+            theirs = job->error;
+            job->fn = nullptr;  // the frame `fn` lives in is about to go away
+        }
+        if (mine) std::rethrow_exception(mine);
+        if (theirs) std::rethrow_exception(theirs);
     }
 
    private:
     struct Job {
         const std::function<void()> *fn = nullptr;
         size_t queued = 0;  // copies in the queue or running (guarded by mu_)
+        std::exception_ptr error;  // first exception thrown by a pool-thread copy (guarded by mu_)
         std::condition_variable done_cv;
     };
     void loop() {
@@ -59,9 +78,16 @@ class HostPool {
             cv_.wait(lk, [&] { return !queue_.empty(); });
             std::shared_ptr<Job> job = queue_.front();
             queue_.pop_front();
+            const std::function<void()> *fn = job->fn;
             lk.unlock();
-            (*job->fn)();
+            std::exception_ptr err;
+            try {
+                if (fn) (*fn)();
+            } catch (...) {
+                err = std::current_exception();
+            }
             lk.lock();
+            if (err && !job->error) job->error = err;
             if (--job->queued == 0) job->done_cv.notify_all();
         }
     }

@@ -780,8 +780,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_decrypt_dot(const u64 *__restri
     else
         decrypt_dot_body<MQ1>(ct + op * 4 * kN, sk, xbuf + op * 2 * kN, smem, threadIdx.x);
 }
+// exhausted[op] (optional) is set when the op's invariant noise budget is 0 -- SEAL Decryptor::invariant_noise_budget:
+// bit_count(q) - bit_count(max_i |t x_i mod q|, centred) - 1 <= 0, i.e. the centred remainder of some coefficient reaches
+// 2^70 -- which sunscreen's Runtime::decrypt turns into an error (-> FailedDecryption, fhe.rs:640-643, 692-696).
 __global__ void __launch_bounds__(256) k_decrypt_round(const u64 *__restrict__ xbuf, unsigned short *__restrict__ plain,
-                                                       size_t n_ops) {
+                                                       size_t n_ops, int *__restrict__ exhausted) {
     using Q0 = Mod<MQ0>;
     using Q1 = Mod<MQ1>;
     size_t total = n_ops * kN;
@@ -818,29 +821,61 @@ __global__ void __launch_bounds__(256) k_decrypt_round(const u64 *__restrict__ x
         // round to nearest (ties up): floor((tX + (q-1)/2) / q) = quo + [rem + (q-1)/2 >= q]
         u64 sl = lo + kc.qhalf_lo;
         u64 sh = hi + kc.qhalf_hi + (sl < lo);
-        if (sh > qhi || (sh == qhi && sl >= qlo)) quo += 1;
+        const bool up = sh > qhi || (sh == qhi && sl >= qlo);
+        if (up) quo += 1;
         plain[g] = (unsigned short)(quo & (kT - 1));
+        if (exhausted) {
+            // centred remainder: rem if it rounds down, q - rem if it rounds up; bits 70.. of the 128-bit value
+            const u64 nh = up ? qhi - hi - (qlo < lo) : hi;
+            if (nh >> 6) exhausted[op] = 1;
+        }
     }
 }
 
 // =====================================================================================
 // K11b: public-key encryption   (SEAL Encryptor::encrypt_zero_asymmetric at the key level +
 //       RNSTool::divide_and_round_q_last_inplace + multiply_add_plain_with_scaling_variant; fhe.rs:594-618)
-// Randomness is a counter-based generator keyed by a caller-supplied 64-bit seed per op: a valid BFV
-// encryption with SEAL's distributions (uniform ternary u, truncated sigma = 3.2 Gaussian errors), deterministic in
-// (seed, plaintext, key), NOT SEAL's Blake2xb sampler stream.
+// Randomness: ChaCha12 keyed by the caller's 512-bit seed per op (the reference hands SEAL the whole SHA-512 digest,
+// fhe.rs:611-616): key = seed words 0..3 xor words 4..7 (256 bits), nonce = word 4, counter = (thread, stream) with
+// stream 0 = u, 1 = e0, 2 = e1.  One 64-byte block per thread and stream; word r of thread t's block drives coefficient
+// r*512 + t.  A valid BFV encryption with SEAL's distributions (uniform ternary u; errors Gaussian, sigma = 3.2, clipped at
+// 6 sigma and truncated toward zero), deterministic in (seed, plaintext, key), restated bit for bit by oracle/bfv.py
+// (gpu_sampler_*); NOT SEAL's Blake2xb sampler stream.
 //   k_encrypt_core   : INTT_J(pk_j[J] * NTT_J(u)) + e_j    grid (3 moduli, ops) -> encbuf [op][2][3][N]
 //   k_encrypt_finish : drop P with rounding, add Delta*m   per coefficient      -> ct [op][2][2][N]
 // =====================================================================================
-__device__ __forceinline__ u64 mix64(u64 z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
+__device__ __forceinline__ void chacha_qr(u32 &a, u32 &b, u32 &c, u32 &d) {
+    a += b, d ^= a, d = __funnelshift_l(d, d, 16);
+    c += d, b ^= c, b = __funnelshift_l(b, b, 12);
+    a += b, d ^= a, d = __funnelshift_l(d, d, 8);
+    c += d, b ^= c, b = __funnelshift_l(b, b, 7);
 }
-// ternary secret-like sample in {-1,0,1}, uniform (rejection on 2-bit draws)
-__device__ __forceinline__ int sample_ternary(u64 seed, int i) {
-    u64 r = mix64(seed ^ (0x7465726eull << 32) ^ (u64)i);
+// the 8 u64 output words of block (counter, stream) under the op's seed
+__device__ __forceinline__ void chacha12_block(const u64 *__restrict__ seed, u32 counter, u32 stream, u64 (&out)[8]) {
+    u32 in[16], x[16];
+    in[0] = 0x61707865u, in[1] = 0x3320646eu, in[2] = 0x79622d32u, in[3] = 0x6b206574u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) unpack64(seed[i] ^ seed[i + 4], in[4 + 2 * i], in[5 + 2 * i]);
+    in[12] = counter, in[13] = stream;
+    unpack64(seed[4], in[14], in[15]);
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = in[i];
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        chacha_qr(x[0], x[4], x[8], x[12]);
+        chacha_qr(x[1], x[5], x[9], x[13]);
+        chacha_qr(x[2], x[6], x[10], x[14]);
+        chacha_qr(x[3], x[7], x[11], x[15]);
+        chacha_qr(x[0], x[5], x[10], x[15]);
+        chacha_qr(x[1], x[6], x[11], x[12]);
+        chacha_qr(x[2], x[7], x[8], x[13]);
+        chacha_qr(x[3], x[4], x[9], x[14]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = pack64(x[2 * i] + in[2 * i], x[2 * i + 1] + in[2 * i + 1]);
+}
+// ternary sample in {-1,0,1}, uniform: the first 2-bit group of the word that is not 3 (all 32 groups 3: 0)
+__device__ __forceinline__ int sample_ternary(u64 r) {
     for (int k = 0; k < 32; k++) {
         int d = (int)((r >> (2 * k)) & 3);
         if (d != 3) return d - 1;
@@ -848,23 +883,34 @@ __device__ __forceinline__ int sample_ternary(u64 seed, int i) {
     return 0;
 }
 // Error sample with the distribution the reference's SEAL build uses (identified from its key fixtures, DESIGN.md
-// section 7): Gaussian, sigma = 3.2, clipped at 6 sigma, truncated toward zero (P(0) = 0.245, variance 7.9).
-// Box-Muller on two 24-bit uniforms from the counter-based generator; 24 bits reach 5.77 sigma, inside the clip.
-__device__ __forceinline__ int sample_noise(u64 seed, int poly, int i) {
-    u64 r = mix64(seed ^ ((0x65727200ull + (u64)poly) << 32) ^ (u64)i);
-    const float u1 = ((float)(u32)(r >> 40) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
-    const float u2 = (float)(u32)((r >> 16) & 0xffffffu) * (1.0f / 16777216.0f);
-    const float g = sqrtf(-2.0f * __logf(u1)) * cospif(2.0f * u2) * 3.2f;
-    return (int)fminf(fmaxf(g, -19.0f), 19.0f);
+// section 7): Gaussian, sigma = 3.2, clipped at 6 sigma, truncated toward zero (P(0) = 0.245, variance 8.0).  Inverse-CDF
+// lookup on 63 uniform bits: kNoiseCdf[k] = floor(2^63 P(|x| < k+1)); bit 0 is the sign.  Integer only, so the CPU oracle
+// reproduces it exactly.
+__device__ const u64 kNoiseCdf[20] = {
+    0x1f67485e1414e200ull, 0x3be85f5582810200ull, 0x53644e2dedd21400ull, 0x64f422f09cf1bc00ull, 0x70dfcc250f890800ull,
+    0x7837f1b047d3fc00ull, 0x7c535c45b5071400ull, 0x7e690b1eb1011400ull, 0x7f5eeb470d610c00ull, 0x7fc5bca5a5143c00ull,
+    0x7fecc2f990af3800ull, 0x7ffa349ee365e800ull, 0x7ffe68c004b14800ull, 0x7fff9a26cfa95400ull, 0x7fffe8d1193b7400ull,
+    0x7ffffb3514071000ull, 0x7fffff1c06e24c00ull, 0x7fffffdc665b1800ull, 0x7ffffffe05c3f800ull, 0x8000000000000000ull};
+__device__ __forceinline__ int sample_noise(u64 r) {
+    const u64 v = r >> 1;
+    int mag = 0;
+#pragma unroll
+    for (int k = 0; k < 19; k++) mag += v >= kNoiseCdf[k] ? 1 : 0;
+    return (r & 1) ? -mag : mag;
 }
 template <int MI>
-__device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, u64 seed, u64 *__restrict__ enc, u64 *smem, int t) {
+__device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, const u64 *__restrict__ seed, u64 *__restrict__ enc,
+                                                  u64 *smem, int t) {
     using M = Mod<MI>;
     u64 v[1][8];
+    {
+        u64 rnd[8];
+        chacha12_block(seed, (u32)t, 0, rnd);
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        int u = sample_ternary(seed, r * kThreads + t);
-        v[0][r] = u < 0 ? M::q - 1 : (u64)u;
+        for (int r = 0; r < 8; r++) {
+            int u = sample_ternary(rnd[r]);
+            v[0][r] = u < 0 ? M::q - 1 : (u64)u;
+        }
     }
     ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
     u64 w[2][8];
@@ -878,9 +924,11 @@ __device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, u6
     ntt_inverse<M, 2>(w, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
 #pragma unroll
     for (int j = 0; j < 2; j++) {
+        u64 rnd[8];
+        chacha12_block(seed, (u32)t, 1 + j, rnd);
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            int e = sample_noise(seed, j, r * kThreads + t);
+            int e = sample_noise(rnd[r]);
             u64 ev = e < 0 ? M::q - (u64)(-e) : (u64)e;
             w[j][r] = addmod<M>(w[j][r], ev);
         }
@@ -891,7 +939,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_encrypt_core(const u64 *__restr
                                                                u64 *__restrict__ encbuf) {
     extern __shared__ __align__(16) u64 smem[];
     const size_t op = blockIdx.y;
-    const u64 seed = seeds[op];
+    const u64 *seed = seeds + op * 8;  // 512 bits per op
     u64 *enc = encbuf + op * 6 * kN;
     switch (blockIdx.x) {
         case 0: encrypt_core_body<MQ0>(pk, seed, enc, smem, threadIdx.x); break;
@@ -1202,10 +1250,15 @@ cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
-cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s) {
+cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s,
+                           int *exhausted) {
     if (n_ops == 0) return cudaSuccess;
+    if (exhausted) {
+        cudaError_t e = cudaMemsetAsync(exhausted, 0, n_ops * sizeof(int), s);
+        if (e != cudaSuccess) return e;
+    }
     k_decrypt_dot<<<dim3(2, (unsigned)n_ops), kThreads, kSmem1, s>>>(ct, sk, xbuf);
-    k_decrypt_round<<<eltwise_grid(n_ops * kN, 256), 256, 0, s>>>(xbuf, plain, n_ops);
+    k_decrypt_round<<<eltwise_grid(n_ops * kN, 256), 256, 0, s>>>(xbuf, plain, n_ops, exhausted);
     g_launches.fetch_add(2, std::memory_order_relaxed);
     return cudaGetLastError();
 }

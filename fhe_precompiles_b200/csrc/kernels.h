@@ -31,7 +31,9 @@ cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaS
 cudaError_t launch_digit_ntt(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s);
 cudaError_t launch_ks_intt(const u64 *dig, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
 // decrypt n size-2 ciphertexts with sk [>=2 limbs][N] (NTT form): xbuf scratch [n][2][N], plain out [n][N] u16
-cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s);
+// exhausted (optional, [n_ops] ints on the device): set to 1 where the invariant noise budget is 0
+cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s,
+                           int *exhausted = nullptr);
 // pk-encrypt n plaintexts under pk [2][3][N] (NTT form) with per-op seeds; encbuf scratch [n][2][3][N]
 cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64 *seeds, u64 *encbuf, u64 *ct, size_t n_ops,
                            cudaStream_t s);

@@ -201,12 +201,13 @@ def set_fused(on: bool) -> None:
 
 
 def encrypt(pk: torch.Tensor, plain: torch.Tensor, seeds: torch.Tensor) -> torch.Tensor:
-    """pk [2,3,4096] int64, plain [n,4096] int16, seeds [n] int64 (all on one CUDA device) -> ct [n,2,2,4096]."""
+    """pk [2,3,4096] int64, plain [n,4096] int16, seeds [n,8] int64 -- one 512-bit seed per op -- (all on one CUDA device)
+    -> ct [n,2,2,4096]."""
     dev = _dev(pk)
     _dev(plain)
     _dev(seeds)
     n = plain.shape[0]
-    assert plain.dtype == torch.int16 and seeds.dtype == torch.int64 and seeds.numel() == n
+    assert plain.dtype == torch.int16 and seeds.dtype == torch.int64 and tuple(seeds.shape) == (n, 8)
     ct = torch.empty((n, 2, 2, N), dtype=torch.int64, device=pk.device)
     _check(_lib.lib().fhe_b200_encrypt(dev, pk.data_ptr(), plain.data_ptr(), seeds.data_ptr(), ct.data_ptr(), n, _stream(dev)))
     return ct
@@ -219,3 +220,22 @@ def decrypt(ct: torch.Tensor, sk: torch.Tensor) -> torch.Tensor:
     plain = torch.empty((ct.shape[0], N), dtype=torch.int16, device=ct.device)
     _check(_lib.lib().fhe_b200_decrypt(dev, ct.data_ptr(), sk.data_ptr(), plain.data_ptr(), ct.shape[0], _stream(dev)))
     return plain
+
+
+def decrypt_checked(ct: torch.Tensor, sk: torch.Tensor):
+    """decrypt() plus SEAL's invariant-noise-budget test: returns (plain [n,4096] int16, exhausted [n] int32), exhausted[i] = 1
+    where ciphertext i has no noise budget left (its plaintext is meaningless; the byte surface returns code 5 there)."""
+    dev = _dev(ct)
+    _dev(sk)
+    plain = torch.empty((ct.shape[0], N), dtype=torch.int16, device=ct.device)
+    flags = torch.empty((ct.shape[0],), dtype=torch.int32, device=ct.device)
+    _check(_lib.lib().fhe_b200_decrypt_checked(dev, ct.data_ptr(), sk.data_ptr(), plain.data_ptr(), flags.data_ptr(), ct.shape[0], _stream(dev)))
+    return plain, flags
+
+
+def set_chunk_ops(ops: int) -> int:
+    """Ops per chunk of the device-resident entry points (default 4,096); ops <= 0 only queries. Returns the previous value."""
+    prev = int(_lib.lib().fhe_b200_set_chunk_ops(int(ops)))
+    if prev < 0:
+        raise RuntimeError("fhe_precompiles_b200: " + _lib.last_error())
+    return prev

@@ -136,12 +136,21 @@ int32_t fhe_b200_multiply(int32_t device, const uint64_t *a, const uint64_t *b, 
 int32_t fhe_b200_relinearize(int32_t device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, void *stream);
 int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
                            size_t n, void *stream);
-/* Public-key encryption of n plaintexts (uint16 [n][4096]) under pk [2][3][4096] (NTT form, key level) with one
- * 64-bit seed per op: a valid BFV encryption, deterministic in (seed, plaintext, key); the sampler stream is this
- * library's own, not SEAL's. Decryption of n size-2 ciphertexts with sk [>=2 limbs][4096] (NTT form) -> plaintexts. */
+/* Public-key encryption of n plaintexts (uint16 [n][4096]) under pk [2][3][4096] (NTT form, key level) with one 512-bit seed
+ * per op (seeds [n][8] words; the byte surface passes the eight little-endian words of its SHA-512 digest, fhe.rs:611-616).
+ * A valid BFV encryption with SEAL's distributions, deterministic in (seed, plaintext, key).  The samples u, e0, e1 are
+ * expanded from the seed with ChaCha12 under a 256-bit key (seed words 0..3 xor 4..7; nonce = word 4), so the encryption
+ * randomness carries 256 bits of key entropy -- above the parameter set's 128-bit target; the sampler stream is this
+ * library's own, not SEAL's Blake2xb one (an encrypt_* result differs from the reference's in bytes, not in validity).
+ * Decryption of n size-2 ciphertexts with sk [>=2 limbs][4096] (NTT form) -> plaintexts. */
 int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
                          void *stream);
 int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, void *stream);
+/* The same with SEAL's invariant-noise-budget test: exhausted[i] (device ints) = 1 where ciphertext i has no budget left
+ * (max |t x mod q| centred >= 2^70), i.e. where sunscreen's Runtime::decrypt fails and c_fhe_decrypt_* / c_fhe_reencrypt_*
+ * return 5 (FailedDecryption, fhe.rs:640-643, 692-696); plain[i] is then meaningless. */
+int32_t fhe_b200_decrypt_checked(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, int32_t *exhausted, size_t n,
+                                 void *stream);
 /* Same op on HOST buffers (pin them for full PCIe rate): copies in, computes and copies out chunk by chunk with
  * the three phases of consecutive chunks overlapped; returns when `out` is complete. rk: host words. */
 int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
@@ -164,6 +173,13 @@ int32_t fhe_b200_int_peak(int32_t device, int32_t wide, double *tera_mads_per_s)
 /* Register-only NTT butterfly rate of `device` in 1e9 butterflies/s for modulus class of `mod` (0-2: 36/37-bit,
  * 3-5: 61-bit): the compute ceiling of the transform's inner loop without memory or barriers. */
 int32_t fhe_b200_bfly_peak(int32_t device, int32_t mod, double *giga_bfly_per_s);
+/* Which of the four operand kinds a Ciphertext data_type string ("<type name>,<version>,<is_encrypted>") belongs to:
+ * 0 u256, 1 u64, 2 i64, 3 frac64, -1 none.  This is the check every binary precompile applies to its ciphertext operands
+ * (a mismatch is code 7, like sunscreen's argument check behind fhe.rs:28).  Host only. */
+int32_t fhe_b200_data_type_kind(const char *data_type);
+/* Ops per chunk of the device-resident entry points (default 4,096, FHE_B200_CHUNK_OPS): a batch larger than this runs chunk
+ * after chunk through one scratch arena.  ops <= 0 only queries.  Returns the previous value (-1 without a device). */
+int64_t fhe_b200_set_chunk_ops(int64_t ops);
 /* Kernel variant of multiply / relinearise: 0 (default) one polynomial per CTA (k_ext_ntt, k_tensor_intt,
  * k_digit_ntt, k_ks_intt); 1 multi-polynomial CTAs (k_behz_tensor, k_relin_ks). Same results. */
 void fhe_b200_set_fused(int32_t on);

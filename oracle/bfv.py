@@ -48,6 +48,7 @@ def lib() -> ctypes.CDLL:
         L.bfvo_decrypt.restype = ctypes.c_int
         L.bfvo_decrypt.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.bfvo_encrypt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_void_p]
+        L.bfvo_encrypt_samples.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 4
         L.bfvo_batch_mul_relin.restype = ctypes.c_double
         L.bfvo_batch_mul_relin.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_int]
         L.bfvo_batch_ntt.restype = ctypes.c_double
@@ -255,6 +256,87 @@ def encrypt(pk: np.ndarray, plain: np.ndarray, seed: int) -> np.ndarray:
     pk, pl = _c(pk), _c(plain)
     out = np.empty((2, 2, N), dtype=np.uint64)
     lib().bfvo_encrypt(_p(pk), _p(pl), pl.size, seed, _p(out))
+    return out
+
+
+# ---------------------------------------------------------------- restatement of the GPU encryptor's sampler
+# (fhe_precompiles_b200/csrc/kernels.cu: chacha12_block, sample_ternary, sample_noise).  The reference hands SEAL the
+# 512-bit SHA-512 digest as PRNG seed (/root/reference/src/fhe.rs:611-616); SEAL's own Blake2xb stream is not reproduced
+# (SURVEY 8f-1), so the product expands the same seed with ChaCha12 and this is its bit-exact CPU twin.
+NOISE_CDF = np.array([
+    0x1f67485e1414e200, 0x3be85f5582810200, 0x53644e2dedd21400, 0x64f422f09cf1bc00, 0x70dfcc250f890800,
+    0x7837f1b047d3fc00, 0x7c535c45b5071400, 0x7e690b1eb1011400, 0x7f5eeb470d610c00, 0x7fc5bca5a5143c00,
+    0x7fecc2f990af3800, 0x7ffa349ee365e800, 0x7ffe68c004b14800, 0x7fff9a26cfa95400, 0x7fffe8d1193b7400,
+    0x7ffffb3514071000, 0x7fffff1c06e24c00, 0x7fffffdc665b1800, 0x7ffffffe05c3f800], dtype=np.uint64)
+
+
+def chacha_core(x: np.ndarray, double_rounds: int) -> np.ndarray:
+    """ChaCha block function (RFC 7539 2.3) on columns of x (uint32 [16, n]) with 2 * double_rounds rounds."""
+    x = x.astype(np.uint32)
+    w = x.copy()
+    rotl = lambda v, n: (v << np.uint32(n)) | (v >> np.uint32(32 - n))
+
+    def qr(a, b, c, d):
+        w[a] += w[b]; w[d] = rotl(w[d] ^ w[a], 16)
+        w[c] += w[d]; w[b] = rotl(w[b] ^ w[c], 12)
+        w[a] += w[b]; w[d] = rotl(w[d] ^ w[a], 8)
+        w[c] += w[d]; w[b] = rotl(w[b] ^ w[c], 7)
+
+    with np.errstate(over="ignore"):
+        for _ in range(double_rounds):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
+        w += x
+    return w
+
+
+def _chacha12_blocks(seed8: np.ndarray, stream: int) -> np.ndarray:
+    """[512 counters][8] u64 output words under the 512-bit seed (8 u64 words): key = words 0..3 xor 4..7, state words
+    12 / 13 = (counter, stream), 14 / 15 = seed word 4; 12 rounds."""
+    seed8 = np.asarray(seed8, dtype=np.uint64)
+    key = seed8[:4] ^ seed8[4:]
+    x = np.zeros((16, 512), dtype=np.uint32)
+    x[0], x[1], x[2], x[3] = 0x61707865, 0x3320646E, 0x79622D32, 0x6B206574
+    for i in range(4):
+        x[4 + 2 * i] = np.uint32(int(key[i]) & 0xFFFFFFFF)
+        x[5 + 2 * i] = np.uint32(int(key[i]) >> 32)
+    x[12] = np.arange(512, dtype=np.uint32)
+    x[13] = stream
+    x[14] = np.uint32(int(seed8[4]) & 0xFFFFFFFF)
+    x[15] = np.uint32(int(seed8[4]) >> 32)
+    w = chacha_core(x, 6)
+    out = w[0::2].astype(np.uint64) | (w[1::2].astype(np.uint64) << np.uint64(32))  # [8][512]
+    return out.T.copy()
+
+
+def gpu_sampler(seed8) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """(u, e0, e1) int8 [N] exactly as k_encrypt_core draws them: word r of thread t's block -> coefficient r*512 + t."""
+    res = []
+    for stream in range(3):
+        words = _chacha12_blocks(seed8, stream).T.reshape(-1)  # index r*512 + t
+        if stream == 0:
+            smp = np.zeros(N, dtype=np.int8)
+            done = np.zeros(N, dtype=bool)
+            for k in range(32):
+                d = ((words >> np.uint64(2 * k)) & np.uint64(3)).astype(np.int8)
+                take = ~done & (d != 3)
+                smp[take] = d[take] - 1
+                done |= take
+        else:
+            v = words >> np.uint64(1)
+            mag = (v[:, None] >= NOISE_CDF[None, :]).sum(axis=1).astype(np.int8)
+            smp = np.where((words & np.uint64(1)) == 1, -mag, mag).astype(np.int8)
+        res.append(smp)
+    return tuple(res)
+
+
+def encrypt_seeded(pk: np.ndarray, plain: np.ndarray, seed8) -> np.ndarray:
+    """What fhe_b200_encrypt / c_fhe_encrypt_* compute for the 512-bit seed (8 u64 words)."""
+    pk, pl = _c(pk), _c(plain)
+    u, e0, e1 = (np.ascontiguousarray(x) for x in gpu_sampler(seed8))
+    out = np.empty((2, 2, N), dtype=np.uint64)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    lib().bfvo_encrypt_samples(_p(pk), _p(pl), pl.size, vp(u), vp(e0), vp(e1), _p(out))
     return out
 
 

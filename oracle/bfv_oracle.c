@@ -735,15 +735,26 @@ static inline u64 splitmix(u64 *s) {
 /* Shape of SEAL encrypt_zero_asymmetric at key level + divide_and_round_q_last_inplace +
  * multiply_add_plain_with_scaling_variant; randomness is our own. */
 void bfvo_encrypt(const u64 *pk, const u64 *plain, size_t len, u64 seed, u64 *ct) {
-    bfvo_init();
     u64 st = seed * 0xD1342543DE82EF95ull + 0x1234567;
-    int8_t *u = (int8_t *)malloc(N);
+    int8_t *smp = (int8_t *)malloc((size_t)3 * N);
     for (size_t i = 0; i < N; i++) {
         u64 r;
         do r = splitmix(&st) & 3;
         while (r == 3);
-        u[i] = (int8_t)r - 1;
+        smp[i] = (int8_t)r - 1;
     }
+    for (int j = 0; j < 2; j++)
+        for (size_t i = 0; i < N; i++) { /* centred binomial, 21 bits each side (sigma ~3.24) */
+            u64 r = splitmix(&st);
+            smp[(size_t)(1 + j) * N + i] = (int8_t)(__builtin_popcountll(r & 0x1fffff) - __builtin_popcountll((r >> 21) & 0x1fffff));
+        }
+    bfvo_encrypt_samples(pk, plain, len, smp, smp + N, smp + 2 * N, ct);
+    free(smp);
+}
+/* The same with the samples supplied by the caller: u ternary, e0 / e1 small errors (int8).  Used to check the GPU
+ * encryptor, whose sampler (ChaCha12 + inverse-CDF, kernels.cu) is restated in oracle/bfv.py. */
+void bfvo_encrypt_samples(const u64 *pk, const u64 *plain, size_t len, const int8_t *u, const int8_t *e0, const int8_t *e1, u64 *ct) {
+    bfvo_init();
     u64 *un = (u64 *)malloc((size_t)3 * N * 8);
     for (int J = 0; J < 3; J++) {
         for (size_t i = 0; i < N; i++) un[(size_t)J * N + i] = u[i] < 0 ? C.mod[J].q - 1 : (u64)u[i];
@@ -751,11 +762,7 @@ void bfvo_encrypt(const u64 *pk, const u64 *plain, size_t len, u64 seed, u64 *ct
     }
     u64 *c = (u64 *)malloc((size_t)3 * N * 8);
     for (int j = 0; j < 2; j++) {
-        int8_t *e = (int8_t *)malloc(N);
-        for (size_t i = 0; i < N; i++) { /* centred binomial, 21 bits each side (sigma ~3.24) */
-            u64 r = splitmix(&st);
-            e[i] = (int8_t)(__builtin_popcountll(r & 0x1fffff) - __builtin_popcountll((r >> 21) & 0x1fffff));
-        }
+        const int8_t *e = j == 0 ? e0 : e1;
         for (int J = 0; J < 3; J++) {
             const Mod *m = &C.mod[J];
             u64 *x = c + (size_t)J * N;
@@ -776,10 +783,8 @@ void bfvo_encrypt(const u64 *pk, const u64 *plain, size_t len, u64 seed, u64 *ct
                 o[i] = mulmod(submod(c[(size_t)l * N + i], tl, m), C.inv_P_mod_q[l], m);
             }
         }
-        free(e);
     }
     plain_scaled(ct, plain, len, 0);
-    free(u);
     free(un);
     free(c);
 }

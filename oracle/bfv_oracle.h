@@ -89,6 +89,9 @@ double bfvo_decode_f64(const uint64_t *plain, size_t len);
 /* Public-key encryption (valid BFV encryption, own PRNG -- NOT SEAL's sampler stream).
  * pk: [2][3][N] NTT form at key level. ct_out: [2][2][N]. */
 void bfvo_encrypt(const uint64_t *pk, const uint64_t *plain, size_t plain_len, uint64_t seed, uint64_t *ct_out);
+/* the same computation with caller-supplied samples (u ternary, e0 / e1 errors, N int8 each) */
+void bfvo_encrypt_samples(const uint64_t *pk, const uint64_t *plain, size_t plain_len, const int8_t *u, const int8_t *e0,
+                          const int8_t *e1, uint64_t *ct_out);
 /* Decrypt size-2 or size-3 data-level ciphertext with sk [3][N] (NTT form).
  * plain_out gets N coefficients < t.  Returns the invariant noise budget in bits (<=0: failed). */
 int bfvo_decrypt(const uint64_t *ct, size_t npolys, const uint64_t *sk, uint64_t *plain_out);

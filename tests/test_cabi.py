@@ -142,3 +142,32 @@ def test_sha512_matches_hashlib():
         for portable in (0, 1):
             L.fhe_b200_sha512(data, n, portable, out)
             assert out.raw == hashlib.sha512(data).digest(), (n, portable)
+
+
+def test_host_pool_exception_safety(tmp_path):
+    """csrc/host_pool.h: a throwing work item reaches the caller of run() (-> code 7 through guarded()), never std::terminate,
+    and run() returns only after every copy has finished (tests/host_pool_test.cpp)."""
+    import subprocess
+
+    exe = tmp_path / "host_pool_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "fhe_precompiles_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "host_pool_test.cpp"), "-o", str(exe), "-lpthread"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stdout + r.stderr
+
+
+def test_data_type_rule_is_exact_per_kind(lib):
+    """A ciphertext's data_type belongs to exactly one kind (sunscreen's runtime rejects an argument whose Type differs from the
+    program's signature -> code 7, fhe.rs:28): u64 never passes for u256 and a foreign type passes for nothing."""
+    f = lib.fhe_b200_data_type_kind
+    f.argtypes, f.restype = [ctypes.c_char_p], ctypes.c_int32
+    from oracle import formats as F
+
+    kinds = {"u256": 0, "u64": 1, "i64": 2, "frac64": 3}
+    for k, idx in kinds.items():
+        assert f((F.TYPE_NAMES[k] + ",0.8.1,true").encode()) == idx
+        assert f((F.TYPE_NAMES[k] + ",0.8.1,false").encode()) == -1  # a plaintext type is not a ciphertext operand
+    for bad in ("sunscreen::types::bfv::unsigned::Unsigned<2>,0.8.1,true", "sunscreen::types::bfv::unsigned::Unsigned,0.8.1,true",
+                "my::Signedish,0.8.1,true", "NotSigned,0.8.1,true", "sunscreen::types::bfv::rational::Rational,0.8.1,true",
+                "Signed", "", "sunscreen::types::bfv::fractional::Fractional<32>,0.8.1,true"):
+        assert f(bad.encode()) == -1, bad

@@ -142,18 +142,83 @@ def test_fused_kernel_variant(dev, keys):
 
 
 def test_mul_relin_real_encryptions_chunked(dev, keys):
-    """batch larger than the engine's chunk (FHE_B200_CHUNK_OPS=128 set by the driver line below): bit-exact vs oracle on a sample, all decrypt."""
+    """batch larger than the engine's chunk (set to 128 ops here: chunks of 128, 128 and 44): bit-exact vs the oracle on a
+    sample that straddles every chunk boundary, all decrypt."""
     rng = np.random.default_rng(2)
     n = 300
     vals_a = rng.integers(-(2**15), 2**15, size=n)
     vals_b = rng.integers(-(2**15), 2**15, size=n)
     a = np.stack([encrypt_value(keys, "i64", int(v), 1000 + i) for i, v in enumerate(vals_a)])
     b = np.stack([encrypt_value(keys, "i64", int(v), 5000 + i) for i, v in enumerate(vals_b)])
-    out = to_np(dev.mul_relin(to_dev(a), to_dev(b), to_dev(keys.rk)))
-    for i in list(range(0, n, 37)) + [147, 148, 149, n - 1]:
+    prev = dev.set_chunk_ops(128)
+    try:
+        assert dev.set_chunk_ops(0) == 128
+        out = to_np(dev.mul_relin(to_dev(a), to_dev(b), to_dev(keys.rk)))
+        c3 = to_np(dev.multiply(to_dev(a), to_dev(b)))
+        out2 = to_np(dev.relinearize(to_dev(c3), to_dev(keys.rk)))
+    finally:
+        dev.set_chunk_ops(prev)
+    assert np.array_equal(out, out2), "multiply then relinearize, chunked, equals the fused call"
+    for i in list(range(0, n, 37)) + [127, 128, 129, 255, 256, 257, n - 1]:
         assert np.array_equal(out[i], bfv.mul_relin(a[i], b[i], keys.rk)), f"op {i}"
     for i in range(0, n, 5):
         assert decrypt_value(keys, "i64", out[i]) == int(vals_a[i]) * int(vals_b[i])
+    # one chunk (the default 4,096) gives the same bits
+    assert np.array_equal(to_np(dev.mul_relin(to_dev(a), to_dev(b), to_dev(keys.rk))), out)
+
+
+def test_mul_relin_more_than_one_default_chunk(dev, keys):
+    """n > 4,096 at the default chunk size (what config 4's 65,536 calls need): Engine::mul_relin's second chunk.  Ops are
+    drawn from a pool of 67 distinct random ciphertexts so the expected values cost 67 oracle calls."""
+    import torch
+
+    assert dev.set_chunk_ops(0) == 4096
+    n, pool = 4096 + 203, 67
+    rng = np.random.default_rng(77)
+    pa, pb = random_ct(rng, pool), random_ct(rng, pool)
+    idx = torch.arange(n) % pool
+    a, b = to_dev(pa)[idx.cuda()].contiguous(), to_dev(pb)[idx.cuda()].contiguous()
+    out = dev.mul_relin(a, b, to_dev(keys.rk))
+    want = to_dev(np.stack([bfv.mul_relin(pa[i], pb[i], keys.rk) for i in range(pool)]))
+    assert torch.equal(out, want[idx.cuda()]), "every op of both chunks"
+
+
+def test_streams_do_not_share_scratch(dev, keys):
+    """two streams on one GPU, interleaved enqueues from one thread and concurrent enqueues from two threads: each
+    (device, stream) has its own scratch arena, so results are bit-exact (they used to overwrite each other's scratch)."""
+    import threading
+
+    import torch
+
+    rng = np.random.default_rng(31)
+    n = 96
+    a, b = random_ct(rng, n), random_ct(rng, n)
+    rk = to_dev(keys.rk)
+    want = dev.mul_relin(to_dev(a), to_dev(b), rk)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    da, db = to_dev(a), to_dev(b)
+    outs = []
+    for rep in range(6):
+        for s in (s1, s2):
+            with torch.cuda.stream(s):
+                outs.append(dev.mul_relin(da, db, rk))
+    torch.cuda.synchronize()
+    assert all(torch.equal(o, want) for o in outs)
+
+    res = {}
+
+    def worker(k):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            mine = [dev.mul_relin(da, db, rk) for _ in range(8)]
+        s.synchronize()
+        res[k] = all(torch.equal(o, want) for o in mine)
+
+    ts = [threading.Thread(target=worker, args=(k,)) for k in range(6)]  # more threads than idle arenas kept per device
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert res == {k: True for k in range(6)}
 
 
 # ---------------------------------------------------------------- the byte surface (C ABI part 1)
@@ -418,7 +483,7 @@ def test_device_encrypt_roundtrip(dev, keys):
     n = 64
     vals = [int(v) for v in rng.integers(-(2**62), 2**62, size=n)]
     plains = np.stack([plain_u16("i64", v) for v in vals])
-    seeds = torch.arange(1000, 1000 + n, dtype=torch.int64).cuda()
+    seeds = torch.arange(1000 * 8, (1000 + n) * 8, dtype=torch.int64).reshape(n, 8).cuda()
     dpl = torch.from_numpy(plains.view(np.int16)).cuda()
     dpk = to_dev(keys.net_pk)
     ct = dev.encrypt(dpk, dpl, seeds)
@@ -505,8 +570,8 @@ def test_full_batch_roundtrip_properties(dev, keys):
         return torch.from_numpy(out).cuda()
 
     pk, rk, sk = to_dev(keys.net_pk), to_dev(keys.net_rk), to_dev(keys.net_sk)
-    a = dev.encrypt(pk, plains(va), torch.arange(n, dtype=torch.int64).cuda())
-    b = dev.encrypt(pk, plains(vb), torch.arange(n, 2 * n, dtype=torch.int64).cuda())
+    a = dev.encrypt(pk, plains(va), torch.arange(8 * n, dtype=torch.int64).reshape(n, 8).cuda())
+    b = dev.encrypt(pk, plains(vb), torch.arange(8 * n, 16 * n, dtype=torch.int64).reshape(n, 8).cuda())
     prod = dev.mul_relin(a, b, rk)
     dec = dev.decrypt(prod, sk).cpu().numpy().view(np.uint16).astype(np.int64)
     dec = np.where(dec >= 2048, dec - 4096, dec)  # centred coefficients; value = sum c_i 2^i
@@ -725,6 +790,9 @@ def test_mul_relin_frames_matches_oracle(dev, keys):
     import torch
 
     n, bad_layout, bad_range = 300, 7, 123
+    # one corrupted FIXED byte per frame (frame header, block headers, literal headers, sequence sections): what any zstd decoder
+    # -- and so SEAL -- would reject or read differently must never come back with status 0
+    bad_header = {20: 4, 21: 5, 22: 9, 23: 12, 24: 14 + 110 + 1, 25: 14 + 110 + 6, 26: 9 + 122, 27: 9 + 122 + 3, 28: 82054 - 7, 29: 82054 - 1}
     cts_a, cts_b = random_ct(np.random.default_rng(41), n), random_ct(np.random.default_rng(42), n)  # (constant polynomials are not
     # written as structured frames by any writer: they take the status-1 route like the libzstd frame below)
     fb_, fs = dev.frame_bytes(), dev.frame_stride()
@@ -746,6 +814,10 @@ def test_mul_relin_frames_matches_oracle(dev, keys):
     over[0, 0, 5] = MODULI[0]  # residue == q0
     fbuf[bad_range, :fb_] = np.frombuffer(F.zstd_structured_frame(F.fresh_data_ciphertext(over).payload()), dtype=np.uint8)
 
+    assert fb_ == 82054
+    for i, off in bad_header.items():
+        (fa if i & 1 else fbuf)[i, off] ^= 0x10
+
     ta, tb = torch.from_numpy(fa).pin_memory(), torch.from_numpy(fbuf).pin_memory()
     out = torch.zeros((n, fs), dtype=torch.uint8).pin_memory()
     status = torch.full((n,), -1, dtype=torch.int32).pin_memory()
@@ -753,8 +825,244 @@ def test_mul_relin_frames_matches_oracle(dev, keys):
     dev.mul_relin_frames(ta, tb, rk, out, status)
     st = status.numpy()
     assert st[bad_layout] == 1 and st[bad_range] == 1
-    ok = [i for i in range(n) if i not in (bad_layout, bad_range)]
+    assert all(st[i] == 1 for i in bad_header), [int(st[i]) for i in bad_header]
+    ok = [i for i in range(n) if i not in (bad_layout, bad_range) and i not in bad_header]
     assert (st[ok] == 0).all()
     for i in ok[:6] + ok[250:262] + ok[-4:]:
         want = F.zstd_structured_frame(F.fresh_data_ciphertext(bfv.mul_relin(cts_a[i], cts_b[i], keys.rk)).payload())
         assert out[i, :fb_].numpy().tobytes() == want, f"result frame {i} differs from the oracle's"
+
+
+# ---------------------------------------------------------------- round 2: encryptor parity, noise budget, exact types, configs 4 / 5
+# the reference's private 512-bit constant mixed into the encrypt seed (fhe.rs:604-609)
+SEED_CONSTANT = bytes([15, 17, 225, 5, 30, 1, 237, 218, 130, 19, 37, 95, 222, 218, 244, 172, 214, 175, 175, 110, 173, 103, 172, 60, 43,
+                       76, 40, 150, 215, 96, 23, 78, 22, 39, 30, 177, 107, 130, 124, 109, 27, 96, 206, 125, 104, 241, 10, 40, 88, 238,
+                       117, 118, 79, 113, 213, 110, 148, 179, 53, 19, 227, 154, 151, 122])
+
+
+def seed_words(msg: bytes) -> np.ndarray:
+    """u8_bits_to_u64_512_bits(SHA-512(msg)) (fhe.rs:47-54, 611)"""
+    import hashlib
+
+    return np.frombuffer(hashlib.sha512(msg).digest(), dtype="<u8").copy()
+
+
+def test_device_encrypt_matches_oracle(dev, keys):
+    """fhe_b200_encrypt against the oracle's restatement of its sampler (ChaCha12 over the 512-bit seed + inverse-CDF noise,
+    oracle/bfv.py gpu_sampler) and of SEAL's encrypt_zero_asymmetric + mod-switch + scaling: bit-exact, all four kinds."""
+    import torch
+
+    rng = np.random.default_rng(91)
+    vals = [("i64", -12345), ("i64", 2**62 + 17), ("u64", 2**64 - 1), ("u256", 2**255 + 9), ("frac64", -2.75), ("frac64", 1e9 + 0.5),
+            ("i64", 0), ("u64", 0)]
+    n = len(vals)
+    seeds = rng.integers(0, 2**63, size=(n, 8), dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    seeds[0] = 0  # the all-zero seed is a seed like any other
+    plains = np.stack([plain_u16(k, v) for k, v in vals])
+    for pk_np in (keys.net_pk, keys.pk):
+        ct = to_np(dev.encrypt(to_dev(pk_np), torch.from_numpy(plains.view(np.int16)).cuda(), to_dev(seeds)))
+        for i, (k, v) in enumerate(vals):
+            assert np.array_equal(ct[i], bfv.encrypt_seeded(pk_np, bfv.encode(k, v), seeds[i])), f"op {i} ({k} {v})"
+    # one flipped seed bit anywhere in the 512 changes the samples
+    base = to_np(dev.encrypt(to_dev(keys.net_pk), torch.from_numpy(plains[:1].view(np.int16)).cuda(), to_dev(seeds[1:2])))
+    for word in range(8):
+        s2 = seeds[1:2].copy()
+        s2[0, word] ^= np.uint64(1) << np.uint64(63 if word % 2 else 0)
+        other = to_np(dev.encrypt(to_dev(keys.net_pk), torch.from_numpy(plains[:1].view(np.int16)).cuda(), to_dev(s2)))
+        assert not np.array_equal(other[0, 1], base[0, 1]), f"seed word {word} is ignored"
+
+
+@pytest.mark.parametrize("kind,value", [("i64", -7), ("u64", 2**64 - 1), ("u256", 2**200 + 5), ("frac64", -2.75)])
+def test_encrypt_and_reencrypt_bytes_match_oracle(keys, kind, value):
+    """c_fhe_encrypt_* / c_fhe_reencrypt_* through the byte surface: seed = SHA-512 exactly as fhe.rs:600-611 and
+    fhe.rs:646-649, 676 build it, all 512 bits expanded by the library's sampler; bytes == the oracle's."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    ser = pack.SERIALIZE[kind](value)
+    public = bytes([9, 8, 7])
+    enc = getattr(FHE, f"encrypt_{kind}")(pack.pack_two_arguments(ser, public))
+    want = bfv.encrypt_seeded(keys.net_pk, bfv.encode(kind, value), seed_words(public + SEED_CONSTANT + ser))
+    assert enc == F.make_ciphertext(kind, want).to_bytes(structured=True)
+    packed = pack.pack_binary_operation(keys.pub_bytes, enc, public)
+    re = getattr(FHE, f"reencrypt_{kind}")(packed)
+    want2 = bfv.encrypt_seeded(keys.pk, bfv.encode(kind, value), seed_words(public + packed + ser))
+    assert re == F.make_ciphertext(kind, want2).to_bytes(structured=True)
+    assert decrypt_value(keys, kind, F.Ciphertext.from_bytes(re).polys()) == value_of(kind, value)
+
+
+def test_exhausted_noise_budget_is_failed_decryption(dev, keys):
+    """sunscreen's Runtime::decrypt refuses a ciphertext whose invariant noise budget is 0 (-> FailedDecryption = 5,
+    fhe.rs:640-643, 692-696).  A product of two products has none left at these parameters; the byte surface still
+    multiplies it happily (as the reference does), but decrypt_* and reencrypt_* must return 5, not a garbage scalar."""
+    import torch
+
+    from fhe_precompiles_b200 import FHE, FheError, pack
+
+    cts = [encrypt_value(keys, "i64", v, 40 + i, network=True) for i, v in enumerate((3, 5, 7, 11))]
+    p1 = bfv.mul_relin(cts[0], cts[1], keys.net_rk)
+    p2 = bfv.mul_relin(cts[2], cts[3], keys.net_rk)
+    deep = bfv.mul_relin(p1, p2, keys.net_rk)
+    budgets = [bfv.decrypt(c, keys.net_sk)[1] for c in (cts[0], p1, deep)]
+    assert budgets[0] > 40 and budgets[1] > 0 and budgets[2] <= 0, budgets
+    plain, flags = dev.decrypt_checked(to_dev(np.stack([cts[0], p1, deep, p2])), to_dev(keys.net_sk))
+    assert flags.cpu().tolist() == [0, 0, 1, 0]
+    assert bfv.decode("i64", plain[1].cpu().numpy().view(np.uint16).astype(np.uint64)) == 15
+    ser = lambda c: F.make_ciphertext("i64", c).to_bytes()
+    assert pack.deserialize_scalar("i64", FHE.decrypt_i64(ser(p1))) == 15
+    with pytest.raises(FheError) as e:
+        FHE.decrypt_i64(ser(deep))
+    assert e.value.code == 5
+    with pytest.raises(FheError) as e:
+        FHE.reencrypt_i64(pack.pack_binary_operation(keys.pub_bytes, ser(deep), b"\x01"))
+    assert e.value.code == 5
+    # the over-multiplied ciphertext is still a valid OPERAND (the reference's add/mul never look at the budget)
+    out = FHE.add_cipheri64_cipheri64(pack.pack_binary_operation(keys.net_pub_bytes, ser(deep), ser(p1)))
+    assert F.Ciphertext.from_bytes(out).polys().shape == (2, 2, N)
+
+
+def test_u64_and_u256_ciphertexts_do_not_mix(keys):
+    """A u64 ciphertext fed to a u256 precompile (or the reverse, or a foreign type) is an argument-type mismatch in
+    sunscreen's runtime -> code 7 (fhe.rs:28), in single calls and inside batch tiles, for every operand position."""
+    from fhe_precompiles_b200 import FHE, FheError, pack
+
+    c64 = F.make_ciphertext("u64", encrypt_value(keys, "u64", 5, 1)).to_bytes()
+    c256 = F.make_ciphertext("u256", encrypt_value(keys, "u256", 5, 2)).to_bytes()
+    s64, s256 = pack.serialize_u64(3), pack.serialize_u256(3)
+    foreign = F.Ciphertext.from_bytes(c64)
+    foreign.data_type = "sunscreen::types::bfv::rational::Rational,0.8.1,true"
+    cases = [
+        ("add_cipheru256_cipheru256", (c64, c256)), ("add_cipheru256_cipheru256", (c256, c64)), ("mul_cipheru64_cipheru64", (c256, c64)),
+        ("sub_cipheru64_cipheru64", (c64, c256)), ("add_cipheru256_u256", (c64, s256)), ("mul_u64_cipheru64", (s64, c256)),
+        ("sub_u256_cipheru256", (s256, c64)), ("add_cipheru64_cipheru64", (foreign.to_bytes(), c64)),
+        ("add_cipheri64_cipheri64", (c64, c64)),
+    ]
+    calls = []
+    for name, (x, y) in cases:
+        data = pack.pack_binary_operation(keys.pub_bytes, x, y)
+        calls.append((name, data))
+        with pytest.raises(FheError) as e:
+            getattr(FHE, name)(data)
+        assert e.value.code == 7, name
+    good = ("add_cipheru64_cipheru64", pack.pack_binary_operation(keys.pub_bytes, c64, c64))
+    res = FHE.run_batch(calls + [good] + calls, host_threads=2)
+    assert [r[0] for r in res] == [7] * len(cases) + [0] + [7] * len(cases)
+    # decrypt_* of the wrong kind: FailedDecryption (fhe.rs:696)
+    enc = FHE.encrypt_u64(pack.pack_two_arguments(s64, b"x"))
+    with pytest.raises(FheError) as e:
+        FHE.decrypt_u256(enc)
+    assert e.value.code == 5
+
+
+SCALAR_EDGES = {
+    "i64": [0, 1, -1, 2**63 - 1, -(2**63), -5, 12345],
+    "u64": [0, 1, 2**64 - 1, 2**63],
+    "u256": [0, 1, 2**256 - 1, 2**255, 2**128 + 3],
+    "frac64": [0.0, 1.0, -1.0, 0.5, -0.375, 2.0**40 + 0.25, 1.0 / 3.0, -123456.789],
+}
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_scalar_edge_cases_through_the_c_abi(keys, kind):
+    """ct o pt and pt o ct with edge scalars (0 -> transparent product accepted, negative, extreme, fractions): result
+    bytes == oracle, and the decrypted value equals the plain arithmetic in the type's own wrap-around."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    base = {"i64": -3, "u64": 7, "u256": 2**130 + 1, "frac64": 1.5}[kind]
+    ct = encrypt_value(keys, kind, base, 77)
+    ser_ct = F.make_ciphertext(kind, ct).to_bytes()
+    calls, wants = [], []
+    for v in SCALAR_EDGES[kind]:
+        for op in ("add", "sub", "mul"):
+            for shape in ("ctpt", "ptct"):
+                sc = pack.SERIALIZE[kind](v)
+                args, oargs = ((ser_ct, sc), (ct, v)) if shape == "ctpt" else ((sc, ser_ct), (v, ct))
+                calls.append((precompile_name(op, shape, kind), pack.pack_binary_operation(keys.pub_bytes, *args)))
+                wants.append(oracle_binary(op, shape, kind, *oargs, keys.rk))
+    res = FHE.run_batch(calls)
+    for (name, data), (st, out), want in zip(calls, res, wants):
+        assert st == 0, name
+        assert out == F.make_ciphertext(kind, want).to_bytes(structured=True), name  # (constant results fall back to libzstd in both)
+    # single calls give the same bytes (spot check incl. the transparent case, fhe.rs:2124-2140)
+    for i in (0, 1, 4, len(calls) - 1):
+        assert getattr(FHE, calls[i][0])(calls[i][1]) == res[i][1]
+    # decrypted values: the mul-by-0 result is all-zero (transparent) and decrypts to 0
+    k0 = [i for i, (name, _) in enumerate(calls) if name.startswith("mul")][0]
+    assert not F.Ciphertext.from_bytes(res[k0][1]).polys().any()
+    wrap = {"i64": lambda x: (x + 2**63) % 2**64 - 2**63, "u64": lambda x: x % 2**64, "u256": lambda x: x % 2**256, "frac64": float}[kind]
+    j = 0
+    for v in SCALAR_EDGES[kind]:
+        for op in ("add", "sub", "mul"):
+            for shape in ("ctpt", "ptct"):
+                x, y = (base, v) if shape == "ctpt" else (v, base)
+                exact = {"add": x + y, "sub": x - y, "mul": x * y}[op]
+                got = decrypt_value(keys, kind, F.Ciphertext.from_bytes(res[j][1]).polys())
+                if kind == "frac64":
+                    assert abs(got - exact) <= 1e-9 * max(1.0, abs(exact)), (calls[j][0], v)  # f64 rounding of the encoder only
+                else:
+                    assert got == wrap(exact), (calls[j][0], v)
+                j += 1
+
+
+def test_config4_mixed_batch_matches_oracle(keys):
+    """BASELINE config 4 at one GPU's share: 4,608 calls drawn (seed 3) uniformly from {add, sub, mul} x {ct.ct, ct.pt, pt.ct}
+    x {u64, i64, u256, frac64} -- every one of the 36 precompiles many times -- through fhe_b200_batch in tiles; EVERY result
+    byte-compared with the oracle's.  Operands come from a pool of 24 ciphertexts per kind (half libzstd level-3 frames as
+    SEAL writes them, half structured frames) so that the expected values stay a few thousand oracle calls."""
+    from fhe_precompiles_b200 import FHE, pack
+
+    rng = np.random.default_rng(3)
+    pool_n, n_calls = 24, 4608
+    vals = {"u64": lambda i: 3 + 5 * i, "i64": lambda i: (-1) ** i * (7 + i), "u256": lambda i: 2**100 + i, "frac64": lambda i: 0.5 * i - 3.25}
+    pool = {k: [encrypt_value(keys, k, value_of(k, vals[k](i)), 2000 + 100 * ki + i) for i in range(pool_n)] for ki, k in enumerate(KINDS)}
+    ser = {k: [F.make_ciphertext(k, c).to_bytes(structured=bool(i & 1)) for i, c in enumerate(pool[k])] for k in KINDS}
+    scal = {k: [value_of(k, vals[k](i + 1)) for i in range(6)] for k in KINDS}
+    calls, keys_of = [], []
+    cache = {}
+    for _ in range(n_calls):
+        op = ("add", "sub", "mul")[rng.integers(3)]
+        shape = SHAPES[rng.integers(3)]
+        kind = KINDS[rng.integers(4)]
+        i, j = int(rng.integers(pool_n)), int(rng.integers(pool_n if shape == "ctct" else 6))
+        if shape == "ctct":
+            args, oargs = (ser[kind][i], ser[kind][j]), (pool[kind][i], pool[kind][j])
+        elif shape == "ctpt":
+            args, oargs = (ser[kind][i], pack.SERIALIZE[kind](scal[kind][j])), (pool[kind][i], scal[kind][j])
+        else:
+            args, oargs = (pack.SERIALIZE[kind](scal[kind][j]), ser[kind][i]), (scal[kind][j], pool[kind][i])
+        key = (op, shape, kind, i, j)
+        if key not in cache:
+            cache[key] = (pack.pack_binary_operation(keys.pub_bytes, *args), oargs)
+        calls.append((precompile_name(op, shape, kind), cache[key][0]))
+        keys_of.append(key)
+    assert len({c[0] for c in calls}) == 36
+    res = FHE.run_batch(calls)
+    assert all(st == 0 for st, _ in res)
+    want_bytes = {}
+    for key, (st, out) in zip(keys_of, res):
+        if key not in want_bytes:
+            op, shape, kind = key[:3]
+            w = oracle_binary(op, shape, kind, *cache[key][1], keys.rk)
+            want_bytes[key] = F.make_ciphertext(kind, w).to_bytes(structured=True)
+        assert out == want_bytes[key], key
+
+
+def test_config5_encrypt_decrypt_roundtrip(dev, keys):
+    """BASELINE config 5 at one GPU's share of 16,384: pk-encrypt 2,048 random i64 under network.pub on the GPU, decrypt with
+    network.pri, all equal, no ciphertext flagged as exhausted; 32 ciphertexts bit-compared with the oracle's encryptor."""
+    import torch
+
+    n = 2048
+    rng = np.random.default_rng(5)
+    vals = rng.integers(-(2**62), 2**62, size=n)
+    mag = np.abs(vals).astype(np.uint64)
+    bits = ((mag[:, None] >> np.arange(64, dtype=np.uint64)[None, :]) & 1).astype(np.int64)
+    plains = np.zeros((n, N), dtype=np.uint16)
+    plains[:, :64] = np.where(vals[:, None] < 0, bits * 4095, bits).astype(np.uint16)
+    seeds = rng.integers(0, 2**63, size=(n, 8), dtype=np.uint64)
+    ct = dev.encrypt(to_dev(keys.net_pk), torch.from_numpy(plains.view(np.int16)).cuda(), to_dev(seeds))
+    plain, flags = dev.decrypt_checked(ct, to_dev(keys.net_sk))
+    assert not flags.any()
+    assert np.array_equal(plain.cpu().numpy().view(np.uint16), plains)
+    cts = to_np(ct)
+    for i in range(0, n, 64):
+        assert np.array_equal(cts[i], bfv.encrypt_seeded(keys.net_pk, plains[i, :64].astype(np.uint64), seeds[i])), f"op {i}"
