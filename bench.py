@@ -28,16 +28,31 @@ CT_BYTES = 2 * 2 * N * 8  # 131,072
 ALGO_BYTES_PER_OP = 3 * CT_BYTES  # read a, read b, write result = 393,216 B
 # 47 limb-NTTs x 24,576 butterflies per op
 BUTTERFLIES_PER_OP = 47 * 24576
-# FMA-pipe cost of the arithmetic as written (modarith.cuh), in IMAD.WIDE equivalents (IMAD.WIDE is quarter rate on B200: 32 per
-# clock per SM, measured; IMAD half rate = 0.5 equivalents):
-#   butterflies: 14 forward on 36/37-bit primes 4 wide + 5 low = 6.5, 12 inverse on them 5 + 4 = 7, 21 on 61-bit primes 6 + 3 = 7.5
-#                -> 7.07 on average
-#   pointwise  : counted from the kernels' SASS per coefficient -- k_ext_conv 42.5 x 16,384, k_floor_sk 113 x 12,288, the tensor
-#                (mulsum) 0.51 M, the key-switch MAC 0.28 M, the division by P 0.13 M -> 3.0 M per op
-# (the base conversions as SEAL states them, 0.79 M 64-bit modmuls, would be about twice the pointwise figure)
-WIDE_EQ_PER_BUTTERFLY = 7.07
-POINTWISE_WIDE_EQ_PER_OP = 3.0e6
-WIDE_EQ_PER_OP = BUTTERFLIES_PER_OP * WIDE_EQ_PER_BUTTERFLY + POINTWISE_WIDE_EQ_PER_OP
+# Integer-pipe roofline.  The binding resource is the SM's 32-bit multiplier (the "heavy" half of the FMA pipe): IMAD.WIDE /
+# IMAD.HI issue at 32 results per clock per SM (quarter rate), IMAD at 64 (half rate = 0.5 IMAD.WIDE-equivalents).
+# ALGORITHMIC multiplier work of one ct x ct multiply + relinearise, in IMAD.WIDE-equivalents -- the cheapest exact
+# formulation we know on a 32-bit multiplier, independent of how a kernel happens to be scheduled:
+#   one Shoup butterfly X +- w Y by a precomputed (w, floor(w 2^64 / q)):
+#     36/37-bit primes, forward : quotient estimate 2 wide + 1 low, low product 1 wide + 2 low, -H q 1 wide + 2 low = 4 w + 5 l = 6.5
+#     36/37-bit primes, inverse : operand range 2^51 needs one more partial product of the quotient            = 5 w + 4 l = 7.0
+#     61-bit primes             : exact quotient 4 partial products (the lowest feeds one carry), low product 1 w + 2 l,
+#                                 -H q as H c - (H << 61): 1 w + 1 l                                            = 6 w + 3 l = 7.5
+#   NTTs per op: 14 forward + 12 inverse on 36/37-bit primes, 12 forward + 9 inverse on 61-bit primes (26 + 21)
+#   pointwise (base conversions in the integer domain, tensor, key-switch MAC, division by P), per kernel below.
+# Per kernel (what bench.py's live CUDA-event timing is divided into):
+KERNEL_WIDE_EQ = {
+    "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
+    "k_ext_ntt": 24576 * (8 * 6.5 + 12 * 7.5),                   # 20 forward NTTs: 8 on q limbs, 12 on the Bsk limbs
+    "k_tensor_intt": 24576 * (6 * 7.0 + 9 * 7.5) + 0.51e6,       # 15 inverse NTTs + the dyadic tensor
+    "k_floor_sk": 113.0 * 12288,                                 # fast_floor + fastbconv_sk per coefficient of the 3 output polys
+    "k_digit_ntt": 24576 * 6 * 6.5,                              # 6 key-switch digit NTTs
+    "k_ks_finish": 24576 * 6 * 7.0 + 0.28e6 + 0.13e6,            # key MAC + 6 inverse NTTs + rounded division by P
+}
+KERNEL_WIDE_EQ["k_ks_intt"] = 24576 * 6 * 7.0 + 0.28e6           # the unfused tail (small chunks): MAC + inverse NTTs
+KERNEL_WIDE_EQ["k_relin_finish"] = 0.13e6                        #   ... and the division by P
+WIDE_EQ_PER_OP = sum(KERNEL_WIDE_EQ[k] for k in ("k_ext_conv", "k_ext_ntt", "k_tensor_intt", "k_floor_sk", "k_digit_ntt", "k_ks_finish"))
+SM_COUNT = 148
+WIDE_PER_CLK_PER_SM = 32  # IMAD.WIDE results per clock per SM (scripts/pipe_probe.cu: 0.25 warp-instructions / clk / SMSP)
 METRIC = "ct_ct_fhe_multiply_relin_ops_per_sec"
 WORKLOAD = "batch of 4096 ct*ct fhe_multiply+relinearize per GPU, testnet BFV params (N=4096, q=72b, t=4096)"
 
@@ -197,6 +212,117 @@ def e2e_frames(fdev, a_h, b_h, out_h, rk_host, device_index, steps, world, barri
     }
 
 
+def e2e_byte_surface(fdev, a, b, net_pub: bytes, steps: int, world: int, barrier, dist, n_calls: int = 4096, distinct: int = 512) -> dict:
+    """The metric through the reference's TRUE byte surface: `n_calls` packed mul_cipheri64_cipheri64 inputs (pack.rs framing:
+    offsets + the 411 KB PublicKey + two bincode ciphertexts whose SEAL blobs are libzstd level-3 frames, as SEAL writes them)
+    in ordinary host memory -> fhe_b200_batch -> packed result bytes in malloc'd buffers.  Everything the reference does per
+    call is inside the timed region: framing, key lookup, operand inflate + validation, H2D, kernels, D2H, result framing."""
+    import ctypes
+
+    import numpy as np
+
+    from fhe_precompiles_b200 import FHE, _lib, pack
+    from fhe_precompiles_b200.sharding import max_over_ranks
+
+    L = _lib.lib()
+    dt_ = b"sunscreen::types::bfv::signed::Signed,0.8.1,true"
+
+    def to_bytes(words) -> bytes:
+        o, ln = ctypes.c_void_p(), ctypes.c_int64()
+        w = np.ascontiguousarray(words)
+        assert L.fhe_b200_write_ciphertext(w.ctypes.data, dt_, ctypes.byref(o), ctypes.byref(ln)) == 0
+        buf = ctypes.string_at(o.value, ln.value)
+        L.fhe_free(o)
+        return buf
+
+    an, bn = a[:distinct].cpu().numpy().view(np.uint64), b[:distinct].cpu().numpy().view(np.uint64)
+    prev = L.fhe_b200_set_zstd_writer(0)  # operands as SEAL writes them: libzstd level 3
+    packed = [pack.pack_binary_operation(net_pub, to_bytes(an[i]), to_bytes(bn[i])) for i in range(distinct)]
+    L.fhe_b200_set_zstd_writer(prev)
+    bufs = [(ctypes.c_char * len(p)).from_buffer_copy(p) for p in packed]  # every call has its own copy of the key bytes
+    op_index = L.fhe_b200_op_index(b"mul_cipheri64_cipheri64")
+    arr = (_lib.BatchCall * n_calls)()
+    in_bytes = 0
+    for i in range(n_calls):
+        arr[i].op, arr[i].bytes, arr[i].bytes_length = op_index, ctypes.cast(bufs[i % distinct], ctypes.c_void_p), len(packed[i % distinct])
+        in_bytes += len(packed[i % distinct])
+    threads = max(2, 2 * (os.cpu_count() or 2) // world)
+
+    def one_batch(check: bool = False) -> int:
+        failed = L.fhe_b200_batch(arr, n_calls, threads)
+        out_bytes = 0
+        first = ctypes.string_at(arr[0].output, arr[0].output_length) if check and arr[0].status == 0 else None
+        for i in range(n_calls):
+            out_bytes += arr[i].output_length
+            L.fhe_free(arr[i].output)
+        if check:
+            assert failed == 0 and first == FHE.mul_cipheri64_cipheri64(packed[0])
+        return out_bytes
+
+    out_bytes = one_batch(check=True)  # warm (lanes grow to their tile size) + result check against the single-call symbol
+    one_batch()
+    barrier()
+    reps = max(2, min(steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        one_batch()
+    dt = time.perf_counter() - t0
+    barrier()
+    dt_max = max_over_ranks(dt, dist)
+    return {
+        "value": world * n_calls * reps / dt_max,
+        "unit": "calls/s",
+        "calls_per_step": n_calls,
+        "distinct_inputs": distinct,
+        "host_threads": threads,
+        "input_bytes_per_step": in_bytes,
+        "output_bytes_per_step": out_bytes,
+        "api": "fhe_b200_batch over pack.rs-framed inputs (c_fhe_mul_cipheri64_cipheri64 semantics per call); operand frames libzstd level 3",
+        "device_zstd": os.environ.get("FHE_B200_DEVICE_ZSTD", "default"),
+    }
+
+
+def pcie_ceiling(torch, dev, world: int, barrier, dist, seconds: float = 0.6) -> dict:
+    """Platform ceiling of the host-buffer paths: pinned-memory H2D and D2H cudaMemcpyAsync running concurrently on two streams
+    (64 MiB per copy, like one pipeline chunk), every rank at once; whole-job GB/s = sum over ranks."""
+    from fhe_precompiles_b200.sharding import max_over_ranks
+
+    nbytes = 64 << 20
+    h_in = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def run(both: bool, h2d: bool, iters: int):
+        for _ in range(iters):
+            if both or h2d:
+                with torch.cuda.stream(s1):
+                    d_in.copy_(h_in, non_blocking=True)
+            if both or not h2d:
+                with torch.cuda.stream(s2):
+                    h_out.copy_(d_out, non_blocking=True)
+        s1.synchronize(), s2.synchronize()
+
+    res = {}
+    for name, both, h2d in (("h2d_alone", False, True), ("d2h_alone", False, False), ("concurrent", True, True)):
+        run(both, h2d, 4)
+        iters = 8
+        barrier()
+        t0 = time.perf_counter()
+        run(both, h2d, iters)
+        dt = time.perf_counter() - t0
+        while dt < seconds / 4 and iters < 4096:
+            iters *= 2
+            t0 = time.perf_counter()
+            run(both, h2d, iters)
+            dt = time.perf_counter() - t0
+        barrier()
+        dt_max = max_over_ranks(dt, dist)
+        res[name + "_GBps_per_direction"] = world * iters * nbytes / dt_max / 1e9
+    return res
+
+
 def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 1000) -> dict:
     """p50 / p99 of one c_fhe_mul_cipheri64_cipheri64 call (warm key cache): packed bytes in, packed bytes out,
     i.e. bincode + zstd inflate of two ciphertexts, H2D, six kernels, D2H, zstd deflate.  Also times the codec alone."""
@@ -307,6 +433,66 @@ def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 100
     }
 
 
+# ---- the reference's byte-surface call on the CPU (fhe.rs:21-30 + pack.rs:238-266), restated with the format oracle:
+# deserialise the PublicKey (two zstd blobs), both ciphertext operands, multiply + relinearise, serialise the result with
+# zstd level 3.  Forked workers (one per host core) share the packed inputs through the parent's address space.
+_BS_CALLS = None
+
+
+def _bs_worker(rng_):
+    from oracle import bfv
+    from oracle import formats as F
+
+    from fhe_precompiles_b200 import pack  # pure-Python mirror of pack.rs (no GPU, no library call)
+
+    lo, hi = rng_
+    total = 0
+    for i in range(lo, hi):
+        pkb, ab, bb = pack.unpack_binary_operation(_BS_CALLS[i])
+        rk = bfv.rk_array(F.PublicKey.from_bytes(pkb).relin())
+        a, b = F.Ciphertext.from_bytes(ab), F.Ciphertext.from_bytes(bb)
+        out = bfv.mul_relin(a.polys(), b.polys(), rk)
+        total += len(F.make_ciphertext("i64", out).to_bytes())
+    return total
+
+
+def cpu_byte_surface(calls, cores: int, reps: int = 1):
+    """calls/s of the CPU byte-surface path over `calls` (list of packed inputs) on `cores` forked workers."""
+    import multiprocessing as mp
+
+    global _BS_CALLS
+    _BS_CALLS = calls
+    n = len(calls)
+    step = (n + cores - 1) // cores
+    ranges = [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_bs_worker, [(0, 1)] * cores)  # warm: imports, liboracle, libzstd in every worker
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pool.map(_bs_worker, ranges)
+        dt = time.perf_counter() - t0
+    return n * reps / dt, dt
+
+
+def oracle_packed_calls(n: int, seed: int, net_pub: bytes):
+    """n packed `mul_cipheri64_cipheri64` inputs whose operands are serialised as SEAL writes them (bincode + zstd level 3)."""
+    import numpy as np
+
+    from oracle import formats as F
+
+    from fhe_precompiles_b200 import pack
+
+    rng = np.random.default_rng(seed)
+    calls = []
+    for _ in range(n):
+        cts = np.empty((2, 2, 2, N), dtype=np.uint64)
+        for l in range(2):
+            cts[:, :, l, :] = rng.integers(0, Q[l], size=(2, 2, N), dtype=np.uint64)
+        sa, sb = (F.make_ciphertext("i64", c).to_bytes() for c in cts)
+        calls.append(pack.pack_binary_operation(net_pub, sa, sb))
+    return calls
+
+
 def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -318,13 +504,14 @@ def run_reference(args) -> None:
 
     cores = os.cpu_count() or 1
     rng = np.random.default_rng(2)
-    sample = max(cores * 16, 256)  # ~0.1 s of wall time per step with every host thread busy
+    sample = args.batch  # the SAME batch as the b200 arm: 4,096 ct x ct multiply + relinearise per step
     a = np.empty((sample, 2, 2, N), dtype=np.uint64)
     b = np.empty_like(a)
     for l in range(2):
         a[:, :, l, :] = rng.integers(0, Q[l], size=(sample, 2, N), dtype=np.uint64)
         b[:, :, l, :] = rng.integers(0, Q[l], size=(sample, 2, N), dtype=np.uint64)
-    pk = F.PublicKey.from_bytes(open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read())
+    net_pub = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read()
+    pk = F.PublicKey.from_bytes(net_pub)
     rk = bfv.rk_array(pk.relin())
     for _ in range(args.warmup):
         bfv.batch_mul_relin(a, b, rk, cores)
@@ -333,6 +520,14 @@ def run_reference(args) -> None:
         bfv.batch_mul_relin(a, b, rk, cores)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
+    # the same op through the reference's BYTE surface on the CPU (packed bytes in, packed bytes out), bounded sample
+    bs = None
+    if not args.no_e2e:
+        n_bs = max(4 * cores, 128)
+        calls = oracle_packed_calls(n_bs, 5, net_pub)
+        rate, secs = cpu_byte_surface(calls, cores)
+        bs = {"value": rate, "unit": "calls/s", "cores": cores, "sample": f"{n_bs} packed mul_cipheri64_cipheri64 calls, {secs:.2f} s",
+              "what": "PublicKey + 2 operands inflated (libzstd), oracle multiply + relinearise, result deflated at zstd level 3, per call"}
     line = {
         "impl": "reference",
         "metric": METRIC,
@@ -346,8 +541,9 @@ def run_reference(args) -> None:
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "u64",
-        "data": "synthetic uniform residues",
-        "config": {"workload": WORKLOAD, "sample_ops_per_step": sample},
+        "data": "synthetic uniform residues mod (q0,q1), seed 2",
+        "config": {"workload": WORKLOAD, "ops_per_gpu_per_step": sample, "same_config": sample == 4096,
+                   "note": "one step = the whole 4,096-op batch on every host thread (limb arrays in host memory, like the b200 arm's e2e)"},
         "cpu_baseline": {
             "value": value,
             "unit": "ops/s",
@@ -359,6 +555,8 @@ def run_reference(args) -> None:
         "e2e": {"value": value, "unit": "ops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if bs is not None:
+        line["byte_surface"] = bs
     print(json.dumps(line), flush=True)
 
 
@@ -371,6 +569,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=4096, help="ct x ct ops per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the quick runs of BASELINE configs 2, 4 and 5")
+    ap.add_argument("--sustain-seconds", type=float, default=0.0, help="extra device-resident run of at least this long with the clock sampler (recorded under `sustained`)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="ops in the CPU-baseline sample (0 = ~20 s of CPU work)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -397,7 +597,9 @@ def main() -> None:
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("gloo")
+        import datetime
+
+        dist.init_process_group("gloo", timeout=datetime.timedelta(seconds=600))  # a lost rank fails the run instead of hanging it
 
     os.environ.setdefault("FHE_B200_DEVICES", str(local_rank))  # this rank's byte-surface calls stay on its own GPU
     from fhe_precompiles_b200 import device as fdev
@@ -442,6 +644,27 @@ def main() -> None:
     ms_max = max_over_ranks(ms, dist)
     value = whole_job_rate(n * args.steps, world, ms_max * 1e-3)
 
+    # ---------------- optional sustained run (>= --sustain-seconds of back-to-back steps): clocks, power and rate under a long load
+    sustained = None
+    if args.sustain_seconds > 0:
+        sampler2 = ClockSampler(local_rank)
+        sampler2.start()
+        steps_s = 0
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall = time.perf_counter()
+        s0.record()
+        while time.perf_counter() - t_wall < args.sustain_seconds:
+            for _ in range(25):
+                fdev.mul_relin(a, b, rk, out=out)
+            steps_s += 25
+            torch.cuda.synchronize()
+        s1.record()
+        torch.cuda.synchronize()
+        ms_s = s0.elapsed_time(s1)
+        sustained = {"seconds": ms_s * 1e-3, "steps": steps_s, "ops_per_s_per_gpu": n * steps_s / (ms_s * 1e-3), "clocks": sampler2.stop(),
+                     "ratio_to_timed_region": (n * steps_s / ms_s) / (n * args.steps / ms)}
+        barrier()
+
     # ---------------- end to end through the C ABI with host buffers
     e2e = None
     if not args.no_e2e:
@@ -473,6 +696,37 @@ def main() -> None:
             e2e["serialized"] = e2e_frames(fdev, a_h, b_h, out_h, rk_host, local_rank, args.steps, world, barrier, dist)
         except Exception as ex:  # pragma: no cover
             e2e["serialized"] = {"error": str(ex)}
+        del a_h, b_h, out_h
+        # the platform's ceiling for those two paths: concurrent pinned H2D + D2H on every rank at once
+        try:
+            ceil = pcie_ceiling(torch, dev, world, barrier, dist)
+            both = ceil["concurrent_GBps_per_direction"] * 1e9
+            lim = lambda h2d, d2h: min(both / (h2d / n), both / (d2h / n))  # ops/s if the copies were all there is
+            ceil["limb_arrays_ops_per_s"] = lim(e2e["h2d_bytes_per_step"], e2e["d2h_bytes_per_step"])
+            e2e["frac_of_platform_ceiling"] = e2e["value"] / ceil["limb_arrays_ops_per_s"]
+            if "value" in e2e["serialized"]:
+                ceil["frames_ops_per_s"] = lim(e2e["serialized"]["h2d_bytes_per_step"], e2e["serialized"]["d2h_bytes_per_step"])
+                e2e["serialized"]["frac_of_platform_ceiling"] = e2e["serialized"]["value"] / ceil["frames_ops_per_s"]
+            e2e["platform_ceiling"] = ceil
+        except Exception as ex:  # pragma: no cover
+            e2e["platform_ceiling"] = {"error": str(ex)}
+        # the reference's true byte surface (packed bytes with libzstd-written operands in, packed bytes out)
+        try:
+            e2e["byte_surface"] = e2e_byte_surface(fdev, a, b, net_pub, args.steps, world, barrier, dist)
+        except Exception as ex:  # pragma: no cover
+            e2e["byte_surface"] = {"error": str(ex)}
+
+    # ---------------- the other BASELINE configs (2: NTT microbenchmark, 4: 65,536 mixed calls, 5: 16,384 encrypt + decrypt),
+    # sharded over the ranks like the headline (no collective); quick settings, the full sweep is scripts/bench_configs.py
+    configs = None
+    if not args.no_configs:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_configs
+
+            configs = bench_configs.run_configs(rank, world, dist, quick=True)
+        except Exception as ex:  # pragma: no cover
+            configs = {"error": str(ex)}
 
     if rank != 0:
         if dist is not None:
@@ -485,72 +739,78 @@ def main() -> None:
         latency = call_latency(fdev, a, b, local_rank, net_pub)
 
     # ---------------- roofline of the dominant kernel (live CUDA-event durations from the timed region)
+    # bound = the 32-bit integer multiplier (FMA-heavy pipe), not HBM: SURVEY 8(d).  achieved = ALGORITHMIC IMAD.WIDE-equivalents
+    # per launch of the dominant kernel / its average launch duration; peak = the mul.wide.u32 rate measured on this GPU right
+    # here (fhe_b200_int_peak; MEASURED_PEAKS.json holds no integer figure), with the theoretical 148 SM x 32 / clk next to it.
     peak_gbs, peak_src = measured_peaks()
     dom = max(kt, key=lambda k: kt[k][0])
     dom_ms, dom_launches = kt[dom]
     total_kernel_ms = sum(v[0] for v in kt.values())
     ops_per_launch = n * args.steps / max(dom_launches, 1)
     avg_launch_ms = dom_ms / max(dom_launches, 1)
-    achieved = ops_per_launch * ALGO_BYTES_PER_OP / (avg_launch_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # DRAM bytes per op of each kernel from the committed ncu capture (profiles/), scaled to one launch
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            table = json.load(f)["dram_bytes_per_op"]
-        # the timed slot "k_ext_ntt" runs k_ext_ntt2 (transforms only) since the base extension became its own kernel
-        names = ("k_ext_ntt2",) if dom == "k_ext_ntt" and "k_ext_ntt2" in table else (dom,)
-        parts = [table[k] for k in names if k in table]
-        per_op = sum(parts) if parts else None
-        if per_op is not None:
-            traffic = per_op * ops_per_launch
-    except Exception:
-        traffic = None
-    ncu_heavy = None
-    try:
+    prof = {}
+    try:  # the committed ncu capture (profiles/): DRAM bytes per op and FMA-heavy pipe utilisation of each kernel
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             prof = json.load(f)
-        ncu_heavy = {"tag": prof.get("tag"), "pct": prof.get("fmaheavy_pct")}
     except Exception:
-        pass
-    roofline = {
-        "bound": "hbm",
-        "kernel": dom,
-        "achieved": achieved,
-        "peak": peak_gbs,
-        "unit": "GB/s",
-        "frac": achieved / peak_gbs,
-        "traffic": traffic,
-        "peak_source": peak_src,
-        "avg_launch_ms": avg_launch_ms,
-        "ops_per_launch": ops_per_launch,
-        "kernel_share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
-        "kernel_ms": {k: v[0] for k, v in kt.items()},
-        "note": "the multiply kernels are bound by the FMA (integer multiply) pipe, not HBM (SURVEY 8d); see int_pipe",
-    }
+        prof = {}
+    table = prof.get("dram_bytes_per_op", {})
+    ncu_name = "k_ext_ntt2" if dom == "k_ext_ntt" and "k_ext_ntt2" in table else dom  # the timed slot k_ext_ntt runs k_ext_ntt2
+    traffic = table[ncu_name] * ops_per_launch if ncu_name in table else None
+    sm_clock_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
+    peak_theory = SM_COUNT * WIDE_PER_CLK_PER_SM * sm_clock_ghz / 1e3  # T IMAD.WIDE/s at the clock observed under load
     try:
         peak_wide = fdev.int_peak(local_rank, wide=1)  # T IMAD.WIDE/s (mul.wide.u32 with a loop-carried operand)
         peak_lo = fdev.int_peak(local_rank, wide=0)
-        ops_s = n * args.steps / (ms * 1e-3)
-        ach = ops_s * WIDE_EQ_PER_OP / 1e12
-        # butterfly-rate ceiling: register-only NTT inner loop, per prime class (26 small + 21 large limb-NTTs per op)
         bf_small, bf_big = fdev.bfly_peak(local_rank, 0), fdev.bfly_peak(local_rank, 3)
-        ntt_floor_us = 24576 * (26 / bf_small + 21 / bf_big) * 1e-3
-        int_pipe = {
-            "achieved": ach,
-            "peak": peak_wide,
-            "unit": "T IMAD.WIDE-equivalents/s (FMA pipe)",
-            "frac": ach / peak_wide,
-            "model": f"{BUTTERFLIES_PER_OP} butterflies/op x {WIDE_EQ_PER_BUTTERFLY} + {POINTWISE_WIDE_EQ_PER_OP:.2e} pointwise IMAD.WIDE equivalents "
-            "(multiplies as written in modarith.cuh, IMAD = 0.5); peak = measured mul.wide.u32 rate",
-            "measured_pipe_rates_T_per_s": {"IMAD.WIDE": peak_wide, "IMAD": peak_lo},
-            "butterfly_peak_G_per_s": {"36-37 bit primes": bf_small, "61 bit primes": bf_big},
-            "ntt_only_floor_us_per_op": ntt_floor_us,
-            "frac_of_butterfly_ceiling": ntt_floor_us * 1e-6 * ops_s,
-            # sm__pipe_fmaheavy_cycles_active of the committed ncu capture (profiles/<tag>_kernels.md): IMAD / IMAD.WIDE issue
-            # only to the heavy half of the FMA pipe, so this is the measured utilisation of the limiter, per kernel
-            "ncu_fmaheavy_pct": ncu_heavy,
-        }
     except Exception as e:  # pragma: no cover
-        int_pipe = {"error": str(e)}
+        raise SystemExit(f"bench.py: integer-pipe probe failed: {e}")
+    ops_s = n * args.steps / (ms * 1e-3)
+    dom_weq = KERNEL_WIDE_EQ.get(dom)
+    ach_dom = dom_weq * ops_per_launch / (avg_launch_ms * 1e-3) / 1e12 if dom_weq else None
+    ach_op = ops_s * WIDE_EQ_PER_OP / 1e12
+    per_kernel = {}
+    for k, (kms, kl) in kt.items():
+        if k in KERNEL_WIDE_EQ and kms > 0:
+            a = KERNEL_WIDE_EQ[k] * n * args.steps / (kms * 1e-3) / 1e12
+            per_kernel[k] = {"us_per_op": kms * 1e3 / (n * args.steps), "achieved": a, "frac": a / peak_wide, "frac_of_theoretical": a / peak_theory,
+                             "share_of_step": kms / total_kernel_ms,
+                             "ncu_fmaheavy_pct": (prof.get("fmaheavy_pct") or {}).get("k_ext_ntt2" if k == "k_ext_ntt" else k)}
+    ntt_floor_us = 24576 * (26 / bf_small + 21 / bf_big) * 1e-3
+    hbm_ach = ops_per_launch * ALGO_BYTES_PER_OP / (avg_launch_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "int_pipe",
+        "kernel": dom,
+        "achieved": ach_dom,
+        "peak": peak_wide,
+        "unit": "T IMAD.WIDE-equivalents/s (32-bit multiplier, FMA-heavy pipe)",
+        "frac": ach_dom / peak_wide if ach_dom else None,
+        "traffic": traffic,
+        "peak_source": "measured here: fhe_b200_int_peak (mul.wide.u32, loop-carried operands, 2 x 1024 threads per SM)",
+        "peak_theoretical": peak_theory,
+        "frac_of_theoretical": ach_dom / peak_theory if ach_dom else None,
+        "algorithmic_wide_eq_per_op": {"dominant_kernel": dom_weq, "whole_op": WIDE_EQ_PER_OP,
+                                       "model": "14+12 fwd / 12+9 inv limb-NTTs x 24,576 butterflies at 6.5 / 7.0 (36-37 bit) and 7.5 (61 bit) "
+                                                "IMAD.WIDE-equivalents + pointwise per kernel (bench.py KERNEL_WIDE_EQ, DESIGN.md section 4)"},
+        "whole_op": {"achieved": ach_op, "frac": ach_op / peak_wide, "frac_of_theoretical": ach_op / peak_theory, "us_per_op": 1e6 / ops_s,
+                     "pipe_bound_us_per_op": WIDE_EQ_PER_OP / (peak_wide * 1e12) * 1e6},
+        "per_kernel": per_kernel,
+        "avg_launch_ms": avg_launch_ms,
+        "ops_per_launch": ops_per_launch,
+        "kernel_share_of_step": dom_ms / total_kernel_ms if total_kernel_ms else None,
+        "measured_pipe_rates_T_per_s": {"IMAD.WIDE": peak_wide, "IMAD": peak_lo},
+        "butterfly_peak_G_per_s": {"36-37 bit primes": bf_small, "61 bit primes": bf_big},
+        "ntt_only_floor_us_per_op": ntt_floor_us,
+        "ncu": {"tag": prof.get("tag"), "fmaheavy_pct": prof.get("fmaheavy_pct")},
+        # secondary: the HBM form SURVEY 8(d) defines (393,216 algorithmic bytes per op) -- the op is far from HBM-bound
+        "hbm": {
+            "achieved": hbm_ach, "peak": peak_gbs, "unit": "GB/s", "frac": hbm_ach / peak_gbs, "peak_source": peak_src,
+            "algorithmic_bytes_per_op": ALGO_BYTES_PER_OP,
+            "whole_op_frac": ops_s * ALGO_BYTES_PER_OP / 1e9 / peak_gbs,
+            "dram_bytes_per_op_ncu": prof.get("dram_bytes_per_op_total"),
+            "traffic_over_algorithmic": (prof.get("dram_bytes_per_op_total") or 0) / ALGO_BYTES_PER_OP or None,
+        },
+    }
 
     line = {
         "metric": METRIC,
@@ -575,7 +835,6 @@ def main() -> None:
             "kernels": "split" if not int(os.environ.get("FHE_B200_FUSED", "0")) else "fused",
         },
         "roofline": roofline,
-        "int_pipe": int_pipe,
         "clocks": clocks,
         "gpu_launches": int(launches),
     }
@@ -583,6 +842,10 @@ def main() -> None:
         line["e2e"] = e2e
     if latency is not None:
         line["latency"] = latency
+    if configs is not None:
+        line["configs"] = configs
+    if sustained is not None:
+        line["sustained"] = sustained
 
     # ---------------- CPU baseline on the box's host cores (N=1 only), also the parity checker for the sample
     if world == 1 and not args.no_cpu_baseline:

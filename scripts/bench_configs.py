@@ -43,16 +43,9 @@ def rand_ct(n, seed):
     return out
 
 
-def main():
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist  # barrier + max-over-ranks only (gloo): the configs shard with no collective
-
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("gloo")
+def run_configs(rank: int, world: int, dist, quick: bool = False) -> dict:
+    """Configs 2, 4 and 5 on the current CUDA device of every rank (fdev.init done by the caller); returns the whole-job record
+    (identical on every rank up to rank-0-only fields).  quick: fewer NTT batch sizes and repetitions (bench.py's `configs`)."""
     from fhe_precompiles_b200.sharding import call_cost, max_over_ranks, shard_by_cost, shard_range
 
     def sync():
@@ -60,24 +53,25 @@ def main():
         if dist is not None:
             dist.barrier()
 
-    fdev.init(local)
+    iters = 2 if quick else 3
     res = {"n_gpus": world}
-    # ---- config 2
+    # ---- config 2 (one GPU by definition: every rank runs it, rank 0's numbers are reported)
     ntt = []
     g = torch.Generator(device="cuda")
     g.manual_seed(1)
-    for batch in ((1, 4, 16, 64, 256, 1024, 4096, 16384, 65536) if world == 1 else ()):
+    batches = (1, 256, 4096, 65536) if quick else (1, 4, 16, 64, 256, 1024, 4096, 16384, 65536)
+    for batch in batches:
         x = torch.empty((batch, 3, N), dtype=torch.int64, device="cuda")
         for l in range(3):
             x[:, l, :] = torch.randint(0, MODULI[l], (batch, N), generator=g, device="cuda", dtype=torch.int64)
-        f = timeit(lambda: fdev.ntt_(x, [0, 1, 2]))
-        i = timeit(lambda: fdev.ntt_(x, [0, 1, 2], inverse=True))
+        f = timeit(lambda: fdev.ntt_(x, [0, 1, 2]), iters=iters + 2)
+        i = timeit(lambda: fdev.ntt_(x, [0, 1, 2], inverse=True), iters=iters + 2)
         ntt.append({"polys": batch, "limbs": 3 * batch, "fwd_ms": f, "inv_ms": i,
                     "fwd_Mlimb_per_s": 3 * batch / f / 1e3, "inv_Mlimb_per_s": 3 * batch / i / 1e3,
                     "fwd_GBps": 3 * batch * 65536 / f / 1e6})
         del x
     res["config2_ntt"] = ntt
-    # ---- config 4: 65,536 mixed calls on one GPU (device-resident operands), grouped by kernel family
+    # ---- config 4: 65,536 mixed calls (device-resident operands), grouped by kernel family
     net_pub = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pub"), "rb").read()
     pk_h, rk_h = fdev.parse_public_key(net_pub)
     rk, pk = rk_h.cuda(), pk_h.cuda()
@@ -119,10 +113,11 @@ def main():
             run_family(o, s, n)
 
     sync()
-    ms = max_over_ranks(timeit(run_all, iters=3, warm=1), dist)
+    ms = max_over_ranks(timeit(run_all, iters=iters, warm=1), dist)
     sync()
     res["config4_mixed"] = {"calls": n_calls, "ms": ms, "calls_per_s": n_calls / ms * 1e3, "calls_on_rank0": len(mine),
                             "mix": {f"{'add sub mul'.split()[o]}_{'ctct ctpt ptct'.split()[s]}": n for (o, s), n in counts.items()}}
+    del a, b, plain, out
     # ---- config 5: encrypt 16,384 random i64 under the network key, decrypt, compare
     n_total = 16384
     lo, hi = shard_range(n_total, rank, world)
@@ -134,23 +129,38 @@ def main():
     pl = np.zeros((n, N), dtype=np.int16)
     pl[:, :64] = coeff.astype(np.uint16).view(np.int16)
     dpl = torch.from_numpy(pl).cuda()
-    seeds = torch.arange(lo, hi, dtype=torch.int64, device="cuda") + 7
+    seeds = torch.from_numpy(np.random.default_rng(7 + rank).integers(0, 2**63, size=(n, 8), dtype=np.int64)).cuda()  # 512 bits per op
     sk = torch.empty((3, N), dtype=torch.int64)
     from fhe_precompiles_b200 import _lib
     pri = open(os.path.join(ROOT, "fhe_precompiles_b200/data/network.pri"), "rb").read()
     assert _lib.lib().fhe_b200_parse_private_key(pri, len(pri), sk.data_ptr()) == 0
     dsk = sk.cuda()
     sync()
-    enc_ms = max_over_ranks(timeit(lambda: fdev.encrypt(pk, dpl, seeds), iters=3, warm=1), dist)
+    enc_ms = max_over_ranks(timeit(lambda: fdev.encrypt(pk, dpl, seeds), iters=iters, warm=1), dist)
     ct = fdev.encrypt(pk, dpl, seeds)
     sync()
-    dec_ms = max_over_ranks(timeit(lambda: fdev.decrypt(ct, dsk), iters=3, warm=1), dist)
-    back = fdev.decrypt(ct, dsk)
-    ok = float(torch.equal(back, dpl))
+    dec_ms = max_over_ranks(timeit(lambda: fdev.decrypt_checked(ct, dsk), iters=iters, warm=1), dist)
+    back, flags = fdev.decrypt_checked(ct, dsk)
+    ok = float(torch.equal(back, dpl) and not bool(flags.any()))
     ok = -max_over_ranks(-ok, dist)  # min over ranks
     res["config5_encrypt_decrypt"] = {"plaintexts": n_total, "encrypt_ms": enc_ms, "encrypt_per_s": n_total / enc_ms * 1e3,
                                       "decrypt_ms": dec_ms, "decrypt_per_s": n_total / dec_ms * 1e3,
                                       "roundtrip_all_equal": bool(ok)}
+    return res
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist  # barrier + max-over-ranks only (gloo): the configs shard with no collective
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    fdev.init(local)
+    res = run_configs(rank, world, dist)
     if rank == 0:
         print(json.dumps(res))
     if dist is not None:

@@ -892,8 +892,9 @@ def test_encrypt_and_reencrypt_bytes_match_oracle(keys, kind, value):
 
 def test_exhausted_noise_budget_is_failed_decryption(dev, keys):
     """sunscreen's Runtime::decrypt refuses a ciphertext whose invariant noise budget is 0 (-> FailedDecryption = 5,
-    fhe.rs:640-643, 692-696).  A product of two products has none left at these parameters; the byte surface still
-    multiplies it happily (as the reference does), but decrypt_* and reencrypt_* must return 5, not a garbage scalar."""
+    fhe.rs:640-643, 692-696).  Three multiplications deep there is none left at these parameters (53 -> 30 -> 7 -> 0 bits);
+    the byte surface still multiplies such operands happily (as the reference does), but decrypt_* and reencrypt_* must return
+    5, not a garbage scalar."""
     import torch
 
     from fhe_precompiles_b200 import FHE, FheError, pack
@@ -901,12 +902,14 @@ def test_exhausted_noise_budget_is_failed_decryption(dev, keys):
     cts = [encrypt_value(keys, "i64", v, 40 + i, network=True) for i, v in enumerate((3, 5, 7, 11))]
     p1 = bfv.mul_relin(cts[0], cts[1], keys.net_rk)
     p2 = bfv.mul_relin(cts[2], cts[3], keys.net_rk)
-    deep = bfv.mul_relin(p1, p2, keys.net_rk)
-    budgets = [bfv.decrypt(c, keys.net_sk)[1] for c in (cts[0], p1, deep)]
-    assert budgets[0] > 40 and budgets[1] > 0 and budgets[2] <= 0, budgets
-    plain, flags = dev.decrypt_checked(to_dev(np.stack([cts[0], p1, deep, p2])), to_dev(keys.net_sk))
+    p12 = bfv.mul_relin(p1, p2, keys.net_rk)   # 1155, 7 bits of budget left
+    deep = bfv.mul_relin(p12, p1, keys.net_rk)  # exhausted
+    budgets = [bfv.decrypt(c, keys.net_sk)[1] for c in (cts[0], p1, p12, deep)]
+    assert budgets[0] > 40 and budgets[1] > 20 and 0 < budgets[2] < 12 and budgets[3] <= 0, budgets
+    plain, flags = dev.decrypt_checked(to_dev(np.stack([cts[0], p1, deep, p12])), to_dev(keys.net_sk))
     assert flags.cpu().tolist() == [0, 0, 1, 0]
     assert bfv.decode("i64", plain[1].cpu().numpy().view(np.uint16).astype(np.uint64)) == 15
+    assert bfv.decode("i64", plain[3].cpu().numpy().view(np.uint16).astype(np.uint64)) == 1155
     ser = lambda c: F.make_ciphertext("i64", c).to_bytes()
     assert pack.deserialize_scalar("i64", FHE.decrypt_i64(ser(p1))) == 15
     with pytest.raises(FheError) as e:
