@@ -442,8 +442,8 @@ int32_t fhe_b200_zstd_inflate(int32_t device, const uint8_t *const *frames, cons
     try {
         device_context(device);
         {
-            const char *v = getenv("FHE_B200_ZSTD_TWO_PHASE");
-            if (v) codec_set_two_phase(*v != '0');
+            const char *v = getenv("FHE_B200_ZSTD_TWO_PHASE");  // 0 one warp per frame, 1 two-phase, 2 batch-oriented (default)
+            codec_set_two_phase(v && *v ? atoi(v) : 2);
         }
         std::vector<CodecJob> jobs(n);
         std::vector<uint8_t> staged(n * kFrameSlotBytes, 0);

@@ -11,6 +11,7 @@
 #include "codec_kernels.h"
 #include "params.h"
 #include "zstd_dec.h"
+#include "zstd_plan2.h"
 
 namespace fheb {
 
@@ -51,12 +52,13 @@ struct JobScratch {            // per job, in the `work` buffer
     uint8_t lits[kCtPayloadBytes + 16];
 };
 
-__global__ void __launch_bounds__(128) k_zstd_plan(const uint8_t *frames, const CodecJob *jobs, JobScratch *scratch, int n) {
+// (every decoder indexes the `work` buffer with the common per-job stride, codec_work_bytes())
+__global__ void __launch_bounds__(128) k_zstd_plan(const uint8_t *frames, const CodecJob *jobs, uint8_t *work, size_t work_stride, int n) {
     const int lane = threadIdx.x & 31;
     const int j = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kPlanLanes + lane;
     if (lane >= kPlanLanes || j >= n) return;
     const CodecJob job = jobs[j];
-    JobScratch *sc = scratch + j;
+    JobScratch *sc = (JobScratch *)(work + (size_t)j * work_stride);
     sc->plan.status = zd::kZdFallback;
     if (job.kind != kJobZstd) return;
     zd::work_bind(&sc->work, nullptr);
@@ -64,17 +66,66 @@ __global__ void __launch_bounds__(128) k_zstd_plan(const uint8_t *frames, const 
 }
 
 __global__ void __launch_bounds__(kInflateWarps * 32) k_zstd_execute(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
-                                                                      int32_t *status, const JobScratch *scratch, int n) {
+                                                                      int32_t *status, const uint8_t *work, size_t work_stride, int n) {
     __shared__ __align__(16) uint8_t rings[kInflateWarps][zd::kRingBytes];
     const int warp = threadIdx.x >> 5;
     const int j = blockIdx.x * kInflateWarps + warp;
     if (j >= n) return;
     const CodecJob job = jobs[j];
     if (job.kind != kJobZstd) return;
-    const JobScratch *sc = scratch + j;
+    const JobScratch *sc = (const JobScratch *)(work + (size_t)j * work_stride);
     size_t dlen = 0;
     const int rc = zd::execute_plan(frames + job.src_off, &sc->plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, &dlen,
                                     rings[warp]);
+    if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
+}
+
+// ---- batch-oriented inflate (zstd_plan2.h, the default): parse (thread per frame) -> decode (a block of five warps per 32
+// frames: warps 0..3 walk Huffman stream 0..3 of their lane's frame, warp 4 its sequence streams -- the five dependent chains of
+// a frame run concurrently and a warp never diverges between the two loop bodies) -> execute (warp per frame, byte copies)
+struct JobScratch2 {
+    zd::Plan2 plan;
+    zd::Work work;  // table-construction scratch of the parse step
+    zd::Tables2 tabs;
+    uint64_t seqs[zd::kP2MaxSeqs];
+    uint8_t lits[(kCtPayloadBytes + 16 + 7) & ~(size_t)7];
+};
+union JobScratchAny {  // one workspace slot per job, whichever decoder runs
+    JobScratch a;
+    JobScratch2 b;
+};
+
+__global__ void __launch_bounds__(32) k_zd2_parse(const uint8_t *frames, const CodecJob *jobs, JobScratchAny *scratch, int n) {
+    const int j = blockIdx.x * 32 + threadIdx.x;
+    if (j >= n) return;
+    const CodecJob job = jobs[j];
+    JobScratch2 *sc = &scratch[j].b;
+    sc->plan.status = zd::kZdFallback;
+    if (job.kind != kJobZstd) return;
+    zd::work_bind(&sc->work, nullptr);
+    zd::plan2_parse(frames + job.src_off, job.src_len, kCtPayloadBytes, &sc->work, &sc->plan, &sc->tabs);
+}
+__global__ void __launch_bounds__(160) k_zd2_decode(const uint8_t *frames, const CodecJob *jobs, JobScratchAny *scratch, int n) {
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), role = threadIdx.x >> 5;
+    if (j >= n) return;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobZstd) return;
+    JobScratch2 *sc = &scratch[j].b;
+    const uint8_t *f = frames + job.src_off;
+    if (role < 4) sc->plan.huf_bad[role] = zd::plan2_huf(f, &sc->plan, &sc->tabs, sc->lits, role) ? 0 : 1;
+    else sc->plan.seq_bad = zd::plan2_seq(f, &sc->plan, &sc->tabs, sc->seqs) ? 0 : 1;
+}
+__global__ void __launch_bounds__(kInflateWarps * 32) k_zd2_exec(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
+                                                                  int32_t *status, const JobScratchAny *scratch, int n) {
+    __shared__ __align__(16) uint8_t rings[kInflateWarps][zd::kRingBytes];
+    const int warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * kInflateWarps + warp;
+    if (j >= n) return;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobZstd) return;
+    const JobScratch2 *sc = &scratch[j].b;
+    size_t dlen = 0;
+    const int rc = zd::plan2_exec(frames + job.src_off, &sc->plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, &dlen, rings[warp]);
     if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
 }
 
@@ -212,10 +263,11 @@ __global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *fr
 }
 }  // namespace
 
-size_t codec_work_bytes() { return sizeof(JobScratch); }
+size_t codec_work_bytes() { return sizeof(JobScratchAny); }
 
-static std::atomic<int> g_two_phase{0};
-void codec_set_two_phase(int on) { g_two_phase.store(on ? 1 : 0); }
+// 0 one warp per frame, 1 two-phase (thread-per-frame plan + warp-per-frame execute), 2 (default) batch-oriented: zstd_plan2.h
+static std::atomic<int> g_inflate_mode{2};
+void codec_set_two_phase(int mode) { g_inflate_mode.store(mode < 0 || mode > 2 ? 2 : mode); }
 
 cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status, void *work,
                                  const uint8_t *prefix, u64 *dst_a, u64 *dst_b, int n_jobs, bool any_zstd, bool any_packed,
@@ -223,18 +275,25 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
     if (n_jobs == 0) return cudaSuccess;
     cudaError_t ce = cudaMemsetAsync(status, 0, (size_t)n_jobs * sizeof(int32_t), s);  // kJobPending
     if (ce != cudaSuccess) return ce;
-    if (any_zstd && g_two_phase.load()) {
+    const int mode = g_inflate_mode.load();
+    if (any_zstd && mode == 2) {
+        k_zd2_parse<<<(n_jobs + 31) / 32, 32, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
+        k_zd2_decode<<<(n_jobs + 31) / 32, 160, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
+        k_zd2_exec<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, 0, s>>>(frames, payloads, jobs, status,
+                                                                                               (const JobScratchAny *)work, n_jobs);
+        g_codec_launches.fetch_add(3, std::memory_order_relaxed);
+    } else if (any_zstd && mode == 1) {
         const int warps_per_block = 4, frames_per_block = warps_per_block * kPlanLanes;
-        k_zstd_plan<<<(n_jobs + frames_per_block - 1) / frames_per_block, warps_per_block * 32, 0, s>>>(frames, jobs, (JobScratch *)work,
-                                                                                                        n_jobs);
+        k_zstd_plan<<<(n_jobs + frames_per_block - 1) / frames_per_block, warps_per_block * 32, 0, s>>>(frames, jobs, (uint8_t *)work,
+                                                                                                        codec_work_bytes(), n_jobs);
         k_zstd_execute<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, 0, s>>>(frames, payloads, jobs, status,
-                                                                                                   (const JobScratch *)work, n_jobs);
+                                                                                                   (const uint8_t *)work, codec_work_bytes(), n_jobs);
         g_codec_launches.fetch_add(2, std::memory_order_relaxed);
     } else if (any_zstd) {
         cudaError_t e = cudaFuncSetAttribute(k_zstd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kInflateSmem);
         if (e != cudaSuccess) return e;
         k_zstd_inflate<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, kInflateSmem, s>>>(
-            frames, payloads, jobs, status, (uint8_t *)work, sizeof(JobScratch), n_jobs);
+            frames, payloads, jobs, status, (uint8_t *)work, codec_work_bytes(), n_jobs);
         g_codec_launches.fetch_add(1, std::memory_order_relaxed);
     }
     if ((any_zstd || any_payload) && dst_a) {  // (the standalone inflate entry point stops at the payloads)

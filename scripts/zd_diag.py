@@ -1,4 +1,4 @@
-"""Device zstd inflate timing: one-warp-per-frame kernel against the two-phase pipeline (FHE_B200_ZSTD_TWO_PHASE=0/1)."""
+"""Device zstd inflate timing: batch-oriented pipeline (FHE_B200_ZSTD_TWO_PHASE=2, default), two-phase (1), one warp per frame (0)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -17,12 +17,12 @@ p = ct()
 cts = [ct() for _ in range(16)]
 frs = [z.compress(c, 3) for c in cts]
 t = bytes(rng.choice(list(b"abcdefgh \n"), size=Z.PAYLOAD).astype(np.uint8))
-for mode in ("1", "0"):
+for mode in (sys.argv[1:] or ("2", "1", "0")):
     os.environ["FHE_B200_ZSTD_TWO_PHASE"] = mode
     print("two_phase =", mode)
     run("warm", [frs[0]], [cts[0]])
     run("ct_l3 x1", [frs[0]], [cts[0]])
     run("text_l3 x1", [z.compress(t, 3)], [t])
     run("structured x1", [F.zstd_structured_frame(cts[0])], [cts[0]])
-    for n in (32, 256, 1024, 4096) if mode == "1" else (32, 1024):
+    for n in (32, 256, 1024, 4096, 8192) if mode != "0" else (32, 1024):
         run(f"ct_l3 x{n}", [frs[i % 16] for i in range(n)], [cts[i % 16] for i in range(n)])

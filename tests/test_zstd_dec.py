@@ -33,10 +33,10 @@ def zd_lib(tmp_path_factory):
 
         return decode
 
-    return {"fused": make(lib.zd_decode), "two_phase": make(lib.zd_decode_two_phase)}
+    return {"fused": make(lib.zd_decode), "two_phase": make(lib.zd_decode_two_phase), "v2": make(lib.zd_decode_v2)}
 
 
-@pytest.fixture(params=["fused", "two_phase"])
+@pytest.fixture(params=["fused", "two_phase", "v2"])
 def zd(request, zd_lib):
     return zd_lib[request.param]
 

@@ -32,3 +32,29 @@ extern "C" int zd_decode_two_phase(const uint8_t *src, size_t slen, uint8_t *dst
     if (fheb::zd::plan_frame(f, slen, cap, w, plan, seqs.data(), lits.data()) != fheb::zd::kZdOk) return 1;
     return fheb::zd::execute_plan(f, plan, seqs.data(), lits.data(), dst, dlen);
 }
+
+// the batch-oriented pipeline (zstd_plan2.h): parse -> four Huffman stream "threads" + the sequence "thread" -> execution
+#include "zstd_plan2.h"
+extern "C" int zd_decode_v2(const uint8_t *src, size_t slen, uint8_t *dst, size_t cap, size_t *dlen) {
+    using namespace fheb::zd;
+    static thread_local Work *w = nullptr;
+    static thread_local Plan2 *plan = nullptr;
+    static thread_local Tables2 *tabs = nullptr;
+    static thread_local std::vector<uint64_t> seqs(kP2MaxSeqs);
+    if (!w) {
+        w = new Work();
+        plan = new Plan2();
+        tabs = new Tables2();
+    }
+    work_bind(w, nullptr);
+    // an odd leading pad so that stream starts land on every alignment
+    static thread_local unsigned shift = 0;
+    shift = (shift + 1) & 7;
+    std::vector<uint8_t> buf(slen + 2 * kPad + 8, 0xAA), lits(cap + 16);
+    uint8_t *f = buf.data() + kPad + shift;
+    memcpy(f, src, slen);
+    if (plan2_parse(f, slen, cap, w, plan, tabs) != kZdOk) return 1;
+    for (int k = 0; k < 4; k++) plan->huf_bad[k] = plan2_huf(f, plan, tabs, lits.data(), k) ? 0 : 1;
+    plan->seq_bad = plan2_seq(f, plan, tabs, seqs.data()) ? 0 : 1;
+    return plan2_exec(f, plan, seqs.data(), lits.data(), dst, dlen);
+}
