@@ -115,18 +115,16 @@ __global__ void __launch_bounds__(160) k_zd2_decode(const uint8_t *frames, const
     if (role < 4) sc->plan.huf_bad[role] = zd::plan2_huf(f, &sc->plan, &sc->tabs, sc->lits, role) ? 0 : 1;
     else sc->plan.seq_bad = zd::plan2_seq(f, &sc->plan, &sc->tabs, sc->seqs) ? 0 : 1;
 }
-__global__ void __launch_bounds__(kInflateWarps * 32) k_zd2_exec(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
-                                                                  int32_t *status, const JobScratchAny *scratch, int n) {
-    __shared__ __align__(16) uint8_t rings[kInflateWarps][zd::kRingBytes];
-    const int warp = threadIdx.x >> 5;
-    const int j = blockIdx.x * kInflateWarps + warp;
+__global__ void __launch_bounds__(32) k_zd2_exec(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status,
+                                                 const JobScratchAny *scratch, int n) {
+    const int j = blockIdx.x * 32 + threadIdx.x;
     if (j >= n) return;
     const CodecJob job = jobs[j];
     if (job.kind != kJobZstd) return;
     const JobScratch2 *sc = &scratch[j].b;
     size_t dlen = 0;
-    const int rc = zd::plan2_exec(frames + job.src_off, &sc->plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, &dlen, rings[warp]);
-    if ((threadIdx.x & 31) == 0) status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
+    const int rc = zd::plan2_exec(frames + job.src_off, &sc->plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, &dlen);
+    status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
 }
 
 constexpr int kSplit = 8;  // blocks per ciphertext in the parallel kernels (latency of a single call)
@@ -279,8 +277,7 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
     if (any_zstd && mode == 2) {
         k_zd2_parse<<<(n_jobs + 31) / 32, 32, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
         k_zd2_decode<<<(n_jobs + 31) / 32, 160, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
-        k_zd2_exec<<<(n_jobs + kInflateWarps - 1) / kInflateWarps, kInflateWarps * 32, 0, s>>>(frames, payloads, jobs, status,
-                                                                                               (const JobScratchAny *)work, n_jobs);
+        k_zd2_exec<<<(n_jobs + 31) / 32, 32, 0, s>>>(frames, payloads, jobs, status, (const JobScratchAny *)work, n_jobs);
         g_codec_launches.fetch_add(3, std::memory_order_relaxed);
     } else if (any_zstd && mode == 1) {
         const int warps_per_block = 4, frames_per_block = warps_per_block * kPlanLanes;

@@ -8,7 +8,7 @@
 //                                  scratch), descriptors of every bitstream                                (plan2_parse)
 //   huf     one thread per (frame, Huffman stream): the four literal streams of a block decode concurrently  (plan2_huf)
 //   seq     one thread per frame   FSE sequence streams -> (literal length, match length, resolved offset)   (plan2_seq)
-//   exec    one warp per frame     byte copies through a shared-memory ring (zstd_dec.h execute machinery)   (plan2_exec)
+//   exec    one thread per frame   sequence execution on registers: 64-bit appends, aligned word stores        (plan2_exec)
 // huf and seq are independent of each other and run on two streams.  The bit readers use one aligned 32-bit load per 32 bits
 // consumed and keep the unread bits left-aligned in a 64-bit register; tables are read through the read-only path.
 //
@@ -413,39 +413,119 @@ ZD_FN bool plan2_seq(const uint8_t *src, const Plan2 *plan, const Tables2 *tabs,
     return true;
 }
 
-// ---------------------------------------------------------------- execution (warp-cooperative on the device)
-ZD_FN int plan2_exec(const uint8_t *src, const Plan2 *plan, const uint64_t *seqs, const uint8_t *lits, uint8_t *dst, size_t *dlen,
-                     uint8_t *ring = nullptr) {
+// ---------------------------------------------------------------- execution, one THREAD per frame
+// A warp-per-frame executor spends ~1,300 cycles per sequence on a chain of dependent loads, shared-memory round trips and warp
+// barriers (11 ms per ciphertext frame, measured) while 31 of its lanes have next to nothing to copy: a ciphertext's typical
+// sequence is five literal bytes and a three-byte match.  Here one thread keeps the output position, the word being assembled
+// and the previous word in REGISTERS, appends up to eight bytes per step with shifts, and stores aligned 64-bit words; a match
+// whose source lies in the last 8..15 bytes (offset 8: the zero bytes of the previous residue) never touches memory.  Thirty-two
+// frames share a warp, so the batch's frames all run at once.
+struct Sink64 {
+    uint64_t *dst;  // 8-byte aligned; the caller leaves room up to the next multiple of 8 after the content
+    uint64_t acc;   // bytes [pos & ~7, pos) of the word being assembled, low byte first, upper bytes zero
+    uint64_t prev;  // the word before it
+    size_t pos;
+    ZD_HD void put(uint64_t v, int k) {  // appends the k (1..8) low bytes of v; the other bytes of v are zero
+        const int a = (int)(pos & 7);
+        acc |= v << (8 * a);
+        if (a + k >= 8) {
+            dst[pos >> 3] = acc;
+            prev = acc;
+            acc = a ? v >> (8 * (8 - a)) : 0;
+        }
+        pos += (size_t)k;
+    }
+    // k (1..8) bytes that are already part of the output, starting at absolute position p (p + k <= pos), upper bytes garbage.
+    // *k is reduced when the range would straddle the flushed / register boundary.
+    ZD_HD uint64_t get(size_t p, int *k) const {
+        const size_t wordpos = pos & ~(size_t)7;
+        if (p + 8 >= wordpos) {  // inside (prev, acc)
+            const unsigned sh = (unsigned)(p + 8 - wordpos) * 8;  // 0..127
+            if (sh == 0) return prev;
+            if (sh < 64) return (prev >> sh) | (acc << (64 - sh));
+            return acc >> (sh - 64);
+        }
+        const size_t room = wordpos - p;  // bytes of the range that are in memory for sure
+        if ((size_t)*k > room) *k = (int)room;
+        const uint64_t *w = dst + (p >> 3);
+        const unsigned sh = (unsigned)(p & 7) * 8;
+        const uint64_t lo = w[0];
+        if (sh == 0) return lo;
+        return (lo >> sh) | (w[1] << (64 - sh));
+    }
+    ZD_HD void finish() {
+        if (pos & 7) dst[pos >> 3] = acc;
+    }
+};
+ZD_HD uint64_t low_bytes(uint64_t v, int k) { return k >= 8 ? v : v & ((1ull << (8 * k)) - 1); }
+// n bytes of read-only input at src (any alignment, readable kPad bytes around) appended to the sink
+ZD_HD void sink_copy(Sink64 &o, const uint8_t *src, size_t n) {
+    size_t done = 0;
+    while (done < n) {
+        const int k = n - done < 8 ? (int)(n - done) : 8;
+        o.put(low_bytes(window_at(src + done, 0), k), k);
+        done += (size_t)k;
+    }
+}
+ZD_HD void sink_fill(Sink64 &o, uint8_t v, size_t n) {
+    const uint64_t rep = 0x0101010101010101ull * v;
+    size_t done = 0;
+    while (done < n) {
+        const int k = n - done < 8 ? (int)(n - done) : 8;
+        o.put(low_bytes(rep, k), k);
+        done += (size_t)k;
+    }
+}
+
+ZD_FN int plan2_exec(const uint8_t *src, const Plan2 *plan, const uint64_t *seqs, const uint8_t *lits, uint8_t *dst, size_t *dlen) {
     if (plan->status != kZdOk || plan->seq_bad || plan->huf_bad[0] || plan->huf_bad[1] || plan->huf_bad[2] || plan->huf_bad[3])
         return kZdFallback;
-    const size_t window = plan->window;
+    const size_t window = plan->window, cap = plan->content;
     const size_t block_max = window < kBlockMax ? window : kBlockMax;
-    Frame f{dst, (size_t)plan->content, 0, window, {1, 4, 8}, ring, 0};
+    Sink64 o{(uint64_t *)dst, 0, 0, 0};
     for (uint32_t bi = 0; bi < plan->nblocks; bi++) {
         const Block2 &bp = plan->blocks[bi];
         if (bp.type != 2) {
-            if (bp.size > f.cap - f.pos) return kZdFallback;
-            out_run(&f, bp.type == 0 ? src + bp.src_off : nullptr, bp.type == 0 ? -1 : (int)byte_at(src, bp.src_off), bp.size);
+            if (bp.size > cap - o.pos) return kZdFallback;
+            if (bp.type == 0) sink_copy(o, src + bp.src_off, bp.size);
+            else sink_fill(o, byte_at(src, bp.src_off), bp.size);
             continue;
         }
         const uint8_t *lit = bp.lit_mode == 0 ? src + bp.lit_off : lits + bp.lit_off;
         const int lit_rle = bp.lit_mode == 1 ? bp.lit_rle : -1;
-        size_t lpos = 0, opos = f.pos;
-        const size_t block_start = opos;
+        size_t lpos = 0;
+        const size_t block_start = o.pos, regen = bp.regen;
         const uint64_t *so = seqs + bp.seq_off;
         for (uint32_t i = 0; i < bp.nseq; i++) {
+#if defined(__CUDA_ARCH__)
+            const uint64_t e = __ldg((const unsigned long long *)(so + i));
+#else
             const uint64_t e = so[i];
-            if (!exec_sequence(&f, lit, lit_rle, bp.regen, block_start, block_max, (uint32_t)(e & 0x3FFFF), (uint32_t)((e >> 18) & 0x3FFFF),
-                               (uint32_t)(e >> 36), &lpos, &opos))
-                return kZdFallback;
+#endif
+            const uint32_t ll = (uint32_t)(e & 0x3FFFF), ml = (uint32_t)((e >> 18) & 0x3FFFF), offset = (uint32_t)(e >> 36);
+            if (ll > regen - lpos) return kZdFallback;
+            if ((size_t)ll + ml > cap - o.pos || o.pos + ll + ml - block_start > block_max) return kZdFallback;
+            if (offset > o.pos + ll || offset > window || offset == 0) return kZdFallback;
+            if (lit_rle >= 0) sink_fill(o, (uint8_t)lit_rle, ll);
+            else sink_copy(o, lit + lpos, ll);
+            lpos += ll;
+            uint32_t rest = ml;
+            while (rest) {
+                int k = rest < 8 ? (int)rest : 8;
+                if ((uint32_t)k > offset) k = (int)offset;  // an overlapping match repeats its own output: at most one period per step
+                const uint64_t v = o.get(o.pos - offset, &k);
+                o.put(low_bytes(v, k), k);
+                rest -= (uint32_t)k;
+            }
         }
-        const size_t rest = bp.regen - lpos;
-        if (rest > f.cap - opos || opos + rest - block_start > block_max) return kZdFallback;
-        f.pos = opos;
-        out_run(&f, lit_rle >= 0 ? nullptr : lit + lpos, lit_rle, rest);
+        const size_t tail = regen - lpos;
+        if (tail > cap - o.pos || o.pos + tail - block_start > block_max) return kZdFallback;
+        if (lit_rle >= 0) sink_fill(o, (uint8_t)lit_rle, tail);
+        else sink_copy(o, lit + lpos, tail);
     }
-    if (f.pos != (size_t)plan->content) return kZdFallback;
-    *dlen = f.pos;
+    if (o.pos != cap) return kZdFallback;
+    o.finish();
+    *dlen = o.pos;
     return kZdOk;
 }
 

@@ -56,5 +56,9 @@ extern "C" int zd_decode_v2(const uint8_t *src, size_t slen, uint8_t *dst, size_
     if (plan2_parse(f, slen, cap, w, plan, tabs) != kZdOk) return 1;
     for (int k = 0; k < 4; k++) plan->huf_bad[k] = plan2_huf(f, plan, tabs, lits.data(), k) ? 0 : 1;
     plan->seq_bad = plan2_seq(f, plan, tabs, seqs.data()) ? 0 : 1;
-    return plan2_exec(f, plan, seqs.data(), lits.data(), dst, dlen);
+    // the executor stores aligned 64-bit words: an aligned bounce buffer with room up to the next multiple of 8
+    std::vector<uint64_t> out((cap + 15) / 8);
+    const int rc = plan2_exec(f, plan, seqs.data(), lits.data(), (uint8_t *)out.data(), dlen);
+    if (rc == 0) memcpy(dst, out.data(), *dlen);
+    return rc;
 }
