@@ -200,7 +200,15 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     size_t nt = host_threads > 0 ? (size_t)host_threads : 2 * (size_t)std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
     size_t tile = Engine::get().tile_ops();
-    while (tile > 1 && (n + tile - 1) / tile < nt) tile /= 2;  // keep every worker busy on small batches
+    const size_t big = Engine::get().big_tile_ops();
+    if (Engine::get().device_codec() && big > tile && n >= 2 * big) {
+        // a large batch: few big tiles (each stages its calls on the whole host pool and launches thousands of operand frames
+        // at once), a handful of them in flight so that one tile's host phases overlap another's device phases
+        tile = big;
+        nt = std::min<size_t>(nt, 6);
+    } else {
+        while (tile > 1 && (n + tile - 1) / tile < nt) tile /= 2;  // keep every worker busy on small batches
+    }
     const size_t tiles = (n + tile - 1) / tile;
     if (nt > tiles) nt = tiles;
     std::atomic<size_t> next{0};

@@ -13,6 +13,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 #include "kernels.h"
 
@@ -41,6 +42,25 @@ uint64_t cheap_tag(Span s) {
     }
     return h;
 }
+// fn(i) for i in [0, count): on the caller alone for short loops, otherwise shared with pool threads in chunks of `grain`
+template <class F>
+void parallel_for(size_t count, size_t grain, F &&fn) {
+    const size_t hw = std::max(1u, std::thread::hardware_concurrency());
+    if (count < 2 * grain || hw < 2) {
+        for (size_t i = 0; i < count; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    const std::function<void()> body = [&] {
+        for (;;) {
+            const size_t lo = next.fetch_add(grain);
+            if (lo >= count) break;
+            const size_t hi = std::min(count, lo + grain);
+            for (size_t i = lo; i < hi; i++) fn(i);
+        }
+    };
+    HostPool::get().run(std::min(hw - 1, (count + grain - 1) / grain - 1), body);
+}
 }  // namespace
 
 Engine &Engine::get() {
@@ -60,11 +80,17 @@ Engine::Engine() {
         helper_decode_ = !(v && *v == '0');
         v = getenv("FHE_B200_DEVICE_CODEC");
         device_codec_ = !(v && *v == '0');
-        v = getenv("FHE_B200_DEVICE_ZSTD");
-        device_zstd_ = v && *v == '1';
+        v = getenv("FHE_B200_DEVICE_ZSTD");  // 0 never, 1 always, default: when a tile brings enough libzstd frames
+        device_zstd_ = (v && *v == '1') ? 1 : (v && *v == '0') ? 0 : 2;
         v = getenv("FHE_B200_CALL_GRAPHS");
         call_graphs_ = !(v && *v == '0');
     }
+    device_zstd_min_frames_ = env_size("FHE_B200_DEVICE_ZSTD_MIN_FRAMES", 256);
+    {
+        const char *v = getenv("FHE_B200_HOST_INFLATE_PCT");  // share of a tile's libzstd frames the host cores inflate meanwhile
+        host_inflate_pct_ = (v && *v) ? (size_t)std::min(100, std::max(0, atoi(v))) : 35;
+    }
+    big_tile_ops_ = env_size("FHE_B200_BIG_TILE_OPS", 512);
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 4096);
@@ -914,19 +940,20 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
     std::vector<size_t> order;
     order.reserve(cnt);
 
-    // pass 1, reference order (pack.rs:261-263): framing, then the public key
-    for (size_t i = 0; i < cnt; i++) {
+    // pass 1, reference order (pack.rs:261-263): framing, then the public key (a ~400 KB comparison with the cached key per call:
+    // shared with pool threads when the tile is large)
+    parallel_for(cnt, 4, [&](size_t i) {
         TileItem &it = items[i];
         Prep &p = prep[i];
         Span pk;
-        if ((it.rc = unpack_binary_operation(it.in, &pk, &p.sa, &p.sb))) continue;
+        if ((it.rc = unpack_binary_operation(it.in, &pk, &p.sa, &p.sb))) return;
         const bool need_relin = (it.op == Op::Mul && it.shape == Shape::CtCt);
         int32_t rc = relin_key(pk, lane->device, &p.d_rk, need_relin, &p.pin);
         if (rc == kErrSunscreen && need_relin) {
             // missing relin keys is a runtime (not a decoding) error: operands are still decoded first
         } else if (rc) {
             it.rc = rc;
-            continue;
+            return;
         }
         p.key_rc = rc;
         if (it.shape == Shape::CtCt) p.cls = it.op == Op::Mul ? kMulCt : (it.op == Op::Add ? kAddCt : kSubCt);
@@ -934,8 +961,9 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         else if (it.op == Op::Add) p.cls = kAddPt;
         else p.cls = it.shape == Shape::CtPt ? kSubCtPt : kSubPtCt;
         p.live = true;
-        order.push_back(i);
-    }
+    });
+    for (size_t i = 0; i < cnt; i++)
+        if (prep[i].live) order.push_back(i);
     const double t_unpack = us_since(t_start);
     struct Run {
         int cls;
@@ -980,80 +1008,120 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         ensure_codec(lane);
         std::vector<Run> runs;
         std::vector<size_t> slot_item, rest;
-        std::vector<int> slot_job0;
-        std::vector<size_t> staged_copies;  // job indices (= payload slots) of operands inflated on the host, ascending
-        size_t slots = 0, ctct_slots = 0, fcur = 0;
-        int njobs = 0;
-        bool any_zstd = false, any_packed = false, any_payload = false;
         const bool pack_on_device = zstd_writer() == 1;
-        for (size_t i : order) {
+        // (A) per call, in parallel: bincode framing, type check, classification of the SEAL blobs
+        struct Stg {
+            bool clean = false;
+            int nct = 0, kinds[2] = {0, 0};
+            Span frames[2];
+            CipherView views[2];
+            bool on_host[2] = {false, false};  // libzstd-written frame inflated on the host (else staged for the device decoder)
+            int job0 = 0;
+            size_t slot = 0, off[2] = {0, 0};
+            std::atomic<bool> bad{false};      // staging failed: the host pass redoes the call
+        };
+        std::vector<Stg> stg(order.size());
+        parallel_for(order.size(), 8, [&](size_t oi) {
+            const size_t i = order[oi];
             TileItem &it = items[i];
             Prep &p = prep[i];
+            Stg &g = stg[oi];
             bool clean = p.key_rc == 0;
-            Span frames[2];
-            int kinds[2] = {0, 0}, nct = 0;
             const Span cts[2] = {it.shape == Shape::PtCt ? p.sb : p.sa, p.sb};
             const int want_ct = it.shape == Shape::CtCt ? 2 : 1;
-            CipherView views[2];
-            bool host_staged[2] = {false, false};
             for (int k = 0; clean && k < want_ct; k++) {
                 Span blob;
                 uint8_t compr = 0;
-                clean = parse_ciphertext_framing(cts[k], &views[k], &blob) == kOk && data_type_matches(views[k].data_type, it.kind);
+                clean = parse_ciphertext_framing(cts[k], &g.views[k], &blob) == kOk && data_type_matches(g.views[k].data_type, it.kind);
                 if (!clean) break;
-                kinds[k] = classify_ciphertext_blob(blob, &frames[k], &compr);
-                clean = kinds[k] >= 1 && frames[k].n + 2 * kFramePad <= kFrameSlotBytes;
-                views[k].compr_mode = compr;
-                if (clean && kinds[k] == 1 && !device_zstd_) {
-                    // libzstd-written frame: inflated here (the device decoder is opt-in) straight into the pinned payload slot
-                    // of its job; prefix and residues are validated by k_ct_unpack
-                    clean = inflate_ct_payload(frames[k], lane->h_payloads + (size_t)(njobs + k) * kPayloadStride);
-                    host_staged[k] = true;
-                }
-                nct++;
+                g.kinds[k] = classify_ciphertext_blob(blob, &g.frames[k], &compr);
+                clean = g.kinds[k] >= 1 && g.frames[k].n + 2 * kFramePad <= kFrameSlotBytes;
+                g.views[k].compr_mode = compr;
+                g.nct++;
             }
-            if (clean && it.shape != Shape::CtCt)
-                clean = encode_scalar(it.kind, it.shape == Shape::CtPt ? p.sb : p.sa, lane->h_plain + slots * kN) == kOk;
-            if (!clean) {
+            g.clean = clean;
+        });
+        // (B) serial: slots, jobs and staging offsets.  libzstd-written frames go to the device decoder when it is on -- always
+        // (FHE_B200_DEVICE_ZSTD=1) or, by default, when the tile brings enough frames to fill the GPU -- except for the share
+        // the host cores inflate meanwhile (FHE_B200_HOST_INFLATE_PCT): both decoders work on the same tile at once.
+        size_t lib_frames = 0;
+        for (const Stg &g : stg)
+            if (g.clean)
+                for (int k = 0; k < g.nct; k++) lib_frames += g.kinds[k] == 1;
+        const bool dev_zstd = device_zstd_ == 1 || (device_zstd_ == 2 && lib_frames >= device_zstd_min_frames_);
+        size_t slots = 0, ctct_slots = 0, fcur = 0, seen_lib = 0;
+        int njobs = 0;
+        bool any_zstd = false, any_packed = false, any_payload = false;
+        std::vector<size_t> slot_stg;
+        for (size_t oi = 0; oi < order.size(); oi++) {
+            const size_t i = order[oi];
+            Stg &g = stg[oi];
+            Prep &p = prep[i];
+            if (!g.clean) {
                 rest.push_back(i);
                 continue;
             }
-            p.va = views[0];
-            slot_job0.push_back(njobs);
-            for (int k = 0; k < nct; k++) {
-                if (host_staged[k]) {
-                    staged_copies.push_back((size_t)njobs);  // payload slot = job index
-                    lane->h_jobs[njobs++] = CodecJob{0, 0, kJobPayload, (int32_t)slots, k};
+            p.va = g.views[0];
+            g.slot = slots;
+            g.job0 = njobs;
+            for (int k = 0; k < g.nct; k++) {
+                bool host = g.kinds[k] == 1 && !dev_zstd;
+                if (g.kinds[k] == 1 && dev_zstd) {  // Bresenham split of the libzstd frames between host and device
+                    host = (seen_lib + 1) * host_inflate_pct_ / 100 != seen_lib * host_inflate_pct_ / 100;
+                    seen_lib++;
+                }
+                g.on_host[k] = host;
+                if (host) {
+                    lane->h_jobs[njobs++] = CodecJob{0, 0, kJobPayload, (int32_t)slots, k};  // payload slot = job index
                     any_payload = true;
                     continue;
                 }
-                const size_t off = fcur + kFramePad;
-                memcpy(lane->h_frames + off, frames[k].p, frames[k].n);
-                lane->h_jobs[njobs++] = CodecJob{off, (uint32_t)frames[k].n, kinds[k] == 2 ? kJobPacked : kJobZstd, (int32_t)slots, k};
-                (kinds[k] == 2 ? any_packed : any_zstd) = true;
-                fcur += (frames[k].n + 2 * kFramePad + 15) & ~(size_t)15;
+                g.off[k] = fcur + kFramePad;
+                lane->h_jobs[njobs++] = CodecJob{g.off[k], (uint32_t)g.frames[k].n, g.kinds[k] == 2 ? kJobPacked : kJobZstd, (int32_t)slots, k};
+                (g.kinds[k] == 2 ? any_packed : any_zstd) = true;
+                fcur += (g.frames[k].n + 2 * kFramePad + 15) & ~(size_t)15;
             }
             const uint64_t *rk = p.cls == kMulCt ? p.d_rk : nullptr;
             if (runs.empty() || runs.back().cls != p.cls || runs.back().d_rk != rk) runs.push_back(Run{p.cls, rk, slots, slots});
             runs.back().end = ++slots;
             if (p.cls <= kSubCt) ctct_slots = slots;
             slot_item.push_back(i);
+            slot_stg.push_back(oi);
         }
         if (slots) {
-            slot_job0.push_back(njobs);
+            // (C) in parallel: bytes into the pinned staging -- frames as they are, host-inflated payloads, encoded scalars
+            parallel_for(slots, 2, [&](size_t k) {
+                Stg &g = stg[slot_stg[k]];
+                TileItem &it = items[slot_item[k]];
+                Prep &p = prep[slot_item[k]];
+                bool ok = true;
+                for (int c = 0; ok && c < g.nct; c++) {
+                    if (g.on_host[c]) ok = inflate_ct_payload(g.frames[c], lane->h_payloads + (size_t)(g.job0 + c) * kPayloadStride);
+                    else memcpy(lane->h_frames + g.off[c], g.frames[c].p, g.frames[c].n);
+                }
+                if (ok && it.shape != Shape::CtCt)
+                    ok = encode_scalar(it.kind, it.shape == Shape::CtPt ? p.sb : p.sa, lane->h_plain + k * kN) == kOk;
+                if (!ok) {
+                    g.bad = true;
+                    for (int c = 0; c < g.nct; c++) lane->h_jobs[g.job0 + c].kind = kJobNone;  // the kernels skip it; its slot computes on stale data
+                }
+            });
             if (njobs) {
                 if (fcur) cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, fcur, cudaMemcpyHostToDevice, s), "H2D frames");
                 cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)njobs * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
             }
             // payloads inflated on the host: one copy per run of adjacent payload slots
-            for (size_t i0 = 0; i0 < staged_copies.size();) {
-                size_t i1 = i0 + 1;
-                while (i1 < staged_copies.size() && staged_copies[i1] == staged_copies[i1 - 1] + 1) i1++;
-                const size_t j0 = staged_copies[i0];
-                cuda_throw(cudaMemcpyAsync(lane->d_payloads + j0 * kPayloadStride, lane->h_payloads + j0 * kPayloadStride,
-                                           (i1 - i0) * kPayloadStride, cudaMemcpyHostToDevice, s),
+            for (int j0 = 0; j0 < njobs;) {
+                if (lane->h_jobs[j0].kind != kJobPayload) {
+                    j0++;
+                    continue;
+                }
+                int j1 = j0 + 1;
+                while (j1 < njobs && lane->h_jobs[j1].kind == kJobPayload) j1++;
+                cuda_throw(cudaMemcpyAsync(lane->d_payloads + (size_t)j0 * kPayloadStride, lane->h_payloads + (size_t)j0 * kPayloadStride,
+                                           (size_t)(j1 - j0) * kPayloadStride, cudaMemcpyHostToDevice, s),
                            "H2D payloads");
-                i0 = i1;
+                j0 = j1;
             }
             if (slots > ctct_slots)
                 cuda_throw(cudaMemcpyAsync(lane->d_plain + ctct_slots * kN, lane->h_plain + ctct_slots * kN,
@@ -1076,28 +1144,39 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                 cuda_throw(cudaMemcpyAsync(lane->h_status, lane->d_status, (size_t)njobs * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
                            "D2H status");
             cuda_throw(cudaStreamSynchronize(s), "stream sync");
-            for (size_t k = 0; k < slots; k++) {
+            // (D) in parallel: results into their own buffers; calls the device handed back are collected for the host pass
+            std::vector<uint8_t> redo(slots, 0);
+            parallel_for(slots, 4, [&](size_t k) {
                 const size_t i = slot_item[k];
-                bool ok = true;
-                for (int j = slot_job0[k]; j < slot_job0[k + 1]; j++) ok = ok && lane->h_status[j] != kJobFallback;
+                Stg &g = stg[slot_stg[k]];
+                bool ok = !g.bad;
+                for (int j = g.job0; ok && j < g.job0 + g.nct; j++) ok = lane->h_status[j] != kJobFallback;
                 if (!ok) {
-                    rest.push_back(i);
-                    continue;
+                    redo[k] = 1;
+                    return;
                 }
                 TileItem &it = items[i];
                 if (pack_on_device && !h_cflag[k]) {
                     wrap_ciphertext_blob(prep[i].va, lane->h_outframes + k * kPackedFrameStride, kPackedFrameBytes, &it.out);
                     it.rc = kOk;
-                } else {
-                    if (pack_on_device) {  // constant result (a transparent ciphertext): the host writer's libzstd path
-                        cuda_throw(cudaMemcpyAsync(lane->h_out + k * kCtWords, lane->d_out + k * kCtWords, kCtWords * 8,
-                                                   cudaMemcpyDeviceToHost, s),
-                                   "D2H");
-                        cuda_throw(cudaStreamSynchronize(s), "stream sync");
-                    }
+                } else if (!pack_on_device) {
                     it.rc = encode_ciphertext(prep[i].va, lane->h_out + k * kCtWords, &it.out);
+                } else {
+                    redo[k] = 2;  // constant result (a transparent ciphertext): the host writer's libzstd path, below
                 }
-                prep[i].live = false;
+                if (redo[k] == 0) prep[i].live = false;
+            });
+            for (size_t k = 0; k < slots; k++) {
+                const size_t i = slot_item[k];
+                if (redo[k] == 1) {
+                    rest.push_back(i);
+                } else if (redo[k] == 2) {
+                    cuda_throw(cudaMemcpyAsync(lane->h_out + k * kCtWords, lane->d_out + k * kCtWords, kCtWords * 8, cudaMemcpyDeviceToHost, s),
+                               "D2H");
+                    cuda_throw(cudaStreamSynchronize(s), "stream sync");
+                    items[i].rc = encode_ciphertext(prep[i].va, lane->h_out + k * kCtWords, &items[i].out);
+                    prep[i].live = false;
+                }
             }
         }
         std::stable_sort(rest.begin(), rest.end(), by_class);

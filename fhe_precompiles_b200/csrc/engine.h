@@ -114,6 +114,10 @@ class Engine {
     // Per-call results and error codes are exactly those of binary_op (which is a tile of one).
     void binary_tile(TileItem *items, size_t cnt);
     size_t tile_ops() const { return tile_ops_; }
+    // tile size of a large batch: big tiles put thousands of operand frames in flight per launch (the device zstd decoder's
+    // throughput comes from frames in flight) and their staging loops are shared with the host pool
+    size_t big_tile_ops() const { return big_tile_ops_; }
+    bool device_codec() const { return device_codec_; }
     // per-call phase timing of binary_tile (host clock around the codec phases, CUDA events around the copies and the
     // kernels on the lane's stream); off by default
     void set_call_timing(bool on) { call_timing_ = on; }
@@ -192,8 +196,11 @@ class Engine {
     bool device_codec_ = true;  // FHE_B200_DEVICE_CODEC=0: tiles decode and encode everything on the host
     bool call_graphs_ = true;   // FHE_B200_CALL_GRAPHS=0: the single-call fast path launches its kernels one by one
     void drop_graphs(Lane *lane);
-    bool device_zstd_ = false;  // FHE_B200_DEVICE_ZSTD=1: libzstd-written operand frames are inflated on the GPU too (k_zstd_inflate)
-    size_t tile_ops_ = 16;
+    // libzstd-written operand frames inflated on the GPU (zstd_plan2.h): 0 never, 1 always, 2 (default) when a tile brings at
+    // least device_zstd_min_frames_ of them; host_inflate_pct_ % of those frames are inflated by the host cores meanwhile
+    int device_zstd_ = 2;
+    size_t device_zstd_min_frames_ = 256, host_inflate_pct_ = 35;
+    size_t tile_ops_ = 16, big_tile_ops_ = 512;
     bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
     std::atomic<bool> call_timing_{false};
     std::vector<int> lane_devices_;
