@@ -80,8 +80,11 @@ Engine::Engine() {
         helper_decode_ = !(v && *v == '0');
         v = getenv("FHE_B200_DEVICE_CODEC");
         device_codec_ = !(v && *v == '0');
-        v = getenv("FHE_B200_DEVICE_ZSTD");  // 0 never, 1 always, default: when a tile brings enough libzstd frames
-        device_zstd_ = (v && *v == '1') ? 1 : (v && *v == '0') ? 0 : 2;
+        // 0 (default) never, 1 always, 2 when a tile brings at least FHE_B200_DEVICE_ZSTD_MIN_FRAMES libzstd frames.  Opt-in: measured on
+        // B200 (profiles/r2_codec.md) the device decoder sustains 190 k frames/s with 8,192 frames in flight against 145 k frames/s
+        // for libzstd on 16 host cores, but a frame is a chain of ~16 k dependent steps (11 ms on one GPU thread), so a tile
+        // waits tens of ms for its frames and the byte surface as a whole gets slower, not faster.
+        device_zstd_ = (v && *v == '1') ? 1 : (v && *v == '2') ? 2 : 0;
         v = getenv("FHE_B200_CALL_GRAPHS");
         call_graphs_ = !(v && *v == '0');
     }
@@ -90,7 +93,7 @@ Engine::Engine() {
         const char *v = getenv("FHE_B200_HOST_INFLATE_PCT");  // share of a tile's libzstd frames the host cores inflate meanwhile
         host_inflate_pct_ = (v && *v) ? (size_t)std::min(100, std::max(0, atoi(v))) : 35;
     }
-    big_tile_ops_ = env_size("FHE_B200_BIG_TILE_OPS", 512);
+    big_tile_ops_ = env_size("FHE_B200_BIG_TILE_OPS", 0);  // opt-in: large batches run in tiles of this many calls (see c_api.cpp)
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 4096);

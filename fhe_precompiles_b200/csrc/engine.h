@@ -196,11 +196,11 @@ class Engine {
     bool device_codec_ = true;  // FHE_B200_DEVICE_CODEC=0: tiles decode and encode everything on the host
     bool call_graphs_ = true;   // FHE_B200_CALL_GRAPHS=0: the single-call fast path launches its kernels one by one
     void drop_graphs(Lane *lane);
-    // libzstd-written operand frames inflated on the GPU (zstd_plan2.h): 0 never, 1 always, 2 (default) when a tile brings at
+    // libzstd-written operand frames inflated on the GPU (zstd_plan2.h): 0 (default) never, 1 always, 2 when a tile brings at
     // least device_zstd_min_frames_ of them; host_inflate_pct_ % of those frames are inflated by the host cores meanwhile
-    int device_zstd_ = 2;
+    int device_zstd_ = 0;
     size_t device_zstd_min_frames_ = 256, host_inflate_pct_ = 35;
-    size_t tile_ops_ = 16, big_tile_ops_ = 512;
+    size_t tile_ops_ = 16, big_tile_ops_ = 0;
     bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
     std::atomic<bool> call_timing_{false};
     std::vector<int> lane_devices_;

@@ -64,15 +64,12 @@ def main() -> None:
         child(int(sys.argv[2]))
         return
     sweeps = [
-        (4096, {"FHE_B200_DEVICE_ZSTD": "0", "FHE_B200_BIG_TILE_OPS": "16"}),   # round-1 behaviour: 16-call tiles, host inflate
-        (4096, {"FHE_B200_DEVICE_ZSTD": "0"}),                                   # big tiles, host inflate only
-        (4096, {"FHE_B200_HOST_INFLATE_PCT": "0"}),                              # device inflate only
-        (4096, {}),                                                              # default: hybrid
-        (4096, {"FHE_B200_HOST_INFLATE_PCT": "50"}),
-        (4096, {"FHE_B200_BIG_TILE_OPS": "1024"}),
-        (4096, {"FHE_B200_BIG_TILE_OPS": "256"}),
-        (8192, {}),
-        (8192, {"FHE_B200_BIG_TILE_OPS": "1024", "FHE_B200_HOST_INFLATE_PCT": "25"}),
+        (4096, {}),                                                                       # default: 16-call tiles, host inflate
+        (4096, {"FHE_B200_BIG_TILE_OPS": "512"}),                                          # big tiles, host inflate only
+        (4096, {"FHE_B200_BIG_TILE_OPS": "512", "FHE_B200_DEVICE_ZSTD": "2", "FHE_B200_HOST_INFLATE_PCT": "0"}),   # device inflate only
+        (4096, {"FHE_B200_BIG_TILE_OPS": "512", "FHE_B200_DEVICE_ZSTD": "2"}),             # hybrid, 35 % on the host
+        (4096, {"FHE_B200_BIG_TILE_OPS": "1024", "FHE_B200_DEVICE_ZSTD": "2", "FHE_B200_HOST_INFLATE_PCT": "50"}),
+        (8192, {"FHE_B200_BIG_TILE_OPS": "1024", "FHE_B200_DEVICE_ZSTD": "2", "FHE_B200_HOST_INFLATE_PCT": "25"}),
     ]
     for n, env in sweeps:
         e = dict(os.environ)
