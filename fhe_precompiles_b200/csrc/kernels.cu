@@ -36,34 +36,35 @@ cudaError_t upload_constants(const DevConsts &c, const DevTables &t, const DevTw
 // =====================================================================================
 // K1/K2: batched limb NTT (config 2 microbenchmark; also used by the parity tests)
 // =====================================================================================
-template <int MI, bool INV>
+template <int MI, bool INV, bool SHFL>
 __device__ __forceinline__ void ntt_limb_body(u64 *limb, u64 *smem, int t) {
     using M = Mod<MI>;
     u64 v[1][8];
     if (!INV) {
         load_natural(limb, v[0], t);
-        ntt_forward<M, 1, true, false>(v, smem, kt.twf[MI], t);
+        ntt_forward<M, 1, true, false, SHFL>(v, smem, kt.twf[MI], t);
         store_chunk8(limb, v[0], t);
     } else {
         load_chunk8(limb, v[0], t);
-        ntt_inverse<M, 1, true, false>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
+        ntt_inverse<M, 1, true, false, SHFL>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
         store_natural(limb, v[0], t);
     }
 }
 
-template <bool INV>
+// SHFL: the last (intra-warp) exchange through warp shuffles instead of shared memory (A/B variant, see ntt.cuh)
+template <bool INV, bool SHFL>
 // the forward transform fits 40 registers (3 CTAs per SM, +9 % on the 36-bit primes); the inverse does not gain from it
 __global__ void __launch_bounds__(kThreads, INV ? 2 : 3) k_ntt(u64 *data, LimbMods mods) {
     extern __shared__ __align__(16) u64 smem[];
     const int t = threadIdx.x;
     u64 *limb = data + (size_t)blockIdx.x * kN;
     switch (mods.mod[blockIdx.x % mods.n]) {
-        case MQ0: ntt_limb_body<MQ0, INV>(limb, smem, t); break;
-        case MQ1: ntt_limb_body<MQ1, INV>(limb, smem, t); break;
-        case MP: ntt_limb_body<MP, INV>(limb, smem, t); break;
-        case MB0: ntt_limb_body<MB0, INV>(limb, smem, t); break;
-        case MB1: ntt_limb_body<MB1, INV>(limb, smem, t); break;
-        default: ntt_limb_body<MSK, INV>(limb, smem, t); break;
+        case MQ0: ntt_limb_body<MQ0, INV, SHFL>(limb, smem, t); break;
+        case MQ1: ntt_limb_body<MQ1, INV, SHFL>(limb, smem, t); break;
+        case MP: ntt_limb_body<MP, INV, SHFL>(limb, smem, t); break;
+        case MB0: ntt_limb_body<MB0, INV, SHFL>(limb, smem, t); break;
+        case MB1: ntt_limb_body<MB1, INV, SHFL>(limb, smem, t); break;
+        default: ntt_limb_body<MSK, INV, SHFL>(limb, smem, t); break;
     }
 }
 
@@ -1149,10 +1150,14 @@ static int eltwise_grid(size_t n, int block) {
 
 cudaError_t launch_ntt(u64 *data, size_t n_limbs, const LimbMods &mods, bool inverse, cudaStream_t s) {
     if (n_limbs == 0) return cudaSuccess;
-    if (inverse)
-        k_ntt<true><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
-    else
-        k_ntt<false><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
+    static const bool shfl = [] {
+        const char *v = getenv("FHE_B200_NTT_SHFL");
+        return v && *v == '1';
+    }();
+    if (inverse && shfl) k_ntt<true, true><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
+    else if (inverse) k_ntt<true, false><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
+    else if (shfl) k_ntt<false, true><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
+    else k_ntt<false, false><<<(unsigned)n_limbs, kThreads, kSmem1, s>>>(data, mods);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
