@@ -367,6 +367,12 @@ int32_t fhe_b200_mul_relin_frames(int32_t device, const uint8_t *a_frames, const
                                   uint8_t *out_frames, size_t n, int32_t *status) {
     DEV_GUARD(Engine::get().mul_relin_frames(device, a_frames, b_frames, stride, rk, out_frames, n, status));
 }
+int32_t fhe_b200_upload_frames(int32_t device, const uint8_t *frames, size_t stride, size_t n, uint64_t *d_words, int32_t *status) {
+    DEV_GUARD(Engine::get().upload_frames(device, frames, stride, n, d_words, status));
+}
+int32_t fhe_b200_download_frames(int32_t device, const uint64_t *d_words, size_t n, uint8_t *out_frames, int32_t *status) {
+    DEV_GUARD(Engine::get().download_frames(device, d_words, n, out_frames, status));
+}
 size_t fhe_b200_frame_bytes(void) { return kPackedFrameBytes; }
 size_t fhe_b200_frame_stride(void) { return kPackedFrameStride; }
 int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,

@@ -735,6 +735,94 @@ void Engine::mul_relin_frames(int device, const uint8_t *fa, const uint8_t *fb, 
     }
 }
 
+// ---------------------------------------------------------------- serialized <-> device-resident ciphertexts
+Engine::XferPipe &Engine::xfer_pipe(int device, size_t n, size_t slot_bytes) {
+    {
+        std::lock_guard<std::mutex> lk(arena_mu_);
+        if (xfers_.size() < (size_t)n_devices_) xfers_.resize((size_t)n_devices_);
+        if (!xfers_[(size_t)device]) xfers_[(size_t)device].reset(new XferPipe());
+    }
+    XferPipe &X = *xfers_[(size_t)device];
+    if (!X.d_prefix) {
+        uint8_t prefix[kCtPrefixBytes];
+        canonical_ct_prefix(prefix);
+        cuda_throw(cudaMalloc((void **)&X.d_prefix, kCtPrefixBytes), "cudaMalloc");
+        cuda_throw(cudaMemcpy(X.d_prefix, prefix, kCtPrefixBytes, cudaMemcpyHostToDevice), "upload prefix");
+    }
+    for (auto &sl : X.slot) {
+        if (!sl.stream) {
+            cuda_throw(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            cuda_throw(cudaMalloc((void **)&sl.d_jobs, kXferChunk * sizeof(CodecJob)), "cudaMalloc");
+            cuda_throw(cudaMallocHost((void **)&sl.h_jobs, kXferChunk * sizeof(CodecJob)), "cudaMallocHost");
+            cuda_throw(cudaMalloc((void **)&sl.d_status, kXferChunk * sizeof(int32_t)), "cudaMalloc");
+        }
+        if (sl.d_frames_bytes < slot_bytes) {
+            cuda_throw(cudaStreamSynchronize(sl.stream), "sync before staging regrow");
+            cudaFree(sl.d_frames);
+            cuda_throw(cudaMalloc((void **)&sl.d_frames, slot_bytes), "cudaMalloc");
+            cuda_throw(cudaMemset(sl.d_frames, 0, slot_bytes), "cudaMemset");
+            sl.d_frames_bytes = slot_bytes;
+        }
+    }
+    if (X.h_status_cap < n) {
+        if (X.h_status) cudaFreeHost(X.h_status);
+        cuda_throw(cudaMallocHost((void **)&X.h_status, n * sizeof(int32_t)), "cudaMallocHost");
+        X.h_status_cap = n;
+    }
+    return X;
+}
+
+// frames (host, `stride` apart) -> d_words [n][2][2][N] on `device`.  status[i]: 0 ok, 1 not a structured frame or a residue out
+// of range (the words of that ciphertext are then undefined).
+void Engine::upload_frames(int device, const uint8_t *frames, size_t stride, size_t n, uint64_t *d_words, int32_t *status) {
+    if (n == 0) return;
+    if (stride < kPackedFrameBytes) throw std::runtime_error("upload_frames: stride smaller than a structured frame");
+    device_context(device);
+    XferPipe &X = xfer_pipe(device, n, kXferChunk * stride + 2 * kFramePad);
+    std::lock_guard<std::mutex> lk(X.mu);
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += kXferChunk, k++) {
+        const size_t c = std::min(kXferChunk, n - off);
+        XferSlot &sl = X.slot[k & 1];
+        cudaStream_t s = sl.stream;
+        if (k >= 2) cuda_throw(cudaStreamSynchronize(s), "slot sync");  // h_jobs of this slot are free again
+        for (size_t i = 0; i < c; i++) sl.h_jobs[i] = CodecJob{kFramePad + i * stride, (uint32_t)kPackedFrameBytes, kJobPacked, (int32_t)i, 0};
+        cuda_throw(cudaMemcpyAsync(sl.d_jobs, sl.h_jobs, c * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
+        cuda_throw(cudaMemcpyAsync(sl.d_frames + kFramePad, frames + off * stride, (c - 1) * stride + kPackedFrameBytes, cudaMemcpyHostToDevice, s),
+                   "H2D frames");
+        cuda_throw(launch_codec_inflate(sl.d_frames, nullptr, sl.d_jobs, sl.d_status, nullptr, X.d_prefix, d_words + off * kCtWords, nullptr,
+                                        (int)c, false, true, false, s),
+                   "frame unpack");
+        cuda_throw(cudaMemcpyAsync(X.h_status + off, sl.d_status, c * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H status");
+    }
+    for (auto &sl : X.slot) cuda_throw(cudaStreamSynchronize(sl.stream), "xfer sync");
+    if (status)
+        for (size_t i = 0; i < n; i++) status[i] = X.h_status[i] == kJobFallback ? 1 : 0;
+}
+
+// d_words [n][2][2][N] on `device` -> n structured frames (host, kPackedFrameStride apart).  status[i]: 0 ok, 2 the ciphertext is
+// constant (transparent) and has no structured frame: serialise it with fhe_b200_write_ciphertext.
+void Engine::download_frames(int device, const uint64_t *d_words, size_t n, uint8_t *out_frames, int32_t *status) {
+    if (n == 0) return;
+    device_context(device);
+    XferPipe &X = xfer_pipe(device, n, kXferChunk * kPackedFrameStride);
+    std::lock_guard<std::mutex> lk(X.mu);
+    size_t k = 0;
+    for (size_t off = 0; off < n; off += kXferChunk, k++) {
+        const size_t c = std::min(kXferChunk, n - off);
+        XferSlot &sl = X.slot[k & 1];
+        cudaStream_t s = sl.stream;
+        cuda_throw(launch_codec_pack(d_words + off * kCtWords, sl.d_frames, sl.d_status, X.d_prefix, (int)c, s), "frame pack");
+        cuda_throw(cudaMemcpyAsync(out_frames + off * kPackedFrameStride, sl.d_frames, (c - 1) * kPackedFrameStride + kPackedFrameBytes,
+                                   cudaMemcpyDeviceToHost, s),
+                   "D2H frames");
+        cuda_throw(cudaMemcpyAsync(X.h_status + off, sl.d_status, c * sizeof(int32_t), cudaMemcpyDeviceToHost, s), "D2H flags");
+    }
+    for (auto &sl : X.slot) cuda_throw(cudaStreamSynchronize(sl.stream), "xfer sync");
+    if (status)
+        for (size_t i = 0; i < n; i++) status[i] = X.h_status[i] ? 2 : 0;
+}
+
 // ---------------------------------------------------------------- byte surface, one call
 namespace {
 struct LaneGuard {

@@ -136,6 +136,11 @@ class Engine {
     void mul_relin_frames(int device, const uint8_t *fa, const uint8_t *fb, size_t stride, const uint64_t *rk, uint8_t *fout, size_t n,
                           int32_t *status);
 
+    // Device-resident ciphertexts from / to serialized form (structured frames), so that a chain of device-resident ops pays
+    // PCIe once at each end: frames (host) -> validated limb arrays on the device, and back.  Synchronous, chunk-pipelined.
+    void upload_frames(int device, const uint8_t *frames, size_t stride, size_t n, uint64_t *d_words, int32_t *status);
+    void download_frames(int device, const uint64_t *d_words, size_t n, uint8_t *out_frames, int32_t *status);
+
     // Optional per-kernel timing of mul_relin(): CUDA events around every launch on the caller's stream.
     // kernel ids: see kKernelNames.  report() synchronises the device.
     static constexpr int kNumTimedKernels = 10;
@@ -244,6 +249,24 @@ class Engine {
         std::mutex mu;
     };
     std::vector<std::unique_ptr<HostPipe>> pipes_;
+    // staging of upload_frames / download_frames: two slots per device, alternating chunks
+    struct XferSlot {
+        cudaStream_t stream = nullptr;
+        uint8_t *d_frames = nullptr;  // chunk * stride + 2 pads (upload) or chunk * kPackedFrameStride (download)
+        size_t d_frames_bytes = 0;
+        struct CodecJob *d_jobs = nullptr, *h_jobs = nullptr;
+        int32_t *d_status = nullptr;
+    };
+    struct XferPipe {
+        uint8_t *d_prefix = nullptr;
+        int32_t *h_status = nullptr;
+        size_t h_status_cap = 0;
+        XferSlot slot[2];
+        std::mutex mu;
+    };
+    static constexpr size_t kXferChunk = 256;
+    std::vector<std::unique_ptr<XferPipe>> xfers_;
+    XferPipe &xfer_pipe(int device, size_t n, size_t slot_bytes);
 
     struct TimedLaunch {
         int kernel;

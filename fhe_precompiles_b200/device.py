@@ -147,6 +147,30 @@ def mul_relin_frames(fa: torch.Tensor, fb: torch.Tensor, rk: torch.Tensor, out: 
     return out
 
 
+def upload_frames(frames: torch.Tensor, device: int = 0):
+    """frames: HOST uint8 [n, stride] whose rows start with a structured frame -> (ct [n,2,2,4096] int64 on `device`, status [n] int32
+    host: 0 ok, 1 rejected).  The serialized -> device-resident end of a chain of device-resident operations."""
+    if frames.is_cuda or not frames.is_contiguous() or frames.dtype != torch.uint8:
+        raise ValueError("upload_frames takes a contiguous host uint8 tensor")
+    n = frames.shape[0]
+    ct = torch.empty((n, 2, 2, N), dtype=torch.int64, device=torch.device("cuda", device))
+    status = torch.zeros((n,), dtype=torch.int32)
+    _check(_lib.lib().fhe_b200_upload_frames(device, frames.data_ptr(), frames.shape[1], n, ct.data_ptr(), status.data_ptr()))
+    return ct, status
+
+
+def download_frames(ct: torch.Tensor, out: torch.Tensor = None):
+    """ct [n,2,2,4096] on a CUDA device -> (frames HOST uint8 [n, frame_stride()], status [n] int32: 0 ok, 2 constant ciphertext)."""
+    dev = _dev(ct)
+    n = ct.shape[0]
+    torch.cuda.current_stream(dev).synchronize()  # the library copies on its own streams: ct must be complete
+    if out is None:
+        out = torch.zeros((n, frame_stride()), dtype=torch.uint8).pin_memory()
+    status = torch.zeros((n,), dtype=torch.int32)
+    _check(_lib.lib().fhe_b200_download_frames(dev, ct.data_ptr(), n, out.data_ptr(), status.data_ptr()))
+    return out, status
+
+
 def frame_bytes() -> int:
     return int(_lib.lib().fhe_b200_frame_bytes())
 

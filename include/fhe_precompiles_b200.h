@@ -165,6 +165,16 @@ int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_
  * Evaluator::multiply + relinearize_inplace in fhe_binary_op (/root/reference/src/fhe.rs:21-30). */
 int32_t fhe_b200_mul_relin_frames(int32_t device, const uint8_t *a_frames, const uint8_t *b_frames, size_t stride, const uint64_t *rk,
                                   uint8_t *out_frames, size_t n, int32_t *status);
+/* Device-resident ciphertexts from / to SERIALIZED form, so that a chain of device-resident operations (fhe_b200_add ...
+ * fhe_b200_mul_relin on device pointers) crosses PCIe once at each end instead of once per operation.
+ * upload: n structured frames (host, `stride` apart, as for fhe_b200_mul_relin_frames) -> d_words [n][2][2][4096] on `device`,
+ *   validated like SEAL's checked load; status[i] (host, may be NULL): 0 ok, 1 not a structured frame or a residue >= q.
+ * download: d_words -> n structured frames at out_frames + i * fhe_b200_frame_stride() (host); status[i]: 0 ok, 2 the
+ *   ciphertext is constant (transparent) and has no structured frame (serialise it with fhe_b200_write_ciphertext).
+ * Both are synchronous and pipeline chunks of 256 ciphertexts over two streams; pin the host buffers for full PCIe rate.
+ * Replaces bincode::deserialize / serialize of a Ciphertext around a sequence of Runtime::run calls (fhe.rs:21-30). */
+int32_t fhe_b200_upload_frames(int32_t device, const uint8_t *frames, size_t stride, size_t n, uint64_t *d_words, int32_t *status);
+int32_t fhe_b200_download_frames(int32_t device, const uint64_t *d_words, size_t n, uint8_t *out_frames, int32_t *status);
 size_t fhe_b200_frame_bytes(void);
 size_t fhe_b200_frame_stride(void);
 /* Integer-pipe peak of `device` in 1e12 multiply-adds/s, measured by a register-only microbenchmark

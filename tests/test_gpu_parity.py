@@ -1070,3 +1070,51 @@ def test_config5_encrypt_decrypt_roundtrip(dev, keys):
     cts = to_np(ct)
     for i in range(0, n, 64):
         assert np.array_equal(cts[i], bfv.encrypt_seeded(keys.net_pk, plains[i, :64].astype(np.uint64), seeds[i])), f"op {i}"
+
+
+def test_upload_chain_download_frames(dev, keys):
+    """Serialized ciphertexts -> device-resident limb arrays -> a chain of device-resident ops -> serialized result: PCIe is crossed
+    once at each end.  300 ciphertexts (two transfer chunks); result frames byte-identical to the format oracle's frames of the
+    oracle's (a * b + a) - b; a frame with a corrupted fixed byte, a residue >= q and a non-structured frame are rejected
+    (status 1); a transparent result has no structured frame (status 2)."""
+    import torch
+
+    n = 300
+    rng = np.random.default_rng(61)
+    a, b = random_ct(rng, n), random_ct(rng, n)
+    fb_, fs = dev.frame_bytes(), dev.frame_stride()
+    stride = fs + 8
+
+    def frames_of(cts):
+        buf = np.zeros((len(cts), stride), dtype=np.uint8)
+        for i, c in enumerate(cts):
+            buf[i, :fb_] = np.frombuffer(F.zstd_structured_frame(F.fresh_data_ciphertext(c).payload()), dtype=np.uint8)
+        return buf
+
+    fa, fbuf = frames_of(a), frames_of(b)
+    bad = {5: "fixed byte", 17: "range", 200: "libzstd frame"}
+    fa[5, 10] ^= 0x40
+    over = a[17].copy()
+    over[1, 1, 4095] = MODULI[1]
+    fa[17, :fb_] = np.frombuffer(F.zstd_structured_frame(F.fresh_data_ciphertext(over).payload()), dtype=np.uint8)
+    lib_frame = F.zstd().compress(F.fresh_data_ciphertext(a[200]).payload())
+    fa[200, :] = 0
+    fa[200, : len(lib_frame)] = np.frombuffer(lib_frame, dtype=np.uint8)
+    da, sa = dev.upload_frames(torch.from_numpy(fa).pin_memory())
+    db, sb = dev.upload_frames(torch.from_numpy(fbuf))  # pageable memory works too
+    assert sb.tolist() == [0] * n
+    assert [i for i in range(n) if sa[i] != 0] == sorted(bad) and all(sa[i] == 1 for i in bad)
+    ok = [i for i in range(n) if i not in bad]
+    assert np.array_equal(to_np(da)[ok], a[ok]) and np.array_equal(to_np(db), b)
+    rk = to_dev(keys.rk)
+    res = dev.sub(dev.add(dev.mul_relin(da, db, rk), da), db)
+    out, st = dev.download_frames(res)
+    assert st.tolist() == [0] * n
+    for i in ok[:4] + [255, 256, 257, n - 1]:
+        want = bfv.sub(bfv.add(bfv.mul_relin(a[i], b[i], keys.rk), a[i]), b[i])
+        assert out[i, :fb_].numpy().tobytes() == F.zstd_structured_frame(F.fresh_data_ciphertext(want).payload()), f"ciphertext {i}"
+    # round trip of the frames themselves, and a transparent ciphertext
+    back, st2 = dev.download_frames(db)
+    assert st2.tolist() == [0] * n and np.array_equal(back[:, :fb_].numpy(), fbuf[:, :fb_])
+    _, st3 = dev.download_frames(dev.sub(db[:3], db[:3]))
+    assert st3.tolist() == [2, 2, 2]
