@@ -1099,7 +1099,7 @@ def test_upload_chain_download_frames(dev, keys):
     fa[17, :fb_] = np.frombuffer(F.zstd_structured_frame(F.fresh_data_ciphertext(over).payload()), dtype=np.uint8)
     lib_frame = F.zstd().compress(F.fresh_data_ciphertext(a[200]).payload())
     fa[200, :] = 0
-    fa[200, : len(lib_frame)] = np.frombuffer(lib_frame, dtype=np.uint8)
+    fa[200, :] = np.frombuffer(lib_frame[:stride], dtype=np.uint8)
     da, sa = dev.upload_frames(torch.from_numpy(fa).pin_memory())
     db, sb = dev.upload_frames(torch.from_numpy(fbuf))  # pageable memory works too
     assert sb.tolist() == [0] * n
