@@ -619,6 +619,77 @@ __global__ void __launch_bounds__(kThreads, 3) k_digit_ntt(const u64 *__restrict
         default: digit_ntt_body<MP>(src, dst, smem, t); break;
     }
 }
+// ---- persistent variant of k_digit_ntt with TMA staging (FHE_B200_TMA=1; A/B, profiles/r2_tma_ab.md): one CTA per resident slot
+// walks the (digit, modulus, op) work items; while it transforms item i the TMA engine (cp.async.bulk, one elected thread, no
+// registers in the other threads) brings the 32 KiB of item i + gridDim.x into the other half of a 64 KiB shared buffer, so the
+// head of every transform reads shared memory instead of waiting ~1 us for HBM.  Buffer `cur` is first the landing zone of the
+// bulk copy, then -- once every thread has taken its eight coefficients -- the exchange buffer of the transform.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void tma_load_32k(void *dst_smem, const void *src_gmem, unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(32768u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(32768u), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned done = 0;
+    for (int spin = 0; !done; spin++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (spin > (1 << 22)) __trap();  // a lost bulk copy must fail the launch, never hang the GPU
+    }
+}
+template <int kCtasPerSm>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_digit_ntt_tma(const u64 *__restrict__ c3, u64 *__restrict__ dig, unsigned total) {
+    extern __shared__ __align__(128) u64 smem[];  // [2][kN]
+    __shared__ __align__(8) unsigned long long bar[2];
+    const int t = threadIdx.x;
+    if (t == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // the only loop-carried value is `it`: everything else is rebuilt from special registers and kernel parameters each time, so
+    // that the transform keeps its 40 registers (3 CTAs per SM)
+    const auto src_of = [&](unsigned w) { return c3 + (size_t)(w / 6) * 6 * kN + 4 * kN + (size_t)((w % 6) / 3) * kN; };
+    if (t == 0 && blockIdx.x < total) tma_load_32k(smem, src_of(blockIdx.x), &bar[0]);
+#pragma unroll 1
+    for (unsigned it = 0; blockIdx.x + it * gridDim.x < total; it++) {
+        {
+            u64 v[1][8];
+            {
+                const u64 *buf = smem + (it & 1) * kN;
+                mbar_wait(&bar[it & 1], (it >> 1) & 1);
+#pragma unroll
+                for (int r = 0; r < 8; r++) v[0][r] = buf[r * kThreads + t];
+            }
+            __syncthreads();  // every thread holds its coefficients and has left the previous item's exchange buffer
+            if (t == 0) {
+                const unsigned wn = blockIdx.x + (it + 1) * gridDim.x;
+                if (wn < total) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes of the last exchange first
+                    tma_load_32k(smem + ((it + 1) & 1) * kN, src_of(wn), &bar[(it + 1) & 1]);
+                }
+            }
+            switch ((blockIdx.x + it * gridDim.x) % 3) {
+                case 0: ntt_forward<Mod<MQ0>, 1, false, false>(v, smem + (it & 1) * kN, kt.twf[MQ0], t); break;
+                case 1: ntt_forward<Mod<MQ1>, 1, false, false>(v, smem + (it & 1) * kN, kt.twf[MQ1], t); break;
+                default: ntt_forward<Mod<MP>, 1, false, false>(v, smem + (it & 1) * kN, kt.twf[MP], t); break;
+            }
+            store_chunk8(dig + (size_t)(blockIdx.x + it * gridDim.x) * kN, v[0], t);
+        }
+    }
+}
+
 template <int MI>
 __device__ __forceinline__ void ks_intt_body(const u64 *__restrict__ dg, const u64 *__restrict__ rk, int k, u64 *__restrict__ dst,
                                              u64 *smem, int t) {
@@ -1133,6 +1204,10 @@ cudaError_t kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_relin_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_digit_ntt_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_digit_ntt_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ks_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
     return cudaSuccess;
@@ -1229,8 +1304,21 @@ cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaS
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
+static int tma_mode() {  // 0 off (default), 1: 3 CTAs per SM (40 registers, spills), 2: 2 CTAs per SM (64 registers)
+    static const int mode = [] {
+        const char *v = getenv("FHE_B200_TMA");
+        return v ? atoi(v) : 0;
+    }();
+    return mode;
+}
 cudaError_t launch_digit_ntt(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
+    if (tma_mode() && n_ops >= 148) {
+        if (tma_mode() == 2) k_digit_ntt_tma<2><<<148 * 2, kThreads, kSmem2, s>>>(c3, dig, (unsigned)(6 * n_ops));
+        else k_digit_ntt_tma<3><<<148 * 3, kThreads, kSmem2, s>>>(c3, dig, (unsigned)(6 * n_ops));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return cudaGetLastError();
+    }
     k_digit_ntt<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(c3, dig);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();

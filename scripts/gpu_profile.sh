@@ -5,7 +5,7 @@ set -u
 TAG=${1:-r1}
 OUT=gpurun_out
 mkdir -p $OUT
-CMD="python bench.py --steps 2 --warmup 3 --batch 1184 --no-cpu-baseline --no-e2e"
+CMD="python bench.py --steps 2 --warmup 3 --batch 1184 --no-cpu-baseline --no-e2e --no-configs"
 $CMD > $OUT/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv $CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 $CMD > $OUT/${TAG}_plain2.log 2>&1 &&

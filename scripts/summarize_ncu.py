@@ -67,7 +67,8 @@ with open(os.path.join(ROOT, "profiles", f"{tag}_kernels.md"), "w") as out:
     out.write("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
     out.write("\n".join(lines) + "\n")
 with open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w") as out:
-    json.dump({"tag": tag, "ops_per_launch": ops, "dram_bytes_per_op": traffic, "fmaheavy_pct": heavy}, out, indent=1)
+    json.dump({"tag": tag, "ops_per_launch": ops, "dram_bytes_per_op": traffic, "fmaheavy_pct": heavy,
+               "dram_bytes_per_op_total": sum(traffic.values())}, out, indent=1)
 # launch list
 src = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
 if os.path.exists(src):
