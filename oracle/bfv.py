@@ -49,6 +49,11 @@ def lib() -> ctypes.CDLL:
         L.bfvo_decrypt.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.bfvo_encrypt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint64, ctypes.c_void_p]
         L.bfvo_encrypt_samples.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 4
+        L.bfvo_seal_prng.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+        L.bfvo_seal_sample.restype = ctypes.c_size_t
+        L.bfvo_seal_sample.argtypes = [ctypes.c_void_p] * 4
+        L.bfvo_encrypt_samples_data_level.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 4
+        L.bfvo_seal_encrypt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.bfvo_batch_mul_relin.restype = ctypes.c_double
         L.bfvo_batch_mul_relin.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_int]
         L.bfvo_batch_ntt.restype = ctypes.c_double
@@ -259,84 +264,49 @@ def encrypt(pk: np.ndarray, plain: np.ndarray, seed: int) -> np.ndarray:
     return out
 
 
-# ---------------------------------------------------------------- restatement of the GPU encryptor's sampler
-# (fhe_precompiles_b200/csrc/kernels.cu: chacha12_block, sample_ternary, sample_noise).  The reference hands SEAL the
-# 512-bit SHA-512 digest as PRNG seed (/root/reference/src/fhe.rs:611-616); SEAL's own Blake2xb stream is not reproduced
-# (SURVEY 8f-1), so the product expands the same seed with ChaCha12 and this is its bit-exact CPU twin.
-NOISE_CDF = np.array([
-    0x1f67485e1414e200, 0x3be85f5582810200, 0x53644e2dedd21400, 0x64f422f09cf1bc00, 0x70dfcc250f890800,
-    0x7837f1b047d3fc00, 0x7c535c45b5071400, 0x7e690b1eb1011400, 0x7f5eeb470d610c00, 0x7fc5bca5a5143c00,
-    0x7fecc2f990af3800, 0x7ffa349ee365e800, 0x7ffe68c004b14800, 0x7fff9a26cfa95400, 0x7fffe8d1193b7400,
-    0x7ffffb3514071000, 0x7fffff1c06e24c00, 0x7fffffdc665b1800, 0x7ffffffe05c3f800], dtype=np.uint64)
+# ---------------------------------------------------------------- SEAL-exact deterministic encryption
+# What FheApp::encrypt / reencrypt (/root/reference/src/fhe.rs:594-657) obtain from sunscreen's `encrypt_deterministic`:
+# Blake2xb PRNG keyed by the SHA-512 digest, libstdc++ ternary + clipped-normal samplers, encryption at the data level
+# (no special modulus).  C restatement in bfv_oracle.c, pinned by the reference's SHA-512 known answers
+# (tests/test_oracle_kat.py); oracle/seal_encrypt.py is an independent pure-Python restatement of the same stack.
+def _seed8(seed8) -> np.ndarray:
+    if isinstance(seed8, (bytes, bytearray)):
+        assert len(seed8) == 64
+        return np.frombuffer(bytes(seed8), dtype="<u8").astype(np.uint64)
+    a = np.ascontiguousarray(seed8, dtype=np.uint64)
+    assert a.size == 8
+    return a
 
 
-def chacha_core(x: np.ndarray, double_rounds: int) -> np.ndarray:
-    """ChaCha block function (RFC 7539 2.3) on columns of x (uint32 [16, n]) with 2 * double_rounds rounds."""
-    x = x.astype(np.uint32)
-    w = x.copy()
-    rotl = lambda v, n: (v << np.uint32(n)) | (v >> np.uint32(32 - n))
-
-    def qr(a, b, c, d):
-        w[a] += w[b]; w[d] = rotl(w[d] ^ w[a], 16)
-        w[c] += w[d]; w[b] = rotl(w[b] ^ w[c], 12)
-        w[a] += w[b]; w[d] = rotl(w[d] ^ w[a], 8)
-        w[c] += w[d]; w[b] = rotl(w[b] ^ w[c], 7)
-
-    with np.errstate(over="ignore"):
-        for _ in range(double_rounds):
-            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)
-            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)
-        w += x
-    return w
+def seal_prng(seed8, nbytes: int) -> bytes:
+    """First nbytes of SEAL's Blake2xbPRNG stream for the 512-bit seed (8 LE u64 words or the 64 digest bytes)."""
+    out = np.empty(nbytes, dtype=np.uint8)
+    lib().bfvo_seal_prng(_p(_seed8(seed8)), out.ctypes.data_as(ctypes.c_void_p), nbytes)
+    return out.tobytes()
 
 
-def _chacha12_blocks(seed8: np.ndarray, stream: int) -> np.ndarray:
-    """[512 counters][8] u64 output words under the 512-bit seed (8 u64 words): key = words 0..3 xor 4..7, state words
-    12 / 13 = (counter, stream), 14 / 15 = seed word 4; 12 rounds."""
-    seed8 = np.asarray(seed8, dtype=np.uint64)
-    key = seed8[:4] ^ seed8[4:]
-    x = np.zeros((16, 512), dtype=np.uint32)
-    x[0], x[1], x[2], x[3] = 0x61707865, 0x3320646E, 0x79622D32, 0x6B206574
-    for i in range(4):
-        x[4 + 2 * i] = np.uint32(int(key[i]) & 0xFFFFFFFF)
-        x[5 + 2 * i] = np.uint32(int(key[i]) >> 32)
-    x[12] = np.arange(512, dtype=np.uint32)
-    x[13] = stream
-    x[14] = np.uint32(int(seed8[4]) & 0xFFFFFFFF)
-    x[15] = np.uint32(int(seed8[4]) >> 32)
-    w = chacha_core(x, 6)
-    out = w[0::2].astype(np.uint64) | (w[1::2].astype(np.uint64) << np.uint64(32))  # [8][512]
-    return out.T.copy()
+def seal_sample(seed8) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+    """(u, e0, e1, number of 32-bit draws consumed): SEAL's sample_poly_ternary, then sample_poly_normal twice."""
+    smp = [np.empty(N, dtype=np.int8) for _ in range(3)]
+    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    drawn = lib().bfvo_seal_sample(_p(_seed8(seed8)), vp(smp[0]), vp(smp[1]), vp(smp[2]))
+    return smp[0], smp[1], smp[2], int(drawn)
 
 
-def gpu_sampler(seed8) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
-    """(u, e0, e1) int8 [N] exactly as k_encrypt_core draws them: word r of thread t's block -> coefficient r*512 + t."""
-    res = []
-    for stream in range(3):
-        words = _chacha12_blocks(seed8, stream).T.reshape(-1)  # index r*512 + t
-        if stream == 0:
-            smp = np.zeros(N, dtype=np.int8)
-            done = np.zeros(N, dtype=bool)
-            for k in range(32):
-                d = ((words >> np.uint64(2 * k)) & np.uint64(3)).astype(np.int8)
-                take = ~done & (d != 3)
-                smp[take] = d[take] - 1
-                done |= take
-        else:
-            v = words >> np.uint64(1)
-            mag = (v[:, None] >= NOISE_CDF[None, :]).sum(axis=1).astype(np.int8)
-            smp = np.where((words & np.uint64(1)) == 1, -mag, mag).astype(np.int8)
-        res.append(smp)
-    return tuple(res)
+def encrypt_samples_data_level(pk: np.ndarray, plain: np.ndarray, u, e0, e1) -> np.ndarray:
+    pk, pl = _c(pk), _c(plain)
+    out = np.empty((2, 2, N), dtype=np.uint64)
+    vp = lambda x: np.ascontiguousarray(x, dtype=np.int8).ctypes.data_as(ctypes.c_void_p)
+    u, e0, e1 = (np.ascontiguousarray(x, dtype=np.int8) for x in (u, e0, e1))
+    lib().bfvo_encrypt_samples_data_level(_p(pk), _p(pl), pl.size, vp(u), vp(e0), vp(e1), _p(out))
+    return out
 
 
 def encrypt_seeded(pk: np.ndarray, plain: np.ndarray, seed8) -> np.ndarray:
-    """What fhe_b200_encrypt / c_fhe_encrypt_* compute for the 512-bit seed (8 u64 words)."""
+    """sunscreen `encrypt_deterministic(plain, pk, seed)`: what c_fhe_encrypt_* / fhe_b200_encrypt must produce, bit for bit."""
     pk, pl = _c(pk), _c(plain)
-    u, e0, e1 = (np.ascontiguousarray(x) for x in gpu_sampler(seed8))
     out = np.empty((2, 2, N), dtype=np.uint64)
-    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-    lib().bfvo_encrypt_samples(_p(pk), _p(pl), pl.size, vp(u), vp(e0), vp(e1), _p(out))
+    lib().bfvo_seal_encrypt(_p(pk), _p(pl), pl.size, _p(_seed8(seed8)), _p(out))
     return out
 
 

@@ -789,6 +789,197 @@ void bfvo_encrypt_samples(const u64 *pk, const u64 *plain, size_t len, const int
     free(c);
 }
 
+/* ------------------------------------------------------------------ SEAL-exact deterministic encryption
+ * What `FheApp::encrypt` / `reencrypt` (/root/reference/src/fhe.rs:594-657) hand to sunscreen 0.8.1's
+ * `encrypt_deterministic`: the Sunscreen SEAL fork's component-exporting encrypt, seeded with the SHA-512 digest,
+ * WITHOUT the special modulus (the ciphertext is formed directly at the data level from the first two limbs of the
+ * public key), built with SEAL_USE_GAUSSIAN_NOISE.  Pinned by the reference's own SHA-512 known answers
+ * (fhe.rs:2101-2121, 2165-2185, 2224-2244; tests/test_oracle_kat.py reproduces all of them):
+ *   prng   = Blake2xbPRNG(seed): 4096-byte buffers, buffer c = BLAKE2Xb(out 4096, in = c as LE u64, key = 64-byte seed)
+ *   u      = sample_poly_ternary: std::uniform_int_distribution<uint64_t>(0, 2) on 32-bit draws (libstdc++ >= 11: Lemire)
+ *   e0, e1 = sample_poly_normal: ClippedNormalDistribution(0, 3.2, 19.2) over libstdc++ std::normal_distribution<double>
+ *            (Marsaglia polar on generate_canonical<double, 53> = two 32-bit draws, low word first; the second variate
+ *            of a pair is kept for the next call; one distribution object per polynomial), truncated toward zero
+ *   c_j    = INTT(NTT(u) * pk_j) + e_j  mod (q0, q1);  c_0 += round-scaled plaintext
+ * BLAKE2b per RFC 7693; BLAKE2X per the BLAKE2X paper / reference blake2xb.c (node_offset = block index, xof_length in
+ * the upper half of the node-offset field, expansion nodes with fanout = depth = 0, leaf_length = inner_length = 64). */
+static const u64 B2B_IV[8] = {0x6A09E667F3BCC908ull, 0xBB67AE8584CAA73Bull, 0x3C6EF372FE94F82Bull, 0xA54FF53A5F1D36F1ull,
+                              0x510E527FADE682D1ull, 0x9B05688C2B3E6C1Full, 0x1F83D9ABFB41BD6Bull, 0x5BE0CD19137E2179ull};
+static const uint8_t B2B_SIGMA[12][16] = {
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3},
+    {11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4}, {7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8},
+    {9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13}, {2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9},
+    {12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11}, {13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10},
+    {6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5}, {10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0},
+    {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15}, {14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3}};
+static inline u64 rotr64(u64 x, int n) { return (x >> n) | (x << (64 - n)); }
+/* one compression: h <- F(h, m, t, last) (RFC 7693 3.2; t < 2^64 here) */
+static void b2b_compress(u64 h[8], const u64 m[16], u64 t, int last) {
+    u64 v[16];
+    for (int i = 0; i < 8; i++) v[i] = h[i], v[i + 8] = B2B_IV[i];
+    v[12] ^= t;
+    if (last) v[14] = ~v[14];
+#define B2B_G(a, b, c, d, x, y)                                                                                  \
+    v[a] = v[a] + v[b] + (x), v[d] = rotr64(v[d] ^ v[a], 32), v[c] = v[c] + v[d], v[b] = rotr64(v[b] ^ v[c], 24), \
+    v[a] = v[a] + v[b] + (y), v[d] = rotr64(v[d] ^ v[a], 16), v[c] = v[c] + v[d], v[b] = rotr64(v[b] ^ v[c], 63)
+    for (int r = 0; r < 12; r++) {
+        const uint8_t *s = B2B_SIGMA[r];
+        B2B_G(0, 4, 8, 12, m[s[0]], m[s[1]]);
+        B2B_G(1, 5, 9, 13, m[s[2]], m[s[3]]);
+        B2B_G(2, 6, 10, 14, m[s[4]], m[s[5]]);
+        B2B_G(3, 7, 11, 15, m[s[6]], m[s[7]]);
+        B2B_G(0, 5, 10, 15, m[s[8]], m[s[9]]);
+        B2B_G(1, 6, 11, 12, m[s[10]], m[s[11]]);
+        B2B_G(2, 7, 8, 13, m[s[12]], m[s[13]]);
+        B2B_G(3, 4, 9, 14, m[s[14]], m[s[15]]);
+    }
+#undef B2B_G
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+/* parameter block words 0..2 (the rest is zero): digest_length | key_length<<8 | fanout<<16 | depth<<24 | leaf_length<<32,
+ * node_offset | xof_length<<32, node_depth | inner_length<<8 */
+static void b2b_init(u64 h[8], unsigned digest, unsigned keylen, unsigned fanout, unsigned depth, u64 leaf, u64 node_offset,
+                     u64 xof, unsigned inner) {
+    for (int i = 0; i < 8; i++) h[i] = B2B_IV[i];
+    h[0] ^= (u64)digest | ((u64)keylen << 8) | ((u64)fanout << 16) | ((u64)depth << 24) | (leaf << 32);
+    h[1] ^= node_offset | (xof << 32);
+    h[2] ^= (u64)inner << 8;
+}
+#define SEAL_PRNG_BUF 4096
+/* buffer `counter` of the PRNG stream (4096 bytes, as 512 LE words) */
+static void seal_prng_buffer(const u64 seed[8], u64 counter, u64 out[SEAL_PRNG_BUF / 8]) {
+    u64 h[8], m[16] = {0};
+    b2b_init(h, 64, 64, 1, 1, 0, 0, SEAL_PRNG_BUF, 0);
+    for (int i = 0; i < 8; i++) m[i] = seed[i]; /* the key, zero padded to one block */
+    b2b_compress(h, m, 128, 0);
+    for (int i = 0; i < 16; i++) m[i] = 0;
+    m[0] = counter;
+    b2b_compress(h, m, 136, 1);
+    u64 root[16] = {0};
+    for (int i = 0; i < 8; i++) root[i] = h[i];
+    for (u64 node = 0; node < SEAL_PRNG_BUF / 64; node++) {
+        u64 g[8];
+        b2b_init(g, 64, 0, 0, 0, 64, node, SEAL_PRNG_BUF, 64);
+        b2b_compress(g, root, 64, 1);
+        for (int i = 0; i < 8; i++) out[node * 8 + i] = g[i];
+    }
+}
+void bfvo_seal_prng(const uint64_t seed[8], uint8_t *out, size_t nbytes) {
+    u64 buf[SEAL_PRNG_BUF / 8];
+    for (size_t off = 0, c = 0; off < nbytes; off += SEAL_PRNG_BUF, c++) {
+        seal_prng_buffer(seed, c, buf);
+        size_t k = nbytes - off < SEAL_PRNG_BUF ? nbytes - off : SEAL_PRNG_BUF;
+        memcpy(out + off, buf, k); /* little-endian host */
+    }
+}
+typedef struct {
+    u64 seed[8], counter;
+    u64 buf[SEAL_PRNG_BUF / 8];
+    size_t pos; /* in 32-bit words */
+    size_t drawn;
+} SealPrng;
+static void sprng_init(SealPrng *p, const u64 seed[8]) {
+    memcpy(p->seed, seed, 64);
+    p->counter = 0, p->drawn = 0;
+    seal_prng_buffer(p->seed, p->counter++, p->buf);
+    p->pos = 0;
+}
+static inline uint32_t sprng_u32(SealPrng *p) {
+    uint32_t v = (uint32_t)(p->buf[p->pos >> 1] >> (32 * (p->pos & 1)));
+    p->pos++, p->drawn++;
+    if (p->pos == SEAL_PRNG_BUF / 4) {
+        seal_prng_buffer(p->seed, p->counter++, p->buf);
+        p->pos = 0;
+    }
+    return v;
+}
+/* libstdc++ (GCC >= 11) uniform_int_distribution<uint64_t>(0, 2) over a URNG with range exactly 2^32: _S_nd */
+static inline uint32_t uniform3(SealPrng *p) {
+    u64 product = (u64)sprng_u32(p) * 3u;
+    uint32_t low = (uint32_t)product;
+    if (low < 3u) {
+        const uint32_t threshold = (uint32_t)(0u - 3u) % 3u;
+        while (low < threshold) {
+            product = (u64)sprng_u32(p) * 3u;
+            low = (uint32_t)product;
+        }
+    }
+    return (uint32_t)(product >> 32);
+}
+/* libstdc++ generate_canonical<double, 53> over a 32-bit URNG: two draws, low word first */
+static inline double canonical53(SealPrng *p) {
+    double sum = (double)sprng_u32(p);
+    sum += (double)sprng_u32(p) * 4294967296.0;
+    double r = sum / 18446744073709551616.0;
+    return r >= 1.0 ? nextafter(1.0, 0.0) : r;
+}
+static void sample_normal_poly(SealPrng *p, int8_t *out) {
+    int have = 0;
+    double saved = 0.0;
+    for (size_t i = 0; i < N; i++) {
+        double value;
+        for (;;) {
+            double ret;
+            if (have) {
+                have = 0, ret = saved;
+            } else {
+                double x, y, r2;
+                do {
+                    x = 2.0 * canonical53(p) - 1.0;
+                    y = 2.0 * canonical53(p) - 1.0;
+                    r2 = x * x + y * y;
+                } while (r2 > 1.0 || r2 == 0.0);
+                const double mult = sqrt(-2 * log(r2) / r2);
+                saved = x * mult, have = 1;
+                ret = y * mult;
+            }
+            value = ret * 3.2 + 0.0;
+            if (fabs(value - 0.0) <= 19.2) break;
+        }
+        out[i] = (int8_t)(int64_t)value;
+    }
+}
+size_t bfvo_seal_sample(const uint64_t seed[8], int8_t *u, int8_t *e0, int8_t *e1) {
+    SealPrng *p = (SealPrng *)malloc(sizeof(SealPrng));
+    sprng_init(p, seed);
+    for (size_t i = 0; i < N; i++) u[i] = (int8_t)uniform3(p) - 1;
+    sample_normal_poly(p, e0);
+    sample_normal_poly(p, e1);
+    size_t drawn = p->drawn;
+    free(p);
+    return drawn;
+}
+/* encrypt_zero_asymmetric at the DATA level (first two limbs of each public-key polynomial; no modulus switching) +
+ * multiply_add_plain_with_scaling_variant */
+void bfvo_encrypt_samples_data_level(const u64 *pk, const u64 *plain, size_t len, const int8_t *u, const int8_t *e0, const int8_t *e1,
+                                     u64 *ct) {
+    bfvo_init();
+    u64 *un = (u64 *)malloc((size_t)2 * N * 8);
+    for (int J = 0; J < 2; J++) {
+        for (size_t i = 0; i < N; i++) un[(size_t)J * N + i] = u[i] < 0 ? C.mod[J].q - 1 : (u64)u[i];
+        ntt_fwd(un + (size_t)J * N, J);
+    }
+    for (int j = 0; j < 2; j++) {
+        const int8_t *e = j == 0 ? e0 : e1;
+        for (int J = 0; J < 2; J++) {
+            const Mod *m = &C.mod[J];
+            u64 *x = ct + ((size_t)j * 2 + J) * N;
+            const u64 *k = pk + ((size_t)j * 3 + J) * N;
+            for (size_t i = 0; i < N; i++) x[i] = mulmod(k[i], un[(size_t)J * N + i], m);
+            ntt_inv(x, J);
+            for (size_t i = 0; i < N; i++) x[i] = e[i] < 0 ? submod(x[i], (u64)(-e[i]), m) : addmod(x[i], (u64)e[i], m);
+        }
+    }
+    plain_scaled(ct, plain, len, 0);
+    free(un);
+}
+void bfvo_seal_encrypt(const u64 *pk, const u64 *plain, size_t len, const uint64_t seed[8], u64 *ct) {
+    int8_t *smp = (int8_t *)malloc((size_t)3 * N);
+    bfvo_seal_sample(seed, smp, smp + N, smp + 2 * N);
+    bfvo_encrypt_samples_data_level(pk, plain, len, smp, smp + N, smp + 2 * N, ct);
+    free(smp);
+}
+
 /* SEAL Decryptor::bfv_decrypt: dot product with powers of s, then exact round(t*x/q) mod t
  * (SEAL's decrypt_scale_and_round yields the same value whenever the noise budget is > 0). */
 int bfvo_decrypt(const u64 *ct, size_t npolys, const u64 *sk, u64 *plain_out) {

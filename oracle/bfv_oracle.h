@@ -92,6 +92,15 @@ void bfvo_encrypt(const uint64_t *pk, const uint64_t *plain, size_t plain_len, u
 /* the same computation with caller-supplied samples (u ternary, e0 / e1 errors, N int8 each) */
 void bfvo_encrypt_samples(const uint64_t *pk, const uint64_t *plain, size_t plain_len, const int8_t *u, const int8_t *e0,
                           const int8_t *e1, uint64_t *ct_out);
+/* SEAL-exact deterministic encryption (what FheApp::encrypt / reencrypt produce; pinned by the reference's SHA-512
+ * known answers, see bfv_oracle.c).  seed = the SHA-512 digest as 8 little-endian words.
+ * bfvo_seal_prng: the first nbytes of Blake2xbPRNG(seed)'s stream.  bfvo_seal_sample: (u, e0, e1), returns the number of
+ * 32-bit draws consumed.  bfvo_seal_encrypt: pk [2][3][N] NTT form -> ct [2][2][N] (no special modulus). */
+void bfvo_seal_prng(const uint64_t seed[8], uint8_t *out, size_t nbytes);
+size_t bfvo_seal_sample(const uint64_t seed[8], int8_t *u, int8_t *e0, int8_t *e1);
+void bfvo_encrypt_samples_data_level(const uint64_t *pk, const uint64_t *plain, size_t plain_len, const int8_t *u, const int8_t *e0,
+                                     const int8_t *e1, uint64_t *ct_out);
+void bfvo_seal_encrypt(const uint64_t *pk, const uint64_t *plain, size_t plain_len, const uint64_t seed[8], uint64_t *ct_out);
 /* Decrypt size-2 or size-3 data-level ciphertext with sk [3][N] (NTT form).
  * plain_out gets N coefficients < t.  Returns the invariant noise budget in bits (<=0: failed). */
 int bfvo_decrypt(const uint64_t *ct, size_t npolys, const uint64_t *sk, uint64_t *plain_out);

@@ -18,9 +18,10 @@ What it follows
   serialization format.
 
 Pinning: key-file layout, SEAL headers, parms_id rule and zstd level are pinned by the
-fixtures (src/data/network.{pub,pri}, tests/data/{public,private}_key.bin).  The
-`Ciphertext.data_type` string has no fixture in the reference ("parity unpinned" for
-that one field); it is treated as an opaque length-prefixed string everywhere.
+fixtures (src/data/network.{pub,pri}, tests/data/{public,private}_key.bin).  The whole
+`Ciphertext` serialisation -- data_type string, bincode layout, SEAL ciphertext payload and
+its libzstd level-3 compression -- is pinned by the reference's SHA-512 known answers of
+`encrypt` / `reencrypt` (fhe.rs:2101-2244, tests/test_oracle_kat.py).
 """
 from __future__ import annotations
 
@@ -49,12 +50,15 @@ SEAL_MAGIC = 0xA15E
 SEAL_HEADER_SIZE = 16
 COMPR_NONE, COMPR_ZLIB, COMPR_ZSTD = 0, 1, 2
 
-# Type-name strings sunscreen puts in `Ciphertext.data_type` (recollection, unpinned).
+# Type-name strings sunscreen puts in `Ciphertext.data_type`: `#[derive(TypeName)]` = module_path!() + "::" + the struct's
+# identifier WITHOUT generic arguments, so Unsigned<1> (Unsigned64) and Unsigned<4> (Unsigned256) share one name.  The
+# Unsigned spelling and the version are pinned by the reference's SHA-512 known answers (tests/test_oracle_kat.py); Signed
+# and Fractional follow the same derive.
 TYPE_NAMES = {
     "i64": "sunscreen::types::bfv::signed::Signed",
-    "u64": "sunscreen::types::bfv::unsigned::Unsigned<1>",
-    "u256": "sunscreen::types::bfv::unsigned::Unsigned<4>",
-    "frac64": "sunscreen::types::bfv::fractional::Fractional<64>",
+    "u64": "sunscreen::types::bfv::unsigned::Unsigned",
+    "u256": "sunscreen::types::bfv::unsigned::Unsigned",
+    "frac64": "sunscreen::types::bfv::fractional::Fractional",
 }
 SUNSCREEN_VERSION = "0.8.1"
 

@@ -1,14 +1,21 @@
-"""TEST INFRASTRUCTURE ONLY -- attempt at a bit-exact restatement of SEAL 4.0's seeded public-key encryption
-(the path behind `FheApp::encrypt`, /root/reference/src/fhe.rs:594-618, pinned there by SHA-512 known answers at
-fhe.rs:2111-2116 / 2175-2180 / 2234-2239).
+"""TEST INFRASTRUCTURE ONLY -- independent pure-Python restatement of the deterministic public-key encryption behind
+`FheApp::encrypt` / `reencrypt` (/root/reference/src/fhe.rs:594-657): sunscreen 0.8.1 `encrypt_deterministic` ->
+Sunscreen's SEAL 4.0 fork.  PINNED: `encrypt_deterministic()` below + oracle/formats.py reproduce all three SHA-512 known
+answers the reference holds (fhe.rs:2101-2121, 2165-2185, 2224-2244), the Linux ones with the libstdc++ distributions and the
+macOS ones with the libc++ distributions (tests/test_oracle_kat.py).  The C oracle (bfv_oracle.c: bfvo_seal_encrypt) is a
+second restatement of the libstdc++ variant and is compared with this one.
 
-sunscreen 0.8.1 / seal_fhe / SEAL are not vendored, so every piece below is a restatement of published algorithms:
-  * BLAKE2xb (BLAKE2X spec) as SEAL's Blake2xbPRNG uses it: 4096-byte buffers, blake2xb(out, 4096, counter_le64, key=seed)
-  * SEAL util::sample_poly_ternary: std::uniform_int_distribution<uint64_t>(0, 2) over a 32-bit engine -- libstdc++'s
-    algorithm is version dependent, both known variants are provided
-  * SEAL util::sample_poly_cbd (6 bytes per coefficient, 21 + 21 bits)
-  * SEAL util::encrypt_zero_asymmetric + RNSTool::divide_and_round_q_last_inplace + multiply_add_plain_with_scaling_variant
-`scripts/kat_search.py` tries the combinations against the reference's known answers.
+sunscreen / seal_fhe / SEAL are not vendored, so every piece is a restatement of a published algorithm:
+  * BLAKE2Xb (BLAKE2X paper, reference blake2xb.c) as SEAL's Blake2xbPRNG uses it: 4096-byte buffers,
+    buffer c = blake2xb(out 4096, in = c as LE u64, key = 64-byte seed)
+  * SEAL util::sample_poly_ternary: std::uniform_int_distribution<uint64_t>(0, 2) over a 32-bit engine
+    (libstdc++ >= 11: Lemire's method; libc++: independent-bits engine, 2 bits with rejection)
+  * SEAL util::sample_poly_normal (SEAL_USE_GAUSSIAN_NOISE): ClippedNormalDistribution(0, 3.2, 19.2) over
+    std::normal_distribution<double> (both libraries: Marsaglia polar; they differ in which variate is returned first)
+  * SEAL util::encrypt_zero_asymmetric at the DATA level (the fork's component-exporting encrypt disables the special
+    modulus: no divide_and_round_q_last) + multiply_add_plain_with_scaling_variant
+`scripts/kat_search2.py` is the search that found the combination (the stock-SEAL shape with modulus switching, kept below as
+`encrypt_seeded`, does not match).
 """
 from __future__ import annotations
 
@@ -94,20 +101,57 @@ def blake2xb(outlen: int, data: bytes, key: bytes) -> bytes:
     return out
 
 
+_IVN = np.array(IV, dtype=np.uint64)
+
+
+def blake2xb_fast(outlen: int, data: bytes, key: bytes) -> bytes:
+    """blake2xb() with hashlib for the root hash and one numpy pass for all expansion nodes (hashlib refuses depth = 0)."""
+    import hashlib
+
+    root = hashlib.blake2b(data, digest_size=64, key=key, fanout=1, depth=1, node_offset=outlen << 32).digest()
+    assert outlen % 64 == 0
+    nb = outlen // 64
+    p = np.stack([np.frombuffer(_param(64, 0, 0, 0, 64, i, outlen, 0, 64), dtype="<u8") for i in range(nb)])
+    h = (_IVN[None, :] ^ p).T.copy()  # [8][nb]
+    m = np.frombuffer(root.ljust(128, b"\0"), dtype="<u8")
+    v = [h[i].copy() for i in range(8)] + [np.full(nb, _IVN[i], dtype=np.uint64) for i in range(8)]
+    v[12] = v[12] ^ np.uint64(64)
+    v[14] = v[14] ^ np.uint64(MASK64)
+    rotr = lambda x, n: (x >> np.uint64(n)) | (x << np.uint64(64 - n))
+    with np.errstate(over="ignore"):
+        for r in range(12):
+            s = SIGMA[r]
+            for i, (a, b, c, d) in enumerate(((0, 4, 8, 12), (1, 5, 9, 13), (2, 6, 10, 14), (3, 7, 11, 15),
+                                              (0, 5, 10, 15), (1, 6, 11, 12), (2, 7, 8, 13), (3, 4, 9, 14))):
+                x, y = m[s[2 * i]], m[s[2 * i + 1]]
+                v[a] = v[a] + v[b] + x
+                v[d] = rotr(v[d] ^ v[a], 32)
+                v[c] = v[c] + v[d]
+                v[b] = rotr(v[b] ^ v[c], 24)
+                v[a] = v[a] + v[b] + y
+                v[d] = rotr(v[d] ^ v[a], 16)
+                v[c] = v[c] + v[d]
+                v[b] = rotr(v[b] ^ v[c], 63)
+    return np.stack([h[i] ^ v[i] ^ v[i + 8] for i in range(8)], axis=1).astype("<u8").tobytes()
+
+
 class Blake2xbPRNG:
     """SEAL Blake2xbPRNG: 4096-byte buffer refilled with blake2xb(counter as LE u64, key = 64-byte seed)."""
 
     BUF = 4096
 
-    def __init__(self, seed_words: List[int]) -> None:
-        self.seed = struct.pack("<8Q", *seed_words)
+    def __init__(self, seed_words, fast: bool = True) -> None:
+        """seed_words: 8 u64 words (the SHA-512 digest read as little-endian words) or the 64 digest bytes."""
+        self.seed = bytes(seed_words) if isinstance(seed_words, (bytes, bytearray)) else struct.pack("<8Q", *seed_words)
+        self.fast = fast
         self.counter = 0
         self.buf = b""
         self.pos = 0
         self._refill()
 
     def _refill(self) -> None:
-        self.buf = blake2xb(self.BUF, struct.pack("<Q", self.counter), self.seed)
+        data = struct.pack("<Q", self.counter)
+        self.buf = blake2xb_fast(self.BUF, data, self.seed) if self.fast else blake2xb(self.BUF, data, self.seed)
         self.counter += 1
         self.pos = 0
 
@@ -200,7 +244,8 @@ def sample_clipped_normal(prng: Blake2xbPRNG, n: int = F.N, sigma: float = 3.2, 
 
 def encrypt_seeded(pk: np.ndarray, plain: np.ndarray, seed_words: List[int], uniform3=uniform3_lemire,
                    noise=sample_cbd) -> np.ndarray:
-    """SEAL Encryptor::encrypt (BFV, asymmetric, with modulus switching) with a seeded Blake2xb PRNG.
+    """Stock SEAL Encryptor::encrypt (BFV, asymmetric, WITH modulus switching) on a seeded Blake2xb PRNG -- the shape of
+    the reference's randomised `runtime.encrypt`; NOT what `encrypt_deterministic` does (see encrypt_deterministic below).
     pk: [2][3][N] NTT form; returns the data-level ciphertext [2][2][N]."""
     mods = bfv.moduli()[:3]
     prng = Blake2xbPRNG(seed_words)
@@ -229,3 +274,67 @@ def encrypt_seeded(pk: np.ndarray, plain: np.ndarray, seed_words: List[int], uni
             t = (last % q - half % q) % q
             out[j, l] = (((c[j, l].astype(object) - t) % q) * pow(P, -1, q) % q).astype(np.uint64)
     return bfv.add_plain(out, plain)
+
+
+# ---- libc++ (macOS) variants of the two distributions
+def uniform3_libcxx(prng: Blake2xbPRNG) -> int:
+    """libc++ uniform_int_distribution<uint64_t>(0, 2): __independent_bits_engine with w = 2 bits, reject 3."""
+    while True:
+        v = prng.u32() & 3
+        if v < 3:
+            return v
+
+
+def sample_clipped_normal_libcxx(prng: Blake2xbPRNG, n: int = F.N, sigma: float = 3.2, max_dev: float = 19.2) -> np.ndarray:
+    """libc++ std::normal_distribution (polar on uniform_real(-1, 1); returns u*F first and keeps v*F) under SEAL's
+    ClippedNormalDistribution; generate_canonical is the same two-draw sum without the >= 1 clamp."""
+    out = np.empty(n, dtype=np.int64)
+    saved = None
+    canon = lambda: (float(prng.u32()) + float(prng.u32()) * 4294967296.0) / 18446744073709551616.0
+    for i in range(n):
+        while True:
+            if saved is not None:
+                up, saved = saved, None
+            else:
+                while True:
+                    u = 2.0 * canon() + -1.0
+                    v = 2.0 * canon() + -1.0
+                    s = u * u + v * v
+                    if not (s > 1.0 or s == 0.0):
+                        break
+                fp = math.sqrt(-2.0 * math.log(s) / s)
+                saved = v * fp
+                up = u * fp
+            value = up * sigma + 0.0
+            if abs(value) <= max_dev:
+                break
+        out[i] = int(value)
+    return out
+
+
+STDLIBS = {"libstdc++": (uniform3_lemire, sample_clipped_normal), "libc++": (uniform3_libcxx, sample_clipped_normal_libcxx)}
+
+
+def sample_deterministic(seed, stdlib: str = "libstdc++"):
+    """(u, e0, e1, 32-bit draws consumed) in SEAL's order: ternary u, then the two error polynomials, one PRNG."""
+    u3, noise = STDLIBS[stdlib]
+    prng = Blake2xbPRNG(seed)
+    u = sample_ternary(prng, u3)
+    e0 = noise(prng)
+    e1 = noise(prng)
+    return u, e0, e1, (prng.counter - 1) * (prng.BUF // 4) + prng.pos // 4
+
+
+def encrypt_deterministic(pk: np.ndarray, plain: np.ndarray, seed, stdlib: str = "libstdc++") -> np.ndarray:
+    """sunscreen 0.8.1 `encrypt_deterministic` (PINNED by the reference's known answers): c_j = pk_j[:2] * u + e_j at the data
+    level, no modulus switching; c_0 += scaled plaintext.  pk: [2][3][N] NTT form; returns [2][2][N]."""
+    mods = bfv.moduli()[:2]
+    u, e0, e1, _ = sample_deterministic(seed, stdlib)
+    c = np.zeros((2, 2, F.N), dtype=np.uint64)
+    for J, q in enumerate(mods):
+        un = bfv.ntt_fwd(np.where(u < 0, q - 1, u).astype(np.uint64), J)
+        for j, e in enumerate((e0, e1)):
+            prod = (un.astype(object) * pk[j, J].astype(object)) % q
+            cj = bfv.ntt_inv(np.array(prod, dtype=np.uint64), J)
+            c[j, J] = ((cj.astype(object) + np.where(e < 0, q + e, e).astype(object)) % q).astype(np.uint64)
+    return bfv.add_plain(c, plain)
