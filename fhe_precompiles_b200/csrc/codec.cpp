@@ -162,7 +162,7 @@ void write_seal_header(uint8_t *p, uint8_t compr, uint64_t size) {
 //             offset 1); all three symbol tables in RLE mode, so the sequence bitstream is the end marker alone.
 // Any zstd decoder reads it (the reference's SEAL uses ZSTD_decompressStream); words >= 2^40 fall back to libzstd.
 // The reader recognises exactly this layout and unpacks it directly; everything else goes to libzstd.
-std::atomic<int> g_zstd_writer{-1};  // -1 unset (read FHE_B200_ZSTD_WRITER), 0 libzstd level 3, 1 structured frames
+std::atomic<int> g_zstd_writer{-1};  // -1 unset (read FHE_B200_ZSTD_WRITER), 0 libzstd level 3 (default: SEAL's bytes), 1 structured frames
 constexpr size_t kPackPrefix = kCtHeaderBytes;
 constexpr size_t kBlockAContent = kPackPrefix + 16;
 constexpr size_t kBlockALits = kPackPrefix + 13;
@@ -376,7 +376,7 @@ int zstd_writer_mode() {
     int m = g_zstd_writer.load(std::memory_order_relaxed);
     if (m < 0) {
         const char *e = getenv("FHE_B200_ZSTD_WRITER");
-        m = (e && (!strcmp(e, "lib") || !strcmp(e, "0"))) ? 0 : 1;
+        m = (e && (!strcmp(e, "structured") || !strcmp(e, "1"))) ? 1 : 0;
         g_zstd_writer.store(m, std::memory_order_relaxed);
     }
     return m;
@@ -783,28 +783,20 @@ int32_t decode_private_key(Span in, uint64_t *sk_words) {
 
 // ---------------------------------------------------------------- scalar encoders (sunscreen types)
 // sunscreen's runtime compares every argument's Type (name, version, is_encrypted) with the compiled program's signature and
-// fails with an argument-mismatch error otherwise (-> code 7, fhe.rs:28).  The exact type names are pinned by no fixture of
-// the reference, so the rule lives in this one table: a data_type belongs to a kind iff the LAST PATH
-// SEGMENT of its name is exactly one of the kind's spellings -- Unsigned<1> never passes for Unsigned<4>, and a foreign
-// type never passes for anything.
-bool data_type_matches(const std::string &dt, Kind kind) {
-    const size_t c1 = dt.find(',');
-    if (c1 == std::string::npos) return false;
-    const size_t c2 = dt.rfind(',');
-    if (c2 == c1 || dt.compare(c2 + 1, std::string::npos, "true") != 0) return false;
-    size_t seg = dt.rfind("::", c1);
-    seg = (seg == std::string::npos || seg > c1) ? 0 : seg + 2;
-    const std::string last = dt.substr(seg, c1 - seg);
-    static const char *const kNames[4][2] = {
-        {"Unsigned<4>", "Unsigned256"},   // Kind::U256
-        {"Unsigned<1>", "Unsigned64"},    // Kind::U64
-        {"Signed", nullptr},              // Kind::I64
-        {"Fractional<64>", nullptr},      // Kind::Frac64
-    };
-    for (const char *n : kNames[(int)kind])
-        if (n && last == n) return true;
-    return false;
+// fails with an argument-mismatch error otherwise (-> code 7, fhe.rs:28).  `#[derive(TypeName)]` names a type
+// module_path!() + "::" + identifier WITHOUT generic arguments and stamps the sunscreen crate version, so Unsigned<1>
+// (Unsigned64) and Unsigned<4> (Unsigned256) carry the SAME name and the reference cannot tell them apart.  The Unsigned
+// spelling and the version are pinned by the reference's SHA-512 known answers (fhe.rs:2101-2244: the hashed bytes contain
+// the string); Signed and Fractional come from the same derive.
+const char *data_type_of(Kind kind) {
+    switch (kind) {
+        case Kind::I64: return "sunscreen::types::bfv::signed::Signed,0.8.1,true";
+        case Kind::U64:
+        case Kind::U256: return "sunscreen::types::bfv::unsigned::Unsigned,0.8.1,true";
+        default: return "sunscreen::types::bfv::fractional::Fractional,0.8.1,true";
+    }
 }
+bool data_type_matches(const std::string &dt, Kind kind) { return dt == data_type_of(kind); }
 
 static uint64_t be_u64(const uint8_t *p) {
     uint64_t v = 0;

@@ -87,7 +87,8 @@ enum class Kind : int { U256 = 0, U64 = 1, I64 = 2, Frac64 = 3 };
 int32_t encode_scalar(Kind kind, Span bytes, uint16_t *plain);
 // plaintext polynomial -> big-endian scalar bytes
 void decode_scalar(Kind kind, const uint16_t *plain, size_t len, std::vector<uint8_t> *out);
-// does a Ciphertext data_type string belong to `kind` (and say is_encrypted = true)?
+// the `Ciphertext.data_type` string sunscreen 0.8.1 writes for an encrypted value of `kind`, and the argument check against it
+const char *data_type_of(Kind kind);
 bool data_type_matches(const std::string &data_type, Kind kind);
 
 // zstd is loaded from libzstd.so.1 at first use (no headers in the image); throws if missing

@@ -1402,14 +1402,6 @@ Seed512 seed_from_hash(const std::vector<uint8_t> &msg) {
     memcpy(s.w, h, 64);
     return s;
 }
-const char *type_name_of(Kind k) {
-    switch (k) {
-        case Kind::I64: return "sunscreen::types::bfv::signed::Signed,0.8.1,true";
-        case Kind::U64: return "sunscreen::types::bfv::unsigned::Unsigned<1>,0.8.1,true";
-        case Kind::U256: return "sunscreen::types::bfv::unsigned::Unsigned<4>,0.8.1,true";
-        default: return "sunscreen::types::bfv::fractional::Fractional<64>,0.8.1,true";
-    }
-}
 void testnet_params(uint8_t out[kParamsBytes]) {
     uint64_t w[6] = {(uint64_t)kN, 3, kModulus[MQ0], kModulus[MQ1], kModulus[MP], kT};
     memcpy(out, w, 48);
@@ -1430,9 +1422,12 @@ int32_t Engine::encrypt_plain(Kind kind, Span scalar, Span pk_bytes, const uint6
     memcpy(lane->h_b, seed, 64);
     cuda_throw(cudaMemcpyAsync(lane->d_plain, lane->h_plain, kN * 2, cudaMemcpyHostToDevice, s), "H2D plain");
     cuda_throw(cudaMemcpyAsync(lane->d_b, lane->h_b, 64, cudaMemcpyHostToDevice, s), "H2D seed");
-    cuda_throw(launch_encrypt(d_pk, lane->d_plain, lane->d_b, lane->d_scratch, lane->d_out, 1, s), "encrypt");
+    int *d_failed = reinterpret_cast<int *>(lane->d_scratch + 6 * kN);  // right behind the [6][N] encryption scratch
+    cuda_throw(launch_encrypt(d_pk, lane->d_plain, lane->d_b, lane->d_scratch, lane->d_out, 1, s, d_failed), "encrypt");
     cuda_throw(cudaMemcpyAsync(lane->h_out, lane->d_out, kCtWords * 8, cudaMemcpyDeviceToHost, s), "D2H");
+    cuda_throw(cudaMemcpyAsync(lane->h_b + 8, d_failed, sizeof(int), cudaMemcpyDeviceToHost, s), "D2H sampler flag");
     cuda_throw(cudaStreamSynchronize(s), "stream sync");
+    if (*reinterpret_cast<const int *>(lane->h_b + 8)) return kErrFailedEncryption;  // PRNG stream window exhausted (~24 sigma)
     return encode_ciphertext(*view, lane->h_out, out);
 }
 
@@ -1448,7 +1443,7 @@ int32_t Engine::encrypt(Kind kind, Span in, Span net_pub, Span, std::vector<uint
     LaneGuard guard{this, lane, &Engine::release_lane};
     cuda_throw(cudaSetDevice(lane->device), "cudaSetDevice");
     CipherView view;
-    view.data_type = type_name_of(kind);
+    view.data_type = data_type_of(kind);
     testnet_params(view.params);
     return encrypt_plain(kind, plain, net_pub, seed_from_hash(msg).w, &view, lane, out);
 }

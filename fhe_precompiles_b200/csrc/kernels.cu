@@ -905,84 +905,278 @@ __global__ void __launch_bounds__(256) k_decrypt_round(const u64 *__restrict__ x
 }
 
 // =====================================================================================
-// K11b: public-key encryption   (SEAL Encryptor::encrypt_zero_asymmetric at the key level +
-//       RNSTool::divide_and_round_q_last_inplace + multiply_add_plain_with_scaling_variant; fhe.rs:594-618)
-// Randomness: ChaCha12 keyed by the caller's 512-bit seed per op (the reference hands SEAL the whole SHA-512 digest,
-// fhe.rs:611-616): key = seed words 0..3 xor words 4..7 (256 bits), nonce = word 4, counter = (thread, stream) with
-// stream 0 = u, 1 = e0, 2 = e1.  One 64-byte block per thread and stream; word r of thread t's block drives coefficient
-// r*512 + t.  A valid BFV encryption with SEAL's distributions (uniform ternary u; errors Gaussian, sigma = 3.2, clipped at
-// 6 sigma and truncated toward zero), deterministic in (seed, plaintext, key), restated bit for bit by oracle/bfv.py
-// (gpu_sampler_*); NOT SEAL's Blake2xb sampler stream.
-//   k_encrypt_core   : INTT_J(pk_j[J] * NTT_J(u)) + e_j    grid (3 moduli, ops) -> encbuf [op][2][3][N]
-//   k_encrypt_finish : drop P with rounding, add Delta*m   per coefficient      -> ct [op][2][2][N]
+// K11b: deterministic public-key encryption, bit-exact with the reference (fhe.rs:594-657 -> sunscreen 0.8.1
+//       `encrypt_deterministic` -> Sunscreen's SEAL 4.0 fork built with SEAL_USE_GAUSSIAN_NOISE).  Pinned by the reference's
+//       SHA-512 known answers (tests/test_gpu_parity.py::test_reference_known_answers_through_the_c_abi).
+//   k_seal_prng    : SEAL's Blake2xbPRNG stream for the op's 512-bit seed: buffer c (4096 bytes) = BLAKE2Xb(in = c as LE
+//                    u64, key = seed).  The buffers and the 64 expansion nodes of a buffer are independent, so one CTA per
+//                    op computes kSealBuffers roots and then 64 x kSealBuffers one-block BLAKE2b compressions in parallel.
+//   k_seal_sample  : SEAL's samplers on that stream, in SEAL's order with one PRNG: sample_poly_ternary
+//                    (std::uniform_int_distribution<uint64_t>(0, 2), libstdc++ >= 11 = Lemire on 32-bit draws), then
+//                    sample_poly_normal twice (ClippedNormalDistribution(0, 3.2, 19.2) over libstdc++'s Marsaglia-polar
+//                    std::normal_distribution<double>, truncated toward zero).  Draw consumption is data dependent
+//                    (rejections), so acceptance flags are computed in parallel and compacted with a block scan; the rare
+//                    cases (a zero draw in u, a clipped variate) take an exact sequential path on one thread.
+//                    IEEE double arithmetic without contraction; log() is CUDA's (<= 1 ulp from glibc's), which can move
+//                    a sample only if the scaled variate lies within ~2^-48 of an integer (~1e-11 per ciphertext).
+//   k_encrypt_seal : encrypt_zero_asymmetric at the DATA level (the fork's deterministic encrypt disables the special
+//                    modulus: the first two limbs of each public-key polynomial, no divide_and_round_q_last) +
+//                    multiply_add_plain_with_scaling_variant:  c_j = INTT(NTT(u) * pk_j) + e_j,  c_0 += scaled(m).
+//                    grid (2 limbs, ops) -> ct [op][2][2][N]
 // =====================================================================================
-__device__ __forceinline__ void chacha_qr(u32 &a, u32 &b, u32 &c, u32 &d) {
-    a += b, d ^= a, d = __funnelshift_l(d, d, 16);
-    c += d, b ^= c, b = __funnelshift_l(b, b, 12);
-    a += b, d ^= a, d = __funnelshift_l(d, d, 8);
-    c += d, b ^= c, b = __funnelshift_l(b, b, 7);
+constexpr int kSealBuffers = 28;                   // 28 x 4096 bytes = 28,672 draws; a ciphertext consumes ~25,000 (sigma ~150)
+constexpr int kSealStreamWords = kSealBuffers * 512;  // u64 words of stream per op; the samples (3 x N int8) follow it
+constexpr int kSealAttempts = 6;                   // polar attempts per thread and error polynomial (512 x 6 >= 2,608 +- 27)
+
+#define B2B_G(a, b, c, d, x, y)                \
+    a = a + b + (x), d = rotr64(d ^ a, 32);    \
+    c = c + d, b = rotr64(b ^ c, 24);          \
+    a = a + b + (y), d = rotr64(d ^ a, 16);    \
+    c = c + d, b = rotr64(b ^ c, 63);
+#define B2B_ROUND(s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12, s13, s14, s15) \
+    B2B_G(v[0], v[4], v[8], v[12], m[s0], m[s1])                                       \
+    B2B_G(v[1], v[5], v[9], v[13], m[s2], m[s3])                                       \
+    B2B_G(v[2], v[6], v[10], v[14], m[s4], m[s5])                                      \
+    B2B_G(v[3], v[7], v[11], v[15], m[s6], m[s7])                                      \
+    B2B_G(v[0], v[5], v[10], v[15], m[s8], m[s9])                                      \
+    B2B_G(v[1], v[6], v[11], v[12], m[s10], m[s11])                                    \
+    B2B_G(v[2], v[7], v[8], v[13], m[s12], m[s13])                                     \
+    B2B_G(v[3], v[4], v[9], v[14], m[s14], m[s15])
+__device__ __forceinline__ u64 rotr64(u64 x, int n) { return (x >> n) | (x << (64 - n)); }
+__device__ __forceinline__ u64 b2b_iv(int i) {
+    constexpr u64 iv[8] = {0x6A09E667F3BCC908ull, 0xBB67AE8584CAA73Bull, 0x3C6EF372FE94F82Bull, 0xA54FF53A5F1D36F1ull,
+                           0x510E527FADE682D1ull, 0x9B05688C2B3E6C1Full, 0x1F83D9ABFB41BD6Bull, 0x5BE0CD19137E2179ull};
+    return iv[i];
 }
-// the 8 u64 output words of block (counter, stream) under the op's seed
-__device__ __forceinline__ void chacha12_block(const u64 *__restrict__ seed, u32 counter, u32 stream, u64 (&out)[8]) {
-    u32 in[16], x[16];
-    in[0] = 0x61707865u, in[1] = 0x3320646eu, in[2] = 0x79622d32u, in[3] = 0x6b206574u;
+// BLAKE2b compression F (RFC 7693 3.2) with t < 2^64: h <- F(h, m, t, last)
+__device__ __noinline__ void b2b_compress(u64 *__restrict__ h, const u64 *__restrict__ m_in, u64 t, bool last) {
+    u64 v[16], m[16];
 #pragma unroll
-    for (int i = 0; i < 4; i++) unpack64(seed[i] ^ seed[i + 4], in[4 + 2 * i], in[5 + 2 * i]);
-    in[12] = counter, in[13] = stream;
-    unpack64(seed[4], in[14], in[15]);
+    for (int i = 0; i < 16; i++) m[i] = m_in[i];
 #pragma unroll
-    for (int i = 0; i < 16; i++) x[i] = in[i];
+    for (int i = 0; i < 8; i++) v[i] = h[i], v[i + 8] = b2b_iv(i);
+    v[12] ^= t;
+    if (last) v[14] = ~v[14];
+    B2B_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B2B_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
+    B2B_ROUND(11, 8, 12, 0, 5, 2, 15, 13, 10, 14, 3, 6, 7, 1, 9, 4)
+    B2B_ROUND(7, 9, 3, 1, 13, 12, 11, 14, 2, 6, 5, 10, 4, 0, 15, 8)
+    B2B_ROUND(9, 0, 5, 7, 2, 4, 10, 15, 14, 1, 11, 12, 6, 8, 3, 13)
+    B2B_ROUND(2, 12, 6, 10, 0, 11, 8, 3, 4, 13, 7, 5, 15, 14, 1, 9)
+    B2B_ROUND(12, 5, 1, 15, 14, 13, 4, 10, 0, 7, 6, 3, 9, 2, 8, 11)
+    B2B_ROUND(13, 11, 7, 14, 12, 1, 3, 9, 5, 0, 15, 4, 8, 6, 2, 10)
+    B2B_ROUND(6, 15, 14, 9, 11, 3, 0, 8, 12, 2, 13, 7, 1, 4, 10, 5)
+    B2B_ROUND(10, 2, 8, 4, 7, 6, 1, 5, 15, 11, 9, 14, 3, 12, 13, 0)
+    B2B_ROUND(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15)
+    B2B_ROUND(14, 10, 4, 8, 9, 15, 13, 6, 1, 12, 0, 2, 11, 7, 5, 3)
 #pragma unroll
-    for (int r = 0; r < 6; r++) {
-        chacha_qr(x[0], x[4], x[8], x[12]);
-        chacha_qr(x[1], x[5], x[9], x[13]);
-        chacha_qr(x[2], x[6], x[10], x[14]);
-        chacha_qr(x[3], x[7], x[11], x[15]);
-        chacha_qr(x[0], x[5], x[10], x[15]);
-        chacha_qr(x[1], x[6], x[11], x[12]);
-        chacha_qr(x[2], x[7], x[8], x[13]);
-        chacha_qr(x[3], x[4], x[9], x[14]);
+    for (int i = 0; i < 8; i++) h[i] ^= v[i] ^ v[i + 8];
+}
+// h = IV xor parameter block (words 0..2 carry everything BLAKE2X sets; salt / personalisation are zero)
+__device__ __forceinline__ void b2b_init(u64 *h, u64 digest, u64 keylen, u64 fanout, u64 depth, u64 leaf, u64 node_offset, u64 xof,
+                                         u64 inner) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = b2b_iv(i);
+    h[0] ^= digest | (keylen << 8) | (fanout << 16) | (depth << 24) | (leaf << 32);
+    h[1] ^= node_offset | (xof << 32);
+    h[2] ^= inner << 8;
+}
+__global__ void __launch_bounds__(512) k_seal_prng(const u64 *__restrict__ seeds, u64 *__restrict__ scratch, size_t op_stride) {
+    __shared__ u64 roots[kSealBuffers][8];
+    const size_t op = blockIdx.x;
+    const u64 *seed = seeds + op * 8;
+    u64 *stream = scratch + op * op_stride;
+    const int t = threadIdx.x;
+    if (t < kSealBuffers) {
+        u64 h[8], m[16];
+        b2b_init(h, 64, 64, 1, 1, 0, 0, 4096, 0);
+#pragma unroll
+        for (int i = 0; i < 16; i++) m[i] = i < 8 ? seed[i] : 0;  // the key, zero padded to one block
+        b2b_compress(h, m, 128, false);
+#pragma unroll
+        for (int i = 0; i < 16; i++) m[i] = 0;
+        m[0] = (u64)t;  // the buffer counter, 8 bytes of input
+        b2b_compress(h, m, 136, true);
+#pragma unroll
+        for (int i = 0; i < 8; i++) roots[t][i] = h[i];
     }
+    __syncthreads();
+    for (int idx = t; idx < kSealBuffers * 64; idx += 512) {
+        const int b = idx >> 6, node = idx & 63;
+        u64 h[8], m[16];
+        b2b_init(h, 64, 0, 0, 0, 64, (u64)node, 4096, 64);
 #pragma unroll
-    for (int i = 0; i < 8; i++) out[i] = pack64(x[2 * i] + in[2 * i], x[2 * i + 1] + in[2 * i + 1]);
-}
-// ternary sample in {-1,0,1}, uniform: the first 2-bit group of the word that is not 3 (all 32 groups 3: 0)
-__device__ __forceinline__ int sample_ternary(u64 r) {
-    for (int k = 0; k < 32; k++) {
-        int d = (int)((r >> (2 * k)) & 3);
-        if (d != 3) return d - 1;
+        for (int i = 0; i < 16; i++) m[i] = i < 8 ? roots[b][i] : 0;
+        b2b_compress(h, m, 64, true);
+        uint4 *dst = reinterpret_cast<uint4 *>(stream + (size_t)b * 512 + node * 8);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            u32 a0, a1, a2, a3;
+            unpack64(h[2 * i], a0, a1);
+            unpack64(h[2 * i + 1], a2, a3);
+            dst[i] = make_uint4(a0, a1, a2, a3);
+        }
     }
-    return 0;
 }
-// Error sample with the distribution the reference's SEAL build uses (identified from its key fixtures, DESIGN.md
-// section 7): Gaussian, sigma = 3.2, clipped at 6 sigma, truncated toward zero (P(0) = 0.245, variance 8.0).  Inverse-CDF
-// lookup on 63 uniform bits: kNoiseCdf[k] = floor(2^63 P(|x| < k+1)); bit 0 is the sign.  Integer only, so the CPU oracle
-// reproduces it exactly.
-__device__ const u64 kNoiseCdf[20] = {
-    0x1f67485e1414e200ull, 0x3be85f5582810200ull, 0x53644e2dedd21400ull, 0x64f422f09cf1bc00ull, 0x70dfcc250f890800ull,
-    0x7837f1b047d3fc00ull, 0x7c535c45b5071400ull, 0x7e690b1eb1011400ull, 0x7f5eeb470d610c00ull, 0x7fc5bca5a5143c00ull,
-    0x7fecc2f990af3800ull, 0x7ffa349ee365e800ull, 0x7ffe68c004b14800ull, 0x7fff9a26cfa95400ull, 0x7fffe8d1193b7400ull,
-    0x7ffffb3514071000ull, 0x7fffff1c06e24c00ull, 0x7fffffdc665b1800ull, 0x7ffffffe05c3f800ull, 0x8000000000000000ull};
-__device__ __forceinline__ int sample_noise(u64 r) {
-    const u64 v = r >> 1;
-    int mag = 0;
+
+// libstdc++ generate_canonical<double, 53> over a 32-bit engine: two draws, low word first
+__device__ __forceinline__ double seal_canonical(u32 lo, u32 hi) {
+    const double sum = __dadd_rn(__uint2double_rn(lo), __dmul_rn(__uint2double_rn(hi), 4294967296.0));
+    const double r = __dmul_rn(sum, 5.42101086242752217e-20);  // / 2^64, exact
+    return r >= 1.0 ? 0.99999999999999989 : r;                   // nextafter(1, 0)
+}
+// one Marsaglia-polar attempt on draws w[0..3]; returns acceptance
+__device__ __forceinline__ bool seal_polar(const u32 *__restrict__ w, double &x, double &y, double &r2) {
+    x = __dadd_rn(__dmul_rn(2.0, seal_canonical(w[0], w[1])), -1.0);
+    y = __dadd_rn(__dmul_rn(2.0, seal_canonical(w[2], w[3])), -1.0);
+    r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    return !(r2 > 1.0 || r2 == 0.0);
+}
+// the two variates of an accepted attempt, scaled by sigma, in the order std::normal_distribution returns them
+__device__ __forceinline__ void seal_pair(double x, double y, double r2, double &first, double &second) {
+    const double mult = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+    first = __dmul_rn(__dmul_rn(y, mult), 3.2);
+    second = __dmul_rn(__dmul_rn(x, mult), 3.2);
+}
+// exact sequential sample_poly_normal from draw index `base` (one thread): returns draws consumed, 0 if the stream ran out
+__device__ __noinline__ u32 seal_normal_sequential(const u32 *__restrict__ w, u32 base, u32 limit, signed char *__restrict__ out) {
+    u32 pos = base;
+    bool have = false;
+    double saved = 0.0;
+    for (int i = 0; i < kN; i++) {
+        double value;
+        for (;;) {
+            if (have) {
+                have = false, value = saved;
+            } else {
+                double x, y, r2;
+                for (;;) {
+                    if (pos + 4 > limit) return 0;
+                    const bool ok = seal_polar(w + pos, x, y, r2);
+                    pos += 4;
+                    if (ok) break;
+                }
+                seal_pair(x, y, r2, value, saved);
+                have = true;
+            }
+            if (fabs(value) <= 19.2) break;
+        }
+        out[i] = (signed char)__double2int_rz(value);
+    }
+    return pos - base;
+}
+// exclusive prefix sum of `v` over the 512 threads of the block; *total = sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int *warp_sums, int *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
 #pragma unroll
-    for (int k = 0; k < 19; k++) mag += v >= kNoiseCdf[k] ? 1 : 0;
-    return (r & 1) ? -mag : mag;
+    for (int d = 1; d < 32; d <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += n;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int s = lane < 16 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= d) s += n;
+        }
+        if (lane < 16) warp_sums[16 + lane] = s;  // inclusive sums of the warps
+    }
+    __syncthreads();
+    *total = warp_sums[31];
+    const int before = wid ? warp_sums[16 + wid - 1] : 0;
+    __syncthreads();
+    return before + inc - v;
+}
+__global__ void __launch_bounds__(512) k_seal_sample(u64 *__restrict__ scratch, size_t op_stride, int *__restrict__ failed) {
+    __shared__ int warp_sums[32];
+    __shared__ u32 sh_consumed;
+    __shared__ int sh_slow;
+    const size_t op = blockIdx.x;
+    const u32 *w = reinterpret_cast<const u32 *>(scratch + op * op_stride);
+    signed char *smp = reinterpret_cast<signed char *>(scratch + op * op_stride + kSealStreamWords);
+    const u32 limit = (u32)kSealStreamWords * 2;
+    const int t = threadIdx.x;
+    // ---- u: draw i gives floor(3 w / 2^32) unless w == 0 (Lemire: low word 0 < threshold 1 -> redraw)
+    int zeros = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const u32 x = w[r * 512 + t];
+        zeros += x == 0;
+        smp[r * 512 + t] = (signed char)((int)__umulhi(x, 3u) - 1);
+    }
+    zeros = __syncthreads_count(zeros);
+    u32 base = kN;
+    if (zeros) {  // ~1e-6 of the seeds: the exact walk on one thread
+        if (t == 0) {
+            u32 pos = 0;
+            for (int i = 0; i < kN; i++) {
+                u32 x;
+                do x = w[pos++];
+                while (x == 0);
+                smp[i] = (signed char)((int)__umulhi(x, 3u) - 1);
+            }
+            sh_consumed = pos;
+        }
+        __syncthreads();
+        base = sh_consumed;
+        __syncthreads();
+    }
+    // ---- e0, e1
+    bool ok = true;
+    for (int j = 0; j < 2; j++) {
+        signed char *e = smp + (1 + j) * kN;
+        if (t == 0) sh_slow = 0, sh_consumed = 0;
+        int acc = 0;
+#pragma unroll
+        for (int r = 0; r < kSealAttempts; r++) {
+            const u32 idx = base + 4u * (u32)(t * kSealAttempts + r);
+            double x, y, r2;
+            if (idx + 4 <= limit) acc += seal_polar(w + idx, x, y, r2) ? 1 : 0;
+        }
+        int total;
+        int p = block_exclusive_scan(acc, warp_sums, &total);  // syncs; sh_slow / sh_consumed are initialised past here
+#pragma unroll
+        for (int r = 0; r < kSealAttempts; r++) {
+            const u32 k = (u32)(t * kSealAttempts + r);
+            const u32 idx = base + 4u * k;
+            double x, y, r2;
+            if (idx + 4 <= limit && seal_polar(w + idx, x, y, r2)) {
+                if (p < kN / 2) {
+                    double a, b;
+                    seal_pair(x, y, r2, a, b);
+                    if (fabs(a) > 19.2 || fabs(b) > 19.2) sh_slow = 1;  // a clipped variate shifts everything behind it
+                    e[2 * p] = (signed char)__double2int_rz(a);
+                    e[2 * p + 1] = (signed char)__double2int_rz(b);
+                    if (p == kN / 2 - 1) sh_consumed = 4u * (k + 1);
+                }
+                p++;
+            }
+        }
+        __syncthreads();
+        if (sh_slow || total < kN / 2) {  // exact sequential path (also when the window of attempts was too short)
+            if (t == 0) sh_consumed = seal_normal_sequential(w, base, limit, e);
+            __syncthreads();
+        }
+        const u32 used = sh_consumed;
+        __syncthreads();
+        if (!used) ok = false;
+        base += used;
+    }
+    if (t == 0 && failed) failed[op] = ok ? 0 : 1;
 }
 template <int MI>
-__device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, const u64 *__restrict__ seed, u64 *__restrict__ enc,
-                                                  u64 *smem, int t) {
+__device__ __forceinline__ void encrypt_seal_body(const u64 *__restrict__ pk, const signed char *__restrict__ smp,
+                                                  const unsigned short *__restrict__ plain, u64 *__restrict__ ct, u64 *smem, int t) {
     using M = Mod<MI>;
     u64 v[1][8];
-    {
-        u64 rnd[8];
-        chacha12_block(seed, (u32)t, 0, rnd);
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            int u = sample_ternary(rnd[r]);
-            v[0][r] = u < 0 ? M::q - 1 : (u64)u;
-        }
+    for (int r = 0; r < 8; r++) {
+        const int u = smp[r * kThreads + t];
+        v[0][r] = u < 0 ? M::q - 1 : (u64)u;
     }
     ntt_forward<M, 1, true>(v, smem, kt.twf[MI], t);
     u64 w[2][8];
@@ -996,57 +1190,29 @@ __device__ __forceinline__ void encrypt_core_body(const u64 *__restrict__ pk, co
     ntt_inverse<M, 2>(w, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
 #pragma unroll
     for (int j = 0; j < 2; j++) {
-        u64 rnd[8];
-        chacha12_block(seed, (u32)t, 1 + j, rnd);
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            int e = sample_noise(rnd[r]);
-            u64 ev = e < 0 ? M::q - (u64)(-e) : (u64)e;
-            w[j][r] = addmod<M>(w[j][r], ev);
+            const int e = smp[(1 + j) * kN + r * kThreads + t];
+            const u64 ev = e < 0 ? M::q - (u64)(-e) : (u64)e;
+            u64 x = addmod<M>(w[j][r], ev);
+            if (j == 0) x = addmod<M>(x, plain_scaled<M>(plain[r * kThreads + t], MI));
+            w[j][r] = x;
         }
-        store_natural(enc + (size_t)(j * 3 + MI) * kN, w[j], t);
+        store_natural(ct + (size_t)(j * 2 + MI) * kN, w[j], t);
     }
 }
-__global__ void __launch_bounds__(kThreads, 1) k_encrypt_core(const u64 *__restrict__ pk, const u64 *__restrict__ seeds,
-                                                               u64 *__restrict__ encbuf) {
+__global__ void __launch_bounds__(kThreads, 1) k_encrypt_seal(const u64 *__restrict__ pk, const u64 *__restrict__ scratch,
+                                                               size_t op_stride, const unsigned short *__restrict__ plain,
+                                                               u64 *__restrict__ ct) {
     extern __shared__ __align__(16) u64 smem[];
     const size_t op = blockIdx.y;
-    const u64 *seed = seeds + op * 8;  // 512 bits per op
-    u64 *enc = encbuf + op * 6 * kN;
-    switch (blockIdx.x) {
-        case 0: encrypt_core_body<MQ0>(pk, seed, enc, smem, threadIdx.x); break;
-        case 1: encrypt_core_body<MQ1>(pk, seed, enc, smem, threadIdx.x); break;
-        default: encrypt_core_body<MP>(pk, seed, enc, smem, threadIdx.x); break;
-    }
-}
-__global__ void __launch_bounds__(256) k_encrypt_finish(const u64 *__restrict__ encbuf, const unsigned short *__restrict__ plain,
-                                                        u64 *__restrict__ ct, size_t n_ops) {
-    using Q0 = Mod<MQ0>;
-    using Q1 = Mod<MQ1>;
-    using PP = Mod<MP>;
-    size_t total = n_ops * 2 * kN;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
-        size_t op = g / (2 * kN);
-        int j = (int)((g / kN) & 1);
-        int i = (int)(g % kN);
-        const u64 *pe = encbuf + (op * 2 + j) * 3 * kN + i;
-        u64 *po = ct + (op * 2 + j) * 2 * kN + i;
-        u64 last = csub<PP>(pe[2 * kN] + kc.half_P, PP::q);
-        u64 m = (j == 0) ? plain[op * kN + i] : 0;
-        {
-            u64 tl = submod<Q0>(canon_k32<Q0>(last), kc.half_P_mod_q[0]);
-            u64 v = shoup<Q0>(submod<Q0>(pe[0], tl), kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws);
-            if (j == 0) v = addmod<Q0>(v, plain_scaled<Q0>(m, 0));
-            po[0] = v;
-        }
-        {
-            u64 tl = submod<Q1>(canon_k32<Q1>(last), kc.half_P_mod_q[1]);
-            u64 v = shoup<Q1>(submod<Q1>(pe[kN], tl), kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws);
-            if (j == 0) v = addmod<Q1>(v, plain_scaled<Q1>(m, 1));
-            po[kN] = v;
-        }
-    }
+    const signed char *smp = reinterpret_cast<const signed char *>(scratch + op * op_stride + kSealStreamWords);
+    const unsigned short *pl = plain + op * kN;
+    u64 *out = ct + op * 4 * kN;
+    if (blockIdx.x == 0)
+        encrypt_seal_body<MQ0>(pk, smp, pl, out, smem, threadIdx.x);
+    else
+        encrypt_seal_body<MQ1>(pk, smp, pl, out, smem, threadIdx.x);
 }
 
 // =====================================================================================
@@ -1200,7 +1366,7 @@ cudaError_t kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_behz_tensor, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem4);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_encrypt_core, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    e = cudaFuncSetAttribute(k_encrypt_seal, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_relin_ks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
@@ -1356,11 +1522,14 @@ cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned sho
     return cudaGetLastError();
 }
 cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64 *seeds, u64 *encbuf, u64 *ct, size_t n_ops,
-                           cudaStream_t s) {
+                           cudaStream_t s, int *failed) {
     if (n_ops == 0) return cudaSuccess;
-    k_encrypt_core<<<dim3(3, (unsigned)n_ops), kThreads, kSmem2, s>>>(pk, seeds, encbuf);
-    k_encrypt_finish<<<eltwise_grid(n_ops * 2 * kN, 256), 256, 0, s>>>(encbuf, plain, ct, n_ops);
-    g_launches.fetch_add(2, std::memory_order_relaxed);
+    static_assert(kSealStreamWords + 3 * kN / 8 <= 6 * kN, "per-op encryption scratch is [6][N] words");
+    const size_t stride = 6 * kN;
+    k_seal_prng<<<(unsigned)n_ops, 512, 0, s>>>(seeds, encbuf, stride);
+    k_seal_sample<<<(unsigned)n_ops, 512, 0, s>>>(encbuf, stride, failed);
+    k_encrypt_seal<<<dim3(2, (unsigned)n_ops), kThreads, kSmem2, s>>>(pk, encbuf, stride, plain, ct);
+    g_launches.fetch_add(3, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {

@@ -34,9 +34,11 @@ cudaError_t launch_ks_intt(const u64 *dig, const u64 *rk, u64 *ks, size_t n_ops,
 // exhausted (optional, [n_ops] ints on the device): set to 1 where the invariant noise budget is 0
 cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s,
                            int *exhausted = nullptr);
-// pk-encrypt n plaintexts under pk [2][3][N] (NTT form) with per-op seeds; encbuf scratch [n][2][3][N]
+// deterministic pk-encryption of n plaintexts under pk [2][3][N] (NTT form), bit-exact with the reference's
+// encrypt_deterministic for the per-op 512-bit seeds; encbuf: scratch [n][6][N] words (PRNG stream + samples);
+// failed[op] (optional) = 1 if the op's PRNG stream window ran out (never observed: ~24 sigma)
 cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64 *seeds, u64 *encbuf, u64 *ct, size_t n_ops,
-                           cudaStream_t s);
+                           cudaStream_t s, int *failed = nullptr);
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s);
 cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
 bool ks_finish_fused();  // default: key-switch MAC + inverse transforms + rounded division by P in one kernel (FHE_B200_KS_FINISH=0: two)

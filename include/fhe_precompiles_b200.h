@@ -136,12 +136,13 @@ int32_t fhe_b200_multiply(int32_t device, const uint64_t *a, const uint64_t *b, 
 int32_t fhe_b200_relinearize(int32_t device, const uint64_t *c3, const uint64_t *rk, uint64_t *out, size_t n, void *stream);
 int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,
                            size_t n, void *stream);
-/* Public-key encryption of n plaintexts (uint16 [n][4096]) under pk [2][3][4096] (NTT form, key level) with one 512-bit seed
- * per op (seeds [n][8] words; the byte surface passes the eight little-endian words of its SHA-512 digest, fhe.rs:611-616).
- * A valid BFV encryption with SEAL's distributions, deterministic in (seed, plaintext, key).  The samples u, e0, e1 are
- * expanded from the seed with ChaCha12 under a 256-bit key (seed words 0..3 xor 4..7; nonce = word 4), so the encryption
- * randomness carries 256 bits of key entropy -- above the parameter set's 128-bit target; the sampler stream is this
- * library's own, not SEAL's Blake2xb one (an encrypt_* result differs from the reference's in bytes, not in validity).
+/* Deterministic public-key encryption of n plaintexts (uint16 [n][4096]) under pk [2][3][4096] (NTT form, as in the key
+ * file) with one 512-bit seed per op (seeds [n][8] words; the byte surface passes the eight little-endian words of its
+ * SHA-512 digest, fhe.rs:611-616).  BIT-EXACT with the reference: this is sunscreen 0.8.1 `encrypt_deterministic` as the
+ * Sunscreen SEAL fork computes it -- Blake2xb PRNG keyed with the seed, std::uniform_int_distribution ternary u and
+ * clipped std::normal_distribution errors (libstdc++, the Linux build), encryption at the data level without the special
+ * modulus -- reproduced on the GPU (k_seal_prng / k_seal_sample / k_encrypt_seal) and pinned by the reference's own SHA-512
+ * known answers (fhe.rs:2101-2244) through c_fhe_encrypt_u256 / c_fhe_reencrypt_u256 in the GPU tests.
  * Decryption of n size-2 ciphertexts with sk [>=2 limbs][4096] (NTT form) -> plaintexts. */
 int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
                          void *stream);
@@ -221,10 +222,12 @@ int32_t fhe_b200_parse_private_key(const uint8_t *bytes, size_t len, uint64_t *s
 int32_t fhe_b200_parse_ciphertext(const uint8_t *bytes, size_t len, uint64_t *words, char *data_type, size_t data_type_cap);
 int32_t fhe_b200_write_ciphertext(const uint64_t *words, const char *data_type, uint8_t **output, int64_t *output_length);
 /* parms_id (4 words) of the key level (which = 0) or the data level (which = 1) */
-/* How zstd-mode ciphertext payloads are WRITTEN: 1 (default) = structure-aware standard zstd frames (raw 5-byte literals +
- * repeat-offset matches for the three zero bytes of every 36-bit residue; ~82 KB, memcpy speed), 0 = libzstd level 3 as
- * SEAL's default does (~88.5 KB, ~1 ms).  Both are RFC 8878 frames any SEAL build reads.  mode < 0 only queries.
- * Returns the previous mode.  Also settable with FHE_B200_ZSTD_WRITER=lib. */
+/* How zstd-mode ciphertext payloads are WRITTEN: 0 (default) = libzstd level 3, byte for byte what SEAL's save() writes
+ * (~88.5 KB, ~1 ms on a host core; pinned by the reference's known answers, which hash the compressed bytes);
+ * 1 = structure-aware standard zstd frames laid out directly (raw 5-byte literals + repeat-offset matches for the three zero
+ * bytes of every 36-bit residue; ~82 KB, memcpy speed, written on the GPU in batches) for deployments where every consumer
+ * only needs a valid frame, not SEAL's exact bytes.  Both are RFC 8878 frames any SEAL build reads.  mode < 0 only queries.
+ * Returns the previous mode.  Also settable with FHE_B200_ZSTD_WRITER=structured. */
 /* The SHA-512 behind the encrypt / reencrypt seed (fhe.rs:600-612): portable != 0 forces the built-in implementation,
  * 0 uses libcrypto's when the machine has it.  Exposed so that tests can pin both against a known-good SHA-512. */
 void fhe_b200_sha512(const uint8_t *bytes, size_t len, int32_t portable, uint8_t out[64]);

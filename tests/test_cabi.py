@@ -157,17 +157,20 @@ def test_host_pool_exception_safety(tmp_path):
 
 
 def test_data_type_rule_is_exact_per_kind(lib):
-    """A ciphertext's data_type belongs to exactly one kind (sunscreen's runtime rejects an argument whose Type differs from the
-    program's signature -> code 7, fhe.rs:28): u64 never passes for u256 and a foreign type passes for nothing."""
+    """A ciphertext argument passes iff its data_type equals the string sunscreen 0.8.1 writes for the precompile's type
+    (its runtime rejects any other Type -> code 7, fhe.rs:28).  derive(TypeName) drops generic arguments, so Unsigned64 and
+    Unsigned256 share one name (pinned by the reference's known answers, tests/test_oracle_kat.py): the first kind that
+    carries the name is reported."""
     f = lib.fhe_b200_data_type_kind
     f.argtypes, f.restype = [ctypes.c_char_p], ctypes.c_int32
     from oracle import formats as F
 
-    kinds = {"u256": 0, "u64": 1, "i64": 2, "frac64": 3}
+    kinds = {"u256": 0, "u64": 0, "i64": 2, "frac64": 3}
     for k, idx in kinds.items():
         assert f((F.TYPE_NAMES[k] + ",0.8.1,true").encode()) == idx
         assert f((F.TYPE_NAMES[k] + ",0.8.1,false").encode()) == -1  # a plaintext type is not a ciphertext operand
-    for bad in ("sunscreen::types::bfv::unsigned::Unsigned<2>,0.8.1,true", "sunscreen::types::bfv::unsigned::Unsigned,0.8.1,true",
+        assert f((F.TYPE_NAMES[k] + ",0.8.0,true").encode()) == -1  # Type equality includes the crate version
+    for bad in ("sunscreen::types::bfv::unsigned::Unsigned<2>,0.8.1,true", "sunscreen::types::bfv::unsigned::Unsigned<4>,0.8.1,true",
                 "my::Signedish,0.8.1,true", "NotSigned,0.8.1,true", "sunscreen::types::bfv::rational::Rational,0.8.1,true",
-                "Signed", "", "sunscreen::types::bfv::fractional::Fractional<32>,0.8.1,true"):
+                "Signed", "Signed,0.8.1,true", "", "sunscreen::types::bfv::fractional::Fractional<64>,0.8.1,true"):
         assert f(bad.encode()) == -1, bad

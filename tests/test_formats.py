@@ -120,11 +120,19 @@ def _frame_of(ct_bytes: bytes) -> bytes:
     return blob[16:]
 
 
-def test_structured_zstd_frames(lib, keys):
-    """The default writer lays ciphertext payloads out as RFC 8878 frames by hand (codec.cpp zstd_pack40). The bytes must
+@pytest.fixture
+def structured_writer(lib):
+    """switch the library to its structured-frame writer for one test (the default is libzstd level 3 = SEAL's bytes)"""
+    prev = lib.fhe_b200_set_zstd_writer(1)
+    assert prev == 0, "libzstd level 3 (SEAL's bytes) is the default writer"
+    yield
+    lib.fhe_b200_set_zstd_writer(prev)
+
+
+def test_structured_zstd_frames(lib, keys, structured_writer):
+    """The structured writer lays ciphertext payloads out as RFC 8878 frames by hand (codec.cpp zstd_pack40). The bytes must
     equal the format oracle's independent restatement, decode to the same payload with libzstd (one-shot and streaming,
     which is what SEAL uses) and with the oracle's RFC-only mini decoder, and both of the library's readers must agree."""
-    assert lib.fhe_b200_set_zstd_writer(-1) == 1, "structured frames are the default writer"
     rng = np.random.default_rng(77)
     dt = F.data_type_string("i64").encode()
     words = np.zeros(4 * N, dtype=np.uint64)
