@@ -259,25 +259,36 @@ def e2e_byte_surface(fdev, a, b, net_pub: bytes, steps: int, world: int, barrier
             assert failed == 0 and first == FHE.mul_cipheri64_cipheri64(packed[0])
         return out_bytes
 
-    out_bytes = one_batch(check=True)  # warm (lanes grow to their tile size) + result check against the single-call symbol
-    one_batch()
-    barrier()
-    reps = max(2, min(steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        one_batch()
-    dt = time.perf_counter() - t0
-    barrier()
-    dt_max = max_over_ranks(dt, dist)
+    def timed(mode: int) -> tuple:
+        prev_ = L.fhe_b200_set_zstd_writer(mode)
+        try:
+            out_bytes_ = one_batch(check=True)  # warm (lanes grow to their tile size) + result check against the single-call symbol
+            one_batch()
+            barrier()
+            reps = max(2, min(steps, 5))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                one_batch()
+            dt = time.perf_counter() - t0
+            barrier()
+            return world * n_calls * reps / max_over_ranks(dt, dist), out_bytes_
+        finally:
+            L.fhe_b200_set_zstd_writer(prev_)
+
+    rate_seal, out_seal = timed(0)
+    rate_struct, out_struct = timed(1)
     return {
-        "value": world * n_calls * reps / dt_max,
+        "value": rate_seal,
         "unit": "calls/s",
         "calls_per_step": n_calls,
         "distinct_inputs": distinct,
         "host_threads": threads,
         "input_bytes_per_step": in_bytes,
-        "output_bytes_per_step": out_bytes,
-        "api": "fhe_b200_batch over pack.rs-framed inputs (c_fhe_mul_cipheri64_cipheri64 semantics per call); operand frames libzstd level 3",
+        "output_bytes_per_step": out_seal,
+        "api": "fhe_b200_batch over pack.rs-framed inputs (c_fhe_mul_cipheri64_cipheri64 semantics per call); operand frames libzstd "
+               "level 3; results written with libzstd level 3 on the host pool = byte for byte what SEAL's save() writes (default)",
+        "structured_writer": {"value": rate_struct, "unit": "calls/s", "output_bytes_per_step": out_struct,
+                              "note": "fhe_b200_set_zstd_writer(1): result frames laid out directly, written on the GPU"},
         "device_zstd": os.environ.get("FHE_B200_DEVICE_ZSTD", "default"),
     }
 
@@ -345,65 +356,27 @@ def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 100
         L.fhe_free(out)
         return buf
 
-    # operands as the reference's SEAL writes them (libzstd level-3 frames); the call's own output uses the library's
-    # default writer (structure-aware standard zstd frames, codec.cpp).  `chained` repeats the measurement with operands
-    # that are outputs of this library.
+    # operands as the reference's SEAL writes them (libzstd level-3 frames).  Measured under both result writers: "seal"
+    # (default: libzstd level 3 on the host, byte-identical to SEAL's save()) and "structured" (frames laid out directly,
+    # written on the GPU); `chained` = operands that are themselves structured frames.
     prev = L.fhe_b200_set_zstd_writer(0)
     ca, cb = to_bytes(a[0]), to_bytes(b[0])
+    L.fhe_b200_set_zstd_writer(1)
+    packed_chained = pack.pack_binary_operation(net_pub, to_bytes(a[0]), to_bytes(b[0]))
     L.fhe_b200_set_zstd_writer(prev)
     packed = pack.pack_binary_operation(net_pub, ca, cb)
-    packed_chained = pack.pack_binary_operation(net_pub, to_bytes(a[0]), to_bytes(b[0]))
-    for _ in range(5):
-        out = FHE.mul_cipheri64_cipheri64(packed)
-    ts = []
-    for _ in range(calls):
-        t0 = time.perf_counter()
-        out = FHE.mul_cipheri64_cipheri64(packed)
-        ts.append(time.perf_counter() - t0)
-    ts.sort()
-    # phase split of the same call: host clock around the codec phases, CUDA events on the lane's stream
-    L.fhe_b200_set_call_timing(1)
-    phases = ("unpack_key", "parse_inflate", "h2d", "kernels", "d2h", "deflate", "total")
-    rows = []
-    us = (ctypes.c_double * 7)()
-    for _ in range(calls):
-        FHE.mul_cipheri64_cipheri64(packed)
-        L.fhe_b200_last_call_breakdown(us)
-        rows.append(list(us))
-    L.fhe_b200_set_call_timing(0)
-    split = {f"{k}_us": sorted(r[i] for r in rows)[len(rows) // 2] for i, k in enumerate(phases)}
-    tc = []
-    for _ in range(calls):
-        t0 = time.perf_counter()
-        FHE.mul_cipheri64_cipheri64(packed_chained)
-        tc.append(time.perf_counter() - t0)
-    tc.sort()
-    # codec alone: inflate both operands + deflate one result, same thread
-    words = np.zeros(4 * N, dtype=np.uint64)
-    name = ctypes.create_string_buffer(128)
-    cs = []
-    for _ in range(50):
-        t0 = time.perf_counter()
-        L.fhe_b200_parse_ciphertext(ca, len(ca), words.ctypes.data, name, 128)
-        L.fhe_b200_parse_ciphertext(cb, len(cb), words.ctypes.data, name, 128)
-        o, n = ctypes.c_void_p(), ctypes.c_int64()
-        L.fhe_b200_write_ciphertext(words.ctypes.data, dt, ctypes.byref(o), ctypes.byref(n))
-        L.fhe_free(o)
-        cs.append(time.perf_counter() - t0)
-    cs.sort()
-    # throughput of the same call through fhe_b200_batch (tiles of calls per lane, codec on all host threads); only the C
-    # call is timed -- building the call array and copying the outputs into Python objects is the harness, not the library
     nb = 2048
-    buf = (ctypes.c_char * len(packed)).from_buffer_copy(packed)
-    buf_chained = (ctypes.c_char * len(packed_chained)).from_buffer_copy(packed_chained)
     op_index = L.fhe_b200_op_index(b"mul_cipheri64_cipheri64")
 
-    def batch_rate(src, nbytes):
+    def batch_rate(src_bytes):
+        # throughput of the same call through fhe_b200_batch (tiles of calls per lane, codec on all host threads); only the C
+        # call is timed -- building the call array and copying the outputs into Python objects is the harness, not the library
+        src = (ctypes.c_char * len(src_bytes)).from_buffer_copy(src_bytes)
         arr = (_lib.BatchCall * nb)()
-        best = 0.0
+        best, first = 0.0, None
         for rep in range(4):  # first repetition warms the lanes (each grows its staging to a tile)
             for i in range(nb):
-                arr[i].op, arr[i].bytes, arr[i].bytes_length = op_index, ctypes.cast(src, ctypes.c_void_p), nbytes
+                arr[i].op, arr[i].bytes, arr[i].bytes_length = op_index, ctypes.cast(src, ctypes.c_void_p), len(src_bytes)
             t0 = time.perf_counter()
             failed = L.fhe_b200_batch(arr, nb, 0)
             dt_ = time.perf_counter() - t0
@@ -415,23 +388,71 @@ def call_latency(fdev, a, b, device_index: int, net_pub: bytes, calls: int = 100
                 best = max(best, nb / dt_)
         return best, first
 
-    rate, first = batch_rate(buf, len(packed))
-    rate_chained, _ = batch_rate(buf_chained, len(packed_chained))
-    assert first == out
+    def p50_p99(data, n):
+        for _ in range(5):
+            out_ = FHE.mul_cipheri64_cipheri64(data)
+        ts = []
+        for _ in range(n):
+            t0 = time.perf_counter()
+            out_ = FHE.mul_cipheri64_cipheri64(data)
+            ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return ts[len(ts) // 2] * 1e3, ts[min(len(ts) - 1, int(len(ts) * 0.99))] * 1e3, out_
+
+    def under(mode: int) -> dict:
+        prev_ = L.fhe_b200_set_zstd_writer(mode)
+        try:
+            p50, p99, out = p50_p99(packed, calls)
+            # phase split of the same call: host clock around the codec phases, CUDA events on the lane's stream
+            L.fhe_b200_set_call_timing(1)
+            phases = ("unpack_key", "parse_inflate", "h2d", "kernels", "d2h", "deflate", "total")
+            rows = []
+            us = (ctypes.c_double * 7)()
+            for _ in range(calls):
+                FHE.mul_cipheri64_cipheri64(packed)
+                L.fhe_b200_last_call_breakdown(us)
+                rows.append(list(us))
+            L.fhe_b200_set_call_timing(0)
+            split = {f"{k}_us": sorted(r[i] for r in rows)[len(rows) // 2] for i, k in enumerate(phases)}
+            # codec alone: inflate both operands + deflate one result, same thread
+            words = np.zeros(4 * N, dtype=np.uint64)
+            name = ctypes.create_string_buffer(128)
+            cs = []
+            for _ in range(50):
+                t0 = time.perf_counter()
+                L.fhe_b200_parse_ciphertext(ca, len(ca), words.ctypes.data, name, 128)
+                L.fhe_b200_parse_ciphertext(cb, len(cb), words.ctypes.data, name, 128)
+                o, n = ctypes.c_void_p(), ctypes.c_int64()
+                L.fhe_b200_write_ciphertext(words.ctypes.data, dt, ctypes.byref(o), ctypes.byref(n))
+                L.fhe_free(o)
+                cs.append(time.perf_counter() - t0)
+            cs.sort()
+            rate, first = batch_rate(packed)
+            assert first == out
+            res = {"p50_ms": p50, "p99_ms": p99, "p50_split": split, "codec_only_p50_ms": cs[len(cs) // 2] * 1e3,
+                   "output_bytes": len(out), "batch_calls_per_s": rate}
+            if mode == 1:
+                res["chained_p50_ms"] = p50_p99(packed_chained, calls)[0]
+                res["chained_batch_calls_per_s"] = batch_rate(packed_chained)[0]
+            return res
+        finally:
+            L.fhe_b200_set_zstd_writer(prev_)
+
+    seal, structured = under(0), under(1)
     return {
-        "byte_surface_batch": {"calls": nb, "calls_per_s": rate, "chained_calls_per_s": rate_chained,
-                               "host_threads": os.cpu_count(),
-                               "api": "fhe_b200_batch (packed bytes; tiles of 16 calls per lane, codec on host threads)"},
-        "api": "c_fhe_mul_cipheri64_cipheri64 (packed bytes in/out, warm key cache)",
+        "api": "c_fhe_mul_cipheri64_cipheri64 (packed bytes in/out, warm key cache); operand frames libzstd level 3 (as SEAL writes them)",
         "calls": calls,
-        "p50_ms": ts[len(ts) // 2] * 1e3,
-        "p99_ms": ts[min(len(ts) - 1, int(len(ts) * 0.99))] * 1e3,
-        "chained_p50_ms": tc[len(tc) // 2] * 1e3,
-        "p50_split": split,
-        "operand_frames": "libzstd level 3 (as SEAL writes them); chained_* = this library's structured frames",
-        "codec_only_p50_ms": cs[len(cs) // 2] * 1e3,
+        "p50_ms": seal["p50_ms"],
+        "p99_ms": seal["p99_ms"],
+        "p50_split": seal["p50_split"],
+        "codec_only_p50_ms": seal["codec_only_p50_ms"],
         "input_bytes": len(packed),
-        "output_bytes": len(out),
+        "output_bytes": seal["output_bytes"],
+        "result_writer": "libzstd level 3 on the host (default): result bytes identical to SEAL's save()",
+        "byte_surface_batch": {"calls": nb, "calls_per_s": seal["batch_calls_per_s"], "host_threads": os.cpu_count(),
+                               "api": "fhe_b200_batch (packed bytes; tiles of 16 calls per lane, codec on host threads)"},
+        "structured_writer": dict(structured, note="fhe_b200_set_zstd_writer(1): result frames laid out directly (82,202 bytes), written "
+                                                   "on the GPU; chained_* = operands that are such frames too"),
     }
 
 

@@ -81,6 +81,10 @@ def lib() -> ctypes.CDLL:
     L.fhe_b200_mul_relin.argtypes = [i32, vp, vp, vp, vp, sz, vp]
     L.fhe_b200_encrypt.argtypes = [i32, vp, vp, vp, vp, sz, vp]
     L.fhe_b200_encrypt.restype = i32
+    L.fhe_b200_seal_sample.argtypes = [i32, vp, vp, sz, vp]
+    L.fhe_b200_seal_sample.restype = i32
+    L.fhe_b200_seal_op_words.argtypes = []
+    L.fhe_b200_seal_op_words.restype = sz
     L.fhe_b200_decrypt.argtypes = [i32, vp, vp, vp, sz, vp]
     L.fhe_b200_decrypt.restype = i32
     L.fhe_b200_decrypt_checked.argtypes = [i32, vp, vp, vp, vp, sz, vp]

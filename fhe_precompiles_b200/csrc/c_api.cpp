@@ -306,6 +306,10 @@ int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *pla
                          void *stream) {
     DEV_GUARD(Engine::get().encrypt_device(device, pk, plain, seeds, ct, n, (cudaStream_t)stream));
 }
+int32_t fhe_b200_seal_sample(int32_t device, uint64_t *streams, int32_t *failed, size_t n, void *stream) {
+    DEV_GUARD(device_context(device); cuda_throw(launch_seal_sample(streams, nullptr, failed, n, (cudaStream_t)stream), "seal_sample"));
+}
+size_t fhe_b200_seal_op_words(void) { return kSealOpWords; }
 int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, void *stream) {
     DEV_GUARD(Engine::get().decrypt_device(device, ct, sk, plain, n, (cudaStream_t)stream));
 }

@@ -1532,6 +1532,14 @@ cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64
     g_launches.fetch_add(3, std::memory_order_relaxed);
     return cudaGetLastError();
 }
+cudaError_t launch_seal_sample(u64 *streams, signed char *samples, int *failed, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    const size_t stride = (size_t)kSealStreamWords + 3 * kN / 8;
+    k_seal_sample<<<(unsigned)n_ops, 512, 0, s>>>(streams, stride, failed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    (void)samples;  // the samples are written behind each op's stream words (see kernels.h)
+    return cudaGetLastError();
+}
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
     k_floor_sk<<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);

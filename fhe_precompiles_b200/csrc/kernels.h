@@ -39,6 +39,11 @@ cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned sho
 // failed[op] (optional) = 1 if the op's PRNG stream window ran out (never observed: ~24 sigma)
 cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64 *seeds, u64 *encbuf, u64 *ct, size_t n_ops,
                            cudaStream_t s, int *failed = nullptr);
+// SEAL's samplers (ternary u, clipped-normal e0 / e1) on caller-supplied streams of 32-bit draws: op i owns
+// kSealOpWords = 28 * 512 + 3 * N / 8 words at streams + i * kSealOpWords -- 28,672 draws followed by room for the three
+// int8 sample polynomials, which the kernel writes there.  failed[i] = 1 if the draws ran out.
+constexpr size_t kSealOpWords = 28 * 512 + 3 * 4096 / 8;
+cudaError_t launch_seal_sample(u64 *streams, signed char *samples, int *failed, size_t n_ops, cudaStream_t s);
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s);
 cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
 bool ks_finish_fused();  // default: key-switch MAC + inverse transforms + rounded division by P in one kernel (FHE_B200_KS_FINISH=0: two)

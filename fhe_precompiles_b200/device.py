@@ -237,6 +237,21 @@ def encrypt(pk: torch.Tensor, plain: torch.Tensor, seeds: torch.Tensor) -> torch
     return ct
 
 
+def seal_sample(draws: torch.Tensor):
+    """draws [n, 28672] int32 on a CUDA device (32-bit draws in stream order) -> (u, e0, e1 as int8 [n, 4096] each, failed
+    int32 [n]): SEAL's sample_poly_ternary + 2 x sample_poly_normal on those draws (the sampling stage of encrypt())."""
+    dev = _dev(draws)
+    n = draws.shape[0]
+    words = int(_lib.lib().fhe_b200_seal_op_words())
+    assert draws.dtype == torch.int32 and draws.shape[1] == 28 * 1024
+    buf = torch.zeros((n, words), dtype=torch.int64, device=draws.device)
+    buf[:, : 28 * 512] = draws.contiguous().view(torch.int64)
+    failed = torch.zeros(n, dtype=torch.int32, device=draws.device)
+    _check(_lib.lib().fhe_b200_seal_sample(dev, buf.data_ptr(), failed.data_ptr(), n, _stream(dev)))
+    smp = buf[:, 28 * 512 :].contiguous().view(torch.int8).reshape(n, 3, N)
+    return smp[:, 0], smp[:, 1], smp[:, 2], failed
+
+
 def decrypt(ct: torch.Tensor, sk: torch.Tensor) -> torch.Tensor:
     """ct [n,2,2,4096], sk [>=2,4096] int64 (NTT form) -> plaintext coefficients [n,4096] int16."""
     dev = _dev(ct)

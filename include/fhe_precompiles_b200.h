@@ -147,6 +147,13 @@ int32_t fhe_b200_mul_relin(int32_t device, const uint64_t *a, const uint64_t *b,
 int32_t fhe_b200_encrypt(int32_t device, const uint64_t *pk, const uint16_t *plain, const uint64_t *seeds, uint64_t *ct, size_t n,
                          void *stream);
 int32_t fhe_b200_decrypt(int32_t device, const uint64_t *ct, const uint64_t *sk, uint16_t *plain, size_t n, void *stream);
+/* The sampling stage of fhe_b200_encrypt on its own, on caller-supplied draws instead of the Blake2xb stream: op i owns
+ * fhe_b200_seal_op_words() device words at streams + i * that -- 28,672 32-bit draws (little-endian word pairs) followed by
+ * room for the three int8[4096] polynomials u, e0, e1, which are written there in SEAL's order (sample_poly_ternary, then
+ * sample_poly_normal twice; libstdc++ distributions).  failed[i] = 1 when the draws ran out.  Lets tests drive the rare
+ * paths (a zero draw inside u, a clipped variate) that no searchable seed reaches. */
+int32_t fhe_b200_seal_sample(int32_t device, uint64_t *streams, int32_t *failed, size_t n, void *stream);
+size_t fhe_b200_seal_op_words(void);
 /* The same with SEAL's invariant-noise-budget test: exhausted[i] (device ints) = 1 where ciphertext i has no budget left
  * (max |t x mod q| centred >= 2^70), i.e. where sunscreen's Runtime::decrypt fails and c_fhe_decrypt_* / c_fhe_reencrypt_*
  * return 5 (FailedDecryption, fhe.rs:640-643, 692-696); plain[i] is then meaningless. */

@@ -52,6 +52,8 @@ def lib() -> ctypes.CDLL:
         L.bfvo_seal_prng.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         L.bfvo_seal_sample.restype = ctypes.c_size_t
         L.bfvo_seal_sample.argtypes = [ctypes.c_void_p] * 4
+        L.bfvo_seal_sample_stream.restype = ctypes.c_size_t
+        L.bfvo_seal_sample_stream.argtypes = [ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 3
         L.bfvo_encrypt_samples_data_level.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t] + [ctypes.c_void_p] * 4
         L.bfvo_seal_encrypt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         L.bfvo_batch_mul_relin.restype = ctypes.c_double
@@ -290,6 +292,15 @@ def seal_sample(seed8) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
     smp = [np.empty(N, dtype=np.int8) for _ in range(3)]
     vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
     drawn = lib().bfvo_seal_sample(_p(_seed8(seed8)), vp(smp[0]), vp(smp[1]), vp(smp[2]))
+    return smp[0], smp[1], smp[2], int(drawn)
+
+
+def seal_sample_stream(words: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray, int]:
+    """the same samplers on a caller-supplied stream of 32-bit draws (rare-path tests); drawn = 0: the stream ran out"""
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    smp = [np.empty(N, dtype=np.int8) for _ in range(3)]
+    vp = lambda x: x.ctypes.data_as(ctypes.c_void_p)
+    drawn = lib().bfvo_seal_sample_stream(vp(w), w.size, vp(smp[0]), vp(smp[1]), vp(smp[2]))
     return smp[0], smp[1], smp[2], int(drawn)
 
 

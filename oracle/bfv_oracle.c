@@ -877,14 +877,24 @@ typedef struct {
     u64 buf[SEAL_PRNG_BUF / 8];
     size_t pos; /* in 32-bit words */
     size_t drawn;
+    const uint32_t *ext; /* test hook: draw from a caller-supplied stream instead (bfvo_seal_sample_stream) */
+    size_t ext_n;
+    int exhausted;
 } SealPrng;
 static void sprng_init(SealPrng *p, const u64 seed[8]) {
     memcpy(p->seed, seed, 64);
-    p->counter = 0, p->drawn = 0;
+    p->counter = 0, p->drawn = 0, p->ext = NULL, p->ext_n = 0, p->exhausted = 0;
     seal_prng_buffer(p->seed, p->counter++, p->buf);
     p->pos = 0;
 }
 static inline uint32_t sprng_u32(SealPrng *p) {
+    if (p->ext) {
+        if (p->drawn >= p->ext_n) {
+            p->exhausted = 1;
+            return 0x9E3779B9u; /* any accepted value: lets the samplers terminate */
+        }
+        return p->ext[p->drawn++];
+    }
     uint32_t v = (uint32_t)(p->buf[p->pos >> 1] >> (32 * (p->pos & 1)));
     p->pos++, p->drawn++;
     if (p->pos == SEAL_PRNG_BUF / 4) {
@@ -946,6 +956,18 @@ size_t bfvo_seal_sample(const uint64_t seed[8], int8_t *u, int8_t *e0, int8_t *e
     sample_normal_poly(p, e0);
     sample_normal_poly(p, e1);
     size_t drawn = p->drawn;
+    free(p);
+    return drawn;
+}
+/* the same samplers on a caller-supplied stream of 32-bit draws (to test the rare paths: a zero draw in u, a clipped
+ * variate); returns the draws consumed, 0 if the stream ran out */
+size_t bfvo_seal_sample_stream(const uint32_t *words, size_t nwords, int8_t *u, int8_t *e0, int8_t *e1) {
+    SealPrng *p = (SealPrng *)calloc(1, sizeof(SealPrng));
+    p->ext = words, p->ext_n = nwords;
+    for (size_t i = 0; i < N; i++) u[i] = (int8_t)uniform3(p) - 1;
+    sample_normal_poly(p, e0);
+    sample_normal_poly(p, e1);
+    size_t drawn = p->exhausted ? 0 : p->drawn;
     free(p);
     return drawn;
 }

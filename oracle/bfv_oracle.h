@@ -98,6 +98,7 @@ void bfvo_encrypt_samples(const uint64_t *pk, const uint64_t *plain, size_t plai
  * 32-bit draws consumed.  bfvo_seal_encrypt: pk [2][3][N] NTT form -> ct [2][2][N] (no special modulus). */
 void bfvo_seal_prng(const uint64_t seed[8], uint8_t *out, size_t nbytes);
 size_t bfvo_seal_sample(const uint64_t seed[8], int8_t *u, int8_t *e0, int8_t *e1);
+size_t bfvo_seal_sample_stream(const uint32_t *words, size_t nwords, int8_t *u, int8_t *e0, int8_t *e1);
 void bfvo_encrypt_samples_data_level(const uint64_t *pk, const uint64_t *plain, size_t plain_len, const int8_t *u, const int8_t *e0,
                                      const int8_t *e1, uint64_t *ct_out);
 void bfvo_seal_encrypt(const uint64_t *pk, const uint64_t *plain, size_t plain_len, const uint64_t seed[8], uint64_t *ct_out);

@@ -956,6 +956,41 @@ def test_device_sampler_rare_paths(dev, keys):
         assert np.array_equal(ct[i], bfv.encrypt_seeded(keys.net_pk, plains[i, :1].astype(np.uint64), seeds[i])), f"seed {i}"
 
 
+def test_device_sampler_exact_paths_on_crafted_draws(dev):
+    """k_seal_sample against the oracle's samplers on the SAME draws, including what no searchable seed reaches: a zero draw
+    inside u (Lemire's redraw shifts every later draw by one), a clipped variate in e0 and in e1 (|3.2 z| > 19.2: it is
+    dropped and everything behind it moves up), both together, a clipped variate as the very last sample, and draws that
+    run out (failed = 1)."""
+    import hashlib
+
+    import torch
+
+    ndraw = 28 * 1024
+    base = [np.frombuffer(bfv.seal_prng(hashlib.sha512(b"crafted %d" % i).digest(), 4 * ndraw), dtype="<u4").copy() for i in range(8)]
+    # an attempt whose first variate is clipped: x = 0 exactly (canonical = 1/2), y = 1e-4 -> r2 = 1e-8, sqrt(-2 ln r2) = 6.07
+    y_hi = 0x80000000 + int(1e-4 * 2**31)
+    clip = np.array([0, 0x80000000, 0, y_hi], dtype=np.uint32)
+    cases = [base[0].copy()]
+    z = base[1].copy(); z[100] = 0; z[4000] = 0; cases.append(z)                       # two redraws in u
+    c = base[2].copy(); c[4096 + 4 * 50: 4096 + 4 * 50 + 4] = clip; cases.append(c)     # clipped variate early in e0
+    c = base[3].copy(); c[4096 + 4 * 4000: 4096 + 4 * 4000 + 4] = clip; cases.append(c)  # ... in e1's range
+    c = base[4].copy(); c[7] = 0; c[4097 + 4 * 10: 4097 + 4 * 10 + 4] = clip; cases.append(c)  # both (attempts start at 4097)
+    c = base[5].copy(); c[4096: 4096 + 4000] = np.tile(clip, 1000); cases.append(c)    # e0's first 1,000 attempts all clip once
+    c = base[6].copy(); c[4096:] = 0xFFFFFFFF; cases.append(c)                          # every attempt rejected: draws run out
+    cases.append(base[7].copy())
+    draws = torch.from_numpy(np.stack(cases).view(np.int32)).cuda()
+    u, e0, e1, failed = (t.cpu().numpy() for t in dev.seal_sample(draws))
+    for i, w in enumerate(cases):
+        wu, we0, we1, drawn = bfv.seal_sample_stream(w)
+        assert bool(failed[i]) == (drawn == 0), f"case {i}: failed flag"
+        if drawn:
+            assert np.array_equal(u[i], wu) and np.array_equal(e0[i], we0) and np.array_equal(e1[i], we1), f"case {i}"
+    assert list(failed) == [0, 0, 0, 0, 0, 0, 1, 0]
+    # the crafted cases really took the rare paths
+    assert not np.array_equal(bfv.seal_sample_stream(base[1])[0], u[1]) and not np.array_equal(bfv.seal_sample_stream(base[2])[1], e0[2])
+    assert (e0[5][:1000] == 0).all() and e0[5][1000:].any()  # only the second variate (x * mult = 0) of those attempts survives
+
+
 def test_exhausted_noise_budget_is_failed_decryption(dev, keys):
     """sunscreen's Runtime::decrypt refuses a ciphertext whose invariant noise budget is 0 (-> FailedDecryption = 5,
     fhe.rs:640-643, 692-696).  Three multiplications deep there is none left at these parameters (53 -> 30 -> 7 -> 0 bits);
