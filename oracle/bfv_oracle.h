@@ -13,9 +13,14 @@
  *   PARAMS                   /root/reference/src/testnet.rs:8-14
  *   encrypt / decrypt        /root/reference/src/fhe.rs:594-618, 688-699
  *
- * Pinning status: "parity unpinned" at the ciphertext-byte level for add/sub/mul
- * (the reference holds no golden ciphertext for those -- SURVEY.md 8c).  The oracle
- * IS pinned against every fixture the reference has for this path:
+ * Pinning status: PINNED to the reference's byte-level known answers -- the three
+ * SHA-512 digests the reference asserts on the output of FheApp::encrypt / reencrypt
+ * (fhe.rs:2101-2121, 2165-2185, 2224-2244) are reproduced by bfvo_seal_encrypt +
+ * bfvo_decrypt + oracle/formats.py (tests/test_oracle_kat.py).  That fixes PRNG,
+ * samplers, primes, roots, NTT order, key layout, encoders, scaling, decryption,
+ * the serialisation and its libzstd level-3 compression against real SEAL output.
+ * For add/sub/mul the reference holds no golden ciphertext; those
+ * routines share all of the conventions above and are pinned in addition by:
  *   - the four key files: sk is ternary under this NTT convention, pk0+pk1*s and
  *     rk[j].c0+rk[j].c1*s-P*s^2[limb j] are small -> fixes primes, roots, NTT order,
  *     key layout and the key-switch digit convention (tests/test_oracle_fixtures.py);
@@ -86,7 +91,8 @@ uint64_t bfvo_decode_u64(const uint64_t *plain, size_t len);
 void bfvo_decode_u256(const uint64_t *plain, size_t len, uint64_t limbs_le[4]);
 double bfvo_decode_f64(const uint64_t *plain, size_t len);
 
-/* Public-key encryption (valid BFV encryption, own PRNG -- NOT SEAL's sampler stream).
+/* Public-key encryption in stock SEAL's shape (key level + modulus switching) with a throw-away PRNG: makes the
+ * operands of the add/sub/mul tests, as the reference's randomised runtime.encrypt does.
  * pk: [2][3][N] NTT form at key level. ct_out: [2][2][N]. */
 void bfvo_encrypt(const uint64_t *pk, const uint64_t *plain, size_t plain_len, uint64_t seed, uint64_t *ct_out);
 /* the same computation with caller-supplied samples (u ternary, e0 / e1 errors, N int8 each) */
