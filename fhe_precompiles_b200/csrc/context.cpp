@@ -342,6 +342,18 @@ void build(HostContext &H) {
         c.Bq[l] = mk_shoup(bq, qs[l]);
         c.nBq[l] = mk_shoup(qs[l] - bq, qs[l]);
     }
+    // exact recovery of the tensor's q-limbs from its Bsk limbs (devconsts.h)
+    for (int i = 0; i < 3; i++) {
+        const u64 p = bsk[i];
+        const u64 o1 = bsk[(i + 1) % 3], o2 = bsk[(i + 2) % 3];  // Bsk / p_i = o1 * o2
+        c.crt3[i] = mk_shoup(h_invmod(h_mulmod(o1 % p, o2 % p, p), p), p);
+        for (int l = 0; l < 2; l++)
+            c.crtK[i][l] = mk_shoup(h_mulmod(h_mulmod(o1 % qs[l], o2 % qs[l], qs[l]), inv_punct_q[l], qs[l]), qs[l]);
+    }
+    for (int l = 0; l < 2; l++) {
+        const u64 b3 = h_mulmod(h_mulmod(b0 % qs[l], b1 % qs[l], qs[l]), msk % qs[l], qs[l]);
+        c.crtNB[l] = mk_shoup(h_mulmod((qs[l] - b3) % qs[l], inv_punct_q[l], qs[l]), qs[l]);
+    }
     // key switching
     c.half_P = P >> 1;
     for (int l = 0; l < 2; l++) {

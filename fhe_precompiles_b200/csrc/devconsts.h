@@ -40,6 +40,14 @@ struct DevConsts {
     Shoup nib;
     Shoup pBq[2][2];       // (B/b_j) mod q_l   [j][l]
     Shoup Bq[2], nBq[2];   // prod(B) mod q_l and its negation
+    // ---- the q-limbs of the tensor product recovered from its Bsk limbs (k_floor_sk): the product of
+    // the extended operands is an INTEGER polynomial with |t D| < 2^166 < Bsk/2 (Bsk = b0 b1 m_sk ~ 2^183), so its residues
+    // mod q_l -- which SEAL obtains from 14 more transforms on the q-limbs -- follow exactly from the three Bsk residues:
+    //   y_i = [r_i (Bsk/p_i)^-1]_{p_i},  v = round(sum y_i / p_i),  t D = sum y_i (Bsk/p_i) - v Bsk
+    //   t_l = [t D (q/q_l)^-1]_{q_l} = [sum y_i crtK[i][l] + v crtNB[l]]_{q_l}        (inv_punct_q merged in)
+    Shoup crt3[3];         // (Bsk/p_i)^-1 mod p_i
+    Shoup crtK[3][2];      // (Bsk/p_i) (q/q_l)^-1 mod q_l
+    Shoup crtNB[2];        // -Bsk (q/q_l)^-1 mod q_l
 
     // ---- key switching (switch_key_inplace, BFV branch)
     Shoup inv_P_mod_q[2];

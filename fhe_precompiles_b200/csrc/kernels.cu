@@ -393,12 +393,14 @@ __device__ __forceinline__ void ntt_only_body(const u64 *__restrict__ src, u64 *
     ntt_forward<M, 1, !M::kSmall, false>(v, smem, kt.twf[MI], t);
     store_chunk8(dst, v[0], t);
 }
+// aux_only (default): grid (12, ops), the Bsk limbs only -- the q-limbs of the tensor product are recovered from its Bsk
+// limbs in k_floor_sk (exactly), so the q-limbs of the operands are never transformed.  Otherwise grid (20, ops).
 __global__ void __launch_bounds__(kThreads, 3) k_ext_ntt2(const u64 *__restrict__ a, const u64 *__restrict__ b,
-                                                           u64 *__restrict__ nttbuf) {
+                                                           u64 *__restrict__ nttbuf, int aux_only) {
     extern __shared__ __align__(16) u64 smem[];
     const size_t op = blockIdx.y;
-    const int p = blockIdx.x / 5, e = blockIdx.x % 5;
-    u64 *dst = nttbuf + (op * 20 + blockIdx.x) * kN;
+    const int p = aux_only ? blockIdx.x / 3 : blockIdx.x / 5, e = aux_only ? 2 + blockIdx.x % 3 : blockIdx.x % 5;
+    u64 *dst = nttbuf + (op * 20 + (size_t)(p * 5 + e)) * kN;
     // q limbs come from the operand, auxiliary limbs are transformed in place (every load precedes the first CTA barrier)
     const u64 *src = e < 2 ? (p < 2 ? a : b) + op * 4 * kN + (size_t)((p & 1) * 2 + e) * kN : dst;
     const int t = threadIdx.x;
@@ -454,12 +456,12 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
     ntt_inverse<M, 1, false, false>(v, smem, kt.twi[MI], t, kc.ninv_t[MI], kc.ninv_t_w[MI]);
     store_natural(dst, v[0], t);
 }
-__global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
+__global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens, int aux_only) {
     extern __shared__ __align__(16) u64 smem[];
     const size_t op = blockIdx.y;
-    const int d = blockIdx.x / 5, e = blockIdx.x % 5;
+    const int d = aux_only ? blockIdx.x / 3 : blockIdx.x / 5, e = aux_only ? 2 + blockIdx.x % 3 : blockIdx.x % 5;
     const u64 *nb = nttbuf + op * 20 * kN;
-    u64 *dst = tens + (op * 15 + blockIdx.x) * kN;
+    u64 *dst = tens + (op * 15 + (size_t)(d * 5 + e)) * kN;
     const int t = threadIdx.x;
     switch (e) {
         case 0: tensor_intt_body<0>(nb, d, dst, smem, t); break;
@@ -474,6 +476,32 @@ __global__ void __launch_bounds__(kThreads, 2) k_tensor_intt(const u64 *__restri
 // K8: fast_floor + fastbconv_sk   (SEAL RNSTool::fast_floor, RNSTool::fastbconv_sk), per coefficient
 //   tens [op][3][5][N] (x t, any representative in [0, 2q))  ->  c3 [op][3][2][N]
 // =====================================================================================
+// t_l = [t D (q/q_l)^-1]_{q_l} from the three Bsk residues of t D alone (devconsts.h: crt3, crtK, crtNB): the q-limbs of the
+// tensor product are never computed.  t D is an integer with |t D| < 2^166 and Bsk ~ 2^183, so sum y_i / p_i lies within
+// 2^-17 of the integer v and 16 bits per term are plenty; any representative of y_i works (v moves with it).
+__device__ __forceinline__ void floor_front_crt(u64 vb0, u64 vb1, u64 vsk, u64 &t0, u64 &t1) {
+    const u64 y0 = shoup_acc<Mod<MB0>, 1>(0, vb0, kc.crt3[0].w, kc.crt3[0].ws);  // [0, 4 p): < 2^63
+    const u64 y1 = shoup_acc<Mod<MB1>, 1>(0, vb1, kc.crt3[1].w, kc.crt3[1].ws);
+    const u64 y2 = shoup_acc<Mod<MSK>, 1>(0, vsk, kc.crt3[2].w, kc.crt3[2].ws);
+    const u64 v = ((y0 >> 45) + (y1 >> 45) + (y2 >> 45) + (1u << 15)) >> 16;  // <= 12
+    {
+        ShoupSum<Mod<MQ0>> s;  // four terms < 3.5 q each
+        s.add_a1(y0, kc.crtK[0][0].w, kc.crtK[0][0].ws);
+        s.add_a1(y1, kc.crtK[1][0].w, kc.crtK[1][0].ws);
+        s.add_a1(y2, kc.crtK[2][0].w, kc.crtK[2][0].ws);
+        s.add_a1(v, kc.crtNB[0].w, kc.crtNB[0].ws);
+        t0 = canon_k32<Mod<MQ0>>(s.value());
+    }
+    {
+        ShoupSum<Mod<MQ1>> s;
+        s.add_a1(y0, kc.crtK[0][1].w, kc.crtK[0][1].ws);
+        s.add_a1(y1, kc.crtK[1][1].w, kc.crtK[1][1].ws);
+        s.add_a1(y2, kc.crtK[2][1].w, kc.crtK[2][1].ws);
+        s.add_a1(v, kc.crtNB[1].w, kc.crtNB[1].ws);
+        t1 = canon_k32<Mod<MQ1>>(s.value());
+    }
+}
+template <bool CRT>
 __device__ __forceinline__ void floor_sk_coeff(u64 v0, u64 v1, u64 vb0, u64 vb1, u64 vsk, u64 &o0, u64 &o1) {
     using Q0 = Mod<MQ0>;
     using Q1 = Mod<MQ1>;
@@ -482,8 +510,13 @@ __device__ __forceinline__ void floor_sk_coeff(u64 v0, u64 v1, u64 vb0, u64 vb1,
     using SK = Mod<MSK>;
     {
         // fast_floor: q-part -> Bsk, f_k = (v_k - conv_k) * q^-1 mod p_k  (constants merged)
-        u64 t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
-        u64 t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
+        u64 t0, t1;
+        if (CRT) {
+            floor_front_crt(vb0, vb1, vsk, t0, t1);
+        } else {
+            t0 = shoup<Q0>(v0, kc.inv_punct_q[0].w, kc.inv_punct_q[0].ws);
+            t1 = shoup<Q1>(v1, kc.inv_punct_q[1].w, kc.inv_punct_q[1].ws);
+        }
         // The q-part of the value is the integer y0 = t0 q1 + t1 q0 (< 2^73); its residue mod a Bsk prime 2^61 - c is a fold.
         u64 ylo, yhi;
         punctured_sum(t0, t1, ylo, yhi);
@@ -530,6 +563,7 @@ __device__ __forceinline__ void floor_sk_coeff(u64 v0, u64 v1, u64 vb0, u64 vb1,
         }
     }
 }
+template <bool CRT>
 __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
     const size_t total = n_ops * 3 * (kN / 2);  // (op, poly, coefficient pair): 16-byte loads and stores
     const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -537,10 +571,12 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
         const size_t opp = g / (kN / 2);  // op*3 + poly
         const int i = 2 * (int)(g % (kN / 2));
         const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(tens + opp * 5 * kN + i);
-        const ulonglong2 v0 = in[0], v1 = in[kN / 2], vb0 = in[2 * (kN / 2)], vb1 = in[3 * (kN / 2)], vsk = in[4 * (kN / 2)];
+        ulonglong2 v0 = make_ulonglong2(0, 0), v1 = v0;
+        if (!CRT) v0 = in[0], v1 = in[kN / 2];  // CRT: the q-limb slots of `tens` are never written
+        const ulonglong2 vb0 = in[2 * (kN / 2)], vb1 = in[3 * (kN / 2)], vsk = in[4 * (kN / 2)];
         u64 ax, ay, bx, by;  // limb q0 / q1 of the two coefficients
-        floor_sk_coeff(v0.x, v1.x, vb0.x, vb1.x, vsk.x, ax, bx);
-        floor_sk_coeff(v0.y, v1.y, vb0.y, vb1.y, vsk.y, ay, by);
+        floor_sk_coeff<CRT>(v0.x, v1.x, vb0.x, vb1.x, vsk.x, ax, bx);
+        floor_sk_coeff<CRT>(v0.y, v1.y, vb0.y, vb1.y, vsk.y, ay, by);
         ulonglong2 *out = reinterpret_cast<ulonglong2 *>(c3 + opp * 2 * kN + i);
         out[0] = make_ulonglong2(ax, ay);
         out[kN / 2] = make_ulonglong2(bx, by);
@@ -1450,6 +1486,17 @@ static int ext_split_mode() {
     return mode;
 }
 bool ext_split() { return ext_split_mode() != 0; }
+// Default: the q-limbs of the tensor product are recovered exactly from its Bsk limbs in k_floor_sk, so the 8 forward and 6
+// inverse q-limb transforms of SEAL's bfv_multiply are never run (33 limb transforms per multiply + relinearise instead of 47).
+// FHE_B200_QLIMB_NTT=1 runs them as SEAL does (A/B; same bits).
+static int qlimb_ntt_mode() {
+    static const int mode = [] {
+        const char *v = getenv("FHE_B200_QLIMB_NTT");
+        return (v && *v == '1') ? 1 : 0;
+    }();
+    return mode;
+}
+bool qlimb_ntt() { return qlimb_ntt_mode() != 0; }
 cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
     k_ext_conv<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
@@ -1459,14 +1506,16 @@ cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_op
 // with ext_split(): the transforms only (launch_ext_conv must have filled the auxiliary limbs); otherwise extension + transforms
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    if (ext_split_mode()) k_ext_ntt2<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
+    if (ext_split_mode() && !qlimb_ntt_mode()) k_ext_ntt2<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 1);
+    else if (ext_split_mode()) k_ext_ntt2<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 0);
     else k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
+    if (qlimb_ntt_mode()) k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 0);
+    else k_tensor_intt<<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 1);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
@@ -1542,7 +1591,8 @@ cudaError_t launch_seal_sample(u64 *streams, signed char *samples, int *failed, 
 }
 cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    k_floor_sk<<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
+    if (qlimb_ntt_mode()) k_floor_sk<false><<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
+    else k_floor_sk<true><<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
