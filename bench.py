@@ -26,8 +26,11 @@ N = 4096
 Q = (0xFFFFEE001, 0xFFFFC4001)
 CT_BYTES = 2 * 2 * N * 8  # 131,072
 ALGO_BYTES_PER_OP = 3 * CT_BYTES  # read a, read b, write result = 393,216 B
-# 47 limb-NTTs x 24,576 butterflies per op
-BUTTERFLIES_PER_OP = 47 * 24576
+# SEAL's form runs 47 limb-NTTs x 24,576 butterflies per op; the default here runs 33 (the 14 q-limb transforms of
+# the BEHZ tensor product are replaced by an exact recovery of its q-limbs from its Bsk limbs)
+QLIMB_NTT = os.environ.get("FHE_B200_QLIMB_NTT") == "1"
+NTTS_PER_OP = 47 if QLIMB_NTT else 33
+BUTTERFLIES_PER_OP = NTTS_PER_OP * 24576
 # Integer-pipe roofline.  The binding resource is the SM's 32-bit multiplier (the "heavy" half of the FMA pipe): IMAD.WIDE /
 # IMAD.HI issue at 32 results per clock per SM (quarter rate), IMAD at 64 (half rate = 0.5 IMAD.WIDE-equivalents).
 # ALGORITHMIC multiplier work of one ct x ct multiply + relinearise, in IMAD.WIDE-equivalents -- the cheapest exact
@@ -37,17 +40,30 @@ BUTTERFLIES_PER_OP = 47 * 24576
 #     36/37-bit primes, inverse : operand range 2^51 needs one more partial product of the quotient            = 5 w + 4 l = 7.0
 #     61-bit primes             : exact quotient 4 partial products (the lowest feeds one carry), low product 1 w + 2 l,
 #                                 -H q as H c - (H << 61): 1 w + 1 l                                            = 6 w + 3 l = 7.5
-#   NTTs per op: 14 forward + 12 inverse on 36/37-bit primes, 12 forward + 9 inverse on 61-bit primes (26 + 21)
+#   NTTs per op, SEAL's form (FHE_B200_QLIMB_NTT=1): 14 forward + 12 inverse on 36/37-bit primes, 12 forward + 9 inverse on
+#   61-bit primes (26 + 21).  Default: the 8 forward + 6 inverse q-limb transforms of the tensor product are not run
+#   (6 + 6 on 36/37-bit primes, 12 + 9 on 61-bit primes); k_floor_sk pays 50 more IMAD.WIDE-equivalents per coefficient for
+#   the exact recovery (3 Shoup products by constants + two 4-term sums of Shoup products, instead of 2 Shoup products).
 #   pointwise (base conversions in the integer domain, tensor, key-switch MAC, division by P), per kernel below.
 # Per kernel (what bench.py's live CUDA-event timing is divided into):
-KERNEL_WIDE_EQ = {
-    "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
-    "k_ext_ntt": 24576 * (8 * 6.5 + 12 * 7.5),                   # 20 forward NTTs: 8 on q limbs, 12 on the Bsk limbs
-    "k_tensor_intt": 24576 * (6 * 7.0 + 9 * 7.5) + 0.51e6,       # 15 inverse NTTs + the dyadic tensor
-    "k_floor_sk": 113.0 * 12288,                                 # fast_floor + fastbconv_sk per coefficient of the 3 output polys
+if QLIMB_NTT:
+    KERNEL_WIDE_EQ = {
+        "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
+        "k_ext_ntt": 24576 * (8 * 6.5 + 12 * 7.5),                   # 20 forward NTTs: 8 on q limbs, 12 on the Bsk limbs
+        "k_tensor_intt": 24576 * (6 * 7.0 + 9 * 7.5) + 0.51e6,       # 15 inverse NTTs + the dyadic tensor
+        "k_floor_sk": 113.0 * 12288,                                 # fast_floor + fastbconv_sk per coefficient of the 3 output polys
+    }
+else:
+    KERNEL_WIDE_EQ = {
+        "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
+        "k_ext_ntt": 24576 * 12 * 7.5,                               # 12 forward NTTs on the Bsk limbs
+        "k_tensor_intt": 24576 * 9 * 7.5 + 0.36e6,                   # 9 inverse NTTs + the dyadic tensor on the Bsk limbs
+        "k_floor_sk": 163.0 * 12288,                                 # q-limb recovery + fast_floor + fastbconv_sk per coefficient
+    }
+KERNEL_WIDE_EQ.update({
     "k_digit_ntt": 24576 * 6 * 6.5,                              # 6 key-switch digit NTTs
     "k_ks_finish": 24576 * 6 * 7.0 + 0.28e6 + 0.13e6,            # key MAC + 6 inverse NTTs + rounded division by P
-}
+})
 KERNEL_WIDE_EQ["k_ks_intt"] = 24576 * 6 * 7.0 + 0.28e6           # the unfused tail (small chunks): MAC + inverse NTTs
 KERNEL_WIDE_EQ["k_relin_finish"] = 0.13e6                        #   ... and the division by P
 WIDE_EQ_PER_OP = sum(KERNEL_WIDE_EQ[k] for k in ("k_ext_conv", "k_ext_ntt", "k_tensor_intt", "k_floor_sk", "k_digit_ntt", "k_ks_finish"))
@@ -800,7 +816,7 @@ def main() -> None:
                              "frac_of_theoretical": ach_k / peak_theory,
                              "share_of_step": kms / total_kernel_ms,
                              "ncu_fmaheavy_pct": (prof.get("fmaheavy_pct") or {}).get("k_ext_ntt2" if k == "k_ext_ntt" else k)}
-    ntt_floor_us = 24576 * (26 / bf_small + 21 / bf_big) * 1e-3
+    ntt_floor_us = 24576 * ((26 if QLIMB_NTT else 12) / bf_small + 21 / bf_big) * 1e-3
     hbm_ach = ops_per_launch * ALGO_BYTES_PER_OP / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "int_pipe",
@@ -814,7 +830,10 @@ def main() -> None:
         "peak_theoretical": peak_theory,
         "frac_of_theoretical": ach_dom / peak_theory if ach_dom else None,
         "algorithmic_wide_eq_per_op": {"dominant_kernel": dom_weq, "whole_op": WIDE_EQ_PER_OP,
-                                       "model": "14+12 fwd / 12+9 inv limb-NTTs x 24,576 butterflies at 6.5 / 7.0 (36-37 bit) and 7.5 (61 bit) "
+                                       "limb_ntts_per_op": NTTS_PER_OP,
+                                       "model": ("SEAL's form, 14+12 fwd / 12+9 inv" if QLIMB_NTT else
+                                                 "q-limbs of the tensor product recovered from its Bsk limbs (no q-limb transforms there): 6+12 fwd / 6+9 inv")
+                                                + " limb-NTTs x 24,576 butterflies at 6.5 / 7.0 (36-37 bit) and 7.5 (61 bit) "
                                                 "IMAD.WIDE-equivalents + pointwise per kernel (bench.py KERNEL_WIDE_EQ, DESIGN.md section 4)"},
         "whole_op": {"achieved": ach_op, "frac": ach_op / peak_wide, "frac_of_theoretical": ach_op / peak_theory, "us_per_op": 1e6 / ops_s,
                      "pipe_bound_us_per_op": WIDE_EQ_PER_OP / (peak_wide * 1e12) * 1e6},

@@ -991,6 +991,48 @@ def test_device_sampler_exact_paths_on_crafted_draws(dev):
     assert (e0[5][:1000] == 0).all() and e0[5][1000:].any()  # only the second variate (x * mult = 0) of those attempts survives
 
 
+def test_qlimb_recovery_equals_seals_form(dev, keys):
+    """default multiply: the q-limbs of the BEHZ tensor product are recovered exactly from its Bsk limbs (33 limb transforms);
+    FHE_B200_QLIMB_NTT=1: they are transformed as SEAL does (47).  Same bits, on random and on extreme residues, and both
+    equal the oracle (which follows SEAL)."""
+    import hashlib
+    import subprocess
+    import sys
+
+    code = r"""
+import hashlib, sys
+import numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from helpers import KeySet, random_ct, MODULI, N
+from fhe_precompiles_b200 import device
+device.init(0)
+keys = KeySet.load()
+rng = np.random.default_rng(606)
+a, b = random_ct(rng, 24), random_ct(rng, 24)
+for l in range(2):
+    a[20, :, l, :] = MODULI[l] - 1; b[20, :, l, :] = MODULI[l] - 1      # every coefficient q-1: the largest |t D|
+    a[21, :, l, :] = MODULI[l] // 2; b[21, :, l, :] = MODULI[l] // 2 + 1
+a[22] = 0; b[23] = 0
+t = lambda x: torch.from_numpy(np.ascontiguousarray(x).view(np.int64)).cuda()
+out = device.mul_relin(t(a), t(b), t(keys.rk)).cpu().numpy()
+print("SHA", hashlib.sha256(out.tobytes()).hexdigest())
+""" % (ROOT, os.path.join(ROOT, "tests"))
+    shas = {}
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, FHE_B200_QLIMB_NTT=mode))
+        assert r.returncode == 0, r.stdout + r.stderr
+        shas[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("SHA")][0]
+    assert shas["0"] == shas["1"]
+    rng = np.random.default_rng(606)
+    a, b = random_ct(rng, 24), random_ct(rng, 24)
+    for l in range(2):
+        a[20, :, l, :] = MODULI[l] - 1; b[20, :, l, :] = MODULI[l] - 1
+        a[21, :, l, :] = MODULI[l] // 2; b[21, :, l, :] = MODULI[l] // 2 + 1
+    a[22] = 0; b[23] = 0
+    want = np.stack([bfv.mul_relin(a[i], b[i], keys.rk) for i in range(24)])
+    assert shas["0"] == "SHA " + hashlib.sha256(want.view(np.int64).tobytes()).hexdigest()
+
+
 def test_exhausted_noise_budget_is_failed_decryption(dev, keys):
     """sunscreen's Runtime::decrypt refuses a ciphertext whose invariant noise budget is 0 (-> FailedDecryption = 5,
     fhe.rs:640-643, 692-696).  Three multiplications deep there is none left at these parameters (53 -> 30 -> 7 -> 0 bits);
