@@ -42,8 +42,10 @@ BUTTERFLIES_PER_OP = NTTS_PER_OP * 24576
 #                                 -H q as H c - (H << 61): 1 w + 1 l                                            = 6 w + 3 l = 7.5
 #   NTTs per op, SEAL's form (FHE_B200_QLIMB_NTT=1): 14 forward + 12 inverse on 36/37-bit primes, 12 forward + 9 inverse on
 #   61-bit primes (26 + 21).  Default: the 8 forward + 6 inverse q-limb transforms of the tensor product are not run
-#   (6 + 6 on 36/37-bit primes, 12 + 9 on 61-bit primes); k_floor_sk pays 50 more IMAD.WIDE-equivalents per coefficient for
-#   the exact recovery (3 Shoup products by constants + two 4-term sums of Shoup products, instead of 2 Shoup products).
+#   (6 + 6 on 36/37-bit primes, 12 + 9 on 61-bit primes); k_floor_sk recovers them exactly (3 Shoup products by constants + two
+#   3-term sums of Shoup products) and lifts the floor result from (b0, b1) by exact rounding instead of Shenoy-Kumaresan's
+#   m_sk correction: 98.5 IMAD.WIDE-equivalents per coefficient (5 x 6.5 Shoup products, 10 x 5 sum terms, 4 x 1.5 small
+#   terms, 4 x 1.5 reductions, 4 for the punctured sum and its folds) against 113 for SEAL's step-by-step form.
 #   pointwise (base conversions in the integer domain, tensor, key-switch MAC, division by P), per kernel below.
 # Per kernel (what bench.py's live CUDA-event timing is divided into):
 if QLIMB_NTT:
@@ -58,7 +60,7 @@ else:
         "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
         "k_ext_ntt": 24576 * 12 * 7.5,                               # 12 forward NTTs on the Bsk limbs
         "k_tensor_intt": 24576 * 9 * 7.5 + 0.36e6,                   # 9 inverse NTTs + the dyadic tensor on the Bsk limbs
-        "k_floor_sk": 163.0 * 12288,                                 # q-limb recovery + fast_floor + fastbconv_sk per coefficient
+        "k_floor_sk": 98.5 * 12288,                                  # q-limb recovery + fast_floor + exact lift from (b0, b1) per coefficient
     }
 KERNEL_WIDE_EQ.update({
     "k_digit_ntt": 24576 * 6 * 6.5,                              # 6 key-switch digit NTTs

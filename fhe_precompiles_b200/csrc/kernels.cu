@@ -483,13 +483,13 @@ __device__ __forceinline__ void floor_front_crt(u64 vb0, u64 vb1, u64 vsk, u64 &
     const u64 y0 = shoup_acc<Mod<MB0>, 1>(0, vb0, kc.crt3[0].w, kc.crt3[0].ws);  // [0, 4 p): < 2^63
     const u64 y1 = shoup_acc<Mod<MB1>, 1>(0, vb1, kc.crt3[1].w, kc.crt3[1].ws);
     const u64 y2 = shoup_acc<Mod<MSK>, 1>(0, vsk, kc.crt3[2].w, kc.crt3[2].ws);
-    const u64 v = ((y0 >> 45) + (y1 >> 45) + (y2 >> 45) + (1u << 15)) >> 16;  // <= 12
+    const u32 v = (u32)(((y0 >> 45) + (y1 >> 45) + (y2 >> 45) + (1u << 15)) >> 16);  // <= 12
     {
-        ShoupSum<Mod<MQ0>> s;  // four terms < 3.5 q each
+        ShoupSum<Mod<MQ0>> s;  // three terms < 3.5 q each + v K' < 12 q
         s.add_a1(y0, kc.crtK[0][0].w, kc.crtK[0][0].ws);
         s.add_a1(y1, kc.crtK[1][0].w, kc.crtK[1][0].ws);
         s.add_a1(y2, kc.crtK[2][0].w, kc.crtK[2][0].ws);
-        s.add_a1(v, kc.crtNB[0].w, kc.crtNB[0].ws);
+        s.add_small(v, kc.crtNB[0].w);
         t0 = canon_k32<Mod<MQ0>>(s.value());
     }
     {
@@ -497,7 +497,7 @@ __device__ __forceinline__ void floor_front_crt(u64 vb0, u64 vb1, u64 vsk, u64 &
         s.add_a1(y0, kc.crtK[0][1].w, kc.crtK[0][1].ws);
         s.add_a1(y1, kc.crtK[1][1].w, kc.crtK[1][1].ws);
         s.add_a1(y2, kc.crtK[2][1].w, kc.crtK[2][1].ws);
-        s.add_a1(v, kc.crtNB[1].w, kc.crtNB[1].ws);
+        s.add_small(v, kc.crtNB[1].w);
         t1 = canon_k32<Mod<MQ1>>(s.value());
     }
 }
@@ -525,6 +525,29 @@ __device__ __forceinline__ void floor_sk_coeff(u64 v0, u64 v1, u64 vb0, u64 vb1,
         // tb_j = [(v_bj - y0) q^-1 (B/b_j)^-1]_{b_j}: one exact Shoup product (skV); canonical, it is carried into other moduli
         const u64 xb0 = vb0 + B0::two_q - (y61 + (u64)(yk * (u32)B0::kC));
         const u64 xb1 = vb1 + B1::two_q - (y61 + (u64)(yk * (u32)B1::kC));
+        if (CRT) {
+            // f = (t D - y0) / q is an integer below 2^96 and B = b0 b1 ~ 2^122, so its lift from (b0, b1) needs no m_sk:
+            // f = tb0 b1 + tb1 b0 - v' B with v' = round(tb0 / b0 + tb1 / b1), exactly what fastbconv_sk's Shenoy-Kumaresan
+            // correction produces (both are the exact f mod q_l); any representative of tb_j works (v' moves with it)
+            const u64 tb0 = shoup_acc<B0, 1>(0, xb0, kc.skV[0], kc.skVs[0]);  // [0, 4 p)
+            const u64 tb1 = shoup_acc<B1, 1>(0, xb1, kc.skV[1], kc.skVs[1]);
+            const u32 vp = (u32)(((tb0 >> 45) + (tb1 >> 45) + (1u << 15)) >> 16);  // <= 8
+            {
+                ShoupSum<Q0> s;  // two terms < 3.5 q each + v' (q - B mod q) < 8 q
+                s.add_a1(tb0, kc.pBq[0][0].w, kc.pBq[0][0].ws);
+                s.add_a1(tb1, kc.pBq[1][0].w, kc.pBq[1][0].ws);
+                s.add_small(vp, kc.nBq[0].w);
+                o0 = canon_k32<Q0>(s.value());
+            }
+            {
+                ShoupSum<Q1> s;
+                s.add_a1(tb0, kc.pBq[0][1].w, kc.pBq[0][1].ws);
+                s.add_a1(tb1, kc.pBq[1][1].w, kc.pBq[1][1].ws);
+                s.add_small(vp, kc.nBq[1].w);
+                o1 = canon_k32<Q1>(s.value());
+            }
+            return;
+        }
         const u64 tb0 = canon_k32<B0>(shoup_lazy<B0>(xb0, kc.skV[0], kc.skVs[0]));
         const u64 tb1 = canon_k32<B1>(shoup_lazy<B1>(xb1, kc.skV[1], kc.skVs[1]));
         // alpha = [(tb0 b1 + tb1 b0  -  (v_msk - y0) q^-1) B^-1]_{m_sk}, and b_j == -(m_sk - b_j) (mod m_sk) is 19 bits:

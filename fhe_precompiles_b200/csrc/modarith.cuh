@@ -178,6 +178,14 @@ struct ShoupSum {
         hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh;
         low_product(xl, xh, w);
     }
+    // x * w for a small x (the product itself stays far below 2^64: no quotient term)                  1 wide + 1 low
+    __device__ __forceinline__ void add_small(u32 x, u64 w) {
+        u32 wl, wh, al, ah;
+        unpack64(w, wl, wh);
+        unpack64(mad_wide(x, wl, lo), al, ah);
+        ah = mad_lo(x, wh, ah);
+        lo = pack64(al, ah);
+    }
     // sum - (sum H) q  =  sum + (sum H) c - ((sum H) << B)   (mod 2^64)
     __device__ __forceinline__ u64 value() const {
         constexpr u32 c = (u32)M::kC;
