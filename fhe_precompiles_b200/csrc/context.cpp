@@ -3,6 +3,8 @@
 // SEALContext::validate (coeff_div_plain_modulus, upper-half constants) and RNSTool::initialize.
 #include "context.h"
 
+#include <cmath>
+
 #include <dlfcn.h>
 
 #include <cstdlib>
@@ -282,6 +284,36 @@ void build(HostContext &H) {
         }
     }
 
+    // --- the dual base: primes, packed twiddles (32-bit Shoup quotients floor(w 2^32 / s))
+    {
+        u64 v = (((u64)1 << 30) - 1) / (2 * kN) * (2 * kN) + 1;
+        for (int i = 0; i < 2 * kNumDual; v -= 2 * kN)
+            if (is_prime_u64(v)) {
+                if (v != kDualPrime[i]) throw std::runtime_error("fhe_b200: dual-base primes differ from compiled constants");
+                i++;
+            }
+    }
+    for (int d = 0; d < kNumDual; d++) {
+        const int ti = kNumMod + d;
+        H.twf[ti].assign(kN, make_ulonglong2(0, 0));
+        H.twi[ti].assign(kN, make_ulonglong2(0, 0));
+        for (int lane = 0; lane < 2; lane++) {
+            const u64 s = kDualPrime[2 * d + lane];
+            const u64 psi = minimal_root(2 * kN, s);
+            const int sh = 32 * lane;
+            u64 pw = 1;
+            for (u32 i = 0; i < (u32)kN; i++) {
+                const u32 k = bitrev12(i);
+                const u64 inv = h_invmod(pw, s);
+                H.twf[ti][k].x |= pw << sh;
+                H.twf[ti][k].y |= ((pw << 32) / s) << sh;
+                H.twi[ti][k].x |= inv << sh;
+                H.twi[ti][k].y |= ((inv << 32) / s) << sh;
+                pw = h_mulmod(pw, psi, s);
+            }
+        }
+    }
+
     DevConsts &c = H.dc;
     memset(&c, 0, sizeof(c));
     const u64 q0 = kModulus[MQ0], q1 = kModulus[MQ1], P = kModulus[MP];
@@ -353,6 +385,62 @@ void build(HostContext &H) {
     for (int l = 0; l < 2; l++) {
         const u64 b3 = h_mulmod(h_mulmod(b0 % qs[l], b1 % qs[l], qs[l]), msk % qs[l], qs[l]);
         c.crtNB[l] = mk_shoup(h_mulmod((qs[l] - b3) % qs[l], inv_punct_q[l], qs[l]), qs[l]);
+    }
+    // BEHZ on the dual base (devconsts.h)
+    {
+        typedef unsigned __int128 U;
+        auto mulmod_many = [](const u64 *f, int n, int skip, u64 m) {  // prod_{i != skip} f_i mod m
+            u64 r = 1 % m;
+            for (int i = 0; i < n; i++)
+                if (i != skip) r = h_mulmod(r, f[i] % m, m);
+            return r;
+        };
+        u64 sp[6];
+        for (int i = 0; i < 6; i++) sp[i] = kDualPrime[i];
+        {   // S must exceed 2 |t D|: |t D| <= t N (q/2)^2 (1 + 2^-29)
+            long double lg = 0;
+            for (int i = 0; i < 6; i++) lg += log2l((long double)sp[i]);
+            const long double need = 1 + kLogT + kLogN + 2 * (log2l((long double)q0) + log2l((long double)q1) - 1) + 0.01L;
+            if (lg < need + 8) throw std::runtime_error("fhe_b200: dual base too small");
+        }
+        for (int i = 0; i < 6; i++) {
+            const u64 s = sp[i];
+            c.d_R32[i] = (u32)(((u64)1 << 32) % s);
+            c.d_R61[i] = (u32)(((u64)1 << 61) % s);
+            c.d_NQ[i] = (u32)((s - (u64)(q % s)) % s);
+            c.d_mu61[i] = (u32)(((u64)1 << 61) / s);
+            const u64 ci = h_invmod(mulmod_many(sp, 6, i, s), s);
+            c.d_C[i] = (u32)ci;
+            c.d_Cs[i] = (u32)((ci << 32) / s);
+            c.d_R48[i] = (u32)(((u64)1 << 48) / s);
+            for (int l = 0; l < 2; l++) c.d_K[i][l] = mk_shoup(h_mulmod(mulmod_many(sp, 6, i, qs[l]), inv_punct_q[l], qs[l]), qs[l]);
+        }
+        for (int l = 0; l < 2; l++) {
+            const u64 sq = mulmod_many(sp, 6, -1, qs[l]);
+            c.d_KN[l] = h_mulmod((qs[l] - sq) % qs[l], inv_punct_q[l], qs[l]);
+            c.d_NS4[l] = (qs[l] - mulmod_many(sp, 4, -1, qs[l])) % qs[l];
+        }
+        for (int i = 0; i < 4; i++) {
+            const u64 s = sp[i];
+            c.d_R58[i] = (u32)(((u64)1 << 58) % s);
+            const u64 w = h_mulmod(h_invmod((u64)(q % s), s), h_invmod(mulmod_many(sp, 4, i, s), s), s);
+            c.d_W[i] = (u32)w;
+            c.d_Ws[i] = (u32)((w << 32) / s);
+            for (int l = 0; l < 2; l++) c.d_P[i][l] = mk_shoup(mulmod_many(sp, 4, i, qs[l]), qs[l]);
+        }
+        for (int d = 0; d < kNumDual; d++) {
+            u64 w[2] = {0, 0}, ws[2] = {0, 0}, ww[2] = {0, 0}, wws[2] = {0, 0};
+            for (int lane = 0; lane < 2; lane++) {
+                const u64 s = sp[2 * d + lane];
+                const u64 nt = h_mulmod(h_invmod(kN, s), kT % s, s);
+                const u64 w_last = (H.twi[kNumMod + d][1].x >> (32 * lane)) & 0xffffffffull;
+                const u64 ntw = h_mulmod(nt, w_last, s);
+                w[lane] = nt, ws[lane] = (nt << 32) / s, ww[lane] = ntw, wws[lane] = (ntw << 32) / s;
+            }
+            c.d_ninv_t[d].w = w[0] | (w[1] << 32), c.d_ninv_t[d].ws = ws[0] | (ws[1] << 32);
+            c.d_ninv_t_w[d].w = ww[0] | (ww[1] << 32), c.d_ninv_t_w[d].ws = wws[0] | (wws[1] << 32);
+        }
+        (void)sizeof(U);
     }
     // key switching
     c.half_P = P >> 1;
@@ -428,8 +516,8 @@ DeviceContext &device_context(int device) {
     const HostContext &H = HostContext::get();
     const size_t per = (size_t)kN * sizeof(ulonglong2);
     void *mem = nullptr;
-    cuda_check(cudaMalloc(&mem, per * kNumMod * 2), "cudaMalloc(twiddles)");
-    for (int mi = 0; mi < kNumMod; mi++) {
+    cuda_check(cudaMalloc(&mem, per * kNumTab * 2), "cudaMalloc(twiddles)");
+    for (int mi = 0; mi < kNumTab; mi++) {
         char *f = (char *)mem + per * (size_t)(2 * mi);
         char *i = f + per;
         cuda_check(cudaMemcpy(f, H.twf[mi].data(), per, cudaMemcpyHostToDevice), "upload twf");
@@ -439,7 +527,7 @@ DeviceContext &device_context(int device) {
     }
     {
         std::vector<DevTwLow> lo(1);
-        for (int mi = 0; mi < kNumMod; mi++)
+        for (int mi = 0; mi < kNumTab; mi++)
             for (int k = 0; k < 64; k++) {
                 lo[0].f[mi][k] = H.twf[mi][(size_t)k];
                 lo[0].i[mi][k] = H.twi[mi][(size_t)k];

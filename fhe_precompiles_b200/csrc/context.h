@@ -11,8 +11,8 @@ namespace fheb {
 
 struct HostContext {
     u64 root[kNumMod];                   // minimal primitive 2N-th roots
-    std::vector<ulonglong2> twf[kNumMod];  // forward twiddles (w, Shoup)
-    std::vector<ulonglong2> twi[kNumMod];  // inverse twiddles
+    std::vector<ulonglong2> twf[kNumTab];  // forward twiddles (w, Shoup); dual limbs: both 32-bit lanes packed in each word
+    std::vector<ulonglong2> twi[kNumTab];  // inverse twiddles
     DevConsts dc;
     uint64_t parms_id_key[4];   // BLAKE2b-256 over [scheme, N, q0, q1, P, t]
     uint64_t parms_id_data[4];  // BLAKE2b-256 over [scheme, N, q0, q1, t]

@@ -49,6 +49,23 @@ struct DevConsts {
     Shoup crtK[3][2];      // (Bsk/p_i) (q/q_l)^-1 mod q_l
     Shoup crtNB[2];        // -Bsk (q/q_l)^-1 mod q_l
 
+    // ---- BEHZ multiply on the dual base s_0..s_5 (params.h: kDualPrime; kernels k_*_d).  S = prod s_i, S4 = s_0 s_1 s_2 s_3.
+    //   extension   : a' = base + m 2^61 (- q)  ->  [base_lo + base_hi R32 + m R61 (+ NQ)]_{s_i}, Barrett from below 2^61
+    //   after INTT  : r_i = t D mod s_i.   y_i = [r_i C_i]_{s_i},  v = round(sum y_i / s_i)  (|t D| / S < 2^-13)
+    //   t_l         = [sum y_i K[i][l] + v KN[l]]_{q_l}            (= t D (q/q_l)^-1 mod q_l, the quantity fast_floor starts from)
+    //   y0          = t0 q1 + t1 q0;   tb_i = [(r_i - y0) W_i]_{s_i}, i < 4,   v' = round(sum tb_i / s_i)  (|f| / S4 < 2^-24)
+    //   out_l       = [sum tb_i P[i][l] + v' NS4[l]]_{q_l}         (= f mod q_l,  f = (t D - y0) / q)
+    u32 d_R32[6], d_R61[6], d_NQ[6], d_mu61[6];  // 2^32 mod s, 2^61 mod s, -q mod s, floor(2^61 / s)
+    Shoup d_ninv_t[3], d_ninv_t_w[3];            // N^-1 t and N^-1 t w_last per dual limb: both lanes packed; ws = 32-bit Shoup quotients
+    u32 d_C[6], d_Cs[6];                         // (S/s_i)^-1 mod s_i and floor(. 2^32 / s_i)
+    u32 d_R48[6];                                // floor(2^48 / s_i): y_i / s_i to 16 bits
+    Shoup d_K[6][2];                             // (S/s_i) (q/q_l)^-1 mod q_l
+    u64 d_KN[2];                                 // -S (q/q_l)^-1 mod q_l
+    u32 d_R58[4];                                // 2^58 mod s_i
+    u32 d_W[4], d_Ws[4];                         // q^-1 (S4/s_i)^-1 mod s_i
+    Shoup d_P[4][2];                             // (S4/s_i) mod q_l
+    u64 d_NS4[2];                                // -S4 mod q_l
+
     // ---- key switching (switch_key_inplace, BFV branch)
     Shoup inv_P_mod_q[2];
     u64 half_P;
@@ -69,13 +86,13 @@ struct DevConsts {
 // twiddles of the first six stages (table indices 1..63), read through the constant cache: they are
 // CTA-uniform (first pass) or warp-uniform (second pass)
 struct DevTwLow {
-    ulonglong2 f[kNumMod][64];
-    ulonglong2 i[kNumMod][64];
+    ulonglong2 f[kNumTab][64];
+    ulonglong2 i[kNumTab][64];
 };
 
 struct DevTables {
-    const ulonglong2 *twf[kNumMod];  // [k] = (rp[k], rp[k] Shoup), rp[bitrev(i)] = psi^i
-    const ulonglong2 *twi[kNumMod];  // [k] = (rp[k]^-1, Shoup)
+    const ulonglong2 *twf[kNumTab];  // [k] = (rp[k], rp[k] Shoup), rp[bitrev(i)] = psi^i
+    const ulonglong2 *twi[kNumTab];  // [k] = (rp[k]^-1, Shoup)
 };
 
 }  // namespace fheb

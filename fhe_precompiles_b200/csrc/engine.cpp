@@ -498,14 +498,15 @@ void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint6
 
 // BEHZ multiply of c ops: a, b -> m.c3 (size-3 ciphertexts)
 void Engine::enqueue_mul(const uint64_t *a, const uint64_t *b, const ScratchMap &m, size_t c, cudaStream_t s, bool timed) {
+    const bool dual = !fused_ && behz_mode() == 0;  // tensor product on the dual base (default) or on SEAL's 61-bit Bsk limbs
     if (fused_) {
         TIMED(0, launch_behz_tensor(a, b, m.tens, c, s), "behz_tensor");
     } else {
-        if (ext_split()) TIMED(8, launch_ext_conv(a, b, m.nttbuf, c, s), "ext_conv");
+        if (ext_split() || dual) TIMED(8, launch_ext_conv(a, b, m.nttbuf, c, s), "ext_conv");
         TIMED(4, launch_ext_ntt(a, b, m.nttbuf, c, s), "ext_ntt");
         TIMED(5, launch_tensor_intt(m.nttbuf, m.tens, c, s), "tensor_intt");
     }
-    TIMED(1, launch_floor_sk(m.tens, m.c3, c, s), "floor_sk");
+    TIMED(1, launch_floor_sk(m.tens, m.c3, c, s, dual), "floor_sk");
 }
 // relinearise c size-3 ciphertexts c3 -> out
 void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out, const ScratchMap &m, size_t c, cudaStream_t s,

@@ -607,6 +607,222 @@ __global__ void __launch_bounds__(256) k_floor_sk(const u64 *__restrict__ tens, 
 }
 
 // =====================================================================================
+// K6d-K8d: the BEHZ multiply on the DUAL base (default; params.h kDualPrime, devconsts.h d_*).  bfv_multiply's result is
+// a function of integer polynomials -- the extended operands a' = (y0 + r q) / m~, their product D, f = (t D - y0') / q --
+// and does not depend on the auxiliary primes that carry them, so they are carried by six primes below 2^30, two per
+// 64-bit word, where a butterfly costs one IMAD.HI + two IMAD per lane (8 multiplier cycles per 30 bits) instead of
+// 6 IMAD.WIDE + 4 IMAD (32 cycles per 61 bits).  Same scratch slots as the 61-bit limbs (e = 2..4 of the 5-limb arrays).
+//   k_ext_conv_d    : a' mod s_i for the 4 input polynomials                         eltwise
+//   k_ext_ntt_d     : 12 forward dual transforms, in place                           grid (12, ops)
+//   k_tensor_intt_d : dyadic tensor + 9 inverse dual transforms (x N^-1 t)           grid (9, ops)
+//   k_floor_sk_d    : exact CRT of t D -> t_l -> y0 -> f on (s_0..s_3) -> f mod q_l   eltwise
+// =====================================================================================
+template <int D>
+__device__ __forceinline__ u64 ext_dual(u64 base, u32 m, bool neg) {
+    u32 bl, bh, r[2];
+    unpack64(base, bl, bh);
+#pragma unroll
+    for (int lane = 0; lane < 2; lane++) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int i = 2 * D + lane;
+        const u32 s = lane ? ModDual<D>::s1 : ModDual<D>::s0;
+        // Z = base + m 2^61 (- q)  ==  base_lo + base_hi R32 + m R61 (+ NQ)   < 2^61
+        u64 V = mad_wide(bh, kc.d_R32[i], (u64)bl);
+        V = mad_wide(m, kc.d_R61[i], V) + (neg ? kc.d_NQ[i] : 0u);
+        r[lane] = barrett61(V, kc.d_mu61[i], s);  // [0, 4s): the forward transform's input range
+    }
+    return pack64(r[0], r[1]);
+}
+__global__ void __launch_bounds__(256) k_ext_conv_d(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf,
+                                                    size_t n_ops) {
+    const size_t total = n_ops * 4 * (kN / 2);
+    for (size_t g = (size_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (size_t)gridDim.x * 256) {
+        const size_t op = g / (4 * (kN / 2));
+        const int p = (int)((g / (kN / 2)) & 3), i = 2 * (int)(g & (kN / 2 - 1));
+        const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
+        const ulonglong2 x0 = *reinterpret_cast<const ulonglong2 *>(ct + i), x1 = *reinterpret_cast<const ulonglong2 *>(ct + kN + i);
+        u64 base0, base1;
+        u32 m0, m1;
+        bool neg0, neg1;
+        ext_shared(x0.x, x1.x, base0, m0, neg0);
+        ext_shared(x0.y, x1.y, base1, m1, neg1);
+        u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN + i;
+        *reinterpret_cast<ulonglong2 *>(dst) = make_ulonglong2(ext_dual<0>(base0, m0, neg0), ext_dual<0>(base1, m1, neg1));
+        *reinterpret_cast<ulonglong2 *>(dst + kN) = make_ulonglong2(ext_dual<1>(base0, m0, neg0), ext_dual<1>(base1, m1, neg1));
+        *reinterpret_cast<ulonglong2 *>(dst + 2 * kN) = make_ulonglong2(ext_dual<2>(base0, m0, neg0), ext_dual<2>(base1, m1, neg1));
+    }
+}
+template <int D>
+__device__ __forceinline__ void ntt_dual_body(u64 *__restrict__ limb, u64 *smem, int t) {
+    using M = ModDual<D>;
+    u64 v[1][8];
+    load_natural(limb, v[0], t);
+    ntt_forward<M, 1, false, false>(v, smem, kt.twf[M::kIndex], t);  // values stay in [0, 4s)
+    store_chunk8(limb, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_d(u64 *__restrict__ nttbuf) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int p = blockIdx.x / 3, d = blockIdx.x % 3;
+    u64 *limb = nttbuf + (op * 20 + (size_t)(p * 5 + 2 + d)) * kN;
+    const int t = threadIdx.x;
+    switch (d) {
+        case 0: ntt_dual_body<0>(limb, smem, t); break;
+        case 1: ntt_dual_body<1>(limb, smem, t); break;
+        default: ntt_dual_body<2>(limb, smem, t); break;
+    }
+}
+// one lane of the dyadic tensor: operands in [0, 4s) -> product(s) mod s in [0, 2s)
+template <int NP>
+__device__ __forceinline__ u32 dual_mulsum(const u32 (&x)[NP], const u32 (&y)[NP], u32 s, u32 mu61) {
+    u64 P = 0;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        const u32 a = csub32(csub32(x[k], 2 * s), s), b = csub32(csub32(y[k], 2 * s), s);  // canonical: a b < 2^60
+        P = mad_wide(a, b, P);
+    }
+    return csub32(barrett61(P, mu61, s), 2 * s);
+}
+template <int D>
+__device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb, int d, u64 *__restrict__ dst, u64 *smem, int t) {
+    using M = ModDual<D>;
+    constexpr int E = 2 + D;
+    const u64 *a0 = nb + (size_t)(0 * 5 + E) * kN, *a1 = nb + (size_t)(1 * 5 + E) * kN;
+    const u64 *b0 = nb + (size_t)(2 * 5 + E) * kN, *b1 = nb + (size_t)(3 * 5 + E) * kN;
+    const u32 mu0 = kc.d_mu61[2 * D], mu1 = kc.d_mu61[2 * D + 1];
+    u64 v[1][8];
+    const ulonglong2 *pa0 = reinterpret_cast<const ulonglong2 *>(a0 + 8 * t), *pa1 = reinterpret_cast<const ulonglong2 *>(a1 + 8 * t);
+    const ulonglong2 *pb0 = reinterpret_cast<const ulonglong2 *>(b0 + 8 * t), *pb1 = reinterpret_cast<const ulonglong2 *>(b1 + 8 * t);
+    auto one = [&](u64 x0, u64 y0) -> u64 {
+        u32 xl, xh, yl, yh;
+        unpack64(x0, xl, xh);
+        unpack64(y0, yl, yh);
+        const u32 xs0[1] = {xl}, ys0[1] = {yl}, xs1[1] = {xh}, ys1[1] = {yh};
+        return pack64(dual_mulsum<1>(xs0, ys0, M::s0, mu0), dual_mulsum<1>(xs1, ys1, M::s1, mu1));
+    };
+    auto two = [&](u64 x0, u64 y0, u64 x1, u64 y1) -> u64 {
+        u32 al, ah, bl, bh, cl, ch, dl, dh;
+        unpack64(x0, al, ah);
+        unpack64(y0, bl, bh);
+        unpack64(x1, cl, ch);
+        unpack64(y1, dl, dh);
+        const u32 xs0[2] = {al, cl}, ys0[2] = {bl, dl}, xs1[2] = {ah, ch}, ys1[2] = {bh, dh};
+        return pack64(dual_mulsum<2>(xs0, ys0, M::s0, mu0), dual_mulsum<2>(xs1, ys1, M::s1, mu1));
+    };
+    if (d == 1) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const ulonglong2 x0 = pa0[r], y1 = pb1[r], x1 = pa1[r], y0 = pb0[r];
+            v[0][2 * r] = two(x0.x, y1.x, x1.x, y0.x);
+            v[0][2 * r + 1] = two(x0.y, y1.y, x1.y, y0.y);
+        }
+    } else {
+        const ulonglong2 *px = d == 0 ? pa0 : pa1, *py = d == 0 ? pb0 : pb1;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const ulonglong2 x = px[r], y = py[r];
+            v[0][2 * r] = one(x.x, y.x);
+            v[0][2 * r + 1] = one(x.y, y.y);
+        }
+    }
+    ntt_inverse<M, 1, false, false>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv_t[D], kc.d_ninv_t_w[D]);  // [0, 2s)
+    store_natural(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 3) k_tensor_intt_d(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int d = blockIdx.x / 3, e = blockIdx.x % 3;
+    const u64 *nb = nttbuf + op * 20 * kN;
+    u64 *dst = tens + (op * 15 + (size_t)(d * 5 + 2 + e)) * kN;
+    const int t = threadIdx.x;
+    switch (e) {
+        case 0: tensor_intt_dual_body<0>(nb, d, dst, smem, t); break;
+        case 1: tensor_intt_dual_body<1>(nb, d, dst, smem, t); break;
+        default: tensor_intt_dual_body<2>(nb, d, dst, smem, t); break;
+    }
+}
+__device__ __forceinline__ u32 dual_prime(int i) {
+    constexpr u32 p[6] = {kDualPrime[0], kDualPrime[1], kDualPrime[2], kDualPrime[3], kDualPrime[4], kDualPrime[5]};
+    return p[i];
+}
+// per coefficient: the three dual words of t D (each lane in [0, 2s))  ->  limbs q0, q1 of the size-3 product
+__device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0, u64 &o1) {
+    using Q0 = Mod<MQ0>;
+    using Q1 = Mod<MQ1>;
+    u32 r[6], y[6];
+    unpack64(w0, r[0], r[1]);
+    unpack64(w1, r[2], r[3]);
+    unpack64(w2, r[4], r[5]);
+    u32 est = 1u << 15;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        y[i] = shoup32(r[i], kc.d_C[i], kc.d_Cs[i], dual_prime(i));  // [(S/s_i)^-1 r_i] in [0, 2s)
+        est += (u32)(mul_wide(y[i], kc.d_R48[i]) >> 32);             // y_i / s_i in units of 2^-16
+    }
+    const u32 v = est >> 16;  // t D = sum y_i (S/s_i) - v S exactly (|t D| / S < 2^-13)
+    u64 t0, t1;
+    {
+        ShoupSum<Q0> s;  // six terms < q + 1 each + v KN < 13 q
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.d_K[i][0].w, kc.d_K[i][0].ws);
+        s.add_small(v, kc.d_KN[0]);
+        t0 = canon_k32<Q0>(s.value());
+    }
+    {
+        ShoupSum<Q1> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.d_K[i][1].w, kc.d_K[i][1].ws);
+        s.add_small(v, kc.d_KN[1]);
+        t1 = canon_k32<Q1>(s.value());
+    }
+    // fast_floor: y0 = t0 q1 + t1 q0 (the q-part of t D with its fast-base-conversion overflow), f = (t D - y0) / q on s_0..s_3
+    u64 ylo, yhi;
+    punctured_sum(t0, t1, ylo, yhi);
+    const u32 u2 = (u32)((ylo >> 58) | (yhi << 6));  // y0 < 2^73
+    const u64 low58 = ylo & ((1ull << 58) - 1);
+    u32 tb[4], est2 = 1u << 15;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const u32 s = dual_prime(i);
+        const u32 yi = csub32(barrett61(mad_wide(u2, kc.d_R58[i], low58), kc.d_mu61[i], s), 2 * s);  // y0 mod s_i in [0, 2s)
+        tb[i] = shoup32(r[i] + 2 * s - yi, kc.d_W[i], kc.d_Ws[i], s);                               // [f (S4/s_i)^-1] in [0, 2s)
+        est2 += (u32)(mul_wide(tb[i], kc.d_R48[i]) >> 32);
+    }
+    const u32 vp = est2 >> 16;  // f = sum tb_i (S4/s_i) - v' S4 exactly (|f| / S4 < 2^-24)
+    {
+        ShoupSum<Q0> s;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s.add32(tb[i], kc.d_P[i][0].w, kc.d_P[i][0].ws);
+        s.add_small(vp, kc.d_NS4[0]);
+        o0 = canon_k32<Q0>(s.value());
+    }
+    {
+        ShoupSum<Q1> s;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s.add32(tb[i], kc.d_P[i][1].w, kc.d_P[i][1].ws);
+        s.add_small(vp, kc.d_NS4[1]);
+        o1 = canon_k32<Q1>(s.value());
+    }
+}
+__global__ void __launch_bounds__(256) k_floor_sk_d(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
+    const size_t total = n_ops * 3 * (kN / 2);
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const size_t opp = g / (kN / 2);  // op*3 + poly
+        const int i = 2 * (int)(g % (kN / 2));
+        const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(tens + opp * 5 * kN + i);
+        const ulonglong2 w0 = in[2 * (kN / 2)], w1 = in[3 * (kN / 2)], w2 = in[4 * (kN / 2)];
+        u64 ax, ay, bx, by;
+        floor_sk_coeff_d(w0.x, w1.x, w2.x, ax, bx);
+        floor_sk_coeff_d(w0.y, w1.y, w2.y, ay, by);
+        ulonglong2 *out = reinterpret_cast<ulonglong2 *>(c3 + opp * 2 * kN + i);
+        out[0] = make_ulonglong2(ax, ay);
+        out[kN / 2] = make_ulonglong2(bx, by);
+    }
+}
+
+// =====================================================================================
 // K9a: key switching core  (SEAL Evaluator::switch_key_inplace, BFV branch, up to the inverse NTTs)
 // one CTA per (key modulus J = q0,q1,P ; op): 2 digit NTTs, MAC with the relin key, 2 INTTs
 //   c3 [op][3][2][N]  ->  ks [op][2][3][N]   (coefficient form, canonical)
@@ -1509,27 +1725,36 @@ static int ext_split_mode() {
     return mode;
 }
 bool ext_split() { return ext_split_mode() != 0; }
-// Default: the q-limbs of the tensor product are recovered exactly from its Bsk limbs in k_floor_sk, so the 8 forward and 6
-// inverse q-limb transforms of SEAL's bfv_multiply are never run (33 limb transforms per multiply + relinearise instead of 47).
-// FHE_B200_QLIMB_NTT=1 runs them as SEAL does (A/B; same bits).
-static int qlimb_ntt_mode() {
+// How bfv_multiply's tensor product is carried (same bits in every mode):
+//   0 "dual" (default): six primes below 2^30, two per word (k_*_d above): 21 dual transforms
+//   1 "bsk"           : SEAL's three 61-bit Bsk primes, q-limbs recovered from them in k_floor_sk: 21 transforms on 61-bit primes
+//   2 "seal"          : SEAL's form, q-limbs transformed too: 35 transforms (FHE_B200_BEHZ=seal or FHE_B200_QLIMB_NTT=1)
+static int behz_mode_() {
     static const int mode = [] {
-        const char *v = getenv("FHE_B200_QLIMB_NTT");
-        return (v && *v == '1') ? 1 : 0;
+        const char *q = getenv("FHE_B200_QLIMB_NTT");
+        if (q && *q == '1') return 2;
+        const char *v = getenv("FHE_B200_BEHZ");
+        if (v && !strcmp(v, "seal")) return 2;
+        if (v && !strcmp(v, "bsk")) return 1;
+        return 0;
     }();
     return mode;
 }
+int behz_mode() { return behz_mode_(); }
+static int qlimb_ntt_mode() { return behz_mode_() == 2; }
 bool qlimb_ntt() { return qlimb_ntt_mode() != 0; }
 cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    k_ext_conv<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
+    if (behz_mode_() == 0) k_ext_conv_d<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
+    else k_ext_conv<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }
 // with ext_split(): the transforms only (launch_ext_conv must have filled the auxiliary limbs); otherwise extension + transforms
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    if (ext_split_mode() && !qlimb_ntt_mode()) k_ext_ntt2<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 1);
+    if (behz_mode_() == 0) k_ext_ntt_d<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
+    else if (ext_split_mode() && !qlimb_ntt_mode()) k_ext_ntt2<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 1);
     else if (ext_split_mode()) k_ext_ntt2<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 0);
     else k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1537,7 +1762,8 @@ cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops
 }
 cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    if (qlimb_ntt_mode()) k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 0);
+    if (behz_mode_() == 0) k_tensor_intt_d<<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
+    else if (qlimb_ntt_mode()) k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 0);
     else k_tensor_intt<<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 1);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
@@ -1612,9 +1838,10 @@ cudaError_t launch_seal_sample(u64 *streams, signed char *samples, int *failed, 
     (void)samples;  // the samples are written behind each op's stream words (see kernels.h)
     return cudaGetLastError();
 }
-cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s) {
+cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s, bool dual) {
     if (n_ops == 0) return cudaSuccess;
-    if (qlimb_ntt_mode()) k_floor_sk<false><<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
+    if (dual) k_floor_sk_d<<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
+    else if (qlimb_ntt_mode()) k_floor_sk<false><<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
     else k_floor_sk<true><<<eltwise_grid(n_ops * 3 * (kN / 2), 256), 256, 0, s>>>(tens, c3, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();

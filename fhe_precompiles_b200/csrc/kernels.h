@@ -44,8 +44,11 @@ cudaError_t launch_encrypt(const u64 *pk, const unsigned short *plain, const u64
 // int8 sample polynomials, which the kernel writes there.  failed[i] = 1 if the draws ran out.
 constexpr size_t kSealOpWords = 28 * 512 + 3 * 4096 / 8;
 cudaError_t launch_seal_sample(u64 *streams, signed char *samples, int *failed, size_t n_ops, cudaStream_t s);
-cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s);
+// dual: `tens` holds the tensor product on the dual base (launch_ext_conv / ext_ntt / tensor_intt in behz_mode() 0); otherwise on
+// SEAL's 61-bit Bsk limbs (the fused kernel, the stage taps, behz_mode() 1 and 2)
+cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t s, bool dual = false);
 cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s);
+int behz_mode();        // 0 dual base (default), 1 SEAL's Bsk primes + q-limb recovery, 2 SEAL's form (FHE_B200_BEHZ=dual|bsk|seal)
 bool qlimb_ntt();       // FHE_B200_QLIMB_NTT=1: transform the q-limbs of the tensor product as SEAL does instead of recovering them from the Bsk limbs
 bool ks_finish_fused();  // default: key-switch MAC + inverse transforms + rounded division by P in one kernel (FHE_B200_KS_FINISH=0: two)
 cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s);

@@ -30,6 +30,7 @@ constexpr int mod_bits(u64 q) {
 
 template <int MI>
 struct Mod {
+    static constexpr bool kDual = false;
     static constexpr int kIndex = MI;
     static constexpr u64 q = kModulus[MI];
     static constexpr u64 two_q = 2 * kModulus[MI];
@@ -139,6 +140,62 @@ __device__ __forceinline__ u64 shoup(u64 x, u64 w, u64 ws) {
     return csub<M>(shoup_lazy<M>(x, w, ws), M::q);
 }
 
+// ---------------------------------------------------------------- dual limbs: two primes below 2^30 in one 64-bit word
+// (params.h: kDualPrime).  32-bit Harvey arithmetic: values live in [0, 4s) < 2^32, a product by a precomputed pair
+// (w, ws = floor(w 2^32 / s)) is one IMAD.HI + two IMAD and lands in [0, 2s) for ANY 32-bit operand.
+template <int D>
+struct ModDual {
+    static constexpr bool kDual = true;
+    static constexpr bool kSmall = false;
+    static constexpr int kIndex = kNumMod + D;  // twiddle-table index
+    static constexpr u32 s0 = kDualPrime[2 * D], s1 = kDualPrime[2 * D + 1];
+};
+__device__ __forceinline__ u32 shoup32(u32 x, u32 w, u32 ws, u32 s) { return x * w - __umulhi(x, ws) * s; }  // [0, 2s)
+__device__ __forceinline__ u32 csub32(u32 x, u32 m) { return min(x, x - m); }                                // [0, 2m) -> [0, m)
+// V < 2^61 -> V mod s in [0, 4s): q^ = floor(floor(V / 2^29) mu / 2^32), mu = floor(2^61 / s), is low by at most 3
+__device__ __forceinline__ u32 barrett61(u64 V, u32 mu61, u32 s) { return (u32)V - __umulhi((u32)(V >> 29), mu61) * s; }
+// forward butterfly on both lanes: inputs in [0, 4s), outputs in [0, 4s)
+template <class M>
+__device__ __forceinline__ void dual_fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
+    u32 x0, x1, y0, y1, w0, w1, q0, q1;
+    unpack64(X, x0, x1);
+    unpack64(Y, y0, y1);
+    unpack64(w, w0, w1);
+    unpack64(ws, q0, q1);
+    x0 = csub32(x0, 2 * M::s0), x1 = csub32(x1, 2 * M::s1);
+    const u32 t0 = shoup32(y0, w0, q0, M::s0), t1 = shoup32(y1, w1, q1, M::s1);
+    X = pack64(x0 + t0, x1 + t1);
+    Y = pack64(x0 + 2 * M::s0 - t0, x1 + 2 * M::s1 - t1);
+}
+// inverse butterfly: inputs in [0, 2s), outputs in [0, 2s)
+template <class M>
+__device__ __forceinline__ void dual_inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
+    u32 x0, x1, y0, y1, w0, w1, q0, q1;
+    unpack64(X, x0, x1);
+    unpack64(Y, y0, y1);
+    unpack64(w, w0, w1);
+    unpack64(ws, q0, q1);
+    const u32 d0 = x0 + 2 * M::s0 - y0, d1 = x1 + 2 * M::s1 - y1;
+    X = pack64(csub32(x0 + y0, 2 * M::s0), csub32(x1 + y1, 2 * M::s1));
+    Y = pack64(shoup32(d0, w0, q0, M::s0), shoup32(d1, w1, q1, M::s1));
+}
+// last inverse stage with the output scaling merged in: (X, Y) -> (sc (X + Y), scw (X - Y)), canonical if kCanon
+template <class M, bool kCanon>
+__device__ __forceinline__ void dual_inv_bfly_last(u64 &X, u64 &Y, u64 sc, u64 scs, u64 scw, u64 scws) {
+    u32 x0, x1, y0, y1, a0, a1, b0, b1, c0, c1, e0, e1;
+    unpack64(X, x0, x1);
+    unpack64(Y, y0, y1);
+    unpack64(sc, a0, a1);
+    unpack64(scs, b0, b1);
+    unpack64(scw, c0, c1);
+    unpack64(scws, e0, e1);
+    u32 s_0 = shoup32(x0 + y0, a0, b0, M::s0), s_1 = shoup32(x1 + y1, a1, b1, M::s1);
+    u32 d_0 = shoup32(x0 + 2 * M::s0 - y0, c0, e0, M::s0), d_1 = shoup32(x1 + 2 * M::s1 - y1, c1, e1, M::s1);
+    if (kCanon) s_0 = csub32(s_0, M::s0), s_1 = csub32(s_1, M::s1), d_0 = csub32(d_0, M::s0), d_1 = csub32(d_1, M::s1);
+    X = pack64(s_0, s_1);
+    Y = pack64(d_0, d_1);
+}
+
 // sum_k x_k * w_k mod q for precomputed Shoup pairs (w_k, ws_k): the products' low 64 bits and the quotient estimates
 // H_k are accumulated separately and -(sum H_k) * q is applied once, so a term costs its partial products only and the
 // whole sum one reduction.  Everything is mod 2^64 (wrap-around in either accumulator is harmless) and the result is
@@ -177,6 +234,16 @@ struct ShoupSum {
         unpack64(mul_wide(xl, sh), vl, vh);
         hs = mad_wide(xh, sh, hs) + (u64)uh + (u64)vh;
         low_product(xl, xh, w);
+    }
+    // 32-bit x: exact quotient from two partial products, term in [0, 2q)                               3 wide + 1 low
+    __device__ __forceinline__ void add32(u32 x, u64 w, u64 ws) {
+        u32 sl, sh, wl, wh, al, ah;
+        unpack64(ws, sl, sh);
+        unpack64(w, wl, wh);
+        hs += mad_wide(x, sh, mul_wide(x, sl) >> 32) >> 32;  // floor(x ws / 2^64), exact
+        unpack64(mad_wide(x, wl, lo), al, ah);
+        ah = mad_lo(x, wh, ah);
+        lo = pack64(al, ah);
     }
     // x * w for a small x (the product itself stays far below 2^64: no quotient term)                  1 wide + 1 low
     __device__ __forceinline__ void add_small(u32 x, u64 w) {

@@ -48,7 +48,9 @@ __device__ __forceinline__ int pass_upper(int t) {
 //                 (3 instructions: q = 2^61 - c) on every third stage.
 template <class M, int G>
 __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
-    if (M::kSmall) {
+    if constexpr (M::kDual) {
+        dual_fwd_bfly<M>(X, Y, w, ws);
+    } else if constexpr (M::kSmall) {
         const u64 Xo = shoup_acc<M, 2>(X, Y, w, ws);  // Y < 2^43 throughout the forward transform
         Y = (X + X + 5 * M::q) - Xo;  // X + 5q - T
         X = Xo;
@@ -66,12 +68,14 @@ __device__ __forceinline__ void fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
 //                 fold X + Y (< 8q) back below 2q.  Y outputs are always < 2q.
 template <class M, int G>
 __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
-    if (M::kSmall) {
+    if constexpr (M::kDual) {
+        dual_inv_bfly<M>(X, Y, w, ws);
+    } else if constexpr (M::kSmall) {
         constexpr u64 K = M::four_q << G;
         const u64 D = X + (K - Y);
         X = X + Y;
         Y = shoup_acc<M, 1>(0, D, w, ws);  // D can reach 2^51: the 16-bit estimate of variant 2 does not apply
-    } else if ((G % 2) == 0) {
+    } else if constexpr ((G % 2) == 0) {
         const u64 D = X + (M::two_q - Y);
         X = X + Y;
         Y = shoup_lazy<M>(D, w, ws);
@@ -121,11 +125,16 @@ __device__ __forceinline__ void fwd_pass(u64 (&v)[NP][8], const ulonglong2 *__re
 // both through exact Shoup multiplications, results in [0, 2q) or canonical
 template <class M, bool kCanon>
 __device__ __forceinline__ void inv_bfly_last(u64 &X, u64 &Y, const Shoup &s, const Shoup &sw) {
+    if constexpr (M::kDual) {
+        dual_inv_bfly_last<M, kCanon>(X, Y, s.w, s.ws, sw.w, sw.ws);
+        return;
+    } else {
     constexpr u64 K = M::kSmall ? (M::four_q << 11) : M::four_q;  // >= the stage's input bound (odd stage: < 4q for 61-bit)
     const u64 D = X + (K - Y);
     const u64 S = X + Y;
     X = kCanon ? shoup<M>(S, s.w, s.ws) : shoup_lazy<M>(S, s.w, s.ws);
     Y = kCanon ? shoup<M>(D, sw.w, sw.ws) : shoup_lazy<M>(D, sw.w, sw.ws);
+    }
 }
 
 // inverse pass over the same register bits, stages in reverse order. G0 = global index of its first stage.
@@ -238,7 +247,7 @@ __device__ __forceinline__ void ntt_forward(u64 (&v)[NP][8], u64 *smem, const ul
         smem_load<NP, 9>(smem, v, t);
     }
     fwd_pass<M, NP, 9>(v, tw, pass_upper<9>(t));
-    if (kCanon) {
+    if constexpr (kCanon && !M::kDual) {
 #pragma unroll
         for (int p = 0; p < NP; p++)
 #pragma unroll

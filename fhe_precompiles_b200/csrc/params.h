@@ -28,6 +28,15 @@ constexpr u64 kModulus[kNumMod] = {
 constexpr u64 kGamma = 0x1ffffffffffce001ull;  // decrypt-only aux prime
 constexpr u64 kMTilde = 1ull << 32;
 
+// The GPU's own auxiliary base for the BEHZ multiply: the result of bfv_multiply is a function of integer
+// polynomials that does not depend on which auxiliary primes carry them, so the tensor product runs on six primes below 2^30
+// (the largest NTT primes there: 1 mod 2N), two per 64-bit word ("dual limb" d holds residues mod kDualPrime[2d] in its low
+// and mod kDualPrime[2d+1] in its high 32 bits): a butterfly is one IMAD.HI + two IMAD per lane on the SM's 32-bit
+// multiplier instead of 6 IMAD.WIDE + 4 IMAD for a 61-bit prime.  Product ~ 2^180 > 2 |t D| (< 2^167).
+constexpr int kNumDual = 3;
+constexpr u32 kDualPrime[2 * kNumDual] = {0x3fff4001u, 0x3ffee001u, 0x3ffea001u, 0x3ffe8001u, 0x3ffd6001u, 0x3ffc0001u};
+constexpr int kNumTab = kNumMod + kNumDual;  // twiddle tables: the six 64-bit-lane moduli, then the three dual limbs
+
 // limb order of the extended BEHZ base q U Bsk used in all 5-limb device buffers
 constexpr int kExtLimb[5] = {MQ0, MQ1, MB0, MB1, MSK};
 
