@@ -673,6 +673,38 @@ __global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_d(u64 *__restrict__ ntt
         default: ntt_dual_body<2>(limb, smem, t); break;
     }
 }
+// A/B variant (FHE_B200_EXT_FUSED=1): base extension and the three dual transforms of one input polynomial in one CTA --
+// the shared part of the extension is computed once per coefficient and kept in registers, so the extended operands never
+// make the round trip through HBM that k_ext_conv_d + k_ext_ntt_d give them.  grid (4 polys, ops), 2 CTAs per SM.
+template <int D>
+__device__ __forceinline__ void ext_ntt_fused_limb(const u64 (&base)[8], const u32 (&mm)[8], u64 *__restrict__ dst, u64 *smem, int t) {
+    using M = ModDual<D>;
+    u64 v[1][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) v[0][r] = ext_dual<D>(base[r], mm[r] & 0x7fffffffu, (mm[r] >> 31) != 0);
+    ntt_forward<M, 1, false, true>(v, smem, kt.twf[M::kIndex], t);
+    store_chunk8(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_ext_ntt_f_d(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int p = blockIdx.x, t = threadIdx.x;
+    const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
+    u64 base[8];
+    u32 mm[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int i = r * kThreads + t;
+        u32 m;
+        bool neg;
+        ext_shared(ct[i], ct[kN + i], base[r], m, neg);
+        mm[r] = m | (neg ? 0x80000000u : 0u);
+    }
+    u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN;
+    ext_ntt_fused_limb<0>(base, mm, dst, smem, t);
+    ext_ntt_fused_limb<1>(base, mm, dst + kN, smem, t);
+    ext_ntt_fused_limb<2>(base, mm, dst + 2 * kN, smem, t);
+}
 // one lane of the dyadic tensor: operands in [0, 4s) -> product(s) mod s in [0, 2s)
 template <int NP>
 __device__ __forceinline__ u32 dual_mulsum(const u32 (&x)[NP], const u32 (&y)[NP], u32 s, u32 mu61) {
@@ -754,13 +786,15 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
     unpack64(w0, r[0], r[1]);
     unpack64(w1, r[2], r[3]);
     unpack64(w2, r[4], r[5]);
+    // v = round(sum y_i / s_i): every s_i is within 2^-12 of 2^30, so y_i / 2^30 (in units of 2^-16: y_i >> 14) is off by
+    // less than 2^-11 per term -- far inside the 1/2 - 2^-13 that the rounding tolerates (|t D| / S < 2^-13)
     u32 est = 1u << 15;
 #pragma unroll
     for (int i = 0; i < 6; i++) {
         y[i] = shoup32(r[i], kc.d_C[i], kc.d_Cs[i], dual_prime(i));  // [(S/s_i)^-1 r_i] in [0, 2s)
-        est += (u32)(mul_wide(y[i], kc.d_R48[i]) >> 32);             // y_i / s_i in units of 2^-16
+        est += y[i] >> 14;
     }
-    const u32 v = est >> 16;  // t D = sum y_i (S/s_i) - v S exactly (|t D| / S < 2^-13)
+    const u32 v = est >> 16;  // t D = sum y_i (S/s_i) - v S exactly
     u64 t0, t1;
     {
         ShoupSum<Q0> s;  // six terms < q + 1 each + v KN < 13 q
@@ -787,7 +821,7 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
         const u32 s = dual_prime(i);
         const u32 yi = csub32(barrett61(mad_wide(u2, kc.d_R58[i], low58), kc.d_mu61[i], s), 2 * s);  // y0 mod s_i in [0, 2s)
         tb[i] = shoup32(r[i] + 2 * s - yi, kc.d_W[i], kc.d_Ws[i], s);                               // [f (S4/s_i)^-1] in [0, 2s)
-        est2 += (u32)(mul_wide(tb[i], kc.d_R48[i]) >> 32);
+        est2 += tb[i] >> 14;
     }
     const u32 vp = est2 >> 16;  // f = sum tb_i (S4/s_i) - v' S4 exactly (|f| / S4 < 2^-24)
     {
@@ -805,7 +839,7 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
         o1 = canon_k32<Q1>(s.value());
     }
 }
-__global__ void __launch_bounds__(256) k_floor_sk_d(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
+__global__ void __launch_bounds__(256, 3) k_floor_sk_d(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
     const size_t total = n_ops * 3 * (kN / 2);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
@@ -1741,10 +1775,18 @@ static int behz_mode_() {
     return mode;
 }
 int behz_mode() { return behz_mode_(); }
+static bool ext_fused_d() {
+    static const bool on = [] {
+        const char *v = getenv("FHE_B200_EXT_FUSED");
+        return v && *v == '1';
+    }();
+    return on;
+}
 static int qlimb_ntt_mode() { return behz_mode_() == 2; }
 bool qlimb_ntt() { return qlimb_ntt_mode() != 0; }
 cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
+    if (behz_mode_() == 0 && ext_fused_d()) return cudaSuccess;  // the fused kernel of launch_ext_ntt does the extension
     if (behz_mode_() == 0) k_ext_conv_d<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
     else k_ext_conv<<<eltwise_grid(n_ops * 4 * (kN / 2), 256), 256, 0, s>>>(a, b, nttbuf, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -1753,7 +1795,8 @@ cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_op
 // with ext_split(): the transforms only (launch_ext_conv must have filled the auxiliary limbs); otherwise extension + transforms
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    if (behz_mode_() == 0) k_ext_ntt_d<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
+    if (behz_mode_() == 0 && ext_fused_d()) k_ext_ntt_f_d<<<dim3(4, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
+    else if (behz_mode_() == 0) k_ext_ntt_d<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
     else if (ext_split_mode() && !qlimb_ntt_mode()) k_ext_ntt2<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 1);
     else if (ext_split_mode()) k_ext_ntt2<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 0);
     else k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
