@@ -314,6 +314,17 @@ void build(HostContext &H) {
         }
     }
 
+    // pass-9 copies (params.h: kTwPass9)
+    for (int ti = 0; ti < kNumTab; ti++)
+        for (auto *tab : {&H.twf[ti], &H.twi[ti]}) {
+            tab->resize(kTwEntries);
+            for (int t = 0; t < 512; t++) {
+                (*tab)[kN + 0 * 512 + t] = (*tab)[512 + t];
+                for (int h = 0; h < 2; h++) (*tab)[kN + (1 + h) * 512 + t] = (*tab)[1024 + 2 * t + h];
+                for (int h = 0; h < 4; h++) (*tab)[kN + (3 + h) * 512 + t] = (*tab)[2048 + 4 * t + h];
+            }
+        }
+
     DevConsts &c = H.dc;
     memset(&c, 0, sizeof(c));
     const u64 q0 = kModulus[MQ0], q1 = kModulus[MQ1], P = kModulus[MP];
@@ -514,7 +525,7 @@ DeviceContext &device_context(int device) {
     cuda_check(cudaSetDevice(device), "cudaSetDevice (no CUDA device? this library has no CPU fallback)");
     if (d.device == device) return d;
     const HostContext &H = HostContext::get();
-    const size_t per = (size_t)kN * sizeof(ulonglong2);
+    const size_t per = (size_t)kTwEntries * sizeof(ulonglong2);
     void *mem = nullptr;
     cuda_check(cudaMalloc(&mem, per * kNumTab * 2), "cudaMalloc(twiddles)");
     for (int mi = 0; mi < kNumTab; mi++) {

@@ -653,14 +653,15 @@ __global__ void __launch_bounds__(256) k_ext_conv_d(const u64 *__restrict__ a, c
         *reinterpret_cast<ulonglong2 *>(dst + 2 * kN) = make_ulonglong2(ext_dual<2>(base0, m0, neg0), ext_dual<2>(base1, m1, neg1));
     }
 }
-template <int D>
+template <int D, bool SHFL>
 __device__ __forceinline__ void ntt_dual_body(u64 *__restrict__ limb, u64 *smem, int t) {
     using M = ModDual<D>;
     u64 v[1][8];
     load_natural(limb, v[0], t);
-    ntt_forward<M, 1, false, false>(v, smem, kt.twf[M::kIndex], t);  // values stay in [0, 4s)
+    ntt_forward<M, 1, false, false, SHFL>(v, smem, kt.twf[M::kIndex], t);  // values stay in [0, 4s)
     store_chunk8(limb, v[0], t);
 }
+template <bool SHFL>
 __global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_d(u64 *__restrict__ nttbuf) {
     extern __shared__ __align__(16) u64 smem[];
     const size_t op = blockIdx.y;
@@ -668,9 +669,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_d(u64 *__restrict__ ntt
     u64 *limb = nttbuf + (op * 20 + (size_t)(p * 5 + 2 + d)) * kN;
     const int t = threadIdx.x;
     switch (d) {
-        case 0: ntt_dual_body<0>(limb, smem, t); break;
-        case 1: ntt_dual_body<1>(limb, smem, t); break;
-        default: ntt_dual_body<2>(limb, smem, t); break;
+        case 0: ntt_dual_body<0, SHFL>(limb, smem, t); break;
+        case 1: ntt_dual_body<1, SHFL>(limb, smem, t); break;
+        default: ntt_dual_body<2, SHFL>(limb, smem, t); break;
     }
 }
 // A/B variant (FHE_B200_EXT_FUSED=1): base extension and the three dual transforms of one input polynomial in one CTA --
@@ -716,7 +717,7 @@ __device__ __forceinline__ u32 dual_mulsum(const u32 (&x)[NP], const u32 (&y)[NP
     }
     return csub32(barrett61(P, mu61, s), 2 * s);
 }
-template <int D>
+template <int D, bool SHFL>
 __device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb, int d, u64 *__restrict__ dst, u64 *smem, int t) {
     using M = ModDual<D>;
     constexpr int E = 2 + D;
@@ -758,9 +759,10 @@ __device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb
             v[0][2 * r + 1] = one(x.y, y.y);
         }
     }
-    ntt_inverse<M, 1, false, false>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv_t[D], kc.d_ninv_t_w[D]);  // [0, 2s)
+    ntt_inverse<M, 1, false, false, SHFL>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv_t[D], kc.d_ninv_t_w[D]);  // [0, 2s)
     store_natural(dst, v[0], t);
 }
+template <bool SHFL>
 __global__ void __launch_bounds__(kThreads, 3) k_tensor_intt_d(const u64 *__restrict__ nttbuf, u64 *__restrict__ tens) {
     extern __shared__ __align__(16) u64 smem[];
     const size_t op = blockIdx.y;
@@ -769,9 +771,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_tensor_intt_d(const u64 *__rest
     u64 *dst = tens + (op * 15 + (size_t)(d * 5 + 2 + e)) * kN;
     const int t = threadIdx.x;
     switch (e) {
-        case 0: tensor_intt_dual_body<0>(nb, d, dst, smem, t); break;
-        case 1: tensor_intt_dual_body<1>(nb, d, dst, smem, t); break;
-        default: tensor_intt_dual_body<2>(nb, d, dst, smem, t); break;
+        case 0: tensor_intt_dual_body<0, SHFL>(nb, d, dst, smem, t); break;
+        case 1: tensor_intt_dual_body<1, SHFL>(nb, d, dst, smem, t); break;
+        default: tensor_intt_dual_body<2, SHFL>(nb, d, dst, smem, t); break;
     }
 }
 __device__ __forceinline__ u32 dual_prime(int i) {
@@ -1775,6 +1777,13 @@ static int behz_mode_() {
     return mode;
 }
 int behz_mode() { return behz_mode_(); }
+static bool dual_shfl() {  // the last exchange of the dual transforms through warp shuffles instead of shared memory (A/B)
+    static const bool on = [] {
+        const char *v = getenv("FHE_B200_DUAL_SHFL");
+        return v && *v == '1';
+    }();
+    return on;
+}
 static bool ext_fused_d() {
     static const bool on = [] {
         const char *v = getenv("FHE_B200_EXT_FUSED");
@@ -1796,7 +1805,8 @@ cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_op
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
     if (behz_mode_() == 0 && ext_fused_d()) k_ext_ntt_f_d<<<dim3(4, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
-    else if (behz_mode_() == 0) k_ext_ntt_d<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
+    else if (behz_mode_() == 0 && dual_shfl()) k_ext_ntt_d<true><<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
+    else if (behz_mode_() == 0) k_ext_ntt_d<false><<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
     else if (ext_split_mode() && !qlimb_ntt_mode()) k_ext_ntt2<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 1);
     else if (ext_split_mode()) k_ext_ntt2<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 0);
     else k_ext_ntt<<<dim3(20, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
@@ -1805,7 +1815,8 @@ cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops
 }
 cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    if (behz_mode_() == 0) k_tensor_intt_d<<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
+    if (behz_mode_() == 0 && dual_shfl()) k_tensor_intt_d<true><<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
+    else if (behz_mode_() == 0) k_tensor_intt_d<false><<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
     else if (qlimb_ntt_mode()) k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 0);
     else k_tensor_intt<<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 1);
     g_launches.fetch_add(1, std::memory_order_relaxed);

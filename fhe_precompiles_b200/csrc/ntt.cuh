@@ -91,6 +91,13 @@ __device__ __forceinline__ void inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
 template <class M, bool kInv, int S0>
 __device__ __forceinline__ ulonglong2 ldtw(const ulonglong2 *__restrict__ tw, int i) {
     if (S0 <= 3) return kInv ? ktl.i[M::kIndex][i] : ktl.f[M::kIndex][i];
+    if (S0 == 9) {
+        // the pass that owns stages 9..11: the slot-major copy behind the table (params.h kTwPass9), coalesced per warp.
+        // i = 512 + t, 1024 + 2t + h or 2048 + 4t + h with h a compile-time constant after unrolling
+        const int lvl = i >= 2048 ? 2 : (i >= 1024 ? 1 : 0);
+        const int t = (i - (512 << lvl)) >> lvl, h = i & ((1 << lvl) - 1);
+        return __ldg(tw + kN + ((1 << lvl) - 1 + h) * 512 + t);
+    }
     return __ldg(tw + i);
 }
 

@@ -35,6 +35,11 @@ constexpr u64 kMTilde = 1ull << 32;
 // multiplier instead of 6 IMAD.WIDE + 4 IMAD for a 61-bit prime.  Product ~ 2^180 > 2 |t D| (< 2^167).
 constexpr int kNumDual = 3;
 constexpr u32 kDualPrime[2 * kNumDual] = {0x3fff4001u, 0x3ffee001u, 0x3ffea001u, 0x3ffe8001u, 0x3ffd6001u, 0x3ffc0001u};
+// every twiddle table has kN entries in SEAL's bit-reversed order followed by a copy of entries 512..4095 regrouped for the
+// transform pass that owns stages 9..11 (thread t needs entries 512+t, 1024+2t+h, 2048+4t+h): slot-major [7][512], so that a
+// warp's loads are contiguous 512-byte runs instead of 32 sectors scattered over 2 KiB
+constexpr int kTwPass9 = 7 * 512;
+constexpr int kTwEntries = kN + kTwPass9;
 constexpr int kNumTab = kNumMod + kNumDual;  // twiddle tables: the six 64-bit-lane moduli, then the three dual limbs
 
 // limb order of the extended BEHZ base q U Bsk used in all 5-limb device buffers
