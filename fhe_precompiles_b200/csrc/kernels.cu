@@ -336,7 +336,7 @@ __device__ __forceinline__ void ext_ntt_body(const u64 *__restrict__ ct, int pol
     load_extended<EI>(ct, poly, v[0], t);
     // 36-bit limbs stay lazy (< 2^43): the tensor's 128-bit accumulate absorbs it; 61-bit limbs must be canonical
     ntt_forward<M, 1, !M::kSmall, false>(v, smem, kt.twf[MI], t);
-    store_chunk8(dst, v[0], t);
+    store_chunk8_lm(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt(const u64 *__restrict__ a, const u64 *__restrict__ b,
                                                           u64 *__restrict__ nttbuf) {
@@ -391,7 +391,7 @@ __device__ __forceinline__ void ntt_only_body(const u64 *__restrict__ src, u64 *
     u64 v[1][8];
     load_natural(src, v[0], t);
     ntt_forward<M, 1, !M::kSmall, false>(v, smem, kt.twf[MI], t);
-    store_chunk8(dst, v[0], t);
+    store_chunk8_lm(dst, v[0], t);
 }
 // aux_only (default): grid (12, ops), the Bsk limbs only -- the q-limbs of the tensor product are recovered from its Bsk
 // limbs in k_floor_sk (exactly), so the q-limbs of the operands are never transformed.  Otherwise grid (20, ops).
@@ -422,12 +422,11 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
     const u64 *b0 = nb + (size_t)(2 * 5 + EI) * kN, *b1 = nb + (size_t)(3 * 5 + EI) * kN;
     u64 v[1][8];
     // two coefficients at a time, so that the products do not keep 32 operands live
-    const ulonglong2 *pa0 = reinterpret_cast<const ulonglong2 *>(a0 + 8 * t), *pa1 = reinterpret_cast<const ulonglong2 *>(a1 + 8 * t);
-    const ulonglong2 *pb0 = reinterpret_cast<const ulonglong2 *>(b0 + 8 * t), *pb1 = reinterpret_cast<const ulonglong2 *>(b1 + 8 * t);
+    const ulonglong2 *pa0 = lm_ptr(a0, t), *pa1 = lm_ptr(a1, t), *pb0 = lm_ptr(b0, t), *pb1 = lm_ptr(b1, t);  // pair r at [r * kLm]
     if (d == 1) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const ulonglong2 x0 = pa0[r], y1 = pb1[r], x1 = pa1[r], y0 = pb0[r];
+            const ulonglong2 x0 = pa0[r * kLm], y1 = pb1[r * kLm], x1 = pa1[r * kLm], y0 = pb0[r * kLm];
             {
                 const u64 xs[2] = {x0.x, x1.x}, ys[2] = {y1.x, y0.x};
                 v[0][2 * r] = mulsum<M, 2>(xs, ys);
@@ -441,7 +440,7 @@ __device__ __forceinline__ void tensor_intt_body(const u64 *__restrict__ nb, int
         const ulonglong2 *px = d == 0 ? pa0 : pa1, *py = d == 0 ? pb0 : pb1;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const ulonglong2 x = px[r], y = py[r];
+            const ulonglong2 x = px[r * kLm], y = py[r * kLm];
             {
                 const u64 xs[1] = {x.x}, ys[1] = {y.x};
                 v[0][2 * r] = mulsum<M, 1>(xs, ys);
@@ -659,7 +658,7 @@ __device__ __forceinline__ void ntt_dual_body(u64 *__restrict__ limb, u64 *smem,
     u64 v[1][8];
     load_natural(limb, v[0], t);
     ntt_forward<M, 1, false, false, SHFL>(v, smem, kt.twf[M::kIndex], t);  // values stay in [0, 4s)
-    store_chunk8(limb, v[0], t);
+    store_chunk8_lm(limb, v[0], t);
 }
 template <bool SHFL>
 __global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_d(u64 *__restrict__ nttbuf) {
@@ -684,7 +683,7 @@ __device__ __forceinline__ void ext_ntt_fused_limb(const u64 (&base)[8], const u
 #pragma unroll
     for (int r = 0; r < 8; r++) v[0][r] = ext_dual<D>(base[r], mm[r] & 0x7fffffffu, (mm[r] >> 31) != 0);
     ntt_forward<M, 1, false, true>(v, smem, kt.twf[M::kIndex], t);
-    store_chunk8(dst, v[0], t);
+    store_chunk8_lm(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 2) k_ext_ntt_f_d(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf) {
     extern __shared__ __align__(16) u64 smem[];
@@ -725,8 +724,7 @@ __device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb
     const u64 *b0 = nb + (size_t)(2 * 5 + E) * kN, *b1 = nb + (size_t)(3 * 5 + E) * kN;
     const u32 mu0 = kc.d_mu61[2 * D], mu1 = kc.d_mu61[2 * D + 1];
     u64 v[1][8];
-    const ulonglong2 *pa0 = reinterpret_cast<const ulonglong2 *>(a0 + 8 * t), *pa1 = reinterpret_cast<const ulonglong2 *>(a1 + 8 * t);
-    const ulonglong2 *pb0 = reinterpret_cast<const ulonglong2 *>(b0 + 8 * t), *pb1 = reinterpret_cast<const ulonglong2 *>(b1 + 8 * t);
+    const ulonglong2 *pa0 = lm_ptr(a0, t), *pa1 = lm_ptr(a1, t), *pb0 = lm_ptr(b0, t), *pb1 = lm_ptr(b1, t);  // pair r at [r * kLm]
     auto one = [&](u64 x0, u64 y0) -> u64 {
         u32 xl, xh, yl, yh;
         unpack64(x0, xl, xh);
@@ -746,7 +744,7 @@ __device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb
     if (d == 1) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const ulonglong2 x0 = pa0[r], y1 = pb1[r], x1 = pa1[r], y0 = pb0[r];
+            const ulonglong2 x0 = pa0[r * kLm], y1 = pb1[r * kLm], x1 = pa1[r * kLm], y0 = pb0[r * kLm];
             v[0][2 * r] = two(x0.x, y1.x, x1.x, y0.x);
             v[0][2 * r + 1] = two(x0.y, y1.y, x1.y, y0.y);
         }
@@ -754,7 +752,7 @@ __device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb
         const ulonglong2 *px = d == 0 ? pa0 : pa1, *py = d == 0 ? pb0 : pb1;
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-            const ulonglong2 x = px[r], y = py[r];
+            const ulonglong2 x = px[r * kLm], y = py[r * kLm];
             v[0][2 * r] = one(x.x, y.x);
             v[0][2 * r + 1] = one(x.y, y.y);
         }
@@ -915,7 +913,7 @@ __device__ __forceinline__ void digit_ntt_body(const u64 *__restrict__ src, u64 
     u64 v[1][8];
     load_natural(src, v[0], t);
     ntt_forward<M, 1, false, false>(v, smem, kt.twf[MI], t);  // lazy (< 2^43): the key MAC reduces a 128-bit sum anyway
-    store_chunk8(dst, v[0], t);
+    store_chunk8_lm(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 3) k_digit_ntt(const u64 *__restrict__ c3, u64 *__restrict__ dig) {
     extern __shared__ __align__(16) u64 smem[];
@@ -996,7 +994,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_digit_ntt_tma(const u6
                 case 1: ntt_forward<Mod<MQ1>, 1, false, false>(v, smem + (it & 1) * kN, kt.twf[MQ1], t); break;
                 default: ntt_forward<Mod<MP>, 1, false, false>(v, smem + (it & 1) * kN, kt.twf[MP], t); break;
             }
-            store_chunk8(dig + (size_t)(blockIdx.x + it * gridDim.x) * kN, v[0], t);
+            store_chunk8_lm(dig + (size_t)(blockIdx.x + it * gridDim.x) * kN, v[0], t);
         }
     }
 }
@@ -1006,8 +1004,8 @@ __device__ __forceinline__ void ks_intt_body(const u64 *__restrict__ dg, const u
                                              u64 *smem, int t) {
     using M = Mod<MI>;
     u64 d0[8], d1[8], k0[8], k1[8];
-    load_chunk8(dg + (size_t)(0 * 3 + MI) * kN, d0, t);
-    load_chunk8(dg + (size_t)(1 * 3 + MI) * kN, d1, t);
+    load_chunk8_lm(dg + (size_t)(0 * 3 + MI) * kN, d0, t);
+    load_chunk8_lm(dg + (size_t)(1 * 3 + MI) * kN, d1, t);
     load_chunk8_ldg(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN, k0, t);
     load_chunk8_ldg(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN, k1, t);
     u64 v[1][8];
@@ -1042,13 +1040,12 @@ template <int MI>
 __device__ __forceinline__ void ks_mac_intt(const u64 *__restrict__ dg, const u64 *__restrict__ rk, int k, u64 (&v)[1][8], u64 *smem,
                                             int t) {
     using M = Mod<MI>;
-    const ulonglong2 *pd0 = reinterpret_cast<const ulonglong2 *>(dg + (size_t)(0 * 3 + MI) * kN + 8 * t);
-    const ulonglong2 *pd1 = reinterpret_cast<const ulonglong2 *>(dg + (size_t)(1 * 3 + MI) * kN + 8 * t);
+    const ulonglong2 *pd0 = lm_ptr(dg + (size_t)(0 * 3 + MI) * kN, t), *pd1 = lm_ptr(dg + (size_t)(1 * 3 + MI) * kN, t);  // pair r at [r * kLm]
     const ulonglong2 *pk0 = reinterpret_cast<const ulonglong2 *>(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN + 8 * t);
     const ulonglong2 *pk1 = reinterpret_cast<const ulonglong2 *>(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN + 8 * t);
 #pragma unroll
     for (int r = 0; r < 4; r++) {  // two coefficients at a time: 16 operand registers live instead of 64
-        const ulonglong2 x0 = pd0[r], x1 = pd1[r], y0 = __ldg(pk0 + r), y1 = __ldg(pk1 + r);
+        const ulonglong2 x0 = pd0[r * kLm], x1 = pd1[r * kLm], y0 = __ldg(pk0 + r), y1 = __ldg(pk1 + r);
         {
             const u64 xs[2] = {x0.x, x1.x}, ys[2] = {y0.x, y1.x};
             v[0][2 * r] = mulsum<M, 2>(xs, ys);

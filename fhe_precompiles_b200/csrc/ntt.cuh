@@ -319,6 +319,26 @@ __device__ __forceinline__ void load_chunk8_ldg(const u64 *__restrict__ g, u64 (
         v[2 * r + 1] = x.y;
     }
 }
+// The library's own NTT-domain scratch limbs (extended operands, key-switch digits: never seen outside) use a LANE-MAJOR chunk
+// layout instead: pair j of thread t -- NTT positions 8t + 2j and 8t + 2j + 1 -- lives in 16-byte slot j * 512 + t, so a warp
+// reads or writes one contiguous 512-byte run per instruction instead of 32 pieces of 16 bytes spread over 2 KiB (the
+// transforms are L1-wavefront bound once the arithmetic is cheap).
+constexpr int kLm = kThreads;  // slot distance between a thread's consecutive pairs
+__device__ __forceinline__ const ulonglong2 *lm_ptr(const u64 *__restrict__ g, int t) { return reinterpret_cast<const ulonglong2 *>(g) + t; }
+__device__ __forceinline__ void store_chunk8_lm(u64 *__restrict__ g, const u64 (&v)[8], int t) {
+    ulonglong2 *p = reinterpret_cast<ulonglong2 *>(g) + t;
+#pragma unroll
+    for (int j = 0; j < 4; j++) p[j * kLm] = make_ulonglong2(v[2 * j], v[2 * j + 1]);
+}
+__device__ __forceinline__ void load_chunk8_lm(const u64 *__restrict__ g, u64 (&v)[8], int t) {
+    const ulonglong2 *p = lm_ptr(g, t);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const ulonglong2 x = p[j * kLm];
+        v[2 * j] = x.x;
+        v[2 * j + 1] = x.y;
+    }
+}
 __device__ __forceinline__ void store_chunk8(u64 *__restrict__ g, const u64 (&v)[8], int t) {
     ulonglong2 *p = reinterpret_cast<ulonglong2 *>(g + 8 * t);
 #pragma unroll
