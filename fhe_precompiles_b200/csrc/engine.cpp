@@ -519,7 +519,8 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
         // 296 resident ones (the 128-op chunks of the host-buffer pipelines included), three times the critical path for a
         // single call or a small tile
         if (ks_finish_fused() && c >= 96) {
-            TIMED(9, launch_ks_finish(m.dig, rk, c3, out, c, s), "ks_finish");
+            // m.ks (6 limbs per op) is free on this path: it holds the lane-major copy of the key
+            TIMED(9, launch_ks_finish(m.dig, rk, c3, out, c, s, m.ks), "ks_finish");
             return;
         }
         TIMED(7, launch_ks_intt(m.dig, rk, m.ks, c, s), "ks_intt");

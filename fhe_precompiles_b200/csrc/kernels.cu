@@ -1036,16 +1036,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks_intt(const u64 *__restrict__
 // The CTA runs the three moduli in the order P, q0, q1: a thread owns the same eight coefficients (r*512 + t) after every
 // inverse transform, so the P-limb values needed by the rounded division stay in its registers and the key-switch result
 // never goes through the [op][2][3][N] scratch (FHE_B200_KS_FINISH=0 selects the two separate kernels).
-template <int MI>
+template <int MI, bool KLM>
 __device__ __forceinline__ void ks_mac_intt(const u64 *__restrict__ dg, const u64 *__restrict__ rk, int k, u64 (&v)[1][8], u64 *smem,
                                             int t) {
     using M = Mod<MI>;
+    constexpr int ks = KLM ? kLm : 1;  // KLM: the key is a lane-major copy (k_rk_lm), else the key file's order
     const ulonglong2 *pd0 = lm_ptr(dg + (size_t)(0 * 3 + MI) * kN, t), *pd1 = lm_ptr(dg + (size_t)(1 * 3 + MI) * kN, t);  // pair r at [r * kLm]
-    const ulonglong2 *pk0 = reinterpret_cast<const ulonglong2 *>(rk + (size_t)((0 * 2 + k) * 3 + MI) * kN + 8 * t);
-    const ulonglong2 *pk1 = reinterpret_cast<const ulonglong2 *>(rk + (size_t)((1 * 2 + k) * 3 + MI) * kN + 8 * t);
+    const u64 *k0 = rk + (size_t)((0 * 2 + k) * 3 + MI) * kN, *k1 = rk + (size_t)((1 * 2 + k) * 3 + MI) * kN;
+    const ulonglong2 *pk0 = KLM ? lm_ptr(k0, t) : reinterpret_cast<const ulonglong2 *>(k0 + 8 * t);
+    const ulonglong2 *pk1 = KLM ? lm_ptr(k1, t) : reinterpret_cast<const ulonglong2 *>(k1 + 8 * t);
 #pragma unroll
     for (int r = 0; r < 4; r++) {  // two coefficients at a time: 16 operand registers live instead of 64
-        const ulonglong2 x0 = pd0[r * kLm], x1 = pd1[r * kLm], y0 = __ldg(pk0 + r), y1 = __ldg(pk1 + r);
+        const ulonglong2 x0 = pd0[r * kLm], x1 = pd1[r * kLm], y0 = __ldg(pk0 + r * ks), y1 = __ldg(pk1 + r * ks);
         {
             const u64 xs[2] = {x0.x, x1.x}, ys[2] = {y0.x, y1.x};
             v[0][2 * r] = mulsum<M, 2>(xs, ys);
@@ -1069,6 +1071,13 @@ __device__ __forceinline__ void ks_finish_limb(const u64 (&v)[8], const u64 *las
         po[r * kThreads + t] = canon_k32<Q>(shoup_acc<Q, 2>(pc[r * kThreads + t], d, kc.inv_P_mod_q[L].w, kc.inv_P_mod_q[L].ws));
     }
 }
+// the relinearisation key regrouped into the lane-major chunk layout (12 limbs, once per chunk of ops)
+__global__ void __launch_bounds__(kThreads) k_rk_lm(const u64 *__restrict__ rk, u64 *__restrict__ out) {
+    u64 v[8];
+    load_chunk8_ldg(rk + (size_t)blockIdx.x * kN, v, threadIdx.x);
+    store_chunk8_lm(out + (size_t)blockIdx.x * kN, v, threadIdx.x);
+}
+template <bool KLM>
 __global__ void __launch_bounds__(kThreads, 2) k_ks_finish(const u64 *__restrict__ dig, const u64 *__restrict__ rk,
                                                             const u64 *__restrict__ c3, u64 *__restrict__ out) {
     extern __shared__ __align__(16) u64 smem[];
@@ -1080,18 +1089,18 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks_finish(const u64 *__restrict
     u64 *po = out + (op * 2 + k) * 2 * kN;
     {
         u64 v[1][8];
-        ks_mac_intt<MP>(dg, rk, k, v, smem, t);
+        ks_mac_intt<MP, KLM>(dg, rk, k, v, smem, t);
 #pragma unroll
         for (int r = 0; r < 8; r++) last[r * kThreads + t] = csub<Mod<MP>>(v[0][r] + kc.half_P, Mod<MP>::q);
     }
     {
         u64 v[1][8];
-        ks_mac_intt<MQ0>(dg, rk, k, v, smem, t);
+        ks_mac_intt<MQ0, KLM>(dg, rk, k, v, smem, t);
         ks_finish_limb<MQ0>(v[0], last, pc, po, t);
     }
     {
         u64 v[1][8];
-        ks_mac_intt<MQ1>(dg, rk, k, v, smem, t);
+        ks_mac_intt<MQ1, KLM>(dg, rk, k, v, smem, t);
         ks_finish_limb<MQ1>(v[0], last, pc + kN, po + kN, t);
     }
 }
@@ -1682,7 +1691,9 @@ cudaError_t kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_digit_ntt_tma<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_ks_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    e = cudaFuncSetAttribute(k_ks_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ks_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
@@ -1852,10 +1863,16 @@ static int ks_finish_mode() {
     return mode;
 }
 bool ks_finish_fused() { return ks_finish_mode() != 0; }
-cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s) {
+cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s, u64 *rk_lm) {
     if (n_ops == 0) return cudaSuccess;
-    k_ks_finish<<<dim3(2, (unsigned)n_ops), kThreads, kSmem2, s>>>(dig, rk, c3, out);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (rk_lm) {  // room for a lane-major copy of the key (12 limbs): coalesced key reads in the MAC
+        k_rk_lm<<<12, kThreads, 0, s>>>(rk, rk_lm);
+        k_ks_finish<true><<<dim3(2, (unsigned)n_ops), kThreads, kSmem2, s>>>(dig, rk_lm, c3, out);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+    } else {
+        k_ks_finish<false><<<dim3(2, (unsigned)n_ops), kThreads, kSmem2, s>>>(dig, rk, c3, out);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_decrypt(const u64 *ct, const u64 *sk, u64 *xbuf, unsigned short *plain, size_t n_ops, cudaStream_t s,

@@ -51,7 +51,8 @@ cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops,
 int behz_mode();        // 0 dual base (default), 1 SEAL's Bsk primes + q-limb recovery, 2 SEAL's form (FHE_B200_BEHZ=dual|bsk|seal)
 bool qlimb_ntt();       // FHE_B200_QLIMB_NTT=1: transform the q-limbs of the tensor product as SEAL does instead of recovering them from the Bsk limbs
 bool ks_finish_fused();  // default: key-switch MAC + inverse transforms + rounded division by P in one kernel (FHE_B200_KS_FINISH=0: two)
-cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s);
+// rk_lm: optional scratch of 12 limbs for a lane-major copy of the key (made on the stream before the kernel)
+cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s, u64 *rk_lm = nullptr);
 cudaError_t launch_relin_finish(const u64 *c3, const u64 *ks, u64 *out, size_t n_ops, cudaStream_t s);
 
 uint64_t launch_count();
