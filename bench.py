@@ -26,9 +26,14 @@ N = 4096
 Q = (0xFFFFEE001, 0xFFFFC4001)
 CT_BYTES = 2 * 2 * N * 8  # 131,072
 ALGO_BYTES_PER_OP = 3 * CT_BYTES  # read a, read b, write result = 393,216 B
-# SEAL's form runs 47 limb-NTTs x 24,576 butterflies per op; the default here runs 33 (the 14 q-limb transforms of
-# the BEHZ tensor product are replaced by an exact recovery of its q-limbs from its Bsk limbs)
-QLIMB_NTT = os.environ.get("FHE_B200_QLIMB_NTT") == "1"
+# SEAL's form runs 47 limb-NTTs x 24,576 butterflies per op.  The library computes the same bits three ways
+# (FHE_B200_BEHZ): "dual" (default) carries the BEHZ tensor product on six primes below 2^30, two per
+# 64-bit word (21 dual transforms + 12 key-switch transforms); "bsk" on SEAL's three 61-bit primes with the q-limbs recovered
+# from them (33 transforms); "seal" transforms the q-limbs too (47).
+BEHZ = "seal" if os.environ.get("FHE_B200_QLIMB_NTT") == "1" else os.environ.get("FHE_B200_BEHZ", "dual")
+if BEHZ not in ("dual", "bsk", "seal"):
+    BEHZ = "dual"
+QLIMB_NTT = BEHZ == "seal"
 NTTS_PER_OP = 47 if QLIMB_NTT else 33
 BUTTERFLIES_PER_OP = NTTS_PER_OP * 24576
 # Integer-pipe roofline.  The binding resource is the SM's 32-bit multiplier (the "heavy" half of the FMA pipe): IMAD.WIDE /
@@ -48,19 +53,27 @@ BUTTERFLIES_PER_OP = NTTS_PER_OP * 24576
 #   terms, 4 x 1.5 reductions, 4 for the punctured sum and its folds) against 113 for SEAL's step-by-step form.
 #   pointwise (base conversions in the integer domain, tensor, key-switch MAC, division by P), per kernel below.
 # Per kernel (what bench.py's live CUDA-event timing is divided into):
-if QLIMB_NTT:
+if BEHZ == "seal":
     KERNEL_WIDE_EQ = {
         "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
         "k_ext_ntt": 24576 * (8 * 6.5 + 12 * 7.5),                   # 20 forward NTTs: 8 on q limbs, 12 on the Bsk limbs
         "k_tensor_intt": 24576 * (6 * 7.0 + 9 * 7.5) + 0.51e6,       # 15 inverse NTTs + the dyadic tensor
         "k_floor_sk": 113.0 * 12288,                                 # fast_floor + fastbconv_sk per coefficient of the 3 output polys
     }
-else:
+elif BEHZ == "bsk":
     KERNEL_WIDE_EQ = {
         "k_ext_conv": 42.5 * 16384,                                  # fastbconv_m_tilde + sm_mrq per coefficient of the 4 input polys
         "k_ext_ntt": 24576 * 12 * 7.5,                               # 12 forward NTTs on the Bsk limbs
         "k_tensor_intt": 24576 * 9 * 7.5 + 0.36e6,                   # 9 inverse NTTs + the dyadic tensor on the Bsk limbs
         "k_floor_sk": 98.5 * 12288,                                  # q-limb recovery + fast_floor + exact lift from (b0, b1) per coefficient
+    }
+else:
+    # dual base: one butterfly = two 32-bit Shoup products (IMAD.HI + 2 IMAD each) = 4 IMAD.WIDE-equivalents for both lanes
+    KERNEL_WIDE_EQ = {
+        "k_ext_conv": (36.5 + 6 * 3.5) * 16384,                      # shared part of the extension + 6 residues (2 wide + Barrett each)
+        "k_ext_ntt": 24576 * 12 * 4.0,                               # 12 forward dual transforms
+        "k_tensor_intt": 24576 * 9 * 4.0 + 9 * 2048 * 4.0 + 17.0 * 12288,  # 9 inverse dual transforms (scaled last stage) + dyadic tensor
+        "k_floor_sk": 115.0 * 12288,                                 # 6-prime CRT -> t_l (12 sum terms), y0 mod 4 primes, 4-prime lift (8 sum terms)
     }
 KERNEL_WIDE_EQ.update({
     "k_digit_ntt": 24576 * 6 * 6.5,                              # 6 key-switch digit NTTs
@@ -795,9 +808,16 @@ def main() -> None:
             prof = json.load(f)
     except Exception:
         prof = {}
-    table = prof.get("dram_bytes_per_op", {})
-    ncu_name = "k_ext_ntt2" if dom == "k_ext_ntt" and "k_ext_ntt2" in table else dom  # the timed slot k_ext_ntt runs k_ext_ntt2
-    traffic = table[ncu_name] * ops_per_launch if ncu_name in table else None
+    def slot_of(ncu_kernel: str) -> str:
+        """timed slot of an ncu kernel name: k_ext_ntt2 / k_ext_ntt_d<0> -> k_ext_ntt, k_ks_finish<1> -> k_ks_finish, ..."""
+        k = ncu_kernel.split("<")[0]
+        if k.endswith("_d"):
+            k = k[:-2]
+        return "k_ext_ntt" if k == "k_ext_ntt2" else k
+
+    table = {slot_of(k): v for k, v in prof.get("dram_bytes_per_op", {}).items()}
+    heavy = {slot_of(k): v for k, v in (prof.get("fmaheavy_pct") or {}).items()}
+    traffic = table[dom] * ops_per_launch if dom in table else None
     sm_clock_ghz = (clocks.get("sm_mhz") or 1965.0) / 1e3
     peak_theory = SM_COUNT * WIDE_PER_CLK_PER_SM * sm_clock_ghz / 1e3  # T IMAD.WIDE/s at the clock observed under load
     try:
@@ -817,8 +837,8 @@ def main() -> None:
             per_kernel[k] = {"us_per_op": kms * 1e3 / (n * args.steps), "achieved": ach_k, "frac": ach_k / peak_wide,
                              "frac_of_theoretical": ach_k / peak_theory,
                              "share_of_step": kms / total_kernel_ms,
-                             "ncu_fmaheavy_pct": (prof.get("fmaheavy_pct") or {}).get("k_ext_ntt2" if k == "k_ext_ntt" else k)}
-    ntt_floor_us = 24576 * ((26 if QLIMB_NTT else 12) / bf_small + 21 / bf_big) * 1e-3
+                             "ncu_fmaheavy_pct": heavy.get(k)}
+    ntt_floor_us = 24576 * ((26 if QLIMB_NTT else 12) / bf_small + 21 / bf_big) * 1e-3  # 64-bit-lane butterfly rates (SEAL's primes)
     hbm_ach = ops_per_launch * ALGO_BYTES_PER_OP / (avg_launch_ms * 1e-3) / 1e9
     roofline = {
         "bound": "int_pipe",
@@ -833,9 +853,12 @@ def main() -> None:
         "frac_of_theoretical": ach_dom / peak_theory if ach_dom else None,
         "algorithmic_wide_eq_per_op": {"dominant_kernel": dom_weq, "whole_op": WIDE_EQ_PER_OP,
                                        "limb_ntts_per_op": NTTS_PER_OP,
-                                       "model": ("SEAL's form, 14+12 fwd / 12+9 inv" if QLIMB_NTT else
-                                                 "q-limbs of the tensor product recovered from its Bsk limbs (no q-limb transforms there): 6+12 fwd / 6+9 inv")
-                                                + " limb-NTTs x 24,576 butterflies at 6.5 / 7.0 (36-37 bit) and 7.5 (61 bit) "
+                                       "behz": BEHZ,
+                                       "model": {"seal": "SEAL's form, 14+12 fwd / 12+9 inv limb-NTTs",
+                                                 "bsk": "q-limbs of the tensor product recovered from its Bsk limbs: 6+12 fwd / 6+9 inv limb-NTTs",
+                                                 "dual": "tensor product on six primes below 2^30, two per word: 12 fwd + 9 inv dual transforms at 4.0 "
+                                                         "IMAD.WIDE-equivalents per butterfly (both lanes), 6 fwd + 6 inv key-switch limb-NTTs"}[BEHZ]
+                                                + " x 24,576 butterflies at 6.5 / 7.0 (36-37 bit) and 7.5 (61 bit) "
                                                 "IMAD.WIDE-equivalents + pointwise per kernel (bench.py KERNEL_WIDE_EQ, DESIGN.md section 4)"},
         "whole_op": {"achieved": ach_op, "frac": ach_op / peak_wide, "frac_of_theoretical": ach_op / peak_theory, "us_per_op": 1e6 / ops_s,
                      "pipe_bound_us_per_op": WIDE_EQ_PER_OP / (peak_wide * 1e12) * 1e6},
