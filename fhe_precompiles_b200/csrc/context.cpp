@@ -451,6 +451,31 @@ void build(HostContext &H) {
             c.d_ninv_t[d].w = w[0] | (w[1] << 32), c.d_ninv_t[d].ws = ws[0] | (ws[1] << 32);
             c.d_ninv_t_w[d].w = ww[0] | (ww[1] << 32), c.d_ninv_t_w[d].ws = wws[0] | (wws[1] << 32);
         }
+        // key switch on the dual base
+        const u64 km[3] = {q0, q1, P};
+        for (int d = 0; d < kNumDual; d++) {
+            u64 w[2], ws[2], ww[2], wws[2];
+            for (int lane = 0; lane < 2; lane++) {
+                const u64 s = sp[2 * d + lane];
+                const u64 ni = h_invmod(kN, s);
+                const u64 w_last = (H.twi[kNumMod + d][1].x >> (32 * lane)) & 0xffffffffull;
+                const u64 niw = h_mulmod(ni, w_last, s);
+                w[lane] = ni, ws[lane] = (ni << 32) / s, ww[lane] = niw, wws[lane] = (niw << 32) / s;
+            }
+            c.d_ninv[d].w = w[0] | (w[1] << 32), c.d_ninv[d].ws = ws[0] | (ws[1] << 32);
+            c.d_ninv_w[d].w = ww[0] | (ww[1] << 32), c.d_ninv_w[d].ws = wws[0] | (wws[1] << 32);
+        }
+        for (int m = 0; m < 3; m++) {
+            const u64 o1 = km[(m + 1) % 3], o2 = km[(m + 2) % 3];  // Q / m = o1 o2
+            c.lk_C[m] = mk_shoup(h_invmod(h_mulmod(o1 % km[m], o2 % km[m], km[m]), km[m]), km[m]);
+            for (int i = 0; i < 6; i++) {
+                const u64 r = h_mulmod(o1 % sp[i], o2 % sp[i], sp[i]);
+                c.lk_R[m][i] = (u32)r;
+                c.lk_Rs[m][i] = (u32)((r << 32) / sp[i]);
+            }
+            c.ksKN[m] = (km[m] - mulmod_many(sp, 6, -1, km[m])) % km[m];
+            for (int i = 0; i < 6; i++) c.ksK[i][m] = mk_shoup(mulmod_many(sp, 6, i, km[m]), km[m]);
+        }
         (void)sizeof(U);
     }
     // key switching

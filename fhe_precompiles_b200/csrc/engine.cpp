@@ -514,6 +514,14 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
     if (fused_) {
         TIMED(2, launch_relin_ks(c3, rk, m.ks, c, s), "relin_ks");
     } else {
+        if (ks_dual() && c >= 96) {
+            // the whole key switch on the dual base; m.tens (15 limbs per op, dead once c3 exists) holds the lifted key
+            TIMED(2, launch_rk_prepare_ksd(rk, m.tens, s), "rk_prepare_ksd");
+            TIMED(6, launch_digit_ntt_ksd(c3, m.dig, c, s), "digit_ntt_ksd");
+            TIMED(7, launch_ks_intt_ksd(m.dig, m.tens + 24 * kN, m.ks, c, s), "ks_intt_ksd");
+            TIMED(3, launch_ks_finish_ksd(m.ks, c3, out, c, s), "ks_finish_ksd");
+            return;
+        }
         TIMED(6, launch_digit_ntt(c3, m.dig, c, s), "digit_ntt");
         // the fused tail runs the three moduli one after the other in two CTAs per op: right once 2c CTAs come close to the
         // 296 resident ones (the 128-op chunks of the host-buffer pipelines included), three times the critical path for a

@@ -1106,6 +1106,203 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks_finish(const u64 *__restrict
 }
 
 // =====================================================================================
+// K9d: the key switch on the dual base (opt-in, FHE_B200_KS=dual; measured +1.3 %).  switch_key_inplace's sums S_km = sum_j d_j * rk_jkm mod m are the
+// residues of ONE integer polynomial per output k: U_k = sum_j d_j * RK_jk with the key lifted to integers RK == rk (mod q0, q1,
+// P), 0 <= RK < 3 Q.  |U_k| < 2 N 2^36 2^111 = 2^160 << S / 2, so U_k is carried exactly by the six dual primes: 6 forward + 6
+// inverse DUAL transforms instead of 6 + 6 on 36/37-bit primes, and U_k mod (q0, q1, P) follows by the same CRT-with-rounding
+// as in k_floor_sk_d.  Same bits as SEAL (the oracle follows SEAL; prototyped in Python first).
+//   k_rk_intt_ksd / k_rk_lift_ksd / k_rk_ntt_ksd : the key -> coefficient form -> integer lift mod s_i -> dual NTT (per call)
+//   k_digit_ntt_ksd : dual NTT of the two digits ([c2]_{q_j} as integers)          grid (6 = j*3+w, ops) -> dig [op][2][3][N]
+//   k_ks_intt_ksd   : MAC with the lifted key + inverse dual NTT                   grid (6 = k*3+w, ops) -> ks  [op][2][3][N]
+//   k_ks_finish_ksd : U mod (P, q0, q1), rounded division by P, add to (c0, c1)    eltwise
+// =====================================================================================
+template <int MI>
+__device__ __forceinline__ void rk_intt_body(const u64 *__restrict__ src, u64 *__restrict__ dst, u64 *smem, int t) {
+    using M = Mod<MI>;
+    u64 v[1][8];
+    load_chunk8_ldg(src, v[0], t);
+    ntt_inverse<M, 1, true, false>(v, smem, kt.twi[MI], t, kc.ninv[MI], kc.ninv_w[MI]);
+    store_natural(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 2) k_rk_intt_ksd(const u64 *__restrict__ rk, u64 *__restrict__ coef) {
+    extern __shared__ __align__(16) u64 smem[];
+    const int limb = blockIdx.x, t = threadIdx.x;
+    switch (limb % 3) {
+        case 0: rk_intt_body<MQ0>(rk + (size_t)limb * kN, coef + (size_t)limb * kN, smem, t); break;
+        case 1: rk_intt_body<MQ1>(rk + (size_t)limb * kN, coef + (size_t)limb * kN, smem, t); break;
+        default: rk_intt_body<MP>(rk + (size_t)limb * kN, coef + (size_t)limb * kN, smem, t); break;
+    }
+}
+// coef [4 = j*2+k][3 moduli][N] -> lifted [4][3 dual words][N], every lane in [0, 4s)
+__global__ void __launch_bounds__(256) k_rk_lift_ksd(const u64 *__restrict__ coef, u64 *__restrict__ lifted) {
+    const int g = blockIdx.x * 256 + threadIdx.x;  // 4 * N threads
+    const int jk = g / kN, i = g % kN;
+    const u64 *c = coef + (size_t)jk * 3 * kN + i;
+    const u64 y[3] = {shoup<Mod<MQ0>>(c[0], kc.lk_C[0].w, kc.lk_C[0].ws), shoup<Mod<MQ1>>(c[kN], kc.lk_C[1].w, kc.lk_C[1].ws),
+                      shoup<Mod<MP>>(c[2 * kN], kc.lk_C[2].w, kc.lk_C[2].ws)};
+    u32 lane[6];
+#pragma unroll
+    for (int l = 0; l < 6; l++) {
+        const u32 s = dual_prime(l);
+        u32 acc = 0;
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            const u32 ym = barrett61(y[m], kc.d_mu61[l], s);                                    // y_m mod s_l, [0, 4s)
+            acc = csub32(acc, 2 * s) + shoup32(ym, kc.lk_R[m][l], kc.lk_Rs[m][l], s);           // < 2s + 2s
+        }
+        lane[l] = acc;
+    }
+    u64 *o = lifted + (size_t)jk * 3 * kN + i;
+    o[0] = pack64(lane[0], lane[1]);
+    o[kN] = pack64(lane[2], lane[3]);
+    o[2 * kN] = pack64(lane[4], lane[5]);
+}
+__global__ void __launch_bounds__(kThreads, 3) k_rk_ntt_ksd(const u64 *__restrict__ lifted, u64 *__restrict__ rkd) {
+    extern __shared__ __align__(16) u64 smem[];
+    const int limb = blockIdx.x, t = threadIdx.x;
+    u64 v[1][8];
+    load_natural(lifted + (size_t)limb * kN, v[0], t);
+    switch (limb % 3) {
+        case 0: ntt_forward<ModDual<0>, 1, false, false>(v, smem, kt.twf[kNumMod + 0], t); break;
+        case 1: ntt_forward<ModDual<1>, 1, false, false>(v, smem, kt.twf[kNumMod + 1], t); break;
+        default: ntt_forward<ModDual<2>, 1, false, false>(v, smem, kt.twf[kNumMod + 2], t); break;
+    }
+    store_chunk8_lm(rkd + (size_t)limb * kN, v[0], t);
+}
+template <int D>
+__device__ __forceinline__ void digit_ntt_ksd_body(const u64 *__restrict__ src, u64 *__restrict__ dst, u64 *smem, int t) {
+    using M = ModDual<D>;
+    u64 v[1][8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const u64 x = src[r * kThreads + t];  // < 2^36
+        v[0][r] = pack64(barrett61(x, kc.d_mu61[2 * D], M::s0), barrett61(x, kc.d_mu61[2 * D + 1], M::s1));
+    }
+    ntt_forward<M, 1, false, false>(v, smem, kt.twf[M::kIndex], t);
+    store_chunk8_lm(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 3) k_digit_ntt_ksd(const u64 *__restrict__ c3, u64 *__restrict__ dig) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int j = blockIdx.x / 3, w = blockIdx.x % 3;
+    const u64 *src = c3 + op * 6 * kN + 4 * kN + (size_t)j * kN;
+    u64 *dst = dig + (op * 6 + blockIdx.x) * kN;
+    const int t = threadIdx.x;
+    switch (w) {
+        case 0: digit_ntt_ksd_body<0>(src, dst, smem, t); break;
+        case 1: digit_ntt_ksd_body<1>(src, dst, smem, t); break;
+        default: digit_ntt_ksd_body<2>(src, dst, smem, t); break;
+    }
+}
+template <int D>
+__device__ __forceinline__ void ks_intt_ksd_body(const u64 *__restrict__ dg, const u64 *__restrict__ rkd, int k, u64 *__restrict__ dst,
+                                                 u64 *smem, int t) {
+    using M = ModDual<D>;
+    const u32 mu0 = kc.d_mu61[2 * D], mu1 = kc.d_mu61[2 * D + 1];
+    const ulonglong2 *pd0 = lm_ptr(dg + (size_t)(0 * 3 + D) * kN, t), *pd1 = lm_ptr(dg + (size_t)(1 * 3 + D) * kN, t);
+    const ulonglong2 *pk0 = lm_ptr(rkd + (size_t)((0 * 2 + k) * 3 + D) * kN, t), *pk1 = lm_ptr(rkd + (size_t)((1 * 2 + k) * 3 + D) * kN, t);
+    u64 v[1][8];
+    auto mac = [&](u64 x0, u64 y0, u64 x1, u64 y1) -> u64 {
+        u32 al, ah, bl, bh, cl, ch, dl, dh;
+        unpack64(x0, al, ah);
+        unpack64(y0, bl, bh);
+        unpack64(x1, cl, ch);
+        unpack64(y1, dl, dh);
+        const u32 xs0[2] = {al, cl}, ys0[2] = {bl, dl}, xs1[2] = {ah, ch}, ys1[2] = {bh, dh};
+        return pack64(dual_mulsum<2>(xs0, ys0, M::s0, mu0), dual_mulsum<2>(xs1, ys1, M::s1, mu1));
+    };
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const ulonglong2 x0 = pd0[r * kLm], x1 = pd1[r * kLm], y0 = __ldg(pk0 + r * kLm), y1 = __ldg(pk1 + r * kLm);
+        v[0][2 * r] = mac(x0.x, y0.x, x1.x, y1.x);
+        v[0][2 * r + 1] = mac(x0.y, y0.y, x1.y, y1.y);
+    }
+    ntt_inverse<M, 1, false, false>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv[D], kc.d_ninv_w[D]);  // [0, 2s)
+    store_natural(dst, v[0], t);
+}
+__global__ void __launch_bounds__(kThreads, 3) k_ks_intt_ksd(const u64 *__restrict__ dig, const u64 *__restrict__ rkd, u64 *__restrict__ ks) {
+    extern __shared__ __align__(16) u64 smem[];
+    const size_t op = blockIdx.y;
+    const int k = blockIdx.x / 3, w = blockIdx.x % 3;
+    const u64 *dg = dig + op * 6 * kN;
+    u64 *dst = ks + (op * 6 + blockIdx.x) * kN;
+    const int t = threadIdx.x;
+    switch (w) {
+        case 0: ks_intt_ksd_body<0>(dg, rkd, k, dst, smem, t); break;
+        case 1: ks_intt_ksd_body<1>(dg, rkd, k, dst, smem, t); break;
+        default: ks_intt_ksd_body<2>(dg, rkd, k, dst, smem, t); break;
+    }
+}
+// one coefficient: the three dual words of U_k (lanes in [0, 2s)), c3's limbs -> the two output limbs
+__device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 c0, u64 c1, u64 &o0, u64 &o1) {
+    using Q0 = Mod<MQ0>;
+    using Q1 = Mod<MQ1>;
+    using PP = Mod<MP>;
+    u32 r[6], y[6];
+    unpack64(w0, r[0], r[1]);
+    unpack64(w1, r[2], r[3]);
+    unpack64(w2, r[4], r[5]);
+    u32 est = 1u << 15;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        y[i] = shoup32(r[i], kc.d_C[i], kc.d_Cs[i], dual_prime(i));
+        est += y[i] >> 14;
+    }
+    const u32 v = est >> 16;  // U = sum y_i (S/s_i) - v S exactly (|U| / S < 2^-19)
+    u64 sp, s0, s1;
+    {
+        ShoupSum<PP> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][2].w, kc.ksK[i][2].ws);
+        s.add_small(v, kc.ksKN[2]);
+        sp = canon_k32<PP>(s.value());
+    }
+    {
+        ShoupSum<Q0> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][0].w, kc.ksK[i][0].ws);
+        s.add_small(v, kc.ksKN[0]);
+        s0 = canon_k32<Q0>(s.value());
+    }
+    {
+        ShoupSum<Q1> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][1].w, kc.ksK[i][1].ws);
+        s.add_small(v, kc.ksKN[1]);
+        s1 = canon_k32<Q1>(s.value());
+    }
+    // RNSTool::divide_and_round_q_last: (S_l - ((S_P + P/2 mod P) mod q_l - (P/2 mod q_l))) P^-1, added to c3
+    const u64 last = csub<PP>(sp + kc.half_P, PP::q);
+    {
+        const u64 tl = submod<Q0>(canon_k32<Q0>(last), kc.half_P_mod_q[0]);
+        o0 = canon_k32<Q0>(shoup_acc<Q0, 2>(c0, submod<Q0>(s0, tl), kc.inv_P_mod_q[0].w, kc.inv_P_mod_q[0].ws));
+    }
+    {
+        const u64 tl = submod<Q1>(canon_k32<Q1>(last), kc.half_P_mod_q[1]);
+        o1 = canon_k32<Q1>(shoup_acc<Q1, 2>(c1, submod<Q1>(s1, tl), kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws));
+    }
+}
+__global__ void __launch_bounds__(256, 3) k_ks_finish_ksd(const u64 *__restrict__ ks, const u64 *__restrict__ c3, u64 *__restrict__ out,
+                                                           size_t n_ops) {
+    const size_t total = n_ops * 2 * (kN / 2);  // (op, k, coefficient pair)
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += stride) {
+        const size_t op = g / kN;
+        const int k = (int)((g / (kN / 2)) & 1), i = 2 * (int)(g % (kN / 2));
+        const ulonglong2 *in = reinterpret_cast<const ulonglong2 *>(ks + (op * 6 + (size_t)k * 3) * kN + i);
+        const ulonglong2 w0 = in[0], w1 = in[kN / 2], w2 = in[2 * (kN / 2)];
+        const ulonglong2 *pc = reinterpret_cast<const ulonglong2 *>(c3 + (op * 3 + k) * 2 * kN + i);
+        const ulonglong2 c0 = pc[0], c1 = pc[kN / 2];
+        u64 ax, ay, bx, by;
+        ks_finish_coeff_ksd(w0.x, w1.x, w2.x, c0.x, c1.x, ax, bx);
+        ks_finish_coeff_ksd(w0.y, w1.y, w2.y, c0.y, c1.y, ay, by);
+        ulonglong2 *po = reinterpret_cast<ulonglong2 *>(out + (op * 2 + k) * 2 * kN + i);
+        po[0] = make_ulonglong2(ax, ay);
+        po[kN / 2] = make_ulonglong2(bx, by);
+    }
+}
+
+// =====================================================================================
 // K9b: rounded division by P and accumulation into (c0, c1)   (tail of switch_key_inplace)
 //   out[op][k][l][i] = c3[op][k][l][i] + (ks[k][l][i] - ((ks[k][P][i] + P/2 mod P) mod q_l - (P/2 mod q_l))) * P^-1 mod q_l
 // =====================================================================================
@@ -1917,6 +2114,41 @@ cudaError_t launch_floor_sk(const u64 *tens, u64 *c3, size_t n_ops, cudaStream_t
 cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
     k_relin_ks<<<dim3(3, (unsigned)n_ops), kThreads, kSmem2, s>>>(c3, rk, ks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+bool ks_dual() {
+    static const bool on = [] {
+        const char *v = getenv("FHE_B200_KS");
+        return v && !strcmp(v, "dual");  // opt-in: +1.3 % for a second key domain and four more kernels
+    }();
+    return on;
+}
+// the key switch on the dual base in four steps; tmp = 36 limbs of scratch (coefficient-form key, lifted key, dual-NTT key at
+// tmp + 24 limbs)
+cudaError_t launch_rk_prepare_ksd(const u64 *rk, u64 *tmp, cudaStream_t s) {
+    u64 *coef = tmp, *lifted = tmp + 12 * kN, *rkd = tmp + 24 * kN;
+    k_rk_intt_ksd<<<12, kThreads, kSmem1, s>>>(rk, coef);
+    k_rk_lift_ksd<<<4 * kN / 256, 256, 0, s>>>(coef, lifted);
+    k_rk_ntt_ksd<<<12, kThreads, kSmem1, s>>>(lifted, rkd);
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_digit_ntt_ksd(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_digit_ntt_ksd<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(c3, dig);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_ks_intt_ksd(const u64 *dig, const u64 *rkd, u64 *ks, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ks_intt_ksd<<<dim3(6, (unsigned)n_ops), kThreads, kSmem1, s>>>(dig, rkd, ks);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_ks_finish_ksd(const u64 *ks, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ks_finish_ksd<<<eltwise_grid(n_ops * 2 * (kN / 2), 256), 256, 0, s>>>(ks, c3, out, n_ops);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

@@ -53,6 +53,12 @@ bool qlimb_ntt();       // FHE_B200_QLIMB_NTT=1: transform the q-limbs of the te
 bool ks_finish_fused();  // default: key-switch MAC + inverse transforms + rounded division by P in one kernel (FHE_B200_KS_FINISH=0: two)
 // rk_lm: optional scratch of 12 limbs for a lane-major copy of the key (made on the stream before the kernel)
 cudaError_t launch_ks_finish(const u64 *dig, const u64 *rk, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s, u64 *rk_lm = nullptr);
+bool ks_dual();  // FHE_B200_KS=dual: the key switch on the dual base too (opt-in A/B; default: on SEAL's 36/37-bit primes; same bits)
+// tmp36: 36 limbs of scratch; the dual-NTT key ends up at tmp36 + 24 limbs
+cudaError_t launch_rk_prepare_ksd(const u64 *rk, u64 *tmp36, cudaStream_t s);
+cudaError_t launch_digit_ntt_ksd(const u64 *c3, u64 *dig, size_t n_ops, cudaStream_t s);
+cudaError_t launch_ks_intt_ksd(const u64 *dig, const u64 *rkd, u64 *ks, size_t n_ops, cudaStream_t s);
+cudaError_t launch_ks_finish_ksd(const u64 *ks, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s);
 cudaError_t launch_relin_finish(const u64 *c3, const u64 *ks, u64 *out, size_t n_ops, cudaStream_t s);
 
 uint64_t launch_count();

@@ -992,9 +992,10 @@ def test_device_sampler_exact_paths_on_crafted_draws(dev):
 
 
 def test_qlimb_recovery_equals_seals_form(dev, keys):
-    """default multiply: the q-limbs of the BEHZ tensor product are recovered exactly from its Bsk limbs (33 limb transforms);
-    FHE_B200_QLIMB_NTT=1: they are transformed as SEAL does (47).  Same bits, on random and on extreme residues, and both
-    equal the oracle (which follows SEAL)."""
+    """The multiply is computed four ways -- default (tensor product on the GPU's dual base), SEAL's form (FHE_B200_QLIMB_NTT=1:
+    47 transforms), SEAL's 61-bit primes with the q-limbs recovered (FHE_B200_BEHZ=bsk) and the default with the key switch on
+    the dual base too (FHE_B200_KS=dual) -- same bits on random and on extreme residues, equal to the oracle (which follows
+    SEAL).  The key-switch paths only differ for batches >= 96 ops, hence the 128-op batch."""
     import hashlib
     import subprocess
     import sys
@@ -1008,7 +1009,7 @@ from fhe_precompiles_b200 import device
 device.init(0)
 keys = KeySet.load()
 rng = np.random.default_rng(606)
-a, b = random_ct(rng, 24), random_ct(rng, 24)
+a, b = random_ct(rng, 128), random_ct(rng, 128)
 for l in range(2):
     a[20, :, l, :] = MODULI[l] - 1; b[20, :, l, :] = MODULI[l] - 1      # every coefficient q-1: the largest |t D|
     a[21, :, l, :] = MODULI[l] // 2; b[21, :, l, :] = MODULI[l] // 2 + 1
@@ -1018,18 +1019,20 @@ out = device.mul_relin(t(a), t(b), t(keys.rk)).cpu().numpy()
 print("SHA", hashlib.sha256(out.tobytes()).hexdigest())
 """ % (ROOT, os.path.join(ROOT, "tests"))
     shas = {}
-    for mode in ("0", "1"):
-        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, FHE_B200_QLIMB_NTT=mode))
+    # "0": the default (tensor product on the dual base); "1": SEAL's form (47 transforms); "bsk": SEAL's 61-bit primes with the
+    # q-limbs recovered (33 transforms); "ksd": the default with the key switch on the dual base too
+    for mode, env in (("0", {}), ("1", {"FHE_B200_QLIMB_NTT": "1"}), ("bsk", {"FHE_B200_BEHZ": "bsk"}), ("ksd", {"FHE_B200_KS": "dual"})):
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
         assert r.returncode == 0, r.stdout + r.stderr
         shas[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("SHA")][0]
-    assert shas["0"] == shas["1"]
+    assert shas["0"] == shas["1"] == shas["bsk"] == shas["ksd"]
     rng = np.random.default_rng(606)
-    a, b = random_ct(rng, 24), random_ct(rng, 24)
+    a, b = random_ct(rng, 128), random_ct(rng, 128)
     for l in range(2):
         a[20, :, l, :] = MODULI[l] - 1; b[20, :, l, :] = MODULI[l] - 1
         a[21, :, l, :] = MODULI[l] // 2; b[21, :, l, :] = MODULI[l] // 2 + 1
     a[22] = 0; b[23] = 0
-    want = np.stack([bfv.mul_relin(a[i], b[i], keys.rk) for i in range(24)])
+    want = np.stack([bfv.mul_relin(a[i], b[i], keys.rk) for i in range(128)])
     assert shas["0"] == "SHA " + hashlib.sha256(want.view(np.int64).tobytes()).hexdigest()
 
 
