@@ -622,8 +622,6 @@ __device__ __forceinline__ u64 ext_dual(u64 base, u32 m, bool neg) {
     unpack64(base, bl, bh);
 #pragma unroll
     for (int lane = 0; lane < 2; lane++) {
-        constexpr int dummy = 0;
-        (void)dummy;
         const int i = 2 * D + lane;
         const u32 s = lane ? ModDual<D>::s1 : ModDual<D>::s0;
         // Z = base + m 2^61 (- q)  ==  base_lo + base_hi R32 + m R61 (+ NQ)   < 2^61
