@@ -70,6 +70,7 @@ struct DevConsts {
     //   RK = sum_m [rk_m (Q/m)^-1]_m (Q/m) (Q = q0 q1 P, RK < 3 Q, == rk mod every m), |U_k| < 2^161 << S / 2.
     //   lift: y_m = [coef_m lk_C[m]]_m,  RK mod s_i = sum_m (y_m mod s_i) lk_R[m][i]
     //   finish: y_i = [r_i C_i]_{s_i}, v = round(sum y_i / s_i), U mod m = [sum y_i ksK[i][m] + v ksKN[m]]_m for m = q0, q1, P
+    u32 opaque_zero;               // 0, but unknown to ptxas: a third addend that keeps two-input adds off the multiplier pipe (IMAD.IADD)
     Shoup d_ninv[3], d_ninv_w[3];  // N^-1 and N^-1 w_last per dual limb (lanes packed, 32-bit Shoup quotients)
     Shoup lk_C[3];                 // (Q/m)^-1 mod m
     u32 lk_R[3][6], lk_Rs[3][6];   // (Q/m) mod s_i and its 32-bit Shoup quotient

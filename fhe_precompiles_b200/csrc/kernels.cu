@@ -17,12 +17,12 @@
 
 namespace fheb {
 __constant__ DevTwLow ktl;  // defined before ntt.cuh, which reads it
+__constant__ DevConsts kc;  // likewise (modarith.cuh: opaque_zero)
 }
 #include "ntt.cuh"
 
 namespace fheb {
 
-__constant__ DevConsts kc;
 __constant__ DevTables kt;
 
 cudaError_t upload_constants(const DevConsts &c, const DevTables &t, const DevTwLow &lo) {

@@ -164,7 +164,8 @@ __device__ __forceinline__ void dual_fwd_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     unpack64(ws, q0, q1);
     x0 = csub32(x0, 2 * M::s0), x1 = csub32(x1, 2 * M::s1);
     const u32 t0 = shoup32(y0, w0, q0, M::s0), t1 = shoup32(y1, w1, q1, M::s1);
-    X = pack64(x0 + t0, x1 + t1);
+    const u32 z = kc.opaque_zero;  // a third addend: IADD3 on the ALU pipe instead of IMAD.IADD on the multiplier pipe
+    X = pack64(x0 + t0 + z, x1 + t1 + z);
     Y = pack64(x0 + 2 * M::s0 - t0, x1 + 2 * M::s1 - t1);
 }
 // inverse butterfly: inputs in [0, 2s), outputs in [0, 2s)
@@ -176,7 +177,8 @@ __device__ __forceinline__ void dual_inv_bfly(u64 &X, u64 &Y, u64 w, u64 ws) {
     unpack64(w, w0, w1);
     unpack64(ws, q0, q1);
     const u32 d0 = x0 + 2 * M::s0 - y0, d1 = x1 + 2 * M::s1 - y1;
-    X = pack64(csub32(x0 + y0, 2 * M::s0), csub32(x1 + y1, 2 * M::s1));
+    const u32 z = kc.opaque_zero;
+    X = pack64(csub32(x0 + y0 + z, 2 * M::s0), csub32(x1 + y1 + z, 2 * M::s1));
     Y = pack64(shoup32(d0, w0, q0, M::s0), shoup32(d1, w1, q1, M::s1));
 }
 // last inverse stage with the output scaling merged in: (X, Y) -> (sc (X + Y), scw (X - Y)), canonical if kCanon
