@@ -15,6 +15,10 @@
 
 #include "kernels.h"
 
+#ifndef FHE_B200_WIDESUM
+#define FHE_B200_WIDESUM 1  // CRT recoveries on exact two-accumulator sums (modarith.cuh WideSum); 0 = the ShoupSum form
+#endif
+
 namespace fheb {
 __constant__ DevTwLow ktl;  // defined before ntt.cuh, which reads it
 __constant__ DevConsts kc;  // likewise (modarith.cuh: opaque_zero)
@@ -794,6 +798,22 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
     }
     const u32 v = est >> 16;  // t D = sum y_i (S/s_i) - v S exactly
     u64 t0, t1;
+#if FHE_B200_WIDESUM
+    {
+        WideSum<Q0> s;  // exact sum of the six products + v KN, one reduction (modarith.cuh)
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.d_K[i][0].w);
+        s.add_small(v, kc.d_KN[0]);
+        t0 = s.value();
+    }
+    {
+        WideSum<Q1> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.d_K[i][1].w);
+        s.add_small(v, kc.d_KN[1]);
+        t1 = s.value();
+    }
+#else
     {
         ShoupSum<Q0> s;  // six terms < q + 1 each + v KN < 13 q
 #pragma unroll
@@ -808,6 +828,7 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
         s.add_small(v, kc.d_KN[1]);
         t1 = canon_k32<Q1>(s.value());
     }
+#endif
     // fast_floor: y0 = t0 q1 + t1 q0 (the q-part of t D with its fast-base-conversion overflow), f = (t D - y0) / q on s_0..s_3
     u64 ylo, yhi;
     punctured_sum(t0, t1, ylo, yhi);
@@ -822,6 +843,22 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
         est2 += tb[i] >> 14;
     }
     const u32 vp = est2 >> 16;  // f = sum tb_i (S4/s_i) - v' S4 exactly (|f| / S4 < 2^-24)
+#if FHE_B200_WIDESUM
+    {
+        WideSum<Q0> s;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s.add32(tb[i], kc.d_P[i][0].w);
+        s.add_small(vp, kc.d_NS4[0]);
+        o0 = s.value();
+    }
+    {
+        WideSum<Q1> s;
+#pragma unroll
+        for (int i = 0; i < 4; i++) s.add32(tb[i], kc.d_P[i][1].w);
+        s.add_small(vp, kc.d_NS4[1]);
+        o1 = s.value();
+    }
+#else
     {
         ShoupSum<Q0> s;
 #pragma unroll
@@ -836,6 +873,7 @@ __device__ __forceinline__ void floor_sk_coeff_d(u64 w0, u64 w1, u64 w2, u64 &o0
         s.add_small(vp, kc.d_NS4[1]);
         o1 = canon_k32<Q1>(s.value());
     }
+#endif
 }
 __global__ void __launch_bounds__(256, 3) k_floor_sk_d(const u64 *__restrict__ tens, u64 *__restrict__ c3, size_t n_ops) {
     const size_t total = n_ops * 3 * (kN / 2);
@@ -1248,6 +1286,29 @@ __device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 
     }
     const u32 v = est >> 16;  // U = sum y_i (S/s_i) - v S exactly (|U| / S < 2^-19)
     u64 sp, s0, s1;
+#if FHE_B200_WIDESUM
+    {
+        WideSum<PP> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][2].w);
+        s.add_small(v, kc.ksKN[2]);
+        sp = s.value();
+    }
+    {
+        WideSum<Q0> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][0].w);
+        s.add_small(v, kc.ksKN[0]);
+        s0 = s.value();
+    }
+    {
+        WideSum<Q1> s;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][1].w);
+        s.add_small(v, kc.ksKN[1]);
+        s1 = s.value();
+    }
+#else
     {
         ShoupSum<PP> s;
 #pragma unroll
@@ -1269,6 +1330,7 @@ __device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 
         s.add_small(v, kc.ksKN[1]);
         s1 = canon_k32<Q1>(s.value());
     }
+#endif
     // RNSTool::divide_and_round_q_last: (S_l - ((S_P + P/2 mod P) mod q_l - (P/2 mod q_l))) P^-1, added to c3
     const u64 last = csub<PP>(sp + kc.half_P, PP::q);
     {

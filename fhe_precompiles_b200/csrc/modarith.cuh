@@ -267,6 +267,42 @@ struct ShoupSum {
     }
 };
 
+// Exact sum of up to seven products x_k * w_k with x_k < 2^31 (a dual-lane residue in [0, 2s)) and constants w_k < q < 2^37,
+// reduced ONCE: the low 30 bits of every w_k feed `lo` (each product < 2^61), the remaining <= 7 bits feed `hi` (each < 2^38),
+// and value() folds lo + hi 2^30 with q = 2^B - c.  A term costs two wide multiplies (8 multiplier-pipe cycles) against three
+// wide + one low (14) for a ShoupSum term, whose per-term quotient estimate buys nothing when the factors are this short; the
+// result is the canonical residue, so callers that canonicalised a ShoupSum value get the same bits.
+template <class M>
+struct WideSum {
+    static constexpr int kHiBits = M::kBits - 30;  // 6 or 7
+    u64 lo = 0, hi = 0;
+    __device__ __forceinline__ void add32(u32 x, u64 w) {
+        u32 wl, wh;
+        unpack64(w, wl, wh);
+        lo = mad_wide(x, wl & 0x3fffffffu, lo);
+        hi = mad_wide(x, (wl >> 30) | (wh << 2), hi);
+    }
+    // x * w for x < 2^8: the product is below 2^45 and goes to `lo` whole                                1 wide + 1 low
+    __device__ __forceinline__ void add_small(u32 x, u64 w) {
+        u32 wl, wh, al, ah;
+        unpack64(w, wl, wh);
+        unpack64(mad_wide(x, wl, lo), al, ah);
+        lo = pack64(al, mad_lo(x, wh, ah));
+    }
+    // canonical residue of lo + hi 2^30: with A = floor(lo / 2^B) + floor(hi / 2^(B-30)) < 2^35 the sum is congruent to
+    // (lo mod 2^B) + ((hi mod 2^(B-30)) << 30) + A c < 2^54; one more fold leaves < 2^B + 2^35 < 2q          2 wide + 1 low
+    __device__ __forceinline__ u64 value() const {
+        constexpr u32 c = (u32)M::kC;
+        const u64 A = (lo >> M::kBits) + (hi >> kHiBits);
+        const u64 base = (lo & M::kMask) + ((hi & ((1u << kHiBits) - 1)) << 30);
+        u32 al, ah, yl, yh;
+        unpack64(A, al, ah);
+        unpack64(mad_wide(al, c, base), yl, yh);
+        const u64 Y = pack64(yl, mad_lo(ah, c, yh));
+        return csub<M>(mad_wide((u32)(Y >> M::kBits), c, Y & M::kMask), M::q);
+    }
+};
+
 // pseudo-Mersenne fold: x -> (x mod 2^b) + floor(x / 2^b) * c, congruent to x mod q.
 // Result < 2^b + 2^(64-b) * c; one more conditional subtraction is canonical whenever that is < 2q.
 template <class M>
