@@ -73,15 +73,25 @@ else:
         "k_ext_conv": (36.5 + 6 * 3.5) * 16384,                      # shared part of the extension + 6 residues (2 wide + Barrett each)
         "k_ext_ntt": 24576 * 12 * 4.0,                               # 12 forward dual transforms
         "k_tensor_intt": 24576 * 9 * 4.0 + 9 * 2048 * 4.0 + 17.0 * 12288,  # 9 inverse dual transforms (scaled last stage) + dyadic tensor
-        "k_floor_sk": 115.0 * 12288,                                 # 6-prime CRT -> t_l (12 sum terms), y0 mod 4 primes, 4-prime lift (8 sum terms)
+        # 6 Shoup products on 32 bits (2.0 each), 12 + 8 terms of exact two-accumulator sums (2 wide each, WideSum), 4 reductions of
+        # such sums (4.0), the punctured sum (6), y0 mod 4 primes and the 4-prime lift (4.5 each): 92 per coefficient; it was 115
+        # while the sums were sums of Shoup products (3 wide + 1 low per term)
+        "k_floor_sk": 92.0 * 12288,
     }
+# key switch: "dual" (default for chunks >= 96 ops) carries switch_key_inplace's sums on the dual base too -- 6 + 6 dual transforms
+# and one CRT recovery per output coefficient; "seal" runs the 6 + 6 transforms on SEAL's key primes q0, q1, P
+KS = "seal" if os.environ.get("FHE_B200_KS") == "seal" else "dual"
 KERNEL_WIDE_EQ.update({
     "k_digit_ntt": 24576 * 6 * 6.5,                              # 6 key-switch digit NTTs
     "k_ks_finish": 24576 * 6 * 7.0 + 0.28e6 + 0.13e6,            # key MAC + 6 inverse NTTs + rounded division by P
+    "k_digit_ntt_ksd": 24576 * 6 * 4.0 + 2 * 4096 * 6 * 1.5,     # 6 forward dual transforms + the digits reduced mod the six primes
+    "k_ks_intt_ksd": 24576 * 6 * 4.0 + 6 * 2048 * 4.0 + 3.5 * 2 * 4096 * 6,  # 6 inverse dual transforms (scaled last stage) + key MAC
+    "k_ks_finish_ksd": 75.0 * 8192,                              # 6-prime CRT -> U mod (P, q0, q1) (18 sum terms), division by P
 })
 KERNEL_WIDE_EQ["k_ks_intt"] = 24576 * 6 * 7.0 + 0.28e6           # the unfused tail (small chunks): MAC + inverse NTTs
 KERNEL_WIDE_EQ["k_relin_finish"] = 0.13e6                        #   ... and the division by P
-WIDE_EQ_PER_OP = sum(KERNEL_WIDE_EQ[k] for k in ("k_ext_conv", "k_ext_ntt", "k_tensor_intt", "k_floor_sk", "k_digit_ntt", "k_ks_finish"))
+KS_KERNELS = ("k_digit_ntt_ksd", "k_ks_intt_ksd", "k_ks_finish_ksd") if KS == "dual" else ("k_digit_ntt", "k_ks_finish")
+WIDE_EQ_PER_OP = sum(KERNEL_WIDE_EQ[k] for k in ("k_ext_conv", "k_ext_ntt", "k_tensor_intt", "k_floor_sk") + KS_KERNELS)
 SM_COUNT = 148
 WIDE_PER_CLK_PER_SM = 32  # IMAD.WIDE results per clock per SM (scripts/pipe_probe.cu: 0.25 warp-instructions / clk / SMSP)
 METRIC = "ct_ct_fhe_multiply_relin_ops_per_sec"
@@ -831,6 +841,8 @@ def main() -> None:
     def slot_of(ncu_kernel: str) -> str:
         """timed slot of an ncu kernel name: k_ext_ntt2 / k_ext_ntt_d<0> -> k_ext_ntt, k_ks_finish<1> -> k_ks_finish, ..."""
         k = ncu_kernel.split("<")[0]
+        if k.endswith("_ksd"):
+            return k
         if k.endswith("_d"):
             k = k[:-2]
         return "k_ext_ntt" if k == "k_ext_ntt2" else k
@@ -874,10 +886,12 @@ def main() -> None:
         "algorithmic_wide_eq_per_op": {"dominant_kernel": dom_weq, "whole_op": WIDE_EQ_PER_OP,
                                        "limb_ntts_per_op": NTTS_PER_OP,
                                        "behz": BEHZ,
+                                       "key_switch": KS,
                                        "model": {"seal": "SEAL's form, 14+12 fwd / 12+9 inv limb-NTTs",
                                                  "bsk": "q-limbs of the tensor product recovered from its Bsk limbs: 6+12 fwd / 6+9 inv limb-NTTs",
                                                  "dual": "tensor product on six primes below 2^30, two per word: 12 fwd + 9 inv dual transforms at 4.0 "
-                                                         "IMAD.WIDE-equivalents per butterfly (both lanes), 6 fwd + 6 inv key-switch limb-NTTs"}[BEHZ]
+                                                         "IMAD.WIDE-equivalents per butterfly (both lanes), 6 fwd + 6 inv key-switch transforms (dual too "
+                                                         "unless FHE_B200_KS=seal)"}[BEHZ]
                                                 + " x 24,576 butterflies at 6.5 / 7.0 (36-37 bit) and 7.5 (61 bit) "
                                                 "IMAD.WIDE-equivalents + pointwise per kernel (bench.py KERNEL_WIDE_EQ, DESIGN.md section 4)"},
         "whole_op": {"achieved": ach_op, "frac": ach_op / peak_wide, "frac_of_theoretical": ach_op / peak_theory, "us_per_op": 1e6 / ops_s,

@@ -481,7 +481,8 @@ void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint6
 }
 
 // kernel ids: 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt, 5 k_tensor_intt,
-//             6 k_digit_ntt, 7 k_ks_intt, 8 k_ext_conv, 9 k_ks_finish
+//             6 k_digit_ntt, 7 k_ks_intt, 8 k_ext_conv, 9 k_ks_finish, 10 k_rk_*_ksd (key preparation), 11 k_digit_ntt_ksd,
+//             12 k_ks_intt_ksd, 13 k_ks_finish_ksd
 #define TIMED(id, call, what)                                        \
     do {                                                             \
         if (timed) {                                                 \
@@ -516,10 +517,10 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
     } else {
         if (ks_dual() && c >= 96) {
             // the whole key switch on the dual base; m.tens (15 limbs per op, dead once c3 exists) holds the lifted key
-            TIMED(2, launch_rk_prepare_ksd(rk, m.tens, s), "rk_prepare_ksd");
-            TIMED(6, launch_digit_ntt_ksd(c3, m.dig, c, s), "digit_ntt_ksd");
-            TIMED(7, launch_ks_intt_ksd(m.dig, m.tens + 24 * kN, m.ks, c, s), "ks_intt_ksd");
-            TIMED(3, launch_ks_finish_ksd(m.ks, c3, out, c, s), "ks_finish_ksd");
+            TIMED(10, launch_rk_prepare_ksd(rk, m.tens, s), "rk_prepare_ksd");
+            TIMED(11, launch_digit_ntt_ksd(c3, m.dig, c, s), "digit_ntt_ksd");
+            TIMED(12, launch_ks_intt_ksd(m.dig, m.tens + 24 * kN, m.ks, c, s), "ks_intt_ksd");
+            TIMED(13, launch_ks_finish_ksd(m.ks, c3, out, c, s), "ks_finish_ksd");
             return;
         }
         TIMED(6, launch_digit_ntt(c3, m.dig, c, s), "digit_ntt");

@@ -1142,7 +1142,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_ks_finish(const u64 *__restrict
 }
 
 // =====================================================================================
-// K9d: the key switch on the dual base (opt-in, FHE_B200_KS=dual; measured +1.3 %).  switch_key_inplace's sums S_km = sum_j d_j * rk_jkm mod m are the
+// K9d: the key switch on the dual base (default for chunks >= 96 ops; FHE_B200_KS=seal keeps SEAL's three key primes; +3 %).  switch_key_inplace's sums S_km = sum_j d_j * rk_jkm mod m are the
 // residues of ONE integer polynomial per output k: U_k = sum_j d_j * RK_jk with the key lifted to integers RK == rk (mod q0, q1,
 // P), 0 <= RK < 3 Q.  |U_k| < 2 N 2^36 2^111 = 2^160 << S / 2, so U_k is carried exactly by the six dual primes: 6 forward + 6
 // inverse DUAL transforms instead of 6 + 6 on 36/37-bit primes, and U_k mod (q0, q1, P) follows by the same CRT-with-rounding
@@ -2180,7 +2180,7 @@ cudaError_t launch_relin_ks(const u64 *c3, const u64 *rk, u64 *ks, size_t n_ops,
 bool ks_dual() {
     static const bool on = [] {
         const char *v = getenv("FHE_B200_KS");
-        return v && !strcmp(v, "dual");  // opt-in: +1.3 % for a second key domain and four more kernels
+        return !(v && !strcmp(v, "seal"));  // default since the CRT recoveries run on WideSum: +3 % over SEAL's three key primes
     }();
     return on;
 }

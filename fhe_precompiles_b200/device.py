@@ -180,7 +180,7 @@ def frame_stride() -> int:
 
 
 KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt",
-                "k_ext_conv", "k_ks_finish")
+                "k_ext_conv", "k_ks_finish", "k_rk_prepare_ksd", "k_digit_ntt_ksd", "k_ks_intt_ksd", "k_ks_finish_ksd")
 
 
 def set_kernel_timing(on: bool) -> None:
@@ -189,10 +189,10 @@ def set_kernel_timing(on: bool) -> None:
 
 def kernel_timing_report(device: int = 0) -> dict:
     """{kernel: (total ms, launches)} accumulated by mul_relin() since the last report."""
-    ms = (ctypes.c_double * 10)()
-    cnt = (ctypes.c_uint64 * 10)()
+    ms = (ctypes.c_double * len(KERNEL_NAMES))()
+    cnt = (ctypes.c_uint64 * len(KERNEL_NAMES))()
     _check(_lib.lib().fhe_b200_kernel_timing_report(device, ms, cnt))
-    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(10) if cnt[i]}
+    return {KERNEL_NAMES[i]: (float(ms[i]), int(cnt[i])) for i in range(len(KERNEL_NAMES)) if cnt[i]}
 
 
 def parse_public_key(data: bytes):
