@@ -476,6 +476,14 @@ void build(HostContext &H) {
             c.ksKN[m] = (km[m] - mulmod_many(sp, 6, -1, km[m])) % km[m];
             for (int i = 0; i < 6; i++) c.ksK[i][m] = mk_shoup(mulmod_many(sp, 6, i, km[m]), km[m]);
         }
+        for (int l = 0; l < 2; l++) {  // the division by P folded into the q-limb sums (k_ks_finish_ksd)
+            const u64 ql = km[l], ip = h_invmod(P % ql, ql);
+            for (int i = 0; i < 6; i++) c.ksKd[i][l] = h_mulmod(c.ksK[i][l].w, ip, ql);
+            c.ksKNd[l] = h_mulmod(c.ksKN[l], ip, ql);
+            c.ksNd[l] = (ql - ip) % ql;
+            c.ksNd30[l] = h_mulmod(c.ksNd[l], (1ull << 30) % ql, ql);
+            c.ksHd[l] = h_mulmod((P >> 1) % ql, ip, ql);
+        }
         (void)sizeof(U);
     }
     // key switching

@@ -76,6 +76,12 @@ struct DevConsts {
     u32 lk_R[3][6], lk_Rs[3][6];   // (Q/m) mod s_i and its 32-bit Shoup quotient
     Shoup ksK[6][3];               // (S/s_i) mod m,  m = q0, q1, P
     u64 ksKN[3];                   // -S mod m
+    // the rounded division by P folded into the sums for q0, q1: out_l = [c_l + sum y_i ksKd[i][l] + v ksKNd[l] + last_lo ksNd[l]
+    //   + last_hi ksNd30[l] + ksHd[l]]_{q_l} with last = (U mod P + P/2) mod P = last_lo + 2^30 last_hi
+    u64 ksKd[6][2];                // (S/s_i) P^-1 mod q_l
+    u64 ksKNd[2];                  // -S P^-1 mod q_l
+    u64 ksNd[2], ksNd30[2];        // -P^-1 mod q_l and -2^30 P^-1 mod q_l
+    u64 ksHd[2];                   // (P/2 mod q_l) P^-1 mod q_l
 
     // ---- key switching (switch_key_inplace, BFV branch)
     Shoup inv_P_mod_q[2];

@@ -1285,8 +1285,8 @@ __device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 
         est += y[i] >> 14;
     }
     const u32 v = est >> 16;  // U = sum y_i (S/s_i) - v S exactly (|U| / S < 2^-19)
-    u64 sp, s0, s1;
 #if FHE_B200_WIDESUM
+    u64 sp;
     {
         WideSum<PP> s;
 #pragma unroll
@@ -1294,21 +1294,32 @@ __device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 
         s.add_small(v, kc.ksKN[2]);
         sp = s.value();
     }
+    // RNSTool::divide_and_round_q_last with its multiplication by P^-1 folded into the sums (devconsts.h ksKd ...):
+    //   out_l = c_l + (U - (last - P/2)) P^-1 mod q_l,  last = (U mod P + P/2) mod P < 2^37 split at bit 30
+    const u64 last = csub<PP>(sp + kc.half_P, PP::q);
+    const u32 last_lo = (u32)last & 0x3fffffffu, last_hi = (u32)(last >> 30);
     {
-        WideSum<Q0> s;
+        WideSum<Q0> s;  // seven products below 2^61 + small terms: < 2^64
 #pragma unroll
-        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][0].w);
-        s.add_small(v, kc.ksKN[0]);
-        s0 = s.value();
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksKd[i][0]);
+        s.add32(last_lo, kc.ksNd[0]);
+        s.add_small(v, kc.ksKNd[0]);
+        s.add_small(last_hi, kc.ksNd30[0]);
+        s.lo += c0 + kc.ksHd[0];
+        o0 = s.value();
     }
     {
         WideSum<Q1> s;
 #pragma unroll
-        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksK[i][1].w);
-        s.add_small(v, kc.ksKN[1]);
-        s1 = s.value();
+        for (int i = 0; i < 6; i++) s.add32(y[i], kc.ksKd[i][1]);
+        s.add32(last_lo, kc.ksNd[1]);
+        s.add_small(v, kc.ksKNd[1]);
+        s.add_small(last_hi, kc.ksNd30[1]);
+        s.lo += c1 + kc.ksHd[1];
+        o1 = s.value();
     }
 #else
+    u64 sp, s0, s1;
     {
         ShoupSum<PP> s;
 #pragma unroll
@@ -1330,7 +1341,6 @@ __device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 
         s.add_small(v, kc.ksKN[1]);
         s1 = canon_k32<Q1>(s.value());
     }
-#endif
     // RNSTool::divide_and_round_q_last: (S_l - ((S_P + P/2 mod P) mod q_l - (P/2 mod q_l))) P^-1, added to c3
     const u64 last = csub<PP>(sp + kc.half_P, PP::q);
     {
@@ -1341,6 +1351,7 @@ __device__ __forceinline__ void ks_finish_coeff_ksd(u64 w0, u64 w1, u64 w2, u64 
         const u64 tl = submod<Q1>(canon_k32<Q1>(last), kc.half_P_mod_q[1]);
         o1 = canon_k32<Q1>(shoup_acc<Q1, 2>(c1, submod<Q1>(s1, tl), kc.inv_P_mod_q[1].w, kc.inv_P_mod_q[1].ws));
     }
+#endif
 }
 __global__ void __launch_bounds__(256, 3) k_ks_finish_ksd(const u64 *__restrict__ ks, const u64 *__restrict__ c3, u64 *__restrict__ out,
                                                            size_t n_ops) {
