@@ -86,7 +86,9 @@ KERNEL_WIDE_EQ.update({
     "k_ks_finish": 24576 * 6 * 7.0 + 0.28e6 + 0.13e6,            # key MAC + 6 inverse NTTs + rounded division by P
     "k_digit_ntt_ksd": 24576 * 6 * 4.0 + 2 * 4096 * 6 * 1.5,     # 6 forward dual transforms + the digits reduced mod the six primes
     "k_ks_intt_ksd": 24576 * 6 * 4.0 + 6 * 2048 * 4.0 + 3.5 * 2 * 4096 * 6,  # 6 inverse dual transforms (scaled last stage) + key MAC
-    "k_ks_finish_ksd": 75.0 * 8192,                              # 6-prime CRT -> U mod (P, q0, q1) (18 sum terms), division by P
+    # 6 Shoup products on 32 bits (2.0), U mod P (6 sum terms x 2 + 4), then per q-limb 7 sum terms (the P^-1-scaled CRT terms and
+    # the low part of the P-limb correction) + 2 small terms + one reduction: 68 per coefficient of the two output polynomials
+    "k_ks_finish_ksd": 68.0 * 8192,
 })
 KERNEL_WIDE_EQ["k_ks_intt"] = 24576 * 6 * 7.0 + 0.28e6           # the unfused tail (small chunks): MAC + inverse NTTs
 KERNEL_WIDE_EQ["k_relin_finish"] = 0.13e6                        #   ... and the division by P

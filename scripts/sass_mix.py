@@ -10,7 +10,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 obj = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "fhe_precompiles_b200/csrc/build/kernels.o")
 sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True, check=True).stdout
-HOT = ["k_ext_conv_d", "k_ext_ntt_d", "k_tensor_intt_d", "k_floor_sk_d", "k_ext_conv", "k_ext_ntt2", "k_tensor_intt", "k_floor_sk", "k_digit_ntt",
+HOT = ["k_ext_conv_d", "k_ext_ntt_d", "k_tensor_intt_d", "k_floor_sk_d", "k_digit_ntt_ksd", "k_ks_intt_ksd", "k_ks_finish_ksd", "k_ext_conv", "k_ext_ntt2", "k_tensor_intt", "k_floor_sk", "k_digit_ntt",
        "k_ks_finish", "k_ks_intt", "k_ntt"]
 # FMA-heavy pipe cycles per warp instruction (scripts/pipe_probe.cu: IMAD.WIDE / IMAD.HI quarter rate, other IMAD half rate)
 def fma_cycles(op):
