@@ -90,10 +90,14 @@ KERNEL_WIDE_EQ.update({
     # the low part of the P-limb correction) + 2 small terms + one reduction: 68 per coefficient of the two output polynomials
     "k_ks_finish_ksd": 68.0 * 8192,
 })
+# the fused tails (default; FHE_B200_FUSE_TAIL=0 splits them): the same arithmetic without the HBM round trip of the tensor product / of U_k
+FUSE_TAIL = int(os.environ.get("FHE_B200_FUSE_TAIL", "3"))
+KERNEL_WIDE_EQ["k_tensor_floor_d"] = KERNEL_WIDE_EQ["k_tensor_intt"] + KERNEL_WIDE_EQ["k_floor_sk"]
+KERNEL_WIDE_EQ["k_ks_tail_ksd"] = KERNEL_WIDE_EQ["k_ks_intt_ksd"] + KERNEL_WIDE_EQ["k_ks_finish_ksd"]
 KERNEL_WIDE_EQ["k_ks_intt"] = 24576 * 6 * 7.0 + 0.28e6           # the unfused tail (small chunks): MAC + inverse NTTs
 KERNEL_WIDE_EQ["k_relin_finish"] = 0.13e6                        #   ... and the division by P
 KS_KERNELS = ("k_digit_ntt_ksd", "k_ks_intt_ksd", "k_ks_finish_ksd") if KS == "dual" else ("k_digit_ntt", "k_ks_finish")
-WIDE_EQ_PER_OP = sum(KERNEL_WIDE_EQ[k] for k in ("k_ext_conv", "k_ext_ntt", "k_tensor_intt", "k_floor_sk") + KS_KERNELS)
+WIDE_EQ_PER_OP = sum(KERNEL_WIDE_EQ[k] for k in ("k_ext_conv", "k_ext_ntt", "k_tensor_intt", "k_floor_sk") + KS_KERNELS)  # fusing changes no count
 SM_COUNT = 148
 WIDE_PER_CLK_PER_SM = 32  # IMAD.WIDE results per clock per SM (scripts/pipe_probe.cu: 0.25 warp-instructions / clk / SMSP)
 METRIC = "ct_ct_fhe_multiply_relin_ops_per_sec"
@@ -843,7 +847,7 @@ def main() -> None:
     def slot_of(ncu_kernel: str) -> str:
         """timed slot of an ncu kernel name: k_ext_ntt2 / k_ext_ntt_d<0> -> k_ext_ntt, k_ks_finish<1> -> k_ks_finish, ..."""
         k = ncu_kernel.split("<")[0]
-        if k.endswith("_ksd"):
+        if k.endswith("_ksd") or k == "k_tensor_floor_d":
             return k
         if k.endswith("_d"):
             k = k[:-2]

@@ -360,7 +360,7 @@ void fhe_b200_set_kernel_timing(int32_t on) {
         set_error(e.what());
     }
 }
-int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[14], uint64_t launches[14]) {
+int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[16], uint64_t launches[16]) {
     DEV_GUARD(Engine::get().kernel_timing_report(device, ms, launches));
 }
 int32_t fhe_b200_mul_relin_host(int32_t device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out,

@@ -482,7 +482,7 @@ void Engine::kernel_timing_report(int device, double ms[kNumTimedKernels], uint6
 
 // kernel ids: 0 k_behz_tensor, 1 k_floor_sk, 2 k_relin_ks, 3 k_relin_finish, 4 k_ext_ntt, 5 k_tensor_intt,
 //             6 k_digit_ntt, 7 k_ks_intt, 8 k_ext_conv, 9 k_ks_finish, 10 k_rk_*_ksd (key preparation), 11 k_digit_ntt_ksd,
-//             12 k_ks_intt_ksd, 13 k_ks_finish_ksd
+//             12 k_ks_intt_ksd, 13 k_ks_finish_ksd, 14 k_tensor_floor_d, 15 k_ks_tail_ksd
 #define TIMED(id, call, what)                                        \
     do {                                                             \
         if (timed) {                                                 \
@@ -505,6 +505,12 @@ void Engine::enqueue_mul(const uint64_t *a, const uint64_t *b, const ScratchMap 
     } else {
         if (ext_split() || dual) TIMED(8, launch_ext_conv(a, b, m.nttbuf, c, s), "ext_conv");
         TIMED(4, launch_ext_ntt(a, b, m.nttbuf, c, s), "ext_ntt");
+        // three dual words one after the other in one CTA: right for chunks that fill the GPU, three times the critical path for
+        // a single call or a small tile (as for the key-switch tail below)
+        if (dual && (fuse_tail() & 1) && c >= 96) {
+            TIMED(14, launch_tensor_floor(m.nttbuf, m.c3, c, s), "tensor_floor");
+            return;
+        }
         TIMED(5, launch_tensor_intt(m.nttbuf, m.tens, c, s), "tensor_intt");
     }
     TIMED(1, launch_floor_sk(m.tens, m.c3, c, s, dual), "floor_sk");
@@ -519,6 +525,10 @@ void Engine::enqueue_relin(const uint64_t *c3, const uint64_t *rk, uint64_t *out
             // the whole key switch on the dual base; m.tens (15 limbs per op, dead once c3 exists) holds the lifted key
             TIMED(10, launch_rk_prepare_ksd(rk, m.tens, s), "rk_prepare_ksd");
             TIMED(11, launch_digit_ntt_ksd(c3, m.dig, c, s), "digit_ntt_ksd");
+            if (fuse_tail() & 2) {
+                TIMED(15, launch_ks_tail_ksd(m.dig, m.tens + 24 * kN, c3, out, c, s), "ks_tail_ksd");
+                return;
+            }
             TIMED(12, launch_ks_intt_ksd(m.dig, m.tens + 24 * kN, m.ks, c, s), "ks_intt_ksd");
             TIMED(13, launch_ks_finish_ksd(m.ks, c3, out, c, s), "ks_finish_ksd");
             return;

@@ -143,7 +143,7 @@ class Engine {
 
     // Optional per-kernel timing of mul_relin(): CUDA events around every launch on the caller's stream.
     // kernel ids: see kKernelNames.  report() synchronises the device.
-    static constexpr int kNumTimedKernels = 14;
+    static constexpr int kNumTimedKernels = 16;
     void set_kernel_timing(bool on);
     void set_fused(bool on) { fused_ = on; }  // choose k_behz_tensor/k_relin_ks (true) or the split kernels (false)
     void kernel_timing_report(int device, double ms[kNumTimedKernels], uint64_t launches[kNumTimedKernels]);

@@ -718,14 +718,14 @@ __device__ __forceinline__ u32 dual_mulsum(const u32 (&x)[NP], const u32 (&y)[NP
     }
     return csub32(barrett61(P, mu61, s), 2 * s);
 }
-template <int D, bool SHFL>
-__device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb, int d, u64 *__restrict__ dst, u64 *smem, int t) {
+// the dyadic tensor of dual word D for output polynomial d + its inverse transform, left in registers (lanes in [0, 2s))
+template <int D, bool SHFL, bool kTrailSync>
+__device__ __forceinline__ void tensor_intt_dual_regs(const u64 *__restrict__ nb, int d, u64 (&v)[1][8], u64 *smem, int t) {
     using M = ModDual<D>;
     constexpr int E = 2 + D;
     const u64 *a0 = nb + (size_t)(0 * 5 + E) * kN, *a1 = nb + (size_t)(1 * 5 + E) * kN;
     const u64 *b0 = nb + (size_t)(2 * 5 + E) * kN, *b1 = nb + (size_t)(3 * 5 + E) * kN;
     const u32 mu0 = kc.d_mu61[2 * D], mu1 = kc.d_mu61[2 * D + 1];
-    u64 v[1][8];
     const ulonglong2 *pa0 = lm_ptr(a0, t), *pa1 = lm_ptr(a1, t), *pb0 = lm_ptr(b0, t), *pb1 = lm_ptr(b1, t);  // pair r at [r * kLm]
     auto one = [&](u64 x0, u64 y0) -> u64 {
         u32 xl, xh, yl, yh;
@@ -759,7 +759,12 @@ __device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb
             v[0][2 * r + 1] = one(x.y, y.y);
         }
     }
-    ntt_inverse<M, 1, false, false, SHFL>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv_t[D], kc.d_ninv_t_w[D]);  // [0, 2s)
+    ntt_inverse<M, 1, false, kTrailSync, SHFL>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv_t[D], kc.d_ninv_t_w[D]);  // [0, 2s)
+}
+template <int D, bool SHFL>
+__device__ __forceinline__ void tensor_intt_dual_body(const u64 *__restrict__ nb, int d, u64 *__restrict__ dst, u64 *smem, int t) {
+    u64 v[1][8];
+    tensor_intt_dual_regs<D, SHFL, false>(nb, d, v, smem, t);
     store_natural(dst, v[0], t);
 }
 template <bool SHFL>
@@ -889,6 +894,41 @@ __global__ void __launch_bounds__(256, 3) k_floor_sk_d(const u64 *__restrict__ t
         ulonglong2 *out = reinterpret_cast<ulonglong2 *>(c3 + opp * 2 * kN + i);
         out[0] = make_ulonglong2(ax, ay);
         out[kN / 2] = make_ulonglong2(bx, by);
+    }
+}
+
+// ---- K7d + K8d in one kernel (default for chunks >= 96 ops; FHE_B200_FUSE_TAIL=0 keeps the two kernels): one CTA per (output polynomial d, op) runs the three
+// dual words one after the other -- dyadic tensor, inverse transform -- parks the first two results at each thread's own eight
+// slots in shared memory (r * 512 + t: the coefficients it owns after every inverse transform) and finishes with
+// floor_sk_coeff_d on its eight coefficients, so the tensor product never goes through HBM (0.59 MB per op less DRAM traffic:
+// the batch runs into the board's power limit, where bytes not moved are clock).  Same structure as k_ks_finish: 2 CTAs per SM.
+__global__ void __launch_bounds__(kThreads, 2) k_tensor_floor_d(const u64 *__restrict__ nttbuf, u64 *__restrict__ c3) {
+    extern __shared__ __align__(16) u64 smem[];  // [3][kN]: exchange buffer, word 0, word 1
+    const size_t op = blockIdx.y;
+    const int d = blockIdx.x, t = threadIdx.x;
+    const u64 *nb = nttbuf + op * 20 * kN;
+    u64 *park0 = smem + kN, *park1 = smem + 2 * kN;
+    {
+        u64 v[1][8];
+        tensor_intt_dual_regs<0, false, true>(nb, d, v, smem, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) park0[r * kThreads + t] = v[0][r];
+    }
+    {
+        u64 v[1][8];
+        tensor_intt_dual_regs<1, false, true>(nb, d, v, smem, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) park1[r * kThreads + t] = v[0][r];
+    }
+    u64 v[1][8];
+    tensor_intt_dual_regs<2, false, false>(nb, d, v, smem, t);
+    u64 *out = c3 + (op * 3 + d) * 2 * kN;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        u64 o0, o1;
+        floor_sk_coeff_d(park0[r * kThreads + t], park1[r * kThreads + t], v[0][r], o0, o1);
+        out[r * kThreads + t] = o0;
+        out[kN + r * kThreads + t] = o1;
     }
 }
 
@@ -1230,14 +1270,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_digit_ntt_ksd(const u64 *__rest
         default: digit_ntt_ksd_body<2>(src, dst, smem, t); break;
     }
 }
-template <int D>
-__device__ __forceinline__ void ks_intt_ksd_body(const u64 *__restrict__ dg, const u64 *__restrict__ rkd, int k, u64 *__restrict__ dst,
-                                                 u64 *smem, int t) {
+template <int D, bool kTrailSync>
+__device__ __forceinline__ void ks_intt_ksd_regs(const u64 *__restrict__ dg, const u64 *__restrict__ rkd, int k, u64 (&v)[1][8], u64 *smem,
+                                                 int t) {
     using M = ModDual<D>;
     const u32 mu0 = kc.d_mu61[2 * D], mu1 = kc.d_mu61[2 * D + 1];
     const ulonglong2 *pd0 = lm_ptr(dg + (size_t)(0 * 3 + D) * kN, t), *pd1 = lm_ptr(dg + (size_t)(1 * 3 + D) * kN, t);
     const ulonglong2 *pk0 = lm_ptr(rkd + (size_t)((0 * 2 + k) * 3 + D) * kN, t), *pk1 = lm_ptr(rkd + (size_t)((1 * 2 + k) * 3 + D) * kN, t);
-    u64 v[1][8];
     auto mac = [&](u64 x0, u64 y0, u64 x1, u64 y1) -> u64 {
         u32 al, ah, bl, bh, cl, ch, dl, dh;
         unpack64(x0, al, ah);
@@ -1253,7 +1292,13 @@ __device__ __forceinline__ void ks_intt_ksd_body(const u64 *__restrict__ dg, con
         v[0][2 * r] = mac(x0.x, y0.x, x1.x, y1.x);
         v[0][2 * r + 1] = mac(x0.y, y0.y, x1.y, y1.y);
     }
-    ntt_inverse<M, 1, false, false>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv[D], kc.d_ninv_w[D]);  // [0, 2s)
+    ntt_inverse<M, 1, false, kTrailSync>(v, smem, kt.twi[M::kIndex], t, kc.d_ninv[D], kc.d_ninv_w[D]);  // [0, 2s)
+}
+template <int D>
+__device__ __forceinline__ void ks_intt_ksd_body(const u64 *__restrict__ dg, const u64 *__restrict__ rkd, int k, u64 *__restrict__ dst,
+                                                 u64 *smem, int t) {
+    u64 v[1][8];
+    ks_intt_ksd_regs<D, false>(dg, rkd, k, v, smem, t);
     store_natural(dst, v[0], t);
 }
 __global__ void __launch_bounds__(kThreads, 3) k_ks_intt_ksd(const u64 *__restrict__ dig, const u64 *__restrict__ rkd, u64 *__restrict__ ks) {
@@ -1370,6 +1415,40 @@ __global__ void __launch_bounds__(256, 3) k_ks_finish_ksd(const u64 *__restrict_
         ulonglong2 *po = reinterpret_cast<ulonglong2 *>(out + (op * 2 + k) * 2 * kN + i);
         po[0] = make_ulonglong2(ax, ay);
         po[kN / 2] = make_ulonglong2(bx, by);
+    }
+}
+
+// ---- k_ks_intt_ksd + k_ks_finish_ksd in one kernel (default for chunks >= 96 ops; FHE_B200_FUSE_TAIL=0 keeps the two kernels): one CTA per (output polynomial k, op), the three dual
+// words of U_k one after the other with the first two parked in shared memory (as k_tensor_floor_d): U_k never goes through HBM
+__global__ void __launch_bounds__(kThreads, 2) k_ks_tail_ksd(const u64 *__restrict__ dig, const u64 *__restrict__ rkd,
+                                                              const u64 *__restrict__ c3, u64 *__restrict__ out) {
+    extern __shared__ __align__(16) u64 smem[];  // [3][kN]
+    const size_t op = blockIdx.y;
+    const int k = blockIdx.x, t = threadIdx.x;
+    const u64 *dg = dig + op * 6 * kN;
+    u64 *park0 = smem + kN, *park1 = smem + 2 * kN;
+    {
+        u64 v[1][8];
+        ks_intt_ksd_regs<0, true>(dg, rkd, k, v, smem, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) park0[r * kThreads + t] = v[0][r];
+    }
+    {
+        u64 v[1][8];
+        ks_intt_ksd_regs<1, true>(dg, rkd, k, v, smem, t);
+#pragma unroll
+        for (int r = 0; r < 8; r++) park1[r * kThreads + t] = v[0][r];
+    }
+    u64 v[1][8];
+    ks_intt_ksd_regs<2, false>(dg, rkd, k, v, smem, t);
+    const u64 *pc = c3 + (op * 3 + k) * 2 * kN;
+    u64 *po = out + (op * 2 + k) * 2 * kN;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        u64 o0, o1;
+        ks_finish_coeff_ksd(park0[r * kThreads + t], park1[r * kThreads + t], v[0][r], pc[r * kThreads + t], pc[kN + r * kThreads + t], o0, o1);
+        po[r * kThreads + t] = o0;
+        po[kN + r * kThreads + t] = o1;
     }
 }
 
@@ -1963,6 +2042,10 @@ cudaError_t kernels_configure() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ks_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_tensor_floor_d, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem3);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ks_tail_ksd, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem3);
+    if (e != cudaSuccess) return e;
     return cudaSuccess;
 }
 
@@ -2095,6 +2178,27 @@ cudaError_t launch_tensor_intt(const u64 *nttbuf, u64 *tens, size_t n_ops, cudaS
     else if (behz_mode_() == 0) k_tensor_intt_d<false><<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens);
     else if (qlimb_ntt_mode()) k_tensor_intt<<<dim3(15, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 0);
     else k_tensor_intt<<<dim3(9, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf, tens, 1);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+// FHE_B200_FUSE_TAIL: bit 0 = tensor product + floor in one kernel (k_tensor_floor_d), bit 1 = key-switch MAC / inverse transforms +
+// division by P in one kernel (k_ks_tail_ksd).  Both trade a launch's occupancy (2 CTAs per SM) for 0.6 / 0.4 MB per op of HBM traffic.
+int fuse_tail() {
+    static const int mode = [] {
+        const char *v = getenv("FHE_B200_FUSE_TAIL");
+        return v ? atoi(v) : 3;  // default: both (964 k against 940 k ops/s in a short run, 958 k against 895 k sustained under the power cap)
+    }();
+    return mode;
+}
+cudaError_t launch_tensor_floor(const u64 *nttbuf, u64 *c3, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_tensor_floor_d<<<dim3(3, (unsigned)n_ops), kThreads, kSmem3, s>>>(nttbuf, c3);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return cudaGetLastError();
+}
+cudaError_t launch_ks_tail_ksd(const u64 *dig, const u64 *rkd, const u64 *c3, u64 *out, size_t n_ops, cudaStream_t s) {
+    if (n_ops == 0) return cudaSuccess;
+    k_ks_tail_ksd<<<dim3(2, (unsigned)n_ops), kThreads, kSmem3, s>>>(dig, rkd, c3, out);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return cudaGetLastError();
 }

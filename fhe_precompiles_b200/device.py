@@ -180,7 +180,7 @@ def frame_stride() -> int:
 
 
 KERNEL_NAMES = ("k_behz_tensor", "k_floor_sk", "k_relin_ks", "k_relin_finish", "k_ext_ntt", "k_tensor_intt", "k_digit_ntt", "k_ks_intt",
-                "k_ext_conv", "k_ks_finish", "k_rk_prepare_ksd", "k_digit_ntt_ksd", "k_ks_intt_ksd", "k_ks_finish_ksd")
+                "k_ext_conv", "k_ks_finish", "k_rk_prepare_ksd", "k_digit_ntt_ksd", "k_ks_intt_ksd", "k_ks_finish_ksd", "k_tensor_floor_d", "k_ks_tail_ksd")
 
 
 def set_kernel_timing(on: bool) -> None:

@@ -210,7 +210,7 @@ void fhe_b200_set_fused(int32_t on);
 void fhe_b200_set_call_timing(int32_t on);
 void fhe_b200_last_call_breakdown(double us[7]);
 void fhe_b200_set_kernel_timing(int32_t on);
-int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[14], uint64_t launches[14]);
+int32_t fhe_b200_kernel_timing_report(int32_t device, double ms[16], uint64_t launches[16]);
 /* Batched negacyclic NTT in place over n_limbs limbs of 4096 words; limb i uses modulus mods[i % n_mods]
  * (0 q0, 1 q1, 2 P, 3 b0, 4 b1, 5 m_sk). inverse != 0: bit-reversed -> natural, scaled by N^-1. */
 int32_t fhe_b200_ntt(int32_t device, uint64_t *data, size_t n_limbs, const int32_t *mods, int32_t n_mods, int32_t inverse,

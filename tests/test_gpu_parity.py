@@ -992,7 +992,8 @@ def test_device_sampler_exact_paths_on_crafted_draws(dev):
 
 
 def test_qlimb_recovery_equals_seals_form(dev, keys):
-    """The multiply is computed four ways -- default (tensor product AND key switch on the GPU's dual base), SEAL's form
+    """The multiply is computed five ways -- default (tensor product AND key switch on the GPU's dual base, fused tails), the
+    same with split tails (FHE_B200_FUSE_TAIL=0), SEAL's form
     (FHE_B200_QLIMB_NTT=1: 47 transforms), SEAL's 61-bit primes with the q-limbs recovered (FHE_B200_BEHZ=bsk), and the default
     with the key switch on SEAL's three key primes (FHE_B200_KS=seal) -- same bits on random and on extreme residues, equal to
     the oracle (which follows SEAL).  The key-switch paths only differ for batches >= 96 ops, hence the 128-op batch."""
@@ -1021,12 +1022,13 @@ print("SHA", hashlib.sha256(out.tobytes()).hexdigest())
     shas = {}
     # "0": the default (tensor product and key switch on the dual base); "1": SEAL's form (47 transforms) with SEAL's key switch;
     # "bsk": SEAL's 61-bit primes with the q-limbs recovered (33 transforms); "kss": the default with SEAL's key switch
+    # "split": the default arithmetic with the tensor product and U_k going through HBM between two kernels each
     for mode, env in (("0", {}), ("1", {"FHE_B200_QLIMB_NTT": "1", "FHE_B200_KS": "seal"}), ("bsk", {"FHE_B200_BEHZ": "bsk"}),
-                      ("kss", {"FHE_B200_KS": "seal"})):
+                      ("kss", {"FHE_B200_KS": "seal"}), ("split", {"FHE_B200_FUSE_TAIL": "0"})):
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=dict(os.environ, **env))
         assert r.returncode == 0, r.stdout + r.stderr
         shas[mode] = [ln for ln in r.stdout.splitlines() if ln.startswith("SHA")][0]
-    assert shas["0"] == shas["1"] == shas["bsk"] == shas["kss"]
+    assert shas["0"] == shas["1"] == shas["bsk"] == shas["kss"] == shas["split"]
     rng = np.random.default_rng(606)
     a, b = random_ct(rng, 128), random_ct(rng, 128)
     for l in range(2):
