@@ -675,37 +675,44 @@ __global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_d(u64 *__restrict__ ntt
         default: ntt_dual_body<2, SHFL>(limb, smem, t); break;
     }
 }
-// A/B variant (FHE_B200_EXT_FUSED=1): base extension and the three dual transforms of one input polynomial in one CTA --
-// the shared part of the extension is computed once per coefficient and kept in registers, so the extended operands never
-// make the round trip through HBM that k_ext_conv_d + k_ext_ntt_d give them.  grid (4 polys, ops), 2 CTAs per SM.
+// FHE_B200_EXT_FUSED=1: base extension and the three dual transforms of one input polynomial in one CTA -- the shared part
+// of the extension is computed once per coefficient and parked in shared memory at the thread's own eight slots (62-bit base as a
+// word, m and the sign as 16 bits), so the extended operands never make the round trip through HBM that k_ext_conv_d +
+// k_ext_ntt_d give them (0.7 MB per op) and the transforms keep their 40 registers: 72 KiB per CTA, 3 CTAs per SM.
+// grid (4 polys, ops).
 template <int D>
-__device__ __forceinline__ void ext_ntt_fused_limb(const u64 (&base)[8], const u32 (&mm)[8], u64 *__restrict__ dst, u64 *smem, int t) {
+__device__ __forceinline__ void ext_ntt_fused_limb(const u64 *park, const unsigned short *park_m, u64 *__restrict__ dst, u64 *smem, int t) {
     using M = ModDual<D>;
     u64 v[1][8];
 #pragma unroll
-    for (int r = 0; r < 8; r++) v[0][r] = ext_dual<D>(base[r], mm[r] & 0x7fffffffu, (mm[r] >> 31) != 0);
+    for (int r = 0; r < 8; r++) {
+        const u32 mm = park_m[r * kThreads + t];
+        v[0][r] = ext_dual<D>(park[r * kThreads + t], mm & 0x7fffu, (mm >> 15) != 0);
+    }
     ntt_forward<M, 1, false, true>(v, smem, kt.twf[M::kIndex], t);
     store_chunk8_lm(dst, v[0], t);
 }
-__global__ void __launch_bounds__(kThreads, 2) k_ext_ntt_f_d(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf) {
-    extern __shared__ __align__(16) u64 smem[];
+__global__ void __launch_bounds__(kThreads, 3) k_ext_ntt_f_d(const u64 *__restrict__ a, const u64 *__restrict__ b, u64 *__restrict__ nttbuf) {
+    extern __shared__ __align__(16) u64 smem[];  // [kN] exchange buffer | [kN] base | [kN] u16 m + sign
     const size_t op = blockIdx.y;
     const int p = blockIdx.x, t = threadIdx.x;
     const u64 *ct = (p < 2 ? a : b) + op * 4 * kN + (size_t)(p & 1) * 2 * kN;
-    u64 base[8];
-    u32 mm[8];
-#pragma unroll
+    u64 *park = smem + kN;
+    unsigned short *park_m = reinterpret_cast<unsigned short *>(smem + 2 * kN);
+#pragma unroll 1
     for (int r = 0; r < 8; r++) {
         const int i = r * kThreads + t;
+        u64 base;
         u32 m;
         bool neg;
-        ext_shared(ct[i], ct[kN + i], base[r], m, neg);
-        mm[r] = m | (neg ? 0x80000000u : 0u);
+        ext_shared(ct[i], ct[kN + i], base, m, neg);
+        park[i] = base;
+        park_m[i] = (unsigned short)(m | (neg ? 0x8000u : 0u));
     }
     u64 *dst = nttbuf + (op * 20 + (size_t)p * 5 + 2) * kN;
-    ext_ntt_fused_limb<0>(base, mm, dst, smem, t);
-    ext_ntt_fused_limb<1>(base, mm, dst + kN, smem, t);
-    ext_ntt_fused_limb<2>(base, mm, dst + 2 * kN, smem, t);
+    ext_ntt_fused_limb<0>(park, park_m, dst, smem, t);
+    ext_ntt_fused_limb<1>(park, park_m, dst + kN, smem, t);
+    ext_ntt_fused_limb<2>(park, park_m, dst + 2 * kN, smem, t);
 }
 // one lane of the dyadic tensor: operands in [0, 4s) -> product(s) mod s in [0, 2s)
 template <int NP>
@@ -2023,6 +2030,7 @@ cudaError_t measure_int_peak(int mode, double *tera_ops_per_s) {
 // launchers
 // =====================================================================================
 static const int kSmem1 = 1 * kN * 8, kSmem2 = 2 * kN * 8, kSmem3 = 3 * kN * 8, kSmem4 = 4 * kN * 8;
+static const int kSmemExtF = 2 * kN * 8 + kN * 2;  // k_ext_ntt_f_d: exchange buffer + parked base + parked (m, sign)
 
 cudaError_t kernels_configure() {
     cudaError_t e;
@@ -2041,6 +2049,8 @@ cudaError_t kernels_configure() {
     e = cudaFuncSetAttribute(k_ks_finish<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_ks_finish<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem2);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_ext_ntt_f_d, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemExtF);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_tensor_floor_d, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem3);
     if (e != cudaSuccess) return e;
@@ -2163,7 +2173,7 @@ cudaError_t launch_ext_conv(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_op
 // with ext_split(): the transforms only (launch_ext_conv must have filled the auxiliary limbs); otherwise extension + transforms
 cudaError_t launch_ext_ntt(const u64 *a, const u64 *b, u64 *nttbuf, size_t n_ops, cudaStream_t s) {
     if (n_ops == 0) return cudaSuccess;
-    if (behz_mode_() == 0 && ext_fused_d()) k_ext_ntt_f_d<<<dim3(4, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf);
+    if (behz_mode_() == 0 && ext_fused_d()) k_ext_ntt_f_d<<<dim3(4, (unsigned)n_ops), kThreads, kSmemExtF, s>>>(a, b, nttbuf);
     else if (behz_mode_() == 0 && dual_shfl()) k_ext_ntt_d<true><<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
     else if (behz_mode_() == 0) k_ext_ntt_d<false><<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(nttbuf);
     else if (ext_split_mode() && !qlimb_ntt_mode()) k_ext_ntt2<<<dim3(12, (unsigned)n_ops), kThreads, kSmem1, s>>>(a, b, nttbuf, 1);
