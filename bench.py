@@ -940,7 +940,8 @@ def main() -> None:
             "sharding": f"{world} rank(s), independent batches, no collective",
             "chunk_ops": int(os.environ.get("FHE_B200_CHUNK_OPS", "4096")),
             "subchunk_ops": int(os.environ.get("FHE_B200_SUBCHUNK_OPS", "0")),
-            "kernels": "split" if not int(os.environ.get("FHE_B200_FUSED", "0")) else "fused",
+            "kernels": ("multi-polynomial CTAs (FHE_B200_FUSED)" if int(os.environ.get("FHE_B200_FUSED", "0")) else
+                        f"one polynomial per CTA; BEHZ base {BEHZ}, key switch {KS}, fused tails {FUSE_TAIL}"),
         },
         "roofline": roofline,
         "clocks": clocks,
