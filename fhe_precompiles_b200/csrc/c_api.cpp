@@ -199,13 +199,17 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     // is paid per tile, not per call.  Two workers per core: while one waits on its lane another runs the codec.
     size_t nt = host_threads > 0 ? (size_t)host_threads : 2 * (size_t)std::thread::hardware_concurrency();
     if (nt == 0) nt = 1;
-    size_t tile = Engine::get().tile_ops();
+    if (const char *e = getenv("FHE_B200_BATCH_THREADS"))
+        if (host_threads <= 0 && atoi(e) > 0) nt = (size_t)atoi(e);
+    size_t tile = Engine::get().tile_ops_for(n);
     const size_t big = Engine::get().big_tile_ops();
+    bool serial_loops = true;
     if (Engine::get().device_codec() && big > tile && n >= 2 * big) {
         // a large batch: few big tiles (each stages its calls on the whole host pool and launches thousands of operand frames
         // at once), a handful of them in flight so that one tile's host phases overlap another's device phases
         tile = big;
         nt = std::min<size_t>(nt, 6);
+        serial_loops = false;
     } else {
         while (tile > 1 && (n + tile - 1) / tile < nt) tile /= 2;  // keep every worker busy on small batches
     }
@@ -213,9 +217,15 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     if (nt > tiles) nt = tiles;
     std::atomic<size_t> next{0};
     std::atomic<int64_t> failed{0};
+    if (nt < std::max<size_t>(2, std::thread::hardware_concurrency() / 2)) serial_loops = false;  // few workers: let tiles use idle cores
     auto worker = [&]() {
         std::vector<TileItem> items;
         std::vector<size_t> which;
+        struct SerialLoops {
+            bool on;
+            explicit SerialLoops(bool v) : on(v) { if (on) Engine::set_thread_serial_loops(true); }
+            ~SerialLoops() { if (on) Engine::set_thread_serial_loops(false); }
+        } serial_guard(serial_loops);
         for (;;) {
             const size_t t = next.fetch_add(1);
             if (t >= tiles) break;
@@ -460,8 +470,8 @@ int32_t fhe_b200_zstd_inflate(int32_t device, const uint8_t *const *frames, cons
     try {
         device_context(device);
         {
-            const char *v = getenv("FHE_B200_ZSTD_TWO_PHASE");  // 0 one warp per frame, 1 two-phase, 2 batch-oriented (default)
-            codec_set_two_phase(v && *v ? atoi(v) : 2);
+            const char *v = getenv("FHE_B200_ZSTD_TWO_PHASE");  // 0 one warp per frame, 1 two-phase, 2 batch-oriented, 3 (default) zstd_plan3.cuh
+            codec_set_two_phase(v && *v ? atoi(v) : 3);
         }
         std::vector<CodecJob> jobs(n);
         std::vector<uint8_t> staged(n * kFrameSlotBytes, 0);

@@ -12,6 +12,7 @@
 #include "params.h"
 #include "zstd_dec.h"
 #include "zstd_plan2.h"
+#include "zstd_plan3.cuh"
 
 namespace fheb {
 
@@ -125,6 +126,43 @@ __global__ void __launch_bounds__(32) k_zd2_exec(const uint8_t *frames, uint8_t 
     size_t dlen = 0;
     const int rc = zd::plan2_exec(frames + job.src_off, &sc->plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, &dlen);
     status[j] = (rc == zd::kZdOk && dlen == kCtPayloadBytes) ? kJobOk : kJobFallback;
+}
+
+// ---- fourth generation (zstd_plan3.cuh, the default): parse as above -> Huffman streams (thread per stream; ciphertext frames
+// have raw literals and skip it) and sequence chains (warp per frame, tables in shared memory) -> execution (CTA per frame)
+__global__ void __launch_bounds__(128) k_zd3_huf(const uint8_t *frames, const CodecJob *jobs, JobScratchAny *scratch, int n) {
+    const int j = blockIdx.x * 32 + (threadIdx.x & 31), role = threadIdx.x >> 5;
+    if (j >= n) return;
+    const CodecJob job = jobs[j];
+    if (job.kind != kJobZstd) return;
+    JobScratch2 *sc = &scratch[j].b;
+    sc->plan.huf_bad[role] = zd::plan2_huf(frames + job.src_off, &sc->plan, &sc->tabs, sc->lits, role) ? 0 : 1;
+}
+__global__ void __launch_bounds__(32) k_zd3_seq(const uint8_t *frames, const CodecJob *jobs, JobScratchAny *scratch, int n) {
+    extern __shared__ __align__(16) uint8_t smem3[];
+    const int j = blockIdx.x * zd3::kSeqFrames + (threadIdx.x >> 3);
+    const bool in_range = j < n;
+    const CodecJob job = in_range ? jobs[j] : CodecJob{0, 0, kJobNone, 0, 0};
+    JobScratch2 *sc = &scratch[in_range ? j : 0].b;
+    const bool have = in_range && job.kind == kJobZstd && sc->plan.status == zd::kZdOk;
+    const bool ok = zd3::seq_frames(frames + job.src_off, &sc->plan, &sc->tabs, sc->seqs, have, (uint32_t *)smem3);
+    if (have && (threadIdx.x & 7) == 0) sc->plan.seq_bad = ok ? 0 : 1;
+}
+__global__ void __launch_bounds__(zd3::kExecThreads, 1) k_zd3_exec(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs,
+                                                                     int32_t *status, JobScratchAny *scratch, int n) {
+    extern __shared__ __align__(16) uint8_t smem3[];
+    for (int j = blockIdx.x; j < n; j += gridDim.x) {
+        const CodecJob job = jobs[j];
+        if (job.kind != kJobZstd) continue;
+        JobScratch2 *sc = &scratch[j].b;
+        const zd::Plan2 *plan = &sc->plan;
+        int rc = zd::kZdFallback;
+        if (plan->status == zd::kZdOk && !plan->seq_bad && !plan->huf_bad[0] && !plan->huf_bad[1] && !plan->huf_bad[2] && !plan->huf_bad[3] &&
+            plan->content == kCtPayloadBytes)
+            rc = zd3::exec_frame(frames + job.src_off, plan, sc->seqs, sc->lits, payloads + (size_t)j * kPayloadStride, smem3);
+        __syncthreads();  // the shared buffers are reused by the next frame
+        if (threadIdx.x == 0) status[j] = rc == zd::kZdOk ? kJobOk : kJobFallback;
+    }
 }
 
 constexpr int kSplit = 8;  // blocks per ciphertext in the parallel kernels (latency of a single call)
@@ -263,9 +301,10 @@ __global__ void __launch_bounds__(256) k_ct_pack40(const u64 *words, uint8_t *fr
 
 size_t codec_work_bytes() { return sizeof(JobScratchAny); }
 
-// 0 one warp per frame, 1 two-phase (thread-per-frame plan + warp-per-frame execute), 2 (default) batch-oriented: zstd_plan2.h
-static std::atomic<int> g_inflate_mode{2};
-void codec_set_two_phase(int mode) { g_inflate_mode.store(mode < 0 || mode > 2 ? 2 : mode); }
+// 0 one warp per frame, 1 two-phase (thread-per-frame plan + warp-per-frame execute), 2 batch-oriented (zstd_plan2.h),
+// 3 (default) warp-per-frame sequence chains on shared-memory tables + CTA-per-frame parallel execution (zstd_plan3.cuh)
+static std::atomic<int> g_inflate_mode{3};
+void codec_set_two_phase(int mode) { g_inflate_mode.store(mode < 0 || mode > 3 ? 3 : mode); }
 
 cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const CodecJob *jobs, int32_t *status, void *work,
                                  const uint8_t *prefix, u64 *dst_a, u64 *dst_b, int n_jobs, bool any_zstd, bool any_packed,
@@ -274,7 +313,23 @@ cudaError_t launch_codec_inflate(const uint8_t *frames, uint8_t *payloads, const
     cudaError_t ce = cudaMemsetAsync(status, 0, (size_t)n_jobs * sizeof(int32_t), s);  // kJobPending
     if (ce != cudaSuccess) return ce;
     const int mode = g_inflate_mode.load();
-    if (any_zstd && mode == 2) {
+    if (any_zstd && mode == 3) {
+        static std::atomic<int> configured{0};  // (per process; the attributes are per function and device-independent in effect)
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (!((configured.load() >> dev) & 1)) {
+            cudaError_t e = cudaFuncSetAttribute(k_zd3_exec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zd3::kExecSmem);
+            if (e != cudaSuccess) return e;
+            configured.fetch_or(1 << dev);
+        }
+        k_zd2_parse<<<(n_jobs + 31) / 32, 32, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
+        k_zd3_huf<<<(n_jobs + 31) / 32, 128, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
+        k_zd3_seq<<<(n_jobs + zd3::kSeqFrames - 1) / zd3::kSeqFrames, 32, zd3::kSeqSmem, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
+        k_zd3_exec<<<n_jobs < 2 * sms ? n_jobs : 2 * sms, zd3::kExecThreads, zd3::kExecSmem, s>>>(frames, payloads, jobs, status,
+                                                                                                    (JobScratchAny *)work, n_jobs);
+        g_codec_launches.fetch_add(4, std::memory_order_relaxed);
+    } else if (any_zstd && mode == 2) {
         k_zd2_parse<<<(n_jobs + 31) / 32, 32, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
         k_zd2_decode<<<(n_jobs + 31) / 32, 160, 0, s>>>(frames, jobs, (JobScratchAny *)work, n_jobs);
         k_zd2_exec<<<(n_jobs + 31) / 32, 32, 0, s>>>(frames, payloads, jobs, status, (const JobScratchAny *)work, n_jobs);

@@ -42,11 +42,15 @@ uint64_t cheap_tag(Span s) {
     }
     return h;
 }
+// Set on the workers of a batch that already runs one tile per host thread: their tiles' loops stay on the worker.  (Measured:
+// with 32 tile workers on 16 cores, a nested parallel_for waited ~400 us per call for helper copies that had been started and
+// then descheduled - more than the loops' own work.)
+thread_local bool tl_serial_loops = false;
 // fn(i) for i in [0, count): on the caller alone for short loops, otherwise shared with pool threads in chunks of `grain`
 template <class F>
 void parallel_for(size_t count, size_t grain, F &&fn) {
     const size_t hw = std::max(1u, std::thread::hardware_concurrency());
-    if (count < 2 * grain || hw < 2) {
+    if (count < 2 * grain || hw < 2 || tl_serial_loops) {
         for (size_t i = 0; i < count; i++) fn(i);
         return;
     }
@@ -61,12 +65,47 @@ void parallel_for(size_t count, size_t grain, F &&fn) {
     };
     HostPool::get().run(std::min(hw - 1, (count + grain - 1) / grain - 1), body);
 }
+// FHE_B200_TILE_PROFILE=<n >= 1>: wall time of binary_tile's phases summed over all tile workers, printed when the process exits;
+// the first n calls (warm-up: lanes, pinned buffers, key upload) are not counted
+struct TileProfile {
+    static constexpr int kPhases = 8;
+    std::atomic<uint64_t> ns[kPhases];
+    std::atomic<uint64_t> tiles{0}, calls{0}, seen{0};
+    uint64_t skip = 0;
+    bool on = false;
+    TileProfile() {
+        for (auto &v : ns) v = 0;
+        const char *e = getenv("FHE_B200_TILE_PROFILE");
+        on = e && atoll(e) >= 1;
+        skip = on ? (uint64_t)atoll(e) : 0;
+    }
+    ~TileProfile() {
+        if (!on || !tiles.load()) return;
+        static const char *names[kPhases] = {"unpack+key", "framing", "plan", "stage", "enqueue", "device wait", "wrap", "host pass"};
+        fprintf(stderr, "[fhe_b200 tile profile] %llu tiles, %llu calls; us per call (summed over workers):", (unsigned long long)tiles.load(),
+                (unsigned long long)calls.load());
+        for (int k = 0; k < kPhases; k++) fprintf(stderr, " %s %.1f", names[k], ns[k].load() * 1e-3 / (double)calls.load());
+        fprintf(stderr, "\n");
+    }
+};
+TileProfile g_tile_profile;
+struct PhaseClock {
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    bool counted = false;
+    void lap(int phase) {
+        if (!counted) return;
+        const auto now = std::chrono::steady_clock::now();
+        g_tile_profile.ns[phase] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(now - t).count();
+        t = now;
+    }
+};
 }  // namespace
 
 Engine &Engine::get() {
     static Engine *e = new Engine();
     return *e;
 }
+void Engine::set_thread_serial_loops(bool on) { tl_serial_loops = on; }
 
 Engine::Engine() {
     HostContext::get();
@@ -80,18 +119,21 @@ Engine::Engine() {
         helper_decode_ = !(v && *v == '0');
         v = getenv("FHE_B200_DEVICE_CODEC");
         device_codec_ = !(v && *v == '0');
-        // 0 (default) never, 1 always, 2 when a tile brings at least FHE_B200_DEVICE_ZSTD_MIN_FRAMES libzstd frames.  Opt-in: measured on
-        // B200 (profiles/r2_codec.md) the device decoder sustains 190 k frames/s with 8,192 frames in flight against 145 k frames/s
-        // for libzstd on 16 host cores, but a frame is a chain of ~16 k dependent steps (11 ms on one GPU thread), so a tile
-        // waits tens of ms for its frames and the byte surface as a whole gets slower, not faster.
-        device_zstd_ = (v && *v == '1') ? 1 : (v && *v == '2') ? 2 : 0;
+        // libzstd-written operand frames of a tile are inflated on the GPU (codec_kernels.cu, zstd_plan3.cuh): 0 never, 1 always,
+        // 2 (default) when the tile brings at least FHE_B200_DEVICE_ZSTD_MIN_FRAMES of them.  fhe_b200_batch cuts a large batch
+        // into tiles of zstd_tile_ops() calls so that the default applies to it; single calls and small batches inflate on the
+        // host (a frame is a 16 k-step chain: ~3 ms on the GPU however few frames there are, 0.11 ms on a host core).
+        v = getenv("FHE_B200_DEVICE_ZSTD");
+        device_zstd_ = (v && *v == '1') ? 1 : (v && *v == '0') ? 0 : 2;
         v = getenv("FHE_B200_CALL_GRAPHS");
         call_graphs_ = !(v && *v == '0');
     }
-    device_zstd_min_frames_ = env_size("FHE_B200_DEVICE_ZSTD_MIN_FRAMES", 256);
+    device_zstd_min_frames_ = env_size("FHE_B200_DEVICE_ZSTD_MIN_FRAMES", 128);
+    zstd_tile_ops_ = env_size("FHE_B200_ZSTD_TILE_OPS", 128);
+    zstd_tile_min_batch_ = env_size("FHE_B200_ZSTD_TILE_MIN_BATCH", 2048);
     {
         const char *v = getenv("FHE_B200_HOST_INFLATE_PCT");  // share of a tile's libzstd frames the host cores inflate meanwhile
-        host_inflate_pct_ = (v && *v) ? (size_t)std::min(100, std::max(0, atoi(v))) : 35;
+        host_inflate_pct_ = (v && *v) ? (size_t)std::min(100, std::max(0, atoi(v))) : 0;
     }
     big_tile_ops_ = env_size("FHE_B200_BIG_TILE_OPS", 0);  // opt-in: large batches run in tiles of this many calls (see c_api.cpp)
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
@@ -1051,6 +1093,9 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
     std::vector<Prep> prep(cnt);
     std::vector<size_t> order;
     order.reserve(cnt);
+    PhaseClock pc;
+    if (g_tile_profile.on && g_tile_profile.seen.fetch_add(cnt) >= g_tile_profile.skip)
+        pc.counted = true, g_tile_profile.tiles++, g_tile_profile.calls += cnt;
 
     // pass 1, reference order (pack.rs:261-263): framing, then the public key (a ~400 KB comparison with the cached key per call:
     // shared with pool threads when the tile is large)
@@ -1076,6 +1121,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
     });
     for (size_t i = 0; i < cnt; i++)
         if (prep[i].live) order.push_back(i);
+    pc.lap(0);
     const double t_unpack = us_since(t_start);
     struct Run {
         int cls;
@@ -1153,6 +1199,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
             }
             g.clean = clean;
         });
+        pc.lap(1);
         // (B) serial: slots, jobs and staging offsets.  libzstd-written frames go to the device decoder when it is on -- always
         // (FHE_B200_DEVICE_ZSTD=1) or, by default, when the tile brings enough frames to fill the GPU -- except for the share
         // the host cores inflate meanwhile (FHE_B200_HOST_INFLATE_PCT): both decoders work on the same tile at once.
@@ -1200,6 +1247,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
             slot_item.push_back(i);
             slot_stg.push_back(oi);
         }
+        pc.lap(2);
         if (slots) {
             // (C) in parallel: bytes into the pinned staging -- frames as they are, host-inflated payloads, encoded scalars
             parallel_for(slots, 2, [&](size_t k) {
@@ -1218,6 +1266,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                     for (int c = 0; c < g.nct; c++) lane->h_jobs[g.job0 + c].kind = kJobNone;  // the kernels skip it; its slot computes on stale data
                 }
             });
+            pc.lap(3);
             if (njobs) {
                 if (fcur) cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, fcur, cudaMemcpyHostToDevice, s), "H2D frames");
                 cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)njobs * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
@@ -1255,7 +1304,9 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
             if (njobs)
                 cuda_throw(cudaMemcpyAsync(lane->h_status, lane->d_status, (size_t)njobs * sizeof(int32_t), cudaMemcpyDeviceToHost, s),
                            "D2H status");
+            pc.lap(4);
             cuda_throw(cudaStreamSynchronize(s), "stream sync");
+            pc.lap(5);
             // (D) in parallel: results into their own buffers; calls the device handed back are collected for the host pass
             std::vector<uint8_t> redo(slots, 0);
             parallel_for(slots, 4, [&](size_t k) {
@@ -1293,6 +1344,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         }
         std::stable_sort(rest.begin(), rest.end(), by_class);
         order.swap(rest);
+        pc.lap(6);
     }
 
     // ---- host pass: operands into adjacent staging slots, class by class; a call that fails here gives its slot to the next
@@ -1364,6 +1416,7 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         TileItem &it = items[slot_item[k]];
         it.rc = encode_ciphertext(prep[slot_item[k]].va, lane->h_out + k * kCtWords, &it.out);
     }
+    pc.lap(7);
     if (timed) {
         CallBreakdown &b = tl_breakdown;
         float ms[3] = {0, 0, 0};

@@ -114,6 +114,13 @@ class Engine {
     // Per-call results and error codes are exactly those of binary_op (which is a tile of one).
     void binary_tile(TileItem *items, size_t cnt);
     size_t tile_ops() const { return tile_ops_; }
+    // tile size for a batch of n calls: large batches run in tiles big enough for the device zstd decoder to take their operand
+    // frames (device_zstd_ == 2), everything else in tile_ops_
+    size_t tile_ops_for(size_t n) const {
+        return (device_codec_ && device_zstd_ == 2 && n >= zstd_tile_min_batch_ && zstd_tile_ops_ > tile_ops_) ? zstd_tile_ops_ : tile_ops_;
+    }
+    // the calling thread is one of many tile workers: binary_tile keeps its per-call loops on it instead of sharing them with the pool
+    static void set_thread_serial_loops(bool on);
     // tile size of a large batch: big tiles put thousands of operand frames in flight per launch (the device zstd decoder's
     // throughput comes from frames in flight) and their staging loops are shared with the host pool
     size_t big_tile_ops() const { return big_tile_ops_; }
@@ -203,8 +210,9 @@ class Engine {
     void drop_graphs(Lane *lane);
     // libzstd-written operand frames inflated on the GPU (zstd_plan2.h): 0 (default) never, 1 always, 2 when a tile brings at
     // least device_zstd_min_frames_ of them; host_inflate_pct_ % of those frames are inflated by the host cores meanwhile
-    int device_zstd_ = 0;
-    size_t device_zstd_min_frames_ = 256, host_inflate_pct_ = 35;
+    int device_zstd_ = 2;
+    size_t device_zstd_min_frames_ = 128, host_inflate_pct_ = 0;
+    size_t zstd_tile_ops_ = 128, zstd_tile_min_batch_ = 2048;
     size_t tile_ops_ = 16, big_tile_ops_ = 0;
     bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
     std::atomic<bool> call_timing_{false};

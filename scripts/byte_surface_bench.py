@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def child(n: int, distinct: int = 256) -> None:
+def child(n: int, distinct: int = int(os.environ.get("BSB_DISTINCT", "256"))) -> None:
     from fhe_precompiles_b200 import FHE, _lib, pack
 
     L = _lib.lib()
@@ -54,7 +54,7 @@ def child(n: int, distinct: int = 256) -> None:
         for i in range(n):
             L.fhe_free(arr[i].output)
         rates.append(n / dt_)
-    knobs = {k: os.environ.get(k, "default") for k in ("FHE_B200_DEVICE_ZSTD", "FHE_B200_HOST_INFLATE_PCT", "FHE_B200_BIG_TILE_OPS")}
+    knobs = {k: os.environ.get(k, "default") for k in ("FHE_B200_DEVICE_ZSTD", "FHE_B200_HOST_INFLATE_PCT", "FHE_B200_BIG_TILE_OPS", "FHE_B200_ZSTD_WRITER")}
     print(json.dumps({"calls": n, "cores": os.cpu_count(), **knobs, "calls_per_s_by_rep": [round(r) for r in rates], "best": round(max(rates[1:]))}),
           flush=True)
 
@@ -71,6 +71,12 @@ def main() -> None:
         (4096, {"FHE_B200_BIG_TILE_OPS": "1024", "FHE_B200_DEVICE_ZSTD": "2", "FHE_B200_HOST_INFLATE_PCT": "50"}),
         (8192, {"FHE_B200_BIG_TILE_OPS": "1024", "FHE_B200_DEVICE_ZSTD": "2", "FHE_B200_HOST_INFLATE_PCT": "25"}),
     ]
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep3":  # the fourth-generation device decoder (zstd_plan3.cuh)
+        sweeps = [(4096, {}), (4096, {"FHE_B200_ZSTD_WRITER": "1"})]
+        for big in ("128", "256", "512"):
+            for pct in ("0", "25", "50"):
+                sweeps.append((8192, {"FHE_B200_BIG_TILE_OPS": big, "FHE_B200_DEVICE_ZSTD": "2", "FHE_B200_HOST_INFLATE_PCT": pct,
+                                      "FHE_B200_DEVICE_ZSTD_MIN_FRAMES": "64", "FHE_B200_ZSTD_WRITER": "1"}))
     for n, env in sweeps:
         e = dict(os.environ)
         e.update(env)

@@ -17,7 +17,7 @@ p = ct()
 cts = [ct() for _ in range(16)]
 frs = [z.compress(c, 3) for c in cts]
 t = bytes(rng.choice(list(b"abcdefgh \n"), size=Z.PAYLOAD).astype(np.uint8))
-for mode in (sys.argv[1:] or ("2", "1", "0")):
+for mode in (sys.argv[1:] or ("3", "2", "1", "0")):
     os.environ["FHE_B200_ZSTD_TWO_PHASE"] = mode
     print("two_phase =", mode)
     run("warm", [frs[0]], [cts[0]])

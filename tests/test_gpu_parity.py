@@ -359,9 +359,9 @@ def test_batch_tiles_equal_single_calls(keys):
     assert all(got[k] == want[i] for k, i in enumerate(order))
 
 
-@pytest.mark.parametrize("two_phase", ["0", "1", "2"])
+@pytest.mark.parametrize("two_phase", ["0", "1", "2", "3"])
 def test_device_zstd_inflate_matches_libzstd(dev, two_phase, monkeypatch):
-    """k_zstd_inflate (0) / k_zstd_plan + k_zstd_execute (1) / k_zd2_parse + k_zd2_decode + k_zd2_exec (2, the default; csrc/zstd_dec.h
+    """k_zstd_inflate (0) / k_zstd_plan + k_zstd_execute (1) / k_zd2_parse + k_zd2_decode + k_zd2_exec (2) / k_zd2_parse + k_zd3_seq + k_zd3_exec (3, the default; csrc/zstd_dec.h
     and zstd_plan2.h on the device): ciphertext-payload frames written by libzstd at several levels, by the
     structured writer, other content of the same size (Huffman literals, RLE, raw blocks) and corrupted frames. A frame the
     device accepts must be byte-identical to libzstd's output; everything else must be handed back (status 2)."""

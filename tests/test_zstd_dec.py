@@ -33,10 +33,25 @@ def zd_lib(tmp_path_factory):
 
         return decode
 
-    return {"fused": make(lib.zd_decode), "two_phase": make(lib.zd_decode_two_phase), "v2": make(lib.zd_decode_v2)}
+    def make_v3():
+        fn = lib.zd_decode_v3
+        fn.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                       ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_long)]
+
+        def decode(frame: bytes):
+            n, rounds, polls = ctypes.c_size_t(), ctypes.c_int(), ctypes.c_long()
+            rc = fn(frame, len(frame), buf, cap, ctypes.byref(n), ctypes.byref(rounds), ctypes.byref(polls))
+            assert rc != 2, "the parallel executor's copy phase stopped making progress"
+            decode.rounds, decode.polls = rounds.value, polls.value
+            return rc, (buf.raw[: n.value] if rc == 0 else None)
+
+        decode.max_content = 131169  # one ciphertext payload: what k_zd3_exec holds in shared memory
+        return decode
+
+    return {"fused": make(lib.zd_decode), "two_phase": make(lib.zd_decode_two_phase), "v2": make(lib.zd_decode_v2), "v3": make_v3()}
 
 
-@pytest.fixture(params=["fused", "two_phase", "v2"])
+@pytest.fixture(params=["fused", "two_phase", "v2", "v3"])
 def zd(request, zd_lib):
     return zd_lib[request.param]
 
@@ -69,7 +84,11 @@ def test_reference_fixtures_decode_identically(zd):
         frames.append(_frame_in(F.WithContext.read(r).blob))
     for fr in frames:
         rc, got = zd(fr)
-        assert rc == 0 and got == F.zstd().decompress(fr)
+        want = F.zstd().decompress(fr)
+        if len(want) > getattr(zd, "max_content", 1 << 30):
+            assert rc == 1  # (keys: the parallel executor holds one ciphertext payload)
+            continue
+        assert rc == 0 and got == want
 
 
 def _samples(rng):
@@ -94,6 +113,9 @@ def test_random_frames_at_many_levels(zd):
                 fr = z.compress(data, lvl)
                 rc, got = zd(fr)
                 assert rc in (0, 1) and (rc == 1 or got == data), (len(data), lvl)
+                if len(data) > getattr(zd, "max_content", 1 << 30):
+                    assert rc == 1
+                    continue
                 ok += rc == 0
                 total += 1
     payload = b"\x07" * 97 + np.stack([rng.integers(0, 1 << 36, 4096, dtype=np.uint64) for _ in range(4)]).tobytes()
@@ -131,3 +153,22 @@ def test_mutated_frames_never_decode_wrongly(zd):
         else:
             handed_back += 1
     assert accepted > 100 and handed_back > 100
+
+
+def test_parallel_executor_resolves_ciphertext_frames_by_jumping(zd_lib):
+    """zstd_exec3.h on what it is built for: a level-3 ciphertext frame has ~16 k matches in 16 dependency chains ~1,000 long
+    (the top-nibble tails), most 5-byte matches read a literal followed by a match.  The pointer jumping (with the one split)
+    must leave next to nothing to the copy phase's polling, in a logarithmic number of rounds."""
+    zd = zd_lib["v3"]
+    rng = np.random.default_rng(8)
+    q = (0xFFFFEE001, 0xFFFFC4001)
+    z = F.zstd()
+    for _ in range(4):
+        data = bytes(rng.integers(0, 256, 97, dtype=np.uint8)) + np.stack(
+            [rng.integers(0, q[l], 4096, dtype=np.uint64) for _ in range(2) for l in range(2)]).tobytes()
+        for lvl in (1, 3, 7):
+            rc, got = zd(z.compress(data, lvl))
+            assert rc == 0 and got == data
+            assert zd.rounds <= 24 and zd.polls <= 2000, (lvl, zd.rounds, zd.polls)
+    rc, got = zd(F.zstd_structured_frame(data))  # one chain of 16,382 matches at offset 8
+    assert rc == 0 and got == data and zd.rounds <= 24
