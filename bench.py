@@ -342,7 +342,9 @@ def e2e_byte_surface(fdev, a, b, net_pub: bytes, steps: int, world: int, barrier
                "level 3; results written with libzstd level 3 on the host pool = byte for byte what SEAL's save() writes (default)",
         "structured_writer": {"value": rate_struct, "unit": "calls/s", "output_bytes_per_step": out_struct,
                               "note": "fhe_b200_set_zstd_writer(1): result frames laid out directly, written on the GPU"},
-        "device_zstd": os.environ.get("FHE_B200_DEVICE_ZSTD", "default"),
+        "device_zstd": os.environ.get("FHE_B200_DEVICE_ZSTD", "default") + " (default 2: a batch of >= 2,048 calls runs in 128-call tiles "
+                       "whose libzstd operand frames are inflated on the GPU - k_zd2_parse / k_zd3_seq / k_zd3_exec, byte-identical to libzstd "
+                       "or handed back; 0: host libzstd only)",
     }
 
 

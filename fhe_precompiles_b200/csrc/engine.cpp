@@ -1249,27 +1249,45 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
         }
         pc.lap(2);
         if (slots) {
-            // (C) in parallel: bytes into the pinned staging -- frames as they are, host-inflated payloads, encoded scalars
+            // (C) bytes into the pinned staging -- frames as they are, encoded scalars -- and the device decoder is started on the
+            // frames; (C2) the payloads the host inflates follow while the GPU decodes (hybrid tiles: FHE_B200_HOST_INFLATE_PCT)
+            const auto fail_slot = [&](Stg &g) {
+                g.bad = true;
+                for (int c = 0; c < g.nct; c++) lane->h_jobs[g.job0 + c].kind = kJobNone;  // the kernels skip it; its slot computes on stale data
+            };
             parallel_for(slots, 2, [&](size_t k) {
                 Stg &g = stg[slot_stg[k]];
                 TileItem &it = items[slot_item[k]];
                 Prep &p = prep[slot_item[k]];
-                bool ok = true;
-                for (int c = 0; ok && c < g.nct; c++) {
-                    if (g.on_host[c]) ok = inflate_ct_payload(g.frames[c], lane->h_payloads + (size_t)(g.job0 + c) * kPayloadStride);
-                    else memcpy(lane->h_frames + g.off[c], g.frames[c].p, g.frames[c].n);
-                }
-                if (ok && it.shape != Shape::CtCt)
-                    ok = encode_scalar(it.kind, it.shape == Shape::CtPt ? p.sb : p.sa, lane->h_plain + k * kN) == kOk;
-                if (!ok) {
-                    g.bad = true;
-                    for (int c = 0; c < g.nct; c++) lane->h_jobs[g.job0 + c].kind = kJobNone;  // the kernels skip it; its slot computes on stale data
-                }
+                for (int c = 0; c < g.nct; c++)
+                    if (!g.on_host[c]) memcpy(lane->h_frames + g.off[c], g.frames[c].p, g.frames[c].n);
+                if (it.shape != Shape::CtCt && encode_scalar(it.kind, it.shape == Shape::CtPt ? p.sb : p.sa, lane->h_plain + k * kN) != kOk)
+                    fail_slot(g);
             });
             pc.lap(3);
+            const bool split_codec = any_zstd && any_payload;  // decode on the device first, inflate the host's share meanwhile
             if (njobs) {
                 if (fcur) cuda_throw(cudaMemcpyAsync(lane->d_frames, lane->h_frames, fcur, cudaMemcpyHostToDevice, s), "H2D frames");
                 cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)njobs * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
+            }
+            if (split_codec)
+                cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix,
+                                                lane->d_a, lane->d_b, njobs, any_zstd, any_packed, any_payload, s, kCodecDecode),
+                           "codec decode");
+            if (any_payload) {
+                std::atomic<bool> any_failed{false};
+                parallel_for(slots, 2, [&](size_t k) {
+                    Stg &g = stg[slot_stg[k]];
+                    if (g.bad) return;
+                    for (int c = 0; c < g.nct; c++)
+                        if (g.on_host[c] && !inflate_ct_payload(g.frames[c], lane->h_payloads + (size_t)(g.job0 + c) * kPayloadStride)) {
+                            fail_slot(g);
+                            any_failed = true;
+                            break;
+                        }
+                });
+                if (any_failed)  // (the first copy of the job list may or may not have seen the cleared kinds: either is fine)
+                    cuda_throw(cudaMemcpyAsync(lane->d_jobs, lane->h_jobs, (size_t)njobs * sizeof(CodecJob), cudaMemcpyHostToDevice, s), "H2D jobs");
             }
             // payloads inflated on the host: one copy per run of adjacent payload slots
             for (int j0 = 0; j0 < njobs;) {
@@ -1289,7 +1307,8 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                                            (slots - ctct_slots) * kN * 2, cudaMemcpyHostToDevice, s),
                            "H2D plain");
             cuda_throw(launch_codec_inflate(lane->d_frames, lane->d_payloads, lane->d_jobs, lane->d_status, lane->d_work, lane->d_prefix,
-                                            lane->d_a, lane->d_b, njobs, any_zstd, any_packed, any_payload, s),
+                                            lane->d_a, lane->d_b, njobs, any_zstd, any_packed, any_payload, s,
+                                            split_codec ? kCodecUnpack : kCodecAll),
                        "codec inflate");
             launch_runs(runs);
             int32_t *d_cflag = lane->d_status + 2 * lane->cap, *h_cflag = lane->h_status + 2 * lane->cap;

@@ -1,7 +1,9 @@
 // Parallel execution of a zstd block's sequences: the per-sequence steps of k_zd3_exec (zstd_plan3.cuh).  Host + device source:
 // tests/zd_host.cpp runs the same steps thread by thread (zd_decode_v3) against libzstd, so the logic is tested without a GPU.
 //
-// One CTA per frame.  Shared memory: the frame's output (131,200 B), one "pending" bit and one "match start" bit per output byte.
+// One CTA per frame.  Shared memory: the frame's output (131,200 B), one "pending" bit and one "match start" bit per output byte,
+// and the block's literals when they fit in 56 KB (a ciphertext block has 55.7 KB of raw literals: staged with coalesced loads,
+// so that the per-sequence byte copies of step 1 do not wait on global memory one byte at a time).
 //  1 positions   block-wide prefix sums over (literal length, literal + match length) give every sequence the place of its
 //                literals and of its match; literals are copied, the match region is marked pending, its first byte marked as a
 //                start and its first three bytes (a match is >= 3 bytes) hold the match's PUBLISHED OFFSET (start - source):
@@ -35,7 +37,8 @@ constexpr uint32_t kExecChunk = kExecThreads * kExecPer;          // sequences p
 constexpr int kExecMaxRounds = 64;
 constexpr size_t kExecOutBytes = 131200;                          // kPayloadStride: the frame's content (131,169) + store slack
 constexpr size_t kExecBitWords = (kExecOutBytes + 31) / 32 + 2;   // one bit per output byte (+ slack for pair loads)
-constexpr size_t kExecSmem = kExecOutBytes + 2 * kExecBitWords * 4 + 64 * 8 + 64;
+constexpr size_t kExecLitBytes = 56 << 10;                        // a block's literals are staged in shared memory when they fit
+constexpr size_t kExecSmem = kExecOutBytes + 2 * kExecBitWords * 4 + 64 * 8 + 64 + kExecLitBytes;  // 221,936 of 232,448
 
 #if defined(__CUDA_ARCH__)
 #define ZD3_OR(p, v) atomicOr((p), (v))

@@ -263,6 +263,7 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
     uint32_t *start = pend + kExecBitWords;
     uint64_t *tmp = (uint64_t *)(start + kExecBitWords);
     int *bad = (int *)(tmp + 64);
+    uint8_t *lit_smem = (uint8_t *)(tmp + 64) + 64;
     const int t = threadIdx.x;
     if (t == 0) *bad = 0;
     for (uint32_t k = t; k < 2 * kExecBitWords; k += kExecThreads) pend[k] = 0;  // both bitmaps
@@ -291,23 +292,60 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
         const int lit_rle = bp.lit_mode == 1 ? bp.lit_rle : -1;
         const uint32_t nseq = bp.nseq, regen = bp.regen;
         uint64_t *so = seqs + bp.seq_off;
-        // ---- 1 positions: thread t owns sequences [lo, hi)
-        const uint32_t per = (nseq + kExecThreads - 1) / kExecThreads;
-        const uint32_t lo = min((uint32_t)t * per, nseq), hi = min(lo + per, nseq);
+        if (lit_rle < 0 && regen <= kExecLitBytes) {  // (the barriers of the scans below order these stores before their readers)
+            for (uint32_t k = t; k < regen; k += kExecThreads) lit_smem[k] = lit[k];
+            lit = lit_smem;
+        }
+        // ---- 1 positions: warp w owns a run of consecutive sequences, lane l its sequences l, l + 32, ...: neighbouring lanes
+        // work on neighbouring sequences, so their records load coalesced and their output bytes fall in different banks
+        // (16 consecutive sequences per THREAD put every lane of a warp 128 bytes apart: 32-way conflicts on each store)
+        const int lane = t & 31, warp = t >> 5;
+        const uint32_t rows = ((nseq + 31) / 32 + 31) / 32;  // rows of 32 sequences per warp
+        const uint32_t wlo = min((uint32_t)warp * rows * 32, nseq), whi = min(wlo + rows * 32, nseq);
         uint64_t s_ll = 0, s_o = 0;
-        for (uint32_t i = lo; i < hi; i++) {
+        for (uint32_t i = wlo + lane; i < whi; i += 32) {
             const uint64_t e = so[i];
             const uint32_t ll = (uint32_t)(e & 0x3FFFF), ml = (uint32_t)((e >> 18) & 0x3FFFF);
             s_ll += ll;
             s_o += (uint64_t)ll + ml;
         }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            s_ll += __shfl_xor_sync(0xFFFFFFFFu, s_ll, d);
+            s_o += __shfl_xor_sync(0xFFFFFFFFu, s_o, d);
+        }
         uint64_t tot_ll, tot_o;
-        const uint64_t ex_ll = block_exscan(s_ll, tmp, &tot_ll);
-        const uint64_t ex_o = block_exscan(s_o, tmp, &tot_o);
+        uint64_t run_ll = block_exscan(lane == 0 ? s_ll : 0, tmp, &tot_ll);  // lane 0: the sum over the warps before this one
+        uint64_t run_o = block_exscan(lane == 0 ? s_o : 0, tmp, &tot_o);
+        run_ll = __shfl_sync(0xFFFFFFFFu, run_ll, 0);
+        run_o = __shfl_sync(0xFFFFFFFFu, run_o, 0);
         if (tot_ll > regen) return zd::kZdFallback;  // (uniform: the totals are)
         const uint64_t total_out = tot_o + (regen - tot_ll);
         if (total_out > (uint64_t)(cap - pos) || total_out > block_max) return zd::kZdFallback;
-        if (!place_sequences(so, lo, hi, (uint32_t)ex_ll, pos + (uint32_t)ex_o, lit, lit_rle, window, out, pend, start)) *bad = 1;
+        {
+            bool ok = true;
+            for (uint32_t r0 = wlo; r0 < whi; r0 += 32) {  // (uniform per warp)
+                const uint32_t i = r0 + lane;
+                uint32_t ll = 0, both = 0;
+                if (i < whi) {
+                    const uint64_t e = so[i];
+                    ll = (uint32_t)(e & 0x3FFFF);
+                    both = ll + (uint32_t)((e >> 18) & 0x3FFFF);
+                }
+                uint32_t inc_ll = ll, inc_o = both;  // (a row's totals fit 32 bits: 32 x 2^19)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t a_ = __shfl_up_sync(0xFFFFFFFFu, inc_ll, d), b_ = __shfl_up_sync(0xFFFFFFFFu, inc_o, d);
+                    if (lane >= d) inc_ll += a_, inc_o += b_;
+                }
+                if (i < whi)
+                    ok &= place_sequences(so, i, i + 1, (uint32_t)run_ll + inc_ll - ll, pos + (uint32_t)run_o + inc_o - both, lit, lit_rle,
+                                          window, out, pend, start);
+                run_ll += __shfl_sync(0xFFFFFFFFu, inc_ll, 31);
+                run_o += __shfl_sync(0xFFFFFFFFu, inc_o, 31);
+            }
+            if (!ok) *bad = 1;
+        }
         {
             const uint32_t tail = regen - (uint32_t)tot_ll, tpos = pos + (uint32_t)tot_o;
             if (lit_rle >= 0) {
