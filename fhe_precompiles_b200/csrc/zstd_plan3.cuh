@@ -63,17 +63,16 @@ __device__ __forceinline__ uint32_t shr32(uint32_t v, uint32_t n) {
 // backward bit reader on aligned 32-bit words (zstd_plan2.h Back32) with the next word already in a register
 struct Back32P {
     const uint32_t *wp, *w0;
-    uint32_t lo_bits, nextw;
+    uint32_t lo_bits, nextw, nextmask;  // the prefetched word is masked when it is CONSUMED: nothing waits for the load before
     uint64_t c;   // unread bits, left-aligned
     int avail;    // how many of them are valid
     int left;     // stream bits not yet consumed (negative after an over-read; a stream is < 2^20 bits)
-    __device__ __forceinline__ uint32_t fetch() const {
-        uint32_t w = 0;
+    __device__ __forceinline__ void fetch() {
+        nextw = 0, nextmask = 0;
         if (wp >= w0) {
-            w = __ldg(wp);
-            if (wp == w0 && lo_bits) w &= ~((1u << lo_bits) - 1);
+            nextw = __ldg(wp);
+            nextmask = wp == w0 ? ~((1u << lo_bits) - 1) : 0xFFFFFFFFu;
         }
-        return w;
     }
     __device__ __forceinline__ bool init(const uint8_t *base, size_t len) {
         if (len == 0 || len > (1u << 17)) return false;
@@ -95,15 +94,15 @@ struct Back32P {
             avail = (int)r;
         }
         wp--;
-        nextw = fetch();
+        fetch();
         return true;
     }
     __device__ __forceinline__ void refill() {  // afterwards avail >= 32
         if (avail < 32) {
-            c |= (uint64_t)nextw << (32 - avail);
+            c |= (uint64_t)(nextw & nextmask) << (32 - avail);
             avail += 32;
             wp--;
-            nextw = fetch();
+            fetch();
         }
     }
     __device__ __forceinline__ uint32_t read(int n) {  // n in [0, 32], n <= avail
