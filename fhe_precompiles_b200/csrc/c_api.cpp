@@ -192,6 +192,11 @@ static bool binary_desc(int32_t index, Op *op, Shape *shape, Kind *kind) {
     return true;
 }
 
+static size_t env_or(const char *name, size_t dflt) {
+    const char *e = getenv(name);
+    return (e && atoll(e) > 0) ? (size_t)atoll(e) : dflt;
+}
+
 int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     if (!calls || n == 0) return 0;
     // Workers take TILES of consecutive calls: the binary precompiles of a tile share one lane, one H2D / D2H per operand
@@ -202,13 +207,13 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
     if (const char *e = getenv("FHE_B200_BATCH_THREADS"))
         if (host_threads <= 0 && atoi(e) > 0) nt = (size_t)atoi(e);
     size_t tile = Engine::get().tile_ops_for(n);
-    const size_t big = Engine::get().big_tile_ops();
+    const size_t big = Engine::get().big_tile_ops_for(n);
     bool serial_loops = true;
     if (Engine::get().device_codec() && big > tile && n >= 2 * big) {
         // a large batch: few big tiles (each stages its calls on the whole host pool and launches thousands of operand frames
         // at once), a handful of them in flight so that one tile's host phases overlap another's device phases
         tile = big;
-        nt = std::min<size_t>(nt, 6);
+        nt = std::min<size_t>(nt, env_or("FHE_B200_BIG_TILE_WORKERS", 6));
         serial_loops = false;
     } else {
         while (tile > 1 && (n + tile - 1) / tile < nt) tile /= 2;  // keep every worker busy on small batches
@@ -258,9 +263,22 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
                     set_error("unknown exception");
                     for (auto &it : items) it.rc = kErrSunscreen;
                 }
-                for (size_t k = 0; k < items.size(); k++) {
+                // results into caller-owned buffers (a malloc + an 82 KB copy per call): shared with the pool when this worker
+                // runs a big tile, like the tile's own per-call loops
+                const auto finish_one = [&](size_t k) {
                     fhe_b200_call &c = calls[which[k]];
                     c.status = finish(items[k].rc, items[k].out, &c.output, &c.output_length);
+                    std::vector<uint8_t>().swap(items[k].out);
+                };
+                if (!serial_loops && items.size() >= 64) {
+                    std::atomic<size_t> nextk{0};
+                    const std::function<void()> body = [&] {
+                        for (size_t k; (k = nextk.fetch_add(8)) < items.size();)
+                            for (size_t j = k; j < std::min(items.size(), k + 8); j++) finish_one(j);
+                    };
+                    HostPool::get().run(std::min<size_t>(std::thread::hardware_concurrency(), items.size() / 8) - 1, body);
+                } else {
+                    for (size_t k = 0; k < items.size(); k++) finish_one(k);
                 }
             }
             for (size_t i = lo; i < hi; i++)

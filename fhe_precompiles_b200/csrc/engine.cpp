@@ -135,7 +135,8 @@ Engine::Engine() {
         const char *v = getenv("FHE_B200_HOST_INFLATE_PCT");  // share of a tile's libzstd frames the host cores inflate meanwhile
         host_inflate_pct_ = (v && *v) ? (size_t)std::min(100, std::max(0, atoi(v))) : 0;
     }
-    big_tile_ops_ = env_size("FHE_B200_BIG_TILE_OPS", 0);  // opt-in: large batches run in tiles of this many calls (see c_api.cpp)
+    big_tile_set_ = getenv("FHE_B200_BIG_TILE_OPS") != nullptr;
+    big_tile_ops_ = env_size("FHE_B200_BIG_TILE_OPS", 0);  // fixed big-tile size (0: never); default: engine.h big_tile_ops_for
     tile_ops_ = env_size("FHE_B200_TILE_OPS", 16);
     if (tile_ops_ < 1) tile_ops_ = 1;
     chunk_ops_ = env_size("FHE_B200_CHUNK_OPS", 4096);

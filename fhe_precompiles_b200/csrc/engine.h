@@ -123,7 +123,17 @@ class Engine {
     static void set_thread_serial_loops(bool on);
     // tile size of a large batch: big tiles put thousands of operand frames in flight per launch (the device zstd decoder's
     // throughput comes from frames in flight) and their staging loops are shared with the host pool
-    size_t big_tile_ops() const { return big_tile_ops_; }
+    // Big tiles: a large batch runs as a few tiles of this many calls, each staging its calls on the whole host pool and
+    // launching thousands of operand frames at once (the device zstd decoder's rate grows with the frames per launch: 183 k
+    // frames/s at 1,024, 410 k at 8,192).  FHE_B200_BIG_TILE_OPS fixes the size (0 there: never); by default a batch of
+    // >= 2,048 calls takes an eighth of itself, between 256 and 1,024 calls.
+    size_t big_tile_ops_for(size_t n) const {
+        if (big_tile_set_) return big_tile_ops_;
+        if (!(device_codec_ && device_zstd_ == 2 && n >= zstd_tile_min_batch_)) return 0;
+        size_t b = 256;
+        while (b < 1024 && 2 * b <= n / 8) b *= 2;
+        return b;
+    }
     bool device_codec() const { return device_codec_; }
     // per-call phase timing of binary_tile (host clock around the codec phases, CUDA events around the copies and the
     // kernels on the lane's stream); off by default
@@ -214,6 +224,7 @@ class Engine {
     size_t device_zstd_min_frames_ = 128, host_inflate_pct_ = 0;
     size_t zstd_tile_ops_ = 128, zstd_tile_min_batch_ = 2048;
     size_t tile_ops_ = 16, big_tile_ops_ = 0;
+    bool big_tile_set_ = false;
     bool helper_decode_ = true;  // FHE_B200_HELPER_DECODE=0 turns the helper-thread inflate of single calls off
     std::atomic<bool> call_timing_{false};
     std::vector<int> lane_devices_;
