@@ -46,6 +46,7 @@ uint64_t cheap_tag(Span s) {
 // with 32 tile workers on 16 cores, a nested parallel_for waited ~400 us per call for helper copies that had been started and
 // then descheduled - more than the loops' own work.)
 thread_local bool tl_serial_loops = false;
+thread_local size_t tl_loop_width = 0;  // threads a loop of this thread may occupy, itself included (0: every core)
 // fn(i) for i in [0, count): on the caller alone for short loops, otherwise shared with pool threads in chunks of `grain`
 template <class F>
 void parallel_for(size_t count, size_t grain, F &&fn) {
@@ -63,7 +64,12 @@ void parallel_for(size_t count, size_t grain, F &&fn) {
             for (size_t i = lo; i < hi; i++) fn(i);
         }
     };
-    HostPool::get().run(std::min(hw - 1, (count + grain - 1) / grain - 1), body);
+    const size_t width = tl_loop_width ? std::min(tl_loop_width, hw) : hw;
+    if (width < 2) {
+        body();
+        return;
+    }
+    HostPool::get().run(std::min(width - 1, (count + grain - 1) / grain - 1), body);
 }
 // FHE_B200_TILE_PROFILE=<n >= 1>: wall time of binary_tile's phases summed over all tile workers, printed when the process exits;
 // the first n calls (warm-up: lanes, pinned buffers, key upload) are not counted
@@ -106,6 +112,7 @@ Engine &Engine::get() {
     return *e;
 }
 void Engine::set_thread_serial_loops(bool on) { tl_serial_loops = on; }
+void Engine::set_thread_loop_width(size_t threads) { tl_loop_width = threads; }
 
 Engine::Engine() {
     HostContext::get();

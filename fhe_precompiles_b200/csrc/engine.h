@@ -121,6 +121,8 @@ class Engine {
     }
     // the calling thread is one of many tile workers: binary_tile keeps its per-call loops on it instead of sharing them with the pool
     static void set_thread_serial_loops(bool on);
+    // ... or may share them with at most `threads` - 1 pool threads (0: no limit): a batch divides its thread budget among its workers
+    static void set_thread_loop_width(size_t threads);
     // tile size of a large batch: big tiles put thousands of operand frames in flight per launch (the device zstd decoder's
     // throughput comes from frames in flight) and their staging loops are shared with the host pool
     // Big tiles: a large batch runs as a few tiles of this many calls, each staging its calls on the whole host pool and
