@@ -35,6 +35,7 @@ constexpr int kExecThreads = 1024;
 constexpr int kExecPer = 16;                                      // sequences a thread carries in registers
 constexpr uint32_t kExecChunk = kExecThreads * kExecPer;          // sequences per pass (a ciphertext block has 16,354)
 constexpr int kExecMaxRounds = 64;
+constexpr uint32_t kExecMaxSpins = 1u << 20;                      // polls of one match before the frame is handed back
 constexpr size_t kExecOutBytes = 131200;                          // kPayloadStride: the frame's content (131,169) + store slack
 constexpr size_t kExecBitWords = (kExecOutBytes + 31) / 32 + 2;   // one bit per output byte (+ slack for pair loads)
 constexpr size_t kExecLitBytes = 56 << 10;                        // a block's literals are staged in shared memory when they fit

@@ -387,7 +387,10 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
                 const uint32_t i = cbase + (uint32_t)k * kExecThreads + t;
                 CopyJob job = copy_job(i < nseq ? so[i] : 0, F[k], MI[k]);
                 bool waiting = job.ml != 0;
-                while (__any_sync(0xFFFFFFFFu, waiting)) {
+                // (the spin bound is insurance, not logic: dependencies point backwards, so the earliest pending match is always
+                // ready and every poll loop ends; should that reasoning ever be wrong, the frame goes back to the host instead
+                // of hanging the GPU)
+                for (uint32_t spins = 0; __any_sync(0xFFFFFFFFu, waiting); spins++) {
                     if (waiting && copy_ready(pend, job)) {
                         __threadfence_block();  // the bytes behind the cleared bits
                         copy_match(out, job);
@@ -395,9 +398,14 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
                         pend_clear(pend, job.m, job.ml);
                         waiting = false;
                     }
+                    if (spins >= kExecMaxSpins) {
+                        *bad = 1;
+                        waiting = false;
+                    }
                 }
             }
             __syncthreads();
+            if (*bad) return zd::kZdFallback;
         }
         pos += (uint32_t)total_out;
     }
