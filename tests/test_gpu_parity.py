@@ -413,9 +413,12 @@ def test_device_zstd_inflate_matches_libzstd(dev, two_phase, monkeypatch):
             assert payloads[i] is not None and raw[i * size : (i + 1) * size] == payloads[i], i
 
 
-def test_batch_tiles_with_device_zstd(keys):
-    """FHE_B200_DEVICE_ZSTD=1: the operands of a tile are inflated by k_zstd_inflate instead of libzstd. Same statuses and bytes
-    as the single-call symbols (the knob is read when the engine starts, hence the subprocess)."""
+@pytest.mark.parametrize("host_pct,writer", [("0", "0"), ("40", "0"), ("40", "1")])
+def test_batch_tiles_with_device_zstd(keys, host_pct, writer):
+    """FHE_B200_DEVICE_ZSTD=1: the operands of a tile are inflated by the device decoder (k_zd2_parse / k_zd3_seq / k_zd3_exec)
+    instead of libzstd - all of them, or (FHE_B200_HOST_INFLATE_PCT=40) a hybrid tile whose device share is decoded while the
+    host inflates the rest.  Same statuses and bytes as the single-call symbols, with either result writer (the knobs are read
+    when the engine starts, hence the subprocess)."""
     import subprocess
     import sys
 
@@ -450,7 +453,7 @@ assert got == want, [(g[0], w[0]) for g, w in zip(got, want)]
 assert sum(1 for st, _ in want if st == 0) >= 16 and any(st for st, _ in want)
 print("device-zstd tiles ok")
 """ % (ROOT, os.path.join(ROOT, "tests"))
-    env = dict(os.environ, FHE_B200_DEVICE_ZSTD="1")
+    env = dict(os.environ, FHE_B200_DEVICE_ZSTD="1", FHE_B200_HOST_INFLATE_PCT=host_pct, FHE_B200_ZSTD_WRITER=writer)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "device-zstd tiles ok" in r.stdout, r.stdout + r.stderr
 
