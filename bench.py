@@ -330,22 +330,23 @@ def e2e_byte_surface(fdev, a, b, net_pub: bytes, steps: int, world: int, barrier
 
     rate_seal, out_seal = timed(0)
     rate_struct, out_struct = timed(1)
-    # a larger batch with the structured writer: the device zstd decoder's rate grows with the frames per launch
-    big_n = 4 * n_calls
-    big = (_lib.BatchCall * big_n)()
-    for i in range(big_n):
-        big[i].op, big[i].bytes, big[i].bytes_length = op_index, ctypes.cast(bufs[i % distinct], ctypes.c_void_p), len(packed[i % distinct])
-    prev_ = L.fhe_b200_set_zstd_writer(1)
-    try:
-        one_batch(check=True, arr=big, n_calls=big_n)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(2):
+    # a larger batch with the structured writer: the device zstd decoder's rate grows with the frames per launch (one rank only:
+    # with several ranks on one host the leg is host-bound either way and its pinned lanes would only add warm-up time)
+    big_n, rate_big = 4 * n_calls, None
+    if world == 1:
+        big = (_lib.BatchCall * big_n)()
+        for i in range(big_n):
+            big[i].op, big[i].bytes, big[i].bytes_length = op_index, ctypes.cast(bufs[i % distinct], ctypes.c_void_p), len(packed[i % distinct])
+        prev_ = L.fhe_b200_set_zstd_writer(1)
+        try:
+            one_batch(check=True, arr=big, n_calls=big_n)
             one_batch(arr=big, n_calls=big_n)
-        rate_big = world * big_n * 2 / max_over_ranks(time.perf_counter() - t0, dist)
-        barrier()
-    finally:
-        L.fhe_b200_set_zstd_writer(prev_)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                one_batch(arr=big, n_calls=big_n)
+            rate_big = big_n * 3 / (time.perf_counter() - t0)
+        finally:
+            L.fhe_b200_set_zstd_writer(prev_)
     return {
         "value": rate_seal,
         "unit": "calls/s",
