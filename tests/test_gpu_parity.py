@@ -1178,6 +1178,50 @@ def test_scalar_edge_cases_through_the_c_abi(keys, kind):
                 j += 1
 
 
+def test_large_batch_device_decoder_equals_small_batches(keys):
+    """fhe_b200_batch on a batch large enough for the default big tiles + device zstd decoder (>= 2,048 calls: operand frames
+    inflated by k_zd2_parse / k_zd3_seq / k_zd3_exec) against the same calls in 16-call batches (operands inflated by libzstd
+    on the host): 2,304 ct.ct calls over 96 distinct uniformly random ciphertexts (libzstd level-3 frames), some corrupted;
+    every status and every output byte equal."""
+    import ctypes
+
+    from fhe_precompiles_b200 import FHE, _lib, pack
+
+    L = _lib.lib()
+    rng = np.random.default_rng(77)
+    dt = b"sunscreen::types::bfv::signed::Signed,0.8.1,true"
+
+    def blob() -> bytes:
+        w = np.stack([rng.integers(0, MODULI[l], N, dtype=np.uint64) for _ in range(2) for l in range(2)]).reshape(-1)
+        out, ln = ctypes.c_void_p(), ctypes.c_int64()
+        assert L.fhe_b200_write_ciphertext(w.ctypes.data, dt, ctypes.byref(out), ctypes.byref(ln)) == 0
+        b = ctypes.string_at(out.value, ln.value)
+        L.fhe_free(out)
+        return b
+
+    prev = L.fhe_b200_set_zstd_writer(0)  # operands as SEAL writes them
+    try:
+        cts = [blob() for _ in range(96)]
+    finally:
+        L.fhe_b200_set_zstd_writer(prev)
+    calls = []
+    for i in range(2304):
+        a, b = cts[int(rng.integers(96))], cts[int(rng.integers(96))]
+        if i % 97 == 13:  # a flipped bit somewhere in the first operand's frame: the device decoder or the range check hands it back
+            bad = bytearray(a)
+            bad[-int(rng.integers(1, 80000))] ^= 1 << int(rng.integers(8))
+            a = bytes(bad)
+        op = ("mul", "add", "sub")[i % 3]
+        calls.append((f"{op}_cipheri64_cipheri64", pack.pack_binary_operation(keys.pub_bytes, a, b)))
+    big = FHE.run_batch(calls)
+    small = []
+    for k in range(0, len(calls), 16):
+        small += FHE.run_batch(calls[k : k + 16], host_threads=2)
+    assert [g[0] for g in big] == [w[0] for w in small]
+    assert sum(1 for st, _ in big if st == 0) >= 2200
+    assert all(g[1] == w[1] for g, w in zip(big, small))
+
+
 def test_config4_mixed_batch_matches_oracle(keys):
     """BASELINE config 4 at one GPU's share: 4,608 calls drawn (seed 3) uniformly from {add, sub, mul} x {ct.ct, ct.pt, pt.ct}
     x {u64, i64, u256, frac64} -- every one of the 36 precompiles many times -- through fhe_b200_batch in tiles; EVERY result
