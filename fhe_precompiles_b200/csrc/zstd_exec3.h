@@ -35,6 +35,10 @@ constexpr int kExecThreads = 1024;
 constexpr int kExecPer = 16;                                      // sequences a thread carries in registers
 constexpr uint32_t kExecChunk = kExecThreads * kExecPer;          // sequences per pass (a ciphertext block has 16,354)
 constexpr int kExecMaxRounds = 64;
+// The jumping stops once a round moves fewer than 1/kExecStopShare of the pass's sequences: the last rounds serve a few per
+// cent of the matches (chains through matches that keep their offset advance one link per round) at the full price of a round
+// for every warp; what is left then waits in step 3 for the few links in front of it (a ciphertext frame: 9 rounds instead of 14).
+constexpr uint32_t kExecStopShare = 8;
 constexpr uint32_t kExecMaxSpins = 1u << 20;                      // polls of one match before the frame is handed back
 constexpr size_t kExecOutBytes = 131200;                          // kPayloadStride: the frame's content (131,169) + store slack
 constexpr size_t kExecBitWords = (kExecOutBytes + 31) / 32 + 2;   // one bit per output byte (+ slack for pair loads)

@@ -262,6 +262,7 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
     uint32_t *start = pend + kExecBitWords;
     uint64_t *tmp = (uint64_t *)(start + kExecBitWords);
     int *bad = (int *)(tmp + 64);
+    uint32_t *moved_cnt = (uint32_t *)(tmp + 64) + 2;  // matches moved in a jump round (two alternating counters)
     uint8_t *lit_smem = (uint8_t *)(tmp + 64) + 64;
     const int t = threadIdx.x;
     if (t == 0) *bad = 0;
@@ -365,21 +366,32 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
                 F[k] = 0, MI[k] = 0;
                 if (i < nseq && jump_init(so[i], &F[k], &MI[k])) act |= 1u << k;
             }
+            const uint32_t stop_below = min(nseq - cbase, kExecChunk) / kExecStopShare;
+            if (t == 0) moved_cnt[0] = moved_cnt[1] = 0;
+            __syncthreads();
             for (int round = 0; round < kExecMaxRounds; round++) {
-                uint32_t chg = 0;
+                uint32_t chg = 0, nmoved = 0;
 #pragma unroll
                 for (int k = 0; k < kExecPer; k++) {
                     if (!((act >> k) & 1)) continue;
                     const int r = jump_look(pend, start, out, &F[k], &MI[k], so + cbase + (uint32_t)k * kExecThreads + t);
-                    if (r == kJumpStop) act &= ~(1u << k);
-                    else if (r == kJumpPublish) chg |= 1u << k;
+                    if (r == kJumpStop) {
+                        act &= ~(1u << k);
+                        continue;
+                    }
+                    nmoved++;
+                    if (r == kJumpPublish) chg |= 1u << k;
                     else chg |= 1u << 16;  // (moved, nothing to publish)
                 }
+                nmoved = __reduce_add_sync(0xFFFFFFFFu, nmoved);
+                if ((t & 31) == 0 && nmoved) atomicAdd(&moved_cnt[round & 1], nmoved);
                 __syncthreads();  // every offset has been read
 #pragma unroll
                 for (int k = 0; k < kExecPer; k++)
                     if ((chg >> k) & 1) jump_publish(out, F[k], MI[k]);
+                if (t == 0) moved_cnt[(round + 1) & 1] = 0;
                 if (!__syncthreads_or((int)chg)) break;
+                if (moved_cnt[round & 1] < stop_below) break;  // (uniform: read by everyone between the same two barriers)
             }
             // ---- 3 copies: in order per thread; a warp polls until its 32 current matches are copied
 #pragma unroll

@@ -138,16 +138,22 @@ extern "C" int zd_decode_v3(const uint8_t *src, size_t slen, uint8_t *dst, size_
                     const uint32_t i = cbase + (uint32_t)k * T + t;
                     if (i < nseq && jump_init(so[i], &F[t * kExecPer + k], &MI[t * kExecPer + k])) act[t] |= 1u << k;
                 }
+            const uint32_t stop_below = std::min(nseq - cbase, kExecChunk) / kExecStopShare;
             for (int round = 0; round < kExecMaxRounds; round++) {
                 bool any = false;
+                uint32_t moved = 0;
                 for (int t = 0; t < T; t++) {
                     chg[t] = 0;
                     for (int k = 0; k < kExecPer; k++) {
                         if (!((act[t] >> k) & 1)) continue;
                         const int r = jump_look(pend.data(), start.data(), out.data(), &F[t * kExecPer + k], &MI[t * kExecPer + k],
                                                 so + cbase + (uint32_t)k * T + t);
-                        if (r == kJumpStop) act[t] &= ~(1u << k);
-                        else if (r == kJumpPublish) chg[t] |= 1u << k;
+                        if (r == kJumpStop) {
+                            act[t] &= ~(1u << k);
+                            continue;
+                        }
+                        moved++;
+                        if (r == kJumpPublish) chg[t] |= 1u << k;
                         else chg[t] |= 1u << 16;
                     }
                     any |= chg[t] != 0;
@@ -155,8 +161,8 @@ extern "C" int zd_decode_v3(const uint8_t *src, size_t slen, uint8_t *dst, size_
                 for (int t = 0; t < T; t++)
                     for (int k = 0; k < kExecPer; k++)
                         if ((chg[t] >> k) & 1) jump_publish(out.data(), F[t * kExecPer + k], MI[t * kExecPer + k]);
-                if (!any) break;
                 if (rounds && round + 1 > *rounds) *rounds = round + 1;
+                if (!any || moved < stop_below) break;
             }
             // step 3: warps of 32 threads, each polling until its current 32 matches are copied; the warps take turns
             std::vector<int> kcur(T / 32, 0);
