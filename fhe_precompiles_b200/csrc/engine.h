@@ -127,7 +127,7 @@ class Engine {
     // throughput comes from frames in flight) and their staging loops are shared with the host pool
     // Big tiles: a large batch runs as a few tiles of this many calls, each staging its calls on the whole host pool and
     // launching thousands of operand frames at once (the device zstd decoder's rate grows with the frames per launch: 183 k
-    // frames/s at 1,024, 410 k at 8,192).  FHE_B200_BIG_TILE_OPS fixes the size (0 there: never); by default a batch of
+    // frames/s at 1,024, 431 k at 8,192).  FHE_B200_BIG_TILE_OPS fixes the size (0 there: never); by default a batch of
     // >= 2,048 calls takes an eighth of itself, between 256 and 1,024 calls.
     size_t big_tile_ops_for(size_t n) const {
         if (big_tile_set_) return big_tile_ops_;
