@@ -257,6 +257,7 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
                 Kind kind;
                 if (binary_desc(c.op, &op, &shape, &kind)) {
                     items.push_back(TileItem{op, shape, kind, Span{c.bytes, c.bytes_length}, {}, 0});
+                    items.back().take_malloc = true;
                     which.push_back(i);
                 } else if (c.op < 0 || c.op >= kNumOps) {
                     c.status = kErrSunscreen;
@@ -280,6 +281,15 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
                 // runs a big tile, like the tile's own per-call loops
                 const auto finish_one = [&](size_t k) {
                     fhe_b200_call &c = calls[which[k]];
+                    if (items[k].out_malloc) {  // written in place by the tile: the caller frees it with fhe_free
+                        if (items[k].rc == 0) {
+                            c.status = 0, c.output = items[k].out_malloc, c.output_length = (int64_t)items[k].out_malloc_len;
+                            items[k].out_malloc = nullptr;
+                            return;
+                        }
+                        free(items[k].out_malloc);
+                        items[k].out_malloc = nullptr;
+                    }
                     c.status = finish(items[k].rc, items[k].out, &c.output, &c.output_length);
                     std::vector<uint8_t>().swap(items[k].out);
                 };

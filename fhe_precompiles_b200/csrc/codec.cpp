@@ -588,10 +588,15 @@ void canonical_ct_prefix(uint8_t *p) {
     memcpy(p + 89, &count, 8);
 }
 
+size_t wrapped_ciphertext_size(const CipherView &view, size_t body_len) {
+    return 8 + view.data_type.size() + 12 + kParamsBytes + 8 + kSealHeader + body_len;
+}
 void wrap_ciphertext_blob(const CipherView &view, const uint8_t *body, size_t body_len, std::vector<uint8_t> *out) {
+    out->resize(wrapped_ciphertext_size(view, body_len));
+    wrap_ciphertext_blob_to(view, body, body_len, out->data());
+}
+void wrap_ciphertext_blob_to(const CipherView &view, const uint8_t *body, size_t body_len, uint8_t *o) {
     const size_t blob = kSealHeader + body_len;
-    out->resize(8 + view.data_type.size() + 12 + kParamsBytes + 8 + blob);
-    uint8_t *o = out->data();
     const uint64_t dl = view.data_type.size(), one = 1, bl = blob;
     const uint32_t zero = 0;
     memcpy(o, &dl, 8), o += 8;

@@ -64,6 +64,9 @@ bool inflate_ct_payload(Span frame, uint8_t *dst);
 void canonical_ct_prefix(uint8_t *prefix97);
 // bincode(Ciphertext) around an already compressed payload `body` (SEAL header with view.compr_mode added here)
 void wrap_ciphertext_blob(const CipherView &view, const uint8_t *body, size_t body_len, std::vector<uint8_t> *out);
+// the same into a caller-provided buffer of wrapped_ciphertext_size(view, body_len) bytes
+size_t wrapped_ciphertext_size(const CipherView &view, size_t body_len);
+void wrap_ciphertext_blob_to(const CipherView &view, const uint8_t *body, size_t body_len, uint8_t *dst);
 
 // Serialises a size-2 data-level ciphertext (bincode + SEAL + compression) into `out`.
 int32_t encode_ciphertext(const CipherView &view, const uint64_t *words, std::vector<uint8_t> *out);

@@ -1347,7 +1347,18 @@ void Engine::binary_tile(TileItem *items, size_t cnt) {
                 }
                 TileItem &it = items[i];
                 if (pack_on_device && !h_cflag[k]) {
-                    wrap_ciphertext_blob(prep[i].va, lane->h_outframes + k * kPackedFrameStride, kPackedFrameBytes, &it.out);
+                    const uint8_t *frame = lane->h_outframes + k * kPackedFrameStride;
+                    uint8_t *direct = nullptr;
+                    if (it.take_malloc) {
+                        it.out_malloc_len = wrapped_ciphertext_size(prep[i].va, kPackedFrameBytes);
+                        direct = (uint8_t *)malloc(it.out_malloc_len);
+                    }
+                    if (direct) {
+                        wrap_ciphertext_blob_to(prep[i].va, frame, kPackedFrameBytes, direct);
+                        it.out_malloc = direct;
+                    } else {
+                        wrap_ciphertext_blob(prep[i].va, frame, kPackedFrameBytes, &it.out);
+                    }
                     it.rc = kOk;
                 } else if (!pack_on_device) {
                     it.rc = encode_ciphertext(prep[i].va, lane->h_out + k * kCtWords, &it.out);

@@ -71,6 +71,11 @@ struct TileItem {
     Span in;
     std::vector<uint8_t> out;
     int32_t rc = 0;
+    // a result the tile already wrote into a malloc'ed buffer (batch workers: handed to the caller as it is, no second copy);
+    // used only when `take_malloc` was set by the caller of binary_tile, who then owns the buffer
+    bool take_malloc = false;
+    uint8_t *out_malloc = nullptr;
+    size_t out_malloc_len = 0;
 };
 
 struct KeyEntry {

@@ -1,9 +1,8 @@
 // Parallel execution of a zstd block's sequences: the per-sequence steps of k_zd3_exec (zstd_plan3.cuh).  Host + device source:
 // tests/zd_host.cpp runs the same steps thread by thread (zd_decode_v3) against libzstd, so the logic is tested without a GPU.
 //
-// One CTA per frame.  Shared memory: the frame's output (131,200 B), one "pending" bit and one "match start" bit per output byte,
-// and the block's literals when they fit in 56 KB (a ciphertext block has 55.7 KB of raw literals: staged with coalesced loads,
-// so that the per-sequence byte copies of step 1 do not wait on global memory one byte at a time).
+// One CTA per frame.  Shared memory: the frame's output (131,200 B), one "pending" bit and one "match start" bit per output byte
+// (and, optionally, the block's literals: kExecLitBytes).
 //  1 positions   block-wide prefix sums over (literal length, literal + match length) give every sequence the place of its
 //                literals and of its match; literals are copied, the match region is marked pending, its first byte marked as a
 //                start and its first three bytes (a match is >= 3 bytes) hold the match's PUBLISHED OFFSET (start - source):
@@ -42,8 +41,11 @@ constexpr uint32_t kExecStopShare = 8;
 constexpr uint32_t kExecMaxSpins = 1u << 20;                      // polls of one match before the frame is handed back
 constexpr size_t kExecOutBytes = 131200;                          // kPayloadStride: the frame's content (131,169) + store slack
 constexpr size_t kExecBitWords = (kExecOutBytes + 31) / 32 + 2;   // one bit per output byte (+ slack for pair loads)
-constexpr size_t kExecLitBytes = 56 << 10;                        // a block's literals are staged in shared memory when they fit
-constexpr size_t kExecSmem = kExecOutBytes + 2 * kExecBitWords * 4 + 64 * 8 + 64 + kExecLitBytes;  // 221,936 of 232,448
+// A block's literals can be staged in shared memory (56 KB hold a ciphertext block's 55.7 KB) - measured: no gain once the
+// placement was free of bank conflicts, while 222 KB per CTA keep every other kernel off the SM: with 165 KB three sequence-chain
+// CTAs of other tiles (20.8 KB each) fit beside an execution CTA, and in the tile pipeline that is what counts.
+constexpr size_t kExecLitBytes = 0;
+constexpr size_t kExecSmem = kExecOutBytes + 2 * kExecBitWords * 4 + 64 * 8 + 64 + kExecLitBytes;  // 164,592 of 232,448
 
 #if defined(__CUDA_ARCH__)
 #define ZD3_OR(p, v) atomicOr((p), (v))

@@ -292,7 +292,7 @@ __device__ __forceinline__ int exec_frame(const uint8_t *src, const Plan2 *plan,
         const int lit_rle = bp.lit_mode == 1 ? bp.lit_rle : -1;
         const uint32_t nseq = bp.nseq, regen = bp.regen;
         uint64_t *so = seqs + bp.seq_off;
-        if (lit_rle < 0 && regen <= kExecLitBytes) {  // (the barriers of the scans below order these stores before their readers)
+        if (kExecLitBytes && lit_rle < 0 && regen <= kExecLitBytes) {  // (the barriers of the scans below order these stores before their readers)
             for (uint32_t k = t; k < regen; k += kExecThreads) lit_smem[k] = lit[k];
             lit = lit_smem;
         }
