@@ -7,13 +7,14 @@
 //     sequence) with 32 frames diverging inside one warp;
 //   * execution was one THREAD per frame: 16 k sequences one after the other although only the match copies depend on each other.
 // Here:
-//   k_zd3_seq   four frames per warp (a one-lane warp costs as many issue slots as a full one, and shared memory - 10 KB of FSE
-//               tables per frame - bounds the frames per SM either way): each frame's tables are staged in shared memory, the
-//               bit reader keeps the next stream word prefetched, and a sequence's six bit fields come out of one register
-//   k_zd3_exec  one CTA (1,024 threads) per frame, the frame's output assembled in shared memory: block-wide prefix sums give
-//               every sequence its literal and output positions, literals are copied in parallel, match copies resolve through a
-//               per-byte "pending" bitmap (a match is copied as soon as none of its source bytes is pending; dependencies point
-//               backwards only, so the earliest pending match is always ready), and the payload leaves with 16-byte stores
+//   k_zd3_seq   four frames per warp (a one-lane warp costs as many issue slots as a full one, and shared memory - 5 KB of FSE
+//               tables per frame as 4-byte cells - bounds the frames per SM either way): each frame's tables are staged in shared
+//               memory, the bit reader keeps the next stream word prefetched, a sequence's six bit fields come out of one register
+//   k_zd3_exec  one CTA (1,024 threads) per frame, the frame's output assembled in shared memory: prefix sums give every
+//               sequence its literal and output positions, literals are copied in parallel, pointer jumping moves every match's
+//               source back along its chain of pending matches (zstd_exec3.h), and the copies go through a per-byte "pending"
+//               bitmap (a match is copied once none of its source bytes is pending; dependencies point backwards only, so the
+//               earliest pending match is always ready); the payload leaves with 16-byte stores
 // Parsing (headers, table construction) and the Huffman streams stay zstd_plan2.h's plan2_parse / plan2_huf.
 #pragma once
 #include "codec_kernels.h"
