@@ -215,7 +215,9 @@ int64_t fhe_b200_batch(fhe_b200_call *calls, size_t n, int32_t host_threads) {
         // at once), a handful of them in flight so that one tile's host phases overlap another's device phases
         tile = big;
         budget = nt;
-        nt = std::min<size_t>(nt, env_or("FHE_B200_BIG_TILE_WORKERS", 6));
+        // six tiles in flight keep one GPU and the host pool busy (8, 10, 12 measured no better); with several GPUs in one
+        // process, one more per extra GPU
+        nt = std::min<size_t>(nt, env_or("FHE_B200_BIG_TILE_WORKERS", std::max<size_t>(6, Engine::get().lane_device_count() + 2)));
         serial_loops = false;
     } else {
         while (tile > 1 && (n + tile - 1) / tile < nt) tile /= 2;  // keep every worker busy on small batches

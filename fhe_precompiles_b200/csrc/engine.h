@@ -119,6 +119,7 @@ class Engine {
     // Per-call results and error codes are exactly those of binary_op (which is a tile of one).
     void binary_tile(TileItem *items, size_t cnt);
     size_t tile_ops() const { return tile_ops_; }
+    size_t lane_device_count() const { return lane_devices_.size(); }  // GPUs the byte surface spreads its lanes over
     // tile size for a batch of n calls: large batches run in tiles big enough for the device zstd decoder to take their operand
     // frames (device_zstd_ == 2), everything else in tile_ops_
     size_t tile_ops_for(size_t n) const {
