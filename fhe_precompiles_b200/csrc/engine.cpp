@@ -675,6 +675,18 @@ void Engine::relinearize(int device, const uint64_t *c3, const uint64_t *rk, uin
 }
 
 // ---------------------------------------------------------------- host-buffer batch (H2D | kernels | D2H overlapped)
+// Chunk schedule of the host pipelines: full chunks in the middle, a short first one (the kernels start after 0.5 ms of copies
+// instead of 1.3) and a short last one (less to drain) - both still >= 96 ops, the size from which the fused kernel set runs.
+// A function of (off, n, chunk) only: every loop over the same batch sees the same chunks.
+static size_t pipe_chunk(size_t off, size_t n, size_t chunk) {
+    const size_t rem = n - off, edge = 96;
+    if (chunk <= edge || rem <= edge) return rem < chunk ? rem : chunk;
+    if (off == 0) return edge;
+    if (rem <= chunk) return rem > 2 * edge ? rem - edge : rem;
+    if (rem <= chunk + edge) return rem - edge;
+    return chunk;
+}
+
 void Engine::mul_relin_host(int device, const uint64_t *a, const uint64_t *b, const uint64_t *rk, uint64_t *out, size_t n) {
     device_context(device);
     {
@@ -699,8 +711,8 @@ void Engine::mul_relin_host(int device, const uint64_t *a, const uint64_t *b, co
     cuda_throw(cudaMemcpyAsync(P.d_rk, rk, kRkWords * 8, cudaMemcpyHostToDevice, P.slot[0].stream), "H2D rk");
     cuda_throw(cudaStreamSynchronize(P.slot[0].stream), "sync rk");
     size_t i = 0;
-    for (size_t off = 0; off < n; off += P.chunk, i++) {
-        const size_t c = n - off < P.chunk ? n - off : P.chunk;
+    for (size_t off = 0, c = 0; off < n; off += c, i++) {
+        c = pipe_chunk(off, n, P.chunk);
         PipeSlot &sl = P.slot[i % kPipeSlots];
         cudaStream_t s = sl.stream;
         cuda_throw(cudaMemcpyAsync(sl.d_a, a + off * kCtWords, c * kCtWords * 8, cudaMemcpyHostToDevice, s), "H2D a");
@@ -771,8 +783,8 @@ void Engine::mul_relin_frames(int device, const uint8_t *fa, const uint8_t *fb, 
     cuda_throw(cudaMemcpyAsync(P.d_rk, rk, kRkWords * 8, cudaMemcpyHostToDevice, P.slot[0].stream), "H2D rk");
     cuda_throw(cudaStreamSynchronize(P.slot[0].stream), "sync rk");
     size_t k = 0;
-    for (size_t off = 0; off < n; off += P.chunk, k++) {
-        const size_t c = n - off < P.chunk ? n - off : P.chunk;
+    for (size_t off = 0, c = 0; off < n; off += c, k++) {
+        c = pipe_chunk(off, n, P.chunk);
         PipeSlot &sl = P.slot[k % kPipeSlots];
         cudaStream_t s = sl.stream;
         // the last frame of an array may end before its stride does: never read past fa / fb + (n-1) * stride + frame
@@ -795,8 +807,8 @@ void Engine::mul_relin_frames(int device, const uint8_t *fa, const uint8_t *fb, 
     }
     for (auto &sl : P.slot) cuda_throw(cudaStreamSynchronize(sl.stream), "pipe sync");
     if (status) {
-        for (size_t off = 0; off < n; off += P.chunk) {
-            const size_t c = n - off < P.chunk ? n - off : P.chunk;
+        for (size_t off = 0, c = 0; off < n; off += c) {
+            c = pipe_chunk(off, n, P.chunk);
             const int32_t *st = P.h_status + 3 * off;
             for (size_t i = 0; i < c; i++) {
                 const bool ok = st[2 * i] != kJobFallback && st[2 * i + 1] != kJobFallback;  // the unpack kernel only flags failures
